@@ -1,0 +1,213 @@
+/*
+ * libia_b200 -- C ABI of the B200-native IntrinsicAvatar render path.
+ *
+ * The reference (taconite/IntrinsicAvatar) has no plugin ABI: its seams are a Python model class
+ * and five pybind11 extension modules.  Each entry point below names the
+ * reference interface it replaces (file:line relative to the reference tree).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative IA_E* code otherwise; ia_last_error() gives text;
+ *   - nothing throws, nothing synchronises the device unless stated ("syncs");
+ *   - `d_` arguments are DEVICE pointers owned by the caller, `h_` arguments are HOST pointers
+ *     (small parameter blocks), `stream` is a cudaStream_t passed as void*;
+ *   - a context is bound to one device and is not thread-safe; use one context per host thread/stream.
+ */
+#ifndef IA_B200_H
+#define IA_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IA_OK 0
+#define IA_EINVAL -1
+#define IA_ECUDA -2
+#define IA_ESTATE -3
+#define IA_EOVERFLOW -4
+
+#define IA_N_COUNTERS 16
+
+typedef struct ia_ctx ia_ctx;
+
+const char* ia_last_error(void);
+int ia_version(void);
+
+/* lifetime ---------------------------------------------------------------------------------- */
+int ia_create(ia_ctx** out, int device);
+int ia_destroy(ia_ctx* ctx);
+
+/* ---- model state -------------------------------------------------------------------------- */
+/* tiny-cuda-nn HashGrid tables + folded MLP weights (replaces the nn.Module parameters of
+ * models/rf/geometry.py:107-122, models/rf/radiance.py:82-110, models/pbr/material.py:13-30,
+ * models/rf/density.py:20-34).  Hash tables are referenced, not copied (caller keeps them alive).
+ * h_level_* : 16 entries each.  MLP matrices are row-major [out][in] fp32 host arrays.          */
+int ia_set_fields(ia_ctx* ctx, const float* d_geo_hash, const float* d_rad_hash, int64_t n_entries,
+                  const float* h_level_scale, const int32_t* h_level_res, const int32_t* h_level_size,
+                  const int32_t* h_level_offset,
+                  const float* h_geo_w1, const float* h_geo_b1, const float* h_geo_w2, const float* h_geo_b2,
+                  const float* h_rad_w1, const float* h_rad_b1, const float* h_rad_w2, const float* h_rad_b2,
+                  const float* h_rad_w3, const float* h_rad_b3,
+                  const float* h_mat_w1, const float* h_mat_b1, const float* h_mat_w2, const float* h_mat_b2,
+                  const float* h_mat_w3, const float* h_mat_b3,
+                  const float* h_mat_scale5, const float* h_mat_bias5,
+                  const float* h_bbox6 /* canonical bbox min,max: prepare_bbox, geometry.py:61-68 */,
+                  float beta, void* stream);
+
+/* Skinning-weight voxel grid, reference layout [24, D, H, W] fp32 (ForwardDeformer.lbs_voxel_final,
+ * models/deformers/fast_snarf/deformer_torch.py:195); repacked channels-last into the context.     */
+int ia_set_lbs_voxels(ia_ctx* ctx, const float* d_lbs_voxel, int D, int H, int W,
+                      const float* h_offset_kernel3, const float* h_scale_kernel3, void* stream);
+
+/* Per-frame pose: tfs [24,4,4], w2s [4,4] (SNARFDeformer.prepare_deformer, snarf_deformer.py:98-106)
+ * and runs the voxel precompute (precompute_kernel, .../cuda/precompute/precompute.cu:22-103).       */
+int ia_set_pose(ia_ctx* ctx, const float* h_tfs, const float* h_w2s, void* stream);
+
+/* Render constants (configs/config.yaml:43-80).  albedo_align_ratio may be NULL (= 1).               */
+int ia_set_render_config(ia_ctx* ctx, const float* h_scene_aabb6, int num_samples_per_ray,
+                         int num_samples_per_secondary_ray, float secondary_near, float secondary_far,
+                         float occ_thre, const float* h_background3, const float* h_albedo_align_ratio3);
+
+/* Test-time occupancy grid (IntrinsicAvatarModel.prepare_test_occupancy_grid /
+ * _compute_occupancy_grid, models/intrinsic_avatar.py:307-381; max_connected_component,
+ * models/utils.py:152-163).  d_jitter: [res^3,3,3] uniforms in [0,1) (the reference's rand_like).
+ * d_binaries_out (optional, may be NULL): res^3 bytes.                                              */
+int ia_build_occupancy(ia_ctx* ctx, const float* h_aabb6, int res, const float* d_jitter,
+                       uint8_t* d_binaries_out, void* stream);
+/* Install a caller-provided grid instead (res^3 bytes, cell = (x*res+y)*res+z).                      */
+int ia_set_occupancy(ia_ctx* ctx, const float* h_aabb6, int res, const uint8_t* d_binaries, void* stream);
+
+/* Environment light (EnvironmentLightTensor.update_pdf/sample/pdf/eval, lib/torch_pbr/light.py:259-446).
+ * d_envmap [H,W,3] fp32 (referenced); d_u1/d_u2 [spp] uniforms replacing torch.rand in sample().
+ * Must be called after ia_set_pose (directions are rotated into the SMPL-root frame).
+ * Optional outputs (may be NULL): d_dirs_world_out [spp,3], d_em_out [spp,3], d_pdf_out [spp].        */
+int ia_set_light(ia_ctx* ctx, const float* d_envmap, int H, int W, const float* d_u1, const float* d_u2,
+                 int spp, float* d_dirs_world_out, float* d_em_out, float* d_pdf_out, void* stream);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+/* Output buffers of one forward pass, all DEVICE pointers, row-major [n_rays, C].  Any may be NULL.  */
+typedef struct ia_outputs {
+    float* comp_rgb;        /* [n,3] */
+    float* comp_normal;     /* [n,3] */
+    float* opacity;         /* [n,1] */
+    float* depth;           /* [n,1] */
+    float* comp_albedo;     /* [n,3] */
+    float* comp_roughness;  /* [n,1] */
+    float* comp_metallic;   /* [n,1] */
+    float* comp_rgb_phys;   /* [n,3] linear */
+    float* comp_demod_phys; /* [n,3] linear */
+    int32_t* num_samples;   /* [n]   shading samples per ray */
+    /* composited "_full" buffers (models/intrinsic_avatar.py:1625-1645) */
+    float* comp_rgb_full;        /* [n,3] sRGB, clamped */
+    float* comp_rgb_phys_full;   /* [n,3] sRGB, clamped */
+    float* comp_demod_phys_full; /* [n,3] sRGB, clamped */
+    float* comp_albedo_full;     /* [n,3] */
+    float* comp_roughness_full;  /* [n,1] */
+    float* comp_metallic_full;   /* [n,1] */
+} ia_outputs;
+
+#define IA_RENDER_PRIMARY_ONLY 1 /* stop after the primary volume render (albedo_only / config 2) */
+#define IA_RENDER_GI 2           /* global_illumination = true: add one indirect bounce           */
+
+/* IntrinsicAvatarModel.forward in eval mode, render_mode = "light"
+ * (models/intrinsic_avatar.py:950-1666; compute_indirect_radiance :396-545; pbr_light_forward :755-861;
+ * models/volrend.py:810-1020; models/pbr/utils.py:70-229).  d_rays [n,8] world-space o,d,near,far.
+ * The per-ray light permutation (reference: CPU rand + argsort, :1355-1378) is the stateless keyed
+ * permutation of (seed, ray_index_base + ray).  Does not sync.                                        */
+int ia_render(ia_ctx* ctx, const float* d_rays, int64_t n_rays, int64_t ray_index_base, int flags,
+              uint32_t seed, const ia_outputs* out, void* stream);
+
+/* Counters of the last ia_render / ia_query call (syncs the stream): see IA_CNT_* below.             */
+int ia_get_counters(ia_ctx* ctx, uint64_t* h_counters, void* stream);
+#define IA_CNT_HIT_RAYS 0
+#define IA_CNT_SAMPLES 1        /* primary shading samples */
+#define IA_CNT_QUERIES 2        /* posed-point queries (SDF only) */
+#define IA_CNT_QUERIES_GRAD 3   /* posed-point queries with gradient/feature */
+#define IA_CNT_BROYDEN_FETCH 4  /* voxel_J trilinear fetches */
+#define IA_CNT_GEO_EVAL 5       /* canonical geometry evaluations (hash grid + MLP) */
+#define IA_CNT_RAD_EVAL 6       /* radiance (+material) evaluations */
+#define IA_CNT_SECONDARY_RAYS 7
+#define IA_CNT_OVERFLOW 8       /* rays that exceeded the per-ray edge capacity / sample pool */
+#define IA_CNT_SKIN_FETCH 9     /* 24-channel skinning-weight fetches */
+
+/* Per-stage device timing (CUDA events recorded on the launching stream around each stage's kernels).
+ * ia_set_timing(ctx, 1) enables recording; ia_get_timings syncs the stream and returns, for each
+ * IA_STAGE_*, the elapsed ms of the most recent execution (-1 if the stage did not run), and the
+ * total number of kernels launched by this context since creation.                                  */
+#define IA_N_STAGES 8
+#define IA_STAGE_PRECOMPUTE 0
+#define IA_STAGE_OCCUPANCY 1
+#define IA_STAGE_LIGHT 2
+#define IA_STAGE_SETUP 3
+#define IA_STAGE_PRIMARY 4
+#define IA_STAGE_RESAMPLE 5
+#define IA_STAGE_SHADE 6
+#define IA_STAGE_COMPOSITE 7
+int ia_set_timing(ia_ctx* ctx, int enable);
+int ia_get_timings(ia_ctx* ctx, float* h_ms /* [IA_N_STAGES] */, uint64_t* h_launches, void* stream);
+
+/* ---- op-level entry points (A/B tests against the reference's pybind modules) --------------- */
+/* precompute.precompute(voxel_w, tfs, voxel_d, voxel_J, offset, scale)  precompute.cpp:6-13.
+ * d_voxel_J_out: reference layout [12, D, H, W].                                                      */
+int ia_op_precompute(ia_ctx* ctx, float* d_voxel_J_out, void* stream);
+
+/* fuse_cuda.fuse_broyden(...) + filter.filter(x, mask)  fuse_cuda.cpp:14-28, filter.cpp:12-22.
+ * d_xd [n,3] -> d_x [n,13,3], d_J_inv [n,13,3,3] (may be NULL), d_valid_raw [n,13] (before filter,
+ * may be NULL), d_valid [n,13] (after filter).                                                        */
+int ia_op_broyden(ia_ctx* ctx, const float* d_xd, int64_t n, float* d_x, float* d_J_inv,
+                  uint8_t* d_valid_raw, uint8_t* d_valid, void* stream);
+
+/* SNARFDeformer.deform + VolumeSDF.forward fused (snarf_deformer.py:187-261; geometry.py:124-172).
+ * Outputs (any may be NULL): d_sdf [n], d_xc [n,3], d_valid [n]; with_grad: d_grad [n,3] (posed),
+ * d_grad_cano [n,3], d_feature [n,13].                                                                */
+int ia_op_query(ia_ctx* ctx, const float* d_xd, int64_t n, int with_grad, float* d_sdf, float* d_xc,
+                uint8_t* d_valid, float* d_grad, float* d_grad_cano, float* d_feature, void* stream);
+
+/* radiance + material at canonical points (radiance.py:111-135, material.py:31-51):
+ * d_xc [n,3], d_feature [n,13], d_view_world [n,3], d_normal_world [n,3] -> d_rgb [n,3], d_mat [n,5]. */
+int ia_op_shade_fields(ia_ctx* ctx, const float* d_xc, const float* d_feature, const float* d_view_world,
+                       const float* d_normal_world, int64_t n, float* d_rgb, float* d_mat, void* stream);
+
+/* nerfacc traverse_grids as used by sampling_override (models/intrinsic_avatar.py:49-141), on the
+ * context's occupancy grid.  Two calls: d_vals == NULL counts (d_n_edges, d_n_samples [n]); else writes
+ * at the caller-computed exclusive prefix offsets d_edge_base / d_sample_base.                        */
+int ia_op_traverse(ia_ctx* ctx, const float* d_rays_o, const float* d_rays_d, int64_t n, float near_plane,
+                   float far_plane, float step, int32_t* d_n_edges, int32_t* d_n_samples,
+                   const int32_t* d_edge_base, const int32_t* d_sample_base, float* d_vals,
+                   uint8_t* d_is_left, uint8_t* d_is_right, float* d_t_starts, float* d_t_ends, void* stream);
+
+/* lib.nerfacc ray_resampling (cdf.cu:151-215): packed_info [n_rays,2]; d_resample_packed_info
+ * [n_rays,2] is an INPUT (exclusive prefix of (steps>0)*spp, spp) computed by the caller.             */
+int ia_op_ray_resampling(ia_ctx* ctx, const int32_t* d_packed_info, const float* d_starts,
+                         const float* d_ends, const float* d_weights, const float* d_sdfs, int64_t n_rays,
+                         int spp, const int32_t* d_resample_packed_info, float* d_ts, float* d_offsets,
+                         int64_t* d_indices, int32_t* d_fg_counts, int32_t* d_bg_counts,
+                         int64_t* d_surface_idx, void* stream);
+/* lib.nerfacc ray_resampling_merge (cdf.cu:336-401); outputs pre-zeroed by the caller.                */
+int ia_op_ray_resampling_merge(ia_ctx* ctx, const int32_t* d_packed_info, const float* d_vals,
+                               const uint8_t* d_is_left, const uint8_t* d_is_right, const float* d_weights,
+                               int64_t n_rays, const int32_t* d_resample_packed_info, float* d_vals_out,
+                               float* d_dists_out, uint8_t* d_is_left_out, uint8_t* d_is_right_out,
+                               uint8_t* d_is_resample_out, uint8_t* d_is_fg_out, void* stream);
+/* lib.nerfacc ray_resampling_sdf_fine (cdf.cu:640-696); outputs pre-zeroed by the caller.             */
+int ia_op_ray_resampling_sdf_fine(ia_ctx* ctx, const int32_t* d_packed_info, const float* d_starts,
+                                  const float* d_ends, const float* d_alphas, const float* d_sdfs,
+                                  int64_t n_rays, const int32_t* d_resample_packed_info, float* d_starts_out,
+                                  float* d_ends_out, uint8_t* d_is_fg_out, void* stream);
+/* lib.nerfacc unpack_info (pack.cu:84-107)                                                            */
+int ia_op_unpack_info(ia_ctx* ctx, const int32_t* d_packed_info, int64_t n_rays, int64_t* d_ray_indices,
+                      void* stream);
+/* secondary-ray transmittance / indirect radiance (compute_indirect_radiance,
+ * models/intrinsic_avatar.py:396-545): d_o, d_d [n,3] in the SMPL-root frame -> d_T [n], d_rgb [n,3]. */
+int ia_op_secondary(ia_ctx* ctx, const float* d_o, const float* d_d, int64_t n, int gi, float* d_T,
+                    float* d_rgb, void* stream);
+/* MultiLobe.eval (lib/torch_pbr/bxdf.py:321-330): wi, n, wo [n,3], rough [n], albedo [n,3], metal [n]
+ * -> diff [n], spec [n,3] (both include the cosine).                                                  */
+int ia_op_brdf(ia_ctx* ctx, const float* d_wi, const float* d_n, const float* d_wo, const float* d_rough,
+               const float* d_albedo, const float* d_metal, int64_t n, float* d_diff, float* d_spec,
+               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IA_B200_H */

@@ -1,0 +1,91 @@
+"""ctypes binding of ``libia_b200.so`` (include/ia_b200.h).  No torch types cross the ABI:
+tensors are passed as ``data_ptr()`` integers and the current CUDA stream handle.
+
+The library is the product; there is no fallback.  ``load()`` raises if it is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libia_b200.so")
+SRC_DIR = os.path.join(_HERE, "csrc")
+N_COUNTERS = 16
+COUNTER_NAMES = ["hit_rays", "samples", "queries", "queries_grad", "broyden_fetch", "geo_eval", "rad_eval",
+                 "secondary_rays", "overflow", "skin_fetch"]
+
+STAGE_NAMES = ["precompute", "occupancy", "light", "setup", "primary", "resample", "shade", "composite"]
+
+RENDER_PRIMARY_ONLY = 1
+RENDER_GI = 2
+
+
+class IaOutputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "comp_rgb", "comp_normal", "opacity", "depth", "comp_albedo", "comp_roughness", "comp_metallic",
+        "comp_rgb_phys", "comp_demod_phys", "num_samples", "comp_rgb_full", "comp_rgb_phys_full",
+        "comp_demod_phys_full", "comp_albedo_full", "comp_roughness_full", "comp_metallic_full")]
+
+
+EXPORTS = [
+    "ia_last_error", "ia_version", "ia_create", "ia_destroy", "ia_set_fields", "ia_set_lbs_voxels", "ia_set_pose",
+    "ia_set_render_config", "ia_build_occupancy", "ia_set_occupancy", "ia_set_light", "ia_render", "ia_get_counters", "ia_set_timing", "ia_get_timings",
+    "ia_op_precompute", "ia_op_broyden", "ia_op_query", "ia_op_shade_fields", "ia_op_traverse",
+    "ia_op_ray_resampling", "ia_op_ray_resampling_merge", "ia_op_ray_resampling_sdf_fine", "ia_op_unpack_info",
+    "ia_op_secondary", "ia_op_brdf",
+]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -> libia_b200.so for sm_100a (cross-compiles without a GPU)."""
+    srcs = [os.path.join(SRC_DIR, f) for f in sorted(os.listdir(SRC_DIR))]
+    hdr = os.path.join(_HERE, "..", "include", "ia_b200.h")
+    newest = max(os.path.getmtime(p) for p in srcs + [hdr])
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
+        return LIB_PATH
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+           "-Xcompiler", "-fPIC", "-o", LIB_PATH, os.path.join(SRC_DIR, "ia_kernels.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "There is no CPU or PyTorch fallback for the render path.")
+    lib = C.CDLL(LIB_PATH)
+    lib.ia_last_error.restype = C.c_char_p
+    for name in EXPORTS:
+        getattr(lib, name)  # raises AttributeError if a declared symbol is not exported
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().ia_last_error().decode()
+        raise RuntimeError(f"libia_b200 {what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor (or None) as c_void_p."""
+    if t is None:
+        return C.c_void_p(0)
+    assert t.is_contiguous(), "libia_b200 takes contiguous buffers"
+    return C.c_void_p(t.data_ptr())
+
+
+def fptr(a):
+    """Host float32/int32 numpy array -> pointer."""
+    return a.ctypes.data_as(C.c_void_p)

@@ -1,0 +1,921 @@
+// Render pipeline kernels (included at the end of ia_kernels.cu).
+//
+//   k_primary_setup : world->SMPL ray transform, grid march count, hit list, default outputs
+//   k_primary       : team-per-hit-ray: march -> 2x (SDF query + CDF merge resample) -> shading
+//                     (deform + geometry w/ gradient + radiance + material) -> accumulate; emits
+//                     the per-ray shading samples for the PBR stage
+//   k_resample      : warp-per-hit-ray `ray_resampling` (spp shading samples, zero-crossing snap)
+//   k_shade         : persistent tiles of 1024 shading samples: light pick, cosine test,
+//                     compaction of live secondary rays into a shared queue, team-per-ray lazy
+//                     secondary tracing, BRDF, accumulation
+//   k_composite     : background composite + sRGB
+#pragma once
+
+#define IA_PRIMARY_THREADS 256
+#define IA_SHADE_THREADS 256
+#define IA_TILE 1024
+#define IA_TILE_PIX 520  // >= IA_TILE / 2 + 2 pixel slots per tile (spp >= 2)
+
+// work counter slots in ctx->d_work
+#define IA_W_NHIT 0
+#define IA_W_NSAMPLES 1
+#define IA_W_PRIMARY_NEXT 2
+#define IA_W_TILE_NEXT 3
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ia_ray_w2s(const IaFrame& p, const float* __restrict__ ray, float o[3], float d[3],
+                                           float& far) {
+    // transform_rays_w2s (models/deformers/snarf_deformer.py:128-144)
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        o[i] = ray[0] * p.w2s[i * 4 + 0] + ray[1] * p.w2s[i * 4 + 1] + ray[2] * p.w2s[i * 4 + 2] + p.w2s[i * 4 + 3];
+        d[i] = ray[3] * p.w2s[i * 4 + 0] + ray[4] * p.w2s[i * 4 + 1] + ray[5] * p.w2s[i * 4 + 2];
+    }
+    far = sqrtf(o[0] * o[0] + o[1] * o[1] + o[2] * o[2]) + 1.0f;
+}
+
+__global__ void k_primary_setup(const __grid_constant__ IaFrame p, const float* __restrict__ rays, long long n_rays,
+                                int* __restrict__ hit_rays, float* __restrict__ hit_od, int* __restrict__ work,
+                                ia_outputs out, float* __restrict__ acc6) {
+    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit = false;
+    float o[3], d[3], far = 0.f;
+    if (r < n_rays) {
+        ia_ray_w2s(p, rays + r * 8, o, d, far);
+        IaMarcher m;
+        m.init(p, o, d, 0.0f, 1e10f, p.step_primary);
+        float ts, te;
+        bool cont;
+        hit = m.next(p.occ_bits, p.occ_res, ts, te, cont);
+        // defaults of a ray without samples
+        if (out.comp_rgb) { out.comp_rgb[r * 3] = 0.f; out.comp_rgb[r * 3 + 1] = 0.f; out.comp_rgb[r * 3 + 2] = 0.f; }
+        if (out.comp_normal) { out.comp_normal[r * 3] = 0.f; out.comp_normal[r * 3 + 1] = 0.f; out.comp_normal[r * 3 + 2] = 0.f; }
+        if (out.comp_albedo) { out.comp_albedo[r * 3] = 0.f; out.comp_albedo[r * 3 + 1] = 0.f; out.comp_albedo[r * 3 + 2] = 0.f; }
+        if (out.opacity) out.opacity[r] = 0.f;
+        if (out.depth) out.depth[r] = far;
+        if (out.comp_roughness) out.comp_roughness[r] = 0.f;
+        if (out.comp_metallic) out.comp_metallic[r] = 0.f;
+        if (out.num_samples) out.num_samples[r] = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) acc6[r * 6 + k] = hit ? 0.f : p.background[k % 3];
+    }
+    // warp-aggregated append to the hit list
+    unsigned b = __ballot_sync(0xffffffffu, hit);
+    int lane = threadIdx.x & 31;
+    int base = 0;
+    if (b && lane == 0) base = atomicAdd(&work[IA_W_NHIT], __popc(b));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (hit) {
+        int slot = base + __popc(b & ((1u << lane) - 1));
+        hit_rays[slot] = (int)r;
+        float* od = hit_od + (size_t)slot * 8;
+        od[0] = o[0]; od[1] = o[1]; od[2] = o[2]; od[3] = d[0]; od[4] = d[1]; od[5] = d[2]; od[6] = far; od[7] = 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct IaPrimarySmem {
+    float vals[2][IA_CAP];
+    float aux[IA_CAP];
+    uint8_t flags[2][IA_CAP];
+};
+
+__global__ void __launch_bounds__(IA_PRIMARY_THREADS, 1)
+k_primary(const __grid_constant__ IaFrame p, const int* __restrict__ hit_rays, float* __restrict__ hit_od,
+          int* __restrict__ hit_info, IaSample* __restrict__ samples, long long sample_cap, int* __restrict__ work,
+          ia_outputs out, unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) float smem[];
+    float* wmlp = smem;
+    IaPrimarySmem* tsm = reinterpret_cast<IaPrimarySmem*>(smem + IA_MLP_END);
+    ia_stage(wmlp, p.mlp, IA_MLP_END);
+    __syncthreads();
+    Team team = cg::tiled_partition<IA_TEAM>(cg::this_thread_block());
+    const int lane = team.thread_rank();
+    IaPrimarySmem& S = tsm[threadIdx.x / IA_TEAM];
+    const int n_hit = work[IA_W_NHIT];
+    unsigned c_q = 0, c_qg = 0, c_fetch = 0, c_geo = 0, c_rad = 0, c_over = 0, c_samples = 0;
+    const float step = p.step_primary;
+
+    while (true) {
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(&work[IA_W_PRIMARY_NEXT], 1);
+        slot = team.shfl(slot, 0);
+        if (slot >= n_hit) break;
+        const int ray = hit_rays[slot];
+        float* od = hit_od + (size_t)slot * 8;
+        const float o[3] = {od[0], od[1], od[2]}, d[3] = {od[3], od[4], od[5]};
+        const float far = od[6];
+
+        // ---- 1. grid march -> edge list (uniform across the team; lane 0 writes)
+        int ne = 0;
+        {
+            IaMarcher m;
+            m.init(p, o, d, 0.0f, 1e10f, step);
+            float ts, te;
+            bool cont;
+            bool over = false;
+            while (m.next(p.occ_bits, p.occ_res, ts, te, cont)) {
+                if (ne + 2 > IA_CAP - 34) { over = true; break; }
+                if (!cont) {
+                    if (lane == 0) { S.vals[0][ne] = ts; S.flags[0][ne] = 1; S.vals[0][ne + 1] = te; S.flags[0][ne + 1] = 2; }
+                    ne += 2;
+                } else {
+                    if (lane == 0) { S.vals[0][ne] = te; S.flags[0][ne - 1] |= 1; S.flags[0][ne] = 2; }
+                    ne += 1;
+                }
+            }
+            if (over) c_over++;
+        }
+        team.sync();
+        int cur = 0;
+        IaQuery q;
+        // ---- 2. two rounds of importance resampling (models/intrinsic_avatar.py:1185-1238)
+        for (int round = 0; round < 2; round++) {
+            const float* vals = S.vals[cur];
+            const uint8_t* fl = S.flags[cur];
+            if (round == 0) {
+                // coarse_alpha_fn: SDF at every edge
+                for (int e = 0; e < ne; e++) {
+                    float t = vals[e];
+                    float x[3] = {o[0] + d[0] * t, o[1] + d[1] * t, o[2] + d[2] * t};
+                    ia_team_query<false>(team, p, wmlp, x, q);
+                    c_q++; c_fetch += q.n_fetch; c_geo += q.n_valid;
+                    if (lane == 0) S.aux[e] = q.sdf;
+                }
+                team.sync();
+                if (lane == 0) {
+                    // alpha from min(sdf_L, sdf_R), fixed dist; then weights = T * alpha
+                    float T = 1.f;
+                    for (int e = 0; e < ne; e++) {
+                        float a = 0.f;
+                        if ((fl[e] & 1) && e + 1 < ne) a = ia_alpha(fminf(S.aux[e], S.aux[e + 1]), step, p.beta);
+                        S.aux[e] = T * a;
+                        T *= (1.f - a);
+                    }
+                }
+            } else {
+                // alpha_fn: SDF at interval midpoints, dist = t_R - t_L
+                for (int e = 0; e + 1 < ne; e++) {
+                    float sd = 0.f;
+                    bool is_iv = (fl[e] & 1) != 0;
+                    if (is_iv) {
+                        float t = (vals[e] + vals[e + 1]) / 2.0f;
+                        float x[3] = {o[0] + d[0] * t, o[1] + d[1] * t, o[2] + d[2] * t};
+                        ia_team_query<false>(team, p, wmlp, x, q);
+                        c_q++; c_fetch += q.n_fetch; c_geo += q.n_valid;
+                        sd = q.sdf;
+                    }
+                    if (lane == 0) S.aux[e] = is_iv ? sd : 1e10f;
+                }
+                team.sync();
+                if (lane == 0) {
+                    float T = 1.f;
+                    for (int e = 0; e < ne; e++) {
+                        float a = 0.f;
+                        if ((fl[e] & 1) && e + 1 < ne) a = ia_alpha(S.aux[e], vals[e + 1] - vals[e], p.beta);
+                        S.aux[e] = T * a;
+                        T *= (1.f - a);
+                    }
+                }
+            }
+            team.sync();
+            int n_out = 0;
+            if (lane == 0) n_out = ia_merge_resample(vals, fl, S.aux, ne, 16, S.vals[cur ^ 1], S.flags[cur ^ 1], nullptr);
+            n_out = team.shfl(n_out, 0);
+            team.sync();
+            ne = n_out;
+            cur ^= 1;
+        }
+        // ---- 3. shading (rendering_with_normals_mats_sdf + rgb_normal_mats_alpha_fn)
+        const float* vals = S.vals[cur];
+        const uint8_t* fl = S.flags[cur];
+        int n_iv = 0;
+        for (int e = 0; e + 1 < ne; e++) n_iv += (fl[e] & 1);
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&work[IA_W_NSAMPLES], n_iv);
+        base = team.shfl(base, 0);
+        bool pool_ok = (long long)base + n_iv <= sample_cap;
+        if (!pool_ok) c_over++;
+        float view_w[3];
+        ia_dir_s2w(p, d, view_w);
+        float T = 1.f;
+        float a_rgb[3] = {0, 0, 0}, a_n[3] = {0, 0, 0}, a_alb[3] = {0, 0, 0}, a_r = 0, a_m = 0, a_op = 0, a_dep = 0;
+        int k = 0;
+        for (int e = 0; e + 1 < ne; e++) {
+            if (!(fl[e] & 1)) continue;
+            float ts = vals[e], te = vals[e + 1];
+            float tm = (ts + te) / 2.0f;
+            float x[3] = {o[0] + d[0] * tm, o[1] + d[1] * tm, o[2] + d[2] * tm};
+            ia_team_query<true>(team, p, wmlp, x, q);
+            c_qg++; c_fetch += q.n_fetch; c_geo += q.n_valid + (q.valid ? 1 : 0);
+            float alpha = ia_alpha(q.sdf, te - ts, p.beta);
+            float w = T * alpha;
+            T *= (1.f - alpha);
+            float nsm[3], nw[3], rgb[3] = {0, 0, 0}, mat[5] = {0, 0, 0, 0, 0};
+            ia_normalize(q.grad, nsm, 1e-6f);
+            ia_dir_s2w(p, q.grad, nw);
+            if (q.valid) {
+                ia_team_radiance<true>(team, p, wmlp, q.xc, q.feat, view_w, nw, rgb, mat);
+                c_rad++;
+            }
+#pragma unroll
+            for (int c3 = 0; c3 < 3; c3++) {
+                a_rgb[c3] += w * rgb[c3];
+                a_n[c3] += w * nw[c3];
+                a_alb[c3] += w * mat[c3];
+            }
+            a_r += w * mat[3]; a_m += w * mat[4]; a_op += w; a_dep += w * tm;
+            if (pool_ok && lane == 0) {
+                IaSample s;
+                s.ts = ts; s.te = te; s.w = w; s.sdf = q.sdf;
+                s.n[0] = nsm[0]; s.n[1] = nsm[1]; s.n[2] = nsm[2];
+                s.albedo[0] = mat[0]; s.albedo[1] = mat[1]; s.albedo[2] = mat[2];
+                s.rough = mat[3]; s.metal = mat[4];
+                samples[(size_t)base + k] = s;
+            }
+            k++;
+        }
+        c_samples += n_iv;
+        if (lane == 0) {
+            hit_info[slot * 2 + 0] = base;
+            hit_info[slot * 2 + 1] = pool_ok ? n_iv : 0;
+            od[7] = a_op;
+            size_t r = (size_t)ray;
+            if (out.comp_rgb) { out.comp_rgb[r * 3] = a_rgb[0]; out.comp_rgb[r * 3 + 1] = a_rgb[1]; out.comp_rgb[r * 3 + 2] = a_rgb[2]; }
+            if (out.comp_normal) { out.comp_normal[r * 3] = a_n[0]; out.comp_normal[r * 3 + 1] = a_n[1]; out.comp_normal[r * 3 + 2] = a_n[2]; }
+            if (out.comp_albedo) { out.comp_albedo[r * 3] = a_alb[0]; out.comp_albedo[r * 3 + 1] = a_alb[1]; out.comp_albedo[r * 3 + 2] = a_alb[2]; }
+            if (out.opacity) out.opacity[r] = a_op;
+            if (out.depth) out.depth[r] = a_dep + (1.0f - a_op) * far;
+            if (out.comp_roughness) out.comp_roughness[r] = a_r;
+            if (out.comp_metallic) out.comp_metallic[r] = a_m;
+            if (out.num_samples) out.num_samples[r] = n_iv;
+        }
+        team.sync();
+    }
+    if (lane == 0) {
+        if (c_q) atomicAdd(&counters[IA_CNT_QUERIES], c_q);
+        if (c_qg) atomicAdd(&counters[IA_CNT_QUERIES_GRAD], c_qg);
+        if (c_rad) atomicAdd(&counters[IA_CNT_RAD_EVAL], c_rad);
+        if (c_geo) atomicAdd(&counters[IA_CNT_GEO_EVAL], c_geo);
+        if (c_over) atomicAdd(&counters[IA_CNT_OVERFLOW], c_over);
+        if (c_samples) atomicAdd(&counters[IA_CNT_SAMPLES], c_samples);
+        if (c_qg) atomicAdd(&counters[IA_CNT_SKIN_FETCH], c_qg);
+    }
+    if (c_fetch) atomicAdd(&counters[IA_CNT_BROYDEN_FETCH], c_fetch);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ray_resampling (cdf_resampling_kernel, cdf.cu:9-149) for one ray by one warp, parallel over the
+// spp outputs.  The serial walk of the reference is equivalent to, per output j:
+//   idx_j = first interval with u_j < cdf_next[idx]   (none -> background)
+// and the zero-crossing snap only depends on i* = first crossing interval and j0 = first output at
+// or past it whose interpolated SDF is negative.  Every float operation on a given
+// output is the same as in the serial kernel.
+// Generic strided input so it serves both the pipeline (IaSample AoS) and the op-level entry point.
+struct IaResampleIn {
+    const float* starts; const float* ends; const float* weights; const float* sdfs;
+    int stride;  // in floats
+};
+
+__device__ __forceinline__ int ia_count_below(const float* __restrict__ u, int n, float c) {  // #{j : u_j < c}
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (u[mid] < c) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// cdf: per-warp shared scratch [IA_CAP].  Outputs may be NULL individually.
+__device__ __forceinline__ void ia_warp_resample(const IaResampleIn& in, int steps, int spp, const float* __restrict__ u_table,
+                                                 float* cdf, float transmittance, long long src_base,
+                                                 float* __restrict__ o_t, float* __restrict__ o_off, long long* __restrict__ o_idx64,
+                                                 int* __restrict__ o_src, float* __restrict__ o_w,
+                                                 int* __restrict__ o_fg_counts, int* __restrict__ o_bg_count,
+                                                 long long* __restrict__ o_surface) {
+    const int lane = threadIdx.x & 31;
+    const int st = in.stride;
+    if (lane == 0) {
+        float weights_sum = 0.0f;
+        for (int j = 0; j < steps; j++) weights_sum += in.weights[(size_t)j * st];
+        weights_sum += fmaxf(1.0f - weights_sum, 0.0f);
+        float c = in.weights[0] / weights_sum;
+        cdf[0] = c;
+        for (int i = 1; i < steps; i++) { c += in.weights[(size_t)i * st] / weights_sum; cdf[i] = c; }
+    }
+    __syncwarp();
+    // first crossing interval
+    int istar = 0x7fffffff;
+    for (int i = lane; i < steps - 1; i += 32) {
+        float a = in.sdfs[(size_t)i * st], b = in.sdfs[(size_t)(i + 1) * st];
+        if (a >= 0 && b < 0) istar = min(istar, i);
+    }
+    for (int o = 16; o > 0; o >>= 1) istar = min(istar, __shfl_xor_sync(0xffffffffu, istar, o));
+    // pass 1: j0
+    int j0 = 0x7fffffff;
+    for (int j = lane; j < spp; j += 32) {
+        float u = u_table[j];
+        int idx = ia_count_below(cdf, steps, u);  // cdf non-decreasing: first idx with u < cdf[idx] == #{cdf <= u}
+        // (ia_count_below counts cdf[i] < u; ties u == cdf[i] must NOT count as "u < cdf": fix up)
+        while (idx < steps && !(u < cdf[idx])) idx++;
+        if (idx < steps) {
+            bool snap = idx > istar;
+            if (idx == istar) {
+                float s = in.starts[(size_t)idx * st], e = in.ends[(size_t)idx * st];
+                float cp = idx ? cdf[idx - 1] : 0.0f, cn = cdf[idx];
+                float scaling = (e - s) / (cn - cp);
+                float offset = (u - cp) * scaling;
+                float sp = in.sdfs[(size_t)idx * st], sn = in.sdfs[(size_t)(idx + 1) * st];
+                float sdf_approx = sp + (sn - sp) * (offset / (e - s));
+                snap = !(sdf_approx >= 0);
+            }
+            if (snap) j0 = min(j0, j);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) j0 = min(j0, __shfl_xor_sync(0xffffffffu, j0, o));
+    // the t every snapped output repeats
+    float t_snap = 0.f;
+    if (j0 != 0x7fffffff) {
+        int jj = j0 > 0 ? j0 - 1 : 0;
+        float u = u_table[jj];
+        int idx = ia_count_below(cdf, steps, u);
+        while (idx < steps && !(u < cdf[idx])) idx++;
+        float s = in.starts[(size_t)idx * st], e = in.ends[(size_t)idx * st];
+        if (j0 > 0) {
+            float cp = idx ? cdf[idx - 1] : 0.0f, cn = cdf[idx];
+            float scaling = (e - s) / (cn - cp);
+            float offset = (u - cp) * scaling;
+            t_snap = offset + s;
+        } else {
+            t_snap = s;
+        }
+    }
+    const int n_fg = ia_count_below(u_table, spp, cdf[steps - 1]);
+    const int n_bg = spp - n_fg;
+    if (o_bg_count && lane == 0) *o_bg_count = n_bg;
+    if (o_surface && lane == 0) {
+        // surface_idx is recorded when the walk advances past i*: that needs an output at or beyond
+        // interval i*+1, or the walk ending there; the walk stops advancing once all spp are placed.
+        // It advances past i* iff some output (or the end) lies beyond: last fg idx > i* or n_bg > 0.
+        int last_idx = -1;
+        if (n_fg > 0) {
+            float u = u_table[n_fg - 1];
+            last_idx = ia_count_below(cdf, steps, u);
+            while (last_idx < steps && !(u < cdf[last_idx])) last_idx++;
+        }
+        bool passed = istar != 0x7fffffff && (last_idx > istar || n_bg > 0);
+        *o_surface = passed ? (long long)istar + src_base : -1;
+    }
+    if (o_fg_counts) {
+        for (int i = lane; i < steps; i += 32) {
+            float cp = i ? cdf[i - 1] : 0.0f;
+            o_fg_counts[i] = ia_count_below(u_table, spp, cdf[i]) - ia_count_below(u_table, spp, cp);
+        }
+    }
+    const float end_last = in.ends[(size_t)(steps - 1) * st];
+    // pass 2: outputs
+    for (int j = lane; j < spp; j += 32) {
+        float u = u_table[j];
+        int idx = ia_count_below(cdf, steps, u);
+        while (idx < steps && !(u < cdf[idx])) idx++;
+        if (idx < steps) {
+            float s = in.starts[(size_t)idx * st], e = in.ends[(size_t)idx * st];
+            float cp = idx ? cdf[idx - 1] : 0.0f, cn = cdf[idx];
+            float scaling = (e - s) / (cn - cp);
+            float offset = (u - cp) * scaling;
+            float t = offset + s;
+            if (j >= j0) t = t_snap;
+            if (o_t) o_t[j] = t;
+            if (o_off) o_off[j] = offset;
+            if (o_idx64) o_idx64[j] = idx + src_base;
+            if (o_src) o_src[j] = (int)(idx + src_base);
+            if (o_w) {
+                int cnt = ia_count_below(u_table, spp, cn) - ia_count_below(u_table, spp, cp);
+                o_w[j] = in.weights[(size_t)idx * st] / (float)cnt;
+            }
+        } else {
+            float offset = 10000.f;
+            if (o_t) o_t[j] = offset + end_last;
+            if (o_off) o_off[j] = offset;
+            if (o_idx64) o_idx64[j] = steps - 1 + src_base;
+            if (o_src) o_src[j] = -1;
+            if (o_w) o_w[j] = transmittance / (float)n_bg;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_resample(const int* __restrict__ hit_info, const float* __restrict__ hit_od,
+                                                  const IaSample* __restrict__ samples, const int* __restrict__ work,
+                                                  int spp, const float* __restrict__ u_table, float* __restrict__ rs_t,
+                                                  int* __restrict__ rs_src, float* __restrict__ rs_w) {
+    __shared__ float cdf_s[8][IA_CAP];
+    const int n_hit = work[IA_W_NHIT];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int slot = blockIdx.x * 8 + warp; slot < n_hit; slot += gridDim.x * 8) {
+        int base = hit_info[slot * 2], steps = hit_info[slot * 2 + 1];
+        size_t ob = (size_t)slot * spp;
+        if (steps == 0) {
+            // no shading sample survived: all background with the ray's full transmittance
+            for (int j = lane; j < spp; j += 32) { rs_t[ob + j] = 0.f; rs_src[ob + j] = -1; rs_w[ob + j] = 1.0f / (float)spp; }
+            continue;
+        }
+        const float* sp = reinterpret_cast<const float*>(samples + base);
+        IaResampleIn in{sp + 0, sp + 1, sp + 2, sp + 3, (int)(sizeof(IaSample) / sizeof(float))};
+        float trans = 1.0f - hit_od[(size_t)slot * 8 + 7];
+        ia_warp_resample(in, steps, spp, u_table, cdf_s[warp], trans, (long long)base, rs_t + ob, nullptr, nullptr,
+                         rs_src + ob, rs_w + ob, nullptr, nullptr, nullptr);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool GI>
+__global__ void __launch_bounds__(IA_SHADE_THREADS, 2)
+k_shade(const __grid_constant__ IaFrame p, const int* __restrict__ hit_rays, const float* __restrict__ hit_od,
+        const IaSample* __restrict__ samples, const float* __restrict__ rs_t, const int* __restrict__ rs_src,
+        const float* __restrict__ rs_w, int* __restrict__ work, int spp, long long ray_index_base, uint32_t seed,
+        const float* __restrict__ light_dir_s, const float* __restrict__ light_em, const float* __restrict__ light_pdf,
+        float* __restrict__ acc6, unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) float smem[];
+    const int n_w = GI ? IA_RAD_END : IA_GEO_END;
+    float* wmlp = smem;
+    uint32_t* occ = reinterpret_cast<uint32_t*>(smem + n_w);
+    const int occ_words = p.occ_res * p.occ_res * p.occ_res / 32;
+    float* pix_acc = reinterpret_cast<float*>(occ + occ_words);                 // [IA_TILE_PIX][6]
+    uint16_t* queue = reinterpret_cast<uint16_t*>(pix_acc + IA_TILE_PIX * 6);   // [IA_TILE]
+    __shared__ int s_qcount, s_qhead, s_tile;
+    ia_stage(wmlp, p.mlp, n_w);
+    for (int i = threadIdx.x; i < occ_words; i += blockDim.x) occ[i] = p.occ_bits[i];
+    __syncthreads();
+    Team team = cg::tiled_partition<IA_TEAM>(cg::this_thread_block());
+    const int lane = team.thread_rank();
+    const long long n_total = (long long)work[IA_W_NHIT] * spp;
+    const long long n_tiles = (n_total + IA_TILE - 1) / IA_TILE;
+    IaTraceCounters cnt = {0, 0, 0, 0, 0, 0};
+    unsigned c_rays = 0;
+
+    while (true) {
+        if (threadIdx.x == 0) {
+            s_tile = atomicAdd(&work[IA_W_TILE_NEXT], 1);
+            s_qcount = 0;
+            s_qhead = 0;
+        }
+        for (int i = threadIdx.x; i < IA_TILE_PIX * 6; i += blockDim.x) pix_acc[i] = 0.f;
+        __syncthreads();
+        const long long tile = s_tile;
+        if (tile >= n_tiles) break;
+        const long long s0 = tile * IA_TILE;
+        const int first_slot = (int)(s0 / spp);
+        // ---- phase 1: per-sample cosine test, compaction of live rays
+        for (int i = threadIdx.x; i < IA_TILE; i += blockDim.x) {
+            long long s = s0 + i;
+            if (s >= n_total) break;
+            int slot = (int)(s / spp), j = (int)(s % spp);
+            int src = rs_src[s];
+            float w = rs_w[s];
+            float* pa = pix_acc + (slot - first_slot) * 6;
+            if (src < 0) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    atomicAdd(&pa[k], w * p.background[k]);
+                    atomicAdd(&pa[3 + k], w * p.background[k]);
+                }
+                continue;
+            }
+            const IaSample& sm = samples[src];
+            uint32_t key = ia_pixel_key(seed, (uint64_t)(ray_index_base + hit_rays[slot]));
+            uint32_t kk = ia_permute((uint32_t)j, (uint32_t)spp, key);
+            const float* wo = light_dir_s + kk * 3;
+            float cosv = sm.n[0] * wo[0] + sm.n[1] * wo[1] + sm.n[2] * wo[2];
+            if (cosv > 1e-6f) {
+                int qi = atomicAdd(&s_qcount, 1);
+                queue[qi] = (uint16_t)i;
+            }
+        }
+        __syncthreads();
+        const int qn = s_qcount;
+        // ---- phase 2: teams pull live secondary rays
+        while (true) {
+            int qi = 0;
+            if (lane == 0) qi = atomicAdd(&s_qhead, 1);
+            qi = team.shfl(qi, 0);
+            if (qi >= qn) break;
+            const int i = queue[qi];
+            const long long s = s0 + i;
+            const int slot = (int)(s / spp), j = (int)(s % spp);
+            const IaSample sm = samples[rs_src[s]];
+            const float w = rs_w[s], t = rs_t[s];
+            const float* od = hit_od + (size_t)slot * 8;
+            const float d[3] = {od[3], od[4], od[5]};
+            const float pos[3] = {od[0] + d[0] * t, od[1] + d[1] * t, od[2] + d[2] * t};
+            uint32_t key = ia_pixel_key(seed, (uint64_t)(ray_index_base + hit_rays[slot]));
+            uint32_t kk = ia_permute((uint32_t)j, (uint32_t)spp, key);
+            const float wo[3] = {light_dir_s[kk * 3], light_dir_s[kk * 3 + 1], light_dir_s[kk * 3 + 2]};
+            float T, ind[3];
+            ia_team_trace<GI>(team, p, wmlp, wmlp, occ, pos, wo, T, ind, cnt);
+            c_rays++;
+            if (lane == 0) {
+                float tr = fminf(fmaxf(T, 0.f), 1.f);
+                const float wi[3] = {-d[0], -d[1], -d[2]};
+                float diff, spec[3];
+                ia_brdf_multilobe(wi, sm.n, wo, sm.rough, sm.albedo, sm.metal, diff, spec);
+                bool lit = tr > 0.0f;
+                float pdf = lit ? light_pdf[kk] : 1.0f;
+                if (!(pdf > 0)) pdf = 1.0f;
+                float* pa = pix_acc + (slot - (int)(s0 / spp)) * 6;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    float em = lit ? light_em[kk * 3 + k] : 0.f;
+                    float Li = em * tr;
+                    if (GI) Li += ind[k];
+                    float Ld = Li * diff / pdf, Ls = Li * spec[k] / pdf;
+                    float kd = (1.0f - sm.metal) * sm.albedo[k];
+                    atomicAdd(&pa[k], w * (kd * Ld + Ls));
+                    atomicAdd(&pa[3 + k], w * (Ld + Ls));
+                }
+            }
+        }
+        __syncthreads();
+        // ---- flush the tile's pixel accumulators
+        const int last_slot = (int)((min(s0 + IA_TILE, n_total) - 1) / spp);
+        for (int i = threadIdx.x; i < (last_slot - first_slot + 1) * 6; i += blockDim.x) {
+            int slot = first_slot + i / 6;
+            atomicAdd(&acc6[(size_t)hit_rays[slot] * 6 + i % 6], pix_acc[i]);
+        }
+        __syncthreads();
+    }
+    if (lane == 0) {
+        if (cnt.q) atomicAdd(&counters[IA_CNT_QUERIES], cnt.q);
+        if (cnt.qg) atomicAdd(&counters[IA_CNT_QUERIES_GRAD], cnt.qg);
+        if (cnt.geo) atomicAdd(&counters[IA_CNT_GEO_EVAL], cnt.geo);
+        if (cnt.rad) atomicAdd(&counters[IA_CNT_RAD_EVAL], cnt.rad);
+        if (cnt.skin) atomicAdd(&counters[IA_CNT_SKIN_FETCH], cnt.skin);
+        if (c_rays) atomicAdd(&counters[IA_CNT_SECONDARY_RAYS], c_rays);
+    }
+    if (cnt.fetch) atomicAdd(&counters[IA_CNT_BROYDEN_FETCH], cnt.fetch);
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ia_srgb(float f) {
+    float v = f <= 0.0031308f ? f * 12.92f : powf(fmaxf(f, 0.0031308f), 1.0f / 2.4f) * 1.055f - 0.055f;
+    return fminf(fmaxf(v, 0.f), 1.f);
+}
+
+__global__ void k_composite(const __grid_constant__ IaFrame p, long long n, const float* __restrict__ acc6, ia_outputs out,
+                            int primary_only) {
+    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    float op = out.opacity ? out.opacity[r] : 0.f;
+    float bgm = (p.background[0] + p.background[1] + p.background[2]) / 3.0f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float phys = primary_only ? p.background[k] : acc6[r * 6 + k];
+        float dem = primary_only ? p.background[k] : acc6[r * 6 + 3 + k];
+        if (out.comp_rgb_phys) out.comp_rgb_phys[r * 3 + k] = phys;
+        if (out.comp_demod_phys) out.comp_demod_phys[r * 3 + k] = dem;
+        if (out.comp_rgb_phys_full) out.comp_rgb_phys_full[r * 3 + k] = ia_srgb(phys);
+        if (out.comp_demod_phys_full) out.comp_demod_phys_full[r * 3 + k] = ia_srgb(dem);
+        if (out.comp_rgb_full && out.comp_rgb) out.comp_rgb_full[r * 3 + k] = ia_srgb(out.comp_rgb[r * 3 + k] + p.background[k] * (1.0f - op));
+        if (out.comp_albedo_full && out.comp_albedo) out.comp_albedo_full[r * 3 + k] = out.comp_albedo[r * 3 + k] + 0.f * (1.0f - op);
+    }
+    if (out.comp_roughness_full && out.comp_roughness) out.comp_roughness_full[r] = out.comp_roughness[r] + bgm * (1.0f - op);
+    if (out.comp_metallic_full && out.comp_metallic) out.comp_metallic_full[r] = out.comp_metallic[r] + bgm * (1.0f - op);
+}
+
+// ================================================================================================
+static int ia_ws_reserve(ia_ctx* c, int64_t n_rays, int spp, bool need_pbr) {
+    if (n_rays > c->ws_rays) {
+        if (ia_realloc(&c->d_hit_rays, (size_t)n_rays) || ia_realloc(&c->d_hit_od, (size_t)n_rays * 8) ||
+            ia_realloc(&c->d_hit_info, (size_t)n_rays * 2) || ia_realloc(&c->d_acc, (size_t)n_rays * 6))
+            return IA_ECUDA;
+        c->ws_rays = n_rays;
+    }
+    int64_t want_samples = std::max<int64_t>(n_rays * 24, 1 << 16);
+    if (want_samples > c->ws_samples) {
+        if (ia_realloc(&c->d_samples, (size_t)want_samples)) return IA_ECUDA;
+        c->ws_samples = want_samples;
+    }
+    if (need_pbr) {
+        // worst case every ray hits; grown lazily to n_rays * spp (805 MB at 512^2 x 1024 for 25 % hits
+        // would suffice, but the hit count is only known on the device)
+        int64_t want = n_rays * (int64_t)spp;
+        if (want > c->ws_resamples) {
+            if (ia_realloc(&c->d_rs_t, (size_t)want) || ia_realloc(&c->d_rs_w, (size_t)want) ||
+                ia_realloc(&c->d_rs_src, (size_t)want))
+                return IA_ECUDA;
+            c->ws_resamples = want;
+        }
+    }
+    return IA_OK;
+}
+
+extern "C" int ia_render(ia_ctx* c, const float* d_rays, int64_t n_rays, int64_t ray_index_base, int flags, uint32_t seed,
+                         const ia_outputs* out, void* stream) {
+    IA_REQUIRE(c && d_rays && out, IA_EINVAL, "ia_render: NULL argument");
+    IA_REQUIRE(c->have_fields && c->have_pose && c->have_occ && c->have_cfg, IA_ESTATE,
+               "ia_render: fields / pose / occupancy / render config must be set");
+    const bool primary_only = flags & IA_RENDER_PRIMARY_ONLY;
+    const bool gi = flags & IA_RENDER_GI;
+    IA_REQUIRE(primary_only || c->have_light, IA_ESTATE, "ia_render: call ia_set_light first");
+    IA_REQUIRE(c->f.occ_res * c->f.occ_res * c->f.occ_res / 8 <= 64 * 1024, IA_EINVAL, "ia_render: occupancy grid too large for shared memory");
+    IA_CHECK_CUDA(cudaSetDevice(c->device));
+    if (n_rays == 0) return IA_OK;
+    IA_REQUIRE(n_rays < (1ll << 31), IA_EINVAL, "ia_render: too many rays");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int e = ia_ws_reserve(c, n_rays, c->spp, !primary_only)) return e;
+    IA_CHECK_CUDA(cudaMemsetAsync(c->d_work, 0, 8 * sizeof(int), st));
+    IA_CHECK_CUDA(cudaMemsetAsync(c->d_counters, 0, IA_N_COUNTERS * sizeof(unsigned long long), st));
+    IA_STAGE_BEGIN(c, IA_STAGE_SETUP, st);
+    k_primary_setup<<<(unsigned)((n_rays + 255) / 256), 256, 0, st>>>(c->f, d_rays, n_rays, c->d_hit_rays, c->d_hit_od, c->d_work,
+                                                                       *out, c->d_acc);
+    IA_STAGE_END(c, IA_STAGE_SETUP, st, 1);
+    IA_LAUNCH_CHECK();
+    {
+        size_t sm = IA_MLP_END * sizeof(float) + (IA_PRIMARY_THREADS / IA_TEAM) * sizeof(IaPrimarySmem);
+        IA_CHECK_CUDA(cudaFuncSetAttribute(k_primary, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        IA_STAGE_BEGIN(c, IA_STAGE_PRIMARY, st);
+        k_primary<<<c->n_sm, IA_PRIMARY_THREADS, sm, st>>>(c->f, c->d_hit_rays, c->d_hit_od, c->d_hit_info, c->d_samples,
+                                                            c->ws_samples, c->d_work, *out, c->d_counters);
+        IA_STAGE_END(c, IA_STAGE_PRIMARY, st, 1);
+        IA_LAUNCH_CHECK();
+    }
+    if (!primary_only) {
+        IA_STAGE_BEGIN(c, IA_STAGE_RESAMPLE, st);
+        k_resample<<<c->n_sm * 4, 256, 0, st>>>(c->d_hit_info, c->d_hit_od, c->d_samples, c->d_work, c->spp, c->d_u_table,
+                                                c->d_rs_t, c->d_rs_src, c->d_rs_w);
+        IA_STAGE_END(c, IA_STAGE_RESAMPLE, st, 1);
+        IA_LAUNCH_CHECK();
+        size_t occ_bytes = (size_t)c->f.occ_res * c->f.occ_res * c->f.occ_res / 8;
+        size_t sm = (gi ? IA_RAD_END : IA_GEO_END) * sizeof(float) + occ_bytes + IA_TILE_PIX * 6 * sizeof(float) +
+                    IA_TILE * sizeof(uint16_t);
+        IA_STAGE_BEGIN(c, IA_STAGE_SHADE, st);
+        if (gi) {
+            IA_CHECK_CUDA(cudaFuncSetAttribute(k_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k_shade<true><<<c->n_sm * 2, IA_SHADE_THREADS, sm, st>>>(
+                c->f, c->d_hit_rays, c->d_hit_od, c->d_samples, c->d_rs_t, c->d_rs_src, c->d_rs_w, c->d_work, c->spp,
+                ray_index_base, seed, c->d_light_dir_s, c->d_light_em, c->d_light_pdf, c->d_acc, c->d_counters);
+        } else {
+            IA_CHECK_CUDA(cudaFuncSetAttribute(k_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k_shade<false><<<c->n_sm * 2, IA_SHADE_THREADS, sm, st>>>(
+                c->f, c->d_hit_rays, c->d_hit_od, c->d_samples, c->d_rs_t, c->d_rs_src, c->d_rs_w, c->d_work, c->spp,
+                ray_index_base, seed, c->d_light_dir_s, c->d_light_em, c->d_light_pdf, c->d_acc, c->d_counters);
+        }
+        IA_STAGE_END(c, IA_STAGE_SHADE, st, 1);
+        IA_LAUNCH_CHECK();
+    }
+    IA_STAGE_BEGIN(c, IA_STAGE_COMPOSITE, st);
+    k_composite<<<(unsigned)((n_rays + 255) / 256), 256, 0, st>>>(c->f, n_rays, c->d_acc, *out, primary_only ? 1 : 0);
+    IA_STAGE_END(c, IA_STAGE_COMPOSITE, st, 1);
+    IA_LAUNCH_CHECK();
+    return IA_OK;
+}
+
+extern "C" int ia_get_counters(ia_ctx* c, uint64_t* h, void* stream) {
+    IA_REQUIRE(c && h, IA_EINVAL, "ia_get_counters: NULL argument");
+    IA_CHECK_CUDA(cudaSetDevice(c->device));
+    unsigned long long tmp[IA_N_COUNTERS];
+    int work[8];
+    IA_CHECK_CUDA(cudaMemcpyAsync(tmp, c->d_counters, sizeof(tmp), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    IA_CHECK_CUDA(cudaMemcpyAsync(work, c->d_work, sizeof(work), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    IA_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int i = 0; i < IA_N_COUNTERS; i++) h[i] = tmp[i];
+    h[IA_CNT_HIT_RAYS] = (uint64_t)work[IA_W_NHIT];
+    return IA_OK;
+}
+
+// ================================================================================================
+// remaining op-level entry points
+__global__ void k_op_resample(const int* __restrict__ packed, const float* __restrict__ starts, const float* __restrict__ ends,
+                              const float* __restrict__ weights, const float* __restrict__ sdfs, long long n_rays, int spp,
+                              const int* __restrict__ rpacked, const float* __restrict__ u_table, float* __restrict__ ts,
+                              float* __restrict__ offs, long long* __restrict__ idx, int* __restrict__ fg, int* __restrict__ bg,
+                              long long* __restrict__ surf) {
+    __shared__ float cdf_s[8][IA_CAP];
+    const int warp = threadIdx.x >> 5;
+    for (long long r = (long long)blockIdx.x * 8 + warp; r < n_rays; r += (long long)gridDim.x * 8) {
+        int base = packed[r * 2], steps = packed[r * 2 + 1];
+        if (steps == 0) continue;
+        if (steps > IA_CAP) continue;  // guarded by the host
+        int rb = rpacked[r * 2];
+        IaResampleIn in{starts + base, ends + base, weights + base, sdfs + base, 1};
+        ia_warp_resample(in, steps, spp, u_table, cdf_s[warp], 0.f, (long long)base, ts + rb, offs + rb, idx + rb, nullptr,
+                         nullptr, fg + base, bg + r, surf + r);
+        __syncwarp();
+    }
+}
+
+__global__ void k_make_u_table(float* u, int spp) {
+    if (threadIdx.x || blockIdx.x) return;
+    float step = (1.0f - 1.0 / spp) / (spp - 1);
+    float cu = 1.0 / (2 * spp);
+    for (int j = 0; j < spp; j++) { u[j] = cu; cu += step; }
+}
+
+extern "C" int ia_op_ray_resampling(ia_ctx* c, const int32_t* d_packed, const float* d_starts, const float* d_ends,
+                                    const float* d_weights, const float* d_sdfs, int64_t n_rays, int spp,
+                                    const int32_t* d_rpacked, float* d_ts, float* d_offs, int64_t* d_idx, int32_t* d_fg,
+                                    int32_t* d_bg, int64_t* d_surf, void* stream) {
+    IA_REQUIRE(c && d_packed && d_starts && d_ends && d_weights && d_sdfs && d_rpacked && d_ts && d_offs && d_idx && d_fg &&
+                   d_bg && d_surf, IA_EINVAL, "ia_op_ray_resampling: NULL argument");
+    IA_REQUIRE(spp > 1, IA_EINVAL, "ia_op_ray_resampling: n_samples must be > 1");
+    if (n_rays == 0) return IA_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* u = nullptr;
+    IA_CHECK_CUDA(cudaMallocAsync((void**)&u, spp * sizeof(float), st));
+    k_make_u_table<<<1, 1, 0, st>>>(u, spp);
+    IA_CHECK_CUDA(cudaMemsetAsync(d_surf, 0xff, n_rays * sizeof(int64_t), st));
+    k_op_resample<<<(unsigned)std::min<int64_t>((n_rays + 7) / 8, 65535), 256, 0, st>>>(
+        d_packed, d_starts, d_ends, d_weights, d_sdfs, n_rays, spp, d_rpacked, u, d_ts, d_offs, (long long*)d_idx, d_fg, d_bg,
+        (long long*)d_surf);
+    IA_LAUNCH_CHECK();
+    IA_CHECK_CUDA(cudaFreeAsync(u, st));
+    return IA_OK;
+}
+
+__global__ void k_op_merge(const int* __restrict__ packed, const float* __restrict__ vals, const uint8_t* __restrict__ il,
+                           const uint8_t* __restrict__ ir, const float* __restrict__ weights, long long n_rays,
+                           const int* __restrict__ rpacked, float* __restrict__ ovals, float* __restrict__ odists,
+                           uint8_t* __restrict__ oil, uint8_t* __restrict__ oir, uint8_t* __restrict__ oisr,
+                           uint8_t* __restrict__ oisfg) {
+    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    int base = packed[r * 2], steps = packed[r * 2 + 1];
+    if (steps == 0 || steps > IA_CAP - 16) return;
+    int rb = rpacked[r * 2];
+    uint8_t fl[IA_CAP], ofl[IA_CAP];
+    for (int i = 0; i < steps; i++) fl[i] = (il[base + i] ? 1 : 0) | (ir[base + i] ? 2 : 0);
+    int n = ia_merge_resample(vals + base, fl, weights + base, steps, rpacked[r * 2 + 1] - steps, ovals + rb, ofl, odists + rb);
+    for (int i = 0; i < n; i++) {
+        oil[rb + i] = ofl[i] & 1; oir[rb + i] = (ofl[i] >> 1) & 1; oisr[rb + i] = (ofl[i] >> 2) & 1; oisfg[rb + i] = 1;
+    }
+}
+
+extern "C" int ia_op_ray_resampling_merge(ia_ctx* c, const int32_t* d_packed, const float* d_vals, const uint8_t* d_il,
+                                          const uint8_t* d_ir, const float* d_weights, int64_t n_rays, const int32_t* d_rpacked,
+                                          float* d_ovals, float* d_odists, uint8_t* d_oil, uint8_t* d_oir, uint8_t* d_oisr,
+                                          uint8_t* d_oisfg, void* stream) {
+    IA_REQUIRE(c && d_packed && d_vals && d_il && d_ir && d_weights && d_rpacked && d_ovals && d_odists && d_oil && d_oir &&
+                   d_oisr && d_oisfg, IA_EINVAL, "ia_op_ray_resampling_merge: NULL argument");
+    if (n_rays == 0) return IA_OK;
+    k_op_merge<<<(unsigned)((n_rays + 63) / 64), 64, 0, (cudaStream_t)stream>>>(d_packed, d_vals, d_il, d_ir, d_weights, n_rays,
+                                                                               d_rpacked, d_ovals, d_odists, d_oil, d_oir, d_oisr,
+                                                                               d_oisfg);
+    IA_LAUNCH_CHECK();
+    return IA_OK;
+}
+
+// cdf_resampling_sdf_fine_kernel (cdf.cu:536-638), thread per ray (op-level twin of the lazy tracer)
+__global__ void k_op_sdf_fine(const int* __restrict__ packed, const float* __restrict__ starts_all, const float* __restrict__ ends_all,
+                              const float* __restrict__ alphas_all, const float* __restrict__ sdfs_all, long long n_rays,
+                              const int* __restrict__ rpacked, float* __restrict__ rs_all, float* __restrict__ re_all,
+                              uint8_t* __restrict__ isfg_all) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rays) return;
+    const int base = packed[i * 2], steps = packed[i * 2 + 1];
+    const int rb = rpacked[i * 2], rsteps = rpacked[i * 2 + 1];
+    if (steps == 0) return;
+    const float *starts = starts_all + base, *ends = ends_all + base, *alphas = alphas_all + base, *sdfs = sdfs_all + base;
+    float *rs = rs_all + rb, *re = re_all + rb;
+    uint8_t* isfg = isfg_all + rb;
+    int idx = 0;
+    float sdf_prev = sdfs[0];
+    bool found = false;
+    while (idx < steps) {
+        idx += 1;
+        if (idx >= steps) break;
+        if (sdf_prev >= 0 && sdfs[idx] < 0 && !found) { idx -= 1; found = true; break; }
+        sdf_prev = sdfs[idx];
+    }
+    if (!found) return;
+    int num_bins = rsteps + 1;
+    float cdf_step_size = (1.0f - 1.0 / num_bins) / rsteps;
+    int j = 0;
+    float trans = 1.0f;
+    float weight = alphas[idx];
+    trans *= (1.0f - alphas[idx]);
+    float cdf_prev = 0.0f, cdf_next = weight;
+    float cdf_u = 1.0 / (2 * num_bins);
+    while (j < num_bins && idx < steps) {
+        if (cdf_u < cdf_next) {
+            float scaling = (ends[idx] - starts[idx]) / (cdf_next - cdf_prev);
+            float t = (cdf_u - cdf_prev) * scaling + starts[idx];
+            if (j < num_bins - 1) rs[j] = t;
+            if (j > 0) { re[j - 1] = t; isfg[j - 1] = 1; }
+            cdf_u += cdf_step_size;
+            j += 1;
+        } else {
+            idx += 1;
+            if (idx >= steps) break;
+            weight = trans * alphas[idx];
+            trans *= (1.0f - alphas[idx]);
+            cdf_prev = cdf_next;
+            cdf_next += weight;
+        }
+    }
+}
+
+extern "C" int ia_op_ray_resampling_sdf_fine(ia_ctx* c, const int32_t* d_packed, const float* d_starts, const float* d_ends,
+                                             const float* d_alphas, const float* d_sdfs, int64_t n_rays, const int32_t* d_rpacked,
+                                             float* d_rs, float* d_re, uint8_t* d_isfg, void* stream) {
+    IA_REQUIRE(c && d_packed && d_starts && d_ends && d_alphas && d_sdfs && d_rpacked && d_rs && d_re && d_isfg, IA_EINVAL,
+               "ia_op_ray_resampling_sdf_fine: NULL argument");
+    if (n_rays == 0) return IA_OK;
+    k_op_sdf_fine<<<(unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_packed, d_starts, d_ends, d_alphas, d_sdfs,
+                                                                                     n_rays, d_rpacked, d_rs, d_re, d_isfg);
+    IA_LAUNCH_CHECK();
+    return IA_OK;
+}
+
+__global__ void k_op_unpack_info(const int* __restrict__ packed, long long n_rays, long long* __restrict__ ray_indices) {
+    // one warp per ray, coalesced fill (unpack_info_kernel, pack.cu:7-28)
+    long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_rays) return;
+    int base = packed[r * 2], steps = packed[r * 2 + 1];
+    for (int j = threadIdx.x & 31; j < steps; j += 32) ray_indices[base + j] = r;
+}
+
+extern "C" int ia_op_unpack_info(ia_ctx* c, const int32_t* d_packed, int64_t n_rays, int64_t* d_ray_indices, void* stream) {
+    IA_REQUIRE(c && d_packed, IA_EINVAL, "ia_op_unpack_info: NULL argument");
+    if (n_rays == 0 || !d_ray_indices) return IA_OK;  // a zero-sample output buffer has no address
+    k_op_unpack_info<<<(unsigned)((n_rays * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_packed, n_rays,
+                                                                                           (long long*)d_ray_indices);
+    IA_LAUNCH_CHECK();
+    return IA_OK;
+}
+
+template <bool GI>
+__global__ void __launch_bounds__(256, 2) k_op_secondary(const __grid_constant__ IaFrame p, const float* __restrict__ ro,
+                                                         const float* __restrict__ rd, long long n, float* __restrict__ T_out,
+                                                         float* __restrict__ rgb_out, unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) float smem[];
+    const int n_w = GI ? IA_RAD_END : IA_GEO_END;
+    ia_stage(smem, p.mlp, n_w);
+    uint32_t* occ = reinterpret_cast<uint32_t*>(smem + n_w);
+    const int occ_words = p.occ_res * p.occ_res * p.occ_res / 32;
+    for (int i = threadIdx.x; i < occ_words; i += blockDim.x) occ[i] = p.occ_bits[i];
+    __syncthreads();
+    Team team = cg::tiled_partition<IA_TEAM>(cg::this_thread_block());
+    long long teams = (long long)gridDim.x * (blockDim.x / IA_TEAM);
+    IaTraceCounters cnt = {0, 0, 0, 0, 0, 0};
+    unsigned c_rays = 0;
+    for (long long i = (long long)blockIdx.x * (blockDim.x / IA_TEAM) + threadIdx.x / IA_TEAM; i < n; i += teams) {
+        float o[3] = {ro[i * 3], ro[i * 3 + 1], ro[i * 3 + 2]}, d[3] = {rd[i * 3], rd[i * 3 + 1], rd[i * 3 + 2]};
+        float T, rgb[3];
+        ia_team_trace<GI>(team, p, smem, smem, occ, o, d, T, rgb, cnt);
+        c_rays++;
+        if (team.thread_rank() == 0) {
+            T_out[i] = T;
+            if (rgb_out) { rgb_out[i * 3] = rgb[0]; rgb_out[i * 3 + 1] = rgb[1]; rgb_out[i * 3 + 2] = rgb[2]; }
+        }
+    }
+    if (team.thread_rank() == 0) {
+        if (cnt.q) atomicAdd(&counters[IA_CNT_QUERIES], cnt.q);
+        if (cnt.qg) atomicAdd(&counters[IA_CNT_QUERIES_GRAD], cnt.qg);
+        if (cnt.geo) atomicAdd(&counters[IA_CNT_GEO_EVAL], cnt.geo);
+        if (cnt.rad) atomicAdd(&counters[IA_CNT_RAD_EVAL], cnt.rad);
+        if (c_rays) atomicAdd(&counters[IA_CNT_SECONDARY_RAYS], c_rays);
+    }
+    if (cnt.fetch) atomicAdd(&counters[IA_CNT_BROYDEN_FETCH], cnt.fetch);
+}
+
+extern "C" int ia_op_secondary(ia_ctx* c, const float* d_o, const float* d_d, int64_t n, int gi, float* d_T, float* d_rgb,
+                               void* stream) {
+    IA_REQUIRE(c && d_o && d_d && d_T, IA_EINVAL, "ia_op_secondary: NULL argument");
+    IA_REQUIRE(c->have_fields && c->have_pose && c->have_occ && c->have_cfg, IA_ESTATE, "ia_op_secondary: state not set");
+    if (n == 0) return IA_OK;
+    size_t occ_bytes = (size_t)c->f.occ_res * c->f.occ_res * c->f.occ_res / 8;
+    size_t sm = (gi ? IA_RAD_END : IA_GEO_END) * sizeof(float) + occ_bytes;
+    int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 15) / 16, (int64_t)c->n_sm * 2));
+    if (gi) {
+        IA_CHECK_CUDA(cudaFuncSetAttribute(k_op_secondary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_op_secondary<true><<<blocks, 256, sm, (cudaStream_t)stream>>>(c->f, d_o, d_d, n, d_T, d_rgb, c->d_counters);
+    } else {
+        IA_CHECK_CUDA(cudaFuncSetAttribute(k_op_secondary<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_op_secondary<false><<<blocks, 256, sm, (cudaStream_t)stream>>>(c->f, d_o, d_d, n, d_T, d_rgb, c->d_counters);
+    }
+    IA_LAUNCH_CHECK();
+    return IA_OK;
+}
+
+__global__ void k_op_brdf(const float* __restrict__ wi, const float* __restrict__ nn, const float* __restrict__ wo,
+                          const float* __restrict__ rough, const float* __restrict__ albedo, const float* __restrict__ metal,
+                          long long n, float* __restrict__ diff, float* __restrict__ spec) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a[3] = {wi[i * 3], wi[i * 3 + 1], wi[i * 3 + 2]}, b[3] = {nn[i * 3], nn[i * 3 + 1], nn[i * 3 + 2]};
+    float cc[3] = {wo[i * 3], wo[i * 3 + 1], wo[i * 3 + 2]}, al[3] = {albedo[i * 3], albedo[i * 3 + 1], albedo[i * 3 + 2]};
+    float df, sp[3];
+    ia_brdf_multilobe(a, b, cc, rough[i], al, metal[i], df, sp);
+    diff[i] = df;
+    spec[i * 3] = sp[0]; spec[i * 3 + 1] = sp[1]; spec[i * 3 + 2] = sp[2];
+}
+
+extern "C" int ia_op_brdf(ia_ctx* c, const float* d_wi, const float* d_n, const float* d_wo, const float* d_rough,
+                          const float* d_albedo, const float* d_metal, int64_t n, float* d_diff, float* d_spec, void* stream) {
+    IA_REQUIRE(c && d_wi && d_n && d_wo && d_rough && d_albedo && d_metal && d_diff && d_spec, IA_EINVAL, "ia_op_brdf: NULL");
+    if (n == 0) return IA_OK;
+    k_op_brdf<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_wi, d_n, d_wo, d_rough, d_albedo, d_metal, n, d_diff,
+                                                                           d_spec);
+    IA_LAUNCH_CHECK();
+    return IA_OK;
+}

@@ -1,0 +1,74 @@
+// Shared device-side types for the IntrinsicAvatar render path (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <stdint.h>
+
+namespace cg = cooperative_groups;
+
+#define IA_N_BONES 24
+#define IA_N_INIT 13
+#define IA_N_LEVELS 16
+#define IA_TEAM 16  // lanes that cooperate on one posed point: 13 Broyden inits / 16 hash levels
+#define IA_CAP 256  // max edges (and samples) per primary ray
+
+// Offsets (in floats) inside the packed MLP weight blob. "T" = stored input-major [in][64].
+#define IA_GEO_W1T 0                          // [35][64]
+#define IA_GEO_B1 (IA_GEO_W1T + 35 * 64)      // [64]
+#define IA_GEO_W2 (IA_GEO_B1 + 64)            // [13][64]
+#define IA_GEO_B2 (IA_GEO_W2 + 13 * 64)       // [16] (13 used)
+#define IA_GEO_END (IA_GEO_B2 + 16)
+#define IA_RAD_W1T IA_GEO_END                 // [67][64]
+#define IA_RAD_B1 (IA_RAD_W1T + 67 * 64)
+#define IA_RAD_W2T (IA_RAD_B1 + 64)           // [64][64]
+#define IA_RAD_B2 (IA_RAD_W2T + 64 * 64)
+#define IA_RAD_W3 (IA_RAD_B2 + 64)            // [3][64]
+#define IA_RAD_B3 (IA_RAD_W3 + 3 * 64)        // [4]
+#define IA_RAD_END (IA_RAD_B3 + 4)
+#define IA_MAT_W1T IA_RAD_END                 // [48][64]
+#define IA_MAT_B1 (IA_MAT_W1T + 48 * 64)
+#define IA_MAT_W2T (IA_MAT_B1 + 64)           // [64][64]
+#define IA_MAT_B2 (IA_MAT_W2T + 64 * 64)
+#define IA_MAT_W3 (IA_MAT_B2 + 64)            // [5][64]
+#define IA_MAT_B3 (IA_MAT_W3 + 5 * 64)        // [8]
+#define IA_MLP_END (IA_MAT_B3 + 8)
+
+// Per-frame constants, passed to every kernel by value (__grid_constant__).
+struct IaFrame {
+    // --- fast-SNARF
+    float tfs[IA_N_BONES][12];  // rows 0..2 of each bone transform, row-major 3x4
+    float w2s[12];              // world -> SMPL-root, row-major 3x4
+    int init_bones[IA_N_INIT];
+    float off[3], scl[3];       // reference offset_kernel / scale_kernel
+    int D, H, W;                // LBS voxel grid (32,128,128)
+    const float4* voxel_J;      // [D*H*W][3] float4  : blended 3x4 per voxel, channels-last
+    const float4* lbs_w;        // [D*H*W][6] float4  : 24 skinning weights per voxel, channels-last
+    // --- canonical fields
+    const float2* geo_hash;
+    const float2* rad_hash;
+    float lvl_scale[IA_N_LEVELS];
+    uint32_t lvl_res[IA_N_LEVELS], lvl_size[IA_N_LEVELS], lvl_off[IA_N_LEVELS];
+    float center[3], scale[3];  // canonical bbox centre / extent (geometry.py:61-68)
+    float beta;                 // Laplace density scale (already abs()+beta_min)
+    const float* mlp;           // packed weight blob (IA_* offsets)
+    float mat_scale[5], mat_bias[5];
+    float albedo_ratio[3];
+    // --- occupancy grid (test-time)
+    const uint32_t* occ_bits;   // [res^3/32], cell = (x*res + y)*res + z
+    int occ_res;
+    float aabb[6];
+    float step_primary;         // diag(scene_aabb) / num_samples_per_ray
+    float sec_near, sec_far, sec_step;
+    float background[3];
+};
+
+// One shading sample of a primary ray (written by the primary kernel, read by the PBR kernels).
+struct IaSample {
+    float ts, te, w, sdf;
+    float n[3];
+    float albedo[3];
+    float rough, metal;
+};
+static_assert(sizeof(IaSample) == 48, "IaSample layout");
+
+typedef cg::thread_block_tile<IA_TEAM> Team;

@@ -1,0 +1,322 @@
+"""Thin host wrapper over the C ABI: owns a context, keeps referenced device tensors alive, turns
+torch tensors into pointers.  All compute happens in libia_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import capi
+from .capi import IaOutputs, check, fptr, ptr
+
+_vp, _i32, _i64, _f32, _u32 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32
+
+_ARGTYPES = {
+    "ia_create": [C.POINTER(_vp), _i32],
+    "ia_destroy": [_vp],
+    "ia_set_fields": [_vp, _vp, _vp, _i64] + [_vp] * 4 + [_vp] * 18 + [_vp, _f32, _vp],
+    "ia_set_lbs_voxels": [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp],
+    "ia_set_pose": [_vp, _vp, _vp, _vp],
+    "ia_set_render_config": [_vp, _vp, _i32, _i32, _f32, _f32, _f32, _vp, _vp],
+    "ia_build_occupancy": [_vp, _vp, _i32, _vp, _vp, _vp],
+    "ia_set_occupancy": [_vp, _vp, _i32, _vp, _vp],
+    "ia_set_light": [_vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
+    "ia_render": [_vp, _vp, _i64, _i64, _i32, _u32, C.POINTER(IaOutputs), _vp],
+    "ia_get_counters": [_vp, _vp, _vp],
+    "ia_set_timing": [_vp, _i32],
+    "ia_get_timings": [_vp, _vp, _vp, _vp],
+    "ia_op_precompute": [_vp, _vp, _vp],
+    "ia_op_broyden": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
+    "ia_op_query": [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ia_op_shade_fields": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "ia_op_traverse": [_vp, _vp, _vp, _i64, _f32, _f32, _f32] + [_vp] * 9 + [_vp],
+    "ia_op_ray_resampling": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp] + [_vp] * 6 + [_vp],
+    "ia_op_ray_resampling_merge": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp] + [_vp] * 6 + [_vp],
+    "ia_op_ray_resampling_sdf_fine": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
+    "ia_op_unpack_info": [_vp, _vp, _i64, _vp, _vp],
+    "ia_op_secondary": [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp],
+    "ia_op_brdf": [_vp] * 7 + [_i64, _vp, _vp, _vp],
+}
+
+OUTPUT_SPECS = [  # name, channels, dtype
+    ("comp_rgb", 3, torch.float32), ("comp_normal", 3, torch.float32), ("opacity", 1, torch.float32),
+    ("depth", 1, torch.float32), ("comp_albedo", 3, torch.float32), ("comp_roughness", 1, torch.float32),
+    ("comp_metallic", 1, torch.float32), ("comp_rgb_phys", 3, torch.float32),
+    ("comp_demod_phys", 3, torch.float32), ("num_samples", 1, torch.int32),
+    ("comp_rgb_full", 3, torch.float32), ("comp_rgb_phys_full", 3, torch.float32),
+    ("comp_demod_phys_full", 3, torch.float32), ("comp_albedo_full", 3, torch.float32),
+    ("comp_roughness_full", 1, torch.float32), ("comp_metallic_full", 1, torch.float32),
+]
+
+
+def _lib():
+    lib = capi.load()
+    if not getattr(lib, "_ia_typed", False):
+        for name, at in _ARGTYPES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = at
+            fn.restype = C.c_int
+        lib._ia_typed = True
+    return lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+class RenderEngine:
+    """One libia_b200 context on one CUDA device."""
+
+    def __init__(self, device: int | None = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("RenderEngine needs a CUDA device (sm_100a); there is no CPU path")
+        self.lib = _lib()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.dev = torch.device("cuda", self.device)
+        h = C.c_void_p()
+        check(self.lib.ia_create(C.byref(h), self.device), "ia_create")
+        self.h = h
+        self._keep = {}
+        self.spp = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ia_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------- state ----
+    def set_fields(self, folded: dict, layout: dict, bbox):
+        geo = folded["geo_hash"].to(self.dev, torch.float32).contiguous()
+        rad = folded["rad_hash"].to(self.dev, torch.float32).contiguous()
+        self._keep["geo"], self._keep["rad"] = geo, rad
+        names = ["geo_w1", "geo_b1", "geo_w2", "geo_b2", "rad_w1", "rad_b1", "rad_w2", "rad_b2", "rad_w3", "rad_b3",
+                 "mat_w1", "mat_b1", "mat_w2", "mat_b2", "mat_w3", "mat_b3"]
+        host = [_f32(folded[n].cpu().numpy()) for n in names]
+        lv = [_f32(layout["scale"]), np.ascontiguousarray(layout["res"], np.int32),
+              np.ascontiguousarray(layout["size"], np.int32), np.ascontiguousarray(layout["offset"], np.int32)]
+        mat_scale = _f32(folded.get("mat_scale", [0.77, 0.77, 0.77, 0.9, 1.0]))
+        mat_bias = _f32(folded.get("mat_bias", [0.03, 0.03, 0.03, 0.09, 0.0]))
+        bb = _f32(bbox).reshape(6)
+        check(self.lib.ia_set_fields(self.h, ptr(geo), ptr(rad), geo.numel() // 2, *[fptr(a) for a in lv],
+                                     *[fptr(a) for a in host], fptr(mat_scale), fptr(mat_bias), fptr(bb),
+                                     float(folded["beta"]), _stream()), "ia_set_fields")
+
+    def set_lbs_voxels(self, lbs_voxel, offset_kernel, scale_kernel):
+        v = torch.as_tensor(lbs_voxel, dtype=torch.float32).to(self.dev).contiguous()
+        assert v.dim() == 4 and v.shape[0] == 24
+        check(self.lib.ia_set_lbs_voxels(self.h, ptr(v), v.shape[1], v.shape[2], v.shape[3], fptr(_f32(offset_kernel)),
+                                         fptr(_f32(scale_kernel)), _stream()), "ia_set_lbs_voxels")
+        torch.cuda.current_stream().synchronize()  # v is repacked into the context; safe to drop
+
+    def set_pose(self, tfs, w2s):
+        check(self.lib.ia_set_pose(self.h, fptr(_f32(tfs).reshape(24 * 16)), fptr(_f32(w2s).reshape(16)), _stream()),
+              "ia_set_pose")
+
+    def set_render_config(self, scene_aabb, num_samples_per_ray=128, num_samples_per_secondary_ray=64,
+                          secondary_near=0.0, secondary_far=1.5, occ_thre=0.001, background=(1, 1, 1),
+                          albedo_align_ratio=None):
+        ratio = fptr(_f32(albedo_align_ratio)) if albedo_align_ratio is not None else C.c_void_p(0)
+        check(self.lib.ia_set_render_config(self.h, fptr(_f32(scene_aabb)), num_samples_per_ray,
+                                            num_samples_per_secondary_ray, secondary_near, secondary_far, occ_thre,
+                                            fptr(_f32(background)), ratio), "ia_set_render_config")
+
+    def build_occupancy(self, aabb, jitter, res=64, return_grid=False):
+        j = torch.as_tensor(jitter, dtype=torch.float32).to(self.dev).contiguous()
+        assert j.numel() == res ** 3 * 9
+        out = torch.empty(res ** 3, dtype=torch.uint8, device=self.dev) if return_grid else None
+        check(self.lib.ia_build_occupancy(self.h, fptr(_f32(aabb).reshape(6)), res, ptr(j), ptr(out), _stream()),
+              "ia_build_occupancy")
+        self._keep["jitter"] = j
+        return out.bool().reshape(res, res, res) if return_grid else None
+
+    def set_occupancy(self, aabb, binaries):
+        b = torch.as_tensor(binaries).to(self.dev).to(torch.uint8).contiguous()
+        res = round(b.numel() ** (1 / 3))
+        check(self.lib.ia_set_occupancy(self.h, fptr(_f32(aabb).reshape(6)), res, ptr(b), _stream()), "ia_set_occupancy")
+        torch.cuda.current_stream().synchronize()
+
+    def set_light(self, envmap, u1, u2, return_tables=False):
+        env = torch.as_tensor(envmap, dtype=torch.float32).to(self.dev).contiguous()
+        u1 = torch.as_tensor(u1, dtype=torch.float32).to(self.dev).contiguous()
+        u2 = torch.as_tensor(u2, dtype=torch.float32).to(self.dev).contiguous()
+        self._keep["env"], self._keep["u1"], self._keep["u2"] = env, u1, u2
+        spp = u1.numel()
+        H, W = env.shape[:2]
+        d = e = p = None
+        if return_tables:
+            d = torch.empty(spp, 3, device=self.dev)
+            e = torch.empty(spp, 3, device=self.dev)
+            p = torch.empty(spp, device=self.dev)
+        check(self.lib.ia_set_light(self.h, ptr(env), H, W, ptr(u1), ptr(u2), spp, ptr(d), ptr(e), ptr(p), _stream()),
+              "ia_set_light")
+        self.spp = spp
+        return (d, e, p) if return_tables else None
+
+    # ------------------------------------------------------------------------ render ----
+    def alloc_outputs(self, n):
+        return {name: torch.empty(n, ch, dtype=dt, device=self.dev) for name, ch, dt in OUTPUT_SPECS}
+
+    def render(self, rays: torch.Tensor, *, primary_only=False, gi=False, seed=0, ray_index_base=0, outputs=None):
+        """rays: CUDA float32 [n,8].  Returns dict of CUDA tensors (no sync)."""
+        assert rays.is_cuda and rays.dtype == torch.float32 and rays.shape[-1] == 8
+        rays = rays.contiguous()
+        n = rays.shape[0]
+        out = outputs if outputs is not None else self.alloc_outputs(n)
+        st = IaOutputs(**{name: out[name].data_ptr() for name, _, _ in OUTPUT_SPECS})
+        flags = (capi.RENDER_PRIMARY_ONLY if primary_only else 0) | (capi.RENDER_GI if gi else 0)
+        check(self.lib.ia_render(self.h, ptr(rays), n, ray_index_base, flags, seed, C.byref(st), _stream()), "ia_render")
+        return out
+
+    def counters(self) -> dict:
+        a = np.zeros(capi.N_COUNTERS, np.uint64)
+        check(self.lib.ia_get_counters(self.h, fptr(a), _stream()), "ia_get_counters")
+        return {k: int(a[i]) for i, k in enumerate(capi.COUNTER_NAMES)}
+
+    def set_timing(self, enable=True):
+        check(self.lib.ia_set_timing(self.h, int(enable)), "ia_set_timing")
+
+    def timings(self):
+        """(dict stage -> ms of its last execution, total kernel launches); syncs the stream."""
+        ms = np.zeros(len(capi.STAGE_NAMES), np.float32)
+        n = C.c_uint64(0)
+        check(self.lib.ia_get_timings(self.h, fptr(ms), C.byref(n), _stream()), "ia_get_timings")
+        return {k: float(ms[i]) for i, k in enumerate(capi.STAGE_NAMES)}, int(n.value)
+
+    # ---------------------------------------------------------------------- op level ----
+    def op_precompute(self, D=32, H=128, W=128):
+        out = torch.empty(12, D, H, W, device=self.dev)
+        check(self.lib.ia_op_precompute(self.h, ptr(out), _stream()), "ia_op_precompute")
+        return out
+
+    def op_broyden(self, xd, with_jinv=True):
+        xd = xd.to(self.dev, torch.float32).contiguous()
+        n = xd.shape[0]
+        x = torch.zeros(n, 13, 3, device=self.dev)
+        J = torch.zeros(n, 13, 3, 3, device=self.dev) if with_jinv else None
+        vr = torch.zeros(n, 13, dtype=torch.uint8, device=self.dev)
+        v = torch.zeros(n, 13, dtype=torch.uint8, device=self.dev)
+        check(self.lib.ia_op_broyden(self.h, ptr(xd), n, ptr(x), ptr(J), ptr(vr), ptr(v), _stream()), "ia_op_broyden")
+        return x, J, vr.bool(), v.bool()
+
+    def op_query(self, xd, with_grad=False):
+        xd = xd.to(self.dev, torch.float32).contiguous()
+        n = xd.shape[0]
+        r = {"sdf": torch.empty(n, device=self.dev), "x_c": torch.empty(n, 3, device=self.dev),
+             "valid": torch.empty(n, dtype=torch.uint8, device=self.dev)}
+        g = gc = f = None
+        if with_grad:
+            g, gc, f = (torch.empty(n, 3, device=self.dev), torch.empty(n, 3, device=self.dev),
+                        torch.empty(n, 13, device=self.dev))
+            r.update(grad=g, grad_cano=gc, feature=f)
+        check(self.lib.ia_op_query(self.h, ptr(xd), n, int(with_grad), ptr(r["sdf"]), ptr(r["x_c"]), ptr(r["valid"]),
+                                   ptr(g), ptr(gc), ptr(f), _stream()), "ia_op_query")
+        r["valid"] = r["valid"].bool()
+        return r
+
+    def op_shade_fields(self, xc, feature, view_world, normal_world):
+        a = [t.to(self.dev, torch.float32).contiguous() for t in (xc, feature, view_world, normal_world)]
+        n = a[0].shape[0]
+        rgb, mat = torch.empty(n, 3, device=self.dev), torch.empty(n, 5, device=self.dev)
+        check(self.lib.ia_op_shade_fields(self.h, *[ptr(t) for t in a], n, ptr(rgb), ptr(mat), _stream()),
+              "ia_op_shade_fields")
+        return rgb, mat
+
+    def op_traverse(self, rays_o, rays_d, near, far, step):
+        o = rays_o.to(self.dev, torch.float32).contiguous()
+        d = rays_d.to(self.dev, torch.float32).contiguous()
+        n = o.shape[0]
+        ne = torch.zeros(n, dtype=torch.int32, device=self.dev)
+        ns = torch.zeros(n, dtype=torch.int32, device=self.dev)
+        z = C.c_void_p(0)
+        check(self.lib.ia_op_traverse(self.h, ptr(o), ptr(d), n, near, far, step, ptr(ne), ptr(ns), z, z, z, z, z, z, z,
+                                      _stream()), "ia_op_traverse")
+        eb = (torch.cumsum(ne, 0) - ne).int()
+        sb = (torch.cumsum(ns, 0) - ns).int()
+        E, S = int(ne.sum()), int(ns.sum())
+        vals = torch.zeros(E, device=self.dev)
+        il = torch.zeros(E, dtype=torch.uint8, device=self.dev)
+        ir = torch.zeros(E, dtype=torch.uint8, device=self.dev)
+        ts, te = torch.zeros(S, device=self.dev), torch.zeros(S, device=self.dev)
+        check(self.lib.ia_op_traverse(self.h, ptr(o), ptr(d), n, near, far, step, ptr(ne), ptr(ns), ptr(eb), ptr(sb),
+                                      ptr(vals), ptr(il), ptr(ir), ptr(ts), ptr(te), _stream()), "ia_op_traverse")
+        return {"vals": vals, "is_left": il.bool(), "is_right": ir.bool(), "packed_info": torch.stack([eb, ne], 1),
+                "t_starts": ts, "t_ends": te, "sample_packed_info": torch.stack([sb, ns], 1)}
+
+    @staticmethod
+    def _rpacked(num_steps, add):
+        rs = add.int()
+        cum = torch.cumsum(rs, 0).int()
+        return torch.stack([cum - rs, rs], 1).contiguous(), int(cum[-1]) if len(cum) else 0
+
+    def op_ray_resampling(self, packed_info, starts, ends, weights, sdfs, n_samples):
+        pi = packed_info.to(self.dev).int().contiguous()
+        a = [t.to(self.dev, torch.float32).reshape(-1).contiguous() for t in (starts, ends, weights, sdfs)]
+        n = pi.shape[0]
+        rpi, total = self._rpacked(pi[:, 1], (pi[:, 1] > 0) * n_samples)
+        ts = torch.zeros(total, 1, device=self.dev)
+        offs = torch.zeros(total, 1, device=self.dev)
+        idx = torch.zeros(total, dtype=torch.int64, device=self.dev)
+        fg = torch.zeros(a[2].numel(), dtype=torch.int32, device=self.dev)
+        bg = torch.zeros(n, dtype=torch.int32, device=self.dev)
+        surf = torch.zeros(n, dtype=torch.int64, device=self.dev)
+        check(self.lib.ia_op_ray_resampling(self.h, ptr(pi), *[ptr(t) for t in a], n, n_samples, ptr(rpi), ptr(ts),
+                                            ptr(offs), ptr(idx), ptr(fg), ptr(bg), ptr(surf), _stream()),
+              "ia_op_ray_resampling")
+        return rpi, ts, offs, idx, fg, bg, surf
+
+    def op_ray_resampling_merge(self, packed_info, vals, is_left, is_right, weights, n_samples):
+        pi = packed_info.to(self.dev).int().contiguous()
+        v = vals.to(self.dev, torch.float32).contiguous()
+        w = weights.to(self.dev, torch.float32).contiguous()
+        il = is_left.to(self.dev).to(torch.uint8).contiguous()
+        ir = is_right.to(self.dev).to(torch.uint8).contiguous()
+        n = pi.shape[0]
+        rpi, total = self._rpacked(pi[:, 1], (pi[:, 1] > 0) * n_samples + pi[:, 1])
+        rv, rd = torch.zeros(total, device=self.dev), torch.zeros(total, device=self.dev)
+        o = [torch.zeros(total, dtype=torch.uint8, device=self.dev) for _ in range(4)]
+        check(self.lib.ia_op_ray_resampling_merge(self.h, ptr(pi), ptr(v), ptr(il), ptr(ir), ptr(w), n, ptr(rpi), ptr(rv),
+                                                  ptr(rd), *[ptr(t) for t in o], _stream()), "ia_op_ray_resampling_merge")
+        return (rpi, rv, rd) + tuple(t.bool() for t in o)
+
+    def op_ray_resampling_sdf_fine(self, packed_info, starts, ends, alphas, sdfs, n_samples):
+        pi = packed_info.to(self.dev).int().contiguous()
+        a = [t.to(self.dev, torch.float32).reshape(-1).contiguous() for t in (starts, ends, alphas, sdfs)]
+        n = pi.shape[0]
+        rpi, total = self._rpacked(pi[:, 1], (pi[:, 1] > 0) * n_samples)
+        rs, re = torch.zeros(total, 1, device=self.dev), torch.zeros(total, 1, device=self.dev)
+        fg = torch.zeros(total, dtype=torch.uint8, device=self.dev)
+        check(self.lib.ia_op_ray_resampling_sdf_fine(self.h, ptr(pi), *[ptr(t) for t in a], n, ptr(rpi), ptr(rs), ptr(re),
+                                                     ptr(fg), _stream()), "ia_op_ray_resampling_sdf_fine")
+        return rpi, rs, re, fg.bool()
+
+    def op_unpack_info(self, packed_info, n_samples):
+        pi = packed_info.to(self.dev).int().contiguous()
+        out = torch.zeros(n_samples, dtype=torch.int64, device=self.dev)
+        check(self.lib.ia_op_unpack_info(self.h, ptr(pi), pi.shape[0], ptr(out), _stream()), "ia_op_unpack_info")
+        return out
+
+    def op_secondary(self, o, d, gi=False):
+        o = o.to(self.dev, torch.float32).contiguous()
+        d = d.to(self.dev, torch.float32).contiguous()
+        n = o.shape[0]
+        T, rgb = torch.empty(n, device=self.dev), torch.empty(n, 3, device=self.dev)
+        check(self.lib.ia_op_secondary(self.h, ptr(o), ptr(d), n, int(gi), ptr(T), ptr(rgb), _stream()), "ia_op_secondary")
+        return T, rgb
+
+    def op_brdf(self, wi, n, wo, rough, albedo, metal):
+        a = [t.to(self.dev, torch.float32).contiguous() for t in (wi, n, wo, rough, albedo, metal)]
+        m = a[0].shape[0]
+        diff, spec = torch.empty(m, device=self.dev), torch.empty(m, 3, device=self.dev)
+        check(self.lib.ia_op_brdf(self.h, *[ptr(t) for t in a], m, ptr(diff), ptr(spec), _stream()), "ia_op_brdf")
+        return diff, spec

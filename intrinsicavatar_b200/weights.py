@@ -58,12 +58,13 @@ def hashgrid_layout(n_levels=N_LEVELS, log2_t=LOG2_T, base=BASE_RES, per_level_s
     }
 
 
-def random_state_dict(seed: int = 0, beta: float = 0.01, geo_hash_amp: float = 0.1,
+def random_state_dict(seed: int = 0, beta: float = 0.01, geo_hash_amp: float = 0.2,
                       geo_feat_std: float = 0.05) -> dict:
     """Synthetic weights: sphere-init geometry MLP, Kaiming radiance MLP,
     default-init Lipschitz material MLP.  The geometry hash grid is U(-a_l, a_l) with
-    a_l = geo_hash_amp * 16 / res_l (bounded-gradient "fractal" detail: the SDF stays a bumpy
-    sphere with |grad| ~ 0.85 +- 0.2 instead of white noise), and the first geometry layer gets
+    a_l = geo_hash_amp * (16 / res_l)^2: detail whose gradient contribution decays with the level,
+    like a trained, eikonal-regularised SDF (a bumpy sphere with |grad| ~ 0.8 +- 0.17) instead of
+    white noise whose normals would flip on every 0.5 mm cell face, and the first geometry layer gets
     small weights on the hash features so the grid actually shapes the surface (the reference's
     sphere init leaves them at 0).  Keys follow the reference state_dict."""
     g = torch.Generator().manual_seed(seed)
@@ -71,7 +72,7 @@ def random_state_dict(seed: int = 0, beta: float = 0.01, geo_hash_amp: float = 0
     geo = torch.empty(lay["total"], N_FEAT)
     for l in range(N_LEVELS):
         o, n = int(lay["offset"][l]), int(lay["size"][l])
-        geo[o:o + n] = (torch.rand(n, N_FEAT, generator=g) * 2 - 1) * geo_hash_amp * (16.0 / float(lay["res"][l]))
+        geo[o:o + n] = (torch.rand(n, N_FEAT, generator=g) * 2 - 1) * geo_hash_amp * (16.0 / float(lay["res"][l])) ** 2
     sd = {}
     sd["geometry.encoding.encoding.encoding.params"] = geo.reshape(-1)
     sd["radiance.xyz_encoding.encoding.encoding.params"] = (

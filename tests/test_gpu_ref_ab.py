@@ -1,0 +1,181 @@
+"""A/B against the REFERENCE'S OWN compiled CUDA kernels (oracle/_ref, built from the sources under
+/root/reference by oracle/build_ref.py, shipped prebuilt to the GPU box).
+
+Two things are pinned here:
+  1. the product's ops (libia_b200) == the reference's kernels on identical inputs;
+  2. the CPU oracle's restatements (oracle/serial_ops.c, oracle/deformer.py) == the reference's kernels,
+     which is what lets the oracle stand in for the reference everywhere else.
+Skipped (not failed) if the prebuilt extensions are absent.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import build_ref
+from oracle import deformer as odef
+from oracle import ops as oops
+
+
+def _ref(name):
+    m = build_ref.load_ref(name)
+    if m is None:
+        pytest.skip(f"oracle/_ref/{name} not built (needs /root/reference at build time)")
+    return m
+
+
+@pytest.fixture(scope="module")
+def eng(scene, posed):
+    e = scene.engine()
+    fr = posed["frame"]
+    e.set_pose(fr["tfs"], fr["w2s"])
+    e.set_occupancy(fr["deformed_bbox"], posed["oracle"].binaries)
+    return e
+
+
+@pytest.fixture(scope="module")
+def ref_voxels(scene, posed):
+    """voxel_J / voxel_d from the reference's precompute kernel."""
+    pre = _ref("precompute")
+    R = posed["oracle"]
+    dev = "cuda"
+    w = R.lbs_voxel[None].to(dev).contiguous()
+    tfs = R.tfs[None].to(dev).contiguous()
+    D, H, W = R.lbs_voxel.shape[1:]
+    voxel_d = torch.zeros(1, 3, D, H, W, device=dev)
+    voxel_J = torch.zeros(1, 12, D, H, W, device=dev)
+    off = R.offset.reshape(1, 1, 3).to(dev).contiguous()
+    scl = R.scale.reshape(1, 1, 3).to(dev).contiguous()
+    pre.precompute(w, tfs, voxel_d, voxel_J, off, scl)
+    return {"voxel_d": voxel_d, "voxel_J": voxel_J, "tfs": tfs, "off": off, "scl": scl}
+
+
+def test_precompute_vs_reference(eng, posed, ref_voxels):
+    got = eng.op_precompute()
+    ref = ref_voxels["voxel_J"][0]
+    assert (got - ref).abs().max() < 1e-6
+    assert (posed["oracle"].voxel_J.cuda() - ref).abs().max() < 2e-6       # pins oracle.precompute
+
+
+def _points(posed, n, seed):
+    g = torch.Generator().manual_seed(seed)
+    bb = torch.as_tensor(posed["frame"]["deformed_bbox"])
+    c, h = (bb[:3] + bb[3:]) / 2, (bb[3:] - bb[:3]) / 2
+    a = c + (torch.rand(n // 2, 3, generator=g) * 2 - 1) * h
+    b = c + (torch.rand(n - n // 2, 3, generator=g) * 2 - 1) * h * 0.45
+    return torch.cat([a, b], 0)
+
+
+def test_broyden_filter_vs_reference(eng, posed, ref_voxels):
+    fuse, filt = _ref("fuse_cuda"), _ref("filter")
+    n = 50000
+    xd = _points(posed, n, 21).cuda()
+    x = torch.zeros(1, n, 13, 3, device="cuda")
+    J = torch.zeros(1, n, 13, 3, 3, device="cuda")
+    valid = torch.zeros(1, n, 13, dtype=torch.bool, device="cuda")
+    bones = torch.tensor(odef.INIT_BONES, dtype=torch.int32, device="cuda")
+    fuse.fuse_broyden(x, xd[None].contiguous(), ref_voxels["voxel_d"], ref_voxels["voxel_J"], ref_voxels["tfs"], bones,
+                      True, J, valid, ref_voxels["off"], ref_voxels["scl"], 1e-5, 1e-1)
+    mask = filt.filter(x, valid)
+    gx, gJ, gvraw, gv = eng.op_broyden(xd)
+    # product vs reference kernel: same fp32 arithmetic -> flags identical up to a tiny flip budget
+    assert (gvraw != valid[0]).float().mean() < 1e-4
+    assert (gv != mask[0]).float().mean() < 1e-4
+    both = gvraw & valid[0]
+    assert both.sum() > 5000
+    assert (gx[both] - x[0][both]).abs().max() < 2e-6
+    assert (gJ[both] - J[0][both]).abs().max() < 1e-3
+    assert float((gx[both] == x[0][both]).float().mean()) > 0.9             # mostly bit-identical
+    # oracle vs reference kernel
+    R = posed["oracle"]
+    ox, oJ, ovraw = odef.broyden(xd.cpu(), R.voxel_J, R.tfs, R.offset, R.scale)
+    ov = odef.filter_duplicates(ox, ovraw)
+    assert (ovraw != valid[0].cpu()).float().mean() < 2e-3
+    assert (ov != mask[0].cpu()).float().mean() < 2e-3
+    b2 = ovraw & valid[0].cpu()
+    assert (ox[b2] - x[0].cpu()[b2]).abs().max() < 5e-5
+
+
+def _fake(n_rays, seed):
+    from test_gpu_ops import _fake_ray_samples
+    return _fake_ray_samples(n_rays, seed)
+
+
+@pytest.mark.parametrize("spp", [2, 16, 256, 1024])
+def test_ray_resampling_vs_reference(eng, spp):
+    C = _ref("nerfacc_cuda")
+    packed, starts, ends, sdfs, alphas, weights = _fake(900, 100 + spp)
+    ref = C.ray_resampling(packed.cuda().int(), starts[:, None].cuda().contiguous(), ends[:, None].cuda().contiguous(),
+                           weights.cuda(), sdfs.cuda(), spp)
+    got = eng.op_ray_resampling(packed, starts, ends, weights, sdfs, spp)
+    orc = oops.ray_resampling(packed, starts[:, None], ends[:, None], weights, sdfs, spp)
+    for name, other in (("product", got), ("oracle", [t.cuda() for t in orc])):
+        assert torch.equal(other[0].int(), ref[0].int()), name
+        same = other[3] == ref[3]
+        assert same.float().mean() > 0.9995, name
+        assert (other[1][same] - ref[1][same]).abs().max() < 2e-5, name
+        assert (other[4] != ref[4]).float().mean() < 1e-3, name
+        assert (other[5] != ref[5]).float().mean() < 5e-3, name
+        assert (other[6] != ref[6]).float().mean() < 5e-3, name
+
+
+def test_ray_resampling_merge_vs_reference(eng, posed):
+    C = _ref("nerfacc_cuda")
+    R = posed["oracle"]
+    from test_gpu_ops import _rays_into_body
+    o, d = _rays_into_body(posed, 4000, seed=31)
+    tg = oops.traverse_grid(o, d, R.binaries, R.grid_aabb, 0.0, 1e10, R.render_step_size)
+    g = torch.Generator().manual_seed(1)
+    alphas = torch.rand(tg["vals"].numel(), generator=g) * 0.3 * tg["is_left"].float()
+    weights, _ = oops.render_weight_from_alpha(alphas, tg["packed_info"])
+    ref = C.ray_resampling_merge(tg["packed_info"].cuda().int(), tg["vals"].cuda(), tg["is_left"].cuda(),
+                                 tg["is_right"].cuda(), weights.cuda(), 16)
+    got = eng.op_ray_resampling_merge(tg["packed_info"], tg["vals"], tg["is_left"], tg["is_right"], weights, 16)
+    orc = [t.cuda() for t in oops.ray_resampling_merge(tg["packed_info"], tg["vals"], tg["is_left"], tg["is_right"], weights, 16)]
+    for name, other in (("product", got), ("oracle", orc)):
+        assert torch.equal(other[0].int(), ref[0].int()), name
+        for i in (3, 4, 5, 6):
+            assert (other[i] != ref[i]).float().mean() < 1e-3, (name, i)
+        same = (other[6] == ref[6]) & (other[5] == ref[5])
+        assert (other[1][same] - ref[1][same]).abs().max() < 2e-5, name
+        assert (other[2][same] - ref[2][same]).abs().max() < 2e-5, name
+
+
+def test_ray_resampling_sdf_fine_vs_reference(eng):
+    C = _ref("nerfacc_cuda")
+    packed, starts, ends, sdfs, alphas, weights = _fake(4000, 77)
+    ref = C.ray_resampling_sdf_fine(packed.cuda().int(), starts[:, None].cuda().contiguous(),
+                                    ends[:, None].cuda().contiguous(), alphas.cuda(), sdfs.cuda(), 4)
+    got = eng.op_ray_resampling_sdf_fine(packed, starts, ends, alphas, sdfs, 4)
+    orc = [t.cuda() for t in oops.ray_resampling_sdf_fine(packed, starts[:, None], ends[:, None], alphas, sdfs, 4)]
+    for name, other in (("product", got), ("oracle", orc)):
+        assert torch.equal(other[0].int(), ref[0].int()), name
+        assert (other[3] != ref[3]).float().mean() < 1e-3, name
+        same = other[3] & ref[3]
+        assert (other[1][same] - ref[1][same]).abs().max() < 2e-5, name
+        assert (other[2][same] - ref[2][same]).abs().max() < 2e-5, name
+
+
+def test_ray_resampling_fine_oracle_vs_reference():
+    C = _ref("nerfacc_cuda")
+    packed, starts, ends, sdfs, alphas, weights = _fake(2000, 5)
+    ref = C.ray_resampling_fine(packed.cuda().int(), starts[:, None].cuda().contiguous(), ends[:, None].cuda().contiguous(),
+                                weights.cuda(), 4)
+    orc = [t.cuda() for t in oops.ray_resampling_fine(packed, starts[:, None], ends[:, None], weights, 4)]
+    assert torch.equal(orc[0].int(), ref[0].int())
+    assert (orc[3] != ref[3]).float().mean() < 1e-3
+    same = orc[3] & ref[3]
+    assert (orc[1][same] - ref[1][same]).abs().max() < 2e-5
+
+
+def test_unpack_vs_reference(eng):
+    C = _ref("nerfacc_cuda")
+    packed, starts, *_ = _fake(1500, 9)
+    n = int(packed[:, 1].sum())
+    ref = C.unpack_info(packed.cuda().int(), n)
+    assert torch.equal(eng.op_unpack_info(packed, n), ref)
+    assert torch.equal(oops.unpack_info(packed, n).cuda(), ref)
+    data = torch.arange(n * 2, dtype=torch.float32).reshape(n, 2)
+    ref_d = C.unpack_data(packed.cuda().int(), data.cuda(), 64)
+    assert torch.equal(oops.unpack_data(packed, data, 64).cuda(), ref_d)
