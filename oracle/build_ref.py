@@ -47,6 +47,9 @@ def build_all(verbose: bool = False) -> None:
             raise FileNotFoundError(f"reference sources for {name} not found under {REF}")
         bd = os.path.join(OUT, name)
         os.makedirs(bd, exist_ok=True)
+        stale = os.path.join(bd, "lock")  # left behind by an interrupted build; load() would wait on it forever
+        if os.path.exists(stale):
+            os.remove(stale)
         load(name=name, sources=srcs, build_directory=bd, extra_cflags=["-O3"], extra_cuda_cflags=["-O3"],
              verbose=verbose, is_python_module=False)  # compile + link only; nothing is imported here
 
