@@ -132,12 +132,23 @@ __device__ __forceinline__ bool ia_broyden_chain(const IaFrame& p, int bone, con
 
 // ------------------------------------------------------------------------------------------------
 // tiny-cuda-nn HashGrid, one level, trilinear, optional d/dx.
+// Level parameters of one hash-grid level; kernels that evaluate many points stage the 16 of them in
+// shared memory (lane-indexed reads of the __grid_constant__ copy serialise in the constant cache).
+struct IaLevel {
+    float scale;
+    uint32_t res, size, off;
+};
+__device__ __forceinline__ IaLevel ia_level(const IaFrame& p, int l) {
+    IaLevel v = {p.lvl_scale[l], p.lvl_res[l], p.lvl_size[l], p.lvl_off[l]};
+    return v;
+}
+
 template <bool GRAD>
-__device__ __forceinline__ void ia_hash_level(const float2* __restrict__ table, const IaFrame& p, int l,
+__device__ __forceinline__ void ia_hash_level(const float2* __restrict__ table, const IaLevel lv,
                                               const float xn[3], float& f0, float& f1, float dfdx[6]) {
-    const float scale = p.lvl_scale[l];
-    const uint32_t res = p.lvl_res[l], size = p.lvl_size[l];
-    const float2* tab = table + p.lvl_off[l];
+    const float scale = lv.scale;
+    const uint32_t res = lv.res, size = lv.size;
+    const float2* tab = table + lv.off;
     // dense iff res^3 fits the level (levels 0-4 of the configured grid)
     const bool dense = (uint64_t)res * res * res <= (uint64_t)size;
     uint32_t g[3];
@@ -202,13 +213,14 @@ __device__ __forceinline__ float ia_team_sum(const Team& t, float v) {
 //   GRAD = true  : also feature[13] (= raw network output incl. channel 0) and d sdf / d x (metric)
 template <bool GRAD>
 __device__ __forceinline__ float ia_team_geometry(const Team& team, const IaFrame& p, const float* __restrict__ w,
-                                                  const float xc[3], float feat[13], float grad[3]) {
+                                                  const float xc[3], float feat[13], float grad[3],
+                                                  const IaLevel* __restrict__ lv_s = nullptr) {
     const int lane = team.thread_rank();
     float xn[3];
 #pragma unroll
     for (int d = 0; d < 3; d++) xn[d] = (xc[d] - p.center[d]) / p.scale[d] + 0.5f;
     float f0, f1, dfdx[6];
-    ia_hash_level<GRAD>(p.geo_hash, p, lane, xn, f0, f1, dfdx);
+    ia_hash_level<GRAD>(p.geo_hash, lv_s ? lv_s[lane] : ia_level(p, lane), xn, f0, f1, dfdx);
     // layer 1: pre[k] for hidden units 4*lane + k
     const float4* W1 = reinterpret_cast<const float4*>(w + IA_GEO_W1T) + lane;  // row stride 16 float4
     float4 acc = reinterpret_cast<const float4*>(w + IA_GEO_B1)[lane];
@@ -430,7 +442,7 @@ __device__ __forceinline__ void ia_team_radiance(const Team& team, const IaFrame
 #pragma unroll
     for (int d = 0; d < 3; d++) xn[d] = (xc[d] - p.center[d]) / p.scale[d] + 0.5f;
     float f0, f1;
-    ia_hash_level<false>(p.rad_hash, p, lane, xn, f0, f1, nullptr);
+    ia_hash_level<false>(p.rad_hash, ia_level(p, lane), xn, f0, f1, nullptr);
     // reflect(-view, n) (models/utils.py:115), then the (d+1)/2 -> 2x-1 round trip of the encoding
     float v[3] = {-view_w[0], -view_w[1], -view_w[2]};
     float dn = v[0] * normal_w[0] + v[1] * normal_w[1] + v[2] * normal_w[2];

@@ -22,6 +22,8 @@
 #define IA_W_PRIMARY_NEXT 2
 #define IA_W_TILE_NEXT 3
 
+#include "ia_wavefront.cuh"
+
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void ia_ray_w2s(const IaFrame& p, const float* __restrict__ ray, float o[3], float d[3],
                                            float& far) {
@@ -655,10 +657,15 @@ extern "C" int ia_render(ia_ctx* c, const float* d_rays, int64_t n_rays, int64_t
                 c->f, c->d_hit_rays, c->d_hit_od, c->d_samples, c->d_rs_t, c->d_rs_src, c->d_rs_w, c->d_work, c->spp,
                 ray_index_base, seed, c->d_light_dir_s, c->d_light_em, c->d_light_pdf, c->d_acc, c->d_counters);
         } else {
-            IA_CHECK_CUDA(cudaFuncSetAttribute(k_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            k_shade<false><<<c->n_sm * 2, IA_SHADE_THREADS, sm, st>>>(
-                c->f, c->d_hit_rays, c->d_hit_od, c->d_samples, c->d_rs_t, c->d_rs_src, c->d_rs_w, c->d_work, c->spp,
-                ray_index_base, seed, c->d_light_dir_s, c->d_light_em, c->d_light_pdf, c->d_acc, c->d_counters);
+            // wavefront integrator: one persistent 512-thread CTA per SM
+            IA_REQUIRE((long long)n_rays * c->spp < (1ll << 32), IA_EINVAL, "ia_render: n_rays * spp must be < 2^32");
+            WfShadePolicy pol;
+            pol.p = nullptr; pol.hit_rays = c->d_hit_rays; pol.hit_od = c->d_hit_od; pol.samples = c->d_samples;
+            pol.rs_t = c->d_rs_t; pol.rs_src = c->d_rs_src; pol.rs_w = c->d_rs_w; pol.work = c->d_work; pol.spp = c->spp;
+            pol.ray_index_base = ray_index_base; pol.seed = seed; pol.light_dir_s = c->d_light_dir_s;
+            pol.light_em = c->d_light_em; pol.light_pdf = c->d_light_pdf; pol.acc6 = c->d_acc; pol.n_total = 0;
+            IA_CHECK_CUDA(cudaFuncSetAttribute(k_shade_wf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WfShared)));
+            k_shade_wf<<<c->n_sm, WF_THREADS, sizeof(WfShared), st>>>(c->f, pol, c->d_counters);
         }
         IA_STAGE_END(c, IA_STAGE_SHADE, st, 1);
         IA_LAUNCH_CHECK();
@@ -890,8 +897,14 @@ extern "C" int ia_op_secondary(ia_ctx* c, const float* d_o, const float* d_d, in
         IA_CHECK_CUDA(cudaFuncSetAttribute(k_op_secondary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         k_op_secondary<true><<<blocks, 256, sm, (cudaStream_t)stream>>>(c->f, d_o, d_d, n, d_T, d_rgb, c->d_counters);
     } else {
-        IA_CHECK_CUDA(cudaFuncSetAttribute(k_op_secondary<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        k_op_secondary<false><<<blocks, 256, sm, (cudaStream_t)stream>>>(c->f, d_o, d_d, n, d_T, d_rgb, c->d_counters);
+        IA_REQUIRE(n < (1ll << 32), IA_EINVAL, "ia_op_secondary: too many rays");
+        IA_CHECK_CUDA(cudaMemsetAsync(c->d_work, 0, 8 * sizeof(int), (cudaStream_t)stream));
+        WfRaysPolicy pol;
+        pol.ro = d_o; pol.rd = d_d; pol.n = n; pol.T_out = d_T; pol.work = c->d_work;
+        if (d_rgb) IA_CHECK_CUDA(cudaMemsetAsync(d_rgb, 0, (size_t)n * 3 * sizeof(float), (cudaStream_t)stream));
+        IA_CHECK_CUDA(cudaFuncSetAttribute(k_rays_wf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WfShared)));
+        int wf_blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + WF_FEED - 1) / WF_FEED, (int64_t)c->n_sm));
+        k_rays_wf<<<wf_blocks, WF_THREADS, sizeof(WfShared), (cudaStream_t)stream>>>(c->f, pol, c->d_counters);
     }
     IA_LAUNCH_CHECK();
     return IA_OK;

@@ -1,0 +1,612 @@
+// Wavefront secondary-ray integrator (second kernel generation of the shading stage).
+//
+// Why: the first generation ran one 16-lane team per secondary ray; ncu showed 10.5 of 32 lanes active
+// per instruction (the 13 Broyden chains of a query run in lock-step until the slowest ends) and 45 %
+// instruction-fetch stalls (profiles/r1_k_shade_team_summary.md).  Here one persistent CTA per SM keeps
+// WF_R rays in flight with their state in shared memory and advances all of them one SDF query per
+// round; every round is a sequence of CTA-wide phases that are each dense and convergent:
+//
+//   feed     : a tile of shading samples -> light pick, cosine test -> ring of live secondary rays
+//   advance  : one thread per ray slot: consume the SDF of the previous query, step the lazy state
+//              machine of compute_indirect_radiance (grid march -> first +/- crossing -> CDF walk of
+//              ray_resampling_sdf_fine -> 4 fine intervals), emit the next query point; a finished ray
+//              is shaded (BRDF x light / pdf, accumulated into its pixel) and the slot re-filled
+//   broyden  : the 13 x n_q Broyden chains as independent tasks, grabbed dynamically, ONE voxel fetch
+//              per loop trip for every lane (a lane whose chain ended starts the next task in the same trip)
+//   filter   : duplicate-root removal per query -> compact list of (query, root) geometry tasks
+//   geometry : 16-lane teams evaluate hash grid + MLP for the listed roots only
+//
+// Same arithmetic, in the same order, as the per-ray formulation in ia_pbr.cuh (ia_team_trace) and so
+// as the reference (models/intrinsic_avatar.py:396-545; cdf.cu:536-638; fuse_cuda_kernel_fast.cu:250-413;
+// filter.cu:10-54); only the accumulation order into a pixel differs.
+#pragma once
+
+#define WF_THREADS 512
+#define WF_R 512       // ray slots per CTA (one per thread)
+#define WF_QCAP 2048   // ring capacity (power of two)
+#define WF_FEED 1024   // items examined per feed step
+#define WF_NST 33      // state words per ray
+
+enum { WF_IDLE = 0, WF_FIRST = 1, WF_SEARCH = 2, WF_CDF = 3, WF_FINE = 4 };
+enum { WF_ACT_NEXT = 0, WF_ACT_CDF = 1, WF_ACT_FINE_START = 2, WF_ACT_FINISH = 3 };
+
+// state word indices
+#define WS_O 0        // 0..2  origin
+#define WS_D 3        // 3..5  direction
+#define WS_ID 6       // item id (uint32)
+#define WS_PACK 7     // stage(3) | j(3) << 3 | i(3) << 6 | aux(16) << 16
+#define WS_TLAST 8
+#define WS_TMAX 9
+#define WS_TDIST 10   // 10..12
+#define WS_DELTA 13   // 13..15
+#define WS_CELL 16    // cur(3x6) | (step+1)(3x2) << 18 | continuous << 24 | done << 25
+#define WS_OVER 17    // (over+1)(3x7)
+#define WS_SDFPREV 18
+#define WS_CS 19
+#define WS_CE 20
+#define WS_TS 21
+#define WS_TE 22
+#define WS_TRANS 23   // trans (CDF) / Tacc (fine)
+#define WS_CDFPREV 24 // cdf_prev (CDF) / acc (fine)
+#define WS_CDFNEXT 25
+#define WS_CDFU 26
+#define WS_TPL 27     // 27..31
+#define WS_SPARE 32
+
+struct WfShared {
+    float w_geo[IA_GEO_END];
+    float tfs13[IA_N_INIT * 12];
+    IaLevel lvl[IA_N_LEVELS];
+    float st[WF_NST][WF_R];
+    float qx[3][WF_R];
+    float cand[WF_R * IA_N_INIT * 3];
+    unsigned int qmask[WF_R];
+    unsigned short qlist[WF_R];
+    unsigned short gtask[WF_R * IA_N_INIT];
+    uint2 ring[WF_QCAP];
+    int n_q, task_next, n_gtask, ring_head, ring_tail, tile, more_tiles, pad;
+};
+
+// ------------------------------------------------------------------------------------------------
+// marcher <-> shared state
+__device__ __forceinline__ void wf_store_marcher(WfShared& S, int t, const IaMarcher& m) {
+    S.st[WS_TLAST][t] = m.t_last;
+    S.st[WS_TMAX][t] = m.this_tmax;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { S.st[WS_TDIST + k][t] = m.tdist[k]; S.st[WS_DELTA + k][t] = m.delta[k]; }
+    unsigned a = 0, b = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        a |= ((unsigned)m.cur[k] & 63u) << (6 * k);
+        a |= ((unsigned)(m.step[k] + 1) & 3u) << (18 + 2 * k);
+        b |= ((unsigned)(m.over[k] + 1) & 127u) << (7 * k);
+    }
+    a |= (m.continuous ? 1u : 0u) << 24;
+    a |= (m.done ? 1u : 0u) << 25;
+    S.st[WS_CELL][t] = __uint_as_float(a);
+    S.st[WS_OVER][t] = __uint_as_float(b);
+}
+__device__ __forceinline__ void wf_load_marcher(const WfShared& S, int t, IaMarcher& m, float dt) {
+    m.dt = dt;
+    m.t_last = S.st[WS_TLAST][t];
+    m.this_tmax = S.st[WS_TMAX][t];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { m.tdist[k] = S.st[WS_TDIST + k][t]; m.delta[k] = S.st[WS_DELTA + k][t]; }
+    unsigned a = __float_as_uint(S.st[WS_CELL][t]), b = __float_as_uint(S.st[WS_OVER][t]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        m.cur[k] = (int)((a >> (6 * k)) & 63u);
+        m.step[k] = (int)((a >> (18 + 2 * k)) & 3u) - 1;
+        m.over[k] = (int)((b >> (7 * k)) & 127u) - 1;
+    }
+    m.continuous = (a >> 24) & 1u;
+    m.done = (a >> 25) & 1u;
+    m.cell_loaded = false;  // t_trav / occ are recomputed from (tdist, cur): same values
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int wf_grab(WfShared& S, int n_tasks) {
+    cg::coalesced_group g = cg::coalesced_threads();
+    int base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(&S.task_next, (int)g.size());
+    base = g.shfl(base, 0);
+    int t = base + (int)g.thread_rank();
+    return t < n_tasks ? t : -1;
+}
+
+// Broyden chains of all pending queries (fuse_cuda_kernel_fast.cu:250-413), one voxel fetch per trip.
+__device__ __forceinline__ void wf_broyden_phase(const IaFrame& p, WfShared& S, int n_q, unsigned& c_fetch) {
+    const int n_tasks = n_q * IA_N_INIT;
+    int task = wf_grab(S, n_tasks);
+    bool fresh = true;
+    float x0 = 0, x1 = 0, x2 = 0, xd0 = 0, xd1 = 0, xd2 = 0, g0 = 0, g1 = 0, g2 = 0;
+    float Ji[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int it = 0, q = 0, c = 0;
+    while (task >= 0) {
+        float u0 = 0, u1 = 0, u2 = 0;
+        if (fresh) {
+            c = task / n_q;                       // bone-major: neighbouring lanes = same bone, neighbouring rays
+            q = S.qlist[task - c * n_q];
+            xd0 = S.qx[0][q]; xd1 = S.qx[1][q]; xd2 = S.qx[2][q];
+            const float* T = S.tfs13 + c * 12;
+            float d0 = xd0 - T[3], d1 = xd1 - T[7], d2 = xd2 - T[11];
+            x0 = d0 * T[0] + d1 * T[4] + d2 * T[8];
+            x1 = d0 * T[1] + d1 * T[5] + d2 * T[9];
+            x2 = d0 * T[2] + d1 * T[6] + d2 * T[10];
+        } else {
+            u0 = -Ji[0] * g0 + -Ji[1] * g1 + -Ji[2] * g2;
+            u1 = -Ji[3] * g0 + -Ji[4] * g1 + -Ji[5] * g2;
+            u2 = -Ji[6] * g0 + -Ji[7] * g1 + -Ji[8] * g2;
+            x0 += u0; x1 += u1; x2 += u2;
+        }
+        const float ix = p.scl[0] * (x0 + p.off[0]);
+        const float iy = p.scl[1] * (x1 + p.off[1]);
+        const float iz = p.scl[2] * (x2 + p.off[2]);
+        float J[12];
+        ia_fetch_J(p, ix, iy, iz, J);
+        c_fetch++;
+        const float n0 = J[0] * x0 + J[1] * x1 + J[2] * x2 + J[3] - xd0;
+        const float n1 = J[4] * x0 + J[5] * x1 + J[6] * x2 + J[7] - xd1;
+        const float n2 = J[8] * x0 + J[9] * x1 + J[10] * x2 + J[11] - xd2;
+        if (fresh) {
+            Ji[0] = J[0]; Ji[3] = J[1]; Ji[6] = J[2];
+            Ji[1] = J[4]; Ji[4] = J[5]; Ji[7] = J[6];
+            Ji[2] = J[8]; Ji[5] = J[9]; Ji[8] = J[10];
+            g0 = n0; g1 = n1; g2 = n2;
+            it = 0;
+            fresh = false;
+        } else {
+            const float nrm = n0 * n0 + n1 * n1 + n2 * n2;
+            bool fin = false, ok = false;
+            if (nrm < 1e-5f * 1e-5f) {
+                ok = ix >= -1 && ix <= 1 && iy >= -1 && iy <= 1 && iz >= -1 && iz <= 1;
+                fin = true;
+            } else if (nrm > 1e-1f * 1e-1f) {
+                fin = true;
+            } else {
+                // rank-1 update of the inverse Jacobian (fuse_J_inv_update, :22-55)
+                float dg0 = n0 - g0, dg1 = n1 - g1, dg2 = n2 - g2;
+                float c0 = Ji[0] * u0 + Ji[3] * u1 + Ji[6] * u2;
+                float c1 = Ji[1] * u0 + Ji[4] * u1 + Ji[7] * u2;
+                float c2 = Ji[2] * u0 + Ji[5] * u1 + Ji[8] * u2;
+                float s = c0 * dg0 + c1 * dg1 + c2 * dg2;
+                float r0 = -Ji[0] * dg0 - Ji[1] * dg1 - Ji[2] * dg2;
+                float r1 = -Ji[3] * dg0 - Ji[4] * dg1 - Ji[5] * dg2;
+                float r2 = -Ji[6] * dg0 - Ji[7] * dg1 - Ji[8] * dg2;
+                Ji[0] += c0 * (r0 + u0) / s; Ji[1] += c1 * (r0 + u0) / s; Ji[2] += c2 * (r0 + u0) / s;
+                Ji[3] += c0 * (r1 + u1) / s; Ji[4] += c1 * (r1 + u1) / s; Ji[5] += c2 * (r1 + u1) / s;
+                Ji[6] += c0 * (r2 + u2) / s; Ji[7] += c1 * (r2 + u2) / s; Ji[8] += c2 * (r2 + u2) / s;
+                g0 = n0; g1 = n1; g2 = n2;
+                if (++it >= 10) fin = true;
+            }
+            if (fin) {
+                if (ok) {
+                    float* cd = S.cand + (q * IA_N_INIT + c) * 3;
+                    cd[0] = x0; cd[1] = x1; cd[2] = x2;
+                    atomicOr(&S.qmask[q], 1u << c);
+                }
+                task = wf_grab(S, n_tasks);
+                fresh = true;
+            }
+        }
+    }
+}
+
+// filter.cu:10-54 per pending query, then the list of geometry tasks
+__device__ __forceinline__ void wf_filter_phase(WfShared& S, int n_q) {
+    for (int k = threadIdx.x; k < n_q; k += blockDim.x) {
+        const int q = S.qlist[k];
+        const unsigned mask = S.qmask[q];
+        unsigned keep = mask;
+        const float* cd = S.cand + q * IA_N_INIT * 3;
+        unsigned mi = mask;
+        while (mi) {
+            int i = __ffs(mi) - 1;
+            mi &= mi - 1;
+            unsigned mj = mi;  // later valid candidates
+            while (mj) {
+                int j = __ffs(mj) - 1;
+                mj &= mj - 1;
+                float e0 = cd[i * 3] - cd[j * 3], e1 = cd[i * 3 + 1] - cd[j * 3 + 1], e2 = cd[i * 3 + 2] - cd[j * 3 + 2];
+                if (e0 * e0 + e1 * e1 + e2 * e2 < 0.0001f * 0.0001f) { keep &= ~(1u << i); break; }
+            }
+        }
+        S.qmask[q] = keep;
+        int n = __popc(keep);
+        if (n) {
+            int base = atomicAdd(&S.n_gtask, n);
+            unsigned m = keep;
+            while (m) {
+                int c = __ffs(m) - 1;
+                m &= m - 1;
+                S.gtask[base++] = (unsigned short)(q * 16 + c);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void wf_geometry_phase(const IaFrame& p, WfShared& S, unsigned& c_geo) {
+    Team team = cg::tiled_partition<IA_TEAM>(cg::this_thread_block());
+    const int n = S.n_gtask;
+    const int n_teams = blockDim.x / IA_TEAM;
+    for (int k = threadIdx.x / IA_TEAM; k < n; k += n_teams) {
+        const int tk = S.gtask[k];
+        float* cd = S.cand + ((tk >> 4) * IA_N_INIT + (tk & 15)) * 3;
+        const float xc[3] = {cd[0], cd[1], cd[2]};
+        float s = ia_team_geometry<false>(team, p, S.w_geo, xc, nullptr, nullptr, S.lvl);
+        team.sync();
+        if (team.thread_rank() == 0) { cd[0] = s; c_geo++; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One round of the ray state machines.  Policy P supplies rays and consumes their transmittance:
+//   bool P::init(const uint2 entry, float o[3], float d[3])   ray of a ring entry
+//   void P::finish(const uint2 entry, float T)                 shade / store
+template <class P>
+__device__ __forceinline__ void wf_advance_phase(const IaFrame& p, P& pol, WfShared& S, int ring_tail, unsigned& c_q,
+                                                 unsigned& c_rays) {
+    const int t = threadIdx.x;
+    unsigned pack = __float_as_uint(S.st[WS_PACK][t]);
+    int stage = pack & 7u, j = (pack >> 3) & 7u, i = (pack >> 6) & 7u;
+    uint2 entry = make_uint2(__float_as_uint(S.st[WS_ID][t]), pack >> 16);
+    float o[3], d[3];
+    IaMarcher m;
+    float sdf_prev = 0, cs = 0, ce = 0, ts = 0, te = 0, trans = 0, cdf_prev = 0, cdf_next = 0, cdf_u = 0;
+    int action = WF_ACT_NEXT;
+    bool pending = false;
+    float sdf_cur = 0, Tfin = 1.0f;
+    const float cdf_step_size = (1.0f - 1.0 / 5) / 4;
+    bool active = stage != WF_IDLE;
+    if (active) {
+        // ---- min SDF over the kept roots of the previous query (snarf_deformer.py:242-259)
+        unsigned keep = S.qmask[t];
+        float sdf = 1e5f;
+        while (keep) {
+            int c = __ffs(keep) - 1;
+            keep &= keep - 1;
+            float s = S.cand[(t * IA_N_INIT + c) * 3];
+            if (s < sdf) sdf = s;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) { o[k] = S.st[WS_O + k][t]; d[k] = S.st[WS_D + k][t]; }
+        wf_load_marcher(S, t, m, p.sec_step);
+        ts = S.st[WS_TS][t]; te = S.st[WS_TE][t];
+        if (stage == WF_FIRST) {
+            sdf_prev = sdf; cs = ts; ce = te;
+            stage = WF_SEARCH;
+            action = WF_ACT_NEXT;
+        } else if (stage == WF_SEARCH) {
+            sdf_prev = S.st[WS_SDFPREV][t];
+            if (sdf_prev >= 0 && sdf < 0) {
+                cs = S.st[WS_CS][t]; ce = S.st[WS_CE][t];
+                sdf_cur = sdf;
+                pending = true;  // (ts, te, sdf_cur) is the already-queried interval after the crossing one
+                j = 0;
+                float a = ia_alpha(sdf_prev, ce - cs, p.beta);
+                float weight = a;
+                trans = 1.0f;
+                trans *= (1.0f - a);
+                cdf_prev = 0.0f; cdf_next = weight;
+                cdf_u = 1.0 / (2 * 5);
+                action = WF_ACT_CDF;
+            } else {
+                sdf_prev = sdf; cs = ts; ce = te;
+                action = WF_ACT_NEXT;
+            }
+        } else if (stage == WF_CDF) {
+            trans = S.st[WS_TRANS][t]; cdf_prev = S.st[WS_CDFPREV][t]; cdf_next = S.st[WS_CDFNEXT][t];
+            cdf_u = S.st[WS_CDFU][t];
+            cs = ts; ce = te;
+            float a = ia_alpha(sdf, ce - cs, p.beta);
+            float weight = trans * a;
+            trans *= (1.0f - a);
+            cdf_prev = cdf_next;
+            cdf_next += weight;
+            action = WF_ACT_CDF;
+        } else {  // WF_FINE
+            float Tacc = S.st[WS_TRANS][t], acc = S.st[WS_CDFPREV][t];
+            float s0 = S.st[WS_TPL + i][t], e0 = S.st[WS_TPL + i + 1][t];
+            float al = ia_alpha(sdf, e0 - s0, p.beta);
+            float w = Tacc * al;
+            Tacc *= (1.0f - al);
+            acc += w;
+            i++;
+            if (i + 1 < j) {
+                float s1 = S.st[WS_TPL + i][t], e1 = S.st[WS_TPL + i + 1][t];
+                float mid = (s1 + e1) / 2.0f;
+                S.st[WS_TRANS][t] = Tacc; S.st[WS_CDFPREV][t] = acc;
+                S.st[WS_PACK][t] = __uint_as_float((unsigned)WF_FINE | (j << 3) | (i << 6) | (entry.y << 16));
+                int idx = atomicAdd(&S.n_q, 1);
+                S.qlist[idx] = (unsigned short)t;
+                S.qmask[t] = 0;
+#pragma unroll
+                for (int k = 0; k < 3; k++) S.qx[k][t] = o[k] + d[k] * mid;
+                c_q++;
+                return;
+            }
+            Tfin = 1.0f - acc;
+            action = WF_ACT_FINISH;
+        }
+    }
+    bool have_q = false;
+    float tq = 0.f;
+    for (int tries = 0;;) {
+        if (!active) {
+            if (tries >= 4) break;
+            int h = atomicAdd(&S.ring_head, 1);
+            if (h >= ring_tail) { atomicSub(&S.ring_head, 1); break; }
+            tries++;
+            entry = S.ring[h & (WF_QCAP - 1)];
+            pol.init(entry, o, d);
+            m.init(p, o, d, p.sec_near, p.sec_far, p.sec_step);
+            stage = WF_FIRST;
+            action = WF_ACT_NEXT;
+            active = true;
+            j = 0; i = 0;
+            c_rays++;
+        }
+        // ---- run the state machine until it needs an SDF or the ray is finished
+        for (;;) {
+            if (action == WF_ACT_NEXT) {
+                bool cont;
+                if (m.next(p.occ_bits, p.occ_res, ts, te, cont)) { tq = ts; have_q = true; break; }
+                if (stage == WF_CDF) { action = WF_ACT_FINE_START; continue; }
+                Tfin = 1.0f;  // no crossing: fully visible
+                action = WF_ACT_FINISH;
+                continue;
+            }
+            if (action == WF_ACT_CDF) {
+                bool need_next = false;
+                while (j < 5) {
+                    if (cdf_u < cdf_next) {
+                        float scaling = (ce - cs) / (cdf_next - cdf_prev);
+                        float tt = (cdf_u - cdf_prev) * scaling + cs;
+                        S.st[WS_TPL + j][t] = tt;
+                        cdf_u += cdf_step_size;
+                        j += 1;
+                    } else if (pending) {
+                        cs = ts; ce = te;
+                        pending = false;
+                        float a = ia_alpha(sdf_cur, ce - cs, p.beta);
+                        float weight = trans * a;
+                        trans *= (1.0f - a);
+                        cdf_prev = cdf_next;
+                        cdf_next += weight;
+                    } else {
+                        need_next = true;
+                        break;
+                    }
+                }
+                stage = WF_CDF;
+                action = need_next ? WF_ACT_NEXT : WF_ACT_FINE_START;
+                continue;
+            }
+            if (action == WF_ACT_FINE_START) {
+                i = 0;
+                if (j >= 2) {
+                    float s1 = S.st[WS_TPL][t], e1 = S.st[WS_TPL + 1][t];
+                    tq = (s1 + e1) / 2.0f;
+                    trans = 1.0f;      // Tacc
+                    cdf_prev = 0.0f;   // acc
+                    stage = WF_FINE;
+                    have_q = true;
+                    break;
+                }
+                Tfin = 1.0f;
+                action = WF_ACT_FINISH;
+                continue;
+            }
+            // WF_ACT_FINISH
+            pol.finish(entry, Tfin);
+            stage = WF_IDLE;
+            active = false;
+            break;
+        }
+        if (have_q) break;
+    }
+    if (have_q) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { S.st[WS_O + k][t] = o[k]; S.st[WS_D + k][t] = d[k]; S.qx[k][t] = o[k] + d[k] * tq; }
+        S.st[WS_ID][t] = __uint_as_float(entry.x);
+        wf_store_marcher(S, t, m);
+        S.st[WS_SDFPREV][t] = sdf_prev; S.st[WS_CS][t] = cs; S.st[WS_CE][t] = ce;
+        S.st[WS_TS][t] = ts; S.st[WS_TE][t] = te;
+        S.st[WS_TRANS][t] = trans; S.st[WS_CDFPREV][t] = cdf_prev; S.st[WS_CDFNEXT][t] = cdf_next; S.st[WS_CDFU][t] = cdf_u;
+        int idx = atomicAdd(&S.n_q, 1);
+        S.qlist[idx] = (unsigned short)t;
+        S.qmask[t] = 0;
+        c_q++;
+    }
+    S.st[WS_PACK][t] = __uint_as_float((unsigned)stage | (j << 3) | (i << 6) | (entry.y << 16));
+}
+
+// ------------------------------------------------------------------------------------------------
+template <class P>
+__device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, unsigned long long* __restrict__ counters) {
+    const int tid = threadIdx.x;
+    for (int i = tid * 4; i < IA_GEO_END; i += blockDim.x * 4)
+        *reinterpret_cast<float4*>(S.w_geo + i) = __ldg(reinterpret_cast<const float4*>(p.mlp + i));
+    if (tid < IA_N_INIT * 12) S.tfs13[tid] = p.tfs[p.init_bones[tid / 12]][tid % 12];
+    if (tid < IA_N_LEVELS) S.lvl[tid] = ia_level(p, tid);
+    S.st[WS_PACK][tid] = __uint_as_float(0u);
+    if (tid == 0) { S.ring_head = 0; S.ring_tail = 0; S.more_tiles = 1; S.n_q = 0; S.n_gtask = 0; S.task_next = 0; }
+    __syncthreads();
+    const long long n_tiles = (pol.n_items() + WF_FEED - 1) / WF_FEED;
+    unsigned c_q = 0, c_fetch = 0, c_geo = 0, c_rays = 0;
+    while (true) {
+        // ---- feed the ring while it cannot fill every slot
+        while (true) {
+            const int cnt = S.ring_tail - S.ring_head;
+            const int more = S.more_tiles;
+            if (cnt >= WF_R || !more) break;
+            __syncthreads();
+            if (tid == 0) {
+                int tl = atomicAdd(pol.tile_counter(), 1);
+                S.tile = tl;
+                if (tl >= n_tiles) S.more_tiles = 0;
+            }
+            __syncthreads();
+            const int tl = S.tile;
+            if (tl < n_tiles) pol.feed((long long)tl * WF_FEED, S);
+            __syncthreads();
+        }
+        __syncthreads();
+        if (tid == 0) { S.n_q = 0; S.n_gtask = 0; S.task_next = 0; }
+        const int ring_tail = S.ring_tail;
+        __syncthreads();
+        wf_advance_phase(p, pol, S, ring_tail, c_q, c_rays);
+        __syncthreads();
+        const int n_q = S.n_q;
+        if (n_q == 0) {
+            if (S.ring_tail - S.ring_head <= 0 && !S.more_tiles) break;
+            continue;
+        }
+        wf_broyden_phase(p, S, n_q, c_fetch);
+        __syncthreads();
+        wf_filter_phase(S, n_q);
+        __syncthreads();
+        wf_geometry_phase(p, S, c_geo);
+        __syncthreads();
+    }
+    // counters: warp-reduce then one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) {
+        c_q += __shfl_xor_sync(0xffffffffu, c_q, o);
+        c_fetch += __shfl_xor_sync(0xffffffffu, c_fetch, o);
+        c_geo += __shfl_xor_sync(0xffffffffu, c_geo, o);
+        c_rays += __shfl_xor_sync(0xffffffffu, c_rays, o);
+    }
+    if ((tid & 31) == 0) {
+        if (c_q) atomicAdd(&counters[IA_CNT_QUERIES], c_q);
+        if (c_fetch) atomicAdd(&counters[IA_CNT_BROYDEN_FETCH], c_fetch);
+        if (c_geo) atomicAdd(&counters[IA_CNT_GEO_EVAL], c_geo);
+        if (c_rays) atomicAdd(&counters[IA_CNT_SECONDARY_RAYS], c_rays);
+    }
+}
+
+__device__ __forceinline__ void wf_ring_push(WfShared& S, bool live, uint2 e) {
+    unsigned b = __ballot_sync(0xffffffffu, live);
+    int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && b) base = atomicAdd(&S.ring_tail, __popc(b));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (live) S.ring[(base + __popc(b & ((1u << lane) - 1))) & (WF_QCAP - 1)] = e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Policy 1: the shading stage (pbr_light_forward, models/intrinsic_avatar.py:755-861)
+struct WfShadePolicy {
+    const IaFrame* p;
+    const int* hit_rays; const float* hit_od; const IaSample* samples;
+    const float* rs_t; const int* rs_src; const float* rs_w;
+    int* work; int spp; long long ray_index_base; uint32_t seed;
+    const float* light_dir_s; const float* light_em; const float* light_pdf;
+    float* acc6;
+    long long n_total;
+
+    __device__ __forceinline__ long long n_items() const { return n_total; }
+    __device__ __forceinline__ int* tile_counter() const { return &work[IA_W_TILE_NEXT]; }
+
+    __device__ __forceinline__ void feed(long long s0, WfShared& S) {
+        for (int i = threadIdx.x; i < WF_FEED; i += blockDim.x) {
+            const long long s = s0 + i;
+            bool live = false;
+            uint2 e = make_uint2(0, 0);
+            if (s < n_total) {
+                const unsigned su = (unsigned)s;
+                const int slot = (int)(su / (unsigned)spp), j = (int)(su % (unsigned)spp);
+                const int src = rs_src[s];
+                if (src < 0) {
+                    // background-assigned shading sample (models/intrinsic_avatar.py:1319-1341)
+                    const float w = rs_w[s];
+                    float* pa = acc6 + (size_t)hit_rays[slot] * 6;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        atomicAdd(&pa[k], w * p->background[k]);
+                        atomicAdd(&pa[3 + k], w * p->background[k]);
+                    }
+                } else {
+                    const float* n = samples[src].n;
+                    uint32_t key = ia_pixel_key(seed, (uint64_t)(ray_index_base + hit_rays[slot]));
+                    uint32_t kk = ia_permute((uint32_t)j, (uint32_t)spp, key);
+                    const float* wo = light_dir_s + kk * 3;
+                    float cosv = n[0] * wo[0] + n[1] * wo[1] + n[2] * wo[2];
+                    live = cosv > 1e-6f;
+                    e = make_uint2(su, kk);
+                }
+            }
+            wf_ring_push(S, live, e);
+        }
+    }
+
+    __device__ __forceinline__ void init(const uint2 e, float o[3], float d[3]) const {
+        const int slot = (int)(e.x / (unsigned)spp);
+        const float t = rs_t[e.x];
+        const float* od = hit_od + (size_t)slot * 8;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            o[k] = od[k] + od[3 + k] * t;
+            d[k] = light_dir_s[e.y * 3 + k];
+        }
+    }
+
+    __device__ __forceinline__ void finish(const uint2 e, float T) const {
+        const int slot = (int)(e.x / (unsigned)spp);
+        const unsigned kk = e.y;
+        const IaSample sm = samples[rs_src[e.x]];
+        const float w = rs_w[e.x];
+        const float* od = hit_od + (size_t)slot * 8;
+        const float wi[3] = {-od[3], -od[4], -od[5]};
+        const float wo[3] = {light_dir_s[kk * 3], light_dir_s[kk * 3 + 1], light_dir_s[kk * 3 + 2]};
+        float tr = fminf(fmaxf(T, 0.f), 1.f);
+        float diff, spec[3];
+        ia_brdf_multilobe(wi, sm.n, wo, sm.rough, sm.albedo, sm.metal, diff, spec);
+        bool lit = tr > 0.0f;
+        float pdf = lit ? light_pdf[kk] : 1.0f;
+        if (!(pdf > 0)) pdf = 1.0f;
+        float* pa = acc6 + (size_t)hit_rays[slot] * 6;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            float em = lit ? light_em[kk * 3 + k] : 0.f;
+            float Li = em * tr;
+            float Ld = Li * diff / pdf, Ls = Li * spec[k] / pdf;
+            float kd = (1.0f - sm.metal) * sm.albedo[k];
+            atomicAdd(&pa[k], w * (kd * Ld + Ls));
+            atomicAdd(&pa[3 + k], w * (Ld + Ls));
+        }
+    }
+};
+
+__global__ void __launch_bounds__(WF_THREADS, 1) k_shade_wf(const __grid_constant__ IaFrame p, WfShadePolicy pol,
+                                                            unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) unsigned char wf_smem[];
+    WfShared& S = *reinterpret_cast<WfShared*>(wf_smem);
+    pol.p = &p;
+    pol.n_total = (long long)pol.work[IA_W_NHIT] * pol.spp;
+    wf_run(p, pol, S, counters);
+}
+
+// Policy 2: op-level secondary rays (ia_op_secondary, gi = 0)
+struct WfRaysPolicy {
+    const float* ro; const float* rd; long long n; float* T_out; int* work;
+    __device__ __forceinline__ long long n_items() const { return n; }
+    __device__ __forceinline__ int* tile_counter() const { return &work[IA_W_TILE_NEXT]; }
+    __device__ __forceinline__ void feed(long long s0, WfShared& S) {
+        for (int i = threadIdx.x; i < WF_FEED; i += blockDim.x) {
+            const long long s = s0 + i;
+            wf_ring_push(S, s < n, make_uint2((unsigned)s, 0));
+        }
+    }
+    __device__ __forceinline__ void init(const uint2 e, float o[3], float d[3]) const {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { o[k] = ro[(size_t)e.x * 3 + k]; d[k] = rd[(size_t)e.x * 3 + k]; }
+    }
+    __device__ __forceinline__ void finish(const uint2 e, float T) const { T_out[e.x] = T; }
+};
+
+__global__ void __launch_bounds__(WF_THREADS, 1) k_rays_wf(const __grid_constant__ IaFrame p, WfRaysPolicy pol,
+                                                           unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) unsigned char wf_smem[];
+    WfShared& S = *reinterpret_cast<WfShared*>(wf_smem);
+    wf_run(p, pol, S, counters);
+}
