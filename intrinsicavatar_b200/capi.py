@@ -10,7 +10,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libia_b200.so")
+# IA_B200_LIB selects an alternative build of the same library (tuning variants made by build(defines=...))
+LIB_PATH = os.environ.get("IA_B200_LIB") or os.path.join(_HERE, "libia_b200.so")
 SRC_DIR = os.path.join(_HERE, "csrc")
 N_COUNTERS = 16
 COUNTER_NAMES = ["hit_rays", "samples", "queries", "queries_grad", "broyden_fetch", "geo_eval", "rad_eval",
@@ -38,8 +39,16 @@ EXPORTS = [
 ]
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """nvcc -> libia_b200.so for sm_100a (cross-compiles without a GPU)."""
+def build(force: bool = False, verbose: bool = False, defines: dict | None = None, out: str | None = None) -> str:
+    """nvcc -> libia_b200.so for sm_100a (cross-compiles without a GPU).  ``defines`` / ``out`` build a
+    tuning variant next to the default library."""
+    if defines or out:
+        out = out or LIB_PATH
+        cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+               "-Xcompiler", "-fPIC", "-o", out, os.path.join(SRC_DIR, "ia_kernels.cu")]
+        cmd += [f"-D{k}={v}" for k, v in (defines or {}).items()]
+        subprocess.check_call(cmd)
+        return out
     srcs = [os.path.join(SRC_DIR, f) for f in sorted(os.listdir(SRC_DIR))]
     hdr = os.path.join(_HERE, "..", "include", "ia_b200.h")
     newest = max(os.path.getmtime(p) for p in srcs + [hdr])

@@ -39,20 +39,56 @@ __device__ __forceinline__ float ia_src_index(float coord, int size) {
     return x;
 }
 
-__device__ __forceinline__ void ia_fetch_J(const IaFrame& p, float gx, float gy, float gz, float J[12]) {
-    const int W = p.W, H = p.H, D = p.D;
-    float ix = ia_src_index(gx, W), iy = ia_src_index(gy, H), iz = ia_src_index(gz, D);
+// 256-bit read-only global load (sm_100: LDG.E.256): one 32-byte half voxel per instruction
+__device__ __forceinline__ void ia_ld256(const float4* ptr, float r[8]) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+                 : "l"(ptr));
+}
+
+// Voxel layout (IA_VOXEL_F4 float4 = 64 B, one 128-B line holds two x-neighbours):
+//   half 0 = J[0..5], 0, 0      half 1 = J[6..11], 0, 0
+// Corner set-up shared by the single-lane and the pair-cooperative fetch.
+struct IaCorners {
+    int x0, y0, z0;
+    float wx0, wx1, wy0, wy1, wz0, wz1;
+};
+__device__ __forceinline__ IaCorners ia_corners(const IaFrame& p, float gx, float gy, float gz) {
+    IaCorners c;
+    float ix = ia_src_index(gx, p.W), iy = ia_src_index(gy, p.H), iz = ia_src_index(gz, p.D);
     float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
-    int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
-    float wx1 = ix - fx, wy1 = iy - fy, wz1 = iz - fz;
-    float wx0 = (float)(x0 + 1) - ix, wy0 = (float)(y0 + 1) - iy, wz0 = (float)(z0 + 1) - iz;
-#pragma unroll
-    for (int k = 0; k < 12; k++) J[k] = 0.0f;
-    // reference corner order: tnw tne tsw tse bnw bne bsw bse (x fastest, then y, then z)
+    c.x0 = (int)fx; c.y0 = (int)fy; c.z0 = (int)fz;
+    c.wx1 = ix - fx; c.wy1 = iy - fy; c.wz1 = iz - fz;
+    c.wx0 = (float)(c.x0 + 1) - ix; c.wy0 = (float)(c.y0 + 1) - iy; c.wz0 = (float)(c.z0 + 1) - iz;
+    return c;
+}
+// acc[0..5] += w_c * half `h` of corner c, over the 8 corners in the reference order
+// (tnw tne tsw tse bnw bne bsw bse: x fastest, then y, then z), zero padding.
+__device__ __forceinline__ void ia_gather_half(const IaFrame& p, const IaCorners& cn, int h, float acc[6]) {
+    const int W = p.W, H = p.H, D = p.D;
 #pragma unroll
     for (int c = 0; c < 8; c++) {
-        int xi = x0 + (c & 1), yi = y0 + ((c >> 1) & 1), zi = z0 + (c >> 2);
-        float w = ((c & 1) ? wx1 : wx0) * ((c & 2) ? wy1 : wy0) * ((c & 4) ? wz1 : wz0);
+        int xi = cn.x0 + (c & 1), yi = cn.y0 + ((c >> 1) & 1), zi = cn.z0 + (c >> 2);
+        float w = ((c & 1) ? cn.wx1 : cn.wx0) * ((c & 2) ? cn.wy1 : cn.wy0) * ((c & 4) ? cn.wz1 : cn.wz0);
+        if (xi >= 0 && xi < W && yi >= 0 && yi < H && zi >= 0 && zi < D) {
+            float r[8];
+            ia_ld256(p.voxel_J + ((size_t)((zi * H + yi) * W + xi)) * IA_VOXEL_F4 + h * 2, r);
+#pragma unroll
+            for (int k = 0; k < 6; k++) acc[k] = fmaf(r[k], w, acc[k]);
+        }
+    }
+}
+
+__device__ __forceinline__ void ia_fetch_J(const IaFrame& p, float gx, float gy, float gz, float J[12]) {
+    const IaCorners cn = ia_corners(p, gx, gy, gz);
+#pragma unroll
+    for (int k = 0; k < 12; k++) J[k] = 0.0f;
+#if IA_FETCH_MODE == 0
+    const int W = p.W, H = p.H, D = p.D;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        int xi = cn.x0 + (c & 1), yi = cn.y0 + ((c >> 1) & 1), zi = cn.z0 + (c >> 2);
+        float w = ((c & 1) ? cn.wx1 : cn.wx0) * ((c & 2) ? cn.wy1 : cn.wy0) * ((c & 4) ? cn.wz1 : cn.wz0);
         if (xi >= 0 && xi < W && yi >= 0 && yi < H && zi >= 0 && zi < D) {
             const float4* v = p.voxel_J + ((size_t)((zi * H + yi) * W + xi)) * 3;
             float4 a = __ldg(v), b = __ldg(v + 1), cc = __ldg(v + 2);
@@ -60,6 +96,63 @@ __device__ __forceinline__ void ia_fetch_J(const IaFrame& p, float gx, float gy,
             J[4] = fmaf(b.x, w, J[4]); J[5] = fmaf(b.y, w, J[5]); J[6] = fmaf(b.z, w, J[6]); J[7] = fmaf(b.w, w, J[7]);
             J[8] = fmaf(cc.x, w, J[8]); J[9] = fmaf(cc.y, w, J[9]); J[10] = fmaf(cc.z, w, J[10]); J[11] = fmaf(cc.w, w, J[11]);
         }
+    }
+#else
+    ia_gather_half(p, cn, 0, J);
+    ia_gather_half(p, cn, 1, J + 6);
+#endif
+}
+
+#if IA_FETCH_MODE == 0
+// Row r (0..2) of the trilinear 3x4 transform: one float4 per corner.  Three neighbouring lanes that call
+// this for the same point read the 48 contiguous bytes of each corner voxel together.  All 8 loads are
+// issued before the first use (32 data registers), i.e. one memory round trip per fetch.
+__device__ __forceinline__ float4 ia_fetch_J_row(const IaFrame& p, float gx, float gy, float gz, int r) {
+    const IaCorners cn = ia_corners(p, gx, gy, gz);
+    const int W = p.W, H = p.H, D = p.D;
+    float4 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        int xi = cn.x0 + (c & 1), yi = cn.y0 + ((c >> 1) & 1), zi = cn.z0 + (c >> 2);
+        v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (xi >= 0 && xi < W && yi >= 0 && yi < H && zi >= 0 && zi < D)
+            v[c] = __ldg(p.voxel_J + ((size_t)((zi * H + yi) * W + xi)) * 3 + r);
+    }
+    float4 J = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        int xi = cn.x0 + (c & 1), yi = cn.y0 + ((c >> 1) & 1), zi = cn.z0 + (c >> 2);
+        float w = ((c & 1) ? cn.wx1 : cn.wx0) * ((c & 2) ? cn.wy1 : cn.wy0) * ((c & 4) ? cn.wz1 : cn.wz0);
+        if (xi >= 0 && xi < W && yi >= 0 && yi < H && zi >= 0 && zi < D) {  // zero padding: skipped, not added
+            J.x = fmaf(v[c].x, w, J.x); J.y = fmaf(v[c].y, w, J.y); J.z = fmaf(v[c].z, w, J.z); J.w = fmaf(v[c].w, w, J.w);
+        }
+    }
+    return J;
+}
+#endif
+
+// Pair-cooperative fetch: lanes l and l^1 each read ONE 32-byte half of every corner for both their
+// chains (two lanes share each 64-byte voxel, so a warp-wide request touches half as many lines and
+// every chain needs 8 instead of 24 load instructions per lane-chain), then swap the halves.
+// Must be called by both lanes of each pair (full-warp convergent); a lane without work passes
+// coordinates far outside the grid (no loads are issued for it).
+__device__ __forceinline__ void ia_fetch_J_pair(const IaFrame& p, float gx, float gy, float gz, float J[12]) {
+#if IA_FETCH_MODE != 2
+    ia_fetch_J(p, gx, gy, gz, J);
+    return;
+#endif
+    const int h = threadIdx.x & 1;
+    const float px = __shfl_xor_sync(0xffffffffu, gx, 1), py = __shfl_xor_sync(0xffffffffu, gy, 1),
+                pz = __shfl_xor_sync(0xffffffffu, gz, 1);
+    const IaCorners ca = ia_corners(p, gx, gy, gz), cb = ia_corners(p, px, py, pz);
+    float a[6] = {0, 0, 0, 0, 0, 0}, b[6] = {0, 0, 0, 0, 0, 0};
+    ia_gather_half(p, ca, h, a);
+    ia_gather_half(p, cb, h, b);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        float o = __shfl_xor_sync(0xffffffffu, b[k], 1);  // the partner's sum for MY chain, half h^1
+        J[k] = h ? o : a[k];
+        J[6 + k] = h ? a[k] : o;
     }
 }
 
@@ -143,6 +236,17 @@ __device__ __forceinline__ IaLevel ia_level(const IaFrame& p, int l) {
     return v;
 }
 
+// Hash-table entries of the fine (hashed) levels are touched once: keep them out of L1 so they do not
+// evict the voxel_J lines the Broyden gathers re-use.  IA_HASH_NA: 0 = allocate, 1 = hashed levels only, 2 = all
+#ifndef IA_HASH_NA
+#define IA_HASH_NA 0
+#endif
+__device__ __forceinline__ float2 ia_ldg_na(const float2* ptr) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(ptr));
+    return v;
+}
+
 template <bool GRAD>
 __device__ __forceinline__ void ia_hash_level(const float2* __restrict__ table, const IaLevel lv,
                                               const float xn[3], float& f0, float& f1, float dfdx[6]) {
@@ -151,6 +255,7 @@ __device__ __forceinline__ void ia_hash_level(const float2* __restrict__ table, 
     const float2* tab = table + lv.off;
     // dense iff res^3 fits the level (levels 0-4 of the configured grid)
     const bool dense = (uint64_t)res * res * res <= (uint64_t)size;
+    const bool pow2 = (size & (size - 1u)) == 0u;
     uint32_t g[3];
     float w[3];
 #pragma unroll
@@ -166,8 +271,16 @@ __device__ __forceinline__ void ia_hash_level(const float2* __restrict__ table, 
         uint32_t cx = g[0] + (c & 1), cy = g[1] + ((c >> 1) & 1), cz = g[2] + (c >> 2);
         uint32_t idx_d = cx + cy * res + cz * res * res;
         uint32_t idx_h = (cx * 1u) ^ (cy * 2654435761u) ^ (cz * 805459861u);
-        uint32_t idx = (dense ? idx_d : idx_h) % size;
+        uint32_t idx = dense ? idx_d : idx_h;
+        if (pow2) idx &= size - 1u;            // hashed levels: size = 2^19
+        else if (idx >= size) idx %= size;      // dense levels: only out-of-range corners wrap
+#if IA_HASH_NA == 0
         v[c] = __ldg(tab + idx);
+#elif IA_HASH_NA == 1
+        v[c] = dense ? __ldg(tab + idx) : ia_ldg_na(tab + idx);
+#else
+        v[c] = ia_ldg_na(tab + idx);
+#endif
     }
     f0 = 0.f; f1 = 0.f;
 #pragma unroll

@@ -78,6 +78,7 @@ struct ia_ctx {
     float* d_acc = nullptr;          // [n_rays][6] rgb_phys, demod_phys accumulators
     unsigned long long* d_counters = nullptr;  // IA_N_COUNTERS
     int* d_work = nullptr;           // [8] work-stealing counters / n_hit / n_samples
+    unsigned char* d_wf_scratch = nullptr;  // wavefront integrator: per-CTA candidate / task scratch
     // stage timing (CUDA events on the launching stream) and launch accounting
     bool timing = false;
     cudaEvent_t ev0[IA_N_STAGES] = {}, ev1[IA_N_STAGES] = {};
@@ -158,7 +159,7 @@ extern "C" int ia_destroy(ia_ctx* c) {
                     c->d_light_em, c->d_light_pdf, c->d_u_table, c->d_env_pdf, c->d_env_cols, c->d_env_rows,
                     c->d_env_rowsum, c->d_env_total, c->d_hit_rays, c->d_hit_od, c->d_hit_info, c->d_samples,
                     c->d_rs_t, c->d_rs_w, c->d_rs_src, c->d_acc, c->d_counters, c->d_work, c->d_occ_a, c->d_occ_b,
-                    c->d_occ_hist, c->d_occ_sum};
+                    c->d_occ_hist, c->d_occ_sum, c->d_wf_scratch};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete c;
@@ -226,7 +227,7 @@ extern "C" int ia_set_lbs_voxels(ia_ctx* c, const float* d_lbs_voxel, int D, int
     IA_REQUIRE(c && d_lbs_voxel && off && scl, IA_EINVAL, "ia_set_lbs_voxels: NULL argument");
     IA_CHECK_CUDA(cudaSetDevice(c->device));
     size_t nvox = (size_t)D * H * W;
-    if (ia_realloc(&c->d_lbs_w, nvox * 6) || ia_realloc(&c->d_voxel_J, nvox * 3)) return IA_ECUDA;
+    if (ia_realloc(&c->d_lbs_w, nvox * 6) || ia_realloc(&c->d_voxel_J, nvox * IA_VOXEL_F4)) return IA_ECUDA;
     k_repack_lbs<<<(unsigned)((nvox + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_lbs_voxel, (float*)c->d_lbs_w,
                                                                                  (int)nvox);
     IA_LAUNCH_CHECK();
@@ -257,9 +258,17 @@ __global__ void k_precompute(const __grid_constant__ IaFrame p, float4* __restri
         for (int j = 0; j < IA_N_BONES; j++) s += w[j] * p.tfs[j][k];
         J[k] = s;
     }
-    voxel_J[(size_t)v * 3 + 0] = make_float4(J[0], J[1], J[2], J[3]);
-    voxel_J[(size_t)v * 3 + 1] = make_float4(J[4], J[5], J[6], J[7]);
-    voxel_J[(size_t)v * 3 + 2] = make_float4(J[8], J[9], J[10], J[11]);
+    float4* o = voxel_J + (size_t)v * IA_VOXEL_F4;
+#if IA_FETCH_MODE == 0
+    o[0] = make_float4(J[0], J[1], J[2], J[3]);
+    o[1] = make_float4(J[4], J[5], J[6], J[7]);
+    o[2] = make_float4(J[8], J[9], J[10], J[11]);
+#else
+    o[0] = make_float4(J[0], J[1], J[2], J[3]);
+    o[1] = make_float4(J[4], J[5], 0.f, 0.f);
+    o[2] = make_float4(J[6], J[7], J[8], J[9]);
+    o[3] = make_float4(J[10], J[11], 0.f, 0.f);
+#endif
 }
 
 extern "C" int ia_set_pose(ia_ctx* c, const float* tfs, const float* w2s, void* stream) {
@@ -301,9 +310,9 @@ extern "C" int ia_set_render_config(ia_ctx* c, const float* aabb, int n_per_ray,
 __global__ void k_op_precompute_out(const float4* __restrict__ vj, float* __restrict__ out, int nvox) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nvox) return;
-    const float* s = reinterpret_cast<const float*>(vj + (size_t)v * 3);
+    const float* s = reinterpret_cast<const float*>(vj + (size_t)v * IA_VOXEL_F4);
 #pragma unroll
-    for (int k = 0; k < 12; k++) out[(size_t)k * nvox + v] = s[k];
+    for (int k = 0; k < 12; k++) out[(size_t)k * nvox + v] = s[IA_VOXEL_F4 == 3 ? k : (k < 6 ? k : k + 2)];
 }
 
 extern "C" int ia_op_precompute(ia_ctx* c, float* d_out, void* stream) {

@@ -585,6 +585,11 @@ __global__ void k_composite(const __grid_constant__ IaFrame p, long long n, cons
 }
 
 // ================================================================================================
+static int ia_wf_scratch(ia_ctx* c) {
+    if (!c->d_wf_scratch) return ia_realloc(&c->d_wf_scratch, (size_t)c->n_sm * WF_SCRATCH_BYTES);
+    return IA_OK;
+}
+
 static int ia_ws_reserve(ia_ctx* c, int64_t n_rays, int spp, bool need_pbr) {
     if (n_rays > c->ws_rays) {
         if (ia_realloc(&c->d_hit_rays, (size_t)n_rays) || ia_realloc(&c->d_hit_od, (size_t)n_rays * 8) ||
@@ -665,7 +670,8 @@ extern "C" int ia_render(ia_ctx* c, const float* d_rays, int64_t n_rays, int64_t
             pol.ray_index_base = ray_index_base; pol.seed = seed; pol.light_dir_s = c->d_light_dir_s;
             pol.light_em = c->d_light_em; pol.light_pdf = c->d_light_pdf; pol.acc6 = c->d_acc; pol.n_total = 0;
             IA_CHECK_CUDA(cudaFuncSetAttribute(k_shade_wf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WfShared)));
-            k_shade_wf<<<c->n_sm, WF_THREADS, sizeof(WfShared), st>>>(c->f, pol, c->d_counters);
+            if (int e = ia_wf_scratch(c)) return e;
+            k_shade_wf<<<c->n_sm, WF_THREADS, sizeof(WfShared), st>>>(c->f, pol, c->d_wf_scratch, c->d_counters);
         }
         IA_STAGE_END(c, IA_STAGE_SHADE, st, 1);
         IA_LAUNCH_CHECK();
@@ -904,7 +910,8 @@ extern "C" int ia_op_secondary(ia_ctx* c, const float* d_o, const float* d_d, in
         if (d_rgb) IA_CHECK_CUDA(cudaMemsetAsync(d_rgb, 0, (size_t)n * 3 * sizeof(float), (cudaStream_t)stream));
         IA_CHECK_CUDA(cudaFuncSetAttribute(k_rays_wf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WfShared)));
         int wf_blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + WF_FEED - 1) / WF_FEED, (int64_t)c->n_sm));
-        k_rays_wf<<<wf_blocks, WF_THREADS, sizeof(WfShared), (cudaStream_t)stream>>>(c->f, pol, c->d_counters);
+        if (int e = ia_wf_scratch(c)) return e;
+        k_rays_wf<<<wf_blocks, WF_THREADS, sizeof(WfShared), (cudaStream_t)stream>>>(c->f, pol, c->d_wf_scratch, c->d_counters);
     }
     IA_LAUNCH_CHECK();
     return IA_OK;

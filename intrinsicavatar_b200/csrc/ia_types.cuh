@@ -11,6 +11,18 @@ namespace cg = cooperative_groups;
 #define IA_N_LEVELS 16
 #define IA_TEAM 16  // lanes that cooperate on one posed point: 13 Broyden inits / 16 hash levels
 #define IA_CAP 256  // max edges (and samples) per primary ray
+// voxel_J fetch variants (tuning knob, default = measured best; see DESIGN.md "Broyden fetch"):
+//   0: 48-byte voxels, 3 x LDG.128 per corner, one lane per chain
+//   1: 64-byte padded voxels, 2 x LDG.256 per corner, one lane per chain
+//   2: 64-byte padded voxels, lane pairs fetch one 32-byte half each for both their chains
+#ifndef IA_FETCH_MODE
+#define IA_FETCH_MODE 0
+#endif
+#if IA_FETCH_MODE == 0
+#define IA_VOXEL_F4 3  // float4 per voxel of voxel_J
+#else
+#define IA_VOXEL_F4 4  // 12 floats padded to 64 bytes: half 0 = J[0..5],0,0 ; half 1 = J[6..11],0,0
+#endif
 
 // Offsets (in floats) inside the packed MLP weight blob. "T" = stored input-major [in][64].
 #define IA_GEO_W1T 0                          // [35][64]
@@ -41,7 +53,7 @@ struct IaFrame {
     int init_bones[IA_N_INIT];
     float off[3], scl[3];       // reference offset_kernel / scale_kernel
     int D, H, W;                // LBS voxel grid (32,128,128)
-    const float4* voxel_J;      // [D*H*W][3] float4  : blended 3x4 per voxel, channels-last
+    const float4* voxel_J;      // [D*H*W][4] float4  : blended 3x4 per voxel, channels-last, two 32-B halves
     const float4* lbs_w;        // [D*H*W][6] float4  : 24 skinning weights per voxel, channels-last
     // --- canonical fields
     const float2* geo_hash;

@@ -21,11 +21,22 @@
 // filter.cu:10-54); only the accumulation order into a pixel differs.
 #pragma once
 
+#ifndef WF_THREADS
 #define WF_THREADS 512
-#define WF_R 512       // ray slots per CTA (one per thread)
+#endif
+#ifndef WF_BROYDEN_LANES
+#define WF_BROYDEN_LANES 1   // lanes per Broyden chain: 1 (one thread per chain) or 3 (row-distributed)
+#endif
+#ifndef WF_R
+#define WF_R 512       // ray slots per CTA
+#endif
 #define WF_QCAP 2048   // ring capacity (power of two)
 #define WF_FEED 1024   // items examined per feed step
 #define WF_NST 33      // state words per ray
+#ifndef WF_STATE_GLOBAL
+#define WF_STATE_GLOBAL 1
+#endif
+#define WF_SCRATCH_BYTES (WF_R * IA_N_INIT * 3 * 4 + WF_R * IA_N_INIT * 2 + WF_NST * WF_R * 4)  // per CTA
 
 enum { WF_IDLE = 0, WF_FIRST = 1, WF_SEARCH = 2, WF_CDF = 3, WF_FINE = 4 };
 enum { WF_ACT_NEXT = 0, WF_ACT_CDF = 1, WF_ACT_FINE_START = 2, WF_ACT_FINISH = 3 };
@@ -57,13 +68,19 @@ struct WfShared {
     float w_geo[IA_GEO_END];
     float tfs13[IA_N_INIT * 12];
     IaLevel lvl[IA_N_LEVELS];
+#if WF_STATE_GLOBAL
+    float (*st)[WF_R];      // [WF_NST][WF_R] ray state, in the CTA's global scratch (read/written once per round)
+#else
     float st[WF_NST][WF_R];
+#endif
     float qx[3][WF_R];
-    float cand[WF_R * IA_N_INIT * 3];
     unsigned int qmask[WF_R];
     unsigned short qlist[WF_R];
-    unsigned short gtask[WF_R * IA_N_INIT];
     uint2 ring[WF_QCAP];
+    // CTA-private scratch in GLOBAL memory (low traffic; keeping it out of shared memory leaves the
+    // L1 carve-out to the voxel_J gathers, which is what the kernel is bound by -- DESIGN.md):
+    float* cand;            // [WF_R][13][3] Broyden roots; [.][.][0] is overwritten with the SDF
+    unsigned short* gtask;  // [WF_R * 13] geometry task list
     int n_q, task_next, n_gtask, ring_head, ring_tail, tile, more_tiles, pad;
 };
 
@@ -115,7 +132,7 @@ __device__ __forceinline__ int wf_grab(WfShared& S, int n_tasks) {
 }
 
 // Broyden chains of all pending queries (fuse_cuda_kernel_fast.cu:250-413), one voxel fetch per trip.
-__device__ __forceinline__ void wf_broyden_phase(const IaFrame& p, WfShared& S, int n_q, unsigned& c_fetch) {
+__device__ __forceinline__ void wf_broyden_phase_1lane(const IaFrame& p, WfShared& S, int n_q, unsigned& c_fetch) {
     const int n_tasks = n_q * IA_N_INIT;
     int task = wf_grab(S, n_tasks);
     bool fresh = true;
@@ -192,6 +209,116 @@ __device__ __forceinline__ void wf_broyden_phase(const IaFrame& p, WfShared& S, 
     }
 }
 
+// Broyden chains of all pending queries (fuse_cuda_kernel_fast.cu:250-413).
+// One chain per group of THREE lanes: lane r owns row r of the fetched 3x4 transform (8 x LDG.128, all
+// in flight together) and column r of the inverse Jacobian; a warp runs 10 chains, lanes 30/31 idle.
+// Values every lane of the group needs (residual n, the Ji columns, c = Ji^T u) are exchanged with
+// shuffles; each scalar is computed by exactly the expression of the one-thread reference kernel.
+// The trip loop is warp-uniform; finished groups are re-filled from the task counter at the trip end.
+__device__ __forceinline__ void wf_broyden_phase(const IaFrame& p, WfShared& S, int n_q, unsigned& c_fetch) {
+    const unsigned FULL = 0xffffffffu;
+    const int n_tasks = n_q * IA_N_INIT;
+    const int lane = threadIdx.x & 31;
+    const bool lane_ok = lane < 30;
+    const int grp = lane / 3, r = lane - grp * 3;
+    const int s0 = lane_ok ? grp * 3 : lane, s1 = lane_ok ? s0 + 1 : lane, s2 = lane_ok ? s0 + 2 : lane;
+    const bool leader = lane_ok && r == 0;
+    auto refill = [&](bool need) -> int {
+        unsigned b = __ballot_sync(FULL, need && leader);
+        int t = -1;
+        if (b) {
+            const int first = __ffs(b) - 1;
+            int cnt = 0;
+            if (lane == first) cnt = atomicAdd(&S.task_next, __popc(b));
+            cnt = __shfl_sync(FULL, cnt, first);
+            if (need && leader) {
+                t = cnt + __popc(b & ((1u << lane) - 1u));
+                if (t >= n_tasks) t = -1;
+            }
+        }
+        return __shfl_sync(FULL, t, s0);
+    };
+    int task = refill(true);
+    bool fresh = true;
+    float x0 = 0, x1 = 0, x2 = 0, xd0 = 0, xd1 = 0, xd2 = 0, g0 = 0, g1 = 0, g2 = 0, u0 = 0, u1 = 0, u2 = 0;
+    float jc0 = 0, jc1 = 0, jc2 = 0;  // column r of Ji: Ji[0][r], Ji[1][r], Ji[2][r]
+    int it = 0, q = 0, c = 0;
+    while (__any_sync(FULL, task >= 0)) {
+        const bool act = task >= 0;
+        // full Ji on every lane of the group (Jab = Ji[a][b], column b lives on lane b)
+        const float J00 = __shfl_sync(FULL, jc0, s0), J10 = __shfl_sync(FULL, jc1, s0), J20 = __shfl_sync(FULL, jc2, s0);
+        const float J01 = __shfl_sync(FULL, jc0, s1), J11 = __shfl_sync(FULL, jc1, s1), J21 = __shfl_sync(FULL, jc2, s1);
+        const float J02 = __shfl_sync(FULL, jc0, s2), J12 = __shfl_sync(FULL, jc1, s2), J22 = __shfl_sync(FULL, jc2, s2);
+        float ix = -100.f, iy = -100.f, iz = -100.f;  // idle group: far outside the grid, no loads
+        if (act) {
+            if (fresh) {
+                c = task / n_q;                       // bone-major: neighbouring groups = same bone, neighbouring rays
+                q = S.qlist[task - c * n_q];
+                xd0 = S.qx[0][q]; xd1 = S.qx[1][q]; xd2 = S.qx[2][q];
+                const float* T = S.tfs13 + c * 12;
+                float d0 = xd0 - T[3], d1 = xd1 - T[7], d2 = xd2 - T[11];
+                x0 = d0 * T[0] + d1 * T[4] + d2 * T[8];
+                x1 = d0 * T[1] + d1 * T[5] + d2 * T[9];
+                x2 = d0 * T[2] + d1 * T[6] + d2 * T[10];
+                u0 = u1 = u2 = 0.f;
+            } else {
+                u0 = -J00 * g0 + -J01 * g1 + -J02 * g2;
+                u1 = -J10 * g0 + -J11 * g1 + -J12 * g2;
+                u2 = -J20 * g0 + -J21 * g1 + -J22 * g2;
+                x0 += u0; x1 += u1; x2 += u2;
+            }
+            ix = p.scl[0] * (x0 + p.off[0]);
+            iy = p.scl[1] * (x1 + p.off[1]);
+            iz = p.scl[2] * (x2 + p.off[2]);
+        }
+        const float4 Jr = ia_fetch_J_row(p, ix, iy, iz, r);
+        const float xdr = r == 0 ? xd0 : (r == 1 ? xd1 : xd2);
+        const float nr = Jr.x * x0 + Jr.y * x1 + Jr.z * x2 + Jr.w - xdr;
+        const float n0 = __shfl_sync(FULL, nr, s0), n1 = __shfl_sync(FULL, nr, s1), n2 = __shfl_sync(FULL, nr, s2);
+        // c = Ji^T u: component r from this lane's column, then shared
+        const float cr = jc0 * u0 + jc1 * u1 + jc2 * u2;
+        const float c0 = __shfl_sync(FULL, cr, s0), c1 = __shfl_sync(FULL, cr, s1), c2 = __shfl_sync(FULL, cr, s2);
+        bool fin = false;
+        if (act) {
+            if (leader) c_fetch++;
+            if (fresh) {
+                jc0 = Jr.x; jc1 = Jr.y; jc2 = Jr.z;   // Ji = (3x3 part of J)^T: column r of Ji = row r of J
+                g0 = n0; g1 = n1; g2 = n2;
+                it = 0;
+                fresh = false;
+            } else {
+                const float nrm = n0 * n0 + n1 * n1 + n2 * n2;
+                bool ok = false;
+                if (nrm < 1e-5f * 1e-5f) {
+                    ok = ix >= -1 && ix <= 1 && iy >= -1 && iy <= 1 && iz >= -1 && iz <= 1;
+                    fin = true;
+                } else if (nrm > 1e-1f * 1e-1f) {
+                    fin = true;
+                } else {
+                    // rank-1 update of the inverse Jacobian (fuse_J_inv_update, :22-55), this lane's column
+                    float dg0 = n0 - g0, dg1 = n1 - g1, dg2 = n2 - g2;
+                    float s = c0 * dg0 + c1 * dg1 + c2 * dg2;
+                    float r0 = -J00 * dg0 - J01 * dg1 - J02 * dg2;
+                    float r1 = -J10 * dg0 - J11 * dg1 - J12 * dg2;
+                    float r2 = -J20 * dg0 - J21 * dg1 - J22 * dg2;
+                    jc0 += cr * (r0 + u0) / s;
+                    jc1 += cr * (r1 + u1) / s;
+                    jc2 += cr * (r2 + u2) / s;
+                    g0 = n0; g1 = n1; g2 = n2;
+                    if (++it >= 10) fin = true;
+                }
+                if (fin && ok && leader) {
+                    float* cd = S.cand + (q * IA_N_INIT + c) * 3;
+                    cd[0] = x0; cd[1] = x1; cd[2] = x2;
+                    atomicOr(&S.qmask[q], 1u << c);
+                }
+            }
+        }
+        const int nt = refill(fin);
+        if (fin) { task = nt; fresh = true; }
+    }
+}
+
 // filter.cu:10-54 per pending query, then the list of geometry tasks
 __device__ __forceinline__ void wf_filter_phase(WfShared& S, int n_q) {
     for (int k = threadIdx.x; k < n_q; k += blockDim.x) {
@@ -244,9 +371,8 @@ __device__ __forceinline__ void wf_geometry_phase(const IaFrame& p, WfShared& S,
 //   bool P::init(const uint2 entry, float o[3], float d[3])   ray of a ring entry
 //   void P::finish(const uint2 entry, float T)                 shade / store
 template <class P>
-__device__ __forceinline__ void wf_advance_phase(const IaFrame& p, P& pol, WfShared& S, int ring_tail, unsigned& c_q,
-                                                 unsigned& c_rays) {
-    const int t = threadIdx.x;
+__device__ __forceinline__ void wf_advance_slot(const IaFrame& p, P& pol, WfShared& S, const int t, int ring_tail,
+                                                unsigned& c_q, unsigned& c_rays) {
     unsigned pack = __float_as_uint(S.st[WS_PACK][t]);
     int stage = pack & 7u, j = (pack >> 3) & 7u, i = (pack >> 6) & 7u;
     uint2 entry = make_uint2(__float_as_uint(S.st[WS_ID][t]), pack >> 16);
@@ -423,13 +549,23 @@ __device__ __forceinline__ void wf_advance_phase(const IaFrame& p, P& pol, WfSha
 
 // ------------------------------------------------------------------------------------------------
 template <class P>
-__device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, unsigned long long* __restrict__ counters) {
+__device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, unsigned char* __restrict__ scratch,
+                                       unsigned long long* __restrict__ counters) {
     const int tid = threadIdx.x;
+    if (tid == 0) {
+        unsigned char* mine = scratch + (size_t)blockIdx.x * WF_SCRATCH_BYTES;
+        S.cand = reinterpret_cast<float*>(mine);
+        S.gtask = reinterpret_cast<unsigned short*>(mine + WF_R * IA_N_INIT * 3 * 4);
+#if WF_STATE_GLOBAL
+        S.st = reinterpret_cast<float (*)[WF_R]>(mine + WF_R * IA_N_INIT * 3 * 4 + WF_R * IA_N_INIT * 2);
+#endif
+    }
+    __syncthreads();
     for (int i = tid * 4; i < IA_GEO_END; i += blockDim.x * 4)
         *reinterpret_cast<float4*>(S.w_geo + i) = __ldg(reinterpret_cast<const float4*>(p.mlp + i));
     if (tid < IA_N_INIT * 12) S.tfs13[tid] = p.tfs[p.init_bones[tid / 12]][tid % 12];
     if (tid < IA_N_LEVELS) S.lvl[tid] = ia_level(p, tid);
-    S.st[WS_PACK][tid] = __uint_as_float(0u);
+    for (int t = tid; t < WF_R; t += blockDim.x) S.st[WS_PACK][t] = __uint_as_float(0u);
     if (tid == 0) { S.ring_head = 0; S.ring_tail = 0; S.more_tiles = 1; S.n_q = 0; S.n_gtask = 0; S.task_next = 0; }
     __syncthreads();
     const long long n_tiles = (pol.n_items() + WF_FEED - 1) / WF_FEED;
@@ -455,14 +591,18 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
         if (tid == 0) { S.n_q = 0; S.n_gtask = 0; S.task_next = 0; }
         const int ring_tail = S.ring_tail;
         __syncthreads();
-        wf_advance_phase(p, pol, S, ring_tail, c_q, c_rays);
+        for (int t = tid; t < WF_R; t += blockDim.x) wf_advance_slot(p, pol, S, t, ring_tail, c_q, c_rays);
         __syncthreads();
         const int n_q = S.n_q;
         if (n_q == 0) {
             if (S.ring_tail - S.ring_head <= 0 && !S.more_tiles) break;
             continue;
         }
+#if WF_BROYDEN_LANES == 1
+        wf_broyden_phase_1lane(p, S, n_q, c_fetch);
+#else
         wf_broyden_phase(p, S, n_q, c_fetch);
+#endif
         __syncthreads();
         wf_filter_phase(S, n_q);
         __syncthreads();
@@ -578,12 +718,13 @@ struct WfShadePolicy {
 };
 
 __global__ void __launch_bounds__(WF_THREADS, 1) k_shade_wf(const __grid_constant__ IaFrame p, WfShadePolicy pol,
+                                                            unsigned char* __restrict__ scratch,
                                                             unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char wf_smem[];
     WfShared& S = *reinterpret_cast<WfShared*>(wf_smem);
     pol.p = &p;
     pol.n_total = (long long)pol.work[IA_W_NHIT] * pol.spp;
-    wf_run(p, pol, S, counters);
+    wf_run(p, pol, S, scratch, counters);
 }
 
 // Policy 2: op-level secondary rays (ia_op_secondary, gi = 0)
@@ -605,8 +746,9 @@ struct WfRaysPolicy {
 };
 
 __global__ void __launch_bounds__(WF_THREADS, 1) k_rays_wf(const __grid_constant__ IaFrame p, WfRaysPolicy pol,
+                                                           unsigned char* __restrict__ scratch,
                                                            unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char wf_smem[];
     WfShared& S = *reinterpret_cast<WfShared*>(wf_smem);
-    wf_run(p, pol, S, counters);
+    wf_run(p, pol, S, scratch, counters);
 }
