@@ -129,6 +129,7 @@ int ia_get_counters(ia_ctx* ctx, uint64_t* h_counters, void* stream);
 #define IA_CNT_SECONDARY_RAYS 7
 #define IA_CNT_OVERFLOW 8       /* rays that exceeded the per-ray edge capacity / sample pool */
 #define IA_CNT_SKIN_FETCH 9     /* 24-channel skinning-weight fetches */
+#define IA_CNT_CHAINS_SKIPPED 10 /* Broyden chains whose initial point lies outside the voxel grid (exactly invalid) */
 
 /* Per-stage device timing (CUDA events recorded on the launching stream around each stage's kernels).
  * ia_set_timing(ctx, 1) enables recording; ia_get_timings syncs the stream and returns, for each

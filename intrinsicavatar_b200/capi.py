@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("IA_B200_LIB") or os.path.join(_HERE, "libia_b200.so")
 SRC_DIR = os.path.join(_HERE, "csrc")
 N_COUNTERS = 16
 COUNTER_NAMES = ["hit_rays", "samples", "queries", "queries_grad", "broyden_fetch", "geo_eval", "rad_eval",
-                 "secondary_rays", "overflow", "skin_fetch"]
+                 "secondary_rays", "overflow", "skin_fetch", "chains_skipped"]
 
 STAGE_NAMES = ["precompute", "occupancy", "light", "setup", "primary", "resample", "shade", "composite"]
 

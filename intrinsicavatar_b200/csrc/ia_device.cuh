@@ -62,6 +62,18 @@ __device__ __forceinline__ IaCorners ia_corners(const IaFrame& p, float gx, floa
     c.wx0 = (float)(c.x0 + 1) - ix; c.wy0 = (float)(c.y0 + 1) - iy; c.wz0 = (float)(c.z0 + 1) - iz;
     return c;
 }
+// True iff all 8 trilinear corners of the (normalised) point lie outside the voxel grid, i.e. the zero-padded
+// fetch returns J == 0 exactly.  A Broyden chain whose INITIAL point is such a point can never become valid:
+// Ji = 0 and g = -x_d, so the first step is u = 0, the fetch repeats with J = 0 and n = -x_d; then either
+// |x_d|^2 < 1e-10 ("converged", but the point is outside [-1,1]^3 -> invalid), or > 1e-2 (diverged), or the
+// rank-1 update divides 0 by 0 and every later residual is NaN (never converges).  Skipping such chains is
+// therefore exact w.r.t. broyden_kernel (fuse_cuda_kernel_fast.cu:250-413).
+__device__ __forceinline__ bool ia_all_corners_oob(const IaFrame& p, float gx, float gy, float gz) {
+    int x0 = (int)floorf(ia_src_index(gx, p.W)), y0 = (int)floorf(ia_src_index(gy, p.H)),
+        z0 = (int)floorf(ia_src_index(gz, p.D));
+    return x0 < -1 || x0 > p.W - 1 || y0 < -1 || y0 > p.H - 1 || z0 < -1 || z0 > p.D - 1;
+}
+
 // acc[0..5] += w_c * half `h` of corner c, over the 8 corners in the reference order
 // (tnw tne tsw tse bnw bne bsw bse: x fastest, then y, then z), zero padding.
 __device__ __forceinline__ void ia_gather_half(const IaFrame& p, const IaCorners& cn, int h, float acc[6]) {

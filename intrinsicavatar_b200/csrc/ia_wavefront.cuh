@@ -36,7 +36,7 @@
 #ifndef WF_STATE_GLOBAL
 #define WF_STATE_GLOBAL 1
 #endif
-#define WF_SCRATCH_BYTES (WF_R * IA_N_INIT * 3 * 4 + WF_R * IA_N_INIT * 2 + WF_NST * WF_R * 4)  // per CTA
+#define WF_SCRATCH_BYTES (WF_R * IA_N_INIT * 3 * 4 + 2 * WF_R * IA_N_INIT * 2 + WF_NST * WF_R * 4)  // per CTA
 
 enum { WF_IDLE = 0, WF_FIRST = 1, WF_SEARCH = 2, WF_CDF = 3, WF_FINE = 4 };
 enum { WF_ACT_NEXT = 0, WF_ACT_CDF = 1, WF_ACT_FINE_START = 2, WF_ACT_FINISH = 3 };
@@ -81,6 +81,8 @@ struct WfShared {
     // L1 carve-out to the voxel_J gathers, which is what the kernel is bound by -- DESIGN.md):
     float* cand;            // [WF_R][13][3] Broyden roots; [.][.][0] is overwritten with the SDF
     unsigned short* gtask;  // [WF_R * 13] geometry task list
+    unsigned short* btask;  // [WF_R * 13] Broyden task list (pruned)
+    int n_btask;
     int n_q, task_next, n_gtask, ring_head, ring_tail, tile, more_tiles, pad;
 };
 
@@ -132,8 +134,38 @@ __device__ __forceinline__ int wf_grab(WfShared& S, int n_tasks) {
 }
 
 // Broyden chains of all pending queries (fuse_cuda_kernel_fast.cu:250-413), one voxel fetch per trip.
-__device__ __forceinline__ void wf_broyden_phase_1lane(const IaFrame& p, WfShared& S, int n_q, unsigned& c_fetch) {
-    const int n_tasks = n_q * IA_N_INIT;
+// Dense pre-pass over the 13 x n_q (query, init bone) pairs: chains whose initial point has all 8 corners
+// outside the voxel grid are exactly invalid (ia_all_corners_oob) and are dropped; the others are
+// compacted, bone-major, into the Broyden task list.
+__device__ __forceinline__ void wf_prune_phase(const IaFrame& p, WfShared& S, int n_q, unsigned& c_skip) {
+    const int n_pairs = n_q * IA_N_INIT;
+    const int lane = threadIdx.x & 31;
+    for (int k0 = (threadIdx.x & ~31); k0 < n_pairs; k0 += blockDim.x) {
+        const int k = k0 + lane;
+        bool live = false;
+        int q = 0, c = 0;
+        if (k < n_pairs) {
+            c = k / n_q;
+            q = S.qlist[k - c * n_q];
+            const float xd0 = S.qx[0][q], xd1 = S.qx[1][q], xd2 = S.qx[2][q];
+            const float* T = S.tfs13 + c * 12;
+            float d0 = xd0 - T[3], d1 = xd1 - T[7], d2 = xd2 - T[11];
+            float x0 = d0 * T[0] + d1 * T[4] + d2 * T[8];
+            float x1 = d0 * T[1] + d1 * T[5] + d2 * T[9];
+            float x2 = d0 * T[2] + d1 * T[6] + d2 * T[10];
+            live = !ia_all_corners_oob(p, p.scl[0] * (x0 + p.off[0]), p.scl[1] * (x1 + p.off[1]), p.scl[2] * (x2 + p.off[2]));
+            if (!live) c_skip++;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, live);
+        int base = 0;
+        if (lane == 0 && b) base = atomicAdd(&S.n_btask, __popc(b));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (live) S.btask[base + __popc(b & ((1u << lane) - 1u))] = (unsigned short)(q * 16 + c);
+    }
+}
+
+__device__ __forceinline__ void wf_broyden_phase_1lane(const IaFrame& p, WfShared& S, unsigned& c_fetch) {
+    const int n_tasks = S.n_btask;
     int task = wf_grab(S, n_tasks);
     bool fresh = true;
     float x0 = 0, x1 = 0, x2 = 0, xd0 = 0, xd1 = 0, xd2 = 0, g0 = 0, g1 = 0, g2 = 0;
@@ -142,8 +174,8 @@ __device__ __forceinline__ void wf_broyden_phase_1lane(const IaFrame& p, WfShare
     while (task >= 0) {
         float u0 = 0, u1 = 0, u2 = 0;
         if (fresh) {
-            c = task / n_q;                       // bone-major: neighbouring lanes = same bone, neighbouring rays
-            q = S.qlist[task - c * n_q];
+            const int tk = S.btask[task];
+            q = tk >> 4; c = tk & 15;
             xd0 = S.qx[0][q]; xd1 = S.qx[1][q]; xd2 = S.qx[2][q];
             const float* T = S.tfs13 + c * 12;
             float d0 = xd0 - T[3], d1 = xd1 - T[7], d2 = xd2 - T[11];
@@ -209,6 +241,7 @@ __device__ __forceinline__ void wf_broyden_phase_1lane(const IaFrame& p, WfShare
     }
 }
 
+#if WF_BROYDEN_LANES == 3
 // Broyden chains of all pending queries (fuse_cuda_kernel_fast.cu:250-413).
 // One chain per group of THREE lanes: lane r owns row r of the fetched 3x4 transform (8 x LDG.128, all
 // in flight together) and column r of the inverse Jacobian; a warp runs 10 chains, lanes 30/31 idle.
@@ -318,6 +351,8 @@ __device__ __forceinline__ void wf_broyden_phase(const IaFrame& p, WfShared& S, 
         if (fin) { task = nt; fresh = true; }
     }
 }
+
+#endif
 
 // filter.cu:10-54 per pending query, then the list of geometry tasks
 __device__ __forceinline__ void wf_filter_phase(WfShared& S, int n_q) {
@@ -556,8 +591,9 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
         unsigned char* mine = scratch + (size_t)blockIdx.x * WF_SCRATCH_BYTES;
         S.cand = reinterpret_cast<float*>(mine);
         S.gtask = reinterpret_cast<unsigned short*>(mine + WF_R * IA_N_INIT * 3 * 4);
+        S.btask = reinterpret_cast<unsigned short*>(mine + WF_R * IA_N_INIT * 3 * 4 + WF_R * IA_N_INIT * 2);
 #if WF_STATE_GLOBAL
-        S.st = reinterpret_cast<float (*)[WF_R]>(mine + WF_R * IA_N_INIT * 3 * 4 + WF_R * IA_N_INIT * 2);
+        S.st = reinterpret_cast<float (*)[WF_R]>(mine + WF_R * IA_N_INIT * 3 * 4 + 2 * WF_R * IA_N_INIT * 2);
 #endif
     }
     __syncthreads();
@@ -569,7 +605,7 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
     if (tid == 0) { S.ring_head = 0; S.ring_tail = 0; S.more_tiles = 1; S.n_q = 0; S.n_gtask = 0; S.task_next = 0; }
     __syncthreads();
     const long long n_tiles = (pol.n_items() + WF_FEED - 1) / WF_FEED;
-    unsigned c_q = 0, c_fetch = 0, c_geo = 0, c_rays = 0;
+    unsigned c_q = 0, c_fetch = 0, c_geo = 0, c_rays = 0, c_skip = 0;
     while (true) {
         // ---- feed the ring while it cannot fill every slot
         while (true) {
@@ -588,7 +624,7 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
             __syncthreads();
         }
         __syncthreads();
-        if (tid == 0) { S.n_q = 0; S.n_gtask = 0; S.task_next = 0; }
+        if (tid == 0) { S.n_q = 0; S.n_gtask = 0; S.task_next = 0; S.n_btask = 0; }
         const int ring_tail = S.ring_tail;
         __syncthreads();
         for (int t = tid; t < WF_R; t += blockDim.x) wf_advance_slot(p, pol, S, t, ring_tail, c_q, c_rays);
@@ -599,7 +635,9 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
             continue;
         }
 #if WF_BROYDEN_LANES == 1
-        wf_broyden_phase_1lane(p, S, n_q, c_fetch);
+        wf_prune_phase(p, S, n_q, c_skip);
+        __syncthreads();
+        wf_broyden_phase_1lane(p, S, c_fetch);
 #else
         wf_broyden_phase(p, S, n_q, c_fetch);
 #endif
@@ -615,12 +653,14 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
         c_fetch += __shfl_xor_sync(0xffffffffu, c_fetch, o);
         c_geo += __shfl_xor_sync(0xffffffffu, c_geo, o);
         c_rays += __shfl_xor_sync(0xffffffffu, c_rays, o);
+        c_skip += __shfl_xor_sync(0xffffffffu, c_skip, o);
     }
     if ((tid & 31) == 0) {
         if (c_q) atomicAdd(&counters[IA_CNT_QUERIES], c_q);
         if (c_fetch) atomicAdd(&counters[IA_CNT_BROYDEN_FETCH], c_fetch);
         if (c_geo) atomicAdd(&counters[IA_CNT_GEO_EVAL], c_geo);
         if (c_rays) atomicAdd(&counters[IA_CNT_SECONDARY_RAYS], c_rays);
+        if (c_skip) atomicAdd(&counters[IA_CNT_CHAINS_SKIPPED], c_skip);
     }
 }
 
