@@ -1,0 +1,206 @@
+#!/usr/bin/env python
+"""Generate tests/golden/reference_vectors.npz by running the REFERENCE's own Python modules on CPU.
+
+Runs only in the build container (needs /root/reference); the .npz is committed and is what the
+`-m "not gpu"` tests (tests/test_oracle_golden.py) hold the oracle to.  Nothing is copied from the
+reference: its modules are imported from where they lie, with the absent third-party packages
+(tinycudann, pytorch_lightning, omegaconf, nerfacc, imageio, pyexr) replaced by empty stub modules
+and `device="cuda"` factory calls redirected to the CPU.
+
+What is pinned (reference file:line):
+  bxdf       MultiLobe.eval (Lambertian + GGX)                    lib/torch_pbr/bxdf.py:111-146,217-265,321-330
+  envlight   EnvironmentLightTensor.update_pdf/sample/pdf/eval    lib/torch_pbr/light.py:221-446
+  srgb       rgb_to_srgb                                          lib/torch_pbr/utils/nvdiffrecmc_util.py:94-102
+  mlp        VanillaMLP (weight-norm, sphere init, softplus100),  models/network_utils.py:201-244
+             VanillaMLP (ReLU), LipshitzMLP                       models/network_utils.py:360-428
+  density    LearnedLaplaceDensity.density_func                   models/rf/density.py:25-34
+  cc         max_connected_component                              models/utils.py:152-163
+  lbs        batch_rodrigues, batch_rigid_transform               models/deformers/smplx/lbs.py:345-401, 152-248
+  reflect    reflect(), get_activation                            models/utils.py
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "tests", "golden", "reference_vectors.npz")
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def _pkg(name, path):
+    m = types.ModuleType(name)
+    m.__path__ = [path]
+    sys.modules[name] = m
+    return m
+
+
+def install_stubs():
+    _stub("tinycudann")
+    _stub("imageio")
+    _stub("pyexr")
+    _stub("nerfacc")
+    _stub("omegaconf", OmegaConf=type("OmegaConf", (), {"register_new_resolver": staticmethod(lambda *a, **k: None)}))
+    _stub("pytorch_lightning")
+    _stub("pytorch_lightning.utilities")
+    _stub("pytorch_lightning.utilities.rank_zero", rank_zero_debug=lambda *a, **k: None,
+          rank_zero_info=lambda *a, **k: None, rank_zero_only=lambda f: f)
+    # packages whose __init__ pulls the whole framework in: expose only their directories
+    models = _pkg("models", os.path.join(REF, "models"))
+    models.register = lambda name: (lambda cls: cls)
+    _pkg("models.deformers", os.path.join(REF, "models", "deformers"))
+    _pkg("models.deformers.smplx", os.path.join(REF, "models", "deformers", "smplx"))
+    _pkg("models.rf", os.path.join(REF, "models", "rf"))
+    _pkg("utils", os.path.join(REF, "utils"))
+    _pkg("systems", os.path.join(REF, "systems"))
+    sys.path.insert(0, REF)
+    # device="cuda" -> CPU for tensor factories and .cuda()
+    for fn in ("rand", "tensor", "arange", "zeros", "ones", "empty", "full", "linspace", "randn", "eye"):
+        orig = getattr(torch, fn)
+
+        def wrap(*a, __o=orig, **k):
+            if str(k.get("device", "")).startswith("cuda"):
+                k["device"] = "cpu"
+            return __o(*a, **k)
+        setattr(torch, fn, wrap)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+
+
+def main():
+    install_stubs()
+    torch.manual_seed(1234)
+    g = {}
+
+    # ------------------------------------------------------------------ bxdf (MultiLobe.eval)
+    from lib.torch_pbr import bxdf as ref_bxdf
+    cfg = types.SimpleNamespace(get=lambda k, d=None: d)
+    N = 512
+    n = torch.nn.functional.normalize(torch.randn(N, 3), dim=-1)
+    wi = torch.nn.functional.normalize(n + 0.8 * torch.randn(N, 3), dim=-1)
+    wo = torch.nn.functional.normalize(n + 0.8 * torch.randn(N, 3), dim=-1)
+    rough = torch.rand(N, 1) * 0.9 + 0.09
+    albedo = torch.rand(N, 3) * 0.77 + 0.03
+    metal = torch.rand(N, 1)
+    lobe = ref_bxdf.MultiLobe(types.SimpleNamespace())
+    # called exactly as pbr_light_forward does (models/intrinsic_avatar.py:816-825)
+    out = lobe.eval(wi=wi, n=n, wo=wo, alpha_x=rough.squeeze(-1), alpha_y=rough.squeeze(-1), albedo=albedo,
+                    metallic=metal, attenuation=torch.zeros(N, 1))
+    diff, spec = out[0], out[1]
+    g.update(bxdf_wi=wi, bxdf_n=n, bxdf_wo=wo, bxdf_rough=rough, bxdf_albedo=albedo, bxdf_metal=metal,
+             bxdf_diff=diff, bxdf_spec=spec)
+
+    # ------------------------------------------------------------------ env light
+    from lib.torch_pbr import light as ref_light
+    ecfg = types.SimpleNamespace(xyz2lonlat_mode=None,
+                                 envlight_config=types.SimpleNamespace(scale=1.0, bias=0.0, base_res=8, hdr_filepath=None))
+    env = ref_light.EnvironmentLightTensor(ecfg)
+    H, W = 24, 48
+    base = torch.rand(H, W, 3) ** 4 * 20.0           # HDR-like dynamic range
+    base[5, 7] = torch.tensor([900.0, 700.0, 500.0])  # a "sun"
+    base[20:, :, :] = 0.0                              # rows with zero radiance (pdf floor 1e-6)
+    env.base.data = base
+    env.pdf_scale = (H * W) / (2 * np.pi * np.pi)
+    env.update_pdf()
+    env.train(False)
+    n_s = 256
+    torch.manual_seed(77)
+    u1, u2 = torch.rand(n_s), torch.rand(n_s)
+    torch.manual_seed(77)
+    dirs = env.sample(n_s)
+    more = torch.nn.functional.normalize(torch.randn(300, 3), dim=-1)
+    alld = torch.cat([dirs, more])
+    g.update(env_base=base, env_pdf_table=env._pdf, env_rows=env.rows, env_cols=env.cols, env_u1=u1, env_u2=u2,
+             env_dirs=dirs, env_query_dirs=alld, env_pdf=env.pdf(alld), env_eval=ref_light.EnvironmentLightTensor.eval(env, alld))
+
+    # ------------------------------------------------------------------ sRGB
+    from lib.torch_pbr.utils import nvdiffrecmc_util as ref_util
+    ramp = torch.cat([torch.linspace(-0.1, 0.01, 50), torch.linspace(0.0, 4.0, 200)])[:, None].repeat(1, 3)
+    g.update(srgb_in=ramp, srgb_out=ref_util.rgb_to_srgb(ramp))
+
+    # ------------------------------------------------------------------ MLPs with OUR random state dict
+    sys.path.insert(0, ROOT)
+    from intrinsicavatar_b200.weights import random_state_dict
+    from models import network_utils as ref_net
+    sd = random_state_dict(0)
+
+    def sub(prefix):
+        return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+    geo = ref_net.VanillaMLP(35, 13, {"n_neurons": 64, "n_hidden_layers": 1, "sphere_init": True,
+                                      "sphere_init_radius": 0.5, "weight_norm": True, "output_activation": "none"})
+    geo.load_state_dict(sub("geometry.network."), strict=True)
+    rad = ref_net.VanillaMLP(67, 3, {"n_neurons": 64, "n_hidden_layers": 2, "output_activation": "none"})
+    rad.load_state_dict(sub("radiance.network."), strict=True)
+    mat = ref_net.LipshitzMLP(48, 5, {"n_neurons": 64, "n_hidden_layers": 2, "output_activation": "none"})
+    msd = sub("material.network.")
+    mat.load_state_dict({k: v for k, v in msd.items()}, strict=False)
+    # LipshitzMLP shares its Linear weights with weights_per_layer: make sure both views carry our values
+    for i in range(3):
+        mat.weights_per_layer[i].data.copy_(msd[f"layers.{i}.weight"])
+        mat.biases_per_layer[i].data.copy_(msd[f"layers.{i}.bias"])
+        mat.lipshitz_bound_per_layer[i].data.copy_(msd[f"lipshitz_bound_per_layer.{i}"].reshape(-1))
+    x35 = torch.cat([torch.rand(400, 3) * 2 - 1, torch.randn(400, 32) * 0.1], 1)
+    x67 = torch.cat([torch.rand(400, 3) * 2 - 1, torch.randn(400, 32) * 1e-2, torch.randn(400, 13) * 0.3,
+                     torch.randn(400, 16), torch.nn.functional.normalize(torch.randn(400, 3), dim=-1)], 1)
+    x48 = torch.cat([torch.rand(400, 3) * 2 - 1, torch.randn(400, 32) * 1e-2, torch.randn(400, 13) * 0.3], 1)
+    with torch.no_grad():
+        g.update(mlp_geo_in=x35, mlp_geo_out=geo(x35), mlp_rad_in=x67, mlp_rad_out=rad(x67),
+                 mlp_mat_in=x48, mlp_mat_out=mat(x48))
+
+    # ------------------------------------------------------------------ Laplace density
+    import importlib.util
+    models_base = _stub("models.base", BaseModel=type("BaseModel", (torch.nn.Module,), {}))
+    spec_ = importlib.util.spec_from_file_location("ref_density", os.path.join(REF, "models/rf/density.py"))
+    dens = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(dens)
+    sdf = torch.cat([torch.linspace(-0.2, 0.2, 401), torch.tensor([0.0, 1e5, -1e-7, 1e-7])])
+    beta = torch.tensor(0.01) + 1e-4
+    sigma = dens.LearnedLaplaceDensity.density_func(None, sdf, beta=beta)
+    g.update(density_sdf=sdf, density_beta=beta, density_sigma=sigma)
+
+    # ------------------------------------------------------------------ connected components, reflect
+    spec_u = importlib.util.spec_from_file_location("ref_models_utils", os.path.join(REF, "models/utils.py"))
+    mu = importlib.util.module_from_spec(spec_u)
+    spec_u.loader.exec_module(mu)
+    grid = torch.zeros(16, 16, 16, dtype=torch.bool)
+    grid[2:7, 3:9, 4:8] = True          # big blob
+    grid[10:12, 10:12, 10:12] = True    # small blob
+    grid[14, 14, 14] = True             # single voxel
+    grid[7, 8, 7] = True                # diagonal neighbour of the big blob (26-connectivity joins it)
+    g.update(cc_grid=grid, cc_labels=mu.max_connected_component(grid[None]))
+    v = torch.nn.functional.normalize(torch.randn(64, 3), dim=-1)
+    nn_ = torch.nn.functional.normalize(torch.randn(64, 3), dim=-1)
+    g.update(reflect_v=v, reflect_n=nn_, reflect_out=mu.reflect(v, nn_))
+
+    # ------------------------------------------------------------------ SMPL skeleton maths
+    from models.deformers.smplx import lbs as ref_lbs
+    rv = torch.randn(24, 3) * 0.6
+    rv[3] = 0.0                          # zero rotation edge case
+    R = ref_lbs.batch_rodrigues(rv)
+    from intrinsicavatar_b200.body import SyntheticBody
+    body = SyntheticBody()
+    from intrinsicavatar_b200.body import PARENTS
+    joints = torch.from_numpy(np.asarray(body.joints_rest, np.float32))[None]
+    parents = torch.from_numpy(np.asarray(PARENTS, np.int64))
+    posed_joints, A = ref_lbs.batch_rigid_transform(R[None], joints, parents)
+    g.update(lbs_rvec=rv, lbs_rotmats=R, lbs_joints=joints[0], lbs_parents=parents, lbs_posed_joints=posed_joints[0],
+             lbs_A=A[0])
+
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    np.savez_compressed(OUT, **{k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in g.items()})
+    print("wrote", OUT, {k: tuple(np.asarray(v.detach() if torch.is_tensor(v) else v).shape) for k, v in g.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,199 @@
+"""CPU (-m "not gpu"): host-side logic and the oracle's own invariants / edge cases (empty and ragged
+inputs, sign-change snapping, permutations), at sizes that run in seconds."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops as oops
+from oracle.pbr import kensler_permute, pixel_key
+
+
+# ------------------------------------------------------------------------------ host logic ----
+def test_hashgrid_layout_matches_tcnn_spec():
+    """16 levels, base 16, scale 2^(8/15), T = 2^19."""
+    from intrinsicavatar_b200.weights import hashgrid_layout
+    L = hashgrid_layout()
+    assert list(L["res"]) == [16, 24, 34, 49, 71, 102, 148, 213, 308, 446, 646, 934, 1352, 1956, 2831, 4096]
+    assert list(L["size"][:5]) == [4096, 13824, 39304, 117656, 357912]
+    assert all(s == 1 << 19 for s in L["size"][5:])
+    assert L["total"] == 6299960 and list(L["offset"]) == list(np.cumsum([0] + list(L["size"][:-1])))
+
+
+def test_fold_weight_norm_and_lipschitz():
+    from intrinsicavatar_b200.weights import fold, random_state_dict
+    sd = random_state_dict(0)
+    w = fold(sd)
+    g, v = sd["geometry.network.layers.0.weight_g"], sd["geometry.network.layers.0.weight_v"]
+    assert torch.allclose(w["geo_w1"].norm(dim=1), g.reshape(-1), rtol=1e-5)      # ||W_row|| = g
+    assert torch.allclose(F_normalize(w["geo_w1"]), F_normalize(v), atol=1e-6)
+    for i, name in enumerate(("mat_w1", "mat_w2", "mat_w3")):
+        c = torch.nn.functional.softplus(sd[f"material.network.lipshitz_bound_per_layer.{i}"]).reshape(-1)
+        assert (w[name].abs().sum(1) <= c + 1e-5).all()                              # row L1 norm bounded by softplus(c)
+    assert set(k.split(".")[0] for k in sd) == {"geometry", "radiance", "material", "density"}
+    assert "geometry.encoding.encoding.encoding.params" in sd and "density.beta" in sd
+
+
+def F_normalize(x):
+    return torch.nn.functional.normalize(x, dim=1)
+
+
+def test_synthetic_rays_and_pose_stream():
+    from intrinsicavatar_b200 import synthetic as syn
+    bp, go, tr = syn.load_pose(0)
+    assert bp.shape == (69,) and go.shape == (3,) and np.allclose(tr, [0, 0.15, 5], atol=1e-6)
+    rays = syn.make_rays(32, 32, tr)
+    assert rays.shape == (1024, 8) and rays.dtype == np.float32
+    assert np.allclose(np.linalg.norm(rays[:, 3:6], axis=1), 1, atol=1e-6)
+    assert np.allclose(rays[:, 7] - rays[:, 6], 2.0, atol=1e-5)
+    env = syn.load_envmap(64, 128)
+    assert env.shape == (64, 128, 3) and env.min() >= 0 and env.max() > 50       # HDR sun survives the down-sampling
+    t = syn.random_tables(8, 4, seed=3)
+    assert t["jitter"].shape == (64, 3, 3) and t["u1"].shape == (8,)
+
+
+def test_snarf_setup_frame(scene):
+    s = scene.snarf
+    assert s.lbs_voxel.shape == (24, 32, 128, 128)
+    assert np.allclose(s.lbs_voxel.sum(0), 1, atol=1e-4)                          # skinning weights are convex
+    fr = scene.frame(None)
+    assert fr["tfs"].shape == (24, 4, 4) and fr["w2s"].shape == (4, 4)
+    assert np.allclose(fr["tfs"][:, 3], [0, 0, 0, 1], atol=1e-6)
+    R = fr["tfs"][:, :3, :3]
+    assert np.allclose(R @ R.transpose(0, 2, 1), np.eye(3), atol=1e-5)            # rigid bones
+    bb = fr["deformed_bbox"]
+    assert np.allclose(bb[3:] - bb[:3], (bb[3:] - bb[:3])[0])                     # cube bbox (get_bbox_from_smpl)
+
+
+def test_model_surface_without_gpu():
+    """The drop-in class refuses to construct without a device (no silent CPU path)."""
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    from intrinsicavatar_b200.model import IntrinsicAvatarModel
+    with pytest.raises(RuntimeError):
+        IntrinsicAvatarModel()
+
+
+# ---------------------------------------------------------------------- oracle edge cases ----
+def test_pack_unpack_empty_and_ragged():
+    ri = torch.tensor([0, 0, 0, 2, 2, 5], dtype=torch.int64)
+    packed = oops.pack_info(ri, 7)
+    assert packed.tolist() == [[0, 3], [3, 0], [3, 2], [5, 0], [5, 0], [5, 1], [6, 0]]
+    assert torch.equal(oops.unpack_info(packed, 6), ri)
+    empty = oops.pack_info(torch.zeros(0, dtype=torch.int64), 4)
+    assert empty[:, 1].sum() == 0 and oops.unpack_info(empty, 0).numel() == 0
+    data = torch.arange(12, dtype=torch.float32).reshape(6, 2)
+    padded = oops.unpack_data(packed, data, 4)
+    assert padded.shape == (7, 4, 2) and torch.equal(padded[2, :2], data[3:5]) and (padded[1] == 0).all()
+
+
+def test_render_weight_and_accumulate():
+    alphas = torch.tensor([0.5, 0.5, 1.0, 0.25, 0.0])
+    packed = torch.tensor([[0, 3], [3, 0], [3, 2]], dtype=torch.int32)
+    w, T = oops.render_weight_from_alpha(alphas, packed)
+    assert torch.allclose(w, torch.tensor([0.5, 0.25, 0.25, 0.25, 0.0]))
+    assert torch.allclose(T, torch.tensor([1.0, 0.5, 0.25, 1.0, 0.75]))
+    ri = oops.unpack_info(packed, 5)
+    acc = oops.accumulate_along_rays(w, None, ri, 3)
+    assert torch.allclose(acc[:, 0], torch.tensor([1.0, 0.0, 0.25]))
+    vals = torch.ones(5, 2) * torch.tensor([1.0, 2.0])
+    assert torch.allclose(oops.accumulate_along_rays(w, vals, ri, 3)[0], torch.tensor([1.0, 2.0]))
+
+
+@pytest.mark.parametrize("spp", [2, 5, 64])
+def test_ray_resampling_invariants(spp):
+    """cdf.cu:9-149: every hit ray gets exactly spp samples; fg counts + bg = spp; t is non-decreasing;
+    after the first +/- SDF crossing all later samples repeat one t (zero-crossing snap)."""
+    g = torch.Generator().manual_seed(spp)
+    n_rays = 40
+    steps = torch.randint(0, 12, (n_rays,), generator=g)
+    steps[3] = 0
+    steps[7] = 1
+    base = torch.cumsum(steps, 0) - steps
+    packed = torch.stack([base, steps], 1).int()
+    n = int(steps.sum())
+    starts = torch.zeros(n)
+    ends = torch.zeros(n)
+    sdfs = torch.zeros(n)
+    alphas = torch.rand(n, generator=g) * 0.6
+    for r in range(n_rays):
+        b, s = int(base[r]), int(steps[r])
+        t = 1.0 + torch.arange(s + 1) * 0.1
+        starts[b:b + s], ends[b:b + s] = t[:-1], t[1:]
+        sdfs[b:b + s] = torch.linspace(0.3, -0.3 if r % 2 == 0 else 0.05, s) if s else torch.zeros(0)
+    w, _ = oops.render_weight_from_alpha(alphas, packed)
+    rpi, ts, offs, idx, fg, bg, surf = oops.ray_resampling(packed, starts[:, None], ends[:, None], w, sdfs, spp)
+    assert torch.equal(rpi[:, 1], (steps > 0).int() * spp)
+    for r in range(n_rays):
+        b, s = int(base[r]), int(steps[r])
+        rb, rn = int(rpi[r, 0]), int(rpi[r, 1])
+        if s == 0:
+            assert rn == 0
+            continue
+        assert int(fg[b:b + s].sum()) + int(bg[r]) == spp
+        is_fg = offs[rb:rb + rn, 0] < 1e4
+        t_fg = ts[rb:rb + rn, 0][is_fg]
+        assert (t_fg[1:] >= t_fg[:-1] - 1e-6).all()
+        assert int(is_fg.sum()) == int(fg[b:b + s].sum())
+        if int(surf[r]) >= 0 and is_fg.sum() > 1:
+            # samples placed after the crossing interval all share the snapped t
+            after = idx[rb:rb + rn][is_fg] > int(surf[r])
+            if after.sum() > 1:
+                assert float(t_fg[after].max() - t_fg[after].min()) == 0.0
+
+
+def test_traverse_grid_lattice_and_miss():
+    """nerfacc traverse_grids semantics: samples live on t = near + k*step, emitted iff their midpoint
+    is in an occupied cell; a ray that misses the box yields nothing."""
+    res = 8
+    binaries = torch.zeros(res, res, res, dtype=torch.bool)
+    binaries[:, 3:5, :] = True                                    # a slab in y
+    aabb = torch.tensor([-1.0, -1, -1, 1, 1, 1])
+    o = torch.tensor([[0.05, -3.0, 0.1], [5.0, 5.0, 5.0]])
+    d = torch.tensor([[0.0, 1.0, 0.0], [0.0, 1.0, 0.0]])
+    step = 0.07
+    tg = oops.traverse_grid(o, d, binaries, aabb, 0.0, 1e10, step)
+    ts, te = tg["t_starts"], tg["t_ends"]
+    assert tg["sample_packed_info"][1, 1] == 0 if "sample_packed_info" in tg else True
+    assert len(ts) > 0 and torch.allclose(te - ts, torch.full_like(ts, step), atol=1e-6)
+    k = ts / step
+    assert torch.allclose(k, torch.round(k), atol=1e-3)           # global lattice from near = 0
+    mid_y = -3.0 + (ts + te) / 2
+    assert (mid_y > -0.25 - 1e-4).all() and (mid_y < 0.25 + 1e-4).all()
+    assert abs(len(ts) - 0.5 / step) <= 1.5
+    # edges: one run -> first edge is_left only, last is_right only, inner both
+    il, ir = tg["is_left"], tg["is_right"]
+    assert il[0] and not ir[0] and ir[-1] and not il[-1] and (il[1:-1] & ir[1:-1]).all()
+
+
+@pytest.mark.parametrize("l", [2, 3, 4, 7, 256, 1000, 1024])
+def test_light_permutation_is_a_permutation(l):
+    for ray in (0, 1, 12345):
+        key = pixel_key(7, np.full(l, ray, np.int64))
+        p = kensler_permute(np.arange(l, dtype=np.uint64), l, key)
+        assert sorted(p.tolist()) == list(range(l))
+    a = kensler_permute(np.arange(l, dtype=np.uint64), l, pixel_key(7, np.full(l, 1, np.int64)))
+    b = kensler_permute(np.arange(l, dtype=np.uint64), l, pixel_key(7, np.full(l, 2, np.int64)))
+    if l >= 256:
+        assert (a != b).mean() > 0.9                               # different pixels decorrelate
+
+
+def test_oracle_tiny_frame(scene):
+    """End-to-end oracle on a 12x12 / 2 spp frame: output contract of forward() (keys, shapes, background)."""
+    fr = scene.frame(0)
+    R = scene.oracle_renderer(spp=2, grid_res=16)
+    R.set_pose(fr["tfs"], fr["w2s"])
+    tabs = scene.syn.random_tables(2, 16, seed=0)
+    R.build_occupancy(fr["deformed_bbox"], tabs["jitter"])
+    R.set_light(scene.syn.load_envmap(), tabs["u1"], tabs["u2"])
+    rays = torch.from_numpy(scene.syn.make_rays(12, 12, fr["transl"]))
+    out = R.forward(rays, seed=0)
+    for k, c in (("comp_rgb", 3), ("comp_normal", 3), ("opacity", 1), ("depth", 1), ("comp_rgb_phys", 3),
+                 ("comp_demod_phys", 3), ("comp_albedo", 3), ("comp_metallic", 1), ("comp_roughness", 1),
+                 ("comp_rgb_full", 3), ("comp_rgb_phys_full", 3)):
+        assert out[k].shape == (144, c), k
+    miss = out["opacity"][:, 0] == 0
+    assert miss.any() and (~miss).any()
+    assert (out["comp_rgb_phys"][miss] == 1).all()                # white background (systems/...:133-136)
+    assert out["opacity"].max() <= 1 + 1e-5 and torch.isfinite(out["comp_rgb_phys"]).all()
+    prim = R.forward(rays, seed=0, albedo_only=True)
+    assert torch.equal(prim["comp_albedo"], out["comp_albedo"]) and (prim["comp_rgb_phys"] == 1).all()

@@ -1,0 +1,66 @@
+"""CPU (-m "not gpu"): the N>1 path with world_size 2 over gloo -- frame partition, pack / gather / unpack."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from intrinsicavatar_b200 import parallel
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mine = parallel.frames_for_rank(5, rank, world)
+        n_pix = 6
+        out = {}
+        for k, c in zip(parallel.FRAME_KEYS, (3, 3, 3, 1, 1, 1, 1, 3)):
+            out[k] = torch.full((n_pix, c), float(rank * 100 + c)) + torch.arange(n_pix)[:, None]
+        block = parallel.pack_frame(out)
+        got = parallel.gather_frames(block, dst=0)
+        ok = True
+        if rank == 0:
+            ok = got is not None and len(got) == world
+            for r, b in enumerate(got):
+                un = parallel.unpack_frame(b)
+                for k, c in zip(parallel.FRAME_KEYS, (3, 3, 3, 1, 1, 1, 1, 3)):
+                    ok = ok and un[k].shape == (n_pix, c) and float(un[k][0, 0]) == r * 100 + c
+        else:
+            ok = got is None
+        t = torch.tensor([float(len(mine))])
+        dist.all_reduce(t)
+        q.put((rank, mine, bool(ok), float(t)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_frames_shard_and_gather_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == [0, 2, 4] and res[1][1] == [1, 3]       # frame i -> rank i mod N, nothing dropped
+    assert all(r[2] for r in res) and res[0][3] == 5.0
+
+
+def test_single_process_gather_is_identity():
+    b = torch.arange(32, dtype=torch.float32).reshape(2, 16)
+    assert parallel.gather_frames(b)[0] is b
+    un = parallel.unpack_frame(b)
+    assert torch.equal(parallel.pack_frame(un), b)
