@@ -313,29 +313,39 @@ def main():
             v = [s[key] for s in stage_ms if s[key] >= 0]
             return sum(v) / len(v) if v else 0.0
         shade_ms = avg("shade")
-        c = {k: sum(cc[k] for cc in cnts) / max(1, len(cnts)) for k in cnts[0]} if cnts else {}
-        # counters cover the whole ia_render call; bytes of the shade launch = frame bytes minus the primary stage's
-        # share is not separable from counters alone, so the roofline is stated for the whole ia_render launch set
-        # against its summed duration, and for k_shade alone with the per-frame bytes (>= 97 % of them are k_shade's).
+        keys = [k for k in cnts[0] if k != "primary"] if cnts else []
+        c = {k: sum(cc[k] for cc in cnts) / max(1, len(cnts)) for k in keys}
+        cp = {k: sum(cc["primary"][k] for cc in cnts) / max(1, len(cnts)) for k in keys if k != "hit_rays"} if cnts else {}
+        # work of the shading kernel alone = totals - snapshot taken when the primary stage had finished
+        cs = {k: c[k] - cp.get(k, 0) for k in keys if k != "hit_rays"}
+        n_samples = c.get("hit_rays", 0) * args.spp
+        # + the sample streams the kernel reads (rs_src, rs_w 4 B each per shading sample; rs_t 4 B, the 48-B
+        #   IaSample and 6 fp32 accumulations per traced ray)
+        alg = (B_BROYDEN_FETCH * cs["broyden_fetch"] + B_HASH_EVAL * cs["geo_eval"] + 8 * n_samples
+               + (4 + 48 + 24) * cs["secondary_rays"]) if cs else 0
+        achieved = alg / (shade_ms * 1e-3) / 1e9 if shade_ms > 0 else 0.0
         render_ms = sum(avg(k) for k in ("setup", "primary", "resample", "shade", "composite"))
-        alg = algorithmic_bytes(c, n_rays, args.spp) if c else 0
-        achieved = alg / (render_ms * 1e-3) / 1e9 if render_ms > 0 else 0.0
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "kernel": "k_shade (+k_primary) via ia_render",
-                    "algorithmic_bytes_per_launch": alg, "launch_ms": render_ms, "k_shade_ms": shade_ms,
-                    "note": "gather working set (hash grid, voxel_J, LBS weights) is L2-resident by design; bytes are "
-                            "the bytes the gathers request, see DESIGN.md"}
+                    "traffic": None, "peak_source": peak_src, "kernel": "k_shade_wf (wavefront secondary-ray integrator)",
+                    "algorithmic_bytes_per_launch": alg, "launch_ms": shade_ms, "share_of_step": shade_ms / (ms_total / args.steps),
+                    "units_per_launch": {"broyden_voxel_fetches": cs.get("broyden_fetch"), "geometry_evals": cs.get("geo_eval"),
+                                         "secondary_rays": cs.get("secondary_rays"), "shading_samples": n_samples},
+                    "bytes_per_unit": {"broyden_voxel_fetch": B_BROYDEN_FETCH, "geometry_eval": B_HASH_EVAL,
+                                       "shading_sample": 8, "secondary_ray": 76},
+                    "note": "the gathers' working set (voxel_J 25 MB, geometry hash grid 50 MB) is L2-resident by design, "
+                            "so the bytes the kernel requests are served by L2/L1, not HBM: DRAM traffic (`traffic`) is far "
+                            "below the algorithmic bytes and frac can exceed what HBM could deliver (DESIGN.md, Roofline)"}
         tfile = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tfile):
             with open(tfile) as f:
-                roofline["traffic"] = json.load(f).get("k_shade_dram_bytes_per_launch")
+                roofline["traffic"] = json.load(f).get("k_shade_wf_dram_bytes_per_launch")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args), "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "stages_ms": {k: avg(k) for k in (stage_ms[0] if stage_ms else {})},
-            "counters_per_frame": c, "wall_ms_total": wall_ms,
+            "counters_per_frame": c, "counters_primary_stage": cp, "wall_ms_total": wall_ms,
             "ms_per_frame": ms_total / args.steps,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -26,7 +26,7 @@ extern "C" {
 #define IA_ESTATE -3
 #define IA_EOVERFLOW -4
 
-#define IA_N_COUNTERS 16
+#define IA_N_COUNTERS 32
 
 typedef struct ia_ctx ia_ctx;
 
@@ -130,6 +130,9 @@ int ia_get_counters(ia_ctx* ctx, uint64_t* h_counters, void* stream);
 #define IA_CNT_OVERFLOW 8       /* rays that exceeded the per-ray edge capacity / sample pool */
 #define IA_CNT_SKIN_FETCH 9     /* 24-channel skinning-weight fetches */
 #define IA_CNT_CHAINS_SKIPPED 10 /* Broyden chains whose initial point lies outside the voxel grid (exactly invalid) */
+/* h_counters[IA_CNT_PRIMARY_BASE + i] = counter i as it stood when the primary stage of the last ia_render
+ * had finished, so (total - primary) is the work of the shading kernel alone (roofline accounting).   */
+#define IA_CNT_PRIMARY_BASE 16
 
 /* Per-stage device timing (CUDA events recorded on the launching stream around each stage's kernels).
  * ia_set_timing(ctx, 1) enables recording; ia_get_timings syncs the stream and returns, for each

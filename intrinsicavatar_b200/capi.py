@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # IA_B200_LIB selects an alternative build of the same library (tuning variants made by build(defines=...))
 LIB_PATH = os.environ.get("IA_B200_LIB") or os.path.join(_HERE, "libia_b200.so")
 SRC_DIR = os.path.join(_HERE, "csrc")
-N_COUNTERS = 16
+N_COUNTERS = 32
+CNT_PRIMARY_BASE = 16
 COUNTER_NAMES = ["hit_rays", "samples", "queries", "queries_grad", "broyden_fetch", "geo_eval", "rad_eval",
                  "secondary_rays", "overflow", "skin_fetch", "chains_skipped"]
 

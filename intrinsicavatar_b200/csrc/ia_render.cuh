@@ -646,6 +646,8 @@ extern "C" int ia_render(ia_ctx* c, const float* d_rays, int64_t n_rays, int64_t
         IA_STAGE_END(c, IA_STAGE_PRIMARY, st, 1);
         IA_LAUNCH_CHECK();
     }
+    IA_CHECK_CUDA(cudaMemcpyAsync(c->d_counters + IA_CNT_PRIMARY_BASE, c->d_counters, IA_CNT_PRIMARY_BASE * sizeof(unsigned long long),
+                                  cudaMemcpyDeviceToDevice, st));
     if (!primary_only) {
         IA_STAGE_BEGIN(c, IA_STAGE_RESAMPLE, st);
         k_resample<<<c->n_sm * 4, 256, 0, st>>>(c->d_hit_info, c->d_hit_od, c->d_samples, c->d_work, c->spp, c->d_u_table,

@@ -181,7 +181,10 @@ class RenderEngine:
     def counters(self) -> dict:
         a = np.zeros(capi.N_COUNTERS, np.uint64)
         check(self.lib.ia_get_counters(self.h, fptr(a), _stream()), "ia_get_counters")
-        return {k: int(a[i]) for i, k in enumerate(capi.COUNTER_NAMES)}
+        out = {k: int(a[i]) for i, k in enumerate(capi.COUNTER_NAMES)}
+        # counters as they stood after the primary stage (hit_rays is a launch-wide figure, not a stage counter)
+        out["primary"] = {k: int(a[capi.CNT_PRIMARY_BASE + i]) for i, k in enumerate(capi.COUNTER_NAMES) if i > 0}
+        return out
 
     def set_timing(self, enable=True):
         check(self.lib.ia_set_timing(self.h, int(enable)), "ia_set_timing")
