@@ -171,7 +171,7 @@ def workload_config(args):
     return {
         "workload": f"{args.res}x{args.res} relight frame, {args.spp} spp, render_mode=light, "
                     f"global_illumination={'true' if args.gi else 'false'}, prepare+forward per step",
-        "frame_source": "AIST pose frames 0..7 (frame = step*N + rank mod 8), synthetic 24-joint body, random-init "
+        "frame_source": "AIST pose frames 0..7 (frame = (step + rank) mod 8), synthetic 24-joint body, random-init "
                         "hash grids + MLPs (seed 0), city.hdr envmap (8x area-downsampled copy, re-expanded to 1024x2048)",
         "rays_per_frame": args.res * args.res, "spp": args.spp, "gi": bool(args.gi),
         "parallelism": f"frame-per-gpu x{args.gpus}",
@@ -241,7 +241,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def frame_of(step):
-        return frames[(step * world + rank) % 8]
+        return frames[(step + rank) % 8]
 
     def step_device(step):
         fr = frame_of(step)

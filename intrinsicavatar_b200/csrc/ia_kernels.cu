@@ -72,6 +72,7 @@ struct ia_ctx {
     float* d_hit_od = nullptr;       // [n_rays][8]: o(3), d(3), far, opacity
     int* d_hit_info = nullptr;       // [n_rays][2]: sample offset, count
     IaSample* d_samples = nullptr;   // [ws_samples]
+    struct IaSampleAux* d_samples_aux = nullptr;  // [ws_samples] rgb, world normal, ray slot
     float* d_rs_t = nullptr;         // [ws_resamples]
     float* d_rs_w = nullptr;
     int* d_rs_src = nullptr;
@@ -159,7 +160,7 @@ extern "C" int ia_destroy(ia_ctx* c) {
                     c->d_light_em, c->d_light_pdf, c->d_u_table, c->d_env_pdf, c->d_env_cols, c->d_env_rows,
                     c->d_env_rowsum, c->d_env_total, c->d_hit_rays, c->d_hit_od, c->d_hit_info, c->d_samples,
                     c->d_rs_t, c->d_rs_w, c->d_rs_src, c->d_acc, c->d_counters, c->d_work, c->d_occ_a, c->d_occ_b,
-                    c->d_occ_hist, c->d_occ_sum, c->d_wf_scratch};
+                    c->d_occ_hist, c->d_occ_sum, c->d_wf_scratch, c->d_samples_aux};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete c;

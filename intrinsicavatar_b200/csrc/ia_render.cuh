@@ -76,26 +76,40 @@ __global__ void k_primary_setup(const __grid_constant__ IaFrame p, const float* 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Primary stage = three kernels (the first generation fused them in one 22k-instruction kernel that spent
+// 87 % of its samples waiting for instruction fetch -- profiles/r1_k_primary_fused_summary.md):
+//   k_prim_edges  : team per hit ray: march -> edges -> 2 x (SDF queries + CDF merge resample) -> final intervals
+//   k_prim_shade  : team per SHADING SAMPLE (flat list): deform + geometry w/ gradient + radiance + material
+//   k_prim_accum  : thread per hit ray: alpha -> weights -> 7 accumulations, weights into the sample records
 struct IaPrimarySmem {
     float vals[2][IA_CAP];
     float aux[IA_CAP];
     uint8_t flags[2][IA_CAP];
 };
 
-__global__ void __launch_bounds__(IA_PRIMARY_THREADS, 1)
-k_primary(const __grid_constant__ IaFrame p, const int* __restrict__ hit_rays, float* __restrict__ hit_od,
-          int* __restrict__ hit_info, IaSample* __restrict__ samples, long long sample_cap, int* __restrict__ work,
-          ia_outputs out, unsigned long long* __restrict__ counters) {
+// per-sample record written by k_prim_shade next to IaSample (which carries ts, te, sdf, n, albedo, rough, metal)
+struct IaSampleAux {
+    float rgb[3];
+    float nw[3];   // world-space unit normal
+    int slot;      // hit-ray slot of the sample
+    int pad;
+};
+static_assert(sizeof(IaSampleAux) == 32, "IaSampleAux layout");
+
+__global__ void __launch_bounds__(IA_PRIMARY_THREADS, 2)
+k_prim_edges(const __grid_constant__ IaFrame p, const float* __restrict__ hit_od, int* __restrict__ hit_info,
+             IaSample* __restrict__ samples, IaSampleAux* __restrict__ aux, long long sample_cap, int* __restrict__ work,
+             unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) float smem[];
-    float* wmlp = smem;
-    IaPrimarySmem* tsm = reinterpret_cast<IaPrimarySmem*>(smem + IA_MLP_END);
-    ia_stage(wmlp, p.mlp, IA_MLP_END);
+    float* wgeo = smem;
+    IaPrimarySmem* tsm = reinterpret_cast<IaPrimarySmem*>(smem + IA_GEO_END);
+    ia_stage(wgeo, p.mlp, IA_GEO_END);
     __syncthreads();
     Team team = cg::tiled_partition<IA_TEAM>(cg::this_thread_block());
     const int lane = team.thread_rank();
     IaPrimarySmem& S = tsm[threadIdx.x / IA_TEAM];
     const int n_hit = work[IA_W_NHIT];
-    unsigned c_q = 0, c_qg = 0, c_fetch = 0, c_geo = 0, c_rad = 0, c_over = 0, c_samples = 0;
+    unsigned c_q = 0, c_fetch = 0, c_geo = 0, c_over = 0, c_samples = 0;
     const float step = p.step_primary;
 
     while (true) {
@@ -103,10 +117,8 @@ k_primary(const __grid_constant__ IaFrame p, const int* __restrict__ hit_rays, f
         if (lane == 0) slot = atomicAdd(&work[IA_W_PRIMARY_NEXT], 1);
         slot = team.shfl(slot, 0);
         if (slot >= n_hit) break;
-        const int ray = hit_rays[slot];
-        float* od = hit_od + (size_t)slot * 8;
+        const float* od = hit_od + (size_t)slot * 8;
         const float o[3] = {od[0], od[1], od[2]}, d[3] = {od[3], od[4], od[5]};
-        const float far = od[6];
 
         // ---- 1. grid march -> edge list (uniform across the team; lane 0 writes)
         int ne = 0;
@@ -130,54 +142,38 @@ k_primary(const __grid_constant__ IaFrame p, const int* __restrict__ hit_rays, f
         }
         team.sync();
         int cur = 0;
-        IaQuery q;
-        // ---- 2. two rounds of importance resampling (models/intrinsic_avatar.py:1185-1238)
+        // ---- 2. two rounds of importance resampling (models/intrinsic_avatar.py:1185-1238); ONE query site:
+        //         round 0 queries every edge position (coarse_alpha_fn), round 1 the interval midpoints (alpha_fn)
+#pragma unroll 1
         for (int round = 0; round < 2; round++) {
             const float* vals = S.vals[cur];
             const uint8_t* fl = S.flags[cur];
-            if (round == 0) {
-                // coarse_alpha_fn: SDF at every edge
-                for (int e = 0; e < ne; e++) {
-                    float t = vals[e];
+            const int n_pts = round == 0 ? ne : ne - 1;
+#pragma unroll 1
+            for (int e = 0; e < n_pts; e++) {
+                const bool need = round == 0 || (fl[e] & 1);
+                float sd = 1e10f;
+                if (need) {
+                    const float t = round == 0 ? vals[e] : (vals[e] + vals[e + 1]) / 2.0f;
                     float x[3] = {o[0] + d[0] * t, o[1] + d[1] * t, o[2] + d[2] * t};
-                    ia_team_query<false>(team, p, wmlp, x, q);
+                    IaQuery q;
+                    ia_team_query<false>(team, p, wgeo, x, q);
                     c_q++; c_fetch += q.n_fetch; c_geo += q.n_valid;
-                    if (lane == 0) S.aux[e] = q.sdf;
+                    sd = q.sdf;
                 }
-                team.sync();
-                if (lane == 0) {
-                    // alpha from min(sdf_L, sdf_R), fixed dist; then weights = T * alpha
-                    float T = 1.f;
-                    for (int e = 0; e < ne; e++) {
-                        float a = 0.f;
-                        if ((fl[e] & 1) && e + 1 < ne) a = ia_alpha(fminf(S.aux[e], S.aux[e + 1]), step, p.beta);
-                        S.aux[e] = T * a;
-                        T *= (1.f - a);
-                    }
-                }
-            } else {
-                // alpha_fn: SDF at interval midpoints, dist = t_R - t_L
-                for (int e = 0; e + 1 < ne; e++) {
-                    float sd = 0.f;
-                    bool is_iv = (fl[e] & 1) != 0;
-                    if (is_iv) {
-                        float t = (vals[e] + vals[e + 1]) / 2.0f;
-                        float x[3] = {o[0] + d[0] * t, o[1] + d[1] * t, o[2] + d[2] * t};
-                        ia_team_query<false>(team, p, wmlp, x, q);
-                        c_q++; c_fetch += q.n_fetch; c_geo += q.n_valid;
-                        sd = q.sdf;
-                    }
-                    if (lane == 0) S.aux[e] = is_iv ? sd : 1e10f;
-                }
-                team.sync();
-                if (lane == 0) {
-                    float T = 1.f;
-                    for (int e = 0; e < ne; e++) {
-                        float a = 0.f;
-                        if ((fl[e] & 1) && e + 1 < ne) a = ia_alpha(S.aux[e], vals[e + 1] - vals[e], p.beta);
-                        S.aux[e] = T * a;
-                        T *= (1.f - a);
-                    }
+                if (lane == 0) S.aux[e] = sd;
+            }
+            team.sync();
+            if (lane == 0) {
+                // round 0: alpha from min(sdf_L, sdf_R) with the fixed step; round 1: midpoint sdf, dist = t_R - t_L
+                float T = 1.f;
+                for (int e = 0; e < ne; e++) {
+                    float a = 0.f;
+                    if ((fl[e] & 1) && e + 1 < ne)
+                        a = round == 0 ? ia_alpha(fminf(S.aux[e], S.aux[e + 1]), step, p.beta)
+                                       : ia_alpha(S.aux[e], vals[e + 1] - vals[e], p.beta);
+                    S.aux[e] = T * a;
+                    T *= (1.f - a);
                 }
             }
             team.sync();
@@ -188,7 +184,7 @@ k_primary(const __grid_constant__ IaFrame p, const int* __restrict__ hit_rays, f
             ne = n_out;
             cur ^= 1;
         }
-        // ---- 3. shading (rendering_with_normals_mats_sdf + rgb_normal_mats_alpha_fn)
+        // ---- 3. hand the final intervals to the shading kernel
         const float* vals = S.vals[cur];
         const uint8_t* fl = S.flags[cur];
         int n_iv = 0;
@@ -196,74 +192,127 @@ k_primary(const __grid_constant__ IaFrame p, const int* __restrict__ hit_rays, f
         int base = 0;
         if (lane == 0) base = atomicAdd(&work[IA_W_NSAMPLES], n_iv);
         base = team.shfl(base, 0);
-        bool pool_ok = (long long)base + n_iv <= sample_cap;
+        const bool pool_ok = (long long)base + n_iv <= sample_cap;
         if (!pool_ok) c_over++;
-        float view_w[3];
-        ia_dir_s2w(p, d, view_w);
-        float T = 1.f;
-        float a_rgb[3] = {0, 0, 0}, a_n[3] = {0, 0, 0}, a_alb[3] = {0, 0, 0}, a_r = 0, a_m = 0, a_op = 0, a_dep = 0;
-        int k = 0;
-        for (int e = 0; e + 1 < ne; e++) {
-            if (!(fl[e] & 1)) continue;
-            float ts = vals[e], te = vals[e + 1];
-            float tm = (ts + te) / 2.0f;
-            float x[3] = {o[0] + d[0] * tm, o[1] + d[1] * tm, o[2] + d[2] * tm};
-            ia_team_query<true>(team, p, wmlp, x, q);
-            c_qg++; c_fetch += q.n_fetch; c_geo += q.n_valid + (q.valid ? 1 : 0);
-            float alpha = ia_alpha(q.sdf, te - ts, p.beta);
-            float w = T * alpha;
-            T *= (1.f - alpha);
-            float nsm[3], nw[3], rgb[3] = {0, 0, 0}, mat[5] = {0, 0, 0, 0, 0};
-            ia_normalize(q.grad, nsm, 1e-6f);
-            ia_dir_s2w(p, q.grad, nw);
-            if (q.valid) {
-                ia_team_radiance<true>(team, p, wmlp, q.xc, q.feat, view_w, nw, rgb, mat);
-                c_rad++;
+        if (pool_ok && lane == 0) {
+            int k = 0;
+            for (int e = 0; e + 1 < ne; e++) {
+                if (!(fl[e] & 1)) continue;
+                samples[(size_t)base + k].ts = vals[e];
+                samples[(size_t)base + k].te = vals[e + 1];
+                aux[(size_t)base + k].slot = slot;
+                k++;
             }
-#pragma unroll
-            for (int c3 = 0; c3 < 3; c3++) {
-                a_rgb[c3] += w * rgb[c3];
-                a_n[c3] += w * nw[c3];
-                a_alb[c3] += w * mat[c3];
-            }
-            a_r += w * mat[3]; a_m += w * mat[4]; a_op += w; a_dep += w * tm;
-            if (pool_ok && lane == 0) {
-                IaSample s;
-                s.ts = ts; s.te = te; s.w = w; s.sdf = q.sdf;
-                s.n[0] = nsm[0]; s.n[1] = nsm[1]; s.n[2] = nsm[2];
-                s.albedo[0] = mat[0]; s.albedo[1] = mat[1]; s.albedo[2] = mat[2];
-                s.rough = mat[3]; s.metal = mat[4];
-                samples[(size_t)base + k] = s;
-            }
-            k++;
         }
-        c_samples += n_iv;
         if (lane == 0) {
             hit_info[slot * 2 + 0] = base;
             hit_info[slot * 2 + 1] = pool_ok ? n_iv : 0;
-            od[7] = a_op;
-            size_t r = (size_t)ray;
-            if (out.comp_rgb) { out.comp_rgb[r * 3] = a_rgb[0]; out.comp_rgb[r * 3 + 1] = a_rgb[1]; out.comp_rgb[r * 3 + 2] = a_rgb[2]; }
-            if (out.comp_normal) { out.comp_normal[r * 3] = a_n[0]; out.comp_normal[r * 3 + 1] = a_n[1]; out.comp_normal[r * 3 + 2] = a_n[2]; }
-            if (out.comp_albedo) { out.comp_albedo[r * 3] = a_alb[0]; out.comp_albedo[r * 3 + 1] = a_alb[1]; out.comp_albedo[r * 3 + 2] = a_alb[2]; }
-            if (out.opacity) out.opacity[r] = a_op;
-            if (out.depth) out.depth[r] = a_dep + (1.0f - a_op) * far;
-            if (out.comp_roughness) out.comp_roughness[r] = a_r;
-            if (out.comp_metallic) out.comp_metallic[r] = a_m;
-            if (out.num_samples) out.num_samples[r] = n_iv;
         }
+        c_samples += pool_ok ? n_iv : 0;
         team.sync();
     }
     if (lane == 0) {
         if (c_q) atomicAdd(&counters[IA_CNT_QUERIES], c_q);
-        if (c_qg) atomicAdd(&counters[IA_CNT_QUERIES_GRAD], c_qg);
-        if (c_rad) atomicAdd(&counters[IA_CNT_RAD_EVAL], c_rad);
         if (c_geo) atomicAdd(&counters[IA_CNT_GEO_EVAL], c_geo);
         if (c_over) atomicAdd(&counters[IA_CNT_OVERFLOW], c_over);
         if (c_samples) atomicAdd(&counters[IA_CNT_SAMPLES], c_samples);
+    }
+    if (c_fetch) atomicAdd(&counters[IA_CNT_BROYDEN_FETCH], c_fetch);
+}
+
+// rendering_with_normals_mats_sdf's per-sample part (rgb_normal_mats_alpha_fn, models/intrinsic_avatar.py:1066-1156)
+__global__ void __launch_bounds__(IA_PRIMARY_THREADS, 1)
+k_prim_shade(const __grid_constant__ IaFrame p, const float* __restrict__ hit_od, IaSample* __restrict__ samples,
+             IaSampleAux* __restrict__ aux, long long sample_cap, const int* __restrict__ work,
+             unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) float smem[];
+    float* wmlp = smem;
+    ia_stage(wmlp, p.mlp, IA_MLP_END);
+    __syncthreads();
+    Team team = cg::tiled_partition<IA_TEAM>(cg::this_thread_block());
+    const int lane = team.thread_rank();
+    const long long n = min((long long)work[IA_W_NSAMPLES], sample_cap);
+    const long long teams = (long long)gridDim.x * (blockDim.x / IA_TEAM);
+    unsigned c_qg = 0, c_fetch = 0, c_geo = 0, c_rad = 0;
+    for (long long i = (long long)blockIdx.x * (blockDim.x / IA_TEAM) + threadIdx.x / IA_TEAM; i < n; i += teams) {
+        const int slot = aux[i].slot;
+        const float* od = hit_od + (size_t)slot * 8;
+        const float o[3] = {od[0], od[1], od[2]}, d[3] = {od[3], od[4], od[5]};
+        const float ts = samples[i].ts, te = samples[i].te;
+        const float tm = (ts + te) / 2.0f;
+        float x[3] = {o[0] + d[0] * tm, o[1] + d[1] * tm, o[2] + d[2] * tm};
+        IaQuery q;
+        ia_team_query<true>(team, p, wmlp, x, q);
+        c_qg++; c_fetch += q.n_fetch; c_geo += q.n_valid + (q.valid ? 1 : 0);
+        float view_w[3], nsm[3], nw[3], rgb[3] = {0, 0, 0}, mat[5] = {0, 0, 0, 0, 0};
+        ia_dir_s2w(p, d, view_w);
+        ia_normalize(q.grad, nsm, 1e-6f);
+        ia_dir_s2w(p, q.grad, nw);
+        if (q.valid) {
+            ia_team_radiance<true>(team, p, wmlp, q.xc, q.feat, view_w, nw, rgb, mat);
+            c_rad++;
+        }
+        if (lane == 0) {
+            IaSample s;
+            s.ts = ts; s.te = te; s.w = 0.f; s.sdf = q.sdf;
+            s.n[0] = nsm[0]; s.n[1] = nsm[1]; s.n[2] = nsm[2];
+            s.albedo[0] = mat[0]; s.albedo[1] = mat[1]; s.albedo[2] = mat[2];
+            s.rough = mat[3]; s.metal = mat[4];
+            samples[i] = s;
+            IaSampleAux a;
+            a.rgb[0] = rgb[0]; a.rgb[1] = rgb[1]; a.rgb[2] = rgb[2];
+            a.nw[0] = nw[0]; a.nw[1] = nw[1]; a.nw[2] = nw[2];
+            a.slot = slot; a.pad = 0;
+            aux[i] = a;
+        }
+    }
+    if (lane == 0) {
+        if (c_qg) atomicAdd(&counters[IA_CNT_QUERIES_GRAD], c_qg);
+        if (c_rad) atomicAdd(&counters[IA_CNT_RAD_EVAL], c_rad);
+        if (c_geo) atomicAdd(&counters[IA_CNT_GEO_EVAL], c_geo);
         if (c_qg) atomicAdd(&counters[IA_CNT_SKIN_FETCH], c_qg);
     }
     if (c_fetch) atomicAdd(&counters[IA_CNT_BROYDEN_FETCH], c_fetch);
+}
+
+// weights (render_weight_from_alpha) and the 7 accumulations (models/volrend.py:952-1010), one thread per hit ray,
+// samples in ray order (same summation order as the fused first generation)
+__global__ void k_prim_accum(const __grid_constant__ IaFrame p, const int* __restrict__ hit_rays, float* __restrict__ hit_od,
+                             const int* __restrict__ hit_info, IaSample* __restrict__ samples,
+                             const IaSampleAux* __restrict__ aux, const int* __restrict__ work, ia_outputs out) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= work[IA_W_NHIT]) return;
+    const int base = hit_info[slot * 2], n_iv = hit_info[slot * 2 + 1];
+    float* od = hit_od + (size_t)slot * 8;
+    const float far = od[6];
+    float T = 1.f;
+    float a_rgb[3] = {0, 0, 0}, a_n[3] = {0, 0, 0}, a_alb[3] = {0, 0, 0}, a_r = 0, a_m = 0, a_op = 0, a_dep = 0;
+    for (int k = 0; k < n_iv; k++) {
+        IaSample& s = samples[(size_t)base + k];
+        const IaSampleAux& a = aux[(size_t)base + k];
+        const float ts = s.ts, te = s.te, tm = (ts + te) / 2.0f;
+        const float alpha = ia_alpha(s.sdf, te - ts, p.beta);
+        const float w = T * alpha;
+        T *= (1.f - alpha);
+#pragma unroll
+        for (int c3 = 0; c3 < 3; c3++) {
+            a_rgb[c3] += w * a.rgb[c3];
+            a_n[c3] += w * a.nw[c3];
+            a_alb[c3] += w * s.albedo[c3];
+        }
+        a_r += w * s.rough; a_m += w * s.metal; a_op += w; a_dep += w * tm;
+        s.w = w;
+    }
+    od[7] = a_op;
+    const size_t r = (size_t)hit_rays[slot];
+    if (out.comp_rgb) { out.comp_rgb[r * 3] = a_rgb[0]; out.comp_rgb[r * 3 + 1] = a_rgb[1]; out.comp_rgb[r * 3 + 2] = a_rgb[2]; }
+    if (out.comp_normal) { out.comp_normal[r * 3] = a_n[0]; out.comp_normal[r * 3 + 1] = a_n[1]; out.comp_normal[r * 3 + 2] = a_n[2]; }
+    if (out.comp_albedo) { out.comp_albedo[r * 3] = a_alb[0]; out.comp_albedo[r * 3 + 1] = a_alb[1]; out.comp_albedo[r * 3 + 2] = a_alb[2]; }
+    if (out.opacity) out.opacity[r] = a_op;
+    if (out.depth) out.depth[r] = a_dep + (1.0f - a_op) * far;
+    if (out.comp_roughness) out.comp_roughness[r] = a_r;
+    if (out.comp_metallic) out.comp_metallic[r] = a_m;
+    if (out.num_samples) out.num_samples[r] = n_iv;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -599,7 +648,7 @@ static int ia_ws_reserve(ia_ctx* c, int64_t n_rays, int spp, bool need_pbr) {
     }
     int64_t want_samples = std::max<int64_t>(n_rays * 24, 1 << 16);
     if (want_samples > c->ws_samples) {
-        if (ia_realloc(&c->d_samples, (size_t)want_samples)) return IA_ECUDA;
+        if (ia_realloc(&c->d_samples, (size_t)want_samples) || ia_realloc(&c->d_samples_aux, (size_t)want_samples)) return IA_ECUDA;
         c->ws_samples = want_samples;
     }
     if (need_pbr) {
@@ -638,12 +687,18 @@ extern "C" int ia_render(ia_ctx* c, const float* d_rays, int64_t n_rays, int64_t
     IA_STAGE_END(c, IA_STAGE_SETUP, st, 1);
     IA_LAUNCH_CHECK();
     {
-        size_t sm = IA_MLP_END * sizeof(float) + (IA_PRIMARY_THREADS / IA_TEAM) * sizeof(IaPrimarySmem);
-        IA_CHECK_CUDA(cudaFuncSetAttribute(k_primary, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        size_t sm1 = IA_GEO_END * sizeof(float) + (IA_PRIMARY_THREADS / IA_TEAM) * sizeof(IaPrimarySmem);
+        size_t sm2 = IA_MLP_END * sizeof(float);
+        IA_CHECK_CUDA(cudaFuncSetAttribute(k_prim_edges, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+        IA_CHECK_CUDA(cudaFuncSetAttribute(k_prim_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
         IA_STAGE_BEGIN(c, IA_STAGE_PRIMARY, st);
-        k_primary<<<c->n_sm, IA_PRIMARY_THREADS, sm, st>>>(c->f, c->d_hit_rays, c->d_hit_od, c->d_hit_info, c->d_samples,
-                                                            c->ws_samples, c->d_work, *out, c->d_counters);
-        IA_STAGE_END(c, IA_STAGE_PRIMARY, st, 1);
+        k_prim_edges<<<c->n_sm * 2, IA_PRIMARY_THREADS, sm1, st>>>(c->f, c->d_hit_od, c->d_hit_info, c->d_samples, c->d_samples_aux,
+                                                                   c->ws_samples, c->d_work, c->d_counters);
+        k_prim_shade<<<c->n_sm, IA_PRIMARY_THREADS, sm2, st>>>(c->f, c->d_hit_od, c->d_samples, c->d_samples_aux, c->ws_samples,
+                                                                   c->d_work, c->d_counters);
+        k_prim_accum<<<(unsigned)((n_rays + 127) / 128), 128, 0, st>>>(c->f, c->d_hit_rays, c->d_hit_od, c->d_hit_info, c->d_samples,
+                                                                       c->d_samples_aux, c->d_work, *out);
+        IA_STAGE_END(c, IA_STAGE_PRIMARY, st, 3);
         IA_LAUNCH_CHECK();
     }
     IA_CHECK_CUDA(cudaMemcpyAsync(c->d_counters + IA_CNT_PRIMARY_BASE, c->d_counters, IA_CNT_PRIMARY_BASE * sizeof(unsigned long long),
