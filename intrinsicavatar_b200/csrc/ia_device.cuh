@@ -109,6 +109,22 @@ __device__ __forceinline__ void ia_fetch_J(const IaFrame& p, float gx, float gy,
             J[8] = fmaf(cc.x, w, J[8]); J[9] = fmaf(cc.y, w, J[9]); J[10] = fmaf(cc.z, w, J[10]); J[11] = fmaf(cc.w, w, J[11]);
         }
     }
+#elif IA_FETCH_MODE == 3
+    const int W = p.W, H = p.H, D = p.D;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        int xi = cn.x0 + (c & 1), yi = cn.y0 + ((c >> 1) & 1), zi = cn.z0 + (c >> 2);
+        float w = ((c & 1) ? cn.wx1 : cn.wx0) * ((c & 2) ? cn.wy1 : cn.wy0) * ((c & 4) ? cn.wz1 : cn.wz0);
+        if (xi >= 0 && xi < W && yi >= 0 && yi < H && zi >= 0 && zi < D) {
+            const size_t v = (size_t)((zi * H + yi) * W + xi);
+            float r[8];
+            ia_ld256(p.voxel_J + v * 2, r);
+            float4 cc = __ldg(p.voxel_JB + v);
+#pragma unroll
+            for (int k = 0; k < 8; k++) J[k] = fmaf(r[k], w, J[k]);
+            J[8] = fmaf(cc.x, w, J[8]); J[9] = fmaf(cc.y, w, J[9]); J[10] = fmaf(cc.z, w, J[10]); J[11] = fmaf(cc.w, w, J[11]);
+        }
+    }
 #else
     ia_gather_half(p, cn, 0, J);
     ia_gather_half(p, cn, 1, J + 6);

@@ -236,6 +236,7 @@ extern "C" int ia_set_lbs_voxels(ia_ctx* c, const float* d_lbs_voxel, int D, int
     for (int i = 0; i < 3; i++) { c->f.off[i] = off[i]; c->f.scl[i] = scl[i]; }
     c->f.lbs_w = c->d_lbs_w;
     c->f.voxel_J = c->d_voxel_J;
+    c->f.voxel_JB = c->d_voxel_J + 2 * nvox;
     c->have_lbs = true;
     return IA_OK;
 }
@@ -260,7 +261,12 @@ __global__ void k_precompute(const __grid_constant__ IaFrame p, float4* __restri
         J[k] = s;
     }
     float4* o = voxel_J + (size_t)v * IA_VOXEL_F4;
-#if IA_FETCH_MODE == 0
+#if IA_FETCH_MODE == 3
+    voxel_J[(size_t)v * 2 + 0] = make_float4(J[0], J[1], J[2], J[3]);
+    voxel_J[(size_t)v * 2 + 1] = make_float4(J[4], J[5], J[6], J[7]);
+    voxel_J[(size_t)nvox * 2 + v] = make_float4(J[8], J[9], J[10], J[11]);
+    (void)o;
+#elif IA_FETCH_MODE == 0
     o[0] = make_float4(J[0], J[1], J[2], J[3]);
     o[1] = make_float4(J[4], J[5], J[6], J[7]);
     o[2] = make_float4(J[8], J[9], J[10], J[11]);
@@ -311,9 +317,16 @@ extern "C" int ia_set_render_config(ia_ctx* c, const float* aabb, int n_per_ray,
 __global__ void k_op_precompute_out(const float4* __restrict__ vj, float* __restrict__ out, int nvox) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nvox) return;
+#if IA_FETCH_MODE == 3
+    const float* sa = reinterpret_cast<const float*>(vj + (size_t)v * 2);
+    const float* sb = reinterpret_cast<const float*>(vj + (size_t)nvox * 2 + v);
+#pragma unroll
+    for (int k = 0; k < 12; k++) out[(size_t)k * nvox + v] = k < 8 ? sa[k] : sb[k - 8];
+#else
     const float* s = reinterpret_cast<const float*>(vj + (size_t)v * IA_VOXEL_F4);
 #pragma unroll
     for (int k = 0; k < 12; k++) out[(size_t)k * nvox + v] = s[IA_VOXEL_F4 == 3 ? k : (k < 6 ? k : k + 2)];
+#endif
 }
 
 extern "C" int ia_op_precompute(ia_ctx* c, float* d_out, void* stream) {

@@ -15,10 +15,11 @@ namespace cg = cooperative_groups;
 //   0: 48-byte voxels, 3 x LDG.128 per corner, one lane per chain
 //   1: 64-byte padded voxels, 2 x LDG.256 per corner, one lane per chain
 //   2: 64-byte padded voxels, lane pairs fetch one 32-byte half each for both their chains
+//   3: split planes, no padding: A[v] = J[0..7] (32 B, one aligned sector, LDG.256), B[v] = J[8..11] (LDG.128)
 #ifndef IA_FETCH_MODE
 #define IA_FETCH_MODE 0
 #endif
-#if IA_FETCH_MODE == 0
+#if IA_FETCH_MODE == 0 || IA_FETCH_MODE == 3
 #define IA_VOXEL_F4 3  // float4 per voxel of voxel_J
 #else
 #define IA_VOXEL_F4 4  // 12 floats padded to 64 bytes: half 0 = J[0..5],0,0 ; half 1 = J[6..11],0,0
@@ -53,7 +54,8 @@ struct IaFrame {
     int init_bones[IA_N_INIT];
     float off[3], scl[3];       // reference offset_kernel / scale_kernel
     int D, H, W;                // LBS voxel grid (32,128,128)
-    const float4* voxel_J;      // [D*H*W][4] float4  : blended 3x4 per voxel, channels-last, two 32-B halves
+    const float4* voxel_J;      // blended 3x4 per voxel, channels-last; layout per IA_FETCH_MODE
+    const float4* voxel_JB;     // IA_FETCH_MODE 3: plane B (= voxel_J + 2 * D*H*W)
     const float4* lbs_w;        // [D*H*W][6] float4  : 24 skinning weights per voxel, channels-last
     // --- canonical fields
     const float2* geo_hash;

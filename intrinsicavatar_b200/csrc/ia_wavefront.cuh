@@ -248,9 +248,9 @@ __device__ __forceinline__ void wf_broyden_phase_1lane(const IaFrame& p, WfShare
 // Values every lane of the group needs (residual n, the Ji columns, c = Ji^T u) are exchanged with
 // shuffles; each scalar is computed by exactly the expression of the one-thread reference kernel.
 // The trip loop is warp-uniform; finished groups are re-filled from the task counter at the trip end.
-__device__ __forceinline__ void wf_broyden_phase(const IaFrame& p, WfShared& S, int n_q, unsigned& c_fetch) {
+__device__ __forceinline__ void wf_broyden_phase(const IaFrame& p, WfShared& S, unsigned& c_fetch) {
     const unsigned FULL = 0xffffffffu;
-    const int n_tasks = n_q * IA_N_INIT;
+    const int n_tasks = S.n_btask;
     const int lane = threadIdx.x & 31;
     const bool lane_ok = lane < 30;
     const int grp = lane / 3, r = lane - grp * 3;
@@ -285,8 +285,8 @@ __device__ __forceinline__ void wf_broyden_phase(const IaFrame& p, WfShared& S, 
         float ix = -100.f, iy = -100.f, iz = -100.f;  // idle group: far outside the grid, no loads
         if (act) {
             if (fresh) {
-                c = task / n_q;                       // bone-major: neighbouring groups = same bone, neighbouring rays
-                q = S.qlist[task - c * n_q];
+                const int tk = S.btask[task];
+                q = tk >> 4; c = tk & 15;
                 xd0 = S.qx[0][q]; xd1 = S.qx[1][q]; xd2 = S.qx[2][q];
                 const float* T = S.tfs13 + c * 12;
                 float d0 = xd0 - T[3], d1 = xd1 - T[7], d2 = xd2 - T[11];
@@ -639,7 +639,9 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
         __syncthreads();
         wf_broyden_phase_1lane(p, S, c_fetch);
 #else
-        wf_broyden_phase(p, S, n_q, c_fetch);
+        wf_prune_phase(p, S, n_q, c_skip);
+        __syncthreads();
+        wf_broyden_phase(p, S, c_fetch);
 #endif
         __syncthreads();
         wf_filter_phase(S, n_q);
