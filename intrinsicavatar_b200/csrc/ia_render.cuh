@@ -5,9 +5,7 @@
 //                     (deform + geometry w/ gradient + radiance + material) -> accumulate; emits
 //                     the per-ray shading samples for the PBR stage
 //   k_resample      : warp-per-hit-ray `ray_resampling` (spp shading samples, zero-crossing snap)
-//   k_shade         : persistent tiles of 1024 shading samples: light pick, cosine test,
-//                     compaction of live secondary rays into a shared queue, team-per-ray lazy
-//                     secondary tracing, BRDF, accumulation
+//   k_shade_wf      : wavefront secondary-ray integrator (ia_wavefront.cuh)
 //   k_composite     : background composite + sRGB
 #pragma once
 
@@ -480,133 +478,6 @@ __global__ void __launch_bounds__(256) k_resample(const int* __restrict__ hit_in
 }
 
 // ------------------------------------------------------------------------------------------------
-template <bool GI>
-__global__ void __launch_bounds__(IA_SHADE_THREADS, 2)
-k_shade(const __grid_constant__ IaFrame p, const int* __restrict__ hit_rays, const float* __restrict__ hit_od,
-        const IaSample* __restrict__ samples, const float* __restrict__ rs_t, const int* __restrict__ rs_src,
-        const float* __restrict__ rs_w, int* __restrict__ work, int spp, long long ray_index_base, uint32_t seed,
-        const float* __restrict__ light_dir_s, const float* __restrict__ light_em, const float* __restrict__ light_pdf,
-        float* __restrict__ acc6, unsigned long long* __restrict__ counters) {
-    extern __shared__ __align__(16) float smem[];
-    const int n_w = GI ? IA_RAD_END : IA_GEO_END;
-    float* wmlp = smem;
-    uint32_t* occ = reinterpret_cast<uint32_t*>(smem + n_w);
-    const int occ_words = p.occ_res * p.occ_res * p.occ_res / 32;
-    float* pix_acc = reinterpret_cast<float*>(occ + occ_words);                 // [IA_TILE_PIX][6]
-    uint16_t* queue = reinterpret_cast<uint16_t*>(pix_acc + IA_TILE_PIX * 6);   // [IA_TILE]
-    __shared__ int s_qcount, s_qhead, s_tile;
-    ia_stage(wmlp, p.mlp, n_w);
-    for (int i = threadIdx.x; i < occ_words; i += blockDim.x) occ[i] = p.occ_bits[i];
-    __syncthreads();
-    Team team = cg::tiled_partition<IA_TEAM>(cg::this_thread_block());
-    const int lane = team.thread_rank();
-    const long long n_total = (long long)work[IA_W_NHIT] * spp;
-    const long long n_tiles = (n_total + IA_TILE - 1) / IA_TILE;
-    IaTraceCounters cnt = {0, 0, 0, 0, 0, 0};
-    unsigned c_rays = 0;
-
-    while (true) {
-        if (threadIdx.x == 0) {
-            s_tile = atomicAdd(&work[IA_W_TILE_NEXT], 1);
-            s_qcount = 0;
-            s_qhead = 0;
-        }
-        for (int i = threadIdx.x; i < IA_TILE_PIX * 6; i += blockDim.x) pix_acc[i] = 0.f;
-        __syncthreads();
-        const long long tile = s_tile;
-        if (tile >= n_tiles) break;
-        const long long s0 = tile * IA_TILE;
-        const int first_slot = (int)(s0 / spp);
-        // ---- phase 1: per-sample cosine test, compaction of live rays
-        for (int i = threadIdx.x; i < IA_TILE; i += blockDim.x) {
-            long long s = s0 + i;
-            if (s >= n_total) break;
-            int slot = (int)(s / spp), j = (int)(s % spp);
-            int src = rs_src[s];
-            float w = rs_w[s];
-            float* pa = pix_acc + (slot - first_slot) * 6;
-            if (src < 0) {
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    atomicAdd(&pa[k], w * p.background[k]);
-                    atomicAdd(&pa[3 + k], w * p.background[k]);
-                }
-                continue;
-            }
-            const IaSample& sm = samples[src];
-            uint32_t key = ia_pixel_key(seed, (uint64_t)(ray_index_base + hit_rays[slot]));
-            uint32_t kk = ia_permute((uint32_t)j, (uint32_t)spp, key);
-            const float* wo = light_dir_s + kk * 3;
-            float cosv = sm.n[0] * wo[0] + sm.n[1] * wo[1] + sm.n[2] * wo[2];
-            if (cosv > 1e-6f) {
-                int qi = atomicAdd(&s_qcount, 1);
-                queue[qi] = (uint16_t)i;
-            }
-        }
-        __syncthreads();
-        const int qn = s_qcount;
-        // ---- phase 2: teams pull live secondary rays
-        while (true) {
-            int qi = 0;
-            if (lane == 0) qi = atomicAdd(&s_qhead, 1);
-            qi = team.shfl(qi, 0);
-            if (qi >= qn) break;
-            const int i = queue[qi];
-            const long long s = s0 + i;
-            const int slot = (int)(s / spp), j = (int)(s % spp);
-            const IaSample sm = samples[rs_src[s]];
-            const float w = rs_w[s], t = rs_t[s];
-            const float* od = hit_od + (size_t)slot * 8;
-            const float d[3] = {od[3], od[4], od[5]};
-            const float pos[3] = {od[0] + d[0] * t, od[1] + d[1] * t, od[2] + d[2] * t};
-            uint32_t key = ia_pixel_key(seed, (uint64_t)(ray_index_base + hit_rays[slot]));
-            uint32_t kk = ia_permute((uint32_t)j, (uint32_t)spp, key);
-            const float wo[3] = {light_dir_s[kk * 3], light_dir_s[kk * 3 + 1], light_dir_s[kk * 3 + 2]};
-            float T, ind[3];
-            ia_team_trace<GI>(team, p, wmlp, wmlp, occ, pos, wo, T, ind, cnt);
-            c_rays++;
-            if (lane == 0) {
-                float tr = fminf(fmaxf(T, 0.f), 1.f);
-                const float wi[3] = {-d[0], -d[1], -d[2]};
-                float diff, spec[3];
-                ia_brdf_multilobe(wi, sm.n, wo, sm.rough, sm.albedo, sm.metal, diff, spec);
-                bool lit = tr > 0.0f;
-                float pdf = lit ? light_pdf[kk] : 1.0f;
-                if (!(pdf > 0)) pdf = 1.0f;
-                float* pa = pix_acc + (slot - (int)(s0 / spp)) * 6;
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    float em = lit ? light_em[kk * 3 + k] : 0.f;
-                    float Li = em * tr;
-                    if (GI) Li += ind[k];
-                    float Ld = Li * diff / pdf, Ls = Li * spec[k] / pdf;
-                    float kd = (1.0f - sm.metal) * sm.albedo[k];
-                    atomicAdd(&pa[k], w * (kd * Ld + Ls));
-                    atomicAdd(&pa[3 + k], w * (Ld + Ls));
-                }
-            }
-        }
-        __syncthreads();
-        // ---- flush the tile's pixel accumulators
-        const int last_slot = (int)((min(s0 + IA_TILE, n_total) - 1) / spp);
-        for (int i = threadIdx.x; i < (last_slot - first_slot + 1) * 6; i += blockDim.x) {
-            int slot = first_slot + i / 6;
-            atomicAdd(&acc6[(size_t)hit_rays[slot] * 6 + i % 6], pix_acc[i]);
-        }
-        __syncthreads();
-    }
-    if (lane == 0) {
-        if (cnt.q) atomicAdd(&counters[IA_CNT_QUERIES], cnt.q);
-        if (cnt.qg) atomicAdd(&counters[IA_CNT_QUERIES_GRAD], cnt.qg);
-        if (cnt.geo) atomicAdd(&counters[IA_CNT_GEO_EVAL], cnt.geo);
-        if (cnt.rad) atomicAdd(&counters[IA_CNT_RAD_EVAL], cnt.rad);
-        if (cnt.skin) atomicAdd(&counters[IA_CNT_SKIN_FETCH], cnt.skin);
-        if (c_rays) atomicAdd(&counters[IA_CNT_SECONDARY_RAYS], c_rays);
-    }
-    if (cnt.fetch) atomicAdd(&counters[IA_CNT_BROYDEN_FETCH], cnt.fetch);
-}
-
-// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float ia_srgb(float f) {
     float v = f <= 0.0031308f ? f * 12.92f : powf(fmaxf(f, 0.0031308f), 1.0f / 2.4f) * 1.055f - 0.055f;
     return fminf(fmaxf(v, 0.f), 1.f);
@@ -713,22 +584,22 @@ extern "C" int ia_render(ia_ctx* c, const float* d_rays, int64_t n_rays, int64_t
         size_t sm = (gi ? IA_RAD_END : IA_GEO_END) * sizeof(float) + occ_bytes + IA_TILE_PIX * 6 * sizeof(float) +
                     IA_TILE * sizeof(uint16_t);
         IA_STAGE_BEGIN(c, IA_STAGE_SHADE, st);
-        if (gi) {
-            IA_CHECK_CUDA(cudaFuncSetAttribute(k_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            k_shade<true><<<c->n_sm * 2, IA_SHADE_THREADS, sm, st>>>(
-                c->f, c->d_hit_rays, c->d_hit_od, c->d_samples, c->d_rs_t, c->d_rs_src, c->d_rs_w, c->d_work, c->spp,
-                ray_index_base, seed, c->d_light_dir_s, c->d_light_em, c->d_light_pdf, c->d_acc, c->d_counters);
-        } else {
-            // wavefront integrator: one persistent 512-thread CTA per SM
+        {
+            // wavefront integrator: one persistent CTA per SM
             IA_REQUIRE((long long)n_rays * c->spp < (1ll << 32), IA_EINVAL, "ia_render: n_rays * spp must be < 2^32");
             WfShadePolicy pol;
             pol.p = nullptr; pol.hit_rays = c->d_hit_rays; pol.hit_od = c->d_hit_od; pol.samples = c->d_samples;
             pol.rs_t = c->d_rs_t; pol.rs_src = c->d_rs_src; pol.rs_w = c->d_rs_w; pol.work = c->d_work; pol.spp = c->spp;
             pol.ray_index_base = ray_index_base; pol.seed = seed; pol.light_dir_s = c->d_light_dir_s;
-            pol.light_em = c->d_light_em; pol.light_pdf = c->d_light_pdf; pol.acc6 = c->d_acc; pol.n_total = 0;
-            IA_CHECK_CUDA(cudaFuncSetAttribute(k_shade_wf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WfShared)));
+            pol.light_em = c->d_light_em; pol.light_pdf = c->d_light_pdf; pol.acc6 = c->d_acc; pol.n_total = 0; pol.gi = gi;
             if (int e = ia_wf_scratch(c)) return e;
-            k_shade_wf<<<c->n_sm, WF_THREADS, sizeof(WfShared), st>>>(c->f, pol, c->d_wf_scratch, c->d_counters);
+            if (gi) {
+                IA_CHECK_CUDA(cudaFuncSetAttribute(k_shade_wf<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_BYTES(true)));
+                k_shade_wf<true><<<c->n_sm, WF_THREADS, WF_SMEM_BYTES(true), st>>>(c->f, pol, c->d_wf_scratch, c->d_counters);
+            } else {
+                IA_CHECK_CUDA(cudaFuncSetAttribute(k_shade_wf<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_BYTES(false)));
+                k_shade_wf<false><<<c->n_sm, WF_THREADS, WF_SMEM_BYTES(false), st>>>(c->f, pol, c->d_wf_scratch, c->d_counters);
+            }
         }
         IA_STAGE_END(c, IA_STAGE_SHADE, st, 1);
         IA_LAUNCH_CHECK();
@@ -913,62 +784,25 @@ extern "C" int ia_op_unpack_info(ia_ctx* c, const int32_t* d_packed, int64_t n_r
     return IA_OK;
 }
 
-template <bool GI>
-__global__ void __launch_bounds__(256, 2) k_op_secondary(const __grid_constant__ IaFrame p, const float* __restrict__ ro,
-                                                         const float* __restrict__ rd, long long n, float* __restrict__ T_out,
-                                                         float* __restrict__ rgb_out, unsigned long long* __restrict__ counters) {
-    extern __shared__ __align__(16) float smem[];
-    const int n_w = GI ? IA_RAD_END : IA_GEO_END;
-    ia_stage(smem, p.mlp, n_w);
-    uint32_t* occ = reinterpret_cast<uint32_t*>(smem + n_w);
-    const int occ_words = p.occ_res * p.occ_res * p.occ_res / 32;
-    for (int i = threadIdx.x; i < occ_words; i += blockDim.x) occ[i] = p.occ_bits[i];
-    __syncthreads();
-    Team team = cg::tiled_partition<IA_TEAM>(cg::this_thread_block());
-    long long teams = (long long)gridDim.x * (blockDim.x / IA_TEAM);
-    IaTraceCounters cnt = {0, 0, 0, 0, 0, 0};
-    unsigned c_rays = 0;
-    for (long long i = (long long)blockIdx.x * (blockDim.x / IA_TEAM) + threadIdx.x / IA_TEAM; i < n; i += teams) {
-        float o[3] = {ro[i * 3], ro[i * 3 + 1], ro[i * 3 + 2]}, d[3] = {rd[i * 3], rd[i * 3 + 1], rd[i * 3 + 2]};
-        float T, rgb[3];
-        ia_team_trace<GI>(team, p, smem, smem, occ, o, d, T, rgb, cnt);
-        c_rays++;
-        if (team.thread_rank() == 0) {
-            T_out[i] = T;
-            if (rgb_out) { rgb_out[i * 3] = rgb[0]; rgb_out[i * 3 + 1] = rgb[1]; rgb_out[i * 3 + 2] = rgb[2]; }
-        }
-    }
-    if (team.thread_rank() == 0) {
-        if (cnt.q) atomicAdd(&counters[IA_CNT_QUERIES], cnt.q);
-        if (cnt.qg) atomicAdd(&counters[IA_CNT_QUERIES_GRAD], cnt.qg);
-        if (cnt.geo) atomicAdd(&counters[IA_CNT_GEO_EVAL], cnt.geo);
-        if (cnt.rad) atomicAdd(&counters[IA_CNT_RAD_EVAL], cnt.rad);
-        if (c_rays) atomicAdd(&counters[IA_CNT_SECONDARY_RAYS], c_rays);
-    }
-    if (cnt.fetch) atomicAdd(&counters[IA_CNT_BROYDEN_FETCH], cnt.fetch);
-}
-
 extern "C" int ia_op_secondary(ia_ctx* c, const float* d_o, const float* d_d, int64_t n, int gi, float* d_T, float* d_rgb,
                                void* stream) {
     IA_REQUIRE(c && d_o && d_d && d_T, IA_EINVAL, "ia_op_secondary: NULL argument");
     IA_REQUIRE(c->have_fields && c->have_pose && c->have_occ && c->have_cfg, IA_ESTATE, "ia_op_secondary: state not set");
     if (n == 0) return IA_OK;
-    size_t occ_bytes = (size_t)c->f.occ_res * c->f.occ_res * c->f.occ_res / 8;
-    size_t sm = (gi ? IA_RAD_END : IA_GEO_END) * sizeof(float) + occ_bytes;
-    int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 15) / 16, (int64_t)c->n_sm * 2));
-    if (gi) {
-        IA_CHECK_CUDA(cudaFuncSetAttribute(k_op_secondary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        k_op_secondary<true><<<blocks, 256, sm, (cudaStream_t)stream>>>(c->f, d_o, d_d, n, d_T, d_rgb, c->d_counters);
-    } else {
+    {
         IA_REQUIRE(n < (1ll << 32), IA_EINVAL, "ia_op_secondary: too many rays");
         IA_CHECK_CUDA(cudaMemsetAsync(c->d_work, 0, 8 * sizeof(int), (cudaStream_t)stream));
         WfRaysPolicy pol;
-        pol.ro = d_o; pol.rd = d_d; pol.n = n; pol.T_out = d_T; pol.work = c->d_work;
-        if (d_rgb) IA_CHECK_CUDA(cudaMemsetAsync(d_rgb, 0, (size_t)n * 3 * sizeof(float), (cudaStream_t)stream));
-        IA_CHECK_CUDA(cudaFuncSetAttribute(k_rays_wf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WfShared)));
-        int wf_blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + WF_FEED - 1) / WF_FEED, (int64_t)c->n_sm));
+        pol.ro = d_o; pol.rd = d_d; pol.n = n; pol.T_out = d_T; pol.rgb_out = d_rgb; pol.work = c->d_work;
         if (int e = ia_wf_scratch(c)) return e;
-        k_rays_wf<<<wf_blocks, WF_THREADS, sizeof(WfShared), (cudaStream_t)stream>>>(c->f, pol, c->d_wf_scratch, c->d_counters);
+        int wf_blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + WF_FEED - 1) / WF_FEED, (int64_t)c->n_sm));
+        if (gi) {
+            IA_CHECK_CUDA(cudaFuncSetAttribute(k_rays_wf<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_BYTES(true)));
+            k_rays_wf<true><<<wf_blocks, WF_THREADS, WF_SMEM_BYTES(true), (cudaStream_t)stream>>>(c->f, pol, c->d_wf_scratch, c->d_counters);
+        } else {
+            IA_CHECK_CUDA(cudaFuncSetAttribute(k_rays_wf<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_BYTES(false)));
+            k_rays_wf<false><<<wf_blocks, WF_THREADS, WF_SMEM_BYTES(false), (cudaStream_t)stream>>>(c->f, pol, c->d_wf_scratch, c->d_counters);
+        }
     }
     IA_LAUNCH_CHECK();
     return IA_OK;

@@ -32,13 +32,19 @@
 #endif
 #define WF_QCAP 2048   // ring capacity (power of two)
 #define WF_FEED 1024   // items examined per feed step
-#define WF_NST 33      // state words per ray
+#define WF_NST 36      // state words per ray
 #ifndef WF_STATE_GLOBAL
 #define WF_STATE_GLOBAL 1
 #endif
-#define WF_SCRATCH_BYTES (WF_R * IA_N_INIT * 3 * 4 + 2 * WF_R * IA_N_INIT * 2 + WF_NST * WF_R * 4)  // per CTA
+// per-CTA scratch: roots [R][13][3] f32, their SDFs [R][13] f32, 2 task lists [R*13] u16, GI task list [R] uint2, ray state
+#define WF_OFF_CSDF (WF_R * IA_N_INIT * 3 * 4)
+#define WF_OFF_GTASK (WF_OFF_CSDF + WF_R * IA_N_INIT * 4)
+#define WF_OFF_BTASK (WF_OFF_GTASK + WF_R * IA_N_INIT * 2)
+#define WF_OFF_GITASK (WF_OFF_BTASK + WF_R * IA_N_INIT * 2)
+#define WF_OFF_STATE (WF_OFF_GITASK + WF_R * 8)
+#define WF_SCRATCH_BYTES (WF_OFF_STATE + WF_NST * WF_R * 4)
 
-enum { WF_IDLE = 0, WF_FIRST = 1, WF_SEARCH = 2, WF_CDF = 3, WF_FINE = 4 };
+enum { WF_IDLE = 0, WF_FIRST = 1, WF_SEARCH = 2, WF_CDF = 3, WF_FINE = 4, WF_GIWAIT = 5 };
 enum { WF_ACT_NEXT = 0, WF_ACT_CDF = 1, WF_ACT_FINE_START = 2, WF_ACT_FINISH = 3 };
 
 // state word indices
@@ -62,10 +68,10 @@ enum { WF_ACT_NEXT = 0, WF_ACT_CDF = 1, WF_ACT_FINE_START = 2, WF_ACT_FINISH = 3
 #define WS_CDFNEXT 25
 #define WS_CDFU 26
 #define WS_TPL 27     // 27..31
-#define WS_SPARE 32
+#define WS_IND 32      // 32..34 indirect radiance accumulated over the fine samples (global illumination)
 
 struct WfShared {
-    float w_geo[IA_GEO_END];
+    float* w;               // MLP weights staged behind this struct (geometry only, or geometry + radiance for GI)
     float tfs13[IA_N_INIT * 12];
     IaLevel lvl[IA_N_LEVELS];
 #if WF_STATE_GLOBAL
@@ -79,7 +85,10 @@ struct WfShared {
     uint2 ring[WF_QCAP];
     // CTA-private scratch in GLOBAL memory (low traffic; keeping it out of shared memory leaves the
     // L1 carve-out to the voxel_J gathers, which is what the kernel is bound by -- DESIGN.md):
-    float* cand;            // [WF_R][13][3] Broyden roots; [.][.][0] is overwritten with the SDF
+    float* cand;            // [WF_R][13][3] Broyden roots
+    float* csdf;            // [WF_R][13] SDF of the kept roots
+    uint2* gitask;          // [WF_R] GI: (slot | root << 16, weight bits) of the fine samples consumed this round
+    int n_gitask;
     unsigned short* gtask;  // [WF_R * 13] geometry task list
     unsigned short* btask;  // [WF_R * 13] Broyden task list (pruned)
     int n_btask;
@@ -393,19 +402,49 @@ __device__ __forceinline__ void wf_geometry_phase(const IaFrame& p, WfShared& S,
     const int n_teams = blockDim.x / IA_TEAM;
     for (int k = threadIdx.x / IA_TEAM; k < n; k += n_teams) {
         const int tk = S.gtask[k];
-        float* cd = S.cand + ((tk >> 4) * IA_N_INIT + (tk & 15)) * 3;
+        const int ci = (tk >> 4) * IA_N_INIT + (tk & 15);
+        const float* cd = S.cand + ci * 3;
         const float xc[3] = {cd[0], cd[1], cd[2]};
-        float s = ia_team_geometry<false>(team, p, S.w_geo, xc, nullptr, nullptr, S.lvl);
-        team.sync();
-        if (team.thread_rank() == 0) { cd[0] = s; c_geo++; }
+        float s = ia_team_geometry<false>(team, p, S.w, xc, nullptr, nullptr, S.lvl);
+        if (team.thread_rank() == 0) { S.csdf[ci] = s; c_geo++; }
+    }
+}
+
+// GI: radiance at the arg-min root of every fine sample consumed this round (rgb_alpha_fn,
+// models/intrinsic_avatar.py:430-456): geometry with gradient + feature, blended forward rotation, radiance MLP.
+__device__ __forceinline__ void wf_gi_phase(const IaFrame& p, WfShared& S, unsigned& c_qg, unsigned& c_geo, unsigned& c_rad) {
+    Team team = cg::tiled_partition<IA_TEAM>(cg::this_thread_block());
+    const int n = S.n_gitask;
+    const int n_teams = blockDim.x / IA_TEAM;
+    for (int k = threadIdx.x / IA_TEAM; k < n; k += n_teams) {
+        const uint2 tk = S.gitask[k];
+        const int t = tk.x & 0xffffu, c = tk.x >> 16;
+        const float w = __uint_as_float(tk.y);
+        const float* cd = S.cand + (t * IA_N_INIT + c) * 3;
+        const float xc[3] = {cd[0], cd[1], cd[2]};
+        const float d[3] = {S.st[WS_D][t], S.st[WS_D + 1][t], S.st[WS_D + 2][t]};
+        float feat[13], gc[3], R[9];
+        ia_team_geometry<true>(team, p, S.w, xc, feat, gc, S.lvl);
+        ia_team_fwd_rotation(team, p, xc, R);
+        const float g[3] = {R[0] * gc[0] + R[1] * gc[1] + R[2] * gc[2], R[3] * gc[0] + R[4] * gc[1] + R[5] * gc[2],
+                            R[6] * gc[0] + R[7] * gc[1] + R[8] * gc[2]};
+        float nw[3], view_w[3], rgb[3];
+        ia_dir_s2w(p, g, nw);
+        ia_dir_s2w(p, d, view_w);
+        ia_team_radiance<false>(team, p, S.w, xc, feat, view_w, nw, rgb, nullptr);
+        if (team.thread_rank() == 0) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) S.st[WS_IND + ch][t] += w * rgb[ch];
+            c_qg++; c_geo++; c_rad++;
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // One round of the ray state machines.  Policy P supplies rays and consumes their transmittance:
 //   bool P::init(const uint2 entry, float o[3], float d[3])   ray of a ring entry
-//   void P::finish(const uint2 entry, float T)                 shade / store
-template <class P>
+//   void P::finish(const uint2 entry, float T, const float ind[3])   shade / store (ind = indirect radiance, GI)
+template <bool GI, class P>
 __device__ __forceinline__ void wf_advance_slot(const IaFrame& p, P& pol, WfShared& S, const int t, int ring_tail,
                                                 unsigned& c_q, unsigned& c_rays) {
     unsigned pack = __float_as_uint(S.st[WS_PACK][t]);
@@ -423,11 +462,12 @@ __device__ __forceinline__ void wf_advance_slot(const IaFrame& p, P& pol, WfShar
         // ---- min SDF over the kept roots of the previous query (snarf_deformer.py:242-259)
         unsigned keep = S.qmask[t];
         float sdf = 1e5f;
+        int best = -1;
         while (keep) {
             int c = __ffs(keep) - 1;
             keep &= keep - 1;
-            float s = S.cand[(t * IA_N_INIT + c) * 3];
-            if (s < sdf) sdf = s;
+            float s = S.csdf[t * IA_N_INIT + c];
+            if (s < sdf) { sdf = s; best = c; }
         }
 #pragma unroll
         for (int k = 0; k < 3; k++) { o[k] = S.st[WS_O + k][t]; d[k] = S.st[WS_D + k][t]; }
@@ -465,6 +505,10 @@ __device__ __forceinline__ void wf_advance_slot(const IaFrame& p, P& pol, WfShar
             cdf_prev = cdf_next;
             cdf_next += weight;
             action = WF_ACT_CDF;
+        } else if (GI && stage == WF_GIWAIT) {
+            Tfin = S.st[WS_TRANS][t];
+            stage = WF_FINE;
+            action = WF_ACT_FINISH;
         } else {  // WF_FINE
             float Tacc = S.st[WS_TRANS][t], acc = S.st[WS_CDFPREV][t];
             float s0 = S.st[WS_TPL + i][t], e0 = S.st[WS_TPL + i + 1][t];
@@ -472,6 +516,14 @@ __device__ __forceinline__ void wf_advance_slot(const IaFrame& p, P& pol, WfShar
             float w = Tacc * al;
             Tacc *= (1.0f - al);
             acc += w;
+            bool gi_pushed = false;
+            if (GI && best >= 0) {
+                // radiance at the arg-min root of this fine sample is added by the GI phase of this round
+                // (before the Broyden phase overwrites the slot's roots): ind += w * rgb
+                int gi = atomicAdd(&S.n_gitask, 1);
+                S.gitask[gi] = make_uint2((unsigned)t | ((unsigned)best << 16), __float_as_uint(w));
+                gi_pushed = true;
+            }
             i++;
             if (i + 1 < j) {
                 float s1 = S.st[WS_TPL + i][t], e1 = S.st[WS_TPL + i + 1][t];
@@ -487,6 +539,12 @@ __device__ __forceinline__ void wf_advance_slot(const IaFrame& p, P& pol, WfShar
                 return;
             }
             Tfin = 1.0f - acc;
+            if (GI && gi_pushed) {
+                // the last fine sample's radiance arrives in this round's GI phase: finish next round
+                S.st[WS_TRANS][t] = Tfin;
+                S.st[WS_PACK][t] = __uint_as_float((unsigned)WF_GIWAIT | (j << 3) | (i << 6) | (entry.y << 16));
+                return;
+            }
             action = WF_ACT_FINISH;
         }
     }
@@ -550,6 +608,7 @@ __device__ __forceinline__ void wf_advance_slot(const IaFrame& p, P& pol, WfShar
                     tq = (s1 + e1) / 2.0f;
                     trans = 1.0f;      // Tacc
                     cdf_prev = 0.0f;   // acc
+                    if (GI) { S.st[WS_IND][t] = 0.f; S.st[WS_IND + 1][t] = 0.f; S.st[WS_IND + 2][t] = 0.f; }
                     stage = WF_FINE;
                     have_q = true;
                     break;
@@ -559,7 +618,11 @@ __device__ __forceinline__ void wf_advance_slot(const IaFrame& p, P& pol, WfShar
                 continue;
             }
             // WF_ACT_FINISH
-            pol.finish(entry, Tfin);
+            {
+                float ind[3] = {0.f, 0.f, 0.f};
+                if (GI && stage == WF_FINE) { ind[0] = S.st[WS_IND][t]; ind[1] = S.st[WS_IND + 1][t]; ind[2] = S.st[WS_IND + 2][t]; }
+                pol.finish(entry, Tfin, ind);
+            }
             stage = WF_IDLE;
             active = false;
             break;
@@ -583,29 +646,33 @@ __device__ __forceinline__ void wf_advance_slot(const IaFrame& p, P& pol, WfShar
 }
 
 // ------------------------------------------------------------------------------------------------
-template <class P>
+template <bool GI, class P>
 __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, unsigned char* __restrict__ scratch,
                                        unsigned long long* __restrict__ counters) {
     const int tid = threadIdx.x;
+    const int n_w = GI ? IA_RAD_END : IA_GEO_END;
     if (tid == 0) {
         unsigned char* mine = scratch + (size_t)blockIdx.x * WF_SCRATCH_BYTES;
+        S.w = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&S) + ((sizeof(WfShared) + 15) & ~15));
         S.cand = reinterpret_cast<float*>(mine);
-        S.gtask = reinterpret_cast<unsigned short*>(mine + WF_R * IA_N_INIT * 3 * 4);
-        S.btask = reinterpret_cast<unsigned short*>(mine + WF_R * IA_N_INIT * 3 * 4 + WF_R * IA_N_INIT * 2);
+        S.csdf = reinterpret_cast<float*>(mine + WF_OFF_CSDF);
+        S.gtask = reinterpret_cast<unsigned short*>(mine + WF_OFF_GTASK);
+        S.btask = reinterpret_cast<unsigned short*>(mine + WF_OFF_BTASK);
+        S.gitask = reinterpret_cast<uint2*>(mine + WF_OFF_GITASK);
 #if WF_STATE_GLOBAL
-        S.st = reinterpret_cast<float (*)[WF_R]>(mine + WF_R * IA_N_INIT * 3 * 4 + 2 * WF_R * IA_N_INIT * 2);
+        S.st = reinterpret_cast<float (*)[WF_R]>(mine + WF_OFF_STATE);
 #endif
     }
     __syncthreads();
-    for (int i = tid * 4; i < IA_GEO_END; i += blockDim.x * 4)
-        *reinterpret_cast<float4*>(S.w_geo + i) = __ldg(reinterpret_cast<const float4*>(p.mlp + i));
+    for (int i = tid * 4; i < n_w; i += blockDim.x * 4)
+        *reinterpret_cast<float4*>(S.w + i) = __ldg(reinterpret_cast<const float4*>(p.mlp + i));
     if (tid < IA_N_INIT * 12) S.tfs13[tid] = p.tfs[p.init_bones[tid / 12]][tid % 12];
     if (tid < IA_N_LEVELS) S.lvl[tid] = ia_level(p, tid);
     for (int t = tid; t < WF_R; t += blockDim.x) S.st[WS_PACK][t] = __uint_as_float(0u);
     if (tid == 0) { S.ring_head = 0; S.ring_tail = 0; S.more_tiles = 1; S.n_q = 0; S.n_gtask = 0; S.task_next = 0; }
     __syncthreads();
     const long long n_tiles = (pol.n_items() + WF_FEED - 1) / WF_FEED;
-    unsigned c_q = 0, c_fetch = 0, c_geo = 0, c_rays = 0, c_skip = 0;
+    unsigned c_q = 0, c_fetch = 0, c_geo = 0, c_rays = 0, c_skip = 0, c_qg = 0, c_rad = 0;
     while (true) {
         // ---- feed the ring while it cannot fill every slot
         while (true) {
@@ -624,11 +691,22 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
             __syncthreads();
         }
         __syncthreads();
-        if (tid == 0) { S.n_q = 0; S.n_gtask = 0; S.task_next = 0; S.n_btask = 0; }
+        if (tid == 0) { S.n_q = 0; S.n_gtask = 0; S.task_next = 0; S.n_btask = 0; S.n_gitask = 0; }
         const int ring_tail = S.ring_tail;
         __syncthreads();
-        for (int t = tid; t < WF_R; t += blockDim.x) wf_advance_slot(p, pol, S, t, ring_tail, c_q, c_rays);
+        for (int t = tid; t < WF_R; t += blockDim.x) wf_advance_slot<GI>(p, pol, S, t, ring_tail, c_q, c_rays);
         __syncthreads();
+        if (GI) {
+            const int n_gi = S.n_gitask;
+            if (n_gi) wf_gi_phase(p, S, c_qg, c_geo, c_rad);
+            __syncthreads();
+            const int n_q0 = S.n_q;
+            if (n_q0 == 0) {
+                // rays waiting for their last radiance (WF_GIWAIT) need one more advance round
+                if (n_gi == 0 && S.ring_tail - S.ring_head <= 0 && !S.more_tiles) break;
+                continue;
+            }
+        }
         const int n_q = S.n_q;
         if (n_q == 0) {
             if (S.ring_tail - S.ring_head <= 0 && !S.more_tiles) break;
@@ -656,6 +734,8 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
         c_geo += __shfl_xor_sync(0xffffffffu, c_geo, o);
         c_rays += __shfl_xor_sync(0xffffffffu, c_rays, o);
         c_skip += __shfl_xor_sync(0xffffffffu, c_skip, o);
+        c_qg += __shfl_xor_sync(0xffffffffu, c_qg, o);
+        c_rad += __shfl_xor_sync(0xffffffffu, c_rad, o);
     }
     if ((tid & 31) == 0) {
         if (c_q) atomicAdd(&counters[IA_CNT_QUERIES], c_q);
@@ -663,6 +743,8 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
         if (c_geo) atomicAdd(&counters[IA_CNT_GEO_EVAL], c_geo);
         if (c_rays) atomicAdd(&counters[IA_CNT_SECONDARY_RAYS], c_rays);
         if (c_skip) atomicAdd(&counters[IA_CNT_CHAINS_SKIPPED], c_skip);
+        if (c_qg) { atomicAdd(&counters[IA_CNT_QUERIES_GRAD], c_qg); atomicAdd(&counters[IA_CNT_SKIN_FETCH], c_qg); }
+        if (c_rad) atomicAdd(&counters[IA_CNT_RAD_EVAL], c_rad);
     }
 }
 
@@ -685,6 +767,7 @@ struct WfShadePolicy {
     const float* light_dir_s; const float* light_em; const float* light_pdf;
     float* acc6;
     long long n_total;
+    int gi;
 
     __device__ __forceinline__ long long n_items() const { return n_total; }
     __device__ __forceinline__ int* tile_counter() const { return &work[IA_W_TILE_NEXT]; }
@@ -732,7 +815,7 @@ struct WfShadePolicy {
         }
     }
 
-    __device__ __forceinline__ void finish(const uint2 e, float T) const {
+    __device__ __forceinline__ void finish(const uint2 e, float T, const float ind[3]) const {
         const int slot = (int)(e.x / (unsigned)spp);
         const unsigned kk = e.y;
         const IaSample sm = samples[rs_src[e.x]];
@@ -751,6 +834,7 @@ struct WfShadePolicy {
         for (int k = 0; k < 3; k++) {
             float em = lit ? light_em[kk * 3 + k] : 0.f;
             float Li = em * tr;
+            if (gi) Li += ind[k];
             float Ld = Li * diff / pdf, Ls = Li * spec[k] / pdf;
             float kd = (1.0f - sm.metal) * sm.albedo[k];
             atomicAdd(&pa[k], w * (kd * Ld + Ls));
@@ -759,6 +843,9 @@ struct WfShadePolicy {
     }
 };
 
+#define WF_SMEM_BYTES(GI) (((sizeof(WfShared) + 15) & ~(size_t)15) + ((GI) ? IA_RAD_END : IA_GEO_END) * sizeof(float))
+
+template <bool GI>
 __global__ void __launch_bounds__(WF_THREADS, 1) k_shade_wf(const __grid_constant__ IaFrame p, WfShadePolicy pol,
                                                             unsigned char* __restrict__ scratch,
                                                             unsigned long long* __restrict__ counters) {
@@ -766,12 +853,13 @@ __global__ void __launch_bounds__(WF_THREADS, 1) k_shade_wf(const __grid_constan
     WfShared& S = *reinterpret_cast<WfShared*>(wf_smem);
     pol.p = &p;
     pol.n_total = (long long)pol.work[IA_W_NHIT] * pol.spp;
-    wf_run(p, pol, S, scratch, counters);
+    pol.gi = GI ? 1 : 0;
+    wf_run<GI>(p, pol, S, scratch, counters);
 }
 
 // Policy 2: op-level secondary rays (ia_op_secondary, gi = 0)
 struct WfRaysPolicy {
-    const float* ro; const float* rd; long long n; float* T_out; int* work;
+    const float* ro; const float* rd; long long n; float* T_out; float* rgb_out; int* work;
     __device__ __forceinline__ long long n_items() const { return n; }
     __device__ __forceinline__ int* tile_counter() const { return &work[IA_W_TILE_NEXT]; }
     __device__ __forceinline__ void feed(long long s0, WfShared& S) {
@@ -784,13 +872,17 @@ struct WfRaysPolicy {
 #pragma unroll
         for (int k = 0; k < 3; k++) { o[k] = ro[(size_t)e.x * 3 + k]; d[k] = rd[(size_t)e.x * 3 + k]; }
     }
-    __device__ __forceinline__ void finish(const uint2 e, float T) const { T_out[e.x] = T; }
+    __device__ __forceinline__ void finish(const uint2 e, float T, const float ind[3]) const {
+        T_out[e.x] = T;
+        if (rgb_out) { rgb_out[(size_t)e.x * 3] = ind[0]; rgb_out[(size_t)e.x * 3 + 1] = ind[1]; rgb_out[(size_t)e.x * 3 + 2] = ind[2]; }
+    }
 };
 
+template <bool GI>
 __global__ void __launch_bounds__(WF_THREADS, 1) k_rays_wf(const __grid_constant__ IaFrame p, WfRaysPolicy pol,
                                                            unsigned char* __restrict__ scratch,
                                                            unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char wf_smem[];
     WfShared& S = *reinterpret_cast<WfShared*>(wf_smem);
-    wf_run(p, pol, S, scratch, counters);
+    wf_run<GI>(p, pol, S, scratch, counters);
 }
