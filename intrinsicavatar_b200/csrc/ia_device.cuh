@@ -372,7 +372,10 @@ __device__ __forceinline__ float ia_team_geometry(const Team& team, const IaFram
         acc.x = fmaf(ww.x, xin, acc.x); acc.y = fmaf(ww.y, xin, acc.y);
         acc.z = fmaf(ww.z, xin, acc.z); acc.w = fmaf(ww.w, xin, acc.w);
     }
-#pragma unroll
+    // (the with-gradient variant keeps its loops rolled: it runs once per shading sample inside kernels whose
+    //  straight-line code would otherwise overflow the instruction caches -- profiles/r1_k_primary_fused_summary.md)
+    constexpr int kUnrollL1 = GRAD ? 1 : 16;
+#pragma unroll kUnrollL1
     for (int l = 0; l < IA_N_LEVELS; l++) {
         float a = team.shfl(f0, l), b = team.shfl(f1, l);
         float4 wa = W1[(3 + 2 * l) * 16], wb = W1[(4 + 2 * l) * 16];
@@ -403,7 +406,7 @@ __device__ __forceinline__ float ia_team_geometry(const Team& team, const IaFram
         }
         // gradient w.r.t. this lane's two hash features
         float gf0 = 0.f, gf1 = 0.f;
-#pragma unroll
+#pragma unroll 1
         for (int l = 0; l < IA_N_LEVELS; l++) {
             float4 wa = W1[(3 + 2 * l) * 16], wb = W1[(4 + 2 * l) * 16];
             float sa = ia_team_sum(team, wa.x * dl[0] + wa.y * dl[1] + wa.z * dl[2] + wa.w * dl[3]);
@@ -561,7 +564,7 @@ __device__ __forceinline__ float4 ia_team_dense64(const Team& team, const float*
     const int lane = team.thread_rank();
     const float4* W = reinterpret_cast<const float4*>(WT) + lane;
     float4 acc = reinterpret_cast<const float4*>(B)[lane];
-#pragma unroll
+#pragma unroll 1
     for (int s = 0; s < IA_TEAM; s++) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -607,7 +610,7 @@ __device__ __forceinline__ void ia_team_radiance(const Team& team, const IaFrame
         ia_axpy4(a, W1 + d * 16, xin);
         if (MATERIAL) ia_axpy4(m, M1 + d * 16, xin);
     }
-#pragma unroll
+#pragma unroll 1
     for (int l = 0; l < IA_N_LEVELS; l++) {
         float e0 = team.shfl(f0, l), e1 = team.shfl(f1, l);
         ia_axpy4(a, W1 + (3 + 2 * l) * 16, e0);
@@ -617,13 +620,20 @@ __device__ __forceinline__ void ia_team_radiance(const Team& team, const IaFrame
             ia_axpy4(m, M1 + (4 + 2 * l) * 16, e1);
         }
     }
+    // lane o keeps feat[o] / sh[o] so the rolled loops can broadcast them with a shuffle (no register indexing)
+    float my_feat = 0.f, my_sh = 0.f;
 #pragma unroll
+    for (int o = 0; o < 13; o++) my_feat = lane == o ? feat[o] : my_feat;
+#pragma unroll
+    for (int o = 0; o < 16; o++) my_sh = lane == o ? sh[o] : my_sh;
+#pragma unroll 1
     for (int o = 0; o < 13; o++) {
-        ia_axpy4(a, W1 + (35 + o) * 16, feat[o]);
-        if (MATERIAL) ia_axpy4(m, M1 + (35 + o) * 16, feat[o]);
+        const float fv = team.shfl(my_feat, o);
+        ia_axpy4(a, W1 + (35 + o) * 16, fv);
+        if (MATERIAL) ia_axpy4(m, M1 + (35 + o) * 16, fv);
     }
-#pragma unroll
-    for (int o = 0; o < 16; o++) ia_axpy4(a, W1 + (48 + o) * 16, sh[o]);
+#pragma unroll 1
+    for (int o = 0; o < 16; o++) ia_axpy4(a, W1 + (48 + o) * 16, team.shfl(my_sh, o));
 #pragma unroll
     for (int d = 0; d < 3; d++) ia_axpy4(a, W1 + (64 + d) * 16, normal_w[d]);
     float h1[4] = {fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f)};

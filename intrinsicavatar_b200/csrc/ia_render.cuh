@@ -506,7 +506,7 @@ __global__ void k_composite(const __grid_constant__ IaFrame p, long long n, cons
 
 // ================================================================================================
 static int ia_wf_scratch(ia_ctx* c) {
-    if (!c->d_wf_scratch) return ia_realloc(&c->d_wf_scratch, (size_t)c->n_sm * WF_SCRATCH_BYTES);
+    if (!c->d_wf_scratch) return ia_realloc(&c->d_wf_scratch, (size_t)c->n_sm * WF_CTAS_PER_SM * WF_SCRATCH_BYTES);
     return IA_OK;
 }
 
@@ -595,10 +595,10 @@ extern "C" int ia_render(ia_ctx* c, const float* d_rays, int64_t n_rays, int64_t
             if (int e = ia_wf_scratch(c)) return e;
             if (gi) {
                 IA_CHECK_CUDA(cudaFuncSetAttribute(k_shade_wf<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_BYTES(true)));
-                k_shade_wf<true><<<c->n_sm, WF_THREADS, WF_SMEM_BYTES(true), st>>>(c->f, pol, c->d_wf_scratch, c->d_counters);
+                k_shade_wf<true><<<c->n_sm * WF_CTAS_PER_SM, WF_THREADS, WF_SMEM_BYTES(true), st>>>(c->f, pol, c->d_wf_scratch, c->d_counters);
             } else {
                 IA_CHECK_CUDA(cudaFuncSetAttribute(k_shade_wf<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_BYTES(false)));
-                k_shade_wf<false><<<c->n_sm, WF_THREADS, WF_SMEM_BYTES(false), st>>>(c->f, pol, c->d_wf_scratch, c->d_counters);
+                k_shade_wf<false><<<c->n_sm * WF_CTAS_PER_SM, WF_THREADS, WF_SMEM_BYTES(false), st>>>(c->f, pol, c->d_wf_scratch, c->d_counters);
             }
         }
         IA_STAGE_END(c, IA_STAGE_SHADE, st, 1);
@@ -795,7 +795,7 @@ extern "C" int ia_op_secondary(ia_ctx* c, const float* d_o, const float* d_d, in
         WfRaysPolicy pol;
         pol.ro = d_o; pol.rd = d_d; pol.n = n; pol.T_out = d_T; pol.rgb_out = d_rgb; pol.work = c->d_work;
         if (int e = ia_wf_scratch(c)) return e;
-        int wf_blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + WF_FEED - 1) / WF_FEED, (int64_t)c->n_sm));
+        int wf_blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + WF_FEED - 1) / WF_FEED, (int64_t)c->n_sm * WF_CTAS_PER_SM));
         if (gi) {
             IA_CHECK_CUDA(cudaFuncSetAttribute(k_rays_wf<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_BYTES(true)));
             k_rays_wf<true><<<wf_blocks, WF_THREADS, WF_SMEM_BYTES(true), (cudaStream_t)stream>>>(c->f, pol, c->d_wf_scratch, c->d_counters);

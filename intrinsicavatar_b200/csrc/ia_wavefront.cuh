@@ -24,6 +24,9 @@
 #ifndef WF_THREADS
 #define WF_THREADS 512
 #endif
+#ifndef WF_CTAS_PER_SM
+#define WF_CTAS_PER_SM 1   // resident CTAs per SM (WF_THREADS * WF_CTAS_PER_SM * regs <= 64K)
+#endif
 #ifndef WF_BROYDEN_LANES
 #define WF_BROYDEN_LANES 1   // lanes per Broyden chain: 1 (one thread per chain) or 3 (row-distributed)
 #endif
@@ -846,7 +849,7 @@ struct WfShadePolicy {
 #define WF_SMEM_BYTES(GI) (((sizeof(WfShared) + 15) & ~(size_t)15) + ((GI) ? IA_RAD_END : IA_GEO_END) * sizeof(float))
 
 template <bool GI>
-__global__ void __launch_bounds__(WF_THREADS, 1) k_shade_wf(const __grid_constant__ IaFrame p, WfShadePolicy pol,
+__global__ void __launch_bounds__(WF_THREADS, WF_CTAS_PER_SM) k_shade_wf(const __grid_constant__ IaFrame p, WfShadePolicy pol,
                                                             unsigned char* __restrict__ scratch,
                                                             unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char wf_smem[];
@@ -879,7 +882,7 @@ struct WfRaysPolicy {
 };
 
 template <bool GI>
-__global__ void __launch_bounds__(WF_THREADS, 1) k_rays_wf(const __grid_constant__ IaFrame p, WfRaysPolicy pol,
+__global__ void __launch_bounds__(WF_THREADS, WF_CTAS_PER_SM) k_rays_wf(const __grid_constant__ IaFrame p, WfRaysPolicy pol,
                                                            unsigned char* __restrict__ scratch,
                                                            unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char wf_smem[];
