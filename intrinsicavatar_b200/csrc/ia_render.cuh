@@ -219,7 +219,10 @@ k_prim_edges(const __grid_constant__ IaFrame p, const float* __restrict__ hit_od
 }
 
 // rendering_with_normals_mats_sdf's per-sample part (rgb_normal_mats_alpha_fn, models/intrinsic_avatar.py:1066-1156)
-__global__ void __launch_bounds__(IA_PRIMARY_THREADS, 1)
+#ifndef IA_PRIM_SHADE_CTAS
+#define IA_PRIM_SHADE_CTAS 2
+#endif
+__global__ void __launch_bounds__(IA_PRIMARY_THREADS, IA_PRIM_SHADE_CTAS)
 k_prim_shade(const __grid_constant__ IaFrame p, const float* __restrict__ hit_od, IaSample* __restrict__ samples,
              IaSampleAux* __restrict__ aux, long long sample_cap, const int* __restrict__ work,
              unsigned long long* __restrict__ counters) {
@@ -517,7 +520,7 @@ static int ia_ws_reserve(ia_ctx* c, int64_t n_rays, int spp, bool need_pbr) {
             return IA_ECUDA;
         c->ws_rays = n_rays;
     }
-    int64_t want_samples = std::max<int64_t>(n_rays * 24, 1 << 16);
+    int64_t want_samples = std::max<int64_t>(n_rays * 64, 1 << 16);  // ~38 per HIT ray observed; 64 per ray covers full coverage
     if (want_samples > c->ws_samples) {
         if (ia_realloc(&c->d_samples, (size_t)want_samples) || ia_realloc(&c->d_samples_aux, (size_t)want_samples)) return IA_ECUDA;
         c->ws_samples = want_samples;
@@ -565,7 +568,7 @@ extern "C" int ia_render(ia_ctx* c, const float* d_rays, int64_t n_rays, int64_t
         IA_STAGE_BEGIN(c, IA_STAGE_PRIMARY, st);
         k_prim_edges<<<c->n_sm * 2, IA_PRIMARY_THREADS, sm1, st>>>(c->f, c->d_hit_od, c->d_hit_info, c->d_samples, c->d_samples_aux,
                                                                    c->ws_samples, c->d_work, c->d_counters);
-        k_prim_shade<<<c->n_sm, IA_PRIMARY_THREADS, sm2, st>>>(c->f, c->d_hit_od, c->d_samples, c->d_samples_aux, c->ws_samples,
+        k_prim_shade<<<c->n_sm * IA_PRIM_SHADE_CTAS, IA_PRIMARY_THREADS, sm2, st>>>(c->f, c->d_hit_od, c->d_samples, c->d_samples_aux, c->ws_samples,
                                                                    c->d_work, c->d_counters);
         k_prim_accum<<<(unsigned)((n_rays + 127) / 128), 128, 0, st>>>(c->f, c->d_hit_rays, c->d_hit_od, c->d_hit_info, c->d_samples,
                                                                        c->d_samples_aux, c->d_work, *out);
