@@ -134,6 +134,121 @@ def multilobe_eval(wi, n, wo, roughness, albedo, metallic):
     return diff, spec
 
 
+def _frame(n):
+    """coordinate_system (warp_utils.py:62-101): returns (t, b) with t = cross(b, n)."""
+    a = n
+    cond = a[:, 0].abs() > a[:, 1].abs()
+    inv1 = 1.0 / torch.sqrt(a[:, 0] ** 2 + a[:, 2] ** 2)
+    inv2 = 1.0 / torch.sqrt(a[:, 1] ** 2 + a[:, 2] ** 2)
+    c1 = torch.stack([a[:, 2] * inv1, torch.zeros_like(inv1), -a[:, 0] * inv1], -1)
+    c2 = torch.stack([torch.zeros_like(inv2), a[:, 2] * inv2, -a[:, 1] * inv2], -1)
+    c = torch.where(cond[:, None], c1, c2)
+    return torch.cross(c, a, dim=-1), c
+
+
+def _to_local(v, t, b, n):
+    return torch.stack([(v * t).sum(-1), (v * b).sum(-1), (v * n).sum(-1)], -1)
+
+
+def _to_world(v, t, b, n):
+    return F.normalize(v[:, 0:1] * t + v[:, 1:2] * b + v[:, 2:3] * n, dim=-1)
+
+
+def luminance(x):
+    return x[..., :1] * 0.212671 + x[..., 1:2] * 0.715160 + x[..., 2:3] * 0.072169
+
+
+def _lobe_weights(wi, n, albedo, metallic):
+    """Lobe selection weights shared by MultiLobe.pdf / .sample (bxdf.py:297-312, 343-358): note the
+    Fresnel term uses the albedo itself as F0."""
+    wd = (1.0 - metallic) * luminance(albedo)
+    cos_t = (wi * n).sum(-1, keepdim=True)
+    fres = albedo + (1.0 - albedo) * 2 ** ((-5.55473 * cos_t - 6.98316) * cos_t)
+    ws = torch.where(cos_t > 0, luminance(fres), torch.zeros_like(cos_t))
+    return wd, ws
+
+
+def multilobe_pdf(wi, n, wo, roughness, albedo, metallic):
+    """MultiLobe.pdf in eval mode (bxdf.py:290-317) = p_d * Lambertian.pdf (:117-123, cosine / pi)
+    + (1 - p_d) * GGX.pdf (:222-236, VNDF / (4 |wo.wh| + eps)); roughness [N], albedo [N,3], metallic [N,1]."""
+    eps = 1e-6
+    wd, ws = _lobe_weights(wi, n, albedo, metallic)
+    p_d = torch.where(wd + ws > eps, wd / (wd + ws + eps), torch.ones_like(wd))
+    pdf_d = (F.relu((n * wo).sum(-1)) / np.pi)[:, None]
+    t, b = _frame(n)
+    wo_l, wi_l = _to_local(wo, t, b, n), _to_local(wi, t, b, n)
+    wh = F.normalize(wi_l + wo_l, dim=-1)
+    alpha = roughness
+    k = (alpha ** 2 + 2 * alpha + 1) / 8.0
+    nom = wi_l[:, 2]
+    den = nom * (1.0 - k) + k
+    g1 = torch.where(den > eps, nom / (den + eps), torch.zeros_like(nom))
+    alpha2 = alpha ** 2
+    ndf = alpha2 * torch.reciprocal(np.pi * (wh[:, 2] ** 2 * (alpha2 - 1) + 1) ** 2 + eps)
+    vndf = torch.where((wh[:, 2] > eps) & (wi_l[:, 2] > eps),
+                       g1 * torch.clamp((wh * wi_l).sum(-1), min=0.0) * ndf / (wi_l[:, 2] + eps),
+                       torch.zeros_like(nom))
+    pdf_s = torch.where(4 * (wi_l * wh).sum(-1).abs() > eps, vndf / (4 * (wo_l * wh).sum(-1).abs() + eps),
+                        torch.zeros_like(nom))[:, None]
+    return p_d * pdf_d + (1 - p_d) * pdf_s
+
+
+def multilobe_sample(n, wi, roughness, albedo, metallic, sample):
+    """MultiLobe.sample in eval mode (bxdf.py:332-388) with explicit uniforms ``sample`` [N,2]:
+    lobe pick on sample[:,0] (rescaled afterwards), GGX VNDF sampling (warp_utils.py:632-690) or
+    cosine-weighted hemisphere via the concentric disk map (warp_utils.py:139-172, 599-616)."""
+    eps = 1e-6
+    wd, ws = _lobe_weights(wi, n, albedo, metallic)
+    p_s = torch.where(wd + ws > eps, ws / (wd + ws + eps), torch.zeros_like(wd)).squeeze(-1)
+    spec_mask = p_s > sample[:, 0]
+    s0 = torch.where(spec_mask, sample[:, 0] / p_s, (sample[:, 0] - p_s) / (1 - p_s))
+    s1 = sample[:, 1]
+    t, b = _frame(n)
+    # --- specular: VNDF
+    wi_l = _to_local(wi, t, b, n)
+    a = roughness
+    vh = F.normalize(torch.stack([a * wi_l[:, 0], a * wi_l[:, 1], wi_l[:, 2]], -1), dim=-1)
+    lensq = vh[:, 0] * vh[:, 0] + vh[:, 1] * vh[:, 1]
+    T1 = torch.where(lensq[:, None] > eps,
+                     torch.stack([-vh[:, 1] / torch.sqrt(lensq + eps), vh[:, 0] / torch.sqrt(lensq + eps),
+                                  torch.zeros_like(lensq)], -1),
+                     torch.tensor([[1.0, 0.0, 0.0]]).expand(len(lensq), 3))
+    T2 = torch.cross(vh, T1, dim=-1)
+    r = torch.sqrt(s0)
+    phi = 2.0 * np.pi * s1
+    t1 = r * torch.cos(phi)
+    t2 = r * torch.sin(phi)
+    sv = 0.5 * (1.0 + vh[:, 2])
+    t2 = (1.0 - sv) * torch.sqrt(torch.clamp(1.0 - t1 * t1, min=0.0)) + sv * t2
+    nh = t1[:, None] * T1 + t2[:, None] * T2 + torch.sqrt(torch.clamp(1.0 - t1 * t1 - t2 * t2, min=0.0))[:, None] * vh
+    wh = F.normalize(torch.stack([a * nh[:, 0], a * nh[:, 1], torch.clamp(nh[:, 2], min=0.0)], -1), dim=-1)
+    wo_s = _to_world(2 * (wi_l * wh).sum(-1, keepdim=True) * wh - wi_l, t, b, n)
+    # --- diffuse: concentric disk -> hemisphere
+    ox, oy = 2.0 * s0 - 1.0, 2.0 * s1 - 1.0
+    big = ox.abs() > oy.abs()
+    rr = torch.where(big, ox, oy)
+    th = torch.where(big, np.pi / 4.0 * (oy / ox), np.pi / 2.0 - np.pi / 4.0 * (ox / oy))
+    x, y = rr * torch.cos(th), rr * torch.sin(th)
+    z = torch.sqrt((1.0 - x ** 2 - y ** 2).clamp(min=0.0))
+    wo_d = _to_world(torch.stack([x, y, z], -1), t, b, n)
+    return torch.where(spec_mask[:, None], wo_s, wo_d)
+
+
+def uniform_sphere_stratified(n_rows=16, n_cols=32):
+    """EnvironmentLightBase.sample_uniform_sphere_stratified in eval mode (light.py:161-217; no jitter):
+    cell centres of an n_rows x n_cols grid mapped by sample_uniform_sphere (warp_utils.py:174-198;
+    the first column -> z).  Returns directions [n_rows*n_cols, 3]; inv_pdf is 4 pi for all of them."""
+    v, u = torch.meshgrid(torch.arange(0, n_rows, dtype=torch.float32) + 0.5,
+                          torch.arange(0, n_cols, dtype=torch.float32) + 0.5, indexing="ij")
+    u = u / n_cols
+    v = v / n_rows
+    s = torch.stack([v, u], -1).reshape(-1, 2)
+    z = s[:, 0] * 2.0 - 1.0
+    phi = 2.0 * np.pi * s[:, 1]
+    r = torch.sqrt(torch.clamp(1.0 - z ** 2, min=0.0))
+    return F.normalize(torch.stack([torch.cos(phi) * r, torch.sin(phi) * r, z], -1), dim=-1)
+
+
 def rgb_to_srgb(f: torch.Tensor) -> torch.Tensor:
     return torch.where(f <= 0.0031308, f * 12.92,
                        torch.pow(torch.clamp(f, 0.0031308), 1.0 / 2.4) * 1.055 - 0.055)

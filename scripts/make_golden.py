@@ -17,6 +17,11 @@ What is pinned (reference file:line):
   cc         max_connected_component                              models/utils.py:152-163
   lbs        batch_rodrigues, batch_rigid_transform               models/deformers/smplx/lbs.py:345-401, 152-248
   reflect    reflect(), get_activation                            models/utils.py
+and, in tests/golden/reference_vectors_bsdf.npz (`make_golden.py bsdf`; the integrators of SURVEY 8f.1):
+  bsdf       MultiLobe.sample (explicit `sample` uniforms), MultiLobe.pdf, eval mode
+                                                                  lib/torch_pbr/bxdf.py:290-388
+  sphere     EnvironmentLightBase.sample_uniform_sphere_stratified(1, 16, 32), eval mode
+                                                                  lib/torch_pbr/light.py:161-217
 """
 from __future__ import annotations
 
@@ -30,6 +35,7 @@ import torch
 REF = "/root/reference"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "tests", "golden", "reference_vectors.npz")
+OUT_BSDF = os.path.join(ROOT, "tests", "golden", "reference_vectors_bsdf.npz")
 
 
 def _stub(name, **attrs):
@@ -202,5 +208,46 @@ def main():
     print("wrote", OUT, {k: tuple(np.asarray(v.detach() if torch.is_tensor(v) else v).shape) for k, v in g.items()})
 
 
+def main_bsdf():
+    """MultiLobe.sample / .pdf and the stratified sphere directions of render_mode = mats | mis | uniform_light."""
+    install_stubs()
+    torch.manual_seed(4321)
+    g = {}
+    from lib.torch_pbr import bxdf as ref_bxdf
+    from lib.torch_pbr import light as ref_light
+    N = 2048
+    n = torch.nn.functional.normalize(torch.randn(N, 3), dim=-1)
+    wi = torch.nn.functional.normalize(n + 0.8 * torch.randn(N, 3), dim=-1)
+    wi[:64] = torch.nn.functional.normalize(-n[:64] + 0.3 * torch.randn(64, 3), dim=-1)   # viewer below the surface
+    rough = torch.rand(N, 1) * 0.9 + 0.09
+    albedo = torch.rand(N, 3) * 0.77 + 0.03
+    metal = torch.rand(N, 1)
+    metal[64:128] = 1.0
+    metal[128:192] = 0.0
+    sample = torch.rand(N, 2)
+    lobe = ref_bxdf.MultiLobe(types.SimpleNamespace())
+    lobe.train(False)   # (.eval is shadowed by the BRDF eval, SURVEY Appendix A.14)
+    kw = dict(alpha_x=rough.squeeze(-1), alpha_y=rough.squeeze(-1), albedo=albedo, metallic=metal,
+              attenuation=torch.zeros(N, 1))
+    # called as pbr_mats_forward does (models/intrinsic_avatar.py:880-903), uniforms made explicit
+    wo = lobe.sample(n=n, wi=wi, sample=sample.clone(), **kw)
+    pdf = lobe.pdf(n=n, wi=wi, wo=wo, **kw)
+    wo2 = torch.nn.functional.normalize(n + 0.8 * torch.randn(N, 3), dim=-1)   # pdf of directions it did not sample (MIS)
+    pdf2 = lobe.pdf(n=n, wi=wi, wo=wo2, **kw)
+    g.update(bsdf_n=n, bsdf_wi=wi, bsdf_rough=rough, bsdf_albedo=albedo, bsdf_metal=metal, bsdf_sample=sample,
+             bsdf_wo=wo, bsdf_pdf=pdf, bsdf_wo2=wo2, bsdf_pdf2=pdf2)
+    ecfg = types.SimpleNamespace(xyz2lonlat_mode=None,
+                                 envlight_config=types.SimpleNamespace(scale=1.0, bias=0.0, base_res=8, hdr_filepath=None))
+    env = ref_light.EnvironmentLightTensor(ecfg)
+    env.train(False)
+    dirs, inv_pdf = env.sample_uniform_sphere_stratified(1, 16, 32, device="cpu")
+    g.update(sphere_dirs=dirs, sphere_inv_pdf=inv_pdf)
+    np.savez_compressed(OUT_BSDF, **{k: v.detach().cpu().numpy() for k, v in g.items()})
+    print("wrote", OUT_BSDF, {k: tuple(v.shape) for k, v in g.items()})
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "bsdf":
+        main_bsdf()
+    else:
+        main()
