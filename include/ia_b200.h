@@ -84,6 +84,13 @@ int ia_set_occupancy(ia_ctx* ctx, const float* h_aabb6, int res, const uint8_t* 
 int ia_set_light(ia_ctx* ctx, const float* d_envmap, int H, int W, const float* d_u1, const float* d_u2,
                  int spp, float* d_dirs_world_out, float* d_em_out, float* d_pdf_out, void* stream);
 
+/* render_mode = uniform_light: the light table is the n_rows x n_cols stratified sphere of
+ * EnvironmentLightBase.sample_uniform_sphere_stratified in eval mode (lib/torch_pbr/light.py:161-217;
+ * the reference uses 16 x 32 and asserts samples_per_pixel == 512, models/intrinsic_avatar.py:1391);
+ * samples_per_pixel becomes n_rows * n_cols.  Optional outputs: d_dirs_world_out, d_em_out [spp,3].     */
+int ia_set_light_uniform(ia_ctx* ctx, const float* d_envmap, int H, int W, int n_rows, int n_cols,
+                         float* d_dirs_world_out, float* d_em_out, void* stream);
+
 /* ---- the hot path --------------------------------------------------------------------------- */
 /* Output buffers of one forward pass, all DEVICE pointers, row-major [n_rays, C].  Any may be NULL.  */
 typedef struct ia_outputs {
@@ -104,16 +111,29 @@ typedef struct ia_outputs {
     float* comp_albedo_full;     /* [n,3] */
     float* comp_roughness_full;  /* [n,1] */
     float* comp_metallic_full;   /* [n,1] */
+    float* visibility;           /* [n,1] render_mode = uniform_light only (models/intrinsic_avatar.py:1427-1432, 1516-1517) */
 } ia_outputs;
 
 #define IA_RENDER_PRIMARY_ONLY 1 /* stop after the primary volume render (albedo_only / config 2) */
 #define IA_RENDER_GI 2           /* global_illumination = true: add one indirect bounce           */
+/* config.model.render_mode (models/intrinsic_avatar.py:1346-1440), bits 2-3 of `flags`:                */
+#define IA_RENDER_MODE_SHIFT 2
+#define IA_RENDER_MODE_MASK (3 << IA_RENDER_MODE_SHIFT)
+#define IA_RENDER_LIGHT (0 << IA_RENDER_MODE_SHIFT)         /* pbr_light_forward :755-861 (default)         */
+#define IA_RENDER_UNIFORM_LIGHT (1 << IA_RENDER_MODE_SHIFT) /* pbr_uniform_light_forward :654-753           */
+#define IA_RENDER_MATS (2 << IA_RENDER_MODE_SHIFT)          /* pbr_mats_forward :863-948 (BSDF sampling)     */
+#define IA_RENDER_MIS (3 << IA_RENDER_MODE_SHIFT)           /* pbr_mis_forward :547-652 (BSDF + light, MIS)  */
+#define IA_RENDER_ADD_EMITTER 16 /* config.model.add_emitter: the envmap along the primary ray replaces the
+                                    background colour in comp_rgb_phys / comp_demod_phys (:1319-1341, 1454-1490) */
 
-/* IntrinsicAvatarModel.forward in eval mode, render_mode = "light"
- * (models/intrinsic_avatar.py:950-1666; compute_indirect_radiance :396-545; pbr_light_forward :755-861;
+/* IntrinsicAvatarModel.forward in eval mode, render_mode = light | uniform_light | mats | mis
+ * (models/intrinsic_avatar.py:950-1666; compute_indirect_radiance :396-545; pbr_*_forward :547-948;
  * models/volrend.py:810-1020; models/pbr/utils.py:70-229).  d_rays [n,8] world-space o,d,near,far.
- * The per-ray light permutation (reference: CPU rand + argsort, :1355-1378) is the stateless keyed
- * permutation of (seed, ray_index_base + ray).  Does not sync.                                        */
+ * Randomness: the per-ray light permutation of light / uniform_light (reference: CPU rand + argsort,
+ * :1355-1378) is the stateless keyed permutation of (seed, ray_index_base + ray); the uniforms of
+ * MultiLobe.sample / emitter.sample in mats / mis (reference: torch.rand) are counter-based:
+ * stream (seed, ray_index_base + ray, shading sample j, dim) -- see ia_rng_uniform in csrc/ia_pbr.cuh.
+ * mats / mis read the envmap given to the last ia_set_light call: it must still be valid.  Does not sync. */
 int ia_render(ia_ctx* ctx, const float* d_rays, int64_t n_rays, int64_t ray_index_base, int flags,
               uint32_t seed, const ia_outputs* out, void* stream);
 
@@ -210,6 +230,16 @@ int ia_op_secondary(ia_ctx* ctx, const float* d_o, const float* d_d, int64_t n, 
 int ia_op_brdf(ia_ctx* ctx, const float* d_wi, const float* d_n, const float* d_wo, const float* d_rough,
                const float* d_albedo, const float* d_metal, int64_t n, float* d_diff, float* d_spec,
                void* stream);
+/* MultiLobe.sample with explicit uniforms d_sample [n,2] (bxdf.py:332-388) -> d_wo [n,3]; and
+ * MultiLobe.pdf (bxdf.py:290-317) of d_wo_query [n,3] -> d_pdf [n].  Either output may be NULL.         */
+int ia_op_bsdf_sample_pdf(ia_ctx* ctx, const float* d_wi, const float* d_n, const float* d_rough,
+                          const float* d_albedo, const float* d_metal, const float* d_sample,
+                          const float* d_wo_query, int64_t n, float* d_wo, float* d_pdf, void* stream);
+/* EnvironmentLightTensor.sample / pdf / eval per direction, on the tables of the last ia_set_light*
+ * call (light.py:259-446): d_u [n,2] -> d_dirs_world_out [n,3] (may be NULL); d_dirs_world [n,3] ->
+ * d_pdf_out [n], d_em_out [n,3] (d_dirs_world NULL: the directions just sampled are used).             */
+int ia_op_env(ia_ctx* ctx, const float* d_u, const float* d_dirs_world, int64_t n, float* d_dirs_world_out,
+              float* d_pdf_out, float* d_em_out, void* stream);
 
 #ifdef __cplusplus
 }

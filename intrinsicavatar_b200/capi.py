@@ -22,21 +22,24 @@ STAGE_NAMES = ["precompute", "occupancy", "light", "setup", "primary", "resample
 
 RENDER_PRIMARY_ONLY = 1
 RENDER_GI = 2
+# config.model.render_mode -> bits 2-3 of the ia_render flags (IA_RENDER_* in include/ia_b200.h)
+RENDER_ADD_EMITTER = 16
+RENDER_MODES = {"light": 0 << 2, "uniform_light": 1 << 2, "mats": 2 << 2, "mis": 3 << 2}
 
 
 class IaOutputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "comp_rgb", "comp_normal", "opacity", "depth", "comp_albedo", "comp_roughness", "comp_metallic",
         "comp_rgb_phys", "comp_demod_phys", "num_samples", "comp_rgb_full", "comp_rgb_phys_full",
-        "comp_demod_phys_full", "comp_albedo_full", "comp_roughness_full", "comp_metallic_full")]
+        "comp_demod_phys_full", "comp_albedo_full", "comp_roughness_full", "comp_metallic_full", "visibility")]
 
 
 EXPORTS = [
     "ia_last_error", "ia_version", "ia_create", "ia_destroy", "ia_set_fields", "ia_set_lbs_voxels", "ia_set_pose",
-    "ia_set_render_config", "ia_build_occupancy", "ia_set_occupancy", "ia_set_light", "ia_render", "ia_get_counters", "ia_set_timing", "ia_get_timings",
+    "ia_set_render_config", "ia_build_occupancy", "ia_set_occupancy", "ia_set_light", "ia_set_light_uniform", "ia_render", "ia_get_counters", "ia_set_timing", "ia_get_timings",
     "ia_op_precompute", "ia_op_broyden", "ia_op_query", "ia_op_shade_fields", "ia_op_traverse",
     "ia_op_ray_resampling", "ia_op_ray_resampling_merge", "ia_op_ray_resampling_sdf_fine", "ia_op_unpack_info",
-    "ia_op_secondary", "ia_op_brdf",
+    "ia_op_secondary", "ia_op_brdf", "ia_op_bsdf_sample_pdf", "ia_op_env",
 ]
 
 

@@ -66,6 +66,10 @@ struct ia_ctx {
     float* d_u_table = nullptr;
     float *d_env_pdf = nullptr, *d_env_cols = nullptr, *d_env_rows = nullptr, *d_env_rowsum = nullptr;
     double* d_env_total = nullptr;
+    IaEnv env = {};              // tables of the last ia_set_light* call (env itself is the caller's buffer)
+    bool light_uniform = false;  // light tables hold the stratified sphere of render_mode = uniform_light
+    float* d_vis = nullptr;      // [n_rays] visibility accumulator (uniform_light)
+    float* d_bg = nullptr;       // [n_rays][3] background radiance per ray (background colour / add_emitter)
     // workspace for ia_render
     int64_t ws_rays = 0, ws_samples = 0, ws_resamples = 0;
     int* d_hit_rays = nullptr;       // [n_rays]
@@ -160,7 +164,7 @@ extern "C" int ia_destroy(ia_ctx* c) {
                     c->d_light_em, c->d_light_pdf, c->d_u_table, c->d_env_pdf, c->d_env_cols, c->d_env_rows,
                     c->d_env_rowsum, c->d_env_total, c->d_hit_rays, c->d_hit_od, c->d_hit_info, c->d_samples,
                     c->d_rs_t, c->d_rs_w, c->d_rs_src, c->d_acc, c->d_counters, c->d_work, c->d_occ_a, c->d_occ_b,
-                    c->d_occ_hist, c->d_occ_sum, c->d_wf_scratch, c->d_samples_aux};
+                    c->d_occ_hist, c->d_occ_sum, c->d_wf_scratch, c->d_samples_aux, c->d_vis, c->d_bg};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete c;
@@ -782,80 +786,53 @@ __global__ void k_env_rows(const float* __restrict__ rowtot, int H, float* __res
     for (int r = 0; r < H; r++) rows[r + 1] /= den;
 }
 
-__device__ __forceinline__ int ia_searchsorted_right(const float* a, int n, float v) {  // first i with a[i] > v
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (a[mid] <= v) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-__device__ __forceinline__ void ia_env_uv(const float d[3], float& u, float& v, float& lat) {
-    const float PI = 3.14159265358979323846f;
-    float lon = atan2f(d[0], d[2]);
-    float nrm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-    lat = asinf(d[1] / nrm);
-    u = lon / (2 * PI) + 0.5f;
-    v = lat / PI + 0.5f;
-}
-
-__global__ void k_env_sample(const __grid_constant__ IaFrame p, const float* __restrict__ env, int H, int W,
-                             const float* __restrict__ pdf, const float* __restrict__ cols, const float* __restrict__ rows,
-                             const float* __restrict__ u1, const float* __restrict__ u2, int spp, float* __restrict__ dir_w,
-                             float* __restrict__ dir_s, float* __restrict__ em, float* __restrict__ pdf_out) {
+__global__ void k_env_sample(const __grid_constant__ IaFrame p, const IaEnv E, const float* __restrict__ u1,
+                             const float* __restrict__ u2, int spp, float* __restrict__ dir_w, float* __restrict__ dir_s,
+                             float* __restrict__ em, float* __restrict__ pdf_out) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= spp) return;
-    const float PI = 3.14159265358979323846f;
-    // sample(): inverse CDF with linear in-bin offset (light.py:341-412)
-    int ri = ia_searchsorted_right(rows, H + 1, u1[k]);
-    int below = max(ri - 1, 0), above = min(ri, H);
-    float rfrac = (u1[k] - rows[below]) / (rows[above] - rows[below]);
-    ri = below;
-    const float* crow = cols + (size_t)ri * (W + 1);
-    int ci = ia_searchsorted_right(crow, W + 1, u2[k]);
-    below = max(ci - 1, 0); above = min(ci, W);
-    float cfrac = (u2[k] - crow[below]) / (crow[above] - crow[below]);
-    ci = below;
-    float uu = ((float)ci + cfrac) / (float)W, vv = ((float)ri + rfrac) / (float)H;
-    float lon = (uu - 0.5f) * 2 * PI, lat = (vv - 0.5f) * PI;
-    float d[3] = {cosf(lat) * sinf(lon), sinf(lat), cosf(lat) * cosf(lon)};
     float dn[3];
-    ia_normalize(d, dn, 1e-12f);
+    ia_env_sample(E, u1[k], u2[k], dn);
     dir_w[k * 3 + 0] = dn[0]; dir_w[k * 3 + 1] = dn[1]; dir_w[k * 3 + 2] = dn[2];
     // direction used by the integrator: w2s, then back s2w for the lookups (pbr_light_forward :784-842)
     float ds[3], dw[3];
     ia_dir_w2s(p, dn, ds);
     dir_s[k * 3 + 0] = ds[0]; dir_s[k * 3 + 1] = ds[1]; dir_s[k * 3 + 2] = ds[2];
     ia_dir_s2w(p, ds, dw);
-    float u, v, la;
-    ia_env_uv(dw, u, v, la);
-    // pdf() (light.py:259-296)
-    int col = (int)fminf(fmaxf(floorf(u * (float)W), 0.f), (float)(W - 1));
-    int row = (int)fminf(fmaxf(floorf(v * (float)H), 0.f), (float)(H - 1));
-    float sin_theta = sinf(PI / 2.0f - la);
-    float pdf_scale = (float)((double)H * (double)W / (2.0 * 3.14159265358979323846 * 3.14159265358979323846));
-    pdf_out[k] = sin_theta > 0 ? pdf[(size_t)row * W + col] * pdf_scale / sin_theta : 0.f;
-    // eval(): bilinear grid_sample, align_corners=True, border (light.py:298-339)
-    float fx = fminf(fmaxf(((u * 2 - 1) + 1.f) / 2 * (W - 1), 0.f), (float)(W - 1));
-    float fy = fminf(fmaxf(((v * 2 - 1) + 1.f) / 2 * (H - 1), 0.f), (float)(H - 1));
-    int x0 = (int)floorf(fx), y0 = (int)floorf(fy);
-    float wx = fx - x0, wy = fy - y0;
-    int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
-    for (int ch = 0; ch < 3; ch++) {
-        float a = env[((size_t)y0 * W + x0) * 3 + ch], b = env[((size_t)y0 * W + x1) * 3 + ch];
-        float c2 = env[((size_t)y1 * W + x0) * 3 + ch], d2 = env[((size_t)y1 * W + x1) * 3 + ch];
-        em[k * 3 + ch] = a * (1 - wx) * (1 - wy) + b * wx * (1 - wy) + c2 * (1 - wx) * wy + d2 * wx * wy;
-    }
+    pdf_out[k] = ia_env_pdf(E, dw);
+    float e3[3];
+    ia_env_eval(E, dw, e3);
+    em[k * 3 + 0] = e3[0]; em[k * 3 + 1] = e3[1]; em[k * 3 + 2] = e3[2];
 }
 
-extern "C" int ia_set_light(ia_ctx* c, const float* d_env, int H, int W, const float* d_u1, const float* d_u2, int spp,
-                            float* d_dirs_out, float* d_em_out, float* d_pdf_out, void* stream) {
-    IA_REQUIRE(c && d_env && d_u1 && d_u2, IA_EINVAL, "ia_set_light: NULL argument");
-    IA_REQUIRE(spp > 1, IA_EINVAL, "ia_set_light: samples_per_pixel must be > 1 (lib/nerfacc/cdf.py:51)");
-    IA_REQUIRE(c->have_pose, IA_ESTATE, "ia_set_light: call ia_set_pose first");
-    IA_CHECK_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = (cudaStream_t)stream;
+// render_mode = uniform_light: the n_rows x n_cols stratified sphere directions of
+// sample_uniform_sphere_stratified in eval mode (lib/torch_pbr/light.py:161-217; sample_uniform_sphere,
+// warp_utils.py:174-198).  They are used as SMPL-frame ray directions as they are
+// (models/intrinsic_avatar.py:672-686); the envmap is looked up at transform_dirs_s2w(d) (:724-730).
+__global__ void k_env_uniform(const __grid_constant__ IaFrame p, const IaEnv E, int n_rows, int n_cols,
+                              float* __restrict__ dir_w, float* __restrict__ dir_s, float* __restrict__ em,
+                              float* __restrict__ pdf_out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_rows * n_cols) return;
+    const float PI = 3.14159265358979323846f;
+    const int row = k / n_cols, col = k - row * n_cols;
+    const float v = ((float)row + 0.5f) / (float)n_rows, u = ((float)col + 0.5f) / (float)n_cols;
+    const float z = v * 2.0f - 1.0f;
+    const float phi = 2.0f * PI * u;
+    const float r = sqrtf(fmaxf(1.0f - z * z, 0.f));
+    float d[3] = {cosf(phi) * r, sinf(phi) * r, z};
+    ia_normalize12(d);
+    dir_s[k * 3 + 0] = d[0]; dir_s[k * 3 + 1] = d[1]; dir_s[k * 3 + 2] = d[2];
+    float dw[3];
+    ia_dir_s2w(p, d, dw);
+    dir_w[k * 3 + 0] = dw[0]; dir_w[k * 3 + 1] = dw[1]; dir_w[k * 3 + 2] = dw[2];
+    float e3[3];
+    ia_env_eval(E, dw, e3);
+    em[k * 3 + 0] = e3[0]; em[k * 3 + 1] = e3[1]; em[k * 3 + 2] = e3[2];
+    pdf_out[k] = 1.0f / (4.0f * PI);
+}
+
+static int ia_light_alloc(ia_ctx* c, int H, int W, int spp, cudaStream_t st) {
     if (c->env_H != H || c->env_W != W) {
         if (ia_realloc(&c->d_env_pdf, (size_t)H * W) || ia_realloc(&c->d_env_cols, (size_t)H * (W + 1)) ||
             ia_realloc(&c->d_env_rows, (size_t)H + 1) || ia_realloc(&c->d_env_rowsum, (size_t)H) ||
@@ -877,20 +854,67 @@ extern "C" int ia_set_light(ia_ctx* c, const float* d_env, int H, int W, const f
         IA_CHECK_CUDA(cudaStreamSynchronize(st));
         c->spp = spp;
     }
-    IA_STAGE_BEGIN(c, IA_STAGE_LIGHT, st);
+    return IA_OK;
+}
+
+// pdf table and row / column CDFs of the envmap (update_pdf, light.py:417-446)
+static int ia_env_tables(ia_ctx* c, const float* d_env, int H, int W, cudaStream_t st) {
     IA_CHECK_CUDA(cudaMemsetAsync(c->d_env_total, 0, sizeof(double), st));
     k_env_pdf<<<H, 256, 0, st>>>(d_env, H, W, c->d_env_pdf, c->d_env_rowsum, c->d_env_total);
     k_env_cols<<<(H + 7) / 8, 256, 0, st>>>(c->d_env_pdf, H, W, c->d_env_total, c->d_env_cols, c->d_env_rowsum);
     k_env_rows<<<1, 32, 0, st>>>(c->d_env_rowsum, H, c->d_env_rows);
-    k_env_sample<<<(spp + 127) / 128, 128, 0, st>>>(c->f, d_env, H, W, c->d_env_pdf, c->d_env_cols, c->d_env_rows, d_u1,
-                                                    d_u2, spp, c->d_light_dir_w, c->d_light_dir_s, c->d_light_em,
-                                                    c->d_light_pdf);
-    IA_STAGE_END(c, IA_STAGE_LIGHT, st, 4);
-    IA_LAUNCH_CHECK();
+    c->env.env = d_env; c->env.pdf = c->d_env_pdf; c->env.cols = c->d_env_cols; c->env.rows = c->d_env_rows;
+    c->env.H = H; c->env.W = W;
+    return IA_OK;
+}
+
+static int ia_light_outputs(ia_ctx* c, int spp, float* d_dirs_out, float* d_em_out, float* d_pdf_out, cudaStream_t st) {
     if (d_dirs_out) IA_CHECK_CUDA(cudaMemcpyAsync(d_dirs_out, c->d_light_dir_w, (size_t)spp * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (d_em_out) IA_CHECK_CUDA(cudaMemcpyAsync(d_em_out, c->d_light_em, (size_t)spp * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (d_pdf_out) IA_CHECK_CUDA(cudaMemcpyAsync(d_pdf_out, c->d_light_pdf, (size_t)spp * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return IA_OK;
+}
+
+extern "C" int ia_set_light(ia_ctx* c, const float* d_env, int H, int W, const float* d_u1, const float* d_u2, int spp,
+                            float* d_dirs_out, float* d_em_out, float* d_pdf_out, void* stream) {
+    IA_REQUIRE(c && d_env && d_u1 && d_u2, IA_EINVAL, "ia_set_light: NULL argument");
+    IA_REQUIRE(spp > 1, IA_EINVAL, "ia_set_light: samples_per_pixel must be > 1 (lib/nerfacc/cdf.py:51)");
+    IA_REQUIRE(spp < 65536, IA_EINVAL, "ia_set_light: samples_per_pixel must be < 65536");
+    IA_REQUIRE(c->have_pose, IA_ESTATE, "ia_set_light: call ia_set_pose first");
+    IA_CHECK_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int e = ia_light_alloc(c, H, W, spp, st)) return e;
+    IA_STAGE_BEGIN(c, IA_STAGE_LIGHT, st);
+    if (int e = ia_env_tables(c, d_env, H, W, st)) return e;
+    k_env_sample<<<(spp + 127) / 128, 128, 0, st>>>(c->f, c->env, d_u1, d_u2, spp, c->d_light_dir_w, c->d_light_dir_s,
+                                                    c->d_light_em, c->d_light_pdf);
+    IA_STAGE_END(c, IA_STAGE_LIGHT, st, 4);
+    IA_LAUNCH_CHECK();
+    if (int e = ia_light_outputs(c, spp, d_dirs_out, d_em_out, d_pdf_out, st)) return e;
     c->have_light = true;
+    c->light_uniform = false;
+    return IA_OK;
+}
+
+extern "C" int ia_set_light_uniform(ia_ctx* c, const float* d_env, int H, int W, int n_rows, int n_cols,
+                                    float* d_dirs_out, float* d_em_out, void* stream) {
+    IA_REQUIRE(c && d_env, IA_EINVAL, "ia_set_light_uniform: NULL argument");
+    IA_REQUIRE(n_rows > 0 && n_cols > 0 && n_rows * n_cols > 1 && n_rows * n_cols < 65536, IA_EINVAL,
+               "ia_set_light_uniform: need 1 < n_rows * n_cols < 65536");
+    IA_REQUIRE(c->have_pose, IA_ESTATE, "ia_set_light_uniform: call ia_set_pose first");
+    IA_CHECK_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int spp = n_rows * n_cols;
+    if (int e = ia_light_alloc(c, H, W, spp, st)) return e;
+    IA_STAGE_BEGIN(c, IA_STAGE_LIGHT, st);
+    if (int e = ia_env_tables(c, d_env, H, W, st)) return e;
+    k_env_uniform<<<(spp + 127) / 128, 128, 0, st>>>(c->f, c->env, n_rows, n_cols, c->d_light_dir_w, c->d_light_dir_s,
+                                                     c->d_light_em, c->d_light_pdf);
+    IA_STAGE_END(c, IA_STAGE_LIGHT, st, 4);
+    IA_LAUNCH_CHECK();
+    if (int e = ia_light_outputs(c, spp, d_dirs_out, d_em_out, nullptr, st)) return e;
+    c->have_light = true;
+    c->light_uniform = true;
     return IA_OK;
 }
 

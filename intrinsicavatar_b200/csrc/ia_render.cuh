@@ -34,9 +34,13 @@ __device__ __forceinline__ void ia_ray_w2s(const IaFrame& p, const float* __rest
     far = sqrtf(o[0] * o[0] + o[1] * o[1] + o[2] * o[2]) + 1.0f;
 }
 
+// bg_rgb [n_rays][3]: what a background-assigned shading sample / an empty ray contributes to the physically
+// based buffers: the background colour, or with add_emitter the envmap along the primary ray
+// (emitter.eval(transform_dirs_s2w(rays_d)), models/intrinsic_avatar.py:1319-1341, 1454-1490).
 __global__ void k_primary_setup(const __grid_constant__ IaFrame p, const float* __restrict__ rays, long long n_rays,
                                 int* __restrict__ hit_rays, float* __restrict__ hit_od, int* __restrict__ work,
-                                ia_outputs out, float* __restrict__ acc6) {
+                                ia_outputs out, float* __restrict__ acc6, float* __restrict__ bg_rgb, const IaEnv E,
+                                int add_emitter) {
     long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool hit = false;
     float o[3], d[3], far = 0.f;
@@ -56,8 +60,16 @@ __global__ void k_primary_setup(const __grid_constant__ IaFrame p, const float* 
         if (out.comp_roughness) out.comp_roughness[r] = 0.f;
         if (out.comp_metallic) out.comp_metallic[r] = 0.f;
         if (out.num_samples) out.num_samples[r] = 0;
+        float bg[3] = {p.background[0], p.background[1], p.background[2]};
+        if (add_emitter) {
+            float dw[3];
+            ia_dir_s2w(p, d, dw);
+            ia_env_eval(E, dw, bg);
+        }
 #pragma unroll
-        for (int k = 0; k < 6; k++) acc6[r * 6 + k] = hit ? 0.f : p.background[k % 3];
+        for (int k = 0; k < 3; k++) bg_rgb[r * 3 + k] = bg[k];
+#pragma unroll
+        for (int k = 0; k < 6; k++) acc6[r * 6 + k] = hit ? 0.f : bg[k % 3];
     }
     // warp-aggregated append to the hit list
     unsigned b = __ballot_sync(0xffffffffu, hit);
@@ -487,14 +499,15 @@ __device__ __forceinline__ float ia_srgb(float f) {
 }
 
 __global__ void k_composite(const __grid_constant__ IaFrame p, long long n, const float* __restrict__ acc6, ia_outputs out,
-                            int primary_only) {
+                            int primary_only, const float* __restrict__ vis) {
     long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
+    if (out.visibility) out.visibility[r] = vis ? vis[r] : 0.f;  // uniform_light only (models/intrinsic_avatar.py:1427-1432)
     float op = out.opacity ? out.opacity[r] : 0.f;
     float bgm = (p.background[0] + p.background[1] + p.background[2]) / 3.0f;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        float phys = primary_only ? p.background[k] : acc6[r * 6 + k];
+        float phys = primary_only ? p.background[k] : acc6[r * 6 + k];  // (primary-only: acc6 may hold a hit ray's zero)
         float dem = primary_only ? p.background[k] : acc6[r * 6 + 3 + k];
         if (out.comp_rgb_phys) out.comp_rgb_phys[r * 3 + k] = phys;
         if (out.comp_demod_phys) out.comp_demod_phys[r * 3 + k] = dem;
@@ -516,7 +529,8 @@ static int ia_wf_scratch(ia_ctx* c) {
 static int ia_ws_reserve(ia_ctx* c, int64_t n_rays, int spp, bool need_pbr) {
     if (n_rays > c->ws_rays) {
         if (ia_realloc(&c->d_hit_rays, (size_t)n_rays) || ia_realloc(&c->d_hit_od, (size_t)n_rays * 8) ||
-            ia_realloc(&c->d_hit_info, (size_t)n_rays * 2) || ia_realloc(&c->d_acc, (size_t)n_rays * 6))
+            ia_realloc(&c->d_hit_info, (size_t)n_rays * 2) || ia_realloc(&c->d_acc, (size_t)n_rays * 6) ||
+            ia_realloc(&c->d_vis, (size_t)n_rays) || ia_realloc(&c->d_bg, (size_t)n_rays * 3))
             return IA_ECUDA;
         c->ws_rays = n_rays;
     }
@@ -539,6 +553,24 @@ static int ia_ws_reserve(ia_ctx* c, int64_t n_rays, int spp, bool need_pbr) {
     return IA_OK;
 }
 
+template <int MODE>
+static int ia_launch_shade(ia_ctx* c, bool gi, int64_t ray_index_base, uint32_t seed, cudaStream_t st) {
+    WfShadePolicy<MODE> pol;
+    pol.p = nullptr; pol.hit_rays = c->d_hit_rays; pol.hit_od = c->d_hit_od; pol.samples = c->d_samples;
+    pol.rs_t = c->d_rs_t; pol.rs_src = c->d_rs_src; pol.rs_w = c->d_rs_w; pol.work = c->d_work; pol.spp = c->spp;
+    pol.ray_index_base = ray_index_base; pol.seed = seed; pol.light_dir_s = c->d_light_dir_s;
+    pol.light_em = c->d_light_em; pol.light_pdf = c->d_light_pdf; pol.acc6 = c->d_acc; pol.n_total = 0; pol.gi = gi;
+    pol.env = c->env; pol.vis = MODE == IA_MODE_UNIFORM_LIGHT ? c->d_vis : nullptr; pol.bg_rgb = c->d_bg;
+    if (gi) {
+        IA_CHECK_CUDA(cudaFuncSetAttribute(k_shade_wf<true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_BYTES(true)));
+        k_shade_wf<true, MODE><<<c->n_sm * WF_CTAS_PER_SM, WF_THREADS, WF_SMEM_BYTES(true), st>>>(c->f, pol, c->d_wf_scratch, c->d_counters);
+    } else {
+        IA_CHECK_CUDA(cudaFuncSetAttribute(k_shade_wf<false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_BYTES(false)));
+        k_shade_wf<false, MODE><<<c->n_sm * WF_CTAS_PER_SM, WF_THREADS, WF_SMEM_BYTES(false), st>>>(c->f, pol, c->d_wf_scratch, c->d_counters);
+    }
+    return IA_OK;
+}
+
 extern "C" int ia_render(ia_ctx* c, const float* d_rays, int64_t n_rays, int64_t ray_index_base, int flags, uint32_t seed,
                          const ia_outputs* out, void* stream) {
     IA_REQUIRE(c && d_rays && out, IA_EINVAL, "ia_render: NULL argument");
@@ -546,7 +578,11 @@ extern "C" int ia_render(ia_ctx* c, const float* d_rays, int64_t n_rays, int64_t
                "ia_render: fields / pose / occupancy / render config must be set");
     const bool primary_only = flags & IA_RENDER_PRIMARY_ONLY;
     const bool gi = flags & IA_RENDER_GI;
+    const int mode = (flags & IA_RENDER_MODE_MASK) >> IA_RENDER_MODE_SHIFT;
+    const bool add_emitter = (flags & IA_RENDER_ADD_EMITTER) && !primary_only;
     IA_REQUIRE(primary_only || c->have_light, IA_ESTATE, "ia_render: call ia_set_light first");
+    IA_REQUIRE(primary_only || (mode == IA_MODE_UNIFORM_LIGHT) == c->light_uniform, IA_ESTATE,
+               "ia_render: render_mode uniform_light needs ia_set_light_uniform, the other modes ia_set_light");
     IA_REQUIRE(c->f.occ_res * c->f.occ_res * c->f.occ_res / 8 <= 64 * 1024, IA_EINVAL, "ia_render: occupancy grid too large for shared memory");
     IA_CHECK_CUDA(cudaSetDevice(c->device));
     if (n_rays == 0) return IA_OK;
@@ -557,7 +593,7 @@ extern "C" int ia_render(ia_ctx* c, const float* d_rays, int64_t n_rays, int64_t
     IA_CHECK_CUDA(cudaMemsetAsync(c->d_counters, 0, IA_N_COUNTERS * sizeof(unsigned long long), st));
     IA_STAGE_BEGIN(c, IA_STAGE_SETUP, st);
     k_primary_setup<<<(unsigned)((n_rays + 255) / 256), 256, 0, st>>>(c->f, d_rays, n_rays, c->d_hit_rays, c->d_hit_od, c->d_work,
-                                                                       *out, c->d_acc);
+                                                                       *out, c->d_acc, c->d_bg, c->env, add_emitter ? 1 : 0);
     IA_STAGE_END(c, IA_STAGE_SETUP, st, 1);
     IA_LAUNCH_CHECK();
     {
@@ -583,32 +619,27 @@ extern "C" int ia_render(ia_ctx* c, const float* d_rays, int64_t n_rays, int64_t
                                                 c->d_rs_t, c->d_rs_src, c->d_rs_w);
         IA_STAGE_END(c, IA_STAGE_RESAMPLE, st, 1);
         IA_LAUNCH_CHECK();
-        size_t occ_bytes = (size_t)c->f.occ_res * c->f.occ_res * c->f.occ_res / 8;
-        size_t sm = (gi ? IA_RAD_END : IA_GEO_END) * sizeof(float) + occ_bytes + IA_TILE_PIX * 6 * sizeof(float) +
-                    IA_TILE * sizeof(uint16_t);
+        if (mode == IA_MODE_UNIFORM_LIGHT) IA_CHECK_CUDA(cudaMemsetAsync(c->d_vis, 0, (size_t)n_rays * sizeof(float), st));
         IA_STAGE_BEGIN(c, IA_STAGE_SHADE, st);
         {
             // wavefront integrator: one persistent CTA per SM
             IA_REQUIRE((long long)n_rays * c->spp < (1ll << 32), IA_EINVAL, "ia_render: n_rays * spp must be < 2^32");
-            WfShadePolicy pol;
-            pol.p = nullptr; pol.hit_rays = c->d_hit_rays; pol.hit_od = c->d_hit_od; pol.samples = c->d_samples;
-            pol.rs_t = c->d_rs_t; pol.rs_src = c->d_rs_src; pol.rs_w = c->d_rs_w; pol.work = c->d_work; pol.spp = c->spp;
-            pol.ray_index_base = ray_index_base; pol.seed = seed; pol.light_dir_s = c->d_light_dir_s;
-            pol.light_em = c->d_light_em; pol.light_pdf = c->d_light_pdf; pol.acc6 = c->d_acc; pol.n_total = 0; pol.gi = gi;
             if (int e = ia_wf_scratch(c)) return e;
-            if (gi) {
-                IA_CHECK_CUDA(cudaFuncSetAttribute(k_shade_wf<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_BYTES(true)));
-                k_shade_wf<true><<<c->n_sm * WF_CTAS_PER_SM, WF_THREADS, WF_SMEM_BYTES(true), st>>>(c->f, pol, c->d_wf_scratch, c->d_counters);
-            } else {
-                IA_CHECK_CUDA(cudaFuncSetAttribute(k_shade_wf<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_BYTES(false)));
-                k_shade_wf<false><<<c->n_sm * WF_CTAS_PER_SM, WF_THREADS, WF_SMEM_BYTES(false), st>>>(c->f, pol, c->d_wf_scratch, c->d_counters);
+            int e = IA_OK;
+            switch (mode) {
+                case IA_MODE_LIGHT: e = ia_launch_shade<IA_MODE_LIGHT>(c, gi, ray_index_base, seed, st); break;
+                case IA_MODE_UNIFORM_LIGHT: e = ia_launch_shade<IA_MODE_UNIFORM_LIGHT>(c, gi, ray_index_base, seed, st); break;
+                case IA_MODE_MATS: e = ia_launch_shade<IA_MODE_MATS>(c, gi, ray_index_base, seed, st); break;
+                default: e = ia_launch_shade<IA_MODE_MIS>(c, gi, ray_index_base, seed, st); break;
             }
+            if (e) return e;
         }
         IA_STAGE_END(c, IA_STAGE_SHADE, st, 1);
         IA_LAUNCH_CHECK();
     }
     IA_STAGE_BEGIN(c, IA_STAGE_COMPOSITE, st);
-    k_composite<<<(unsigned)((n_rays + 255) / 256), 256, 0, st>>>(c->f, n_rays, c->d_acc, *out, primary_only ? 1 : 0);
+    k_composite<<<(unsigned)((n_rays + 255) / 256), 256, 0, st>>>(c->f, n_rays, c->d_acc, *out, primary_only ? 1 : 0,
+                                                                  (!primary_only && mode == IA_MODE_UNIFORM_LIGHT) ? c->d_vis : nullptr);
     IA_STAGE_END(c, IA_STAGE_COMPOSITE, st, 1);
     IA_LAUNCH_CHECK();
     return IA_OK;
@@ -830,6 +861,66 @@ extern "C" int ia_op_brdf(ia_ctx* c, const float* d_wi, const float* d_n, const 
     if (n == 0) return IA_OK;
     k_op_brdf<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_wi, d_n, d_wo, d_rough, d_albedo, d_metal, n, d_diff,
                                                                            d_spec);
+    IA_LAUNCH_CHECK();
+    return IA_OK;
+}
+
+__global__ void k_op_bsdf(const float* __restrict__ wi, const float* __restrict__ nn, const float* __restrict__ rough,
+                          const float* __restrict__ albedo, const float* __restrict__ metal, const float* __restrict__ sample,
+                          const float* __restrict__ woq, long long n, float* __restrict__ wo, float* __restrict__ pdf) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a[3] = {wi[i * 3], wi[i * 3 + 1], wi[i * 3 + 2]}, b[3] = {nn[i * 3], nn[i * 3 + 1], nn[i * 3 + 2]};
+    const float al[3] = {albedo[i * 3], albedo[i * 3 + 1], albedo[i * 3 + 2]};
+    float d[3] = {0.f, 0.f, 1.f};
+    if (wo && sample) {
+        ia_multilobe_sample(b, a, rough[i], al, metal[i], sample[i * 2], sample[i * 2 + 1], d);
+        wo[i * 3] = d[0]; wo[i * 3 + 1] = d[1]; wo[i * 3 + 2] = d[2];
+    }
+    if (pdf) {
+        if (woq) { d[0] = woq[i * 3]; d[1] = woq[i * 3 + 1]; d[2] = woq[i * 3 + 2]; }
+        pdf[i] = ia_multilobe_pdf(a, b, d, rough[i], al, metal[i]);
+    }
+}
+
+extern "C" int ia_op_bsdf_sample_pdf(ia_ctx* c, const float* d_wi, const float* d_n, const float* d_rough,
+                                     const float* d_albedo, const float* d_metal, const float* d_sample,
+                                     const float* d_wo_query, int64_t n, float* d_wo, float* d_pdf, void* stream) {
+    IA_REQUIRE(c && d_wi && d_n && d_rough && d_albedo && d_metal, IA_EINVAL, "ia_op_bsdf_sample_pdf: NULL argument");
+    IA_REQUIRE(!d_wo || d_sample, IA_EINVAL, "ia_op_bsdf_sample_pdf: d_wo needs d_sample");
+    IA_REQUIRE(!d_pdf || d_wo_query || d_wo, IA_EINVAL, "ia_op_bsdf_sample_pdf: d_pdf needs d_wo_query or d_wo");
+    if (n == 0) return IA_OK;
+    k_op_bsdf<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_wi, d_n, d_rough, d_albedo, d_metal, d_sample,
+                                                                           d_wo_query, n, d_wo, d_pdf);
+    IA_LAUNCH_CHECK();
+    return IA_OK;
+}
+
+__global__ void k_op_env(const IaEnv E, const float* __restrict__ u, const float* __restrict__ dirs, long long n,
+                         float* __restrict__ dirs_out, float* __restrict__ pdf, float* __restrict__ em) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float d[3] = {0.f, 0.f, 1.f};
+    if (u) {
+        ia_env_sample(E, u[i * 2], u[i * 2 + 1], d);
+        if (dirs_out) { dirs_out[i * 3] = d[0]; dirs_out[i * 3 + 1] = d[1]; dirs_out[i * 3 + 2] = d[2]; }
+    }
+    if (dirs) { d[0] = dirs[i * 3]; d[1] = dirs[i * 3 + 1]; d[2] = dirs[i * 3 + 2]; }
+    if (pdf) pdf[i] = ia_env_pdf(E, d);
+    if (em) {
+        float e3[3];
+        ia_env_eval(E, d, e3);
+        em[i * 3] = e3[0]; em[i * 3 + 1] = e3[1]; em[i * 3 + 2] = e3[2];
+    }
+}
+
+extern "C" int ia_op_env(ia_ctx* c, const float* d_u, const float* d_dirs_world, int64_t n, float* d_dirs_world_out,
+                         float* d_pdf_out, float* d_em_out, void* stream) {
+    IA_REQUIRE(c && (d_u || d_dirs_world), IA_EINVAL, "ia_op_env: need uniforms or directions");
+    IA_REQUIRE(c->have_light, IA_ESTATE, "ia_op_env: call ia_set_light first");
+    if (n == 0) return IA_OK;
+    k_op_env<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(c->env, d_u, d_dirs_world, n, d_dirs_world_out,
+                                                                          d_pdf_out, d_em_out);
     IA_LAUNCH_CHECK();
     return IA_OK;
 }

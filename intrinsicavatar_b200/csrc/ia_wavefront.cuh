@@ -446,7 +446,9 @@ __device__ __forceinline__ void wf_gi_phase(const IaFrame& p, WfShared& S, unsig
 // ------------------------------------------------------------------------------------------------
 // One round of the ray state machines.  Policy P supplies rays and consumes their transmittance:
 //   bool P::init(const uint2 entry, float o[3], float d[3])   ray of a ring entry
-//   void P::finish(const uint2 entry, float T, const float ind[3])   shade / store (ind = indirect radiance, GI)
+//   void P::finish(const uint2 entry, float T, const float ind[3], const float d[3])   shade / store (ind = indirect
+//                                                                     radiance, GI; d = the ray direction)
+//   int P::tile_items()   shading samples examined per feed step (each may push up to WF_QCAP / 2 / tile_items() rays)
 template <bool GI, class P>
 __device__ __forceinline__ void wf_advance_slot(const IaFrame& p, P& pol, WfShared& S, const int t, int ring_tail,
                                                 unsigned& c_q, unsigned& c_rays) {
@@ -624,7 +626,7 @@ __device__ __forceinline__ void wf_advance_slot(const IaFrame& p, P& pol, WfShar
             {
                 float ind[3] = {0.f, 0.f, 0.f};
                 if (GI && stage == WF_FINE) { ind[0] = S.st[WS_IND][t]; ind[1] = S.st[WS_IND + 1][t]; ind[2] = S.st[WS_IND + 2][t]; }
-                pol.finish(entry, Tfin, ind);
+                pol.finish(entry, Tfin, ind, d);
             }
             stage = WF_IDLE;
             active = false;
@@ -674,7 +676,8 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
     for (int t = tid; t < WF_R; t += blockDim.x) S.st[WS_PACK][t] = __uint_as_float(0u);
     if (tid == 0) { S.ring_head = 0; S.ring_tail = 0; S.more_tiles = 1; S.n_q = 0; S.n_gtask = 0; S.task_next = 0; }
     __syncthreads();
-    const long long n_tiles = (pol.n_items() + WF_FEED - 1) / WF_FEED;
+    const int tile_items = pol.tile_items();
+    const long long n_tiles = (pol.n_items() + tile_items - 1) / tile_items;
     unsigned c_q = 0, c_fetch = 0, c_geo = 0, c_rays = 0, c_skip = 0, c_qg = 0, c_rad = 0;
     while (true) {
         // ---- feed the ring while it cannot fill every slot
@@ -690,7 +693,7 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
             }
             __syncthreads();
             const int tl = S.tile;
-            if (tl < n_tiles) pol.feed((long long)tl * WF_FEED, S);
+            if (tl < n_tiles) pol.feed((long long)tl * tile_items, S);
             __syncthreads();
         }
         __syncthreads();
@@ -761,8 +764,16 @@ __device__ __forceinline__ void wf_ring_push(WfShared& S, bool live, uint2 e) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Policy 1: the shading stage (pbr_light_forward, models/intrinsic_avatar.py:755-861)
+// Policy 1: the shading stage.  One policy, four integrators (config.model.render_mode):
+//   IA_MODE_LIGHT          pbr_light_forward          models/intrinsic_avatar.py:755-861  (table of spp light directions)
+//   IA_MODE_UNIFORM_LIGHT  pbr_uniform_light_forward  :654-753  (stratified sphere table, inv_pdf = 4 pi, visibility map)
+//   IA_MODE_MATS           pbr_mats_forward           :863-948  (BSDF sampling, one ray per shading sample)
+//   IA_MODE_MIS            pbr_mis_forward            :547-652  (BSDF + light sampling, two rays per shading sample)
+enum { IA_MODE_LIGHT = 0, IA_MODE_UNIFORM_LIGHT = 1, IA_MODE_MATS = 2, IA_MODE_MIS = 3 };
+
+template <int MODE>
 struct WfShadePolicy {
+    static constexpr int mode = MODE;   // compile-time: the default light path carries none of the other integrators' code
     const IaFrame* p;
     const int* hit_rays; const float* hit_od; const IaSample* samples;
     const float* rs_t; const int* rs_src; const float* rs_w;
@@ -771,12 +782,17 @@ struct WfShadePolicy {
     float* acc6;
     long long n_total;
     int gi;
+    IaEnv env;     // mats / mis: per-direction envmap look-ups
+    float* vis;    // uniform_light: [n_rays] visibility accumulator
+    const float* bg_rgb;  // [n_rays][3] radiance of a background-assigned sample (background colour or envmap)
 
     __device__ __forceinline__ long long n_items() const { return n_total; }
     __device__ __forceinline__ int* tile_counter() const { return &work[IA_W_TILE_NEXT]; }
+    __device__ __forceinline__ int tile_items() const { return mode == IA_MODE_MIS ? WF_FEED / 2 : WF_FEED; }
 
     __device__ __forceinline__ void feed(long long s0, WfShared& S) {
-        for (int i = threadIdx.x; i < WF_FEED; i += blockDim.x) {
+        const int n_it = tile_items();
+        for (int i = threadIdx.x; i < n_it; i += blockDim.x) {
             const long long s = s0 + i;
             bool live = false;
             uint2 e = make_uint2(0, 0);
@@ -788,11 +804,15 @@ struct WfShadePolicy {
                     // background-assigned shading sample (models/intrinsic_avatar.py:1319-1341)
                     const float w = rs_w[s];
                     float* pa = acc6 + (size_t)hit_rays[slot] * 6;
+                    const float* bg = bg_rgb + (size_t)hit_rays[slot] * 3;
 #pragma unroll
                     for (int k = 0; k < 3; k++) {
-                        atomicAdd(&pa[k], w * p->background[k]);
-                        atomicAdd(&pa[3 + k], w * p->background[k]);
+                        atomicAdd(&pa[k], w * bg[k]);
+                        atomicAdd(&pa[3 + k], w * bg[k]);
                     }
+                } else if (mode >= IA_MODE_MATS) {
+                    live = true;  // no cosine mask: every foreground sample traces its sampled direction(s)
+                    e = make_uint2(su, 0);
                 } else {
                     const float* n = samples[src].n;
                     uint32_t key = ia_pixel_key(seed, (uint64_t)(ray_index_base + hit_rays[slot]));
@@ -804,6 +824,7 @@ struct WfShadePolicy {
                 }
             }
             wf_ring_push(S, live, e);
+            if (mode == IA_MODE_MIS) wf_ring_push(S, live, make_uint2(e.x, 1));  // the light-sampled ray of the pair
         }
     }
 
@@ -812,27 +833,85 @@ struct WfShadePolicy {
         const float t = rs_t[e.x];
         const float* od = hit_od + (size_t)slot * 8;
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            o[k] = od[k] + od[3 + k] * t;
-            d[k] = light_dir_s[e.y * 3 + k];
+        for (int k = 0; k < 3; k++) o[k] = od[k] + od[3 + k] * t;
+        if (mode >= IA_MODE_MATS) {
+            const uint32_t j = e.x % (unsigned)spp;
+            const uint32_t key = ia_pixel_key(seed, (uint64_t)(ray_index_base + hit_rays[slot]));
+            if (e.y == 0) {
+                // scatterer.sample (MultiLobe.sample, lib/torch_pbr/bxdf.py:332-388) in the SMPL frame
+                const IaSample sm = samples[rs_src[e.x]];
+                const float wi[3] = {-od[3], -od[4], -od[5]};
+                ia_multilobe_sample(sm.n, wi, sm.rough, sm.albedo, sm.metal, ia_rng_uniform(key, j, 0),
+                                    ia_rng_uniform(key, j, 1), d);
+            } else {
+                // emitter.sample -> transform_dirs_w2s (models/intrinsic_avatar.py:578-580)
+                float dw[3];
+                ia_env_sample(env, ia_rng_uniform(key, j, 2), ia_rng_uniform(key, j, 3), dw);
+                ia_dir_w2s(*p, dw, d);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; k++) d[k] = light_dir_s[e.y * 3 + k];
         }
     }
 
-    __device__ __forceinline__ void finish(const uint2 e, float T, const float ind[3]) const {
+    __device__ __forceinline__ void finish(const uint2 e, float T, const float ind[3], const float d[3]) const {
         const int slot = (int)(e.x / (unsigned)spp);
-        const unsigned kk = e.y;
         const IaSample sm = samples[rs_src[e.x]];
         const float w = rs_w[e.x];
         const float* od = hit_od + (size_t)slot * 8;
         const float wi[3] = {-od[3], -od[4], -od[5]};
+        float* pa = acc6 + (size_t)hit_rays[slot] * 6;
+        float diff, spec[3];
+        if (mode >= IA_MODE_MATS) {
+            const float wo[3] = {d[0], d[1], d[2]};
+            ia_brdf_multilobe(wi, sm.n, wo, sm.rough, sm.albedo, sm.metal, diff, spec);
+            const float pdf_s = ia_multilobe_pdf(wi, sm.n, wo, sm.rough, sm.albedo, sm.metal);
+            float dw[3], em[3];
+            ia_dir_s2w(*p, wo, dw);
+            ia_env_eval(env, dw, em);
+            float pdf = 1.0f, misw = 0.f;
+            if (mode == IA_MODE_MIS) {
+                const float sum = pdf_s + ia_env_pdf(env, dw);
+                misw = sum > 1e-6f ? 1.0f / sum : 0.f;
+            } else {
+                pdf = pdf_s > 0.f ? pdf_s : 1.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                float Li = em[k] * T;  // (transmittance is not clamped on these two paths)
+                if (gi) Li += ind[k];
+                float Ld, Ls;
+                if (mode == IA_MODE_MIS) { Ld = (Li * diff) * misw; Ls = (Li * spec[k]) * misw; }
+                else { Ld = Li * diff / pdf; Ls = Li * spec[k] / pdf; }
+                float kd = (1.0f - sm.metal) * sm.albedo[k];
+                atomicAdd(&pa[k], w * (kd * Ld + Ls));
+                atomicAdd(&pa[3 + k], w * (Ld + Ls));
+            }
+            return;
+        }
+        const unsigned kk = e.y;
         const float wo[3] = {light_dir_s[kk * 3], light_dir_s[kk * 3 + 1], light_dir_s[kk * 3 + 2]};
         float tr = fminf(fmaxf(T, 0.f), 1.f);
-        float diff, spec[3];
         ia_brdf_multilobe(wi, sm.n, wo, sm.rough, sm.albedo, sm.metal, diff, spec);
         bool lit = tr > 0.0f;
+        if (mode == IA_MODE_UNIFORM_LIGHT) {
+            const float inv_pdf = 4.0f * 3.14159265358979323846f;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                float em = lit ? light_em[kk * 3 + k] : 0.f;
+                float Li = em * tr;
+                if (gi) Li += ind[k];
+                float Ld = Li * diff * inv_pdf, Ls = Li * spec[k] * inv_pdf;
+                float kd = (1.0f - sm.metal) * sm.albedo[k];
+                atomicAdd(&pa[k], w * (kd * Ld + Ls));
+                atomicAdd(&pa[3 + k], w * (Ld + Ls));
+            }
+            if (vis) atomicAdd(&vis[hit_rays[slot]], w * (2.0f * tr));
+            return;
+        }
         float pdf = lit ? light_pdf[kk] : 1.0f;
         if (!(pdf > 0)) pdf = 1.0f;
-        float* pa = acc6 + (size_t)hit_rays[slot] * 6;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             float em = lit ? light_em[kk * 3 + k] : 0.f;
@@ -848,8 +927,8 @@ struct WfShadePolicy {
 
 #define WF_SMEM_BYTES(GI) (((sizeof(WfShared) + 15) & ~(size_t)15) + ((GI) ? IA_RAD_END : IA_GEO_END) * sizeof(float))
 
-template <bool GI>
-__global__ void __launch_bounds__(WF_THREADS, WF_CTAS_PER_SM) k_shade_wf(const __grid_constant__ IaFrame p, WfShadePolicy pol,
+template <bool GI, int MODE>
+__global__ void __launch_bounds__(WF_THREADS, WF_CTAS_PER_SM) k_shade_wf(const __grid_constant__ IaFrame p, WfShadePolicy<MODE> pol,
                                                             unsigned char* __restrict__ scratch,
                                                             unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char wf_smem[];
@@ -865,6 +944,7 @@ struct WfRaysPolicy {
     const float* ro; const float* rd; long long n; float* T_out; float* rgb_out; int* work;
     __device__ __forceinline__ long long n_items() const { return n; }
     __device__ __forceinline__ int* tile_counter() const { return &work[IA_W_TILE_NEXT]; }
+    __device__ __forceinline__ int tile_items() const { return WF_FEED; }
     __device__ __forceinline__ void feed(long long s0, WfShared& S) {
         for (int i = threadIdx.x; i < WF_FEED; i += blockDim.x) {
             const long long s = s0 + i;
@@ -875,7 +955,7 @@ struct WfRaysPolicy {
 #pragma unroll
         for (int k = 0; k < 3; k++) { o[k] = ro[(size_t)e.x * 3 + k]; d[k] = rd[(size_t)e.x * 3 + k]; }
     }
-    __device__ __forceinline__ void finish(const uint2 e, float T, const float ind[3]) const {
+    __device__ __forceinline__ void finish(const uint2 e, float T, const float ind[3], const float*) const {
         T_out[e.x] = T;
         if (rgb_out) { rgb_out[(size_t)e.x * 3] = ind[0]; rgb_out[(size_t)e.x * 3 + 1] = ind[1]; rgb_out[(size_t)e.x * 3 + 2] = ind[2]; }
     }

@@ -22,6 +22,7 @@ _ARGTYPES = {
     "ia_build_occupancy": [_vp, _vp, _i32, _vp, _vp, _vp],
     "ia_set_occupancy": [_vp, _vp, _i32, _vp, _vp],
     "ia_set_light": [_vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
+    "ia_set_light_uniform": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
     "ia_render": [_vp, _vp, _i64, _i64, _i32, _u32, C.POINTER(IaOutputs), _vp],
     "ia_get_counters": [_vp, _vp, _vp],
     "ia_set_timing": [_vp, _i32],
@@ -37,6 +38,8 @@ _ARGTYPES = {
     "ia_op_unpack_info": [_vp, _vp, _i64, _vp, _vp],
     "ia_op_secondary": [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp],
     "ia_op_brdf": [_vp] * 7 + [_i64, _vp, _vp, _vp],
+    "ia_op_bsdf_sample_pdf": [_vp] * 8 + [_i64, _vp, _vp, _vp],
+    "ia_op_env": [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
 }
 
 OUTPUT_SPECS = [  # name, channels, dtype
@@ -47,6 +50,7 @@ OUTPUT_SPECS = [  # name, channels, dtype
     ("comp_rgb_full", 3, torch.float32), ("comp_rgb_phys_full", 3, torch.float32),
     ("comp_demod_phys_full", 3, torch.float32), ("comp_albedo_full", 3, torch.float32),
     ("comp_roughness_full", 1, torch.float32), ("comp_metallic_full", 1, torch.float32),
+    ("visibility", 1, torch.float32),
 ]
 
 
@@ -163,18 +167,35 @@ class RenderEngine:
         self.spp = spp
         return (d, e, p) if return_tables else None
 
+    def set_light_uniform(self, envmap, n_rows=16, n_cols=32, return_tables=False):
+        """render_mode = uniform_light: stratified-sphere light table (samples_per_pixel = n_rows * n_cols)."""
+        env = torch.as_tensor(envmap, dtype=torch.float32).to(self.dev).contiguous()
+        self._keep["env"] = env
+        spp = n_rows * n_cols
+        H, W = env.shape[:2]
+        d = e = None
+        if return_tables:
+            d = torch.empty(spp, 3, device=self.dev)
+            e = torch.empty(spp, 3, device=self.dev)
+        check(self.lib.ia_set_light_uniform(self.h, ptr(env), H, W, n_rows, n_cols, ptr(d), ptr(e), _stream()),
+              "ia_set_light_uniform")
+        self.spp = spp
+        return (d, e) if return_tables else None
+
     # ------------------------------------------------------------------------ render ----
     def alloc_outputs(self, n):
         return {name: torch.empty(n, ch, dtype=dt, device=self.dev) for name, ch, dt in OUTPUT_SPECS}
 
-    def render(self, rays: torch.Tensor, *, primary_only=False, gi=False, seed=0, ray_index_base=0, outputs=None):
+    def render(self, rays: torch.Tensor, *, primary_only=False, gi=False, seed=0, ray_index_base=0, outputs=None,
+               render_mode="light", add_emitter=False):
         """rays: CUDA float32 [n,8].  Returns dict of CUDA tensors (no sync)."""
         assert rays.is_cuda and rays.dtype == torch.float32 and rays.shape[-1] == 8
         rays = rays.contiguous()
         n = rays.shape[0]
         out = outputs if outputs is not None else self.alloc_outputs(n)
         st = IaOutputs(**{name: out[name].data_ptr() for name, _, _ in OUTPUT_SPECS})
-        flags = (capi.RENDER_PRIMARY_ONLY if primary_only else 0) | (capi.RENDER_GI if gi else 0)
+        flags = (capi.RENDER_PRIMARY_ONLY if primary_only else 0) | (capi.RENDER_GI if gi else 0) | \
+            capi.RENDER_MODES[render_mode] | (capi.RENDER_ADD_EMITTER if add_emitter else 0)
         check(self.lib.ia_render(self.h, ptr(rays), n, ray_index_base, flags, seed, C.byref(st), _stream()), "ia_render")
         return out
 
@@ -323,3 +344,25 @@ class RenderEngine:
         diff, spec = torch.empty(m, device=self.dev), torch.empty(m, 3, device=self.dev)
         check(self.lib.ia_op_brdf(self.h, *[ptr(t) for t in a], m, ptr(diff), ptr(spec), _stream()), "ia_op_brdf")
         return diff, spec
+
+    def op_bsdf_sample_pdf(self, wi, n, rough, albedo, metal, sample=None, wo_query=None):
+        """MultiLobe.sample (explicit uniforms) and MultiLobe.pdf: returns (wo or None, pdf or None)."""
+        a = [t.to(self.dev, torch.float32).contiguous() for t in (wi, n, rough, albedo, metal)]
+        m = a[0].shape[0]
+        smp = sample.to(self.dev, torch.float32).contiguous() if sample is not None else None
+        woq = wo_query.to(self.dev, torch.float32).contiguous() if wo_query is not None else None
+        wo = torch.empty(m, 3, device=self.dev) if smp is not None else None
+        pdf = torch.empty(m, device=self.dev) if (woq is not None or wo is not None) else None
+        check(self.lib.ia_op_bsdf_sample_pdf(self.h, *[ptr(t) for t in a], ptr(smp), ptr(woq), m, ptr(wo), ptr(pdf),
+                                             _stream()), "ia_op_bsdf_sample_pdf")
+        return wo, pdf
+
+    def op_env(self, u=None, dirs_world=None):
+        """EnvironmentLightTensor.sample / pdf / eval per direction on the tables of the last set_light call."""
+        uu = u.to(self.dev, torch.float32).contiguous() if u is not None else None
+        dd = dirs_world.to(self.dev, torch.float32).contiguous() if dirs_world is not None else None
+        m = (uu if uu is not None else dd).shape[0]
+        dout = torch.empty(m, 3, device=self.dev) if uu is not None else None
+        pdf, em = torch.empty(m, device=self.dev), torch.empty(m, 3, device=self.dev)
+        check(self.lib.ia_op_env(self.h, ptr(uu), ptr(dd), m, ptr(dout), ptr(pdf), ptr(em), _stream()), "ia_op_env")
+        return dout, pdf, em

@@ -7,7 +7,8 @@ Keeps the reference surface (models/intrinsic_avatar.py:166-305, 1653-1674):
   ``load_state_dict`` with the reference's parameter keys (weights.py).
 It adds ``render_image`` / ``render_image_relight`` conveniences named by BASELINE.json.
 
-Only the eval render path is implemented (render_mode = "light"); training-mode calls raise.
+Only the eval render path is implemented (render_mode = light | uniform_light | mats | mis, with or without
+global_illumination / add_emitter); training-mode calls raise.
 Every numeric step runs in libia_b200.so; this file is glue (pose -> 24 matrices, pointer passing).
 """
 from __future__ import annotations
@@ -51,11 +52,13 @@ class IntrinsicAvatarModel(torch.nn.Module):
         if config:
             self.config.update(config)
         cfg = self.config
-        if cfg["render_mode"] != "light":
-            raise NotImplementedError("only render_mode='light' is on the accelerated path (SURVEY.md 8f.1)")
-        if not (cfg["secondary_importance_sample"] and cfg["zero_crossing_search"]) or cfg["add_emitter"] \
-                or cfg["material_feature"] != "hybrid":
-            raise NotImplementedError("non-default secondary sampling / add_emitter / material_feature not supported")
+        if cfg["render_mode"] not in ("light", "uniform_light", "mats", "mis"):
+            # same failure as the reference's dispatch (models/intrinsic_avatar.py:1435-1438)
+            raise NotImplementedError(f"Render mode {cfg['render_mode']} not supported.")
+        if cfg["render_mode"] == "uniform_light":
+            assert cfg["samples_per_pixel"] == 512  # models/intrinsic_avatar.py:1391 (16 x 32 stratified sphere)
+        if not (cfg["secondary_importance_sample"] and cfg["zero_crossing_search"]) or cfg["material_feature"] != "hybrid":
+            raise NotImplementedError("non-default secondary sampling / material_feature not supported")
         self.engine = RenderEngine(device)
         self.setup_snarf = SnarfSetup(body)
         self.layout = W.hashgrid_layout()
@@ -134,7 +137,10 @@ class IntrinsicAvatarModel(torch.nn.Module):
                     light_uniforms = (torch.rand(spp, device=self.engine.dev), torch.rand(spp, device=self.engine.dev))
                 self._light_key = light_uniforms
             # directions live in the per-frame SMPL-root frame: refresh the tables every frame
-            self.engine.set_light(batch["hdri"], self._light_key[0], self._light_key[1])
+            if self.config["render_mode"] == "uniform_light":
+                self.engine.set_light_uniform(batch["hdri"], 16, 32)
+            else:
+                self.engine.set_light(batch["hdri"], self._light_key[0], self._light_key[1])
 
     # -------------------------------------------------------------------- forward ----
     def forward(self, rays: torch.Tensor, move_to_cpu: bool = True) -> dict:
@@ -145,7 +151,8 @@ class IntrinsicAvatarModel(torch.nn.Module):
         dev = self.engine.dev
         r = rays.to(dev, torch.float32, non_blocking=True)
         primary_only = self.albedo_only or not self.engine.spp
-        o = self.engine.render(r, primary_only=primary_only, gi=bool(self.config["global_illumination"]), seed=self.seed)
+        o = self.engine.render(r, primary_only=primary_only, gi=bool(self.config["global_illumination"]), seed=self.seed,
+                               render_mode=self.config["render_mode"], add_emitter=bool(self.config["add_emitter"]))
         n = r.shape[0]
         bg = torch.as_tensor(self.background_color, dtype=torch.float32, device=dev)
         valid = o["opacity"] > 0
@@ -156,6 +163,8 @@ class IntrinsicAvatarModel(torch.nn.Module):
             "comp_rgb_phys": o["comp_rgb_phys"], "comp_demod_phys": o["comp_demod_phys"],
             "comp_albedo": o["comp_albedo"], "comp_metallic": o["comp_metallic"], "comp_roughness": o["comp_roughness"],
         }
+        if self.config["render_mode"] == "uniform_light":
+            out["visibility"] = o["visibility"]      # models/intrinsic_avatar.py:1516-1517
         zeros_b = torch.zeros_like(valid)
         out_bg = {
             "comp_rgb": bg[None].expand(n, 3), "num_samples": torch.zeros_like(out["num_samples"]),

@@ -307,3 +307,24 @@ def pixel_key(seed: int, ray_index: np.ndarray) -> np.ndarray:
     x = _u32(x * np.uint64(0x846ca68b))
     x ^= x >> np.uint64(16)
     return x
+
+
+def _mix32(x):
+    x = np.asarray(x, np.uint64)
+    x = x ^ (x >> np.uint64(16))
+    x = _u32(x * np.uint64(0x7feb352d))
+    x = x ^ (x >> np.uint64(15))
+    x = _u32(x * np.uint64(0x846ca68b))
+    x = x ^ (x >> np.uint64(16))
+    return x
+
+
+def rng_uniform(key: np.ndarray, j: np.ndarray, dim: int) -> torch.Tensor:
+    """Counter-based uniform in [0,1) (24 bits) standing in for the reference's torch.rand in
+    MultiLobe.sample / emitter.sample: stream ``dim`` of shading sample ``j`` of the pixel with key ``key``
+    (= pixel_key(seed, ray index)).  Same integer recipe as ia_rng_uniform (csrc/ia_pbr.cuh)."""
+    key = np.asarray(key, np.uint64)
+    j = np.asarray(j, np.uint64)
+    inner = _u32(j * np.uint64(0x9E3779B9) + np.uint64(dim) * np.uint64(0x85EBCA6B) + np.uint64(0x6A09E667))
+    x = _mix32(key ^ _mix32(inner))
+    return torch.from_numpy(((x >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)))

@@ -5,15 +5,17 @@ evaluation, no fusion) so it is an independent check of the fused kernels:
 
   prepare            models/intrinsic_avatar.py:281-381 (+ models/utils.py:152-163)
   forward_           models/intrinsic_avatar.py:950-1651  (eval, enable_phys, importance_sample,
-                     render_mode = "light"; albedo_only supported)
+                     render_mode = light | uniform_light | mats | mis; albedo_only, add_emitter supported)
   compute_indirect_radiance   models/intrinsic_avatar.py:396-545
-  pbr_light_forward  models/intrinsic_avatar.py:755-861
+  pbr_light_forward / pbr_uniform_light_forward / pbr_mats_forward / pbr_mis_forward
+                     models/intrinsic_avatar.py:755-861, 654-753, 863-948, 547-652
   rendering_with_normals_mats_sdf / rendering   models/volrend.py:810-1020, 19-194
   sample_volume_interaction   models/pbr/utils.py:70-229
   transform_rays_w2s / dirs   models/deformers/snarf_deformer.py:128-158
 
 Randomness is an explicit input: occupancy jitter ``[res^3,3,3]``, light uniforms ``u1,u2 [spp]``
-and the permutation ``seed`` (oracle/pbr.py) -- SURVEY.md section 7 "RNG".
+and the ``seed`` of the per-ray permutation / of the counter-based uniforms that replace ``torch.rand``
+in MultiLobe.sample and emitter.sample (oracle/pbr.py) -- SURVEY.md section 7 "RNG".
 """
 from __future__ import annotations
 
@@ -23,7 +25,8 @@ import torch.nn.functional as F
 
 from . import ops
 from .deformer import deform, precompute
-from .pbr import EnvLight, kensler_permute, multilobe_eval, pixel_key, rgb_to_srgb
+from .pbr import (EnvLight, kensler_permute, multilobe_eval, multilobe_pdf, multilobe_sample, pixel_key, rgb_to_srgb,
+                  rng_uniform, uniform_sphere_stratified)
 
 SCENE_AABB = (-1.25, -1.55, -1.25, 1.25, 0.95, 1.25)  # configs/dataset/animation/male-3-casual.yaml:10
 
@@ -36,7 +39,10 @@ class OracleRenderer:
     def __init__(self, fields, lbs_voxel, offset_kernel, scale_kernel, *, samples_per_pixel=4,
                  global_illumination=False, num_samples_per_ray=128, num_samples_per_secondary_ray=64,
                  secondary_near=0.0, secondary_far=1.5, occ_thre=0.001, grid_res=64,
-                 query_chunk=65536):
+                 query_chunk=65536, render_mode="light", add_emitter=False):
+        assert render_mode in ("light", "uniform_light", "mats", "mis")
+        self.render_mode = render_mode
+        self.add_emitter = add_emitter
         self.fields = fields
         self.lbs_voxel = torch.as_tensor(lbs_voxel, dtype=torch.float32)
         self.offset = torch.as_tensor(offset_kernel, dtype=torch.float32)
@@ -102,6 +108,12 @@ class OracleRenderer:
         self.light_dirs_world = self.env.sample(torch.as_tensor(u1, dtype=torch.float32),
                                                 torch.as_tensor(u2, dtype=torch.float32))
         assert self.light_dirs_world.shape[0] == self.spp
+
+    def set_light_uniform(self, envmap, n_rows=16, n_cols=32):
+        """render_mode = uniform_light: stratified sphere directions, used in the SMPL frame as they are."""
+        self.env = EnvLight(torch.as_tensor(envmap, dtype=torch.float32))
+        self.uniform_dirs = uniform_sphere_stratified(n_rows, n_cols)
+        assert self.uniform_dirs.shape[0] == self.spp
 
     # ------------------------------------------------------------------------ transforms ----
     def dirs_w2s(self, d):
@@ -179,6 +191,79 @@ class OracleRenderer:
         kd = (1.0 - metallic) * albedo
         Lo = kd * Lo_diff + Lo_spec
         return Lo, Lo_diff, Lo_spec
+
+    def _compose(self, Li_diff, Li_spec, albedo, metallic):
+        kd = (1.0 - metallic) * albedo
+        return kd * Li_diff + Li_spec
+
+    def pbr_uniform_light_forward(self, normal, albedo, roughness, metallic, positions, dirs, light_idx):
+        """models/intrinsic_avatar.py:654-753 (eval: fixed 16x32 directions, inv_pdf = 4 pi)."""
+        wi = -dirs
+        sec_d = self.uniform_dirs[light_idx]
+        inv_pdf = 4 * np.pi
+        cos_mask = (normal * sec_d).sum(-1) > 1e-6
+        tr = torch.zeros(len(cos_mask), 1)
+        sec_rgb = torch.zeros(len(cos_mask), 3)
+        if cos_mask.sum() > 0:
+            t_, r_ = self.compute_indirect_radiance(positions[cos_mask], sec_d[cos_mask])
+            tr[cos_mask] = t_
+            sec_rgb[cos_mask] = r_
+            tr.clamp_(0.0, 1.0)
+        tr_mask = tr[:, 0] > 0.0
+        diff = torch.zeros_like(albedo[:, :1])
+        spec = torch.zeros_like(albedo)
+        if cos_mask.sum() > 0:
+            diff[cos_mask], spec[cos_mask] = multilobe_eval(
+                wi[cos_mask], normal[cos_mask], sec_d[cos_mask], roughness[cos_mask, 0], albedo[cos_mask],
+                metallic[cos_mask])
+        em = torch.zeros_like(sec_rgb)
+        m = cos_mask & tr_mask
+        if m.sum() > 0:
+            em[m] = self.env.eval(self.dirs_s2w(sec_d[m]))
+        Li = em * tr + sec_rgb if self.gi else em * tr
+        Lo_diff = Li * diff * inv_pdf
+        Lo_spec = Li * spec * inv_pdf
+        vis = 2 * torch.ones_like(em) * tr
+        return self._compose(Lo_diff, Lo_spec, albedo, metallic), Lo_diff, Lo_spec, vis
+
+    def _scatter_dirs(self, normal, albedo, roughness, metallic, wi, key, j):
+        u = torch.stack([rng_uniform(key, j, 0), rng_uniform(key, j, 1)], -1)
+        return multilobe_sample(normal, wi, roughness[:, 0], albedo, metallic, u)
+
+    def pbr_mats_forward(self, normal, albedo, roughness, metallic, positions, dirs, key, j):
+        """models/intrinsic_avatar.py:863-948: BSDF sampling, no cosine mask, transmittance not clamped."""
+        wi = -dirs
+        sec_d = self._scatter_dirs(normal, albedo, roughness, metallic, wi, key, j)
+        tr, sec_rgb = self.compute_indirect_radiance(positions, sec_d)
+        pdf = multilobe_pdf(wi, normal, sec_d, roughness[:, 0], albedo, metallic)
+        pdf = torch.where(pdf > 0, pdf, torch.ones_like(pdf))
+        diff, spec = multilobe_eval(wi, normal, sec_d, roughness[:, 0], albedo, metallic)
+        em = self.env.eval(self.dirs_s2w(sec_d))
+        Li = em * tr + sec_rgb if self.gi else em * tr
+        Lo_diff = Li * diff / pdf
+        Lo_spec = Li * spec / pdf
+        return self._compose(Lo_diff, Lo_spec, albedo, metallic), Lo_diff, Lo_spec
+
+    def pbr_mis_forward(self, normal, albedo, roughness, metallic, positions, dirs, key, j):
+        """models/intrinsic_avatar.py:547-652: one BSDF-sampled and one light-sampled ray per shading sample,
+        each weighted 1 / (pdf_scatter + pdf_light)."""
+        wi = -dirs
+        scatter_d = self._scatter_dirs(normal, albedo, roughness, metallic, wi, key, j)
+        light_d = self.dirs_w2s(self.env.sample(rng_uniform(key, j, 2), rng_uniform(key, j, 3)))
+        sec_d = torch.cat([scatter_d, light_d], 0)
+        tr, sec_rgb = self.compute_indirect_radiance(positions.repeat(2, 1), sec_d)
+        n2, wi2, r2, a2, m2 = normal.repeat(2, 1), wi.repeat(2, 1), roughness[:, 0].repeat(2), albedo.repeat(2, 1), \
+            metallic.repeat(2, 1)
+        pdf_s = multilobe_pdf(wi2, n2, sec_d, r2, a2, m2)
+        pdf_l = self.env.pdf(self.dirs_s2w(sec_d))
+        diff, spec = multilobe_eval(wi2, n2, sec_d, r2, a2, m2)
+        em = self.env.eval(self.dirs_s2w(sec_d))
+        Li = em * tr + sec_rgb if self.gi else em * tr
+        w = torch.where(pdf_s + pdf_l > 1e-6, torch.reciprocal(pdf_s + pdf_l), torch.zeros_like(pdf_s))
+        Lo_diff = (Li * diff) * w
+        Lo_spec = (Li * spec) * w
+        Lo = self._compose(Lo_diff, Lo_spec, a2, m2)
+        return (Lo.reshape(2, -1, 3).sum(0), Lo_diff.reshape(2, -1, 3).sum(0), Lo_spec.reshape(2, -1, 3).sum(0))
 
     # ------------------------------------------------------------------- primary rays -----
     def forward(self, rays, seed=0, ray_chunk=4096, albedo_only=False):
@@ -261,8 +346,13 @@ class OracleRenderer:
         depth_map = depth_map + (1.0 - acc_map) * far[:, None]
 
         bgc = self.background
-        rgb_phys = bgc[None].expand(n_rays, 3).clone()
+        # add_emitter: the envmap seen along the primary ray replaces the background colour
+        # (models/intrinsic_avatar.py:1319-1341, 1454-1490)
+        bg_ray = self.env.eval(self.dirs_s2w(rays_d)) if (self.add_emitter and not albedo_only) else \
+            bgc[None].expand(n_rays, 3)
+        rgb_phys = bg_ray.clone()
         demod_phys = rgb_phys.clone()
+        visibility = torch.zeros(n_rays, 1)
         if S > 0 and not albedo_only:
             spp = self.spp
             (rpi, rts, roffs, ridx, fg_cnt, bg_cnt, _surf) = ops.ray_resampling(
@@ -271,11 +361,11 @@ class OracleRenderer:
             bg_i = torch.nonzero(roffs[:, 0] >= 1e4)[:, 0]
             rri = ops.unpack_info(rpi, len(rts))
             if fg_i.numel() > 0:
-                fg_ray, bg_ray = rri[fg_i], rri[bg_i]
+                fg_ray, bg_ray_i = rri[fg_i], rri[bg_i]
                 src = ridx[fg_i]
                 rw = torch.zeros(len(rts))
                 rw[fg_i] = weights[src] / fg_cnt[src].float()
-                rw[bg_i] = (1.0 - acc_map)[bg_ray, 0] / bg_cnt[bg_ray].float()
+                rw[bg_i] = (1.0 - acc_map)[bg_ray_i, 0] / bg_cnt[bg_ray_i].float()
                 t = rts[fg_i]
                 positions = rays_o[fg_ray] + rays_d[fg_ray] * t
                 # per-(ray, sample) light index: sample j of a hit ray is its j-th resample
@@ -283,17 +373,26 @@ class OracleRenderer:
                 key = pixel_key(seed, fg_ray.numpy() + ray_offset)
                 light_idx = torch.from_numpy(kensler_permute(j.astype(np.uint64), spp, key))
                 Lo = torch.zeros(len(rts), 3)
-                Lo[bg_i] = bgc[None]
+                Lo[bg_i] = bg_ray[bg_ray_i]
                 Lo_demod = Lo.clone()
-                fg_Lo, fg_d, fg_s = self.pbr_light_forward(
-                    normal_smpl[src], albedo[src], rough[src], metal[src], positions, rays_d[fg_ray], light_idx)
+                args = (normal_smpl[src], albedo[src], rough[src], metal[src], positions, rays_d[fg_ray])
+                if self.render_mode == "light":
+                    fg_Lo, fg_d, fg_s = self.pbr_light_forward(*args, light_idx)
+                elif self.render_mode == "uniform_light":
+                    fg_Lo, fg_d, fg_s, fg_vis = self.pbr_uniform_light_forward(*args, light_idx)
+                    vis = torch.zeros(len(rts), 3)
+                    vis[fg_i] = fg_vis
+                    visibility = acc(rw, vis, rri, n_rays).mean(-1, keepdim=True)
+                else:
+                    fwd = self.pbr_mats_forward if self.render_mode == "mats" else self.pbr_mis_forward
+                    fg_Lo, fg_d, fg_s = fwd(*args, key, j)
                 Lo[fg_i] = fg_Lo
                 Lo_demod[fg_i] = fg_d + fg_s
                 rgb_phys = acc(rw, Lo, rri, n_rays)
                 demod_phys = acc(rw, Lo_demod, rri, n_rays)
                 empty = torch.nonzero(rpi[:, 1] <= 0)[:, 0]
-                rgb_phys[empty] = bgc[None]
-                demod_phys[empty] = bgc[None]
+                rgb_phys[empty] = bg_ray[empty]
+                demod_phys[empty] = bg_ray[empty]
 
         out = {
             "comp_rgb": rgb_map, "comp_normal": normal_map, "opacity": acc_map, "depth": depth_map,
@@ -311,5 +410,7 @@ class OracleRenderer:
             "comp_roughness_full": rough_map + bgm * (1.0 - acc_map),
         }
         out.update(full)
+        if self.render_mode == "uniform_light":
+            out["visibility"] = visibility
         out["num_samples_per_ray"] = spacked[:, 1:2].clone()
         return out

@@ -127,3 +127,93 @@ def test_full_size_properties(scene):
     assert float((two - 2 * one).abs().max()) <= 1e-4 * float(one.abs().max() + 1)
     c = e.counters()
     assert c["overflow"] == 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# the other integrators of config.model.render_mode and add_emitter
+def _setup_mode(scene, mode, spp, H, gi=False, add_emitter=False, frame_idx=None, grid=(2, 4)):
+    from oracle.render import OracleRenderer
+    fr = scene.frame(frame_idx)
+    R = OracleRenderer(scene.fields, scene.snarf.lbs_voxel, scene.snarf.offset_kernel, scene.snarf.scale_kernel,
+                       samples_per_pixel=spp, global_illumination=gi, render_mode=mode, add_emitter=add_emitter)
+    R.set_pose(fr["tfs"], fr["w2s"])
+    tabs = scene.syn.random_tables(spp, 64, seed=0)
+    R.build_occupancy(fr["deformed_bbox"], tabs["jitter"])
+    env = scene.syn.load_envmap()
+    e = scene.engine()
+    e.set_pose(fr["tfs"], fr["w2s"])
+    e.set_occupancy(fr["deformed_bbox"], R.binaries)
+    if mode == "uniform_light":
+        assert grid[0] * grid[1] == spp
+        R.set_light_uniform(env, *grid)
+        e.set_light_uniform(env, *grid)
+    else:
+        R.set_light(env, tabs["u1"], tabs["u2"])
+        e.set_light(env, tabs["u1"], tabs["u2"])
+    rays = torch.from_numpy(scene.syn.make_rays(H, H, fr["transl"]))
+    return R, e, rays
+
+
+@pytest.mark.parametrize("mode,gi", [("uniform_light", False), ("mats", False), ("mis", False), ("mats", True),
+                                     ("uniform_light", True)])
+def test_render_mode_frame_parity(scene, mode, gi):
+    """64x64 / 8 spp neutral-pose frame in render_mode = uniform_light | mats | mis against the oracle's
+    restatement of pbr_uniform_light_forward / pbr_mats_forward / pbr_mis_forward: relative L2 <= 1e-3."""
+    R, e, rays = _setup_mode(scene, mode, 8, 64, gi=gi)
+    ref = R.forward(rays, seed=0)
+    got = e.render(rays.cuda(), gi=gi, seed=0, render_mode=mode)
+    torch.cuda.synchronize()
+    assert (ref["opacity"] > 0.5).float().mean() > 0.05
+    keys = ["comp_rgb", "comp_albedo", "opacity", "comp_rgb_phys", "comp_demod_phys", "comp_rgb_phys_full"]
+    if mode == "uniform_light":
+        keys.append("visibility")
+        assert float(ref["visibility"].max()) > 0.5
+    for k in keys:
+        err = rel_l2(got[k], ref[k])
+        assert err <= 1e-3, (mode, gi, k, err)
+    assert e.counters()["secondary_rays"] > 0
+
+
+def test_render_mode_light_state_is_checked(scene):
+    """uniform_light needs the stratified table, the other modes the importance-sampled one: a mismatch is an
+    error, not a silently different image."""
+    R, e, rays = _setup_mode(scene, "light", 4, 16)
+    with pytest.raises(RuntimeError, match="uniform_light"):
+        e.render(rays.cuda(), render_mode="uniform_light")
+
+
+def test_add_emitter_frame_parity(scene):
+    """config.model.add_emitter: the envmap along the primary ray replaces the white background in the
+    physically based buffers (models/intrinsic_avatar.py:1319-1341, 1454-1490)."""
+    R, e, rays = _setup_mode(scene, "light", 4, 64, add_emitter=True)
+    ref = R.forward(rays, seed=0)
+    got = e.render(rays.cuda(), seed=0, add_emitter=True)
+    for k in ("comp_rgb_phys", "comp_demod_phys", "comp_rgb", "opacity"):
+        assert rel_l2(got[k], ref[k]) <= 1e-3, (k, rel_l2(got[k], ref[k]))
+    miss = got["num_samples"][:, 0] == 0
+    assert miss.any() and not (got["comp_rgb_phys"][miss] == 1.0).all()     # not the white background any more
+
+
+def test_mis_matches_light_in_expectation(scene):
+    """Size-independent property: the four estimators integrate the same rendering equation, so the frame
+    means of comp_rgb_phys over opaque pixels agree statistically (128x128, 64 spp; 512 for uniform_light)."""
+    means = {}
+    for mode, spp, grid in (("light", 64, None), ("mats", 64, None), ("mis", 64, None), ("uniform_light", 512, (16, 32))):
+        fr = scene.frame(0)
+        e = scene.engine()
+        e.set_pose(fr["tfs"], fr["w2s"])
+        tabs = scene.syn.random_tables(spp, 64, seed=2)
+        e.build_occupancy(fr["deformed_bbox"], tabs["jitter"], 64)
+        env = scene.syn.load_envmap()
+        if grid:
+            e.set_light_uniform(env, *grid)
+        else:
+            e.set_light(env, tabs["u1"], tabs["u2"])
+        rays = torch.from_numpy(scene.syn.make_rays(128, 128, fr["transl"])).cuda()
+        o = e.render(rays, seed=1, render_mode=mode)
+        hit = o["opacity"][:, 0] > 0.99
+        assert torch.isfinite(o["comp_rgb_phys"]).all()
+        means[mode] = float(o["comp_rgb_phys"][hit].mean())
+    ref = means["mis"]
+    for mode, m in means.items():
+        assert abs(m - ref) / ref < 0.15, means

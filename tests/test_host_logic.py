@@ -1,5 +1,7 @@
 """CPU (-m "not gpu"): host-side logic and the oracle's own invariants / edge cases (empty and ragged
 inputs, sign-change snapping, permutations), at sizes that run in seconds."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -197,3 +199,59 @@ def test_oracle_tiny_frame(scene):
     assert out["opacity"].max() <= 1 + 1e-5 and torch.isfinite(out["comp_rgb_phys"]).all()
     prim = R.forward(rays, seed=0, albedo_only=True)
     assert torch.equal(prim["comp_albedo"], out["comp_albedo"]) and (prim["comp_rgb_phys"] == 1).all()
+
+
+def test_counter_rng_is_uniform_and_decorrelated():
+    """oracle.pbr.rng_uniform (the stand-in for torch.rand in MultiLobe.sample / emitter.sample)."""
+    from oracle.pbr import rng_uniform
+    key = pixel_key(3, np.arange(4096, dtype=np.int64))
+    j = np.arange(64, dtype=np.uint64)
+    u = torch.stack([rng_uniform(key[:, None], j[None, :], d) for d in range(4)], -1)     # [4096, 64, 4]
+    assert u.min() >= 0 and u.max() < 1
+    assert abs(float(u.mean()) - 0.5) < 2e-3 and abs(float(u.var()) - 1 / 12) < 2e-3
+    flat = u.reshape(-1, 4)
+    c = torch.corrcoef(flat.t())
+    assert float((c - torch.eye(4)).abs().max()) < 5e-3                                    # streams independent
+    assert float(torch.corrcoef(torch.stack([u[:-1, :, 0].reshape(-1), u[1:, :, 0].reshape(-1)]))[0, 1].abs()) < 5e-3
+
+
+@pytest.mark.parametrize("mode", ["uniform_light", "mats", "mis"])
+def test_oracle_render_modes_tiny_frame(scene, mode):
+    """The oracle's restatements of pbr_uniform_light_forward / pbr_mats_forward / pbr_mis_forward run end to end
+    on a 12x12 / 8 spp frame: finite, non-negative radiance, white background on missed rays, visibility map."""
+    from oracle.render import OracleRenderer
+    fr = scene.frame(0)
+    R = OracleRenderer(scene.fields, scene.snarf.lbs_voxel, scene.snarf.offset_kernel, scene.snarf.scale_kernel,
+                       samples_per_pixel=8, grid_res=16, render_mode=mode)
+    R.set_pose(fr["tfs"], fr["w2s"])
+    tabs = scene.syn.random_tables(8, 16, seed=0)
+    R.build_occupancy(fr["deformed_bbox"], tabs["jitter"])
+    env = scene.syn.load_envmap()
+    if mode == "uniform_light":
+        R.set_light_uniform(env, 2, 4)
+    else:
+        R.set_light(env, tabs["u1"], tabs["u2"])
+    rays = torch.from_numpy(scene.syn.make_rays(12, 12, fr["transl"]))
+    out = R.forward(rays, seed=0)
+    miss = out["opacity"][:, 0] == 0
+    assert miss.any() and (~miss).any()
+    assert (out["comp_rgb_phys"][miss] == 1).all()
+    assert torch.isfinite(out["comp_rgb_phys"]).all() and out["comp_rgb_phys"].min() >= 0
+    if mode == "uniform_light":
+        assert out["visibility"].shape == (144, 1) and (out["visibility"][miss] == 0).all()
+        assert 0 < float(out["visibility"].max()) <= 2 + 1e-5
+    else:
+        assert "visibility" not in out
+
+
+def test_render_flag_constants_match_header():
+    """capi.RENDER_* mirror the IA_RENDER_* macros of include/ia_b200.h."""
+    import re
+    from intrinsicavatar_b200 import capi
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "ia_b200.h")).read()
+    shift = int(re.search(r"#define IA_RENDER_MODE_SHIFT (\d+)", src).group(1))
+    for name, macro in (("light", "LIGHT"), ("uniform_light", "UNIFORM_LIGHT"), ("mats", "MATS"), ("mis", "MIS")):
+        v = int(re.search(rf"#define IA_RENDER_{macro} \((\d+) << IA_RENDER_MODE_SHIFT\)", src).group(1))
+        assert capi.RENDER_MODES[name] == v << shift
+    assert capi.RENDER_ADD_EMITTER == int(re.search(r"#define IA_RENDER_ADD_EMITTER (\d+)", src).group(1))
+    assert capi.RENDER_GI == 2 and capi.RENDER_PRIMARY_ONLY == 1
