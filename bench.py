@@ -151,13 +151,17 @@ def cpu_baseline(args, steps=1, warmup=0):
     env = syn.load_envmap()
     rays = torch.from_numpy(syn.make_rays(res, res, tr))
     R = OracleRenderer(Fields(folded, layout, snarf.bbox), snarf.lbs_voxel, snarf.offset_kernel, snarf.scale_kernel,
-                       samples_per_pixel=spp, global_illumination=bool(args.gi), grid_res=args.cpu_grid)
+                       samples_per_pixel=spp, global_illumination=bool(args.gi), grid_res=args.cpu_grid,
+                       render_mode=args.render_mode)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         R.set_pose(fr["tfs"], fr["w2s"])
         R.build_occupancy(fr["deformed_bbox"], tabs["jitter"])
-        R.set_light(env, tabs["u1"], tabs["u2"])
+        if args.render_mode == "uniform_light":
+            R.set_light_uniform(env, 2, spp // 2)
+        else:
+            R.set_light(env, tabs["u1"], tabs["u2"])
         R.forward(rays, seed=0)
         if it >= warmup:
             times.append(time.perf_counter() - t0)
@@ -169,7 +173,7 @@ def cpu_baseline(args, steps=1, warmup=0):
 
 def workload_config(args):
     return {
-        "workload": f"{args.res}x{args.res} relight frame, {args.spp} spp, render_mode=light, "
+        "workload": f"{args.res}x{args.res} relight frame, {args.spp} spp, render_mode={args.render_mode}, "
                     f"global_illumination={'true' if args.gi else 'false'}, prepare+forward per step",
         "frame_source": "AIST pose frames 0..7 (frame = (step + rank) mod 8), synthetic 24-joint body, random-init "
                         "hash grids + MLPs (seed 0), city.hdr envmap (8x area-downsampled copy, re-expanded to 1024x2048)",
@@ -188,6 +192,8 @@ def main():
     ap.add_argument("--res", type=int, default=512)
     ap.add_argument("--spp", type=int, default=1024)
     ap.add_argument("--gi", type=int, default=0)
+    ap.add_argument("--render-mode", default="light", choices=["light", "uniform_light", "mats", "mis"],
+                    help="config.model.render_mode (uniform_light needs --spp 512); the headline workload is light")
     ap.add_argument("--cpu-res", type=int, default=32)
     ap.add_argument("--cpu-spp", type=int, default=8)
     ap.add_argument("--cpu-grid", type=int, default=32)
@@ -219,7 +225,8 @@ def main():
     from intrinsicavatar_b200 import parallel, synthetic as syn
     from intrinsicavatar_b200.model import IntrinsicAvatarModel
 
-    cfg = {"samples_per_pixel": args.spp, "global_illumination": bool(args.gi), "scene_aabb": SCENE_AABB}
+    cfg = {"samples_per_pixel": args.spp, "global_illumination": bool(args.gi), "scene_aabb": SCENE_AABB,
+           "render_mode": args.render_mode}
     model = IntrinsicAvatarModel(cfg, device=local_rank, seed=0)
     model.train(False)
     model.update_step(250, 25000)
@@ -298,9 +305,10 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        ms_e2e, _, _, _, _ = timed(step_e2e, args.steps, min(args.warmup, 1))
-        out = step_e2e(0)
-        d2h = sum(v.numel() * v.element_size() for k, v in out.items() if torch.is_tensor(v) and k != "beta")
+        # same warm-up count as the device arm, so that both arms time the same frames ((step + rank) mod 8)
+        ms_e2e, _, _, _, _ = timed(step_e2e, args.steps, args.warmup)
+        # forward() brings every output buffer of the frame to the host in one packed copy (engine.outputs_to_host)
+        d2h = eng.alloc_outputs(1)["_block"].numel() * 4 * n_rays
         h2d = frames[0]["rays_h"].numel() * 4 + env_h.numel() * 4 + (24 * 16 + 16) * 4
         e2e = {"value": samples_per_step * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}

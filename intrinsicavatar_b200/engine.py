@@ -183,8 +183,26 @@ class RenderEngine:
         return (d, e) if return_tables else None
 
     # ------------------------------------------------------------------------ render ----
-    def alloc_outputs(self, n):
-        return {name: torch.empty(n, ch, dtype=dt, device=self.dev) for name, ch, dt in OUTPUT_SPECS}
+    def alloc_outputs(self, n, device=None, pin_memory=False):
+        """All output buffers of one forward pass as views of ONE block (key "_block", 4-byte words), so that a
+        frame leaves the device with a single copy.  Each view is a contiguous [n, C] tensor as the C ABI wants."""
+        total = sum(ch for _, ch, _ in OUTPUT_SPECS) * n
+        block = torch.empty(total, dtype=torch.float32, device=self.dev if device is None else device,
+                            pin_memory=pin_memory)
+        out, off = {"_block": block}, 0
+        for name, ch, dt in OUTPUT_SPECS:
+            seg = block[off:off + n * ch]
+            out[name] = (seg if dt == torch.float32 else seg.view(dt)).view(n, ch)
+            off += n * ch
+        return out
+
+    def outputs_to_host(self, out):
+        """One D2H copy of a packed output set into pinned host memory; returns the same views on the host."""
+        n = out["opacity"].shape[0]
+        host = self.alloc_outputs(n, device="cpu", pin_memory=True)
+        host["_block"].copy_(out["_block"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host
 
     def render(self, rays: torch.Tensor, *, primary_only=False, gi=False, seed=0, ray_index_base=0, outputs=None,
                render_mode="light", add_emitter=False):

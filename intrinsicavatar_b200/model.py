@@ -154,7 +154,11 @@ class IntrinsicAvatarModel(torch.nn.Module):
         o = self.engine.render(r, primary_only=primary_only, gi=bool(self.config["global_illumination"]), seed=self.seed,
                                render_mode=self.config["render_mode"], add_emitter=bool(self.config["add_emitter"]))
         n = r.shape[0]
-        bg = torch.as_tensor(self.background_color, dtype=torch.float32, device=dev)
+        if move_to_cpu:
+            # eval outputs are CPU tensors (models/utils.py:48-55): one packed D2H copy into pinned memory
+            o = self.engine.outputs_to_host(o)
+            dev = torch.device("cpu")
+        bg = torch.as_tensor(self.background_color, dtype=torch.float32).to(dev)
         valid = o["opacity"] > 0
         out = {
             "comp_rgb": o["comp_rgb"], "comp_normal": o["comp_normal"], "opacity": o["opacity"], "depth": o["depth"],
@@ -179,8 +183,6 @@ class IntrinsicAvatarModel(torch.nn.Module):
             "comp_metallic": o["comp_metallic_full"], "comp_roughness": o["comp_roughness_full"],
         }
         res = {**out, **{k + "_bg": v for k, v in out_bg.items()}, **{k + "_full": v for k, v in out_full.items()}}
-        if move_to_cpu:
-            res = {k: v.cpu() for k, v in res.items()}
         res["beta"] = torch.tensor(self._beta)
         return res
 
