@@ -31,10 +31,20 @@
 #define WF_BROYDEN_LANES 1   // lanes per Broyden chain: 1 (one thread per chain) or 3 (row-distributed)
 #endif
 #ifndef WF_R
-#define WF_R 512       // ray slots per CTA
-#endif
-#define WF_QCAP 2048   // ring capacity (power of two)
+#define WF_R 1024      // ray slots per CTA (two per thread): longer phases amortise the barriers and phase tails.
+#endif                 // Measured at 512^2 x 1024 spp: R = 512 775 ms, 1024 743 ms, 1536 752 ms, 2048 751 ms, 4096 804 ms;
+                       // 2 CTAs x 256 threads per SM: R = 256 773 ms, 512 756 ms, 1024 751 ms (no gain from co-resident CTAs)
+#ifndef WF_FEED
 #define WF_FEED 1024   // items examined per feed step
+#endif
+// ring capacity: a power of two >= WF_R + WF_FEED (the ring is fed while it holds fewer than WF_R entries)
+#if WF_R + WF_FEED <= 2048
+#define WF_QCAP 2048
+#elif WF_R + WF_FEED <= 4096
+#define WF_QCAP 4096
+#else
+#define WF_QCAP 8192
+#endif
 #define WF_NST 36      // state words per ray
 #ifndef WF_STATE_GLOBAL
 #define WF_STATE_GLOBAL 1
