@@ -16,9 +16,24 @@
 
 // ------------------------------------------------------------------------------------------------
 // small math helpers
+// torch.nn.Softplus(beta=100, threshold=20) (models/network_utils.py:201-244 via get_activation).
+// IA_SOFTPLUS_FAST = 0: the reference's own expression log1p(exp(beta x)) / beta with libdevice expf / log1pf / IEEE
+//   division (~40 instructions; 4 per lane and geometry evaluation = a third of the geometry phase).
+// IA_SOFTPLUS_FAST = 1 (default): the algebraically identical max(x, 0) + log1p(exp(-|beta x|)) / beta on the
+//   MUFU ex2 / lg2 units (~8 instructions).  The correction term is <= ln 2 / 100, so the absolute error of the
+//   approximate exp / log (<= 2e-7) enters the result as <= 2e-9 -- below the one-ulp (~7e-9 at 0.1) rounding noise
+//   the reference's expression has itself.
+#ifndef IA_SOFTPLUS_FAST
+#define IA_SOFTPLUS_FAST 1
+#endif
 __device__ __forceinline__ float ia_softplus100(float x) {
     float bx = 100.0f * x;
-    return bx > 20.0f ? x : log1pf(expf(bx)) / 100.0f;  // torch.nn.Softplus(beta=100, threshold=20)
+#if IA_SOFTPLUS_FAST
+    if (bx > 20.0f) return x;
+    return fmaxf(x, 0.f) + __logf(1.0f + __expf(-fabsf(bx))) * 0.01f;
+#else
+    return bx > 20.0f ? x : log1pf(expf(bx)) / 100.0f;
+#endif
 }
 __device__ __forceinline__ float ia_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 

@@ -106,6 +106,7 @@ struct WfShared {
     unsigned short* btask;  // [WF_R * 13] Broyden task list (pruned)
     int n_btask;
     int n_q, task_next, n_gtask, ring_head, ring_tail, tile, more_tiles, pad;
+    unsigned probe;         // WF_PROBE_SAMECELL builds: Broyden trips that stayed in the voxel cell of the previous trip
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -193,6 +194,10 @@ __device__ __forceinline__ void wf_broyden_phase_1lane(const IaFrame& p, WfShare
     float x0 = 0, x1 = 0, x2 = 0, xd0 = 0, xd1 = 0, xd2 = 0, g0 = 0, g1 = 0, g2 = 0;
     float Ji[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     int it = 0, q = 0, c = 0;
+#ifdef WF_PROBE_SAMECELL
+    int prev_cell = -1;
+    unsigned c_same = 0;
+#endif
     while (task >= 0) {
         float u0 = 0, u1 = 0, u2 = 0;
         if (fresh) {
@@ -216,6 +221,14 @@ __device__ __forceinline__ void wf_broyden_phase_1lane(const IaFrame& p, WfShare
         float J[12];
         ia_fetch_J(p, ix, iy, iz, J);
         c_fetch++;
+#ifdef WF_PROBE_SAMECELL
+        {
+            const IaCorners cn = ia_corners(p, ix, iy, iz);
+            const int cell = (cn.z0 * 256 + cn.y0) * 256 + cn.x0;
+            if (!fresh && cell == prev_cell) c_same++;
+            prev_cell = cell;
+        }
+#endif
         const float n0 = J[0] * x0 + J[1] * x1 + J[2] * x2 + J[3] - xd0;
         const float n1 = J[4] * x0 + J[5] * x1 + J[6] * x2 + J[7] - xd1;
         const float n2 = J[8] * x0 + J[9] * x1 + J[10] * x2 + J[11] - xd2;
@@ -261,6 +274,9 @@ __device__ __forceinline__ void wf_broyden_phase_1lane(const IaFrame& p, WfShare
             }
         }
     }
+#ifdef WF_PROBE_SAMECELL
+    if (c_same) atomicAdd(&S.probe, c_same);
+#endif
 }
 
 #if WF_BROYDEN_LANES == 3
@@ -684,7 +700,7 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
     if (tid < IA_N_INIT * 12) S.tfs13[tid] = p.tfs[p.init_bones[tid / 12]][tid % 12];
     if (tid < IA_N_LEVELS) S.lvl[tid] = ia_level(p, tid);
     for (int t = tid; t < WF_R; t += blockDim.x) S.st[WS_PACK][t] = __uint_as_float(0u);
-    if (tid == 0) { S.ring_head = 0; S.ring_tail = 0; S.more_tiles = 1; S.n_q = 0; S.n_gtask = 0; S.task_next = 0; }
+    if (tid == 0) { S.ring_head = 0; S.ring_tail = 0; S.more_tiles = 1; S.n_q = 0; S.n_gtask = 0; S.task_next = 0; S.probe = 0; }
     __syncthreads();
     const int tile_items = pol.tile_items();
     const long long n_tiles = (pol.n_items() + tile_items - 1) / tile_items;
@@ -753,6 +769,10 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
         c_qg += __shfl_xor_sync(0xffffffffu, c_qg, o);
         c_rad += __shfl_xor_sync(0xffffffffu, c_rad, o);
     }
+#ifdef WF_PROBE_SAMECELL
+    __syncthreads();
+    if (tid == 0 && S.probe) atomicAdd(&counters[IA_CNT_OVERFLOW], (unsigned long long)S.probe);
+#endif
     if ((tid & 31) == 0) {
         if (c_q) atomicAdd(&counters[IA_CNT_QUERIES], c_q);
         if (c_fetch) atomicAdd(&counters[IA_CNT_BROYDEN_FETCH], c_fetch);
