@@ -924,3 +924,91 @@ extern "C" int ia_op_env(ia_ctx* c, const float* d_u, const float* d_dirs_world,
     IA_LAUNCH_CHECK();
     return IA_OK;
 }
+
+// ================================================================================================
+// Frame producer / consumer either side of the render path
+//
+// k_make_rays: AnimationDataset's rays (datasets/animation.py:13-34 make_rays, :29-33 transform_rays, :163-189
+// __getitem__; concatenated to [n,8] by systems/intrinsic_avatar.py:100-109) generated on the device instead of
+// being built with numpy per frame and copied over PCIe (8.4 MB per 512^2 frame).  The reference does this in
+// float64 (K and the extrinsics are float64 arrays) and casts to float32 at the end; so does the kernel.
+//   Kinv  : inv(K), row-major 3x3        c2w : the dataset-level camera (identity for AnimationDataset), 3x4
+//   ext   : inv(w2c) of the frame, 3x4   (test split; identity otherwise)
+__global__ void k_make_rays(const double* __restrict__ m, int H, int W, float near_, float far_, float* __restrict__ rays) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)H * W) return;
+    const double* Kinv = m;       // [9]
+    const double* c2w = m + 9;    // [12]
+    const double* ext = m + 21;   // [12]
+    const double x = (double)(float)(i % W), y = (double)(float)(i / W);
+    // d_c = [x, y, 1] @ inv(K).T ; d_w = d_c @ c2w[:3,:3].T, normalised
+    double dc[3], dw[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) dc[r] = x * Kinv[r * 3 + 0] + y * Kinv[r * 3 + 1] + 1.0 * Kinv[r * 3 + 2];
+#pragma unroll
+    for (int r = 0; r < 3; r++) dw[r] = dc[0] * c2w[r * 4 + 0] + dc[1] * c2w[r * 4 + 1] + dc[2] * c2w[r * 4 + 2];
+    const double nrm = sqrt(dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2]);
+    // make_rays returns float32; transform_rays then works on those float32 arrays with a float32 c2w
+    float o32[3], d32[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) { d32[r] = (float)(dw[r] / nrm); o32[r] = (float)c2w[r * 4 + 3]; }
+    float* out = rays + i * 8;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const float e0 = (float)ext[r * 4 + 0], e1 = (float)ext[r * 4 + 1], e2 = (float)ext[r * 4 + 2], e3 = (float)ext[r * 4 + 3];
+        out[r] = o32[0] * e0 + o32[1] * e1 + o32[2] * e2 + e3;
+        out[3 + r] = d32[0] * e0 + d32[1] * e1 + d32[2] * e2;
+    }
+    out[6] = near_;
+    out[7] = far_;
+}
+
+extern "C" int ia_make_rays(ia_ctx* c, const double* h_Kinv9, const double* h_c2w12, const double* h_ext12, int H, int W,
+                            float near_plane, float far_plane, float* d_rays, void* stream) {
+    IA_REQUIRE(c && h_Kinv9 && d_rays, IA_EINVAL, "ia_make_rays: NULL argument");
+    IA_REQUIRE(H > 0 && W > 0, IA_EINVAL, "ia_make_rays: empty image");
+    IA_CHECK_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    static const double ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    double h[33];
+    memcpy(h, h_Kinv9, 9 * sizeof(double));
+    memcpy(h + 9, h_c2w12 ? h_c2w12 : ident, 12 * sizeof(double));
+    memcpy(h + 21, h_ext12 ? h_ext12 : ident, 12 * sizeof(double));
+    if (!c->d_cam) IA_CHECK_CUDA(cudaMalloc((void**)&c->d_cam, sizeof(h)));
+    IA_CHECK_CUDA(cudaMemcpyAsync(c->d_cam, h, sizeof(h), cudaMemcpyHostToDevice, st));
+    IA_CHECK_CUDA(cudaStreamSynchronize(st));  // h is a stack buffer
+    const long long n = (long long)H * W;
+    k_make_rays<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->d_cam, H, W, near_plane, far_plane, d_rays);
+    c->n_launches += 1;
+    IA_LAUNCH_CHECK();
+    return IA_OK;
+}
+
+// k_pack_rgb8: SaverMixin.get_rgb_image_ (utils/mixins.py:43-53) on the device: clip to [lo, hi], scale to 0..255,
+// truncate to uint8 (numpy astype), optional RGB -> BGR swap (cv2.cvtColor before cv2.imwrite).  A frame then
+// leaves the device as 1 byte per channel instead of 4.
+__global__ void k_pack_rgb8(const float* __restrict__ img, long long n_pix, int C, float lo, float hi, int bgr,
+                            uint8_t* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pix * C) return;
+    const long long p = i / C;
+    const int ch = (int)(i - p * C);
+    float v = img[i];
+    v = fminf(fmaxf(v, lo), hi);
+    v = (v - lo) / (hi - lo) * 255.f;
+    const int oc = (bgr && C >= 3 && ch < 3) ? 2 - ch : ch;
+    out[p * C + oc] = (uint8_t)v;
+}
+
+extern "C" int ia_pack_rgb8(ia_ctx* c, const float* d_img, int64_t n_pix, int channels, float lo, float hi, int bgr,
+                            uint8_t* d_out, void* stream) {
+    IA_REQUIRE(c && d_img && d_out, IA_EINVAL, "ia_pack_rgb8: NULL argument");
+    IA_REQUIRE(channels > 0 && hi > lo, IA_EINVAL, "ia_pack_rgb8: bad channels / data range");
+    if (n_pix == 0) return IA_OK;
+    IA_CHECK_CUDA(cudaSetDevice(c->device));
+    const long long n = (long long)n_pix * channels;
+    k_pack_rgb8<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_img, n_pix, channels, lo, hi, bgr, d_out);
+    c->n_launches += 1;
+    IA_LAUNCH_CHECK();
+    return IA_OK;
+}

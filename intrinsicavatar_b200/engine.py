@@ -40,6 +40,8 @@ _ARGTYPES = {
     "ia_op_brdf": [_vp] * 7 + [_i64, _vp, _vp, _vp],
     "ia_op_bsdf_sample_pdf": [_vp] * 8 + [_i64, _vp, _vp, _vp],
     "ia_op_env": [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
+    "ia_make_rays": [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32, _vp, _vp],
+    "ia_pack_rgb8": [_vp, _vp, _i64, _i32, _f32, _f32, _i32, _vp, _vp],
 }
 
 OUTPUT_SPECS = [  # name, channels, dtype
@@ -181,6 +183,29 @@ class RenderEngine:
               "ia_set_light_uniform")
         self.spp = spp
         return (d, e) if return_tables else None
+
+    # ------------------------------------------------------- frame producer / consumer ----
+    def make_rays(self, K, H, W, near, far, c2w=None, w2c=None, out=None):
+        """AnimationDataset rays [H*W,8] generated on the device (datasets/animation.py:13-34, 163-189)."""
+        def m34(a):
+            return None if a is None else np.ascontiguousarray(np.asarray(a, np.float64)[:3, :4])
+        Kinv = np.ascontiguousarray(np.linalg.inv(np.asarray(K, np.float64)))
+        c = m34(c2w)
+        e = m34(np.linalg.inv(np.asarray(w2c, np.float32))) if w2c is not None else None   # c2w = inv(w2c), float32
+        rays = out if out is not None else torch.empty(H * W, 8, device=self.dev)
+        vp = lambda a: C.c_void_p(0) if a is None else a.ctypes.data_as(C.c_void_p)
+        check(self.lib.ia_make_rays(self.h, vp(Kinv), vp(c), vp(e), H, W, float(near), float(far), ptr(rays), _stream()),
+              "ia_make_rays")
+        return rays
+
+    def pack_rgb8(self, img, data_range=(0.0, 1.0), bgr=False):
+        """SaverMixin.get_rgb_image_ on the device: float [n, C] (CUDA) -> uint8 [n, C]."""
+        img = img.to(self.dev, torch.float32).contiguous()
+        n, ch = img.reshape(-1, img.shape[-1]).shape
+        out = torch.empty(n, ch, dtype=torch.uint8, device=self.dev)
+        check(self.lib.ia_pack_rgb8(self.h, ptr(img), n, ch, float(data_range[0]), float(data_range[1]), int(bgr), ptr(out),
+                                    _stream()), "ia_pack_rgb8")
+        return out.reshape(img.shape)
 
     # ------------------------------------------------------------------------ render ----
     def alloc_outputs(self, n, device=None, pin_memory=False):

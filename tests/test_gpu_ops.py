@@ -348,3 +348,93 @@ def test_uniform_light_table(scene, posed):
     L = opbr.EnvLight(torch.from_numpy(env))
     oem = L.eval(R.dirs_s2w(g["sphere_dirs"]))
     assert float(((em.cpu() - oem).abs() / (oem.abs() + 1e-2)).max()) < 2e-3
+
+
+# ---------------------------------------------------------------------------------------------------
+# frame producer / consumer
+def _ref_rays(K, H, W, transl, w2c=None):
+    """numpy restatement of datasets/animation.py:13-34 (make_rays), :29-33 (transform_rays), :163-189."""
+    x, y = np.meshgrid(np.arange(W), np.arange(H), indexing="xy")
+    xy = np.stack([x, y, np.ones_like(x)], axis=-1).reshape(-1, 3).astype(np.float32)
+    c2w0 = np.eye(4)
+    d_c = xy @ np.linalg.inv(K).T
+    d_w = d_c @ c2w0[:3, :3].T
+    d_w = d_w / np.linalg.norm(d_w, axis=1, keepdims=True)
+    o_w = np.tile(c2w0[:3, 3], (len(d_w), 1))
+    o, d = o_w.astype(np.float32), d_w.astype(np.float32)
+    if w2c is not None:
+        c2w = np.linalg.inv(w2c.astype(np.float32))
+        o, d = o @ c2w[:3, :3].T + c2w[:3, 3], d @ c2w[:3, :3].T
+    dist = np.sqrt(np.square(transl).sum(-1))
+    near = np.ones_like(d[..., 0]) * (dist - 1)
+    far = np.ones_like(d[..., 0]) * (dist + 1)
+    return np.concatenate([o, d, near[:, None], far[:, None]], 1).astype(np.float32)
+
+
+def test_make_rays_matches_dataset(eng, scene):
+    H, W = 96, 128
+    K = np.array([[250.0, 0, W / 2.0], [0, 250.0, H / 2.0], [0, 0, 1]])
+    transl = np.array([0.1, 0.15, 5.0], np.float32)
+    dist = float(np.sqrt(np.square(transl).sum()))
+    got = eng.make_rays(K, H, W, dist - 1, dist + 1).cpu().numpy()
+    ref = _ref_rays(K, H, W, transl)
+    assert np.abs(got - ref).max() < 2e-7
+    # the bench camera: bit-for-bit what synthetic.make_rays (numpy, float64 -> float32) produces
+    f = 1000.0 * 64 / 512.0
+    Kb = np.array([[f, 0, 32.0], [0, f, 32.0], [0, 0, 1]])
+    gb = eng.make_rays(Kb, 64, 64, dist - 1, dist + 1).cpu().numpy()
+    rb = scene.syn.make_rays(64, 64, transl)
+    assert np.abs(gb - rb).max() < 2e-7 and (gb == rb).mean() > 0.99
+    # a rotated / translated test camera (cameras.npz extrinsic)
+    th = 0.3
+    w2c = np.eye(4, dtype=np.float32)
+    w2c[:3, :3] = np.array([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]], np.float32)
+    w2c[:3, 3] = [0.2, -0.1, 0.4]
+    got = eng.make_rays(K, H, W, dist - 1, dist + 1, w2c=w2c).cpu().numpy()
+    ref = _ref_rays(K, H, W, transl, w2c)
+    assert np.abs(got - ref).max() < 1e-6
+    assert np.abs(np.linalg.norm(got[:, 3:6], axis=1) - 1).max() < 1e-6
+
+
+def test_pack_rgb8_matches_saver(eng):
+    """utils/mixins.py:43-53: clip -> scale -> astype(uint8) -> RGB2BGR."""
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(4097, 3, generator=g) * 1.4 - 0.2
+    img[:8] = torch.tensor([[0.0, 1.0, 0.5], [1.0, 1.0, 1.0], [0.0, 0.0, 0.0], [-1.0, 2.0, 0.999999], [0.25, 0.75, 1e-9],
+                            [0.00392157, 0.5019608, 0.99607843], [1.0000001, -1e-9, 0.49999997], [0.3, 0.6, 0.9]])
+    for lo, hi in ((0.0, 1.0), (-0.1, 0.9)):
+        ref = img.numpy().clip(min=lo, max=hi)
+        ref = ((ref - lo) / (hi - lo) * 255.).astype(np.uint8)
+        got = eng.pack_rgb8(img, (lo, hi)).cpu().numpy()
+        assert (got != ref).mean() < 1e-3 and np.abs(got.astype(int) - ref.astype(int)).max() <= 1   # fp32 rounding at bin edges
+        bgr = eng.pack_rgb8(img, (lo, hi), bgr=True).cpu().numpy()
+        assert np.array_equal(bgr, got[:, ::-1])
+    one = eng.pack_rgb8(torch.rand(50, 1, generator=g)).cpu()
+    assert one.shape == (50, 1)
+
+
+def test_animation_frames_producer(scene):
+    """frames.AnimationFrames feeds IntrinsicAvatarModel like the reference's dataset + preprocess_data."""
+    from intrinsicavatar_b200.frames import AnimationFrames, images_to_uint8
+    from intrinsicavatar_b200.model import IntrinsicAvatarModel
+    z = np.load(scene.syn._DATA + "/aist_poses_0_8.npz")
+    H = W = 48
+    f = 1000.0 * W / 512.0
+    K = np.array([[f, 0, W / 2.0], [0, f, H / 2.0], [0, 0, 1]])
+    m = IntrinsicAvatarModel({"samples_per_pixel": 8}, seed=0)
+    m.train(False)
+    m.update_step(250, 25000)
+    frames = AnimationFrames(m.engine, z["poses"], z["trans"], K, H, W, hdri=scene.syn.load_envmap())
+    assert len(frames) == len(z["poses"])
+    b = frames[2]
+    bp, go, tr = scene.syn.load_pose(2)
+    assert np.allclose(b["transl"].numpy()[0], tr) and np.allclose(b["body_pose"].numpy()[0], bp)
+    assert np.abs(b["rays"].cpu().numpy() - scene.syn.make_rays(H, W, tr)).max() < 2e-7
+    m.prepare(b)
+    out = m.forward(b["rays"])
+    assert out["comp_rgb_phys_full"].shape == (H * W, 3) and not out["comp_rgb_phys_full"].is_cuda
+    imgs = images_to_uint8(m.engine, out, H, W)
+    im = imgs["comp_rgb_phys_full"]
+    assert im.dtype == np.uint8 and im.shape == (H, W, 3)
+    ref = (out["comp_rgb_phys_full"].numpy().clip(0, 1) * 255.).astype(np.uint8).reshape(H, W, 3)[..., ::-1]
+    assert np.abs(im.astype(int) - ref.astype(int)).max() <= 1
