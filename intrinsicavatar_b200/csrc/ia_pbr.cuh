@@ -6,7 +6,6 @@
 //   warp_utils helpers                      lib/torch_pbr/utils/warp_utils.py:62-101, 693-702, 730-747, 782-794
 //   cdf_resampling_merge_kernel             lib/nerfacc/cuda/csrc/cdf.cu:217-334
 //   cdf_resampling_sdf_fine_kernel          lib/nerfacc/cuda/csrc/cdf.cu:536-638
-//   compute_indirect_radiance               models/intrinsic_avatar.py:396-545 (lazy, per ray)
 //   light-index shuffle                     models/intrinsic_avatar.py:1355-1378 (stateless permutation)
 #pragma once
 #include "ia_device.cuh"
@@ -343,111 +342,4 @@ __device__ __forceinline__ int ia_merge_resample(const float* vals, const uint8_
         if ((flags[idx] & 1) && (flags[idx + 1] & 2)) oflags[j + idx] |= 1;
     }
     return j + idx + 1;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Secondary ray: compute_indirect_radiance for ONE ray, lazily (models/intrinsic_avatar.py:396-545):
-// coarse samples are generated and queried in order only until the first +->- SDF crossing is found
-// and the 5 fine points of cdf_resampling_sdf_fine_kernel (cdf.cu:536-638) are placed; the <=4 fine
-// intervals are then rendered.  Results equal the reference's evaluate-everything formulation.
-struct IaTraceCounters {
-    unsigned q, qg, fetch, geo, rad, skin;
-};
-
-template <bool GI>
-__device__ __forceinline__ void ia_team_trace(const Team& team, const IaFrame& p, const float* __restrict__ wgeo,
-                                              const float* __restrict__ wmlp, const uint32_t* __restrict__ occ,
-                                              const float o[3], const float d[3], float& T, float rgb[3],
-                                              IaTraceCounters& cnt) {
-    T = 1.0f;
-    rgb[0] = rgb[1] = rgb[2] = 0.f;
-    IaMarcher m;
-    m.init(p, o, d, p.sec_near, p.sec_far, p.sec_step);
-    float ts, te;
-    bool cont;
-    IaQuery q;
-    auto query_sdf = [&](float t) {
-        float x[3] = {o[0] + d[0] * t, o[1] + d[1] * t, o[2] + d[2] * t};
-        ia_team_query<false>(team, p, wgeo, x, q);
-        cnt.q++; cnt.fetch += q.n_fetch; cnt.geo += q.n_valid;
-        return q.sdf;
-    };
-    if (!m.next(occ, p.occ_res, ts, te, cont)) return;
-    float sdf_prev = query_sdf(ts);
-    float cs = ts, ce = te;  // current interval of the CDF walk (the crossing interval once found)
-    float sdf_cur = 0.f;
-    bool found = false;
-    while (m.next(occ, p.occ_res, ts, te, cont)) {
-        sdf_cur = query_sdf(ts);
-        if (sdf_prev >= 0 && sdf_cur < 0) { found = true; break; }
-        sdf_prev = sdf_cur;
-        cs = ts; ce = te;
-    }
-    if (!found) return;
-    bool pending = true;  // (ts, te, sdf_cur) is the already-queried interval after the crossing one
-    const int num_bins = 5;
-    float cdf_step_size = (1.0f - 1.0 / num_bins) / 4;
-    float tpl[5];
-    int j = 0;
-    float trans = 1.0f;
-    float a = ia_alpha(sdf_prev, ce - cs, p.beta);
-    float weight = a;
-    trans *= (1.0f - a);
-    float cdf_prev = 0.0f, cdf_next = weight;
-    float cdf_u = 1.0 / (2 * num_bins);
-    while (j < num_bins) {
-        if (cdf_u < cdf_next) {
-            float scaling = (ce - cs) / (cdf_next - cdf_prev);
-            float t = (cdf_u - cdf_prev) * scaling + cs;
-            tpl[j] = t;
-            cdf_u += cdf_step_size;
-            j += 1;
-        } else {
-            float s;
-            if (pending) {
-                cs = ts; ce = te; s = sdf_cur;
-                pending = false;
-            } else {
-                if (!m.next(occ, p.occ_res, cs, ce, cont)) break;
-                s = query_sdf(cs);
-            }
-            a = ia_alpha(s, ce - cs, p.beta);
-            weight = trans * a;
-            trans *= (1.0f - a);
-            cdf_prev = cdf_next;
-            cdf_next += weight;
-        }
-    }
-    // rendering() over the fine intervals (models/volrend.py:135-187)
-    float Tacc = 1.0f, acc = 0.f;
-    float view_w[3];
-    if (GI) ia_dir_s2w(p, d, view_w);
-    for (int i = 0; i + 1 < j; i++) {
-        float s0 = tpl[i], e0 = tpl[i + 1];
-        float mid = (s0 + e0) / 2.0f;
-        float x[3] = {o[0] + d[0] * mid, o[1] + d[1] * mid, o[2] + d[2] * mid};
-        float w;
-        if (GI) {
-            ia_team_query<true>(team, p, wgeo, x, q);
-            cnt.qg++; cnt.fetch += q.n_fetch; cnt.geo += q.n_valid + (q.valid ? 1 : 0); cnt.skin += q.valid ? 1 : 0;
-            float al = ia_alpha(q.sdf, e0 - s0, p.beta);
-            w = Tacc * al;
-            Tacc *= (1.0f - al);
-            if (q.valid) {
-                float nw[3], c[3];
-                ia_dir_s2w(p, q.grad, nw);
-                ia_team_radiance<false>(team, p, wmlp, q.xc, q.feat, view_w, nw, c, nullptr);
-                cnt.rad++;
-                rgb[0] += w * c[0]; rgb[1] += w * c[1]; rgb[2] += w * c[2];
-            }
-        } else {
-            float sd = query_sdf(mid);
-            (void)x;
-            float al = ia_alpha(sd, e0 - s0, p.beta);
-            w = Tacc * al;
-            Tacc *= (1.0f - al);
-        }
-        acc += w;
-    }
-    T = 1.0f - acc;
 }

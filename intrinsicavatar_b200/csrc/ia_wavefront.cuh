@@ -16,9 +16,8 @@
 //   filter   : duplicate-root removal per query -> compact list of (query, root) geometry tasks
 //   geometry : 16-lane teams evaluate hash grid + MLP for the listed roots only
 //
-// Same arithmetic, in the same order, as the per-ray formulation in ia_pbr.cuh (ia_team_trace) and so
-// as the reference (models/intrinsic_avatar.py:396-545; cdf.cu:536-638; fuse_cuda_kernel_fast.cu:250-413;
-// filter.cu:10-54); only the accumulation order into a pixel differs.
+// Same arithmetic, in the same order, as the reference (models/intrinsic_avatar.py:396-545; cdf.cu:536-638;
+// fuse_cuda_kernel_fast.cu:250-413; filter.cu:10-54); only the accumulation order into a pixel differs.
 #pragma once
 
 #ifndef WF_THREADS

@@ -384,7 +384,9 @@ def test_make_rays_matches_dataset(eng, scene):
     Kb = np.array([[f, 0, 32.0], [0, f, 32.0], [0, 0, 1]])
     gb = eng.make_rays(Kb, 64, 64, dist - 1, dist + 1).cpu().numpy()
     rb = scene.syn.make_rays(64, 64, transl)
-    assert np.abs(gb - rb).max() < 2e-7 and (gb == rb).mean() > 0.99
+    # (synthetic.make_rays takes |transl| in float64, the dataset in float32: near / far may differ by one ulp)
+    assert np.abs(gb[:, :6] - rb[:, :6]).max() < 2e-7 and (gb[:, :6] == rb[:, :6]).mean() > 0.99
+    assert np.abs(gb[:, 6:] - rb[:, 6:]).max() < 1e-6
     # a rotated / translated test camera (cameras.npz extrinsic)
     th = 0.3
     w2c = np.eye(4, dtype=np.float32)
@@ -429,7 +431,9 @@ def test_animation_frames_producer(scene):
     b = frames[2]
     bp, go, tr = scene.syn.load_pose(2)
     assert np.allclose(b["transl"].numpy()[0], tr) and np.allclose(b["body_pose"].numpy()[0], bp)
-    assert np.abs(b["rays"].cpu().numpy() - scene.syn.make_rays(H, W, tr)).max() < 2e-7
+    rb = scene.syn.make_rays(H, W, tr)
+    assert np.abs(b["rays"].cpu().numpy()[:, :6] - rb[:, :6]).max() < 2e-7
+    assert np.abs(b["rays"].cpu().numpy()[:, 6:] - rb[:, 6:]).max() < 1e-6     # float32 vs float64 |transl|
     m.prepare(b)
     out = m.forward(b["rays"])
     assert out["comp_rgb_phys_full"].shape == (H * W, 3) and not out["comp_rgb_phys_full"].is_cuda
