@@ -48,6 +48,10 @@
 #ifndef WF_STATE_GLOBAL
 #define WF_STATE_GLOBAL 1
 #endif
+#ifndef WF_BTASK_SMEM
+#define WF_BTASK_SMEM 0   // 1: Broyden task list in shared memory, so that a chain start reads its task id with shared-memory
+#endif                    // latency (from the global scratch that read is an exposed L2 round trip: 6 % of the Broyden phase's
+                          // stall samples).  Measured: 731 -> 746 ms -- the 26 KB taken from L1 cost more than the latency saved.
 // per-CTA scratch: roots [R][13][3] f32, their SDFs [R][13] f32, 2 task lists [R*13] u16, GI task list [R] uint2, ray state
 #define WF_OFF_CSDF (WF_R * IA_N_INIT * 3 * 4)
 #define WF_OFF_GTASK (WF_OFF_CSDF + WF_R * IA_N_INIT * 4)
@@ -102,7 +106,11 @@ struct WfShared {
     uint2* gitask;          // [WF_R] GI: (slot | root << 16, weight bits) of the fine samples consumed this round
     int n_gitask;
     unsigned short* gtask;  // [WF_R * 13] geometry task list
+#if WF_BTASK_SMEM
+    unsigned short btask[WF_R * IA_N_INIT];  // Broyden task list (pruned)
+#else
     unsigned short* btask;  // [WF_R * 13] Broyden task list (pruned)
+#endif
     int n_btask;
     int n_q, task_next, n_gtask, ring_head, ring_tail, tile, more_tiles, pad;
     unsigned probe;         // WF_PROBE_SAMECELL builds: Broyden trips that stayed in the voxel cell of the previous trip
@@ -428,13 +436,31 @@ __device__ __forceinline__ void wf_geometry_phase(const IaFrame& p, WfShared& S,
     Team team = cg::tiled_partition<IA_TEAM>(cg::this_thread_block());
     const int n = S.n_gtask;
     const int n_teams = blockDim.x / IA_TEAM;
-    for (int k = threadIdx.x / IA_TEAM; k < n; k += n_teams) {
+    // software pipeline: the task id and root of the NEXT task are fetched (two dependent L2 round trips: the lists
+    // were just written by other warps) while the current one is evaluated
+    int k = threadIdx.x / IA_TEAM;
+    int ci = 0;
+    float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+    if (k < n) {
         const int tk = S.gtask[k];
-        const int ci = (tk >> 4) * IA_N_INIT + (tk & 15);
+        ci = (tk >> 4) * IA_N_INIT + (tk & 15);
         const float* cd = S.cand + ci * 3;
-        const float xc[3] = {cd[0], cd[1], cd[2]};
+        x0 = cd[0]; x1 = cd[1]; x2 = cd[2];
+    }
+    while (k < n) {
+        const int kn = k + n_teams;
+        int ci_n = 0;
+        float y0 = 0.f, y1 = 0.f, y2 = 0.f;
+        if (kn < n) {
+            const int tk = S.gtask[kn];
+            ci_n = (tk >> 4) * IA_N_INIT + (tk & 15);
+            const float* cd = S.cand + ci_n * 3;
+            y0 = cd[0]; y1 = cd[1]; y2 = cd[2];
+        }
+        const float xc[3] = {x0, x1, x2};
         float s = ia_team_geometry<false>(team, p, S.w, xc, nullptr, nullptr, S.lvl);
         if (team.thread_rank() == 0) { S.csdf[ci] = s; c_geo++; }
+        k = kn; ci = ci_n; x0 = y0; x1 = y1; x2 = y2;
     }
 }
 
@@ -687,7 +713,9 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
         S.cand = reinterpret_cast<float*>(mine);
         S.csdf = reinterpret_cast<float*>(mine + WF_OFF_CSDF);
         S.gtask = reinterpret_cast<unsigned short*>(mine + WF_OFF_GTASK);
+#if !WF_BTASK_SMEM
         S.btask = reinterpret_cast<unsigned short*>(mine + WF_OFF_BTASK);
+#endif
         S.gitask = reinterpret_cast<uint2*>(mine + WF_OFF_GITASK);
 #if WF_STATE_GLOBAL
         S.st = reinterpret_cast<float (*)[WF_R]>(mine + WF_OFF_STATE);
