@@ -8,8 +8,9 @@ H*W primary rays at ``spp`` shading samples per pixel, render_mode="light".
   python bench.py [--gpus N] [--steps K] [--warmup W] [--res 512] [--spp 1024] [--gi 0|1]
   python bench.py --impl reference ...     # the CPU restatement (oracle port) on the host cores
 
-Default workload = 512x512 / 1024 spp / global_illumination=false -- the reference README's relight
-command (README.md:84-95) and the setting BASELINE.json's metric is quoted on; ``--gi 1`` is configs[3].
+Default workload = BASELINE.json configs[3], the single-GPU configuration its metric is quoted on: 512x512
+relight, 1024 spp, render_mode=light, global_illumination=true (one indirect bounce).  ``--gi 0`` is the
+reference README's relight command (README.md:84-95: same size, global_illumination=false).
 
 Metric: shaded samples/s = (primary rays x spp) / time, whole job over all ranks ("weak" scaling: one
 frame per rank per step, frame f -> rank f mod N, no data-path collective; the finished frame
@@ -191,7 +192,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--res", type=int, default=512)
     ap.add_argument("--spp", type=int, default=1024)
-    ap.add_argument("--gi", type=int, default=0)
+    ap.add_argument("--gi", type=int, default=1, help="config.model.global_illumination (default 1 = BASELINE configs[3])")
     ap.add_argument("--render-mode", default="light", choices=["light", "uniform_light", "mats", "mis"],
                     help="config.model.render_mode (uniform_light needs --spp 512); the headline workload is light")
     ap.add_argument("--cpu-res", type=int, default=32)
@@ -329,16 +330,20 @@ def main():
         n_samples = c.get("hit_rays", 0) * args.spp
         # + the sample streams the kernel reads (rs_src, rs_w 4 B each per shading sample; rs_t 4 B, the 48-B
         #   IaSample and 6 fp32 accumulations per traced ray)
-        alg = (B_BROYDEN_FETCH * cs["broyden_fetch"] + B_HASH_EVAL * cs["geo_eval"] + 8 * n_samples
-               + (4 + 48 + 24) * cs["secondary_rays"]) if cs else 0
+        #   with global illumination also the radiance hash grid and the 24-channel skinning-weight fetch of every
+        #   fine sample's root (its with-gradient geometry evaluation is counted in geo_eval)
+        alg = (B_BROYDEN_FETCH * cs["broyden_fetch"] + B_HASH_EVAL * (cs["geo_eval"] + cs["rad_eval"])
+               + B_SKIN_FETCH * cs["skin_fetch"] + 8 * n_samples + (4 + 48 + 24) * cs["secondary_rays"]) if cs else 0
         achieved = alg / (shade_ms * 1e-3) / 1e9 if shade_ms > 0 else 0.0
         render_ms = sum(avg(k) for k in ("setup", "primary", "resample", "shade", "composite"))
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "kernel": "k_shade_wf (wavefront secondary-ray integrator)",
+                    "traffic": None, "peak_source": peak_src, "kernel": "k_shade_wf<%d,%s> (wavefront secondary-ray integrator)" % (int(bool(args.gi)), args.render_mode),
                     "algorithmic_bytes_per_launch": alg, "launch_ms": shade_ms, "share_of_step": shade_ms / (ms_total / args.steps),
                     "units_per_launch": {"broyden_voxel_fetches": cs.get("broyden_fetch"), "geometry_evals": cs.get("geo_eval"),
+                                         "radiance_evals": cs.get("rad_eval"), "skinning_fetches": cs.get("skin_fetch"),
                                          "secondary_rays": cs.get("secondary_rays"), "shading_samples": n_samples},
                     "bytes_per_unit": {"broyden_voxel_fetch": B_BROYDEN_FETCH, "geometry_eval": B_HASH_EVAL,
+                                       "radiance_eval": B_HASH_EVAL, "skinning_fetch": B_SKIN_FETCH,
                                        "shading_sample": 8, "secondary_ray": 76},
                     "note": "the gathers' working set (voxel_J 25 MB, geometry hash grid 50 MB) is L2-resident by design, "
                             "so the bytes the kernel requests are served by L2/L1, not HBM: DRAM traffic (`traffic`) is far "
@@ -346,7 +351,7 @@ def main():
         tfile = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tfile):
             with open(tfile) as f:
-                roofline["traffic"] = json.load(f).get("k_shade_wf_dram_bytes_per_launch")
+                roofline["traffic"] = json.load(f).get("k_shade_wf_gi%d_dram_bytes_per_launch" % int(bool(args.gi)))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -48,6 +48,10 @@
 #ifndef WF_STATE_GLOBAL
 #define WF_STATE_GLOBAL 1
 #endif
+#ifndef WF_GI_WEIGHTS_SMEM
+#define WF_GI_WEIGHTS_SMEM 1  // global illumination: 1 = the radiance MLP (47 KB) is staged in shared memory next to the geometry
+#endif                        // MLP; 0 = it is read through L1 while the GI phase runs, leaving that capacity to the Broyden gathers.
+                              // Measured at 512^2 x 1024 spp, GI on: shade 887 ms (1) vs 938 ms (0)
 #ifndef WF_BTASK_SMEM
 #define WF_BTASK_SMEM 0   // 1: Broyden task list in shared memory, so that a chain start reads its task id with shared-memory
 #endif                    // latency (from the global scratch that read is an exposed L2 round trip: 6 % of the Broyden phase's
@@ -485,7 +489,7 @@ __device__ __forceinline__ void wf_gi_phase(const IaFrame& p, WfShared& S, unsig
         float nw[3], view_w[3], rgb[3];
         ia_dir_s2w(p, g, nw);
         ia_dir_s2w(p, d, view_w);
-        ia_team_radiance<false>(team, p, S.w, xc, feat, view_w, nw, rgb, nullptr);
+        ia_team_radiance<false>(team, p, WF_GI_WEIGHTS_SMEM ? S.w : p.mlp, xc, feat, view_w, nw, rgb, nullptr);
         if (team.thread_rank() == 0) {
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) S.st[WS_IND + ch][t] += w * rgb[ch];
@@ -706,7 +710,7 @@ template <bool GI, class P>
 __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, unsigned char* __restrict__ scratch,
                                        unsigned long long* __restrict__ counters) {
     const int tid = threadIdx.x;
-    const int n_w = GI ? IA_RAD_END : IA_GEO_END;
+    const int n_w = (GI && WF_GI_WEIGHTS_SMEM) ? IA_RAD_END : IA_GEO_END;
     if (tid == 0) {
         unsigned char* mine = scratch + (size_t)blockIdx.x * WF_SCRATCH_BYTES;
         S.w = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&S) + ((sizeof(WfShared) + 15) & ~15));
@@ -982,7 +986,7 @@ struct WfShadePolicy {
     }
 };
 
-#define WF_SMEM_BYTES(GI) (((sizeof(WfShared) + 15) & ~(size_t)15) + ((GI) ? IA_RAD_END : IA_GEO_END) * sizeof(float))
+#define WF_SMEM_BYTES(GI) (((sizeof(WfShared) + 15) & ~(size_t)15) + (((GI) && WF_GI_WEIGHTS_SMEM) ? IA_RAD_END : IA_GEO_END) * sizeof(float))
 
 template <bool GI, int MODE>
 __global__ void __launch_bounds__(WF_THREADS, WF_CTAS_PER_SM) k_shade_wf(const __grid_constant__ IaFrame p, WfShadePolicy<MODE> pol,
