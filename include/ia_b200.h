@@ -245,8 +245,8 @@ int ia_op_env(ia_ctx* ctx, const float* d_u, const float* d_dirs_world, int64_t 
 /* AnimationDataset's per-frame ray tensor built on the device (datasets/animation.py:13-34 make_rays,
  * :29-33 transform_rays, :163-189 __getitem__; systems/intrinsic_avatar.py:100-109): d_rays [H*W,8] =
  * o, d, near, far.  h_Kinv9 = inv(K) row-major (float64, as numpy computes it); h_c2w12 = dataset camera
- * 3x4 (NULL = identity); h_ext12 = inv(w2c) of the frame 3x4 (NULL = identity).  Syncs the stream once
- * (36 doubles of camera data).                                                                        */
+ * 3x4 (NULL = identity); h_ext12 = inv(w2c) of the frame 3x4 (NULL = identity).  Does not sync (the
+ * matrices travel as a kernel argument).                                                             */
 int ia_make_rays(ia_ctx* ctx, const double* h_Kinv9, const double* h_c2w12, const double* h_ext12, int H, int W,
                  float near_plane, float far_plane, float* d_rays, void* stream);
 /* SaverMixin.get_rgb_image_ (utils/mixins.py:43-53): clip to [lo,hi] -> 0..255 -> uint8 (truncating),

@@ -70,7 +70,6 @@ struct ia_ctx {
     bool light_uniform = false;  // light tables hold the stratified sphere of render_mode = uniform_light
     float* d_vis = nullptr;      // [n_rays] visibility accumulator (uniform_light)
     float* d_bg = nullptr;       // [n_rays][3] background radiance per ray (background colour / add_emitter)
-    double* d_cam = nullptr;     // [33] camera matrices of ia_make_rays
     // workspace for ia_render
     int64_t ws_rays = 0, ws_samples = 0, ws_resamples = 0;
     int* d_hit_rays = nullptr;       // [n_rays]
@@ -165,7 +164,7 @@ extern "C" int ia_destroy(ia_ctx* c) {
                     c->d_light_em, c->d_light_pdf, c->d_u_table, c->d_env_pdf, c->d_env_cols, c->d_env_rows,
                     c->d_env_rowsum, c->d_env_total, c->d_hit_rays, c->d_hit_od, c->d_hit_info, c->d_samples,
                     c->d_rs_t, c->d_rs_w, c->d_rs_src, c->d_acc, c->d_counters, c->d_work, c->d_occ_a, c->d_occ_b,
-                    c->d_occ_hist, c->d_occ_sum, c->d_wf_scratch, c->d_samples_aux, c->d_vis, c->d_bg, c->d_cam};
+                    c->d_occ_hist, c->d_occ_sum, c->d_wf_scratch, c->d_samples_aux, c->d_vis, c->d_bg};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete c;

@@ -934,12 +934,15 @@ extern "C" int ia_op_env(ia_ctx* c, const float* d_u, const float* d_dirs_world,
 // float64 (K and the extrinsics are float64 arrays) and casts to float32 at the end; so does the kernel.
 //   Kinv  : inv(K), row-major 3x3        c2w : the dataset-level camera (identity for AnimationDataset), 3x4
 //   ext   : inv(w2c) of the frame, 3x4   (test split; identity otherwise)
-__global__ void k_make_rays(const double* __restrict__ m, int H, int W, float near_, float far_, float* __restrict__ rays) {
+struct IaCamera {
+    double Kinv[9], c2w[12], ext[12];
+};
+__global__ void k_make_rays(const __grid_constant__ IaCamera cam, int H, int W, float near_, float far_, float* __restrict__ rays) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)H * W) return;
-    const double* Kinv = m;       // [9]
-    const double* c2w = m + 9;    // [12]
-    const double* ext = m + 21;   // [12]
+    const double* Kinv = cam.Kinv;
+    const double* c2w = cam.c2w;
+    const double* ext = cam.ext;
     const double x = (double)(float)(i % W), y = (double)(float)(i / W);
     // d_c = [x, y, 1] @ inv(K).T ; d_w = d_c @ c2w[:3,:3].T, normalised
     double dc[3], dw[3];
@@ -970,15 +973,12 @@ extern "C" int ia_make_rays(ia_ctx* c, const double* h_Kinv9, const double* h_c2
     IA_CHECK_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     static const double ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
-    double h[33];
-    memcpy(h, h_Kinv9, 9 * sizeof(double));
-    memcpy(h + 9, h_c2w12 ? h_c2w12 : ident, 12 * sizeof(double));
-    memcpy(h + 21, h_ext12 ? h_ext12 : ident, 12 * sizeof(double));
-    if (!c->d_cam) IA_CHECK_CUDA(cudaMalloc((void**)&c->d_cam, sizeof(h)));
-    IA_CHECK_CUDA(cudaMemcpyAsync(c->d_cam, h, sizeof(h), cudaMemcpyHostToDevice, st));
-    IA_CHECK_CUDA(cudaStreamSynchronize(st));  // h is a stack buffer
+    IaCamera cam;  // passed by value: no copy, no sync
+    memcpy(cam.Kinv, h_Kinv9, 9 * sizeof(double));
+    memcpy(cam.c2w, h_c2w12 ? h_c2w12 : ident, 12 * sizeof(double));
+    memcpy(cam.ext, h_ext12 ? h_ext12 : ident, 12 * sizeof(double));
     const long long n = (long long)H * W;
-    k_make_rays<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->d_cam, H, W, near_plane, far_plane, d_rays);
+    k_make_rays<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cam, H, W, near_plane, far_plane, d_rays);
     c->n_launches += 1;
     IA_LAUNCH_CHECK();
     return IA_OK;
