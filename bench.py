@@ -14,7 +14,8 @@ reference README's relight command (README.md:84-95: same size, global_illuminat
 
 Metric: shaded samples/s = (primary rays x spp) / time, whole job over all ranks ("weak" scaling: one
 frame per rank per step, frame f -> rank f mod N, no data-path collective; the finished frame
-buffers are gathered to rank 0 with one NCCL gather inside the timed region).
+buffers are gathered to rank 0 with one asynchronous NCCL gather per step, all of them completed
+inside the timed region).
   value : inputs resident in HBM when the timed region starts (rays, envmap on device)
   e2e   : through IntrinsicAvatarModel.prepare/forward with HOST rays + HOST hdri, H2D and the D2H of
           every output buffer inside the timed region
@@ -251,12 +252,26 @@ def main():
     def frame_of(step):
         return frames[(step + rank) % 8]
 
+    pending = []   # (send block, receive blocks, work) of the frame gathers posted and not yet waited for
+
+    def post_gather(block):
+        # the gather is posted asynchronously: frames take different times, and rank 0 renders its next frame instead
+        # of waiting for the slowest rank of this step; all gathers are waited for inside the timed region (drain)
+        bufs, work = parallel.gather_frames_async(block, dst=0)
+        pending.append((block, bufs, work))
+
+    def drain():
+        for _, _, work in pending:
+            if work is not None:
+                work.wait()
+        pending.clear()
+
     def step_device(step):
         fr = frame_of(step)
         model.prepare({**fr["batch"], "hdri": env_d}, jitter=jitter, light_uniforms=lu)
         out = model.forward(fr["rays_d"], move_to_cpu=False)
         if world > 1:
-            parallel.gather_frames(parallel.pack_frame(out), dst=0)
+            post_gather(parallel.pack_frame(out))
         return out
 
     def step_e2e(step):
@@ -264,7 +279,7 @@ def main():
         model.prepare({**fr["batch"], "hdri": env_h.to(dev, non_blocking=True)}, jitter=jitter, light_uniforms=lu)
         out = model.forward(fr["rays_h"], move_to_cpu=True)
         if world > 1:
-            parallel.gather_frames(parallel.pack_frame({k: out[k].to(dev) for k in parallel.FRAME_KEYS}), dst=0)
+            post_gather(parallel.pack_frame({k: out[k].to(dev) for k in parallel.FRAME_KEYS}))
         return out
 
     def barrier():
@@ -276,6 +291,7 @@ def main():
         for s in range(warmup):
             fn(s)
             flush.fill_(s & 0xFF)
+        drain()
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         stage_ms, cnts = [], []
@@ -288,6 +304,7 @@ def main():
             if fn is step_device:
                 stage_ms.append(eng.timings()[0])  # syncs the stream: the stages of this step
                 cnts.append(eng.counters())
+        drain()                                # every frame of the timed steps has arrived on rank 0
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1)

@@ -34,12 +34,20 @@ def unpack_frame(block: torch.Tensor) -> dict:
 def gather_frames(block: torch.Tensor, dst: int = 0):
     """Gather one packed frame per rank to ``dst``.  Returns the list of blocks on dst, None elsewhere.
     Works with NCCL (CUDA tensors) and gloo (CPU tensors)."""
+    bufs, work = gather_frames_async(block, dst)
+    if work is not None:
+        work.wait()
+    return bufs
+
+
+def gather_frames_async(block: torch.Tensor, dst: int = 0):
+    """Post the gather without waiting for it: returns (list of receive blocks on dst / None elsewhere, work handle or
+    None).  Frames take different times (0.8-1.1 s here), so a rank -- rank ``dst`` above all -- should go on rendering
+    its next frame instead of waiting for the slowest rank of this step; call ``work.wait()`` when the blocks are
+    needed.  ``block`` (and the returned list) must stay alive until then."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
-        return [block]
+        return [block], None
     ws, rank = dist.get_world_size(), dist.get_rank()
-    if rank == dst:
-        bufs = [torch.empty_like(block) for _ in range(ws)]
-        dist.gather(block, gather_list=bufs, dst=dst)
-        return bufs
-    dist.gather(block, gather_list=None, dst=dst)
-    return None
+    bufs = [torch.empty_like(block) for _ in range(ws)] if rank == dst else None
+    work = dist.gather(block, gather_list=bufs, dst=dst, async_op=True)
+    return bufs, work

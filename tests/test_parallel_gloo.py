@@ -37,6 +37,18 @@ def _worker(rank, world, port, q):
                     ok = ok and un[k].shape == (n_pix, c) and float(un[k][0, 0]) == r * 100 + c
         else:
             ok = got is None
+        # asynchronous form (bench.py): two steps posted back to back, waited for afterwards, order preserved
+        posted = []
+        for step in range(2):
+            blk = block + 1000.0 * (step + 1)
+            posted.append((blk,) + parallel.gather_frames_async(blk, dst=0))
+        for step, (blk, bufs, work) in enumerate(posted):
+            ok = ok and work is not None
+            work.wait()
+            if rank == 0:
+                ok = ok and all(float(bufs[r][0, 0]) == r * 100 + 3 + 1000.0 * (step + 1) for r in range(world))
+            else:
+                ok = ok and bufs is None
         t = torch.tensor([float(len(mine))])
         dist.all_reduce(t)
         q.put((rank, mine, bool(ok), float(t)))
@@ -62,5 +74,7 @@ def test_frames_shard_and_gather_world2():
 def test_single_process_gather_is_identity():
     b = torch.arange(32, dtype=torch.float32).reshape(2, 16)
     assert parallel.gather_frames(b)[0] is b
+    bufs, work = parallel.gather_frames_async(b)
+    assert bufs[0] is b and work is None
     un = parallel.unpack_frame(b)
     assert torch.equal(parallel.pack_frame(un), b)
