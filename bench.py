@@ -13,7 +13,8 @@ relight, 1024 spp, render_mode=light, global_illumination=true (one indirect bou
 reference README's relight command (README.md:84-95: same size, global_illumination=false).
 
 Metric: shaded samples/s = (primary rays x spp) / time, whole job over all ranks ("weak" scaling: one
-frame per rank per step, frame f -> rank f mod N, no data-path collective; the finished frame
+frame per rank per step -- every rank renders frame (step mod 8) of the sequence so that the per-GPU work is the
+same for every N; --distinct-frames shards the sequence frame f -> rank f mod N instead --, no data-path collective; the finished frame
 buffers are gathered to rank 0 with one asynchronous NCCL gather per step, all of them completed
 inside the timed region).
   value : inputs resident in HBM when the timed region starts (rays, envmap on device)
@@ -177,7 +178,7 @@ def workload_config(args):
     return {
         "workload": f"{args.res}x{args.res} relight frame, {args.spp} spp, render_mode={args.render_mode}, "
                     f"global_illumination={'true' if args.gi else 'false'}, prepare+forward per step",
-        "frame_source": "AIST pose frames 0..7 (frame = (step + rank) mod 8), synthetic 24-joint body, random-init "
+        "frame_source": "AIST pose frames 0..7 (frame = " + ("(step + rank)" if args.distinct_frames else "step") + " mod 8 on every rank), synthetic 24-joint body, random-init "
                         "hash grids + MLPs (seed 0), city.hdr envmap (8x area-downsampled copy, re-expanded to 1024x2048)",
         "rays_per_frame": args.res * args.res, "spp": args.spp, "gi": bool(args.gi),
         "parallelism": f"frame-per-gpu x{args.gpus}",
@@ -199,6 +200,8 @@ def main():
     ap.add_argument("--cpu-res", type=int, default=32)
     ap.add_argument("--cpu-spp", type=int, default=8)
     ap.add_argument("--cpu-grid", type=int, default=32)
+    ap.add_argument("--distinct-frames", action="store_true",
+                    help="N>1: rank r renders frame (step + r) mod 8 instead of every rank rendering frame step mod 8")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -250,7 +253,10 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def frame_of(step):
-        return frames[(step + rank) % 8]
+        # Weak scaling = the same work on every GPU for every N: each rank renders its own copy of the same
+        # animation sequence.  (--distinct-frames: frame = (step + rank) mod 8, the deployment sharding of BASELINE
+        # configs[4]; the frames of this sequence cost 0.85-1.2 s each, so that variant also measures their spread.)
+        return frames[(step + (rank if args.distinct_frames else 0)) % 8]
 
     pending = []   # (send block, receive blocks, work) of the frame gathers posted and not yet waited for
 
@@ -323,7 +329,7 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        # same warm-up count as the device arm, so that both arms time the same frames ((step + rank) mod 8)
+        # same warm-up count as the device arm, so that both arms time the same frames (step mod 8)
         ms_e2e, _, _, _, _ = timed(step_e2e, args.steps, args.warmup)
         # forward() brings every output buffer of the frame to the host in one packed copy (engine.outputs_to_host)
         d2h = eng.alloc_outputs(1)["_block"].numel() * 4 * n_rays
