@@ -191,3 +191,70 @@ def a_pose() -> np.ndarray:
     p[47] = -0.8
     p[50] = 0.8
     return p
+
+
+class SMPLBody:
+    """The real thing: SMPL linear blend skinning from a model file, same call contract as ``SyntheticBody``
+    (SURVEY.md 8f.3).  Restates ``lbs`` (reference models/deformers/smplx/lbs.py:152-248: shape blend shapes ->
+    joint regression -> pose-corrective blend shapes -> ``batch_rigid_transform`` -> skinning) and the translation
+    handling of ``SMPL.forward`` (body_models.py:342-358: ``transl`` is added to vertices, joints and the last column
+    of ``A``).  The licensed SMPL data is not shipped: ``from_file`` reads the official ``SMPL_*.pkl`` (or an ``.npz``
+    with the same arrays); the constructor takes the arrays directly, which is what the parity test does with a
+    random model of SMPL's shapes pushed through the reference's own ``lbs``.
+
+      v_template [V,3], shapedirs [V,3,NB], posedirs [V,3,207] (or the reference's [207, V*3]), J_regressor [24,V],
+      lbs_weights [V,24], parents [24]
+    """
+
+    def __init__(self, v_template, shapedirs, posedirs, J_regressor, lbs_weights, parents=PARENTS, betas=None):
+        self.v_template = np.asarray(v_template, np.float64)
+        V = self.v_template.shape[0]
+        self.shapedirs = np.asarray(shapedirs, np.float64).reshape(V, 3, -1)
+        pd = np.asarray(posedirs, np.float64)
+        # body_models.py:156-159 stores posedirs as [P, V*3]; the .pkl holds [V,3,P]
+        self.posedirs = pd if pd.ndim == 2 else pd.reshape(V * 3, -1).T
+        self.J_regressor = np.asarray(J_regressor, np.float64)
+        self.lbs_weights = np.asarray(lbs_weights, np.float32)
+        self.parents = np.asarray(parents, np.int64)
+        assert self.J_regressor.shape == (24, V) and self.lbs_weights.shape == (V, 24)
+        assert self.posedirs.shape == (23 * 9, V * 3) and np.array_equal(self.parents[1:], PARENTS[1:])
+        self.betas = np.zeros(self.shapedirs.shape[-1]) if betas is None else np.asarray(betas, np.float64).reshape(-1)
+
+    @classmethod
+    def from_file(cls, path: str, betas=None):
+        """``SMPL_NEUTRAL.pkl`` (chumpy-free pickles or the official ones read with ``encoding='latin1'``) or ``.npz``."""
+        if path.endswith(".npz"):
+            d = dict(np.load(path, allow_pickle=True))
+        else:
+            import pickle
+            with open(path, "rb") as f:
+                d = pickle.load(f, encoding="latin1")
+        def arr(x):
+            x = getattr(x, "r", x)                       # chumpy arrays expose their value as .r
+            return np.asarray(x.todense() if hasattr(x, "todense") else x)
+        parents = arr(d["kintree_table"])[0].astype(np.int64) if "kintree_table" in d else PARENTS
+        parents = parents.copy()
+        parents[0] = -1
+        return cls(arr(d["v_template"]), arr(d["shapedirs"])[..., :10], arr(d["posedirs"]), arr(d["J_regressor"]),
+                   arr(d["weights"] if "weights" in d else d["lbs_weights"]), parents, betas)
+
+    def __call__(self, body_pose=None, global_orient=None, transl=None, betas=None):
+        body_pose = np.zeros(69) if body_pose is None else np.asarray(body_pose, np.float64).reshape(69)
+        global_orient = np.zeros(3) if global_orient is None else np.asarray(global_orient, np.float64).reshape(3)
+        transl = np.zeros(3) if transl is None else np.asarray(transl, np.float64).reshape(3)
+        betas = self.betas if betas is None else np.asarray(betas, np.float64).reshape(-1)
+        v_shaped = self.v_template + self.shapedirs[..., :len(betas)] @ betas          # blend_shapes
+        J = self.J_regressor @ v_shaped                                                 # vertices2joints
+        R = rodrigues(np.concatenate([global_orient, body_pose]).reshape(24, 3))
+        pose_feature = (R[1:] - np.eye(3)).reshape(-1)
+        v_posed = v_shaped + (pose_feature @ self.posedirs).reshape(-1, 3)
+        posed_joints, A = rigid_chain(R, J)
+        T = np.einsum("vj,jab->vab", self.lbs_weights.astype(np.float64), A)
+        verts = np.einsum("vab,vb->va", T, np.concatenate([v_posed, np.ones((len(v_posed), 1))], 1))[:, :3]
+        A = A.copy()
+        A[:, :3, 3] += transl
+        return {
+            "vertices": (verts + transl)[None].astype(np.float32),
+            "joints": (posed_joints + transl)[None].astype(np.float32),
+            "A": A[None].astype(np.float32),
+        }

@@ -22,6 +22,9 @@ and, in tests/golden/reference_vectors_bsdf.npz (`make_golden.py bsdf`; the inte
                                                                   lib/torch_pbr/bxdf.py:290-388
   sphere     EnvironmentLightBase.sample_uniform_sphere_stratified(1, 16, 32), eval mode
                                                                   lib/torch_pbr/light.py:161-217
+and, in tests/golden/reference_vectors_smpl.npz (`make_golden.py smpl`):
+  smpl       lbs() + SMPL.forward translation on a random model of SMPL's shapes
+                                                                  models/deformers/smplx/lbs.py:152-248, body_models.py:342-358
 """
 from __future__ import annotations
 
@@ -246,8 +249,44 @@ def main_bsdf():
     print("wrote", OUT_BSDF, {k: tuple(v.shape) for k, v in g.items()})
 
 
+def main_smpl():
+    """The reference's own lbs() (models/deformers/smplx/lbs.py:152-248) + SMPL.forward's translation handling
+    (body_models.py:342-358) on a RANDOM model with SMPL's array shapes (the licensed .pkl is absent): pins
+    intrinsicavatar_b200.body.SMPLBody."""
+    install_stubs()
+    sys.path.insert(0, ROOT)
+    torch.manual_seed(99)
+    from models.deformers.smplx import lbs as ref_lbs
+    from intrinsicavatar_b200.body import PARENTS, SyntheticBody
+    V = 240
+    body = SyntheticBody(n_verts=V)
+    v_template = torch.from_numpy(body.v_template).double()
+    shapedirs = (torch.randn(V, 3, 10) * 0.01).double()              # float32-representable: stored as float32
+    posedirs = (torch.randn(207, V * 3) * 0.002).double()              # stored [P, V*3] as body_models.py:156-159 does
+    # a joint regressor with the right flavour: convex weights over the vertices nearest to each rest joint
+    d = torch.cdist(torch.from_numpy(body.joints_rest).double(), v_template)
+    Jr = torch.softmax(-d / 0.03, dim=1).float().double()
+    w = torch.from_numpy(body.lbs_weights).double()
+    parents = torch.from_numpy(np.asarray(PARENTS, np.int64))
+    betas = torch.randn(1, 10).double()
+    pose = (torch.randn(1, 72) * 0.4).double()
+    transl = torch.tensor([[0.1, -0.2, 3.0]]).double()
+    verts, joints, A, T, so, po = ref_lbs.lbs(betas, pose, v_template[None], shapedirs, posedirs, Jr, parents, w, pose2rot=True)
+    A = A.clone()
+    A[..., :3, 3] += transl.unsqueeze(1)
+    g = dict(smpl_v_template=v_template, smpl_shapedirs=shapedirs, smpl_posedirs=posedirs, smpl_J_regressor=Jr,
+             smpl_weights=w, smpl_betas=betas, smpl_pose=pose, smpl_transl=transl,
+             smpl_vertices=verts + transl.unsqueeze(1), smpl_joints=joints + transl.unsqueeze(1), smpl_A=A)
+    out = os.path.join(ROOT, "tests", "golden", "reference_vectors_smpl.npz")
+    big = ("smpl_shapedirs", "smpl_posedirs", "smpl_J_regressor", "smpl_weights", "smpl_v_template")
+    np.savez_compressed(out, **{k: v.detach().cpu().numpy().astype(np.float32 if k in big else np.float64) for k, v in g.items()})
+    print("wrote", out, {k: tuple(v.shape) for k, v in g.items()})
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "bsdf":
+    if len(sys.argv) > 1 and sys.argv[1] == "smpl":
+        main_smpl()
+    elif len(sys.argv) > 1 and sys.argv[1] == "bsdf":
         main_bsdf()
     else:
         main()

@@ -156,3 +156,39 @@ def test_uniform_sphere_stratified_matches_reference(gb):
     d = uniform_sphere_stratified(16, 32)
     assert torch.allclose(d, gb["sphere_dirs"], atol=1e-6)
     assert torch.allclose(gb["sphere_inv_pdf"], torch.full((512, 1), 4 * np.pi))
+
+
+def test_smpl_body_matches_reference_lbs():
+    """intrinsicavatar_b200.body.SMPLBody (shape + pose blend shapes, joint regression, kinematic chain, skinning,
+    translation) against the reference's own lbs() / SMPL.forward on a random model with SMPL's array shapes
+    (tests/golden/reference_vectors_smpl.npz, scripts/make_golden.py smpl)."""
+    from intrinsicavatar_b200.body import SMPLBody
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors_smpl.npz"))
+    body = SMPLBody(z["smpl_v_template"], z["smpl_shapedirs"], z["smpl_posedirs"], z["smpl_J_regressor"], z["smpl_weights"],
+                    betas=z["smpl_betas"][0])
+    pose = z["smpl_pose"][0]
+    out = body(body_pose=pose[3:], global_orient=pose[:3], transl=z["smpl_transl"][0])
+    assert np.abs(out["vertices"] - z["smpl_vertices"]).max() < 2e-6
+    assert np.abs(out["joints"] - z["smpl_joints"]).max() < 2e-6
+    assert np.abs(out["A"] - z["smpl_A"]).max() < 2e-6
+    # the [V,3,P] layout of the official .pkl is accepted as well
+    pd = z["smpl_posedirs"].T.reshape(-1, 3, 207)
+    body2 = SMPLBody(z["smpl_v_template"], z["smpl_shapedirs"], pd, z["smpl_J_regressor"], z["smpl_weights"], betas=z["smpl_betas"][0])
+    assert np.array_equal(body2(body_pose=pose[3:], global_orient=pose[:3])["vertices"],
+                          body(body_pose=pose[3:], global_orient=pose[:3])["vertices"])
+
+
+def test_smpl_body_drives_snarf_setup():
+    """SnarfSetup takes an SMPLBody like the synthetic one: canonical voxel grid + per-frame bone transforms."""
+    from intrinsicavatar_b200.body import SMPLBody
+    from intrinsicavatar_b200.snarf import SnarfSetup
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors_smpl.npz"))
+    body = SMPLBody(z["smpl_v_template"], z["smpl_shapedirs"], z["smpl_posedirs"], z["smpl_J_regressor"], z["smpl_weights"])
+    s = SnarfSetup(body, resolution=32)
+    assert s.lbs_voxel.shape == (24, 8, 32, 32) and np.allclose(s.lbs_voxel.sum(0), 1.0, atol=1e-4)
+    fr = s.frame(z["smpl_pose"][0][3:], z["smpl_pose"][0][:3], z["smpl_transl"][0])
+    assert fr["tfs"].shape == (24, 4, 4) and np.isfinite(fr["tfs"]).all() and fr["deformed_bbox"].shape == (6,)
+    # bone transforms are rigid: tfs = w2s . A . A_cano^-1
+    for b in range(24):
+        R = fr["tfs"][b, :3, :3].astype(np.float64)
+        assert np.allclose(R @ R.T, np.eye(3), atol=1e-5)
