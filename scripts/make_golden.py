@@ -258,7 +258,7 @@ def main_smpl():
     torch.manual_seed(99)
     from models.deformers.smplx import lbs as ref_lbs
     from intrinsicavatar_b200.body import PARENTS, SyntheticBody
-    V = 240
+    V = 400
     body = SyntheticBody(n_verts=V)
     v_template = torch.from_numpy(body.v_template).double()
     shapedirs = (torch.randn(V, 3, 10) * 0.01).double()              # float32-representable: stored as float32
