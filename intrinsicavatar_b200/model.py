@@ -88,6 +88,11 @@ class IntrinsicAvatarModel(torch.nn.Module):
                                                                       requires_grad=False)
         self._upload_fields()
 
+    def load_checkpoint(self, path: str):
+        """Ingest a Lightning checkpoint of the reference (launch.py:110-124): the render-path parameters under
+        ``model.`` are taken, everything else is ignored (strict=False semantics)."""
+        self.load_state_dict(W.load_lightning_checkpoint(path))
+
     def _upload_fields(self):
         folded = W.fold(self.state_dict())
         self._beta = folded["beta"]

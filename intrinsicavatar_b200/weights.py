@@ -137,3 +137,48 @@ def fold(sd: dict) -> dict:
         out[f"mat_b{li + 1}"] = sd[f"material.network.layers.{li}.bias"].float().contiguous()
     out["beta"] = float(sd["density.beta"].abs() + 1e-4)  # LearnedLaplaceDensity.get_beta, density.py:32-34
     return out
+
+
+RENDER_PATH_PREFIXES = ("geometry.", "radiance.", "material.", "density.")
+
+
+def load_lightning_checkpoint(path: str, map_location="cpu") -> dict:
+    """Reference-keyed state dict of the render path out of a Lightning checkpoint (launch.py:110-124 loads
+    ``ckpt['state_dict']`` into the system with ``strict=False``; the model's parameters live under ``model.``).
+    Keys outside the render path (pose correction, non-rigid, occupancy grids, emitter, loss state) are dropped;
+    the shapes of what remains are checked against the network layout the kernels are built for."""
+    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    sd = ckpt.get("state_dict", ckpt)
+    out = {}
+    for k, v in sd.items():
+        if k.startswith("model."):
+            k = k[len("model."):]
+        if k.startswith(RENDER_PATH_PREFIXES) and torch.is_tensor(v):
+            out[k] = v.detach().float()
+    expect = {k: tuple(v.shape) for k, v in random_state_dict_shapes().items()}
+    missing = sorted(set(expect) - set(out))
+    if missing:
+        raise KeyError(f"checkpoint {path} lacks render-path parameters: {missing[:4]}{'...' if len(missing) > 4 else ''}")
+    for k, shp in expect.items():
+        if tuple(out[k].shape) != shp and out[k].numel() != int(np.prod(shp)):
+            raise ValueError(f"{k}: checkpoint shape {tuple(out[k].shape)} does not match the built network {shp}")
+        out[k] = out[k].reshape(shp)
+    return out
+
+
+def random_state_dict_shapes() -> dict:
+    """Shapes of every render-path parameter (meta tensors, no allocation)."""
+    lay = hashgrid_layout()
+    n = lay["total"] * N_FEAT
+    m = lambda *s: torch.empty(*s, device="meta")
+    sd = {"geometry.encoding.encoding.encoding.params": m(n), "radiance.xyz_encoding.encoding.encoding.params": m(n),
+          "density.beta": m(())}
+    for i, (o, i_) in enumerate([(64, 35), (13, 64)]):
+        k = f"geometry.network.layers.{2 * i}"
+        sd[k + ".weight_v"], sd[k + ".weight_g"], sd[k + ".bias"] = m(o, i_), m(o, 1), m(o)
+    for li, (o, i_) in enumerate([(64, 67), (64, 64), (3, 64)]):
+        sd[f"radiance.network.layers.{2 * li}.weight"], sd[f"radiance.network.layers.{2 * li}.bias"] = m(o, i_), m(o)
+    for li, (o, i_) in enumerate([(64, 48), (64, 64), (5, 64)]):
+        sd[f"material.network.layers.{li}.weight"], sd[f"material.network.layers.{li}.bias"] = m(o, i_), m(o)
+        sd[f"material.network.lipshitz_bound_per_layer.{li}"] = m(1)
+    return sd

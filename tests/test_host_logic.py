@@ -255,3 +255,36 @@ def test_render_flag_constants_match_header():
         assert capi.RENDER_MODES[name] == v << shift
     assert capi.RENDER_ADD_EMITTER == int(re.search(r"#define IA_RENDER_ADD_EMITTER (\d+)", src).group(1))
     assert capi.RENDER_GI == 2 and capi.RENDER_PRIMARY_ONLY == 1
+
+
+def test_lightning_checkpoint_ingestion(tmp_path):
+    """weights.load_lightning_checkpoint: ``model.``-prefixed reference keys in, unrelated keys dropped, shapes checked
+    (launch.py:110-124 strict=False semantics)."""
+    from intrinsicavatar_b200 import weights as W
+    sd = W.random_state_dict(3)
+    shapes = W.random_state_dict_shapes()
+    assert set(shapes) == set(sd) and all(tuple(shapes[k].shape) == tuple(sd[k].shape) for k in sd)
+    ck = {"state_dict": {**{"model." + k: v for k, v in sd.items()},
+                         "model.pose_correction.delta": torch.zeros(3), "model.occupancy_grid.occs": torch.zeros(8),
+                         "model.emitter.base": torch.zeros(4, 8, 3)},
+          "epoch": 249, "global_step": 25000}
+    # tcnn checkpoints hold the hash grid as fp16-sized flat params of the same element count: accept a reshape
+    ck["state_dict"]["model.density.beta"] = sd["density.beta"].reshape(1)
+    p = tmp_path / "last.ckpt"
+    torch.save(ck, p)
+    got = W.load_lightning_checkpoint(str(p))
+    assert set(got) == set(sd)
+    for k in sd:
+        assert torch.equal(got[k], sd[k].float().reshape(got[k].shape)), k
+    a, b = W.fold(got), W.fold(sd)
+    assert all(torch.equal(a[k], b[k]) if torch.is_tensor(a[k]) else a[k] == b[k] for k in b)
+    bad = dict(ck["state_dict"])
+    del bad["model.radiance.network.layers.2.weight"]
+    torch.save({"state_dict": bad}, p)
+    with pytest.raises(KeyError, match="radiance.network.layers.2.weight"):
+        W.load_lightning_checkpoint(str(p))
+    bad = dict(ck["state_dict"])
+    bad["model.geometry.network.layers.0.weight_v"] = torch.zeros(64, 27)
+    torch.save({"state_dict": bad}, p)
+    with pytest.raises(ValueError, match="geometry.network.layers.0.weight_v"):
+        W.load_lightning_checkpoint(str(p))
