@@ -560,6 +560,7 @@ static int ia_launch_shade(ia_ctx* c, bool gi, int64_t ray_index_base, uint32_t 
     pol.rs_t = c->d_rs_t; pol.rs_src = c->d_rs_src; pol.rs_w = c->d_rs_w; pol.work = c->d_work; pol.spp = c->spp;
     pol.ray_index_base = ray_index_base; pol.seed = seed; pol.light_dir_s = c->d_light_dir_s;
     pol.light_em = c->d_light_em; pol.light_pdf = c->d_light_pdf; pol.acc6 = c->d_acc; pol.n_total = 0; pol.gi = gi;
+    pol.light_rank = c->d_light_rank;
     pol.env = c->env; pol.vis = MODE == IA_MODE_UNIFORM_LIGHT ? c->d_vis : nullptr; pol.bg_rgb = c->d_bg;
     if (gi) {
         IA_CHECK_CUDA(cudaFuncSetAttribute(k_shade_wf<true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_BYTES(true)));

@@ -103,6 +103,10 @@ struct WfShared {
     unsigned int qmask[WF_R];
     unsigned short qlist[WF_R];
     uint2 ring[WF_QCAP];
+    // feed: direction-coherent ordering of a tile's live rays (WfShadePolicy, light-table modes)
+    unsigned int sortk[WF_FEED];     // (pixel in tile << 26) | (direction rank of the light << 10) | item in tile; ~0u = no ray
+    unsigned short sortkk[WF_FEED];  // light index of the item
+    int n_live_tile;
     // CTA-private scratch in GLOBAL memory (low traffic; keeping it out of shared memory leaves the
     // L1 carve-out to the voxel_J gathers, which is what the kernel is bound by -- DESIGN.md):
     float* cand;            // [WF_R][13][3] Broyden roots
@@ -840,6 +844,7 @@ struct WfShadePolicy {
     const float* rs_t; const int* rs_src; const float* rs_w;
     int* work; int spp; long long ray_index_base; uint32_t seed;
     const float* light_dir_s; const float* light_em; const float* light_pdf;
+    const unsigned short* light_rank;  // [spp] position of each light direction along a Morton curve over (lon, lat)
     float* acc6;
     long long n_total;
     int gi;
@@ -851,39 +856,89 @@ struct WfShadePolicy {
     __device__ __forceinline__ int* tile_counter() const { return &work[IA_W_TILE_NEXT]; }
     __device__ __forceinline__ int tile_items() const { return mode == IA_MODE_MIS ? WF_FEED / 2 : WF_FEED; }
 
+    // One shading sample of the tile: background-assigned samples are accumulated on the spot; returns whether the
+    // sample traces a ray, and its ring entry.
+    __device__ __forceinline__ bool classify(long long s, uint2& e) const {
+        e = make_uint2(0, 0);
+        if (s >= n_total) return false;
+        const unsigned su = (unsigned)s;
+        const int slot = (int)(su / (unsigned)spp), j = (int)(su % (unsigned)spp);
+        const int src = rs_src[s];
+        if (src < 0) {
+            // background-assigned shading sample (models/intrinsic_avatar.py:1319-1341)
+            const float w = rs_w[s];
+            float* pa = acc6 + (size_t)hit_rays[slot] * 6;
+            const float* bg = bg_rgb + (size_t)hit_rays[slot] * 3;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                atomicAdd(&pa[k], w * bg[k]);
+                atomicAdd(&pa[3 + k], w * bg[k]);
+            }
+            return false;
+        }
+        if (mode >= IA_MODE_MATS) {
+            e = make_uint2(su, 0);
+            return true;  // no cosine mask: every foreground sample traces its sampled direction(s)
+        }
+        const float* n = samples[src].n;
+        uint32_t key = ia_pixel_key(seed, (uint64_t)(ray_index_base + hit_rays[slot]));
+        uint32_t kk = ia_permute((uint32_t)j, (uint32_t)spp, key);
+        const float* wo = light_dir_s + kk * 3;
+        float cosv = n[0] * wo[0] + n[1] * wo[1] + n[2] * wo[2];
+        e = make_uint2(su, kk);
+        return cosv > 1e-6f;
+    }
+
     __device__ __forceinline__ void feed(long long s0, WfShared& S) {
         const int n_it = tile_items();
-        for (int i = threadIdx.x; i < n_it; i += blockDim.x) {
-            const long long s = s0 + i;
-            bool live = false;
-            uint2 e = make_uint2(0, 0);
-            if (s < n_total) {
-                const unsigned su = (unsigned)s;
-                const int slot = (int)(su / (unsigned)spp), j = (int)(su % (unsigned)spp);
-                const int src = rs_src[s];
-                if (src < 0) {
-                    // background-assigned shading sample (models/intrinsic_avatar.py:1319-1341)
-                    const float w = rs_w[s];
-                    float* pa = acc6 + (size_t)hit_rays[slot] * 6;
-                    const float* bg = bg_rgb + (size_t)hit_rays[slot] * 3;
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        atomicAdd(&pa[k], w * bg[k]);
-                        atomicAdd(&pa[3 + k], w * bg[k]);
+        if (WF_FEED == 1024 && mode <= IA_MODE_UNIFORM_LIGHT && spp >= 64 && light_rank) {  // (key layout: 5 + 16 + 10 bits)
+            // Light-table modes: the rays of a pixel enter the ring ordered by the DIRECTION of their light (Morton rank
+            // over lon/lat) instead of by sample index, whose light is a random pick: neighbouring ray slots then walk
+            // through the same voxels and hash cells (secondary stage 7 % faster on the same rays, scripts/coherence_test.py).
+            // Only the order of processing changes: every ray, its sample and its light are what they were.
+            if (threadIdx.x == 0) S.n_live_tile = 0;
+            __syncthreads();
+            const int slot0 = (int)((unsigned)s0 / (unsigned)spp);
+            for (int i = threadIdx.x; i < WF_FEED; i += blockDim.x) {
+                uint2 e;
+                const bool live = i < n_it && classify(s0 + i, e);
+                unsigned key = 0xFFFFFFFFu;
+                if (live) {
+                    const unsigned pix = e.x / (unsigned)spp - (unsigned)slot0;   // <= WF_FEED / 64 pixels per tile
+                    key = (pix << 26) | ((unsigned)light_rank[e.y] << 10) | (unsigned)i;
+                    S.sortkk[i] = (unsigned short)e.y;
+                }
+                S.sortk[i] = key;
+                const unsigned b = __ballot_sync(0xffffffffu, live);
+                if ((threadIdx.x & 31) == 0 && b) atomicAdd(&S.n_live_tile, __popc(b));
+            }
+            // bitonic sort of the WF_FEED keys (dead entries sort to the end)
+            for (int k = 2; k <= WF_FEED; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    __syncthreads();
+                    for (int t = threadIdx.x; t < WF_FEED / 2; t += blockDim.x) {
+                        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                        const int hi = lo | j;
+                        const unsigned a = S.sortk[lo], b = S.sortk[hi];
+                        const bool up = (lo & k) == 0;
+                        if ((a > b) == up) { S.sortk[lo] = b; S.sortk[hi] = a; }
                     }
-                } else if (mode >= IA_MODE_MATS) {
-                    live = true;  // no cosine mask: every foreground sample traces its sampled direction(s)
-                    e = make_uint2(su, 0);
-                } else {
-                    const float* n = samples[src].n;
-                    uint32_t key = ia_pixel_key(seed, (uint64_t)(ray_index_base + hit_rays[slot]));
-                    uint32_t kk = ia_permute((uint32_t)j, (uint32_t)spp, key);
-                    const float* wo = light_dir_s + kk * 3;
-                    float cosv = n[0] * wo[0] + n[1] * wo[1] + n[2] * wo[2];
-                    live = cosv > 1e-6f;
-                    e = make_uint2(su, kk);
                 }
             }
+            __syncthreads();
+            const int n_live = S.n_live_tile;
+            const int base = S.ring_tail;
+            for (int pos = threadIdx.x; pos < n_live; pos += blockDim.x) {
+                const unsigned i = S.sortk[pos] & (unsigned)(WF_FEED - 1);
+                S.ring[(base + pos) & (WF_QCAP - 1)] = make_uint2((unsigned)(s0 + i), (unsigned)S.sortkk[i]);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) S.ring_tail = base + n_live;
+            return;
+        }
+        for (int i = threadIdx.x; i < n_it; i += blockDim.x) {
+            uint2 e;
+            const bool live = classify(s0 + i, e);
             wf_ring_push(S, live, e);
             if (mode == IA_MODE_MIS) wf_ring_push(S, live, make_uint2(e.x, 1));  // the light-sampled ray of the pair
         }
