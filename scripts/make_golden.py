@@ -22,6 +22,9 @@ and, in tests/golden/reference_vectors_bsdf.npz (`make_golden.py bsdf`; the inte
                                                                   lib/torch_pbr/bxdf.py:290-388
   sphere     EnvironmentLightBase.sample_uniform_sphere_stratified(1, 16, 32), eval mode
                                                                   lib/torch_pbr/light.py:161-217
+and, in tests/golden/reference_vectors_voxel.npz (`make_golden.py voxel`):
+  voxel      ForwardDeformer.switch_to_explicit + query_weights_smpl (skinning-weight voxel grid, offset / scale kernels)
+                                                                  models/deformers/fast_snarf/deformer_torch.py:139-197, 234-253
 and, in tests/golden/reference_vectors_smpl.npz (`make_golden.py smpl`):
   smpl       lbs() + SMPL.forward translation on a random model of SMPL's shapes
                                                                   models/deformers/smplx/lbs.py:152-248, body_models.py:342-358
@@ -283,8 +286,48 @@ def main_smpl():
     print("wrote", out, {k: tuple(v.shape) for k, v in g.items()})
 
 
+def main_voxel():
+    """The reference's own skinning-weight voxelisation (ForwardDeformer.switch_to_explicit + query_weights_smpl,
+    models/deformers/fast_snarf/deformer_torch.py:139-197, 234-253) on the synthetic body's A-pose vertices, at
+    resolution 32.  Its two non-Python dependencies are replaced: the JIT-compiled CUDA extensions are not needed on
+    this path (torch.utils.cpp_extension.load is stubbed), and pytorch3d's knn_points (third party, compiled) by a
+    brute-force torch K-nearest-neighbours with the same return convention (squared distances, indices)."""
+    install_stubs()
+    sys.path.insert(0, ROOT)
+    import torch.utils.cpp_extension as cpp
+    cpp.load = lambda *a, **k: types.SimpleNamespace()
+
+    def knn_points(x, y, K=1):
+        d2 = torch.cdist(x.double(), y.double()) ** 2
+        val, idx = torch.topk(d2, K, dim=-1, largest=False)
+        return val.to(x.dtype), idx, None
+    _pkg("lib", os.path.join(REF, "lib"))
+    _pkg("lib.pytorch3d", os.path.join(REF, "lib", "pytorch3d"))
+    _stub("lib.pytorch3d.ops", knn_points=knn_points)
+    sys.modules["lib.pytorch3d"].ops = sys.modules["lib.pytorch3d.ops"]
+    _pkg("models.deformers.fast_snarf", os.path.join(REF, "models", "deformers", "fast_snarf"))
+    from models.deformers.fast_snarf import deformer_torch as ref_def
+    from intrinsicavatar_b200.body import SyntheticBody, a_pose
+    body = SyntheticBody()
+    cano = body(body_pose=a_pose())
+    verts = torch.from_numpy(cano["vertices"])                   # [1,V,3]
+    weights = torch.from_numpy(body.lbs_weights)[None]           # [1,V,24]
+    fd = ref_def.ForwardDeformer.__new__(ref_def.ForwardDeformer)
+    torch.nn.Module.__init__(fd)
+    fd.global_scale = 1.2                                        # deformer_torch.py:32
+    fd.device = torch.device("cpu")
+    fd.switch_to_explicit(resolution=32, smpl_verts=verts, smpl_weights=weights, use_smpl=True)
+    g = dict(voxel_res=np.int64(32), voxel_lbs=fd.lbs_voxel_final[0], voxel_offset_kernel=fd.offset_kernel.reshape(3),
+             voxel_scale_kernel=fd.scale_kernel.reshape(3), voxel_bbox=fd.bbox)
+    out = os.path.join(ROOT, "tests", "golden", "reference_vectors_voxel.npz")
+    np.savez_compressed(out, **{k: (v.detach().cpu().numpy() if torch.is_tensor(v) else v) for k, v in g.items()})
+    print("wrote", out, {k: tuple(np.shape(v)) for k, v in g.items()})
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "smpl":
+    if len(sys.argv) > 1 and sys.argv[1] == "voxel":
+        main_voxel()
+    elif len(sys.argv) > 1 and sys.argv[1] == "smpl":
         main_smpl()
     elif len(sys.argv) > 1 and sys.argv[1] == "bsdf":
         main_bsdf()
