@@ -25,6 +25,8 @@ and, in tests/golden/reference_vectors_bsdf.npz (`make_golden.py bsdf`; the inte
 and, in tests/golden/reference_vectors_voxel.npz (`make_golden.py voxel`):
   voxel      ForwardDeformer.switch_to_explicit + query_weights_smpl (skinning-weight voxel grid, offset / scale kernels)
                                                                   models/deformers/fast_snarf/deformer_torch.py:139-197, 234-253
+and, in tests/golden/reference_vectors_snarf.npz (`make_golden.py snarf`, after `smpl`):
+  snarf      SNARFDeformer.initialize + prepare_deformer, get_bbox_from_smpl    models/deformers/snarf_deformer.py:24-35, 46-126
 and, in tests/golden/reference_vectors_smpl.npz (`make_golden.py smpl`):
   smpl       lbs() + SMPL.forward translation on a random model of SMPL's shapes
                                                                   models/deformers/smplx/lbs.py:152-248, body_models.py:342-358
@@ -324,8 +326,85 @@ def main_voxel():
     print("wrote", out, {k: tuple(np.shape(v)) for k, v in g.items()})
 
 
+def main_snarf():
+    """The reference's own SNARFDeformer.initialize + prepare_deformer (models/deformers/snarf_deformer.py:46-126) driven
+    by a body model that calls the reference's lbs() on the random SMPL-shaped arrays of reference_vectors_smpl.npz (the
+    licensed .pkl is absent) -- pins SnarfSetup.__init__ / .frame (tfs, w2s, root-frame vertices, bboxes)."""
+    install_stubs()
+    sys.path.insert(0, ROOT)
+    import torch.utils.cpp_extension as cpp
+    cpp.load = lambda *a, **k: types.SimpleNamespace()
+
+    def knn_points(x, y, K=1):
+        d2 = torch.cdist(x.double(), y.double()) ** 2
+        val, idx = torch.topk(d2, K, dim=-1, largest=False)
+        return val.to(x.dtype), idx, None
+    _pkg("lib", os.path.join(REF, "lib"))
+    _pkg("lib.pytorch3d", os.path.join(REF, "lib", "pytorch3d"))
+    _stub("lib.pytorch3d.ops", knn_points=knn_points)
+    sys.modules["lib.pytorch3d"].ops = sys.modules["lib.pytorch3d.ops"]
+    _pkg("models.deformers.fast_snarf", os.path.join(REF, "models", "deformers", "fast_snarf"))
+    _stub("torchgeometry")
+    _stub("torchgeometry.core")
+    _stub("torchgeometry.core.conversions",
+          angle_axis_to_rotation_matrix=lambda aa: torch.eye(4)[None].repeat(aa.shape[0], 1, 1))
+    sys.modules["torchgeometry.core"].conversions = sys.modules["torchgeometry.core.conversions"]
+    sys.modules["models.deformers.smplx"].SMPL = object      # (the .pkl-backed class; replaced by FakeSMPL below)
+    from models.deformers import snarf_deformer as ref_sd
+    from models.deformers.smplx import lbs as ref_lbs
+    from intrinsicavatar_b200.body import PARENTS
+    z = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors_smpl.npz"))
+    T = lambda k: torch.from_numpy(z[k]).double()
+
+    class FakeSMPL(torch.nn.Module):
+        """SMPL.forward (body_models.py:288-370) with the arrays above instead of the .pkl."""
+        def __init__(self):
+            super().__init__()
+            self.register_buffer("lbs_weights", T("smpl_weights").float())
+            self.register_buffer("faces_tensor", torch.zeros(1, 3, dtype=torch.long))
+            self.dummy = torch.nn.Parameter(torch.zeros(1))
+
+        def forward(self, betas=None, body_pose=None, global_orient=None, transl=None):
+            go = torch.zeros(1, 3) if global_orient is None else global_orient
+            pose = torch.cat([go, body_pose], 1).double()
+            v, j, A, Tm, so, po = ref_lbs.lbs(betas.double(), pose, T("smpl_v_template")[None], T("smpl_shapedirs"),
+                                             T("smpl_posedirs"), T("smpl_J_regressor"),
+                                             torch.from_numpy(np.asarray(PARENTS, np.int64)), T("smpl_weights"))
+            if transl is not None:
+                v, j = v + transl.double()[:, None], j + transl.double()[:, None]
+                A = A.clone()
+                A[..., :3, 3] += transl.double()[:, None]
+            return types.SimpleNamespace(vertices=v.float(), joints=j.float(), A=A.float())   # SMPL runs in float32
+
+    sd = ref_sd.SNARFDeformer.__new__(ref_sd.SNARFDeformer)
+    sd.body_model = FakeSMPL()
+    fd = ref_sd.ForwardDeformer.__new__(ref_sd.ForwardDeformer)
+    torch.nn.Module.__init__(fd)
+    fd.global_scale = 1.2
+    seen = {}
+    fd.precompute = lambda tfs: seen.__setitem__("tfs", tfs)
+    sd.deformer = fd
+    sd.initialized = False
+    sd.opt = types.SimpleNamespace(cano_pose="a_pose", resolution=32, optimize_betas=False)
+    pose = T("smpl_pose").float()
+    zero = lambda *s_: torch.zeros(*s_)
+    params = {"betas": T("smpl_betas").float(), "body_pose": pose[:, 3:], "global_orient": pose[:, :3],
+              "transl": T("smpl_transl").float(), "pose_correction": zero(1, 69), "global_orient_correction": zero(1, 3),
+              "transl_correction": zero(1, 3)}
+    sd.prepare_deformer(params)
+    g = dict(snarf_tfs=sd.tfs[0], snarf_w2s=sd.w2s[0], snarf_vertices=sd.vertices[0], snarf_cano_bbox=sd.bbox,
+             snarf_tfs_inv_t=sd.tfs_inv_t[0], snarf_lbs_voxel=fd.lbs_voxel_final[0], snarf_offset_kernel=fd.offset_kernel.reshape(3),
+             snarf_scale_kernel=fd.scale_kernel.reshape(3),
+             snarf_deformed_bbox=ref_sd.get_bbox_from_smpl(sd.vertices.float()))
+    out = os.path.join(ROOT, "tests", "golden", "reference_vectors_snarf.npz")
+    np.savez_compressed(out, **{k: v.detach().cpu().numpy().astype(np.float32) for k, v in g.items()})
+    print("wrote", out, {k: tuple(v.shape) for k, v in g.items()})
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "voxel":
+    if len(sys.argv) > 1 and sys.argv[1] == "snarf":
+        main_snarf()
+    elif len(sys.argv) > 1 and sys.argv[1] == "voxel":
         main_voxel()
     elif len(sys.argv) > 1 and sys.argv[1] == "smpl":
         main_smpl()

@@ -212,3 +212,29 @@ def test_lbs_voxelisation_matches_reference():
     # (nearly) equally far: a handful of voxels, smeared by the smoothing passes (observed: 0.024 % above 1e-4, max 0.012)
     assert d.max() < 0.05 and float((d > 1e-4).mean()) < 1e-3 and float(d.mean()) < 1e-6, (d.max(), float((d > 1e-4).mean()))
     assert np.allclose(vox["lbs_voxel"].sum(0), 1.0, atol=1e-5)
+
+
+def test_snarf_setup_matches_reference_prepare_deformer():
+    """SnarfSetup.__init__ / .frame against the reference's own SNARFDeformer.initialize + prepare_deformer
+    (models/deformers/snarf_deformer.py:46-126: tfs = w2s . A . A_cano^-1, root-frame vertices, canonical and deformed
+    cube bboxes, voxel kernels), driven there by the reference's lbs() on the same random SMPL-shaped model
+    (tests/golden/reference_vectors_snarf.npz, scripts/make_golden.py snarf)."""
+    from intrinsicavatar_b200.body import SMPLBody
+    from intrinsicavatar_b200.snarf import SnarfSetup
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z, g = np.load(os.path.join(here, "reference_vectors_smpl.npz")), np.load(os.path.join(here, "reference_vectors_snarf.npz"))
+    body = SMPLBody(z["smpl_v_template"], z["smpl_shapedirs"], z["smpl_posedirs"], z["smpl_J_regressor"], z["smpl_weights"],
+                    betas=z["smpl_betas"][0])
+    s = SnarfSetup(body, resolution=32)
+    assert np.abs(np.linalg.inv(s.tfs_inv_t) - np.linalg.inv(g["snarf_tfs_inv_t"].astype(np.float64))).max() < 1e-5
+    assert np.allclose(s.bbox, g["snarf_cano_bbox"], atol=2e-6)                   # get_bbox_from_smpl, canonical
+    assert np.allclose(s.offset_kernel, g["snarf_offset_kernel"], atol=2e-6)
+    assert np.allclose(s.scale_kernel, g["snarf_scale_kernel"], rtol=2e-6)
+    d = np.abs(s.lbs_voxel - g["snarf_lbs_voxel"])
+    assert d.max() < 0.05 and float((d > 1e-4).mean()) < 2e-3                     # KNN near-ties, as in the voxel test
+    pose = z["smpl_pose"][0]
+    fr = s.frame(pose[3:], pose[:3], z["smpl_transl"][0])
+    assert np.abs(fr["tfs"] - g["snarf_tfs"]).max() < 5e-6
+    assert np.abs(fr["w2s"] - g["snarf_w2s"]).max() < 5e-6
+    assert np.abs(fr["vertices"] - g["snarf_vertices"]).max() < 5e-6
+    assert np.abs(fr["deformed_bbox"].reshape(2, 3) - g["snarf_deformed_bbox"]).max() < 1e-5
