@@ -25,6 +25,10 @@ and, in tests/golden/reference_vectors_bsdf.npz (`make_golden.py bsdf`; the inte
 and, in tests/golden/reference_vectors_voxel.npz (`make_golden.py voxel`):
   voxel      ForwardDeformer.switch_to_explicit + query_weights_smpl (skinning-weight voxel grid, offset / scale kernels)
                                                                   models/deformers/fast_snarf/deformer_torch.py:139-197, 234-253
+and, in tests/golden/reference_vectors_fields.npz (`make_golden.py fields`):
+  fields     VolumeSDF (autograd gradient), VolumeRefDirRadiance, VolumeMaterial with the reference's yaml configs and our
+             state dict; tcnn.Encoding replaced by the oracle's hash grid / SH      models/rf/geometry.py:124-235,
+                                                                  models/rf/radiance.py:82-135, models/pbr/material.py:31-51
 and, in tests/golden/reference_vectors_snarf.npz (`make_golden.py snarf`, after `smpl`):
   snarf      SNARFDeformer.initialize + prepare_deformer, get_bbox_from_smpl    models/deformers/snarf_deformer.py:24-35, 46-126
 and, in tests/golden/reference_vectors_smpl.npz (`make_golden.py smpl`):
@@ -326,6 +330,109 @@ def main_voxel():
     print("wrote", out, {k: tuple(np.shape(v)) for k, v in g.items()})
 
 
+def main_fields():
+    """The reference's own field modules -- VolumeSDF (models/rf/geometry.py:124-235, autograd gradient),
+    VolumeRefDirRadiance (models/rf/radiance.py:82-135), VolumeMaterial (models/pbr/material.py:31-51) with the
+    'hybrid' feature assembly of rgb_normal_mats_alpha_fn (models/intrinsic_avatar.py:1100-1112) -- built from the
+    reference's own yaml configs and loaded with OUR state dict.  tiny-cuda-nn is absent, so `tcnn.Encoding` is a torch
+    module around the oracle's hashgrid / sh4 (the only third-party arithmetic): what this pins is
+    everything first-party around it -- input scaling, include_xyz, the order in which features are concatenated into
+    each MLP (which a real checkpoint depends on), level / SH masks, activations, material scales, the autograd gradient."""
+    import contextlib
+    import yaml
+    install_stubs()
+    sys.path.insert(0, ROOT)
+    from oracle import fields as OF
+    from intrinsicavatar_b200.weights import hashgrid_layout, random_state_dict
+    layout = hashgrid_layout()
+
+    class Encoding(torch.nn.Module):           # stand-in for tcnn.Encoding(n_input_dims, config, dtype)
+        def __init__(self, n_input_dims, config, dtype=torch.float32):
+            super().__init__()
+            self.n_input_dims, self.otype = n_input_dims, config["otype"]
+            if self.otype == "HashGrid":
+                assert (config["n_levels"], config["n_features_per_level"], config["log2_hashmap_size"],
+                        config["base_resolution"]) == (16, 2, 19, 16) and config["interpolation"] == "Linear"
+                self.params = torch.nn.Parameter(torch.zeros(layout["total"] * 2))
+                self.n_output_dims = 32
+            else:
+                assert self.otype == "SphericalHarmonics" and config["degree"] == 4
+                self.n_output_dims = 16
+
+        def forward(self, x):
+            if self.otype == "HashGrid":
+                return OF.hashgrid(x, self.params, layout)
+            return OF.sh4(x * 2.0 - 1.0)     # tcnn maps its [0,1] input to [-1,1]
+    sys.modules["tinycudann"].Encoding = Encoding
+    sys.modules["tinycudann"].free_temporary_memory = lambda: None
+    sys.modules["omegaconf"].OmegaConf.to_container = staticmethod(lambda c, resolve=True: {k: v for k, v in c.items()})
+    torch.cuda.device = lambda *a, **k: contextlib.nullcontext()
+    _stub("cv2")
+    import utils.misc as ref_misc
+    ref_misc.get_rank = lambda: "cpu"
+    models_mod = sys.modules["models"]
+    _stub("lib"); sys.modules["lib"].__path__ = [os.path.join(REF, "lib")]
+    from models import network_utils as ref_net
+    ref_net.get_rank = lambda: "cpu"
+    import models.base as ref_base
+    ref_base.get_rank = lambda: "cpu"
+    _pkg("models.pbr", os.path.join(REF, "models", "pbr"))
+    from models.rf import geometry as ref_geo, radiance as ref_rad
+    ref_geo.get_rank = lambda: "cpu"
+    from models.pbr import material as ref_mat
+
+    class Cfg(dict):
+        __getattr__ = dict.__getitem__
+        def copy(self):
+            return Cfg(self)
+    def cfg(d):
+        return Cfg({k: cfg(v) if isinstance(v, dict) else v for k, v in d.items()})
+    def load(path, **subst):
+        txt = open(os.path.join(REF, "configs", path)).read()
+        for k, v in subst.items():
+            txt = txt.replace(k, str(v))
+        return cfg(yaml.safe_load(txt))
+    gcfg = load("geometry/progressive_hash_grid.yaml", **{"${model.radius}": 1.0})
+    gcfg["isosurface"] = None
+    rcfg = load("radiance/progressive_hash_grid.yaml", **{"${add:${model.geometry.feature_dim}, 3}": 16})
+    mcfg = load("material/shallow_mlp.yaml", **{"${add:${model.geometry.feature_dim}, 35}": 48})
+    geo, rad, mat = ref_geo.VolumeSDF(gcfg), ref_rad.VolumeRefDirRadiance(rcfg), ref_mat.VolumeMaterial(mcfg)
+    sd = random_state_dict(0)
+    sub = lambda pre: {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+    print("geometry:", geo.load_state_dict(sub("geometry."), strict=False))
+    print("radiance:", rad.load_state_dict(sub("radiance."), strict=False))
+    msd = sub("material.")
+    print("material:", mat.load_state_dict(msd, strict=False))
+    for i in range(3):
+        mat.network.weights_per_layer[i].data.copy_(msd[f"network.layers.{i}.weight"])
+        mat.network.biases_per_layer[i].data.copy_(msd[f"network.layers.{i}.bias"])
+        mat.network.lipshitz_bound_per_layer[i].data.copy_(msd[f"network.lipshitz_bound_per_layer.{i}"].reshape(-1))
+    for m in (geo, rad, mat):
+        m.train(False)
+    # the fully warmed-up test-time state: all hash levels and SH bands on (update_step(250, 25000))
+    geo.encoding.encoding.update_step(250, 25000)
+    rad.xyz_encoding.encoding.update_step(250, 25000)
+    rad.sh_mask[:] = 1.0
+    from intrinsicavatar_b200.snarf import SnarfSetup
+    bbox = torch.from_numpy(SnarfSetup().bbox)
+    geo.prepare_bbox(bbox)
+    rad.center, rad.scale = geo.center, geo.scale          # models/intrinsic_avatar.py prepare: radiance shares the bbox
+    torch.manual_seed(5)
+    n = 256
+    pts = geo.center + (torch.rand(n, 3) - 0.5) * geo.scale * 0.7
+    sdf, grad, feat = geo(pts, with_grad=True, with_feature=True)
+    view = torch.nn.functional.normalize(torch.randn(n, 3), dim=-1)
+    nrm = torch.nn.functional.normalize(grad + 0.05 * torch.randn(n, 3), dim=-1)
+    with torch.no_grad():
+        rgb, rgb_feature = rad(pts, feat, view, nrm)
+        materials = mat(torch.cat([rgb_feature, feat], dim=-1))      # material_feature == "hybrid"
+    g = dict(fields_bbox=bbox, fields_points=pts, fields_sdf=sdf, fields_grad=grad, fields_feature=feat, fields_view=view,
+             fields_normal=nrm, fields_rgb=rgb, fields_xyz_embd=rgb_feature, fields_materials=materials)
+    out = os.path.join(ROOT, "tests", "golden", "reference_vectors_fields.npz")
+    np.savez_compressed(out, **{k: v.detach().cpu().numpy().astype(np.float32) for k, v in g.items()})
+    print("wrote", out, {k: tuple(v.shape) for k, v in g.items()})
+
+
 def main_snarf():
     """The reference's own SNARFDeformer.initialize + prepare_deformer (models/deformers/snarf_deformer.py:46-126) driven
     by a body model that calls the reference's lbs() on the random SMPL-shaped arrays of reference_vectors_smpl.npz (the
@@ -402,7 +509,9 @@ def main_snarf():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "snarf":
+    if len(sys.argv) > 1 and sys.argv[1] == "fields":
+        main_fields()
+    elif len(sys.argv) > 1 and sys.argv[1] == "snarf":
         main_snarf()
     elif len(sys.argv) > 1 and sys.argv[1] == "voxel":
         main_voxel()

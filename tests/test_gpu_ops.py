@@ -442,3 +442,14 @@ def test_animation_frames_producer(scene):
     assert im.dtype == np.uint8 and im.shape == (H, W, 3)
     ref = (out["comp_rgb_phys_full"].numpy().clip(0, 1) * 255.).astype(np.uint8).reshape(H, W, 3)[..., ::-1]
     assert np.abs(im.astype(int) - ref.astype(int)).max() <= 1
+
+
+def test_shade_fields_vs_reference_modules(eng):
+    """ia_op_shade_fields (radiance + material kernels) against the REFERENCE's own VolumeRefDirRadiance /
+    VolumeMaterial modules loaded with the same state dict (tests/golden/reference_vectors_fields.npz)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors_fields.npz"))
+    g = {k: torch.from_numpy(z[k]) for k in z.files}
+    rgb, mat = eng.op_shade_fields(g["fields_points"], g["fields_feature"], g["fields_view"], g["fields_normal"])
+    assert (rgb.cpu() - g["fields_rgb"]).abs().max() < 2e-5
+    assert (mat.cpu() - g["fields_materials"]).abs().max() < 2e-5
