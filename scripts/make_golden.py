@@ -25,6 +25,9 @@ and, in tests/golden/reference_vectors_bsdf.npz (`make_golden.py bsdf`; the inte
 and, in tests/golden/reference_vectors_voxel.npz (`make_golden.py voxel`):
   voxel      ForwardDeformer.switch_to_explicit + query_weights_smpl (skinning-weight voxel grid, offset / scale kernels)
                                                                   models/deformers/fast_snarf/deformer_torch.py:139-197, 234-253
+and, in tests/golden/reference_vectors_e2e.npz (`make_golden.py e2e`, through scripts/ref_harness.py):
+  e2e        IntrinsicAvatarModel.forward_ and _compute_occupancy_grid themselves, six frames: render_mode light / mats /
+             mis / uniform_light, global illumination, add_emitter          models/intrinsic_avatar.py:307-362, 396-1651
 and, in tests/golden/reference_vectors_fields.npz (`make_golden.py fields`):
   fields     VolumeSDF (autograd gradient), VolumeRefDirRadiance, VolumeMaterial with the reference's yaml configs and our
              state dict; tcnn.Encoding replaced by the oracle's hash grid / SH      models/rf/geometry.py:124-235,
@@ -433,6 +436,66 @@ def main_fields():
     print("wrote", out, {k: tuple(v.shape) for k, v in g.items()})
 
 
+E2E_CASES = [
+    # name, frame (None = neutral pose), image side, spp, render_mode, global_illumination, add_emitter
+    ("light_neutral", None, 20, 4, "light", False, False),
+    ("light_gi_posed", 0, 20, 8, "light", True, False),
+    ("light_emitter", 0, 16, 4, "light", False, True),
+    ("mats", 0, 16, 8, "mats", False, False),
+    ("mis_gi", 0, 16, 4, "mis", True, False),
+    ("uniform_light", 0, 8, 512, "uniform_light", False, False),
+]
+E2E_KEYS = ("comp_rgb", "comp_normal", "opacity", "depth", "comp_albedo", "comp_roughness", "comp_metallic", "comp_rgb_phys",
+            "comp_demod_phys", "comp_rgb_full", "comp_rgb_phys_full", "comp_albedo_full", "comp_roughness_full")
+
+
+def main_e2e():
+    """The reference's OWN IntrinsicAvatarModel.forward_ (+ _compute_occupancy_grid) executed on CPU through
+    scripts/ref_harness.py (third-party / CUDA ops replaced by the oracle's restatements of exactly those ops; everything
+    else -- control flow and glue of forward_, compute_indirect_radiance, pbr_*_forward, volrend, sample_volume_interaction,
+    the deformer classes, the field modules, torch_pbr -- is the reference's code).  Six small frames covering the four
+    render modes, global illumination and add_emitter."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import ref_harness as H
+    from conftest import Scene
+    H.install()
+    sc = Scene()
+    env = sc.syn.load_envmap()
+    g = {}
+    grids = {}
+    for name, frame, side, spp, mode, gi, emit in E2E_CASES:
+        fr = sc.frame(frame)
+        tabs = sc.syn.random_tables(spp, 32, seed=0)
+        if frame not in grids:
+            # the reference's own test-grid construction (models/intrinsic_avatar.py:307-362) at resolution 32 with the
+            # jitter table product and oracle use in place of torch.rand_like
+            m0 = H.build_model(sc, fr, spp)
+            import models.intrinsic_avatar as ref_ia
+            coords = ref_ia._meshgrid3d(torch.tensor([32, 32, 32])).reshape(-1, 3)
+            orig = torch.rand_like
+            torch.rand_like = lambda t, **k: torch.from_numpy(tabs["jitter"]).reshape(t.shape)
+            try:
+                _, binaries, aabb = m0._compute_occupancy_grid(coords, resolution=32)
+            finally:
+                torch.rand_like = orig
+            assert torch.allclose(aabb, torch.as_tensor(fr["deformed_bbox"]), atol=1e-5)
+            grids[frame] = binaries[0]
+            g[f"grid_{'neutral' if frame is None else frame}"] = np.packbits(binaries[0].numpy().reshape(-1))
+            print("grid", frame, int(binaries.sum()), "occupied cells")
+        m = H.build_model(sc, fr, spp, gi=gi, render_mode=mode, add_emitter=emit, binaries=grids[frame], env=env,
+                          u1=tabs["u1"], u2=tabs["u2"])
+        rays = torch.from_numpy(sc.syn.make_rays(side, side, fr["transl"]))
+        out = H.forward(m, rays, seed=0)
+        for k in E2E_KEYS + (("visibility",) if mode == "uniform_light" else ()):
+            g[f"{name}/{k}"] = out[k].detach().numpy().astype(np.float32)
+        print(name, "hit rays", int((out["opacity"] > 0.5).sum()), "of", rays.shape[0],
+              "mean rgb_phys over hits", float(out["comp_rgb_phys"][out["opacity"][:, 0] > 0.5].mean()))
+    out_path = os.path.join(ROOT, "tests", "golden", "reference_vectors_e2e.npz")
+    np.savez_compressed(out_path, **g)
+    print("wrote", out_path, len(g), "arrays")
+
+
 def main_snarf():
     """The reference's own SNARFDeformer.initialize + prepare_deformer (models/deformers/snarf_deformer.py:46-126) driven
     by a body model that calls the reference's lbs() on the random SMPL-shaped arrays of reference_vectors_smpl.npz (the
@@ -509,7 +572,9 @@ def main_snarf():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "fields":
+    if len(sys.argv) > 1 and sys.argv[1] == "e2e":
+        main_e2e()
+    elif len(sys.argv) > 1 and sys.argv[1] == "fields":
         main_fields()
     elif len(sys.argv) > 1 and sys.argv[1] == "snarf":
         main_snarf()

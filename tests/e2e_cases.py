@@ -1,0 +1,42 @@
+"""Shared by the CPU and GPU end-to-end parity tests: the six frames of tests/golden/reference_vectors_e2e.npz, i.e. the
+outputs of the REFERENCE's own IntrinsicAvatarModel.forward_ / _compute_occupancy_grid executed through
+scripts/ref_harness.py (scripts/make_golden.py e2e)."""
+import os
+
+import numpy as np
+import torch
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors_e2e.npz")
+
+# name, frame (None = neutral pose), image side, spp, render_mode, global_illumination, add_emitter  (= make_golden.E2E_CASES)
+CASES = [
+    ("light_neutral", None, 20, 4, "light", False, False),
+    ("light_gi_posed", 0, 20, 8, "light", True, False),
+    ("light_emitter", 0, 16, 4, "light", False, True),
+    ("mats", 0, 16, 8, "mats", False, False),
+    ("mis_gi", 0, 16, 4, "mis", True, False),
+    ("uniform_light", 0, 8, 512, "uniform_light", False, False),
+]
+KEYS = ("comp_rgb", "comp_normal", "opacity", "depth", "comp_albedo", "comp_roughness", "comp_metallic", "comp_rgb_phys",
+        "comp_demod_phys", "comp_rgb_full", "comp_rgb_phys_full", "comp_albedo_full", "comp_roughness_full")
+GRID_RES = 32
+
+
+def load():
+    z = np.load(GOLD)
+    return {k: z[k] for k in z.files}
+
+
+def grid(gold, frame):
+    bits = np.unpackbits(gold[f"grid_{'neutral' if frame is None else frame}"])[: GRID_RES ** 3]
+    return torch.from_numpy(bits.astype(bool)).reshape(GRID_RES, GRID_RES, GRID_RES)
+
+
+def reference(gold, name, mode):
+    keys = KEYS + (("visibility",) if mode == "uniform_light" else ())
+    return {k: torch.from_numpy(gold[f"{name}/{k}"]) for k in keys}
+
+
+def rel_l2(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float(torch.linalg.norm(a - b) / torch.linalg.norm(b).clamp_min(1e-12))

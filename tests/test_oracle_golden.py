@@ -264,3 +264,51 @@ def test_fields_match_reference_modules(scene):
     mats = F_.material(emb, g["fields_feature"])
     assert torch.allclose(mats, g["fields_materials"], atol=2e-6)
     assert float(g["fields_rgb"].std()) > 1e-3 and float(g["fields_materials"].std()) > 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------
+# End to end: the oracle against the REFERENCE'S OWN forward_ (scripts/ref_harness.py)
+import e2e_cases as E2E
+
+
+@pytest.mark.parametrize("case", E2E.CASES, ids=[c[0] for c in E2E.CASES])
+def test_oracle_matches_reference_forward(scene, case):
+    """oracle/render.py against the outputs of the reference's own IntrinsicAvatarModel.forward_ executed on CPU with only
+    its third-party / CUDA ops replaced (tests/golden/reference_vectors_e2e.npz): control flow and glue of forward_,
+    compute_indirect_radiance, pbr_{light,uniform_light,mats,mis}_forward, rendering_with_normals_mats_sdf,
+    sample_volume_interaction, SNARFDeformer.deform, the field modules, torch_pbr -- relative L2 <= 1e-5 per buffer."""
+    from oracle.render import OracleRenderer
+    name, frame, side, spp, mode, gi, emit = case
+    gold = E2E.load()
+    fr = scene.frame(frame)
+    R = OracleRenderer(scene.fields, scene.snarf.lbs_voxel, scene.snarf.offset_kernel, scene.snarf.scale_kernel,
+                       samples_per_pixel=spp, global_illumination=gi, grid_res=E2E.GRID_RES, render_mode=mode, add_emitter=emit)
+    R.set_pose(fr["tfs"], fr["w2s"])
+    R.binaries = E2E.grid(gold, frame)
+    R.grid_aabb = torch.as_tensor(fr["deformed_bbox"], dtype=torch.float32)
+    tabs = scene.syn.random_tables(spp, E2E.GRID_RES, seed=0)
+    env = scene.syn.load_envmap()
+    if mode == "uniform_light":
+        R.set_light_uniform(env, 16, 32)
+    else:
+        R.set_light(env, tabs["u1"], tabs["u2"])
+    rays = torch.from_numpy(scene.syn.make_rays(side, side, fr["transl"]))
+    got = R.forward(rays, seed=0)
+    ref = E2E.reference(gold, name, mode)
+    assert (ref["opacity"] > 0.5).float().mean() > 0.1
+    for k, r in ref.items():
+        assert E2E.rel_l2(got[k], r) <= 1e-5, (name, k, E2E.rel_l2(got[k], r))
+
+
+@pytest.mark.parametrize("frame", [None, 0])
+def test_oracle_occupancy_grid_matches_reference(scene, frame):
+    """OracleRenderer.build_occupancy against the reference's own _compute_occupancy_grid (models/intrinsic_avatar.py:
+    307-362) run through the harness at resolution 32 with the same jitter table."""
+    gold = E2E.load()
+    fr = scene.frame(frame)
+    R = scene.oracle_renderer(spp=4, grid_res=E2E.GRID_RES)
+    R.set_pose(fr["tfs"], fr["w2s"])
+    tabs = scene.syn.random_tables(4, E2E.GRID_RES, seed=0)
+    mine = R.build_occupancy(fr["deformed_bbox"], tabs["jitter"])
+    ref = E2E.grid(gold, frame)
+    assert ref.sum() > 1000 and torch.equal(mine, ref)
