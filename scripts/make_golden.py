@@ -487,6 +487,11 @@ def main_e2e():
                           u1=tabs["u1"], u2=tabs["u2"])
         rays = torch.from_numpy(sc.syn.make_rays(side, side, fr["transl"]))
         out = H.forward(m, rays, seed=0)
+        if name in ("light_neutral", "uniform_light"):
+            # output contract of the public forward(): key -> (shape, dtype) for n rays (models/intrinsic_avatar.py:1653-1666)
+            pub = H.forward(m, rays, seed=0, public=True)
+            g[f"{name}/contract"] = np.array(sorted(f"{k}|{tuple(v.shape)}|{str(v.dtype).replace('torch.', '')}|{v.device.type}"
+                                                    for k, v in pub.items()))
         for k in E2E_KEYS + (("visibility",) if mode == "uniform_light" else ()):
             g[f"{name}/{k}"] = out[k].detach().numpy().astype(np.float32)
         print(name, "hit rays", int((out["opacity"] > 0.5).sum()), "of", rays.shape[0],

@@ -316,7 +316,7 @@ def build_model(scene, frame, spp, gi=False, render_mode="light", add_emitter=Fa
     m.rank = "cpu"
     m.config = cfg({"global_illumination": gi, "render_mode": render_mode, "resample_light": True,
                     "grid_prune_occ_thre": 0.001, "light": {"name": "envlight-tensor"}, "add_emitter": add_emitter,
-                    "learned_background": False})
+                    "learned_background": False, "ray_chunk": 4096})
     m.geometry, m.density, m.radiance, m.material, m.deformer = geo, den, rad, mat, comp
     m.pose_encoder = lambda *a, **k: None
     m.cond = None
@@ -357,7 +357,7 @@ def ref_def_init_bones():
     return [0, 1, 2, 4, 5, 10, 11, 12, 15, 16, 17, 18, 19]   # deformer_torch.py:27 (ForwardDeformer.__init__ needs .cuda())
 
 
-def forward(m, rays, seed=0, ray_offset=0):
+def forward(m, rays, seed=0, ray_offset=0, public=False):
     """The reference's forward_ on [n,8] world-space rays with the randomness product and oracle use: the keyed per-ray
     light permutation (light / uniform_light) and the counter-based uniforms of MultiLobe.sample / emitter.sample (mats / mis)."""
     import models.intrinsic_avatar as ref_ia
@@ -396,7 +396,7 @@ def forward(m, rays, seed=0, ray_offset=0):
             rt.providers[1] = light_uniform
         try:
             with torch.no_grad():
-                out = m.forward_(rays)
+                out = m.forward(rays) if public else m.forward_(rays)   # public: chunk_batch wrapper + "beta" (:1653-1666)
         finally:
             if m.config.render_mode not in ("light", "uniform_light"):
                 ref_ia.sample_volume_interaction = orig_svi

@@ -260,3 +260,22 @@ def test_product_occupancy_grid_matches_reference(scene, frame):
     grid = e.build_occupancy(fr["deformed_bbox"], tabs["jitter"], E2E.GRID_RES, return_grid=True).cpu()
     ref = E2E.grid(gold, frame)
     assert (grid != ref).float().sum() / ref.sum() < 5e-3
+
+
+@pytest.mark.parametrize("mode,spp,side", [("light", 4, 20), ("uniform_light", 512, 8)])
+def test_model_forward_output_contract_matches_reference(scene, mode, spp, side):
+    """IntrinsicAvatarModel.forward returns exactly what the reference's public forward() returns -- same keys, shapes,
+    dtypes, on the CPU (models/intrinsic_avatar.py:1653-1666 run through the harness; '<case>/contract' in the golden)."""
+    from intrinsicavatar_b200.model import IntrinsicAvatarModel
+    gold = E2E.load()
+    name = "light_neutral" if mode == "light" else "uniform_light"
+    want = sorted(str(s) for s in gold[f"{name}/contract"])
+    frame = None if mode == "light" else 0
+    bp, go, tr = scene.syn.load_pose(frame)
+    m = IntrinsicAvatarModel({"samples_per_pixel": spp, "render_mode": mode, "occ_resolution": 32}, seed=0)
+    m.train(False)
+    m.update_step(250, 25000)
+    m.prepare({"body_pose": bp[None], "global_orient": go[None], "transl": tr[None], "hdri": scene.syn.load_envmap(), "index": 0})
+    out = m.forward(torch.from_numpy(scene.syn.make_rays(side, side, tr)))
+    have = sorted(f"{k}|{tuple(v.shape)}|{str(v.dtype).replace('torch.', '')}|{v.device.type}" for k, v in out.items())
+    assert have == want, (sorted(set(have) - set(want)), sorted(set(want) - set(have)))
