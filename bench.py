@@ -197,7 +197,7 @@ def main():
     ap.add_argument("--gi", type=int, default=1, help="config.model.global_illumination (default 1 = BASELINE configs[3])")
     ap.add_argument("--render-mode", default="light", choices=["light", "uniform_light", "mats", "mis"],
                     help="config.model.render_mode (uniform_light needs --spp 512); the headline workload is light")
-    ap.add_argument("--cpu-res", type=int, default=32)
+    ap.add_argument("--cpu-res", type=int, default=64)
     ap.add_argument("--cpu-spp", type=int, default=8)
     ap.add_argument("--cpu-grid", type=int, default=32)
     ap.add_argument("--distinct-frames", action="store_true",
