@@ -57,6 +57,7 @@ class OracleRenderer:
         self.grid_res = grid_res
         self.chunk = query_chunk
         self.background = torch.ones(3)
+        self.albedo_align_ratio = None     # set externally at test time (systems/intrinsic_avatar.py:601-617)
         self.counters = {"n_query": 0, "n_query_grad": 0, "n_radiance": 0, "n_secondary_rays": 0}
 
     # ------------------------------------------------------------------ per-frame state ----
@@ -327,6 +328,8 @@ class OracleRenderer:
             rgbs, xyz_embd = F_.radiance(q["x_c"], q["feature"], view_w, normal_world)
             self.counters["n_radiance"] += S
             mats = F_.material(xyz_embd, q["feature"])
+            if self.albedo_align_ratio is not None:                      # models/intrinsic_avatar.py:1114-1115
+                mats = torch.cat([mats[:, :3] * torch.as_tensor(self.albedo_align_ratio, dtype=torch.float32), mats[:, 3:]], -1)
             sdf_s = q["sdf"]
         else:
             normal_smpl = normal_world = rgbs = torch.zeros(0, 3)

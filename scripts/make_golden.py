@@ -444,6 +444,9 @@ E2E_CASES = [
     ("mats", 0, 16, 8, "mats", False, False),
     ("mis_gi", 0, 16, 4, "mis", True, False),
     ("uniform_light", 0, 8, 512, "uniform_light", False, False),
+    # externally set test-time attributes (systems/base.py:112-119, systems/intrinsic_avatar.py:601-617): flags after add_emitter
+    ("albedo_only", 0, 16, 4, "light", False, False, {"albedo_only": True}),
+    ("black_bg_albedo_ratio", 0, 16, 4, "light", False, False, {"background": (0.0, 0.0, 0.0), "albedo_align_ratio": (1.2, 0.9, 0.8)}),
 ]
 E2E_KEYS = ("comp_rgb", "comp_normal", "opacity", "depth", "comp_albedo", "comp_roughness", "comp_metallic", "comp_rgb_phys",
             "comp_demod_phys", "comp_rgb_full", "comp_rgb_phys_full", "comp_albedo_full", "comp_roughness_full")
@@ -464,7 +467,8 @@ def main_e2e():
     env = sc.syn.load_envmap()
     g = {}
     grids = {}
-    for name, frame, side, spp, mode, gi, emit in E2E_CASES:
+    for name, frame, side, spp, mode, gi, emit, *extra in E2E_CASES:
+        extra = extra[0] if extra else {}
         fr = sc.frame(frame)
         tabs = sc.syn.random_tables(spp, 32, seed=0)
         if frame not in grids:
@@ -485,6 +489,11 @@ def main_e2e():
             print("grid", frame, int(binaries.sum()), "occupied cells")
         m = H.build_model(sc, fr, spp, gi=gi, render_mode=mode, add_emitter=emit, binaries=grids[frame], env=env,
                           u1=tabs["u1"], u2=tabs["u2"])
+        if "background" in extra:
+            m.background_color = torch.tensor(extra["background"])
+        if "albedo_align_ratio" in extra:
+            m.albedo_align_ratio = torch.tensor(extra["albedo_align_ratio"])
+        m.albedo_only = bool(extra.get("albedo_only", False))
         rays = torch.from_numpy(sc.syn.make_rays(side, side, fr["transl"]))
         out = H.forward(m, rays, seed=0)
         if name in ("light_neutral", "uniform_light"):

@@ -16,6 +16,9 @@ CASES = [
     ("mats", 0, 16, 8, "mats", False, False),
     ("mis_gi", 0, 16, 4, "mis", True, False),
     ("uniform_light", 0, 8, 512, "uniform_light", False, False),
+    # externally set test-time attributes (systems/base.py:112-119, systems/intrinsic_avatar.py:601-617): flags after add_emitter
+    ("albedo_only", 0, 16, 4, "light", False, False, {"albedo_only": True}),
+    ("black_bg_albedo_ratio", 0, 16, 4, "light", False, False, {"background": (0.0, 0.0, 0.0), "albedo_align_ratio": (1.2, 0.9, 0.8)}),
 ]
 KEYS = ("comp_rgb", "comp_normal", "opacity", "depth", "comp_albedo", "comp_roughness", "comp_metallic", "comp_rgb_phys",
         "comp_demod_phys", "comp_rgb_full", "comp_rgb_phys_full", "comp_albedo_full", "comp_roughness_full")

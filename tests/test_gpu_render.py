@@ -229,10 +229,14 @@ def test_product_matches_reference_forward(scene, case):
     """libia_b200 against the outputs of the reference's own IntrinsicAvatarModel.forward_ (executed on CPU with only its
     third-party / CUDA ops replaced by their pinned restatements): relative L2 <= 1e-3 on every buffer, in all four
     render modes, with global illumination and add_emitter."""
-    name, frame, side, spp, mode, gi, emit = case
+    name, frame, side, spp, mode, gi, emit, *extra = case
+    extra = extra[0] if extra else {}
     gold = E2E.load()
     fr = scene.frame(frame)
     e = scene.engine()
+    if extra:
+        e.set_render_config([-1.25, -1.55, -1.25, 1.25, 0.95, 1.25], background=extra.get("background", (1, 1, 1)),
+                            albedo_align_ratio=extra.get("albedo_align_ratio"))
     e.set_pose(fr["tfs"], fr["w2s"])
     e.set_occupancy(fr["deformed_bbox"], E2E.grid(gold, frame))
     tabs = scene.syn.random_tables(spp, E2E.GRID_RES, seed=0)
@@ -242,7 +246,7 @@ def test_product_matches_reference_forward(scene, case):
     else:
         e.set_light(env, tabs["u1"], tabs["u2"])
     rays = torch.from_numpy(scene.syn.make_rays(side, side, fr["transl"])).cuda()
-    got = e.render(rays, gi=gi, seed=0, render_mode=mode, add_emitter=emit)
+    got = e.render(rays, gi=gi, seed=0, render_mode=mode, add_emitter=emit, primary_only=bool(extra.get("albedo_only", False)))
     torch.cuda.synchronize()
     ref = E2E.reference(gold, name, mode)
     for k, r in ref.items():
