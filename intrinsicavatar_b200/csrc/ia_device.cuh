@@ -10,6 +10,7 @@
 //   VolumeRefDirRadiance.forward (+tcnn SH4)   models/rf/radiance.py:111-135
 //   VolumeMaterial.forward (+LipshitzMLP)      models/pbr/material.py:31-51
 #pragma once
+#include <cuda_fp16.h>
 #include "ia_types.cuh"
 
 #define IA_FULL_TEAM 0xFFFFu
@@ -122,6 +123,34 @@ __device__ __forceinline__ void ia_fetch_J(const IaFrame& p, float gx, float gy,
             J[0] = fmaf(a.x, w, J[0]); J[1] = fmaf(a.y, w, J[1]); J[2] = fmaf(a.z, w, J[2]); J[3] = fmaf(a.w, w, J[3]);
             J[4] = fmaf(b.x, w, J[4]); J[5] = fmaf(b.y, w, J[5]); J[6] = fmaf(b.z, w, J[6]); J[7] = fmaf(b.w, w, J[7]);
             J[8] = fmaf(cc.x, w, J[8]); J[9] = fmaf(cc.y, w, J[9]); J[10] = fmaf(cc.z, w, J[10]); J[11] = fmaf(cc.w, w, J[11]);
+        }
+    }
+#elif IA_FETCH_MODE == 5
+    const int W = p.W, H = p.H, D = p.D;
+    // canonical position of voxel (xi, yi, zi): the inverse of g = scl * (x + off) at the align_corners=True lattice
+    const float hx = 2.0f / (float)(W - 1) / p.scl[0], hy = 2.0f / (float)(H - 1) / p.scl[1], hz = 2.0f / (float)(D - 1) / p.scl[2];
+    const float bx = -1.0f / p.scl[0] - p.off[0], by = -1.0f / p.scl[1] - p.off[1], bz = -1.0f / p.scl[2] - p.off[2];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        int xi = cn.x0 + (c & 1), yi = cn.y0 + ((c >> 1) & 1), zi = cn.z0 + (c >> 2);
+        float w = ((c & 1) ? cn.wx1 : cn.wx0) * ((c & 2) ? cn.wy1 : cn.wy0) * ((c & 4) ? cn.wz1 : cn.wz0);
+        if (xi >= 0 && xi < W && yi >= 0 && yi < H && zi >= 0 && zi < D) {
+            float r[8];
+            ia_ld256(p.voxel_J + ((size_t)((zi * H + yi) * W + xi)) * 2, r);
+            // r[0..2] = y_c (fp32); r[3..7] = 10 halves: R00 R01 | R02 R10 | R11 R12 | R20 R21 | R22 pad
+            const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&r[3]));
+            const float2 h1 = __half22float2(*reinterpret_cast<const __half2*>(&r[4]));
+            const float2 h2 = __half22float2(*reinterpret_cast<const __half2*>(&r[5]));
+            const float2 h3 = __half22float2(*reinterpret_cast<const __half2*>(&r[6]));
+            const float2 h4 = __half22float2(*reinterpret_cast<const __half2*>(&r[7]));
+            const float R00 = h0.x, R01 = h0.y, R02 = h1.x, R10 = h1.y, R11 = h2.x, R12 = h2.y, R20 = h3.x, R21 = h3.y, R22 = h4.x;
+            const float cx = fmaf((float)xi, hx, bx), cy = fmaf((float)yi, hy, by), cz = fmaf((float)zi, hz, bz);
+            const float t0 = r[0] - (R00 * cx + R01 * cy + R02 * cz);
+            const float t1 = r[1] - (R10 * cx + R11 * cy + R12 * cz);
+            const float t2 = r[2] - (R20 * cx + R21 * cy + R22 * cz);
+            J[0] = fmaf(R00, w, J[0]); J[1] = fmaf(R01, w, J[1]); J[2] = fmaf(R02, w, J[2]); J[3] = fmaf(t0, w, J[3]);
+            J[4] = fmaf(R10, w, J[4]); J[5] = fmaf(R11, w, J[5]); J[6] = fmaf(R12, w, J[6]); J[7] = fmaf(t1, w, J[7]);
+            J[8] = fmaf(R20, w, J[8]); J[9] = fmaf(R21, w, J[9]); J[10] = fmaf(R22, w, J[10]); J[11] = fmaf(t2, w, J[11]);
         }
     }
 #elif IA_FETCH_MODE == 3

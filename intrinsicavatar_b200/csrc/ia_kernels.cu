@@ -1,6 +1,7 @@
 // libia_b200: kernels + C ABI of the B200-native IntrinsicAvatar render path (sm_100a).
 // See include/ia_b200.h for the ABI and the reference interfaces each entry point replaces.
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -267,7 +268,23 @@ __global__ void k_precompute(const __grid_constant__ IaFrame p, float4* __restri
         J[k] = s;
     }
     float4* o = voxel_J + (size_t)v * IA_VOXEL_F4;
-#if IA_FETCH_MODE == 3
+#if IA_FETCH_MODE == 5
+    {
+        // deformed voxel centre in fp32 (evaluated in double), rotation in fp16
+        const int xi = v % p.W, yi = (v / p.W) % p.H, zi = v / (p.W * p.H);
+        const double cx = (2.0 * xi / (p.W - 1) - 1.0) / p.scl[0] - p.off[0];
+        const double cy = (2.0 * yi / (p.H - 1) - 1.0) / p.scl[1] - p.off[1];
+        const double cz = (2.0 * zi / (p.D - 1) - 1.0) / p.scl[2] - p.off[2];
+        const float y0 = (float)((double)J[0] * cx + (double)J[1] * cy + (double)J[2] * cz + (double)J[3]);
+        const float y1 = (float)((double)J[4] * cx + (double)J[5] * cy + (double)J[6] * cz + (double)J[7]);
+        const float y2 = (float)((double)J[8] * cx + (double)J[9] * cy + (double)J[10] * cz + (double)J[11]);
+        __half2 h[5] = {__floats2half2_rn(J[0], J[1]), __floats2half2_rn(J[2], J[4]), __floats2half2_rn(J[5], J[6]),
+                        __floats2half2_rn(J[8], J[9]), __floats2half2_rn(J[10], 0.f)};
+        const float* hf = reinterpret_cast<const float*>(h);
+        o[0] = make_float4(y0, y1, y2, hf[0]);
+        o[1] = make_float4(hf[1], hf[2], hf[3], hf[4]);
+    }
+#elif IA_FETCH_MODE == 3
     voxel_J[(size_t)v * 2 + 0] = make_float4(J[0], J[1], J[2], J[3]);
     voxel_J[(size_t)v * 2 + 1] = make_float4(J[4], J[5], J[6], J[7]);
     voxel_J[(size_t)nvox * 2 + v] = make_float4(J[8], J[9], J[10], J[11]);
@@ -323,7 +340,12 @@ extern "C" int ia_set_render_config(ia_ctx* c, const float* aabb, int n_per_ray,
 __global__ void k_op_precompute_out(const float4* __restrict__ vj, float* __restrict__ out, int nvox) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nvox) return;
-#if IA_FETCH_MODE == 3
+#if IA_FETCH_MODE == 5
+    // (the 32-byte encoding is lossy: the reference layout cannot be read back; report zeros)
+#pragma unroll
+    for (int k = 0; k < 12; k++) out[(size_t)k * nvox + v] = 0.f;
+    (void)vj;
+#elif IA_FETCH_MODE == 3
     const float* sa = reinterpret_cast<const float*>(vj + (size_t)v * 2);
     const float* sb = reinterpret_cast<const float*>(vj + (size_t)nvox * 2 + v);
 #pragma unroll
