@@ -36,7 +36,7 @@ DEFAULT_CONFIG = {
     "resample_light": True,
     "add_emitter": False,
     "grid_prune_occ_thre": 0.001,
-    "ray_chunk": 4096,                # accepted, unused: the kernels are persistent over all rays
+    "ray_chunk": 4096,                # the kernels are persistent over all rays; only shapes num_samples (one entry per chunk)
     "secondary_shader_chunk": 160000, # accepted, unused
     "material_feature": "hybrid",
     "phys_kick_in_step": 10000,
@@ -168,7 +168,9 @@ class IntrinsicAvatarModel(torch.nn.Module):
         out = {
             "comp_rgb": o["comp_rgb"], "comp_normal": o["comp_normal"], "opacity": o["opacity"], "depth": o["depth"],
             "rays_valid": valid, "rays_valid_phys": valid,
-            "num_samples": o["num_samples"].sum().to(torch.int32).reshape(1),
+            # one entry per ray_chunk rays, as chunk_batch concatenates forward_'s per-chunk count (models/utils.py:16-61;
+            # SURVEY Appendix A.16): [ceil(N / ray_chunk)] int32
+            "num_samples": self._chunk_sums(o["num_samples"].reshape(-1), int(self.config["ray_chunk"])),
             "comp_rgb_phys": o["comp_rgb_phys"], "comp_demod_phys": o["comp_demod_phys"],
             "comp_albedo": o["comp_albedo"], "comp_metallic": o["comp_metallic"], "comp_roughness": o["comp_roughness"],
         }
@@ -190,6 +192,15 @@ class IntrinsicAvatarModel(torch.nn.Module):
         res = {**out, **{k + "_bg": v for k, v in out_bg.items()}, **{k + "_full": v for k, v in out_full.items()}}
         res["beta"] = torch.tensor(self._beta)
         return res
+
+    @staticmethod
+    def _chunk_sums(ns: torch.Tensor, chunk: int) -> torch.Tensor:
+        n = ns.shape[0]
+        n_chunks = max(1, (n + chunk - 1) // chunk)
+        pad = n_chunks * chunk - n
+        if pad:
+            ns = torch.cat([ns, ns.new_zeros(pad)])
+        return ns.reshape(n_chunks, chunk).sum(1).to(torch.int32)
 
     # ---------------------------------------------------------------- conveniences ----
     def render_image(self, batch: dict, rays: torch.Tensor, H: int, W_: int, **kw) -> dict:

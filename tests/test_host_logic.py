@@ -288,3 +288,14 @@ def test_lightning_checkpoint_ingestion(tmp_path):
     torch.save({"state_dict": bad}, p)
     with pytest.raises(ValueError, match="geometry.network.layers.0.weight_v"):
         W.load_lightning_checkpoint(str(p))
+
+
+def test_num_samples_is_reported_per_ray_chunk():
+    """forward() reports num_samples like the reference's chunk_batch does: one entry per ray_chunk rays
+    (models/utils.py:16-61)."""
+    from intrinsicavatar_b200.model import IntrinsicAvatarModel as M
+    assert M._chunk_sums(torch.ones(400, dtype=torch.int32), 4096).tolist() == [400]
+    assert M._chunk_sums(torch.ones(8192, dtype=torch.int32), 4096).tolist() == [4096, 4096]
+    assert M._chunk_sums(torch.arange(10, dtype=torch.int32), 4).tolist() == [6, 22, 17]
+    assert M._chunk_sums(torch.zeros(0, dtype=torch.int32), 4096).tolist() == [0]
+    assert M._chunk_sums(torch.ones(5, dtype=torch.int32), 4096).dtype == torch.int32
