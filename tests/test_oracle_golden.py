@@ -318,3 +318,31 @@ def test_oracle_occupancy_grid_matches_reference(scene, frame):
     mine = R.build_occupancy(fr["deformed_bbox"], tabs["jitter"])
     ref = E2E.grid(gold, frame)
     assert ref.sum() > 1000 and torch.equal(mine, ref)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference tree (build container only)")
+def test_e2e_golden_is_what_the_reference_produces(scene):
+    """Provenance of tests/golden/reference_vectors_e2e.npz: re-run the reference's own forward_ through
+    scripts/ref_harness.py for one case and compare with the committed fixture (runs only where /root/reference exists)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np, torch\n"
+        "sys.path[:0] = ['%(root)s', '%(root)s/tests', '%(root)s/scripts']\n"
+        "import ref_harness as H, e2e_cases as E\n"
+        "from conftest import Scene\n"
+        "sc = Scene(); gold = E.load(); case = [c for c in E.CASES if c[0] == 'light_emitter'][0]\n"
+        "name, frame, side, spp, mode, gi, emit = case[:7]\n"
+        "fr = sc.frame(frame); tabs = sc.syn.random_tables(spp, E.GRID_RES, seed=0)\n"
+        "m = H.build_model(sc, fr, spp, gi=gi, render_mode=mode, add_emitter=emit, binaries=E.grid(gold, frame),\n"
+        "                  env=sc.syn.load_envmap(), u1=tabs['u1'], u2=tabs['u2'])\n"
+        "out = H.forward(m, torch.from_numpy(sc.syn.make_rays(side, side, fr['transl'])), seed=0)\n"
+        "ref = E.reference(gold, name, mode)\n"
+        "worst = max(float((out[k] - r).abs().max()) for k, r in ref.items())\n"
+        "print('WORST', worst)\n"
+    ) % {"root": os.path.dirname(os.path.dirname(os.path.abspath(__file__)))}
+    # a separate interpreter: the harness replaces modules and patches torch
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    worst = float([l for l in res.stdout.splitlines() if l.startswith("WORST")][-1].split()[1])
+    assert worst < 1e-6, worst
