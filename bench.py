@@ -151,7 +151,7 @@ def cpu_baseline(args, steps=1, warmup=0):
     bp, go, tr = syn.load_pose(0)
     fr = snarf.frame(bp, go, tr)
     tabs = syn.random_tables(spp, args.cpu_grid, seed=0)
-    env = syn.load_envmap()
+    env = syn.load_envmap_full()
     rays = torch.from_numpy(syn.make_rays(res, res, tr))
     R = OracleRenderer(Fields(folded, layout, snarf.bbox), snarf.lbs_voxel, snarf.offset_kernel, snarf.scale_kernel,
                        samples_per_pixel=spp, global_illumination=bool(args.gi), grid_res=args.cpu_grid,
@@ -179,7 +179,7 @@ def workload_config(args):
         "workload": f"{args.res}x{args.res} relight frame, {args.spp} spp, render_mode={args.render_mode}, "
                     f"global_illumination={'true' if args.gi else 'false'}, prepare+forward per step",
         "frame_source": "AIST pose frames 0..7 (frame = " + ("(step + rank)" if args.distinct_frames else "step") + " mod 8 on every rank), synthetic 24-joint body, random-init "
-                        "hash grids + MLPs (seed 0), city.hdr envmap (8x area-downsampled copy, re-expanded to 1024x2048)",
+                        "hash grids + MLPs (seed 0), city.hdr envmap at 1024x2048 (the reference's file as AnimationDataset loads it)",
         "rays_per_frame": args.res * args.res, "spp": args.spp, "gi": bool(args.gi),
         "parallelism": f"frame-per-gpu x{args.gpus}",
         "l2": "flushed between steps (256 MiB write) and per-step sample streams (3.2 GB at 512^2 x 1024) exceed L2",
@@ -239,7 +239,7 @@ def main():
     eng.set_timing(True)
 
     n_rays = args.res * args.res
-    env_h = torch.from_numpy(syn.load_envmap()).pin_memory()
+    env_h = torch.from_numpy(syn.load_envmap_full()).pin_memory()
     env_d = env_h.to(dev)
     tabs = syn.random_tables(args.spp, 64, seed=0)
     jitter = torch.from_numpy(tabs["jitter"]).to(dev)

@@ -6,9 +6,12 @@ pose stream, environment map, explicit random tables.  Host-side, numpy.
     (datasets/animation.py:19-27); near/far = |transl| -/+ 1 (:185-189).
   * pose: frames of ``load/animation/aist/poses.npz`` (first 8 frames shipped in data/), transl
     re-based to (0, 0.15, 5) (datasets/animation.py:127-131); ``neutral`` = zero pose.
-  * light: ``data/city_128x256_f16.npy`` = the reference's hdri_images/city.hdr area-downsampled
-    8x (cv2.INTER_AREA), bilinearly re-expanded to 1024x2048 -- the full-resolution file lives only
-    in /root/reference, which does not exist on the GPU box.
+  * light: ``data/city_1024x2048_f16.npz`` = the reference's hdri_images/city.hdr as AnimationDataset hands it
+    to the model (cv2.imread ANYDEPTH|COLOR -> RGB -> cv2.resize(2048, 1024, INTER_AREA), datasets/animation.py:196-204),
+    stored as fp16 -- exact: RGBE texels have 8-bit mantissas, the 52 736-nit sun fits fp16 (``load_envmap_full``; the
+    bench and the high-spp goldens use it).  ``data/city_128x256_f16.npy`` = the same image area-downsampled 8x and
+    bilinearly re-expanded to 1024x2048 (``load_envmap``; the stand-in of round 1, kept because the round-1 goldens
+    were generated with it).
 """
 from __future__ import annotations
 
@@ -59,6 +62,11 @@ def load_envmap(H: int = 1024, W: int = 2048) -> np.ndarray:
     top = small[y0c][:, x0c] * (1 - wx) + small[y0c][:, x1c] * wx
     bot = small[y1c][:, x0c] * (1 - wx) + small[y1c][:, x1c] * wx
     return np.ascontiguousarray(top * (1 - wy) + bot * wy, dtype=np.float32)
+
+
+def load_envmap_full() -> np.ndarray:
+    """The reference's city.hdr at 1024x2048, fp32 RGB, exactly as ``datum["hdri"]`` (datasets/animation.py:196-204)."""
+    return np.ascontiguousarray(np.load(os.path.join(_DATA, "city_1024x2048_f16.npz"))["env"].astype(np.float32))
 
 
 def random_tables(spp: int, grid_res: int = 64, seed: int = 0):

@@ -510,6 +510,55 @@ def main_e2e():
     print("wrote", out_path, len(g), "arrays")
 
 
+def main_e2e_hi():
+    """The reference's own forward_ (scripts/ref_harness.py) at the sample counts the bench runs: 64 / 256 / 1024 spp,
+    the last one with global illumination, AIST frame 0, nonzero ray-index offsets, the real city.hdr.
+    -> tests/golden/reference_vectors_e2e_hi.npz"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import time
+    import e2e_cases as E2E
+    import ref_harness as H
+    from conftest import Scene
+    H.install()
+    sc = Scene()
+    env = sc.syn.load_envmap_full()
+    g = {}
+    grid = None
+    only = sys.argv[2:]
+    out_path = os.path.join(ROOT, "tests", "golden", "reference_vectors_e2e_hi.npz")
+    if only and os.path.exists(out_path):
+        z = np.load(out_path)
+        g = {k: z[k] for k in z.files}
+    for name, frame, side, spp, mode, gi, offset in E2E.HI_CASES:
+        if only and name not in only:
+            continue
+        t0 = time.time()
+        fr = sc.frame(frame)
+        tabs = sc.syn.random_tables(spp, 32, seed=0)
+        if grid is None:
+            m0 = H.build_model(sc, fr, spp)
+            import models.intrinsic_avatar as ref_ia
+            coords = ref_ia._meshgrid3d(torch.tensor([32, 32, 32])).reshape(-1, 3)
+            orig = torch.rand_like
+            torch.rand_like = lambda t, **k: torch.from_numpy(tabs["jitter"]).reshape(t.shape)
+            try:
+                _, binaries, aabb = m0._compute_occupancy_grid(coords, resolution=32)
+            finally:
+                torch.rand_like = orig
+            grid = binaries[0]
+            g["grid_0"] = np.packbits(grid.numpy().reshape(-1))
+        m = H.build_model(sc, fr, spp, gi=gi, render_mode=mode, binaries=grid, env=env, u1=tabs["u1"], u2=tabs["u2"])
+        rays = E2E.hi_rays(sc.syn, fr["transl"], side)
+        out = H.forward(m, rays, seed=0, ray_offset=offset)
+        for k in E2E_KEYS:
+            g[f"{name}/{k}"] = out[k].detach().numpy().astype(np.float32)
+        print(name, "hit rays", int((out["opacity"] > 0.5).sum()), "of", rays.shape[0], "mean rgb_phys over hits",
+              float(out["comp_rgb_phys"][out["opacity"][:, 0] > 0.5].mean()), "%.0f s" % (time.time() - t0), flush=True)
+        np.savez_compressed(out_path, **g)
+    print("wrote", out_path, len(g), "arrays")
+
+
 def main_snarf():
     """The reference's own SNARFDeformer.initialize + prepare_deformer (models/deformers/snarf_deformer.py:46-126) driven
     by a body model that calls the reference's lbs() on the random SMPL-shaped arrays of reference_vectors_smpl.npz (the
@@ -588,6 +637,8 @@ def main_snarf():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "e2e":
         main_e2e()
+    elif len(sys.argv) > 1 and sys.argv[1] == "e2e_hi":
+        main_e2e_hi()
     elif len(sys.argv) > 1 and sys.argv[1] == "fields":
         main_fields()
     elif len(sys.argv) > 1 and sys.argv[1] == "snarf":

@@ -20,6 +20,35 @@ CASES = [
     ("albedo_only", 0, 16, 4, "light", False, False, {"albedo_only": True}),
     ("black_bg_albedo_ratio", 0, 16, 4, "light", False, False, {"background": (0.0, 0.0, 0.0), "albedo_align_ratio": (1.2, 0.9, 0.8)}),
 ]
+# Frames in the regime bench.py times (BASELINE configs[2] / [3]): name, frame, side of the full image whose central
+# HI_WINDOW^2 window is rendered (so that where side = 512 the rays are exactly rays of the benched 512^2 frame), spp,
+# render_mode, global_illumination, ray-index offset (the keyed light permutation of ray r uses pixel index r + offset).
+# Light: the real city.hdr (synthetic.load_envmap_full), whose importance-sampled light set contains the sun.
+# tests/golden/reference_vectors_e2e_hi.npz = the reference's own forward_ on them (scripts/make_golden.py e2e_hi).
+GOLD_HI = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors_e2e_hi.npz")
+HI_CASES = [
+    ("light_64", 0, 24, 64, "light", False, 0),             # straddles the spp >= 64 switch of the direction-coherent feed
+    ("light_256", 0, 48, 256, "light", False, 1000),        # BASELINE configs[2] regime
+    ("light_gi_1024", 0, 512, 1024, "light", True, 70000),  # BASELINE configs[3] regime = the default bench workload
+    ("light_gi_1024_wide", 0, 128, 1024, "light", True, 123456),  # same, window across the silhouette
+]
+HI_WINDOW = 12
+
+
+def hi_rays(syn, transl, side):
+    """HI_WINDOW^2 window of the side x side image of synthetic.make_rays, centred horizontally, at 45 % of the image
+    height (the torso: the window must contain hit pixels)."""
+    full = syn.make_rays(side, side, transl).reshape(side, side, 8)
+    w = HI_WINDOW
+    r0, c0 = int(side * 0.45) - w // 2, side // 2 - w // 2
+    return torch.from_numpy(np.ascontiguousarray(full[r0:r0 + w, c0:c0 + w].reshape(-1, 8)))
+
+
+def load_hi():
+    z = np.load(GOLD_HI)
+    return {k: z[k] for k in z.files}
+
+
 KEYS = ("comp_rgb", "comp_normal", "opacity", "depth", "comp_albedo", "comp_roughness", "comp_metallic", "comp_rgb_phys",
         "comp_demod_phys", "comp_rgb_full", "comp_rgb_phys_full", "comp_albedo_full", "comp_roughness_full")
 GRID_RES = 32

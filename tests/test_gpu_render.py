@@ -253,6 +253,29 @@ def test_product_matches_reference_forward(scene, case):
         assert E2E.rel_l2(got[k], r) <= 1e-3, (name, k, E2E.rel_l2(got[k], r))
 
 
+@pytest.mark.parametrize("case", E2E.HI_CASES, ids=[c[0] for c in E2E.HI_CASES])
+def test_product_matches_reference_forward_hi_spp(scene, case):
+    """Parity in the regime bench.py times: the reference's own forward_ at 64 / 256 spp (global illumination off:
+    BASELINE configs[2]) and at 1024 spp with global illumination (configs[3], the default bench workload; one window of
+    the benched 512^2 frame itself and one across the silhouette), real city.hdr, nonzero ray_index_base -- relative L2
+    <= 1e-3 on every buffer.  These frames run the high-spp feed path of the wavefront integrator (spp >= 64)."""
+    name, frame, side, spp, mode, gi, offset = case
+    gold = E2E.load_hi()
+    fr = scene.frame(frame)
+    e = scene.engine()
+    e.set_pose(fr["tfs"], fr["w2s"])
+    e.set_occupancy(fr["deformed_bbox"], E2E.grid(gold, frame))
+    tabs = scene.syn.random_tables(spp, E2E.GRID_RES, seed=0)
+    e.set_light(scene.syn.load_envmap_full(), tabs["u1"], tabs["u2"])
+    rays = E2E.hi_rays(scene.syn, fr["transl"], side).cuda()
+    got = e.render(rays, gi=gi, seed=0, render_mode=mode, ray_index_base=offset)
+    torch.cuda.synchronize()
+    assert e.counters()["overflow"] == 0
+    for k in E2E.KEYS:
+        r = torch.from_numpy(gold[f"{name}/{k}"])
+        assert E2E.rel_l2(got[k], r) <= 1e-3, (name, k, E2E.rel_l2(got[k], r))
+
+
 @pytest.mark.parametrize("frame", [None, 0])
 def test_product_occupancy_grid_matches_reference(scene, frame):
     """ia_build_occupancy against the reference's own _compute_occupancy_grid (resolution 32, same jitter table)."""

@@ -306,6 +306,28 @@ def test_oracle_matches_reference_forward(scene, case):
         assert E2E.rel_l2(got[k], r) <= 1e-4, (name, k, E2E.rel_l2(got[k], r))
 
 
+@pytest.mark.parametrize("case", E2E.HI_CASES[:2], ids=[c[0] for c in E2E.HI_CASES[:2]])
+def test_oracle_matches_reference_forward_hi_spp(scene, case):
+    """The oracle against the reference's own forward_ in the regime bench.py times (64 / 256 spp here; the 1024-spp frames
+    with global illumination take minutes on the CPU and are held on the GPU, tests/test_gpu_render.py): real city.hdr,
+    nonzero ray-index offset.  Same bar as above."""
+    from oracle.render import OracleRenderer
+    name, frame, side, spp, mode, gi, offset = case
+    gold = E2E.load_hi()
+    fr = scene.frame(frame)
+    R = OracleRenderer(scene.fields, scene.snarf.lbs_voxel, scene.snarf.offset_kernel, scene.snarf.scale_kernel,
+                       samples_per_pixel=spp, global_illumination=gi, grid_res=E2E.GRID_RES, render_mode=mode)
+    R.set_pose(fr["tfs"], fr["w2s"])
+    R.binaries = E2E.grid(gold, frame)
+    R.grid_aabb = torch.as_tensor(fr["deformed_bbox"], dtype=torch.float32)
+    tabs = scene.syn.random_tables(spp, E2E.GRID_RES, seed=0)
+    R.set_light(scene.syn.load_envmap_full(), tabs["u1"], tabs["u2"])
+    got = R.forward_(E2E.hi_rays(scene.syn, fr["transl"], side), offset, 0)
+    for k in E2E.KEYS:
+        r = torch.from_numpy(gold[f"{name}/{k}"])
+        assert E2E.rel_l2(got[k], r) <= 1e-4, (name, k, E2E.rel_l2(got[k], r))
+
+
 @pytest.mark.parametrize("frame", [None, 0])
 def test_oracle_occupancy_grid_matches_reference(scene, frame):
     """OracleRenderer.build_occupancy against the reference's own _compute_occupancy_grid (models/intrinsic_avatar.py:
