@@ -32,6 +32,11 @@ typedef struct ia_ctx ia_ctx;
 
 const char* ia_last_error(void);
 int ia_version(void);
+/* Storage of the per-frame blended bone transform (voxel_J), fixed at build time: 1 = 32-byte voxels (deformed voxel
+ * centre fp32 + rotation fp16; Broyden roots agree with the reference's broyden_kernel,
+ * models/deformers/fast_snarf/cuda/fuse_kernel/fuse_cuda_kernel_fast.cu:250-413, to ~1e-5), 0 = 48-byte fp32 voxels (the
+ * reference's values and order of operations: roots within 2e-6, > 90 % bit-identical).                              */
+int ia_voxel_format(void);
 
 /* lifetime ---------------------------------------------------------------------------------- */
 int ia_create(ia_ctx** out, int device);
@@ -67,6 +72,12 @@ int ia_set_pose(ia_ctx* ctx, const float* h_tfs, const float* h_w2s, void* strea
 int ia_set_render_config(ia_ctx* ctx, const float* h_scene_aabb6, int num_samples_per_ray,
                          int num_samples_per_secondary_ray, float secondary_near, float secondary_far,
                          float occ_thre, const float* h_background3, const float* h_albedo_align_ratio3);
+
+/* Capacity of the primary-sample pool of ia_render, in samples (default: 64 per ray of the call).  A frame that needs
+ * more renders the rays that did not fit as background and counts them in IA_CNT_OVERFLOW; the host grows the pool with
+ * this call and renders again (engine.RenderEngine.render(check_overflow=True)).  The reference has no such limit: its
+ * per-chunk tensors are sized by the sample count (models/intrinsic_avatar.py:1232-1262).                                */
+int ia_reserve_samples(ia_ctx* ctx, int64_t n_samples);
 
 /* Test-time occupancy grid (IntrinsicAvatarModel.prepare_test_occupancy_grid /
  * _compute_occupancy_grid, models/intrinsic_avatar.py:307-381; max_connected_component,

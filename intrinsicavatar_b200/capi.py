@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("IA_B200_LIB") or os.path.join(_HERE, "libia_b200.so")
 SRC_DIR = os.path.join(_HERE, "csrc")
 N_COUNTERS = 32
+MAX_SAMPLES_PER_RAY = 256   # IA_CAP (csrc/ia_types.cuh): edges / samples one primary ray can hold
 CNT_PRIMARY_BASE = 16
 COUNTER_NAMES = ["hit_rays", "samples", "queries", "queries_grad", "broyden_fetch", "geo_eval", "rad_eval",
                  "secondary_rays", "overflow", "skin_fetch", "chains_skipped"]
@@ -35,8 +36,8 @@ class IaOutputs(C.Structure):
 
 
 EXPORTS = [
-    "ia_last_error", "ia_version", "ia_create", "ia_destroy", "ia_set_fields", "ia_set_lbs_voxels", "ia_set_pose",
-    "ia_set_render_config", "ia_build_occupancy", "ia_set_occupancy", "ia_set_light", "ia_set_light_uniform", "ia_render", "ia_get_counters", "ia_set_timing", "ia_get_timings",
+    "ia_last_error", "ia_version", "ia_voxel_format", "ia_create", "ia_destroy", "ia_set_fields", "ia_set_lbs_voxels", "ia_set_pose",
+    "ia_set_render_config", "ia_reserve_samples", "ia_build_occupancy", "ia_set_occupancy", "ia_set_light", "ia_set_light_uniform", "ia_render", "ia_get_counters", "ia_set_timing", "ia_get_timings",
     "ia_op_precompute", "ia_op_broyden", "ia_op_query", "ia_op_shade_fields", "ia_op_traverse",
     "ia_op_ray_resampling", "ia_op_ray_resampling_merge", "ia_op_ray_resampling_sdf_fine", "ia_op_unpack_info",
     "ia_op_secondary", "ia_op_brdf", "ia_op_bsdf_sample_pdf", "ia_op_env",

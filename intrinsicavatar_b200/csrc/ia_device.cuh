@@ -62,9 +62,7 @@ __device__ __forceinline__ void ia_ld256(const float4* ptr, float r[8]) {
                  : "l"(ptr));
 }
 
-// Voxel layout (IA_VOXEL_F4 float4 = 64 B, one 128-B line holds two x-neighbours):
-//   half 0 = J[0..5], 0, 0      half 1 = J[6..11], 0, 0
-// Corner set-up shared by the single-lane and the pair-cooperative fetch.
+// Corner set-up of a trilinear fetch.
 struct IaCorners {
     int x0, y0, z0;
     float wx0, wx1, wy0, wy1, wz0, wz1;
@@ -90,29 +88,14 @@ __device__ __forceinline__ bool ia_all_corners_oob(const IaFrame& p, float gx, f
     return x0 < -1 || x0 > p.W - 1 || y0 < -1 || y0 > p.H - 1 || z0 < -1 || z0 > p.D - 1;
 }
 
-// acc[0..5] += w_c * half `h` of corner c, over the 8 corners in the reference order
-// (tnw tne tsw tse bnw bne bsw bse: x fastest, then y, then z), zero padding.
-__device__ __forceinline__ void ia_gather_half(const IaFrame& p, const IaCorners& cn, int h, float acc[6]) {
-    const int W = p.W, H = p.H, D = p.D;
-#pragma unroll
-    for (int c = 0; c < 8; c++) {
-        int xi = cn.x0 + (c & 1), yi = cn.y0 + ((c >> 1) & 1), zi = cn.z0 + (c >> 2);
-        float w = ((c & 1) ? cn.wx1 : cn.wx0) * ((c & 2) ? cn.wy1 : cn.wy0) * ((c & 4) ? cn.wz1 : cn.wz0);
-        if (xi >= 0 && xi < W && yi >= 0 && yi < H && zi >= 0 && zi < D) {
-            float r[8];
-            ia_ld256(p.voxel_J + ((size_t)((zi * H + yi) * W + xi)) * IA_VOXEL_F4 + h * 2, r);
-#pragma unroll
-            for (int k = 0; k < 6; k++) acc[k] = fmaf(r[k], w, acc[k]);
-        }
-    }
-}
-
+// The blended 3x4 transform at a point of the normalised voxel cube: J = [R | t], 8 corners in the reference order
+// (tnw tne tsw tse bnw bne bsw bse: x fastest, then y, then z), zero padding (out-of-grid corners are skipped).
 __device__ __forceinline__ void ia_fetch_J(const IaFrame& p, float gx, float gy, float gz, float J[12]) {
     const IaCorners cn = ia_corners(p, gx, gy, gz);
+    const int W = p.W, H = p.H, D = p.D;
+#if IA_VOXEL32 == 0
 #pragma unroll
     for (int k = 0; k < 12; k++) J[k] = 0.0f;
-#if IA_FETCH_MODE == 0
-    const int W = p.W, H = p.H, D = p.D;
 #pragma unroll
     for (int c = 0; c < 8; c++) {
         int xi = cn.x0 + (c & 1), yi = cn.y0 + ((c >> 1) & 1), zi = cn.z0 + (c >> 2);
@@ -125,11 +108,18 @@ __device__ __forceinline__ void ia_fetch_J(const IaFrame& p, float gx, float gy,
             J[8] = fmaf(cc.x, w, J[8]); J[9] = fmaf(cc.y, w, J[9]); J[10] = fmaf(cc.z, w, J[10]); J[11] = fmaf(cc.w, w, J[11]);
         }
     }
-#elif IA_FETCH_MODE == 5
-    const int W = p.W, H = p.H, D = p.D;
-    // canonical position of voxel (xi, yi, zi): the inverse of g = scl * (x + off) at the align_corners=True lattice
-    const float hx = 2.0f / (float)(W - 1) / p.scl[0], hy = 2.0f / (float)(H - 1) / p.scl[1], hz = 2.0f / (float)(D - 1) / p.scl[2];
-    const float bx = -1.0f / p.scl[0] - p.off[0], by = -1.0f / p.scl[1] - p.off[1], bz = -1.0f / p.scl[2] - p.off[2];
+#else
+    // 32-byte voxels: r[0..2] = y_c (fp32), r[3..7] = 10 halves R00 R01 | R02 R10 | R11 R12 | R20 R21 | R22 pad.
+    //   sum_c w_c (y_c + R_c (x - c_c)),  c_c = c_000 + (bx hx, by hy, bz hz)
+    //     = ybar + Rbar (x - c_000) - hx CX - hy CY - hz CZ,     CX = sum over corners with bx = 1 of w_c R_c[:, 0], ...
+    // so the corner loop only accumulates (Rbar, ybar and the three column sums) and the translation
+    // t_eff = ybar - Rbar c_000 - hx CX - hy CY - hz CZ is formed once; callers then evaluate Rbar x + t_eff as before
+    // (the fp16 error of Rbar cancels between Rbar x and Rbar c_000 up to |x - c_000| <= one voxel).
+    float Rb[9], yb[3], CX[3], CY[3], CZ[3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Rb[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { yb[k] = 0.f; CX[k] = 0.f; CY[k] = 0.f; CZ[k] = 0.f; }
 #pragma unroll
     for (int c = 0; c < 8; c++) {
         int xi = cn.x0 + (c & 1), yi = cn.y0 + ((c >> 1) & 1), zi = cn.z0 + (c >> 2);
@@ -137,95 +127,33 @@ __device__ __forceinline__ void ia_fetch_J(const IaFrame& p, float gx, float gy,
         if (xi >= 0 && xi < W && yi >= 0 && yi < H && zi >= 0 && zi < D) {
             float r[8];
             ia_ld256(p.voxel_J + ((size_t)((zi * H + yi) * W + xi)) * 2, r);
-            // r[0..2] = y_c (fp32); r[3..7] = 10 halves: R00 R01 | R02 R10 | R11 R12 | R20 R21 | R22 pad
             const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&r[3]));
             const float2 h1 = __half22float2(*reinterpret_cast<const __half2*>(&r[4]));
             const float2 h2 = __half22float2(*reinterpret_cast<const __half2*>(&r[5]));
             const float2 h3 = __half22float2(*reinterpret_cast<const __half2*>(&r[6]));
-            const float2 h4 = __half22float2(*reinterpret_cast<const __half2*>(&r[7]));
-            const float R00 = h0.x, R01 = h0.y, R02 = h1.x, R10 = h1.y, R11 = h2.x, R12 = h2.y, R20 = h3.x, R21 = h3.y, R22 = h4.x;
-            const float cx = fmaf((float)xi, hx, bx), cy = fmaf((float)yi, hy, by), cz = fmaf((float)zi, hz, bz);
-            const float t0 = r[0] - (R00 * cx + R01 * cy + R02 * cz);
-            const float t1 = r[1] - (R10 * cx + R11 * cy + R12 * cz);
-            const float t2 = r[2] - (R20 * cx + R21 * cy + R22 * cz);
-            J[0] = fmaf(R00, w, J[0]); J[1] = fmaf(R01, w, J[1]); J[2] = fmaf(R02, w, J[2]); J[3] = fmaf(t0, w, J[3]);
-            J[4] = fmaf(R10, w, J[4]); J[5] = fmaf(R11, w, J[5]); J[6] = fmaf(R12, w, J[6]); J[7] = fmaf(t1, w, J[7]);
-            J[8] = fmaf(R20, w, J[8]); J[9] = fmaf(R21, w, J[9]); J[10] = fmaf(R22, w, J[10]); J[11] = fmaf(t2, w, J[11]);
+            const float R22 = __low2float(*reinterpret_cast<const __half2*>(&r[7]));
+            const float wR[9] = {w * h0.x, w * h0.y, w * h1.x, w * h1.y, w * h2.x, w * h2.y, w * h3.x, w * h3.y, w * R22};
+#pragma unroll
+            for (int k = 0; k < 9; k++) Rb[k] += wR[k];
+#pragma unroll
+            for (int k = 0; k < 3; k++) yb[k] = fmaf(w, r[k], yb[k]);
+            if (c & 1) { CX[0] += wR[0]; CX[1] += wR[3]; CX[2] += wR[6]; }
+            if (c & 2) { CY[0] += wR[1]; CY[1] += wR[4]; CY[2] += wR[7]; }
+            if (c & 4) { CZ[0] += wR[2]; CZ[1] += wR[5]; CZ[2] += wR[8]; }
         }
     }
-#elif IA_FETCH_MODE == 3
-    const int W = p.W, H = p.H, D = p.D;
+    // canonical position of voxel (x0, y0, z0): the inverse of g = scl * (x + off) on the align_corners=True lattice
+    const float c0 = fmaf((float)cn.x0, p.vox_h[0], p.vox_b[0]), c1 = fmaf((float)cn.y0, p.vox_h[1], p.vox_b[1]),
+                c2 = fmaf((float)cn.z0, p.vox_h[2], p.vox_b[2]);
 #pragma unroll
-    for (int c = 0; c < 8; c++) {
-        int xi = cn.x0 + (c & 1), yi = cn.y0 + ((c >> 1) & 1), zi = cn.z0 + (c >> 2);
-        float w = ((c & 1) ? cn.wx1 : cn.wx0) * ((c & 2) ? cn.wy1 : cn.wy0) * ((c & 4) ? cn.wz1 : cn.wz0);
-        if (xi >= 0 && xi < W && yi >= 0 && yi < H && zi >= 0 && zi < D) {
-            const size_t v = (size_t)((zi * H + yi) * W + xi);
-            float r[8];
-            ia_ld256(p.voxel_J + v * 2, r);
-            float4 cc = __ldg(p.voxel_JB + v);
-#pragma unroll
-            for (int k = 0; k < 8; k++) J[k] = fmaf(r[k], w, J[k]);
-            J[8] = fmaf(cc.x, w, J[8]); J[9] = fmaf(cc.y, w, J[9]); J[10] = fmaf(cc.z, w, J[10]); J[11] = fmaf(cc.w, w, J[11]);
-        }
+    for (int i = 0; i < 3; i++) {
+        J[i * 4 + 0] = Rb[i * 3 + 0]; J[i * 4 + 1] = Rb[i * 3 + 1]; J[i * 4 + 2] = Rb[i * 3 + 2];
+        float t = yb[i];
+        t = fmaf(-Rb[i * 3 + 0], c0, t); t = fmaf(-Rb[i * 3 + 1], c1, t); t = fmaf(-Rb[i * 3 + 2], c2, t);
+        t = fmaf(-p.vox_h[0], CX[i], t); t = fmaf(-p.vox_h[1], CY[i], t); t = fmaf(-p.vox_h[2], CZ[i], t);
+        J[i * 4 + 3] = t;
     }
-#else
-    ia_gather_half(p, cn, 0, J);
-    ia_gather_half(p, cn, 1, J + 6);
 #endif
-}
-
-#if IA_FETCH_MODE == 0
-// Row r (0..2) of the trilinear 3x4 transform: one float4 per corner.  Three neighbouring lanes that call
-// this for the same point read the 48 contiguous bytes of each corner voxel together.  All 8 loads are
-// issued before the first use (32 data registers), i.e. one memory round trip per fetch.
-__device__ __forceinline__ float4 ia_fetch_J_row(const IaFrame& p, float gx, float gy, float gz, int r) {
-    const IaCorners cn = ia_corners(p, gx, gy, gz);
-    const int W = p.W, H = p.H, D = p.D;
-    float4 v[8];
-#pragma unroll
-    for (int c = 0; c < 8; c++) {
-        int xi = cn.x0 + (c & 1), yi = cn.y0 + ((c >> 1) & 1), zi = cn.z0 + (c >> 2);
-        v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (xi >= 0 && xi < W && yi >= 0 && yi < H && zi >= 0 && zi < D)
-            v[c] = __ldg(p.voxel_J + ((size_t)((zi * H + yi) * W + xi)) * 3 + r);
-    }
-    float4 J = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int c = 0; c < 8; c++) {
-        int xi = cn.x0 + (c & 1), yi = cn.y0 + ((c >> 1) & 1), zi = cn.z0 + (c >> 2);
-        float w = ((c & 1) ? cn.wx1 : cn.wx0) * ((c & 2) ? cn.wy1 : cn.wy0) * ((c & 4) ? cn.wz1 : cn.wz0);
-        if (xi >= 0 && xi < W && yi >= 0 && yi < H && zi >= 0 && zi < D) {  // zero padding: skipped, not added
-            J.x = fmaf(v[c].x, w, J.x); J.y = fmaf(v[c].y, w, J.y); J.z = fmaf(v[c].z, w, J.z); J.w = fmaf(v[c].w, w, J.w);
-        }
-    }
-    return J;
-}
-#endif
-
-// Pair-cooperative fetch: lanes l and l^1 each read ONE 32-byte half of every corner for both their
-// chains (two lanes share each 64-byte voxel, so a warp-wide request touches half as many lines and
-// every chain needs 8 instead of 24 load instructions per lane-chain), then swap the halves.
-// Must be called by both lanes of each pair (full-warp convergent); a lane without work passes
-// coordinates far outside the grid (no loads are issued for it).
-__device__ __forceinline__ void ia_fetch_J_pair(const IaFrame& p, float gx, float gy, float gz, float J[12]) {
-#if IA_FETCH_MODE != 2
-    ia_fetch_J(p, gx, gy, gz, J);
-    return;
-#endif
-    const int h = threadIdx.x & 1;
-    const float px = __shfl_xor_sync(0xffffffffu, gx, 1), py = __shfl_xor_sync(0xffffffffu, gy, 1),
-                pz = __shfl_xor_sync(0xffffffffu, gz, 1);
-    const IaCorners ca = ia_corners(p, gx, gy, gz), cb = ia_corners(p, px, py, pz);
-    float a[6] = {0, 0, 0, 0, 0, 0}, b[6] = {0, 0, 0, 0, 0, 0};
-    ia_gather_half(p, ca, h, a);
-    ia_gather_half(p, cb, h, b);
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-        float o = __shfl_xor_sync(0xffffffffu, b[k], 1);  // the partner's sum for MY chain, half h^1
-        J[k] = h ? o : a[k];
-        J[6 + k] = h ? a[k] : o;
-    }
 }
 
 // One Broyden chain (one init bone) for one posed point.  fuse_cuda_kernel_fast.cu:250-413.
@@ -313,6 +241,9 @@ __device__ __forceinline__ IaLevel ia_level(const IaFrame& p, int l) {
 #ifndef IA_HASH_NA
 #define IA_HASH_NA 0
 #endif
+#ifndef IA_HASH_PAIR
+#define IA_HASH_PAIR 0   // 1: x-neighbour table entries that form an aligned 16-byte pair are read with one LDG.128
+#endif
 __device__ __forceinline__ float2 ia_ldg_na(const float2* ptr) {
     float2 v;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(ptr));
@@ -338,6 +269,26 @@ __device__ __forceinline__ void ia_hash_level(const float2* __restrict__ table, 
         w[d] = v - fl;
     }
     float2 v[8];
+#if IA_HASH_PAIR
+    // The two x-neighbours of a corner pair are table entries e and o.  Whenever they differ only in bit 0 -- hashed
+    // levels: always when the lower x is even (the x coordinate enters the hash unmultiplied); dense levels: when e is
+    // even -- they are the two halves of ONE aligned 16-byte pair, read with one LDG.128 instead of two LDG.64 (same
+    // sector, one request less); otherwise the second entry is read on its own.
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+        const uint32_t cy = g[1] + ((c >> 1) & 1), cz = g[2] + (c >> 2);
+        uint32_t e, o;
+        if (dense) { e = g[0] + cy * res + cz * res * res; o = e + 1u; }
+        else { const uint32_t r = (cy * 2654435761u) ^ (cz * 805459861u); e = g[0] ^ r; o = (g[0] + 1u) ^ r; }
+        if (pow2) { e &= size - 1u; o &= size - 1u; }
+        else { if (e >= size) e %= size; if (o >= size) o %= size; }
+        const float4 pr = __ldg(reinterpret_cast<const float4*>(tab + (e & ~1u)));
+        const bool hi = e & 1u;
+        v[c] = hi ? make_float2(pr.z, pr.w) : make_float2(pr.x, pr.y);
+        v[c + 1] = hi ? make_float2(pr.x, pr.y) : make_float2(pr.z, pr.w);
+        if ((e ^ o) != 1u) v[c + 1] = __ldg(tab + o);
+    }
+#else
 #pragma unroll
     for (int c = 0; c < 8; c++) {
         uint32_t cx = g[0] + (c & 1), cy = g[1] + ((c >> 1) & 1), cz = g[2] + (c >> 2);
@@ -354,6 +305,7 @@ __device__ __forceinline__ void ia_hash_level(const float2* __restrict__ table, 
         v[c] = ia_ldg_na(tab + idx);
 #endif
     }
+#endif
     f0 = 0.f; f1 = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; c++) {

@@ -16,7 +16,10 @@
 // error handling
 static thread_local std::string g_err;
 extern "C" const char* ia_last_error(void) { return g_err.c_str(); }
-extern "C" int ia_version(void) { return 100; }
+extern "C" int ia_version(void) { return 200; }
+// 1: voxel_J is stored as 32-byte voxels (IA_VOXEL32: Broyden roots agree with the reference kernel to ~1e-5);
+// 0: 48-byte fp32 voxels (bit-compatible arithmetic, roots within 2e-6)
+extern "C" int ia_voxel_format(void) { return IA_VOXEL32; }
 
 #define IA_CHECK_CUDA(expr)                                                                     \
     do {                                                                                        \
@@ -75,7 +78,9 @@ struct ia_ctx {
     float* d_bg = nullptr;       // [n_rays][3] background radiance per ray (background colour / add_emitter)
     // workspace for ia_render
     int64_t ws_rays = 0, ws_samples = 0, ws_resamples = 0;
-    int* d_hit_rays = nullptr;       // [n_rays]
+    int* d_hit_rays = nullptr;       // [n_rays] ray index of every hit slot, in ray order
+    uint8_t* d_hit_flag = nullptr;   // [n_rays] ray enters an occupied cell
+    int* d_blk_cnt = nullptr;        // [ceil(n_rays / 256)] hits per setup block -> exclusive offsets
     float* d_hit_od = nullptr;       // [n_rays][8]: o(3), d(3), far, opacity
     int* d_hit_info = nullptr;       // [n_rays][2]: sample offset, count
     IaSample* d_samples = nullptr;   // [ws_samples]
@@ -167,7 +172,7 @@ extern "C" int ia_destroy(ia_ctx* c) {
                     c->d_light_em, c->d_light_pdf, c->d_u_table, c->d_env_pdf, c->d_env_cols, c->d_env_rows,
                     c->d_env_rowsum, c->d_env_total, c->d_hit_rays, c->d_hit_od, c->d_hit_info, c->d_samples,
                     c->d_rs_t, c->d_rs_w, c->d_rs_src, c->d_acc, c->d_counters, c->d_work, c->d_occ_a, c->d_occ_b,
-                    c->d_occ_hist, c->d_occ_sum, c->d_wf_scratch, c->d_samples_aux, c->d_vis, c->d_bg, c->d_light_key, c->d_light_rank};
+                    c->d_occ_hist, c->d_occ_sum, c->d_wf_scratch, c->d_samples_aux, c->d_vis, c->d_bg, c->d_light_key, c->d_light_rank, c->d_hit_flag, c->d_blk_cnt};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete c;
@@ -243,15 +248,20 @@ extern "C" int ia_set_lbs_voxels(ia_ctx* c, const float* d_lbs_voxel, int D, int
     for (int i = 0; i < 3; i++) { c->f.off[i] = off[i]; c->f.scl[i] = scl[i]; }
     c->f.lbs_w = c->d_lbs_w;
     c->f.voxel_J = c->d_voxel_J;
-    c->f.voxel_JB = c->d_voxel_J + 2 * nvox;
+    {
+        // voxel (xi, yi, zi) sits at g = 2 i / (n - 1) - 1 of the normalised cube, i.e. at x = g / scl - off
+        const int n[3] = {W, H, D};
+        for (int i = 0; i < 3; i++) {
+            c->f.vox_h[i] = (float)(2.0 / (double)(n[i] - 1) / (double)scl[i]);
+            c->f.vox_b[i] = (float)(-1.0 / (double)scl[i] - (double)off[i]);
+        }
+    }
     c->have_lbs = true;
     return IA_OK;
 }
 
-// precompute_kernel (precompute.cu:22-71): blended 3x4 per voxel; channels-last in and out.
-__global__ void k_precompute(const __grid_constant__ IaFrame p, float4* __restrict__ voxel_J, int nvox) {
-    int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= nvox) return;
+// precompute_kernel (precompute.cu:22-71): blended 3x4 per voxel from the channels-last skinning weights.
+__device__ __forceinline__ void ia_blend_J(const IaFrame& p, int v, float J[12]) {
     float w[IA_N_BONES];
     const float4* src = p.lbs_w + (size_t)v * 6;
 #pragma unroll
@@ -259,7 +269,6 @@ __global__ void k_precompute(const __grid_constant__ IaFrame p, float4* __restri
         float4 a = __ldg(src + q);
         w[q * 4 + 0] = a.x; w[q * 4 + 1] = a.y; w[q * 4 + 2] = a.z; w[q * 4 + 3] = a.w;
     }
-    float J[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) {
         float s = 0.f;
@@ -267,37 +276,37 @@ __global__ void k_precompute(const __grid_constant__ IaFrame p, float4* __restri
         for (int j = 0; j < IA_N_BONES; j++) s += w[j] * p.tfs[j][k];
         J[k] = s;
     }
+}
+
+__global__ void k_precompute(const __grid_constant__ IaFrame p, float4* __restrict__ voxel_J, int nvox) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nvox) return;
+    float J[12];
+    ia_blend_J(p, v, J);
     float4* o = voxel_J + (size_t)v * IA_VOXEL_F4;
-#if IA_FETCH_MODE == 5
+#if IA_VOXEL32
     {
-        // deformed voxel centre in fp32 (evaluated in double), rotation in fp16
+        // deformed voxel centre in fp32 (evaluated in double, with the same fp32 lattice constants the fetch uses),
+        // rotation in fp16
         const int xi = v % p.W, yi = (v / p.W) % p.H, zi = v / (p.W * p.H);
-        const double cx = (2.0 * xi / (p.W - 1) - 1.0) / p.scl[0] - p.off[0];
-        const double cy = (2.0 * yi / (p.H - 1) - 1.0) / p.scl[1] - p.off[1];
-        const double cz = (2.0 * zi / (p.D - 1) - 1.0) / p.scl[2] - p.off[2];
+        const double cx = (double)fmaf((float)xi, p.vox_h[0], p.vox_b[0]);
+        const double cy = (double)fmaf((float)yi, p.vox_h[1], p.vox_b[1]);
+        const double cz = (double)fmaf((float)zi, p.vox_h[2], p.vox_b[2]);
+        __half2 h[5] = {__floats2half2_rn(J[0], J[1]), __floats2half2_rn(J[2], J[4]), __floats2half2_rn(J[5], J[6]),
+                        __floats2half2_rn(J[8], J[9]), __floats2half2_rn(J[10], 0.f)};
+        // y_c is formed with the UNROUNDED rotation: the stored pair then gives y_c + R~ (x - c_c) =
+        // J x + t + (R~ - R)(x - c_c), i.e. the fp16 rounding of R only acts on the offset from the voxel centre
         const float y0 = (float)((double)J[0] * cx + (double)J[1] * cy + (double)J[2] * cz + (double)J[3]);
         const float y1 = (float)((double)J[4] * cx + (double)J[5] * cy + (double)J[6] * cz + (double)J[7]);
         const float y2 = (float)((double)J[8] * cx + (double)J[9] * cy + (double)J[10] * cz + (double)J[11]);
-        __half2 h[5] = {__floats2half2_rn(J[0], J[1]), __floats2half2_rn(J[2], J[4]), __floats2half2_rn(J[5], J[6]),
-                        __floats2half2_rn(J[8], J[9]), __floats2half2_rn(J[10], 0.f)};
         const float* hf = reinterpret_cast<const float*>(h);
         o[0] = make_float4(y0, y1, y2, hf[0]);
         o[1] = make_float4(hf[1], hf[2], hf[3], hf[4]);
     }
-#elif IA_FETCH_MODE == 3
-    voxel_J[(size_t)v * 2 + 0] = make_float4(J[0], J[1], J[2], J[3]);
-    voxel_J[(size_t)v * 2 + 1] = make_float4(J[4], J[5], J[6], J[7]);
-    voxel_J[(size_t)nvox * 2 + v] = make_float4(J[8], J[9], J[10], J[11]);
-    (void)o;
-#elif IA_FETCH_MODE == 0
+#else
     o[0] = make_float4(J[0], J[1], J[2], J[3]);
     o[1] = make_float4(J[4], J[5], J[6], J[7]);
     o[2] = make_float4(J[8], J[9], J[10], J[11]);
-#else
-    o[0] = make_float4(J[0], J[1], J[2], J[3]);
-    o[1] = make_float4(J[4], J[5], 0.f, 0.f);
-    o[2] = make_float4(J[6], J[7], J[8], J[9]);
-    o[3] = make_float4(J[10], J[11], 0.f, 0.f);
 #endif
 }
 
@@ -337,31 +346,22 @@ extern "C" int ia_set_render_config(ia_ctx* c, const float* aabb, int n_per_ray,
 
 // ================================================================================================
 // op-level kernels
-__global__ void k_op_precompute_out(const float4* __restrict__ vj, float* __restrict__ out, int nvox) {
+// the blended fp32 transform in the reference's channel-major layout [12][nvox], recomputed from the context's skinning
+// weights and bone transforms (independent of how voxel_J is stored)
+__global__ void k_op_precompute_out(const __grid_constant__ IaFrame p, float* __restrict__ out, int nvox) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nvox) return;
-#if IA_FETCH_MODE == 5
-    // (the 32-byte encoding is lossy: the reference layout cannot be read back; report zeros)
+    float J[12];
+    ia_blend_J(p, v, J);
 #pragma unroll
-    for (int k = 0; k < 12; k++) out[(size_t)k * nvox + v] = 0.f;
-    (void)vj;
-#elif IA_FETCH_MODE == 3
-    const float* sa = reinterpret_cast<const float*>(vj + (size_t)v * 2);
-    const float* sb = reinterpret_cast<const float*>(vj + (size_t)nvox * 2 + v);
-#pragma unroll
-    for (int k = 0; k < 12; k++) out[(size_t)k * nvox + v] = k < 8 ? sa[k] : sb[k - 8];
-#else
-    const float* s = reinterpret_cast<const float*>(vj + (size_t)v * IA_VOXEL_F4);
-#pragma unroll
-    for (int k = 0; k < 12; k++) out[(size_t)k * nvox + v] = s[IA_VOXEL_F4 == 3 ? k : (k < 6 ? k : k + 2)];
-#endif
+    for (int k = 0; k < 12; k++) out[(size_t)k * nvox + v] = J[k];
 }
 
 extern "C" int ia_op_precompute(ia_ctx* c, float* d_out, void* stream) {
     IA_REQUIRE(c && d_out, IA_EINVAL, "ia_op_precompute: NULL argument");
     IA_REQUIRE(c->have_pose, IA_ESTATE, "ia_op_precompute: call ia_set_pose first");
     int nvox = c->f.D * c->f.H * c->f.W;
-    k_op_precompute_out<<<(nvox + 255) / 256, 256, 0, (cudaStream_t)stream>>>(c->d_voxel_J, d_out, nvox);
+    k_op_precompute_out<<<(nvox + 255) / 256, 256, 0, (cudaStream_t)stream>>>(c->f, d_out, nvox);
     IA_LAUNCH_CHECK();
     return IA_OK;
 }

@@ -37,8 +37,13 @@ __device__ __forceinline__ void ia_ray_w2s(const IaFrame& p, const float* __rest
 // bg_rgb [n_rays][3]: what a background-assigned shading sample / an empty ray contributes to the physically
 // based buffers: the background colour, or with add_emitter the envmap along the primary ray
 // (emitter.eval(transform_dirs_s2w(rays_d)), models/intrinsic_avatar.py:1319-1341, 1454-1490).
-__global__ void k_primary_setup(const __grid_constant__ IaFrame p, const float* __restrict__ rays, long long n_rays,
-                                int* __restrict__ hit_rays, float* __restrict__ hit_od, int* __restrict__ work,
+// Hit list in RAY ORDER (deterministic): k_primary_setup flags the rays that enter an occupied cell and counts them per
+// block, k_hit_scan turns the block counts into offsets, k_hit_compact writes (ray index, o, d, far) at
+// offset[block] + rank within the block.  Neighbouring hit slots are then neighbouring rays of the caller's array
+// (neighbouring pixels of an image row): the shading stage feeds them as bundles of parallel rays (ia_wavefront.cuh).
+// (Round 1 appended with one atomic per warp: slots were chunks of <= 32 pixels from random places of the image.)
+__global__ void __launch_bounds__(256) k_primary_setup(const __grid_constant__ IaFrame p, const float* __restrict__ rays, long long n_rays,
+                                uint8_t* __restrict__ hit_flag, int* __restrict__ blk_cnt,
                                 ia_outputs out, float* __restrict__ acc6, float* __restrict__ bg_rgb, const IaEnv E,
                                 int add_emitter) {
     long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -51,6 +56,7 @@ __global__ void k_primary_setup(const __grid_constant__ IaFrame p, const float* 
         float ts, te;
         bool cont;
         hit = m.next(p.occ_bits, p.occ_res, ts, te, cont);
+        hit_flag[r] = hit ? 1 : 0;
         // defaults of a ray without samples
         if (out.comp_rgb) { out.comp_rgb[r * 3] = 0.f; out.comp_rgb[r * 3 + 1] = 0.f; out.comp_rgb[r * 3 + 2] = 0.f; }
         if (out.comp_normal) { out.comp_normal[r * 3] = 0.f; out.comp_normal[r * 3 + 1] = 0.f; out.comp_normal[r * 3 + 2] = 0.f; }
@@ -71,18 +77,65 @@ __global__ void k_primary_setup(const __grid_constant__ IaFrame p, const float* 
 #pragma unroll
         for (int k = 0; k < 6; k++) acc6[r * 6 + k] = hit ? 0.f : bg[k % 3];
     }
-    // warp-aggregated append to the hit list
-    unsigned b = __ballot_sync(0xffffffffu, hit);
-    int lane = threadIdx.x & 31;
-    int base = 0;
-    if (b && lane == 0) base = atomicAdd(&work[IA_W_NHIT], __popc(b));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (hit) {
-        int slot = base + __popc(b & ((1u << lane) - 1));
-        hit_rays[slot] = (int)r;
-        float* od = hit_od + (size_t)slot * 8;
-        od[0] = o[0]; od[1] = o[1]; od[2] = o[2]; od[3] = d[0]; od[4] = d[1]; od[5] = d[2]; od[6] = far; od[7] = 0.f;
+    const int n = __syncthreads_count(hit);
+    if (threadIdx.x == 0) blk_cnt[blockIdx.x] = n;
+}
+
+// exclusive scan of the per-block hit counts (one CTA; in place) and the total -> work[IA_W_NHIT]
+__global__ void __launch_bounds__(1024) k_hit_scan(int* __restrict__ blk_cnt, int n_blocks, int* __restrict__ work) {
+    __shared__ int warp_sum[32];
+    __shared__ int carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < n_blocks; b0 += 1024) {
+        const int b = b0 + threadIdx.x;
+        const int v = b < n_blocks ? blk_cnt[b] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warp_sum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_sum[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            warp_sum[lane] = winc - w;  // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        if (b < n_blocks) blk_cnt[b] = carry + warp_sum[warp] + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_sum[warp] + inc;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) work[IA_W_NHIT] = carry_s;
+}
+
+__global__ void __launch_bounds__(256) k_hit_compact(const __grid_constant__ IaFrame p, const float* __restrict__ rays, long long n_rays,
+                                                     const uint8_t* __restrict__ hit_flag, const int* __restrict__ blk_off,
+                                                     int* __restrict__ hit_rays, float* __restrict__ hit_od) {
+    __shared__ int warp_cnt[8];
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool hit = r < n_rays && hit_flag[r];
+    const unsigned b = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) warp_cnt[warp] = __popc(b);
+    __syncthreads();
+    if (!hit) return;
+    int slot = blk_off[blockIdx.x] + __popc(b & ((1u << lane) - 1));
+    for (int w = 0; w < warp; w++) slot += warp_cnt[w];
+    float o[3], d[3], far;
+    ia_ray_w2s(p, rays + r * 8, o, d, far);
+    hit_rays[slot] = (int)r;
+    float* od = hit_od + (size_t)slot * 8;
+    od[0] = o[0]; od[1] = o[1]; od[2] = o[2]; od[3] = d[0]; od[4] = d[1]; od[5] = d[2]; od[6] = far; od[7] = 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -203,7 +256,13 @@ k_prim_edges(const __grid_constant__ IaFrame p, const float* __restrict__ hit_od
         if (lane == 0) base = atomicAdd(&work[IA_W_NSAMPLES], n_iv);
         base = team.shfl(base, 0);
         const bool pool_ok = (long long)base + n_iv <= sample_cap;
-        if (!pool_ok) c_over++;
+        if (!pool_ok) {
+            // The sample pool is full: this ray renders as background and IA_CNT_OVERFLOW tells the host (engine.render
+            // grows the pool and renders the frame again).  Its part of the pool below the capacity is marked dead so
+            // that k_prim_shade never reads an unwritten record.
+            c_over++;
+            for (long long i = (long long)base + lane; i < sample_cap && i < (long long)base + n_iv; i += IA_TEAM) aux[i].slot = -1;
+        }
         if (pool_ok && lane == 0) {
             int k = 0;
             for (int e = 0; e + 1 < ne; e++) {
@@ -249,6 +308,7 @@ k_prim_shade(const __grid_constant__ IaFrame p, const float* __restrict__ hit_od
     unsigned c_qg = 0, c_fetch = 0, c_geo = 0, c_rad = 0;
     for (long long i = (long long)blockIdx.x * (blockDim.x / IA_TEAM) + threadIdx.x / IA_TEAM; i < n; i += teams) {
         const int slot = aux[i].slot;
+        if (slot < 0) continue;  // dead record of a ray that did not fit the pool (k_prim_edges)
         const float* od = hit_od + (size_t)slot * 8;
         const float o[3] = {od[0], od[1], od[2]}, d[3] = {od[3], od[4], od[5]};
         const float ts = samples[i].ts, te = samples[i].te;
@@ -530,15 +590,14 @@ static int ia_ws_reserve(ia_ctx* c, int64_t n_rays, int spp, bool need_pbr) {
     if (n_rays > c->ws_rays) {
         if (ia_realloc(&c->d_hit_rays, (size_t)n_rays) || ia_realloc(&c->d_hit_od, (size_t)n_rays * 8) ||
             ia_realloc(&c->d_hit_info, (size_t)n_rays * 2) || ia_realloc(&c->d_acc, (size_t)n_rays * 6) ||
-            ia_realloc(&c->d_vis, (size_t)n_rays) || ia_realloc(&c->d_bg, (size_t)n_rays * 3))
+            ia_realloc(&c->d_vis, (size_t)n_rays) || ia_realloc(&c->d_bg, (size_t)n_rays * 3) ||
+            ia_realloc(&c->d_hit_flag, (size_t)n_rays) || ia_realloc(&c->d_blk_cnt, (size_t)(n_rays + 255) / 256))
             return IA_ECUDA;
         c->ws_rays = n_rays;
     }
-    int64_t want_samples = std::max<int64_t>(n_rays * 64, 1 << 16);  // ~38 per HIT ray observed; 64 per ray covers full coverage
-    if (want_samples > c->ws_samples) {
-        if (ia_realloc(&c->d_samples, (size_t)want_samples) || ia_realloc(&c->d_samples_aux, (size_t)want_samples)) return IA_ECUDA;
-        c->ws_samples = want_samples;
-    }
+    // ~38 samples per HIT ray observed; 64 per ray covers full coverage.  Not a bound: a frame that needs more reports
+    // IA_CNT_OVERFLOW and the host grows the pool (ia_reserve_samples) and renders again.
+    if (int e = ia_reserve_samples(c, std::max<int64_t>(n_rays * 64, 1 << 16))) return e;
     if (need_pbr) {
         // worst case every ray hits; grown lazily to n_rays * spp (805 MB at 512^2 x 1024 for 25 % hits
         // would suffice, but the hit count is only known on the device)
@@ -549,6 +608,18 @@ static int ia_ws_reserve(ia_ctx* c, int64_t n_rays, int spp, bool need_pbr) {
                 return IA_ECUDA;
             c->ws_resamples = want;
         }
+    }
+    return IA_OK;
+}
+
+extern "C" int ia_reserve_samples(ia_ctx* c, int64_t n_samples) {
+    IA_REQUIRE(c && n_samples >= 0, IA_EINVAL, "ia_reserve_samples: bad argument");
+    IA_REQUIRE(n_samples < (1ll << 31), IA_EINVAL, "ia_reserve_samples: the pool is indexed with 32-bit integers");
+    IA_CHECK_CUDA(cudaSetDevice(c->device));
+    if (n_samples > c->ws_samples) {
+        IA_CHECK_CUDA(cudaDeviceSynchronize());  // a render using the old pool may still be in flight
+        if (ia_realloc(&c->d_samples, (size_t)n_samples) || ia_realloc(&c->d_samples_aux, (size_t)n_samples)) return IA_ECUDA;
+        c->ws_samples = n_samples;
     }
     return IA_OK;
 }
@@ -593,9 +664,14 @@ extern "C" int ia_render(ia_ctx* c, const float* d_rays, int64_t n_rays, int64_t
     IA_CHECK_CUDA(cudaMemsetAsync(c->d_work, 0, 8 * sizeof(int), st));
     IA_CHECK_CUDA(cudaMemsetAsync(c->d_counters, 0, IA_N_COUNTERS * sizeof(unsigned long long), st));
     IA_STAGE_BEGIN(c, IA_STAGE_SETUP, st);
-    k_primary_setup<<<(unsigned)((n_rays + 255) / 256), 256, 0, st>>>(c->f, d_rays, n_rays, c->d_hit_rays, c->d_hit_od, c->d_work,
-                                                                       *out, c->d_acc, c->d_bg, c->env, add_emitter ? 1 : 0);
-    IA_STAGE_END(c, IA_STAGE_SETUP, st, 1);
+    {
+        const unsigned nb = (unsigned)((n_rays + 255) / 256);
+        k_primary_setup<<<nb, 256, 0, st>>>(c->f, d_rays, n_rays, c->d_hit_flag, c->d_blk_cnt, *out, c->d_acc, c->d_bg, c->env,
+                                            add_emitter ? 1 : 0);
+        k_hit_scan<<<1, 1024, 0, st>>>(c->d_blk_cnt, (int)nb, c->d_work);
+        k_hit_compact<<<nb, 256, 0, st>>>(c->f, d_rays, n_rays, c->d_hit_flag, c->d_blk_cnt, c->d_hit_rays, c->d_hit_od);
+    }
+    IA_STAGE_END(c, IA_STAGE_SETUP, st, 3);
     IA_LAUNCH_CHECK();
     {
         size_t sm1 = IA_GEO_END * sizeof(float) + (IA_PRIMARY_THREADS / IA_TEAM) * sizeof(IaPrimarySmem);

@@ -11,25 +11,23 @@ namespace cg = cooperative_groups;
 #define IA_N_LEVELS 16
 #define IA_TEAM 16  // lanes that cooperate on one posed point: 13 Broyden inits / 16 hash levels
 #define IA_CAP 256  // max edges (and samples) per primary ray
-// voxel_J fetch variants (tuning knob, default = measured best; see DESIGN.md "Broyden fetch"):
-//   0: 48-byte voxels, 3 x LDG.128 per corner, one lane per chain
-//   1: 64-byte padded voxels, 2 x LDG.256 per corner, one lane per chain
-//   2: 64-byte padded voxels, lane pairs fetch one 32-byte half each for both their chains
-//   3: split planes, no padding: A[v] = J[0..7] (32 B, one aligned sector, LDG.256), B[v] = J[8..11] (LDG.128)
-//   5: 32-byte voxels (prepared for round 2, scripts/voxel_precision_study.py): the deformed voxel centre y_c = R_c c_c + t_c
-//      in fp32 (12 B) + the blended rotation R_c in fp16 (18 B) + 2 B pad = ONE aligned sector, one LDG.256 per corner.
-//      The fetch returns the same 3x4 (R, t_eff = y_c - R_c c_c blended), so the fp16 error multiplies |x - c_c| <= one
-//      voxel instead of |x| ~ 1 m: buffers within 4e-5 relative L2 of fp32 storage (plain fp16 storage: 2e-2).  Not
-//      bit-compatible with the reference kernel (roots agree to ~1e-5 instead of 2e-6).
-#ifndef IA_FETCH_MODE
-#define IA_FETCH_MODE 0
+// voxel_J storage (DESIGN.md "Broyden fetch"):
+//   IA_VOXEL32 = 0: 48-byte voxels, the blended 3x4 transform in fp32, 3 x LDG.128 per trilinear corner.  Bit-compatible with
+//      the reference's broyden_kernel (same values, same order of operations).
+//   IA_VOXEL32 = 1: 32-byte voxels = ONE aligned sector, one LDG.256 per corner: the deformed voxel centre
+//      y_c = R_c c_c + t_c in fp32 (12 B) + the blended rotation R_c in fp16 (18 B) + 2 B pad.  The fetch evaluates
+//      sum_c w_c (y_c + R_c (x - c_c)), so the fp16 error multiplies |x - c_c| <= one voxel (2 cm) instead of |x| ~ 1 m:
+//      frame buffers within 4e-5 relative L2 of fp32 storage (scripts/voxel_precision_study.py; plain fp16 storage of the
+//      3x4: 2e-2).  Roots agree with the reference kernel to ~1e-5 instead of 2e-6.  The L1 charges a scattered gather per
+//      load instruction (scripts/gather_microbench.cu: 18.7 G fetches/s with 3 x LDG.128 per corner -- the rate the Broyden
+//      phase of round 1 ran at -- vs 38.0 with one LDG.256).
+#ifndef IA_VOXEL32
+#define IA_VOXEL32 1
 #endif
-#if IA_FETCH_MODE == 5
-#define IA_VOXEL_F4 2
-#elif IA_FETCH_MODE == 0 || IA_FETCH_MODE == 3
-#define IA_VOXEL_F4 3  // float4 per voxel of voxel_J
+#if IA_VOXEL32
+#define IA_VOXEL_F4 2  // float4 per voxel of voxel_J
 #else
-#define IA_VOXEL_F4 4  // 12 floats padded to 64 bytes: half 0 = J[0..5],0,0 ; half 1 = J[6..11],0,0
+#define IA_VOXEL_F4 3
 #endif
 
 // Offsets (in floats) inside the packed MLP weight blob. "T" = stored input-major [in][64].
@@ -61,8 +59,8 @@ struct IaFrame {
     int init_bones[IA_N_INIT];
     float off[3], scl[3];       // reference offset_kernel / scale_kernel
     int D, H, W;                // LBS voxel grid (32,128,128)
-    const float4* voxel_J;      // blended 3x4 per voxel, channels-last; layout per IA_FETCH_MODE
-    const float4* voxel_JB;     // IA_FETCH_MODE 3: plane B (= voxel_J + 2 * D*H*W)
+    float vox_h[3], vox_b[3];   // canonical position of voxel (xi, yi, zi) = vox_b + (xi, yi, zi) * vox_h (x, y, z order)
+    const float4* voxel_J;      // blended 3x4 per voxel, channels-last; layout per IA_VOXEL32
     const float4* lbs_w;        // [D*H*W][6] float4  : 24 skinning weights per voxel, channels-last
     // --- canonical fields
     const float2* geo_hash;

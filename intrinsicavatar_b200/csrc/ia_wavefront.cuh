@@ -26,9 +26,6 @@
 #ifndef WF_CTAS_PER_SM
 #define WF_CTAS_PER_SM 1   // resident CTAs per SM (WF_THREADS * WF_CTAS_PER_SM * regs <= 64K)
 #endif
-#ifndef WF_BROYDEN_LANES
-#define WF_BROYDEN_LANES 1   // lanes per Broyden chain: 1 (one thread per chain) or 3 (row-distributed)
-#endif
 #ifndef WF_R
 #define WF_R 1024      // ray slots per CTA (two per thread): longer phases amortise the barriers and phase tails.
 #endif                 // Measured at 512^2 x 1024 spp: R = 512 775 ms, 1024 743 ms, 1536 752 ms, 2048 751 ms, 4096 804 ms;
@@ -202,7 +199,7 @@ __device__ __forceinline__ void wf_prune_phase(const IaFrame& p, WfShared& S, in
     }
 }
 
-__device__ __forceinline__ void wf_broyden_phase_1lane(const IaFrame& p, WfShared& S, unsigned& c_fetch) {
+__device__ __forceinline__ void wf_broyden_phase(const IaFrame& p, WfShared& S, unsigned& c_fetch) {
     const int n_tasks = S.n_btask;
     int task = wf_grab(S, n_tasks);
     bool fresh = true;
@@ -293,119 +290,6 @@ __device__ __forceinline__ void wf_broyden_phase_1lane(const IaFrame& p, WfShare
     if (c_same) atomicAdd(&S.probe, c_same);
 #endif
 }
-
-#if WF_BROYDEN_LANES == 3
-// Broyden chains of all pending queries (fuse_cuda_kernel_fast.cu:250-413).
-// One chain per group of THREE lanes: lane r owns row r of the fetched 3x4 transform (8 x LDG.128, all
-// in flight together) and column r of the inverse Jacobian; a warp runs 10 chains, lanes 30/31 idle.
-// Values every lane of the group needs (residual n, the Ji columns, c = Ji^T u) are exchanged with
-// shuffles; each scalar is computed by exactly the expression of the one-thread reference kernel.
-// The trip loop is warp-uniform; finished groups are re-filled from the task counter at the trip end.
-__device__ __forceinline__ void wf_broyden_phase(const IaFrame& p, WfShared& S, unsigned& c_fetch) {
-    const unsigned FULL = 0xffffffffu;
-    const int n_tasks = S.n_btask;
-    const int lane = threadIdx.x & 31;
-    const bool lane_ok = lane < 30;
-    const int grp = lane / 3, r = lane - grp * 3;
-    const int s0 = lane_ok ? grp * 3 : lane, s1 = lane_ok ? s0 + 1 : lane, s2 = lane_ok ? s0 + 2 : lane;
-    const bool leader = lane_ok && r == 0;
-    auto refill = [&](bool need) -> int {
-        unsigned b = __ballot_sync(FULL, need && leader);
-        int t = -1;
-        if (b) {
-            const int first = __ffs(b) - 1;
-            int cnt = 0;
-            if (lane == first) cnt = atomicAdd(&S.task_next, __popc(b));
-            cnt = __shfl_sync(FULL, cnt, first);
-            if (need && leader) {
-                t = cnt + __popc(b & ((1u << lane) - 1u));
-                if (t >= n_tasks) t = -1;
-            }
-        }
-        return __shfl_sync(FULL, t, s0);
-    };
-    int task = refill(true);
-    bool fresh = true;
-    float x0 = 0, x1 = 0, x2 = 0, xd0 = 0, xd1 = 0, xd2 = 0, g0 = 0, g1 = 0, g2 = 0, u0 = 0, u1 = 0, u2 = 0;
-    float jc0 = 0, jc1 = 0, jc2 = 0;  // column r of Ji: Ji[0][r], Ji[1][r], Ji[2][r]
-    int it = 0, q = 0, c = 0;
-    while (__any_sync(FULL, task >= 0)) {
-        const bool act = task >= 0;
-        // full Ji on every lane of the group (Jab = Ji[a][b], column b lives on lane b)
-        const float J00 = __shfl_sync(FULL, jc0, s0), J10 = __shfl_sync(FULL, jc1, s0), J20 = __shfl_sync(FULL, jc2, s0);
-        const float J01 = __shfl_sync(FULL, jc0, s1), J11 = __shfl_sync(FULL, jc1, s1), J21 = __shfl_sync(FULL, jc2, s1);
-        const float J02 = __shfl_sync(FULL, jc0, s2), J12 = __shfl_sync(FULL, jc1, s2), J22 = __shfl_sync(FULL, jc2, s2);
-        float ix = -100.f, iy = -100.f, iz = -100.f;  // idle group: far outside the grid, no loads
-        if (act) {
-            if (fresh) {
-                const int tk = S.btask[task];
-                q = tk >> 4; c = tk & 15;
-                xd0 = S.qx[0][q]; xd1 = S.qx[1][q]; xd2 = S.qx[2][q];
-                const float* T = S.tfs13 + c * 12;
-                float d0 = xd0 - T[3], d1 = xd1 - T[7], d2 = xd2 - T[11];
-                x0 = d0 * T[0] + d1 * T[4] + d2 * T[8];
-                x1 = d0 * T[1] + d1 * T[5] + d2 * T[9];
-                x2 = d0 * T[2] + d1 * T[6] + d2 * T[10];
-                u0 = u1 = u2 = 0.f;
-            } else {
-                u0 = -J00 * g0 + -J01 * g1 + -J02 * g2;
-                u1 = -J10 * g0 + -J11 * g1 + -J12 * g2;
-                u2 = -J20 * g0 + -J21 * g1 + -J22 * g2;
-                x0 += u0; x1 += u1; x2 += u2;
-            }
-            ix = p.scl[0] * (x0 + p.off[0]);
-            iy = p.scl[1] * (x1 + p.off[1]);
-            iz = p.scl[2] * (x2 + p.off[2]);
-        }
-        const float4 Jr = ia_fetch_J_row(p, ix, iy, iz, r);
-        const float xdr = r == 0 ? xd0 : (r == 1 ? xd1 : xd2);
-        const float nr = Jr.x * x0 + Jr.y * x1 + Jr.z * x2 + Jr.w - xdr;
-        const float n0 = __shfl_sync(FULL, nr, s0), n1 = __shfl_sync(FULL, nr, s1), n2 = __shfl_sync(FULL, nr, s2);
-        // c = Ji^T u: component r from this lane's column, then shared
-        const float cr = jc0 * u0 + jc1 * u1 + jc2 * u2;
-        const float c0 = __shfl_sync(FULL, cr, s0), c1 = __shfl_sync(FULL, cr, s1), c2 = __shfl_sync(FULL, cr, s2);
-        bool fin = false;
-        if (act) {
-            if (leader) c_fetch++;
-            if (fresh) {
-                jc0 = Jr.x; jc1 = Jr.y; jc2 = Jr.z;   // Ji = (3x3 part of J)^T: column r of Ji = row r of J
-                g0 = n0; g1 = n1; g2 = n2;
-                it = 0;
-                fresh = false;
-            } else {
-                const float nrm = n0 * n0 + n1 * n1 + n2 * n2;
-                bool ok = false;
-                if (nrm < 1e-5f * 1e-5f) {
-                    ok = ix >= -1 && ix <= 1 && iy >= -1 && iy <= 1 && iz >= -1 && iz <= 1;
-                    fin = true;
-                } else if (nrm > 1e-1f * 1e-1f) {
-                    fin = true;
-                } else {
-                    // rank-1 update of the inverse Jacobian (fuse_J_inv_update, :22-55), this lane's column
-                    float dg0 = n0 - g0, dg1 = n1 - g1, dg2 = n2 - g2;
-                    float s = c0 * dg0 + c1 * dg1 + c2 * dg2;
-                    float r0 = -J00 * dg0 - J01 * dg1 - J02 * dg2;
-                    float r1 = -J10 * dg0 - J11 * dg1 - J12 * dg2;
-                    float r2 = -J20 * dg0 - J21 * dg1 - J22 * dg2;
-                    jc0 += cr * (r0 + u0) / s;
-                    jc1 += cr * (r1 + u1) / s;
-                    jc2 += cr * (r2 + u2) / s;
-                    g0 = n0; g1 = n1; g2 = n2;
-                    if (++it >= 10) fin = true;
-                }
-                if (fin && ok && leader) {
-                    float* cd = S.cand + (q * IA_N_INIT + c) * 3;
-                    cd[0] = x0; cd[1] = x1; cd[2] = x2;
-                    atomicOr(&S.qmask[q], 1u << c);
-                }
-            }
-        }
-        const int nt = refill(fin);
-        if (fin) { task = nt; fresh = true; }
-    }
-}
-
-#endif
 
 // filter.cu:10-54 per pending query, then the list of geometry tasks
 __device__ __forceinline__ void wf_filter_phase(WfShared& S, int n_q) {
@@ -779,15 +663,9 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
             if (S.ring_tail - S.ring_head <= 0 && !S.more_tiles) break;
             continue;
         }
-#if WF_BROYDEN_LANES == 1
-        wf_prune_phase(p, S, n_q, c_skip);
-        __syncthreads();
-        wf_broyden_phase_1lane(p, S, c_fetch);
-#else
         wf_prune_phase(p, S, n_q, c_skip);
         __syncthreads();
         wf_broyden_phase(p, S, c_fetch);
-#endif
         __syncthreads();
         wf_filter_phase(S, n_q);
         __syncthreads();

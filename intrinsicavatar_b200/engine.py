@@ -19,6 +19,7 @@ _ARGTYPES = {
     "ia_set_lbs_voxels": [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp],
     "ia_set_pose": [_vp, _vp, _vp, _vp],
     "ia_set_render_config": [_vp, _vp, _i32, _i32, _f32, _f32, _f32, _vp, _vp],
+    "ia_reserve_samples": [_vp, _i64],
     "ia_build_occupancy": [_vp, _vp, _i32, _vp, _vp, _vp],
     "ia_set_occupancy": [_vp, _vp, _i32, _vp, _vp],
     "ia_set_light": [_vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
@@ -230,8 +231,12 @@ class RenderEngine:
         return host
 
     def render(self, rays: torch.Tensor, *, primary_only=False, gi=False, seed=0, ray_index_base=0, outputs=None,
-               render_mode="light", add_emitter=False):
-        """rays: CUDA float32 [n,8].  Returns dict of CUDA tensors (no sync)."""
+               render_mode="light", add_emitter=False, check_overflow=False):
+        """rays: CUDA float32 [n,8].  Returns dict of CUDA tensors (no sync unless ``check_overflow``).
+
+        ``check_overflow``: read the overflow counter after the launch (syncs the stream); a frame whose primary samples
+        did not fit the pool is rendered again with a pool grown to the per-ray maximum, and a ray with more edges than
+        the per-ray capacity raises -- such a frame is never returned silently."""
         assert rays.is_cuda and rays.dtype == torch.float32 and rays.shape[-1] == 8
         rays = rays.contiguous()
         n = rays.shape[0]
@@ -240,7 +245,17 @@ class RenderEngine:
         flags = (capi.RENDER_PRIMARY_ONLY if primary_only else 0) | (capi.RENDER_GI if gi else 0) | \
             capi.RENDER_MODES[render_mode] | (capi.RENDER_ADD_EMITTER if add_emitter else 0)
         check(self.lib.ia_render(self.h, ptr(rays), n, ray_index_base, flags, seed, C.byref(st), _stream()), "ia_render")
+        if check_overflow and self.counters()["overflow"]:
+            self.reserve_samples(n * capi.MAX_SAMPLES_PER_RAY)
+            check(self.lib.ia_render(self.h, ptr(rays), n, ray_index_base, flags, seed, C.byref(st), _stream()), "ia_render")
+            over = self.counters()["overflow"]
+            if over:
+                raise RuntimeError(f"ia_render: {over} rays exceed the per-ray edge capacity ({capi.MAX_SAMPLES_PER_RAY}); "
+                                   "lower num_samples_per_ray")
         return out
+
+    def reserve_samples(self, n_samples: int):
+        check(self.lib.ia_reserve_samples(self.h, int(n_samples)), "ia_reserve_samples")
 
     def counters(self) -> dict:
         a = np.zeros(capi.N_COUNTERS, np.uint64)

@@ -157,7 +157,8 @@ class IntrinsicAvatarModel(torch.nn.Module):
         r = rays.to(dev, torch.float32, non_blocking=True)
         primary_only = self.albedo_only or not self.engine.spp
         o = self.engine.render(r, primary_only=primary_only, gi=bool(self.config["global_illumination"]), seed=self.seed,
-                               render_mode=self.config["render_mode"], add_emitter=bool(self.config["add_emitter"]))
+                               render_mode=self.config["render_mode"], add_emitter=bool(self.config["add_emitter"]),
+                               check_overflow=True)
         n = r.shape[0]
         if move_to_cpu:
             # eval outputs are CPU tensors (models/utils.py:48-55): one packed D2H copy into pinned memory

@@ -11,6 +11,8 @@ import numpy as np
 import pytest
 import torch
 
+from intrinsicavatar_b200 import capi
+
 pytestmark = pytest.mark.gpu
 
 from oracle import build_ref
@@ -79,14 +81,27 @@ def test_broyden_filter_vs_reference(eng, posed, ref_voxels):
                       True, J, valid, ref_voxels["off"], ref_voxels["scl"], 1e-5, 1e-1)
     mask = filt.filter(x, valid)
     gx, gJ, gvraw, gv = eng.op_broyden(xd)
-    # product vs reference kernel: same fp32 arithmetic -> flags identical up to a tiny flip budget
-    assert (gvraw != valid[0]).float().mean() < 1e-4
-    assert (gv != mask[0]).float().mean() < 1e-4
     both = gvraw & valid[0]
     assert both.sum() > 5000
-    assert (gx[both] - x[0][both]).abs().max() < 2e-6
-    assert (gJ[both] - J[0][both]).abs().max() < 1e-3
-    assert float((gx[both] == x[0][both]).float().mean()) > 0.9             # mostly bit-identical
+    if capi.load().ia_voxel_format() == 0:
+        # 48-byte fp32 voxels: same fp32 arithmetic as the reference kernel -> flags identical up to a tiny flip budget,
+        # roots mostly bit-identical
+        assert (gvraw != valid[0]).float().mean() < 1e-4
+        assert (gv != mask[0]).float().mean() < 1e-4
+        assert (gx[both] - x[0][both]).abs().max() < 2e-6
+        assert (gJ[both] - J[0][both]).abs().max() < 1e-3
+        assert float((gx[both] == x[0][both]).float().mean()) > 0.9
+    else:
+        # 32-byte voxels (deformed voxel centre fp32 + rotation fp16, include/ia_b200.h ia_voxel_format): the same roots to
+        # the solver's own convergence radius -- the bar the torch restatement is held to below
+        assert (gvraw != valid[0]).float().mean() < 2e-3
+        assert (gv != mask[0]).float().mean() < 2e-3
+        err = (gx[both] - x[0][both]).abs().max(-1).values
+        print("voxel32 roots vs reference kernel: median %.2e  p99.9 %.2e  max %.2e; flag flips %.2e" % (
+            float(err.median()), float(torch.quantile(err, 0.999)), float(err.max()), float((gvraw != valid[0]).float().mean())))
+        assert torch.quantile(err, 0.999) < 5e-5
+        assert err.max() < 1e-3
+        assert (gJ[both] - J[0][both]).abs().max() < 2e-2
     # oracle vs reference kernel
     R = posed["oracle"]
     ox, oJ, ovraw = odef.broyden(xd.cpu(), R.voxel_J, R.tfs, R.offset, R.scale)
