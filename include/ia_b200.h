@@ -198,6 +198,12 @@ int ia_op_broyden(ia_ctx* ctx, const float* d_xd, int64_t n, float* d_x, float* 
 int ia_op_query(ia_ctx* ctx, const float* d_xd, int64_t n, int with_grad, float* d_sdf, float* d_xc,
                 uint8_t* d_valid, float* d_grad, float* d_grad_cano, float* d_feature, void* stream);
 
+/* Canonical SDF of n points, evaluated the way the wavefront integrator's geometry phase does: hash grid, then the
+ * 35 -> 64 layer as warp-level tensor-core mma (TF32 inputs split in two, fp32 accumulate), softplus(beta = 100), sdf row
+ * of the output layer.  Replaces VolumeSDF.forward without gradient (models/rf/geometry.py:124-146: encoding ->
+ * VanillaMLP, models/network_utils.py:201-244) for A/B tests against the fp32 evaluation.  d_xc [n,3] -> d_sdf [n].   */
+int ia_op_geometry(ia_ctx* ctx, const float* d_xc, int64_t n, float* d_sdf, void* stream);
+
 /* radiance + material at canonical points (radiance.py:111-135, material.py:31-51):
  * d_xc [n,3], d_feature [n,13], d_view_world [n,3], d_normal_world [n,3] -> d_rgb [n,3], d_mat [n,5]. */
 int ia_op_shade_fields(ia_ctx* ctx, const float* d_xc, const float* d_feature, const float* d_view_world,

@@ -96,6 +96,25 @@ __device__ __forceinline__ void ia_fetch_J(const IaFrame& p, float gx, float gy,
 #if IA_VOXEL32 == 0
 #pragma unroll
     for (int k = 0; k < 12; k++) J[k] = 0.0f;
+#if IA_FETCH_BRANCHLESS
+    // no per-corner branch: an out-of-grid corner reads voxel 0 with weight 0 (acc + 0 * v == acc exactly for finite v), so
+    // that all 24 loads of a fetch can be scheduled ahead of the first use
+    const bool xa = cn.x0 >= 0 && cn.x0 < W, xb = cn.x0 + 1 >= 0 && cn.x0 + 1 < W;
+    const bool ya = cn.y0 >= 0 && cn.y0 < H, yb = cn.y0 + 1 >= 0 && cn.y0 + 1 < H;
+    const bool za = cn.z0 >= 0 && cn.z0 < D, zb = cn.z0 + 1 >= 0 && cn.z0 + 1 < D;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const bool ok = ((c & 1) ? xb : xa) && ((c & 2) ? yb : ya) && ((c & 4) ? zb : za);
+        int xi = cn.x0 + (c & 1), yi = cn.y0 + ((c >> 1) & 1), zi = cn.z0 + (c >> 2);
+        float w = ((c & 1) ? cn.wx1 : cn.wx0) * ((c & 2) ? cn.wy1 : cn.wy0) * ((c & 4) ? cn.wz1 : cn.wz0);
+        w = ok ? w : 0.f;
+        const float4* v = p.voxel_J + (ok ? ((size_t)((zi * H + yi) * W + xi)) * 3 : 0);
+        float4 a = __ldg(v), b = __ldg(v + 1), cc = __ldg(v + 2);
+        J[0] = fmaf(a.x, w, J[0]); J[1] = fmaf(a.y, w, J[1]); J[2] = fmaf(a.z, w, J[2]); J[3] = fmaf(a.w, w, J[3]);
+        J[4] = fmaf(b.x, w, J[4]); J[5] = fmaf(b.y, w, J[5]); J[6] = fmaf(b.z, w, J[6]); J[7] = fmaf(b.w, w, J[7]);
+        J[8] = fmaf(cc.x, w, J[8]); J[9] = fmaf(cc.y, w, J[9]); J[10] = fmaf(cc.z, w, J[10]); J[11] = fmaf(cc.w, w, J[11]);
+    }
+#else
 #pragma unroll
     for (int c = 0; c < 8; c++) {
         int xi = cn.x0 + (c & 1), yi = cn.y0 + ((c >> 1) & 1), zi = cn.z0 + (c >> 2);
@@ -108,6 +127,7 @@ __device__ __forceinline__ void ia_fetch_J(const IaFrame& p, float gx, float gy,
             J[8] = fmaf(cc.x, w, J[8]); J[9] = fmaf(cc.y, w, J[9]); J[10] = fmaf(cc.z, w, J[10]); J[11] = fmaf(cc.w, w, J[11]);
         }
     }
+#endif
 #else
     // 32-byte voxels: r[0..2] = y_c (fp32), r[3..7] = 10 halves R00 R01 | R02 R10 | R11 R12 | R20 R21 | R22 pad.
     //   sum_c w_c (y_c + R_c (x - c_c)),  c_c = c_000 + (bx hx, by hy, bz hz)
@@ -240,6 +260,9 @@ __device__ __forceinline__ IaLevel ia_level(const IaFrame& p, int l) {
 // evict the voxel_J lines the Broyden gathers re-use.  IA_HASH_NA: 0 = allocate, 1 = hashed levels only, 2 = all
 #ifndef IA_HASH_NA
 #define IA_HASH_NA 0
+#endif
+#ifndef IA_FETCH_BRANCHLESS
+#define IA_FETCH_BRANCHLESS 0
 #endif
 #ifndef IA_HASH_PAIR
 #define IA_HASH_PAIR 0   // 1: x-neighbour table entries that form an aligned 16-byte pair are read with one LDG.128

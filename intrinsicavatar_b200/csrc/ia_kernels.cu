@@ -68,8 +68,6 @@ struct ia_ctx {
     int env_H = 0, env_W = 0;
     float *d_light_dir_w = nullptr, *d_light_dir_s = nullptr, *d_light_em = nullptr, *d_light_pdf = nullptr;
     float* d_u_table = nullptr;
-    unsigned int* d_light_key = nullptr;    // [spp] Morton key of each light direction over (lon, lat)
-    unsigned short* d_light_rank = nullptr; // [spp] its rank along that curve (direction-coherent ray order)
     float *d_env_pdf = nullptr, *d_env_cols = nullptr, *d_env_rows = nullptr, *d_env_rowsum = nullptr;
     double* d_env_total = nullptr;
     IaEnv env = {};              // tables of the last ia_set_light* call (env itself is the caller's buffer)
@@ -172,7 +170,7 @@ extern "C" int ia_destroy(ia_ctx* c) {
                     c->d_light_em, c->d_light_pdf, c->d_u_table, c->d_env_pdf, c->d_env_cols, c->d_env_rows,
                     c->d_env_rowsum, c->d_env_total, c->d_hit_rays, c->d_hit_od, c->d_hit_info, c->d_samples,
                     c->d_rs_t, c->d_rs_w, c->d_rs_src, c->d_acc, c->d_counters, c->d_work, c->d_occ_a, c->d_occ_b,
-                    c->d_occ_hist, c->d_occ_sum, c->d_wf_scratch, c->d_samples_aux, c->d_vis, c->d_bg, c->d_light_key, c->d_light_rank, c->d_hit_flag, c->d_blk_cnt};
+                    c->d_occ_hist, c->d_occ_sum, c->d_wf_scratch, c->d_samples_aux, c->d_vis, c->d_bg, c->d_hit_flag, c->d_blk_cnt};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete c;
@@ -867,8 +865,7 @@ static int ia_light_alloc(ia_ctx* c, int H, int W, int spp, cudaStream_t st) {
     if (c->spp != spp) {
         if (ia_realloc(&c->d_light_dir_w, (size_t)spp * 3) || ia_realloc(&c->d_light_dir_s, (size_t)spp * 3) ||
             ia_realloc(&c->d_light_em, (size_t)spp * 3) || ia_realloc(&c->d_light_pdf, (size_t)spp) ||
-            ia_realloc(&c->d_u_table, (size_t)spp) || ia_realloc(&c->d_light_key, (size_t)spp) ||
-            ia_realloc(&c->d_light_rank, (size_t)spp))
+            ia_realloc(&c->d_u_table, (size_t)spp))
             return IA_ECUDA;
         // stratified CDF positions of cdf_resampling_kernel, same float recurrence (cdf.cu:53-58,105)
         std::vector<float> u(spp);
@@ -893,39 +890,6 @@ static int ia_env_tables(ia_ctx* c, const float* d_env, int H, int W, cudaStream
     return IA_OK;
 }
 
-// Rank of every light direction along a Morton curve over (lon, lat) in the SMPL frame: the order in which the wavefront
-// integrator feeds a pixel's rays (WfShadePolicy::feed).  n^2 / 2 comparisons on the device; n = spp <= 65535.
-__global__ void k_light_keys(const float* __restrict__ dir_s, int n, unsigned int* __restrict__ keys) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const float PI = 3.14159265358979323846f;
-    const float* d = dir_s + k * 3;
-    float lon = atan2f(d[0], d[2]), lat = asinf(fminf(fmaxf(d[1], -1.f), 1.f));
-    unsigned qx = (unsigned)fminf(fmaxf((lon / (2 * PI) + 0.5f) * 1023.f, 0.f), 1023.f);
-    unsigned qy = (unsigned)fminf(fmaxf((lat / PI + 0.5f) * 1023.f, 0.f), 1023.f);
-    auto part = [](unsigned v) {
-        v = (v | (v << 8)) & 0x00FF00FFu; v = (v | (v << 4)) & 0x0F0F0F0Fu;
-        v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u;
-        return v;
-    };
-    keys[k] = part(qx) | (part(qy) << 1);
-}
-__global__ void k_light_rank(const unsigned int* __restrict__ keys, int n, unsigned short* __restrict__ rank) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const unsigned mine = keys[k];
-    int r = 0;
-    for (int m = 0; m < n; m++) {
-        const unsigned o = keys[m];
-        r += (o < mine) || (o == mine && m < k);
-    }
-    rank[k] = (unsigned short)r;
-}
-static void ia_light_ranks(ia_ctx* c, int spp, cudaStream_t st) {
-    k_light_keys<<<(spp + 127) / 128, 128, 0, st>>>(c->d_light_dir_s, spp, c->d_light_key);
-    k_light_rank<<<(spp + 127) / 128, 128, 0, st>>>(c->d_light_key, spp, c->d_light_rank);
-}
-
 static int ia_light_outputs(ia_ctx* c, int spp, float* d_dirs_out, float* d_em_out, float* d_pdf_out, cudaStream_t st) {
     if (d_dirs_out) IA_CHECK_CUDA(cudaMemcpyAsync(d_dirs_out, c->d_light_dir_w, (size_t)spp * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (d_em_out) IA_CHECK_CUDA(cudaMemcpyAsync(d_em_out, c->d_light_em, (size_t)spp * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -946,8 +910,7 @@ extern "C" int ia_set_light(ia_ctx* c, const float* d_env, int H, int W, const f
     if (int e = ia_env_tables(c, d_env, H, W, st)) return e;
     k_env_sample<<<(spp + 127) / 128, 128, 0, st>>>(c->f, c->env, d_u1, d_u2, spp, c->d_light_dir_w, c->d_light_dir_s,
                                                     c->d_light_em, c->d_light_pdf);
-    ia_light_ranks(c, spp, st);
-    IA_STAGE_END(c, IA_STAGE_LIGHT, st, 6);
+    IA_STAGE_END(c, IA_STAGE_LIGHT, st, 4);
     IA_LAUNCH_CHECK();
     if (int e = ia_light_outputs(c, spp, d_dirs_out, d_em_out, d_pdf_out, st)) return e;
     c->have_light = true;
@@ -969,8 +932,7 @@ extern "C" int ia_set_light_uniform(ia_ctx* c, const float* d_env, int H, int W,
     if (int e = ia_env_tables(c, d_env, H, W, st)) return e;
     k_env_uniform<<<(spp + 127) / 128, 128, 0, st>>>(c->f, c->env, n_rows, n_cols, c->d_light_dir_w, c->d_light_dir_s,
                                                      c->d_light_em, c->d_light_pdf);
-    ia_light_ranks(c, spp, st);
-    IA_STAGE_END(c, IA_STAGE_LIGHT, st, 6);
+    IA_STAGE_END(c, IA_STAGE_LIGHT, st, 4);
     IA_LAUNCH_CHECK();
     if (int e = ia_light_outputs(c, spp, d_dirs_out, d_em_out, nullptr, st)) return e;
     c->have_light = true;

@@ -631,7 +631,6 @@ static int ia_launch_shade(ia_ctx* c, bool gi, int64_t ray_index_base, uint32_t 
     pol.rs_t = c->d_rs_t; pol.rs_src = c->d_rs_src; pol.rs_w = c->d_rs_w; pol.work = c->d_work; pol.spp = c->spp;
     pol.ray_index_base = ray_index_base; pol.seed = seed; pol.light_dir_s = c->d_light_dir_s;
     pol.light_em = c->d_light_em; pol.light_pdf = c->d_light_pdf; pol.acc6 = c->d_acc; pol.n_total = 0; pol.gi = gi;
-    pol.light_rank = c->d_light_rank;
     pol.env = c->env; pol.vis = MODE == IA_MODE_UNIFORM_LIGHT ? c->d_vis : nullptr; pol.bg_rgb = c->d_bg;
     if (gi) {
         IA_CHECK_CUDA(cudaFuncSetAttribute(k_shade_wf<true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_BYTES(true)));
@@ -915,6 +914,45 @@ extern "C" int ia_op_secondary(ia_ctx* c, const float* d_o, const float* d_d, in
             k_rays_wf<false><<<wf_blocks, WF_THREADS, WF_SMEM_BYTES(false), (cudaStream_t)stream>>>(c->f, pol, c->d_wf_scratch, c->d_counters);
         }
     }
+    IA_LAUNCH_CHECK();
+    return IA_OK;
+}
+
+// op-level twin of the wavefront kernel's geometry phase: canonical SDF of n points on the tensor cores
+// (ia_warp_geometry16: hash grid -> 35 -> 64 layer as 3xTF32 mma -> softplus -> sdf row)
+__global__ void __launch_bounds__(256) k_op_geometry(const __grid_constant__ IaFrame p, const float* __restrict__ xc, long long n,
+                                                     float* __restrict__ sdf) {
+    extern __shared__ __align__(16) float smem[];
+    float* w = smem;
+    float4* w1f = reinterpret_cast<float4*>(smem + IA_GEO_END);
+    float* xs_all = reinterpret_cast<float*>(w1f + IA_GEO_KSTEPS * 8 * 32);
+    __shared__ IaLevel lvl[IA_N_LEVELS];
+    ia_stage(w, p.mlp, IA_GEO_END);
+    ia_stage_bfrag(w1f, IA_GEO_KSTEPS, 8, [&](int k, int nn) { return ia_geo_w1(p.mlp, k, nn); });
+    for (int i = threadIdx.x; i < (int)(blockDim.x >> 5) * 16 * IA_GEO_LD; i += blockDim.x) xs_all[i] = 0.f;
+    if (threadIdx.x < IA_N_LEVELS) lvl[threadIdx.x] = ia_level(p, threadIdx.x);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* xs = xs_all + warp * 16 * IA_GEO_LD;
+    const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long b0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * 16; b0 < n; b0 += n_warps * 16) {
+        const int nb = (int)min((long long)16, n - b0);
+        float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+        if (lane < nb) { x0 = xc[(b0 + lane) * 3]; x1 = xc[(b0 + lane) * 3 + 1]; x2 = xc[(b0 + lane) * 3 + 2]; }
+        const float s = ia_warp_geometry16(p, lvl, w, w1f, xs, x0, x1, x2, nb);
+        if (lane < nb) sdf[b0 + lane] = s;
+    }
+}
+
+extern "C" int ia_op_geometry(ia_ctx* c, const float* d_xc, int64_t n, float* d_sdf, void* stream) {
+    IA_REQUIRE(c && d_xc && d_sdf, IA_EINVAL, "ia_op_geometry: NULL argument");
+    IA_REQUIRE(c->have_fields, IA_ESTATE, "ia_op_geometry: call ia_set_fields first");
+    if (n == 0) return IA_OK;
+    IA_CHECK_CUDA(cudaSetDevice(c->device));
+    const size_t sm = IA_GEO_END * sizeof(float) + IA_GEO_KSTEPS * 8 * 32 * sizeof(float4) + 8 * 16 * IA_GEO_LD * sizeof(float);
+    IA_CHECK_CUDA(cudaFuncSetAttribute(k_op_geometry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 127) / 128, (int64_t)c->n_sm * 2));
+    k_op_geometry<<<blocks, 256, sm, (cudaStream_t)stream>>>(c->f, d_xc, n, d_sdf);
     IA_LAUNCH_CHECK();
     return IA_OK;
 }

@@ -22,7 +22,7 @@ namespace cg = cooperative_groups;
 //      load instruction (scripts/gather_microbench.cu: 18.7 G fetches/s with 3 x LDG.128 per corner -- the rate the Broyden
 //      phase of round 1 ran at -- vs 38.0 with one LDG.256).
 #ifndef IA_VOXEL32
-#define IA_VOXEL32 1
+#define IA_VOXEL32 0
 #endif
 #if IA_VOXEL32
 #define IA_VOXEL_F4 2  // float4 per voxel of voxel_J

@@ -19,6 +19,7 @@
 // Same arithmetic, in the same order, as the reference (models/intrinsic_avatar.py:396-545; cdf.cu:536-638;
 // fuse_cuda_kernel_fast.cu:250-413; filter.cu:10-54); only the accumulation order into a pixel differs.
 #pragma once
+#include "ia_mma.cuh"
 
 #ifndef WF_THREADS
 #define WF_THREADS 512
@@ -61,6 +62,7 @@
 #define WF_OFF_STATE (WF_OFF_GITASK + WF_R * 8)
 #define WF_SCRATCH_BYTES (WF_OFF_STATE + WF_NST * WF_R * 4)
 
+enum { WF_C_Q = 0, WF_C_FETCH, WF_C_GEO, WF_C_RAYS, WF_C_SKIP, WF_C_QG, WF_C_RAD };
 enum { WF_IDLE = 0, WF_FIRST = 1, WF_SEARCH = 2, WF_CDF = 3, WF_FINE = 4, WF_GIWAIT = 5 };
 enum { WF_ACT_NEXT = 0, WF_ACT_CDF = 1, WF_ACT_FINE_START = 2, WF_ACT_FINISH = 3 };
 
@@ -100,10 +102,9 @@ struct WfShared {
     unsigned int qmask[WF_R];
     unsigned short qlist[WF_R];
     uint2 ring[WF_QCAP];
-    // feed: direction-coherent ordering of a tile's live rays (WfShadePolicy, light-table modes)
-    unsigned int sortk[WF_FEED];     // (pixel in tile << 26) | (direction rank of the light << 10) | item in tile; ~0u = no ray
-    unsigned short sortkk[WF_FEED];  // light index of the item
-    int n_live_tile;
+    // tensor-core geometry phase (ia_mma.cuh): pre-split B fragments of the 35 -> 64 layer, one 16-point input tile per warp
+    float4* w1f;            // [IA_GEO_KSTEPS][8][32]
+    float* xs;              // [warps][16][IA_GEO_LD]
     // CTA-private scratch in GLOBAL memory (low traffic; keeping it out of shared memory leaves the
     // L1 carve-out to the voxel_J gathers, which is what the kernel is bound by -- DESIGN.md):
     float* cand;            // [WF_R][13][3] Broyden roots
@@ -118,7 +119,7 @@ struct WfShared {
 #endif
     int n_btask;
     int n_q, task_next, n_gtask, ring_head, ring_tail, tile, more_tiles, pad;
-    unsigned probe;         // WF_PROBE_SAMECELL builds: Broyden trips that stayed in the voxel cell of the previous trip
+    unsigned cnt[8];        // work counters of this CTA (WF_C_*), flushed to the global counters when the kernel ends
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -168,11 +169,19 @@ __device__ __forceinline__ int wf_grab(WfShared& S, int n_tasks) {
     return t < n_tasks ? t : -1;
 }
 
+// A phase counts its work in a register and adds it to the CTA's counters when it ends (the counters do not live in
+// registers across phases: seven of them cost the Broyden loop spills at the 128-register cap).
+__device__ __forceinline__ void wf_count(WfShared& S, int which, unsigned v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&S.cnt[which], v);
+}
+
 // Broyden chains of all pending queries (fuse_cuda_kernel_fast.cu:250-413), one voxel fetch per trip.
 // Dense pre-pass over the 13 x n_q (query, init bone) pairs: chains whose initial point has all 8 corners
 // outside the voxel grid are exactly invalid (ia_all_corners_oob) and are dropped; the others are
 // compacted, bone-major, into the Broyden task list.
-__device__ __forceinline__ void wf_prune_phase(const IaFrame& p, WfShared& S, int n_q, unsigned& c_skip) {
+__device__ __forceinline__ void wf_prune_phase(const IaFrame& p, WfShared& S, int n_q) {
+    unsigned c_skip = 0;
     const int n_pairs = n_q * IA_N_INIT;
     const int lane = threadIdx.x & 31;
     for (int k0 = (threadIdx.x & ~31); k0 < n_pairs; k0 += blockDim.x) {
@@ -197,24 +206,25 @@ __device__ __forceinline__ void wf_prune_phase(const IaFrame& p, WfShared& S, in
         base = __shfl_sync(0xffffffffu, base, 0);
         if (live) S.btask[base + __popc(b & ((1u << lane) - 1u))] = (unsigned short)(q * 16 + c);
     }
+    wf_count(S, WF_C_SKIP, c_skip);
 }
 
-__device__ __forceinline__ void wf_broyden_phase(const IaFrame& p, WfShared& S, unsigned& c_fetch) {
-    const int n_tasks = S.n_btask;
-    int task = wf_grab(S, n_tasks);
-    bool fresh = true;
+__device__ __forceinline__ void wf_broyden_phase(const IaFrame& p, WfShared& S) {
+    // chain state in ONE register (the loop sits at the 128-register cap): task id (q * 16 + c) in bits 0..15, rank-1 update
+    // count in bits 16..19, bit 20 = the next trip is the chain's first; -1 = no task left
+    const int FRESH = 1 << 20;
+    int st;
+    {
+        const int t = wf_grab(S, S.n_btask);
+        st = t >= 0 ? ((int)S.btask[t] | FRESH) : -1;
+    }
     float x0 = 0, x1 = 0, x2 = 0, xd0 = 0, xd1 = 0, xd2 = 0, g0 = 0, g1 = 0, g2 = 0;
     float Ji[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    int it = 0, q = 0, c = 0;
-#ifdef WF_PROBE_SAMECELL
-    int prev_cell = -1;
-    unsigned c_same = 0;
-#endif
-    while (task >= 0) {
+    while (st >= 0) {
         float u0 = 0, u1 = 0, u2 = 0;
+        const bool fresh = st & FRESH;
         if (fresh) {
-            const int tk = S.btask[task];
-            q = tk >> 4; c = tk & 15;
+            const int q = (st & 0xffff) >> 4, c = st & 15;
             xd0 = S.qx[0][q]; xd1 = S.qx[1][q]; xd2 = S.qx[2][q];
             const float* T = S.tfs13 + c * 12;
             float d0 = xd0 - T[3], d1 = xd1 - T[7], d2 = xd2 - T[11];
@@ -232,15 +242,6 @@ __device__ __forceinline__ void wf_broyden_phase(const IaFrame& p, WfShared& S, 
         const float iz = p.scl[2] * (x2 + p.off[2]);
         float J[12];
         ia_fetch_J(p, ix, iy, iz, J);
-        c_fetch++;
-#ifdef WF_PROBE_SAMECELL
-        {
-            const IaCorners cn = ia_corners(p, ix, iy, iz);
-            const int cell = (cn.z0 * 256 + cn.y0) * 256 + cn.x0;
-            if (!fresh && cell == prev_cell) c_same++;
-            prev_cell = cell;
-        }
-#endif
         const float n0 = J[0] * x0 + J[1] * x1 + J[2] * x2 + J[3] - xd0;
         const float n1 = J[4] * x0 + J[5] * x1 + J[6] * x2 + J[7] - xd1;
         const float n2 = J[8] * x0 + J[9] * x1 + J[10] * x2 + J[11] - xd2;
@@ -249,8 +250,7 @@ __device__ __forceinline__ void wf_broyden_phase(const IaFrame& p, WfShared& S, 
             Ji[1] = J[4]; Ji[4] = J[5]; Ji[7] = J[6];
             Ji[2] = J[8]; Ji[5] = J[9]; Ji[8] = J[10];
             g0 = n0; g1 = n1; g2 = n2;
-            it = 0;
-            fresh = false;
+            st &= 0xffff;   // update count 0, not fresh
         } else {
             const float nrm = n0 * n0 + n1 * n1 + n2 * n2;
             bool fin = false, ok = false;
@@ -273,22 +273,24 @@ __device__ __forceinline__ void wf_broyden_phase(const IaFrame& p, WfShared& S, 
                 Ji[3] += c0 * (r1 + u1) / s; Ji[4] += c1 * (r1 + u1) / s; Ji[5] += c2 * (r1 + u1) / s;
                 Ji[6] += c0 * (r2 + u2) / s; Ji[7] += c1 * (r2 + u2) / s; Ji[8] += c2 * (r2 + u2) / s;
                 g0 = n0; g1 = n1; g2 = n2;
-                if (++it >= 10) fin = true;
+                st += 1 << 16;
+                if ((st >> 16) >= 10) fin = true;
             }
             if (fin) {
+                const int q = (st & 0xffff) >> 4, c = st & 15, it = st >> 16;
                 if (ok) {
                     float* cd = S.cand + (q * IA_N_INIT + c) * 3;
                     cd[0] = x0; cd[1] = x1; cd[2] = x2;
                     atomicOr(&S.qmask[q], 1u << c);
                 }
-                task = wf_grab(S, n_tasks);
-                fresh = true;
+                // voxel fetches of this chain: the initial one + one per later trip (`it` counts the rank-1 updates).
+                // Counted here, at the chain's end, so that no counter lives in a register across the loop.
+                atomicAdd(&S.cnt[WF_C_FETCH], 1u + (it >= 10 ? 10u : (unsigned)it + 1u));
+                const int t = wf_grab(S, S.n_btask);
+                st = t >= 0 ? ((int)S.btask[t] | FRESH) : -1;
             }
         }
     }
-#ifdef WF_PROBE_SAMECELL
-    if (c_same) atomicAdd(&S.probe, c_same);
-#endif
 }
 
 // filter.cu:10-54 per pending query, then the list of geometry tasks
@@ -324,41 +326,104 @@ __device__ __forceinline__ void wf_filter_phase(WfShared& S, int n_q) {
     }
 }
 
-__device__ __forceinline__ void wf_geometry_phase(const IaFrame& p, WfShared& S, unsigned& c_geo) {
-    Team team = cg::tiled_partition<IA_TEAM>(cg::this_thread_block());
+// SDF of up to 16 canonical points by one warp on the tensor cores (ia_mma.cuh).  Lane j < n_pts holds point j in
+// (px, py, pz); returns the sdf of point j in lane j < 16.  Tile columns: 0..31 hash features (level l: 2l, 2l + 1),
+// 32..34 the scaled position 2 xn - 1, 35..39 zero (set once at kernel start, never written).
+#define IA_GEO_KSTEPS 5
+#define IA_GEO_LD 44
+__device__ __forceinline__ float ia_geo_w1(const float* __restrict__ mlp, int k, int n) {   // layer-1 weight of tile column k
+    const int in = k < 32 ? 3 + k : (k < 35 ? k - 32 : -1);
+    return in < 0 ? 0.f : mlp[IA_GEO_W1T + in * 64 + n];
+}
+__device__ __forceinline__ float ia_warp_geometry16(const IaFrame& p, const IaLevel* __restrict__ lvl, const float* __restrict__ w,
+                                                    const float4* __restrict__ w1f, float* __restrict__ xs, float px, float py,
+                                                    float pz, int n_pts) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, l = lane & 15, half = lane >> 4;
+    // ---- A: hash-grid features, two points per trip (lane = level), into the warp's input tile
+    for (int i = 0; i < n_pts; i += 2) {
+        const int r = i + half;
+        const float x0 = __shfl_sync(FULL, px, r & 15), x1 = __shfl_sync(FULL, py, r & 15), x2 = __shfl_sync(FULL, pz, r & 15);
+        if (r < n_pts) {
+            float xn[3] = {(x0 - p.center[0]) / p.scale[0] + 0.5f, (x1 - p.center[1]) / p.scale[1] + 0.5f,
+                           (x2 - p.center[2]) / p.scale[2] + 0.5f};
+            float f0, f1;
+            ia_hash_level<false>(p.geo_hash, lvl[l], xn, f0, f1, nullptr);
+            *reinterpret_cast<float2*>(xs + r * IA_GEO_LD + 2 * l) = make_float2(f0, f1);
+            if (l < 3) xs[r * IA_GEO_LD + 32 + l] = xn[l] * 2.0f - 1.0f;
+        }
+    }
+    __syncwarp();
+    // ---- B + C: 35 -> 64 layer (16 x 64 pre-activations in C layout, two halves of 32 hidden units to bound the
+    //      accumulator registers), softplus, row 0 of the 64 -> 13 layer (the sdf)
+    const int t = lane & 3;
+    float lo = 0.f, hi = 0.f;
+#pragma unroll
+    for (int nh = 0; nh < 2; nh++) {
+        float c[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            const float2 b = *reinterpret_cast<const float2*>(w + IA_GEO_B1 + 8 * (4 * nh + nt) + 2 * t);
+            c[nt][0] = b.x; c[nt][1] = b.y; c[nt][2] = b.x; c[nt][3] = b.y;
+        }
+        ia_mma_layer_smem<IA_GEO_KSTEPS, 4, 8>(xs, IA_GEO_LD, w1f + 4 * nh * 32, c);
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            const float2 w2 = *reinterpret_cast<const float2*>(w + IA_GEO_W2 + 8 * (4 * nh + nt) + 2 * t);
+            lo = fmaf(w2.x, ia_softplus100(c[nt][0]), lo); lo = fmaf(w2.y, ia_softplus100(c[nt][1]), lo);
+            hi = fmaf(w2.x, ia_softplus100(c[nt][2]), hi); hi = fmaf(w2.y, ia_softplus100(c[nt][3]), hi);
+        }
+    }
+    __syncwarp();   // the tile may be overwritten by the next batch
+    // reduction over the four lanes of a row
+    lo += __shfl_xor_sync(FULL, lo, 1); hi += __shfl_xor_sync(FULL, hi, 1);
+    lo += __shfl_xor_sync(FULL, lo, 2); hi += __shfl_xor_sync(FULL, hi, 2);
+    // row j < 8 sits in lanes 4j .. 4j + 3 (lo), row j >= 8 in lanes 4 (j - 8) .. (hi)
+    const float slo = __shfl_sync(FULL, lo, 4 * (lane & 7)), shi = __shfl_sync(FULL, hi, 4 * (lane & 7));
+    return ((lane & 8) ? shi : slo) + w[IA_GEO_B2];
+}
+
+__device__ __forceinline__ void wf_geometry_phase(const IaFrame& p, WfShared& S) {
+    unsigned c_geo = 0;
     const int n = S.n_gtask;
-    const int n_teams = blockDim.x / IA_TEAM;
-    // software pipeline: the task id and root of the NEXT task are fetched (two dependent L2 round trips: the lists
-    // were just written by other warps) while the current one is evaluated
-    int k = threadIdx.x / IA_TEAM;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    // an even split of the task list over the warps (the gathers of step A are the cost, and they are per point)
+    const int per = (n + n_warps - 1) / n_warps;
+    const int end = min(n, (warp + 1) * per);
+    float* xs = S.xs + warp * 16 * IA_GEO_LD;
+    // software pipeline: the task ids and roots of the NEXT batch (two dependent L2 round trips: the lists were just
+    // written by other warps) are fetched while the current one is evaluated
+    int b0 = warp * per;
     int ci = 0;
     float x0 = 0.f, x1 = 0.f, x2 = 0.f;
-    if (k < n) {
-        const int tk = S.gtask[k];
+    if (b0 + lane < end && lane < 16) {
+        const int tk = S.gtask[b0 + lane];
         ci = (tk >> 4) * IA_N_INIT + (tk & 15);
         const float* cd = S.cand + ci * 3;
         x0 = cd[0]; x1 = cd[1]; x2 = cd[2];
     }
-    while (k < n) {
-        const int kn = k + n_teams;
+    while (b0 < end) {
+        const int nb = min(16, end - b0);
+        const int bn = b0 + 16;
         int ci_n = 0;
         float y0 = 0.f, y1 = 0.f, y2 = 0.f;
-        if (kn < n) {
-            const int tk = S.gtask[kn];
+        if (bn + lane < end && lane < 16) {
+            const int tk = S.gtask[bn + lane];
             ci_n = (tk >> 4) * IA_N_INIT + (tk & 15);
             const float* cd = S.cand + ci_n * 3;
             y0 = cd[0]; y1 = cd[1]; y2 = cd[2];
         }
-        const float xc[3] = {x0, x1, x2};
-        float s = ia_team_geometry<false>(team, p, S.w, xc, nullptr, nullptr, S.lvl);
-        if (team.thread_rank() == 0) { S.csdf[ci] = s; c_geo++; }
-        k = kn; ci = ci_n; x0 = y0; x1 = y1; x2 = y2;
+        const float s = ia_warp_geometry16(p, S.lvl, S.w, S.w1f, xs, x0, x1, x2, nb);
+        if (lane < nb) { S.csdf[ci] = s; c_geo++; }
+        b0 = bn; ci = ci_n; x0 = y0; x1 = y1; x2 = y2;
     }
+    wf_count(S, WF_C_GEO, c_geo);
 }
 
 // GI: radiance at the arg-min root of every fine sample consumed this round (rgb_alpha_fn,
 // models/intrinsic_avatar.py:430-456): geometry with gradient + feature, blended forward rotation, radiance MLP.
-__device__ __forceinline__ void wf_gi_phase(const IaFrame& p, WfShared& S, unsigned& c_qg, unsigned& c_geo, unsigned& c_rad) {
+__device__ __forceinline__ void wf_gi_phase(const IaFrame& p, WfShared& S) {
+    unsigned c_qg = 0;
     Team team = cg::tiled_partition<IA_TEAM>(cg::this_thread_block());
     const int n = S.n_gitask;
     const int n_teams = blockDim.x / IA_TEAM;
@@ -381,9 +446,10 @@ __device__ __forceinline__ void wf_gi_phase(const IaFrame& p, WfShared& S, unsig
         if (team.thread_rank() == 0) {
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) S.st[WS_IND + ch][t] += w * rgb[ch];
-            c_qg++; c_geo++; c_rad++;
+            c_qg++;
         }
     }
+    wf_count(S, WF_C_QG, c_qg);   // = geometry evaluations with gradient = radiance evaluations = skinning fetches of this phase
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -602,6 +668,8 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
     if (tid == 0) {
         unsigned char* mine = scratch + (size_t)blockIdx.x * WF_SCRATCH_BYTES;
         S.w = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&S) + ((sizeof(WfShared) + 15) & ~15));
+        S.w1f = reinterpret_cast<float4*>(S.w + n_w);
+        S.xs = reinterpret_cast<float*>(S.w1f + IA_GEO_KSTEPS * 8 * 32);
         S.cand = reinterpret_cast<float*>(mine);
         S.csdf = reinterpret_cast<float*>(mine + WF_OFF_CSDF);
         S.gtask = reinterpret_cast<unsigned short*>(mine + WF_OFF_GTASK);
@@ -616,14 +684,16 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
     __syncthreads();
     for (int i = tid * 4; i < n_w; i += blockDim.x * 4)
         *reinterpret_cast<float4*>(S.w + i) = __ldg(reinterpret_cast<const float4*>(p.mlp + i));
+    ia_stage_bfrag(S.w1f, IA_GEO_KSTEPS, 8, [&](int k, int n) { return ia_geo_w1(p.mlp, k, n); });
+    for (int i = tid; i < (int)(blockDim.x >> 5) * 16 * IA_GEO_LD; i += blockDim.x) S.xs[i] = 0.f;
     if (tid < IA_N_INIT * 12) S.tfs13[tid] = p.tfs[p.init_bones[tid / 12]][tid % 12];
     if (tid < IA_N_LEVELS) S.lvl[tid] = ia_level(p, tid);
     for (int t = tid; t < WF_R; t += blockDim.x) S.st[WS_PACK][t] = __uint_as_float(0u);
-    if (tid == 0) { S.ring_head = 0; S.ring_tail = 0; S.more_tiles = 1; S.n_q = 0; S.n_gtask = 0; S.task_next = 0; S.probe = 0; }
+    if (tid == 0) { S.ring_head = 0; S.ring_tail = 0; S.more_tiles = 1; S.n_q = 0; S.n_gtask = 0; S.task_next = 0; }
+    if (tid < 8) S.cnt[tid] = 0;
     __syncthreads();
     const int tile_items = pol.tile_items();
     const long long n_tiles = (pol.n_items() + tile_items - 1) / tile_items;
-    unsigned c_q = 0, c_fetch = 0, c_geo = 0, c_rays = 0, c_skip = 0, c_qg = 0, c_rad = 0;
     while (true) {
         // ---- feed the ring while it cannot fill every slot
         while (true) {
@@ -645,11 +715,16 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
         if (tid == 0) { S.n_q = 0; S.n_gtask = 0; S.task_next = 0; S.n_btask = 0; S.n_gitask = 0; }
         const int ring_tail = S.ring_tail;
         __syncthreads();
-        for (int t = tid; t < WF_R; t += blockDim.x) wf_advance_slot<GI>(p, pol, S, t, ring_tail, c_q, c_rays);
+        {
+            unsigned c_q = 0, c_rays = 0;
+            for (int t = tid; t < WF_R; t += blockDim.x) wf_advance_slot<GI>(p, pol, S, t, ring_tail, c_q, c_rays);
+            wf_count(S, WF_C_Q, c_q);
+            wf_count(S, WF_C_RAYS, c_rays);
+        }
         __syncthreads();
         if (GI) {
             const int n_gi = S.n_gitask;
-            if (n_gi) wf_gi_phase(p, S, c_qg, c_geo, c_rad);
+            if (n_gi) wf_gi_phase(p, S);
             __syncthreads();
             const int n_q0 = S.n_q;
             if (n_q0 == 0) {
@@ -663,37 +738,29 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
             if (S.ring_tail - S.ring_head <= 0 && !S.more_tiles) break;
             continue;
         }
-        wf_prune_phase(p, S, n_q, c_skip);
+        wf_prune_phase(p, S, n_q);
         __syncthreads();
-        wf_broyden_phase(p, S, c_fetch);
+        wf_broyden_phase(p, S);
         __syncthreads();
         wf_filter_phase(S, n_q);
         __syncthreads();
-        wf_geometry_phase(p, S, c_geo);
+        wf_geometry_phase(p, S);
         __syncthreads();
     }
-    // counters: warp-reduce then one atomic per warp
-    for (int o = 16; o > 0; o >>= 1) {
-        c_q += __shfl_xor_sync(0xffffffffu, c_q, o);
-        c_fetch += __shfl_xor_sync(0xffffffffu, c_fetch, o);
-        c_geo += __shfl_xor_sync(0xffffffffu, c_geo, o);
-        c_rays += __shfl_xor_sync(0xffffffffu, c_rays, o);
-        c_skip += __shfl_xor_sync(0xffffffffu, c_skip, o);
-        c_qg += __shfl_xor_sync(0xffffffffu, c_qg, o);
-        c_rad += __shfl_xor_sync(0xffffffffu, c_rad, o);
-    }
-#ifdef WF_PROBE_SAMECELL
     __syncthreads();
-    if (tid == 0 && S.probe) atomicAdd(&counters[IA_CNT_OVERFLOW], (unsigned long long)S.probe);
-#endif
-    if ((tid & 31) == 0) {
-        if (c_q) atomicAdd(&counters[IA_CNT_QUERIES], c_q);
-        if (c_fetch) atomicAdd(&counters[IA_CNT_BROYDEN_FETCH], c_fetch);
-        if (c_geo) atomicAdd(&counters[IA_CNT_GEO_EVAL], c_geo);
-        if (c_rays) atomicAdd(&counters[IA_CNT_SECONDARY_RAYS], c_rays);
-        if (c_skip) atomicAdd(&counters[IA_CNT_CHAINS_SKIPPED], c_skip);
-        if (c_qg) { atomicAdd(&counters[IA_CNT_QUERIES_GRAD], c_qg); atomicAdd(&counters[IA_CNT_SKIN_FETCH], c_qg); }
-        if (c_rad) atomicAdd(&counters[IA_CNT_RAD_EVAL], c_rad);
+    if (tid == 0) {
+        const unsigned long long q = S.cnt[WF_C_Q], f = S.cnt[WF_C_FETCH], g = S.cnt[WF_C_GEO], r = S.cnt[WF_C_RAYS],
+                                 k = S.cnt[WF_C_SKIP], qg = S.cnt[WF_C_QG];
+        if (q) atomicAdd(&counters[IA_CNT_QUERIES], q);
+        if (f) atomicAdd(&counters[IA_CNT_BROYDEN_FETCH], f);
+        if (g + qg) atomicAdd(&counters[IA_CNT_GEO_EVAL], g + qg);
+        if (r) atomicAdd(&counters[IA_CNT_SECONDARY_RAYS], r);
+        if (k) atomicAdd(&counters[IA_CNT_CHAINS_SKIPPED], k);
+        if (qg) {
+            atomicAdd(&counters[IA_CNT_QUERIES_GRAD], qg);
+            atomicAdd(&counters[IA_CNT_SKIN_FETCH], qg);
+            atomicAdd(&counters[IA_CNT_RAD_EVAL], qg);
+        }
     }
 }
 
@@ -722,7 +789,6 @@ struct WfShadePolicy {
     const float* rs_t; const int* rs_src; const float* rs_w;
     int* work; int spp; long long ray_index_base; uint32_t seed;
     const float* light_dir_s; const float* light_em; const float* light_pdf;
-    const unsigned short* light_rank;  // [spp] position of each light direction along a Morton curve over (lon, lat)
     float* acc6;
     long long n_total;
     int gi;
@@ -769,51 +835,6 @@ struct WfShadePolicy {
 
     __device__ __forceinline__ void feed(long long s0, WfShared& S) {
         const int n_it = tile_items();
-        if (WF_FEED == 1024 && mode <= IA_MODE_UNIFORM_LIGHT && spp >= 64 && light_rank) {  // (key layout: 5 + 16 + 10 bits)
-            // Light-table modes: the rays of a pixel enter the ring ordered by the DIRECTION of their light (Morton rank
-            // over lon/lat) instead of by sample index, whose light is a random pick: neighbouring ray slots then walk
-            // through the same voxels and hash cells (secondary stage 7 % faster on the same rays, scripts/coherence_test.py).
-            // Only the order of processing changes: every ray, its sample and its light are what they were.
-            if (threadIdx.x == 0) S.n_live_tile = 0;
-            __syncthreads();
-            const int slot0 = (int)((unsigned)s0 / (unsigned)spp);
-            for (int i = threadIdx.x; i < WF_FEED; i += blockDim.x) {
-                uint2 e;
-                const bool live = i < n_it && classify(s0 + i, e);
-                unsigned key = 0xFFFFFFFFu;
-                if (live) {
-                    const unsigned pix = e.x / (unsigned)spp - (unsigned)slot0;   // <= WF_FEED / 64 pixels per tile
-                    key = (pix << 26) | ((unsigned)light_rank[e.y] << 10) | (unsigned)i;
-                    S.sortkk[i] = (unsigned short)e.y;
-                }
-                S.sortk[i] = key;
-                const unsigned b = __ballot_sync(0xffffffffu, live);
-                if ((threadIdx.x & 31) == 0 && b) atomicAdd(&S.n_live_tile, __popc(b));
-            }
-            // bitonic sort of the WF_FEED keys (dead entries sort to the end)
-            for (int k = 2; k <= WF_FEED; k <<= 1) {
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    __syncthreads();
-                    for (int t = threadIdx.x; t < WF_FEED / 2; t += blockDim.x) {
-                        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                        const int hi = lo | j;
-                        const unsigned a = S.sortk[lo], b = S.sortk[hi];
-                        const bool up = (lo & k) == 0;
-                        if ((a > b) == up) { S.sortk[lo] = b; S.sortk[hi] = a; }
-                    }
-                }
-            }
-            __syncthreads();
-            const int n_live = S.n_live_tile;
-            const int base = S.ring_tail;
-            for (int pos = threadIdx.x; pos < n_live; pos += blockDim.x) {
-                const unsigned i = S.sortk[pos] & (unsigned)(WF_FEED - 1);
-                S.ring[(base + pos) & (WF_QCAP - 1)] = make_uint2((unsigned)(s0 + i), (unsigned)S.sortkk[i]);
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) S.ring_tail = base + n_live;
-            return;
-        }
         for (int i = threadIdx.x; i < n_it; i += blockDim.x) {
             uint2 e;
             const bool live = classify(s0 + i, e);
@@ -919,7 +940,8 @@ struct WfShadePolicy {
     }
 };
 
-#define WF_SMEM_BYTES(GI) (((sizeof(WfShared) + 15) & ~(size_t)15) + (((GI) && WF_GI_WEIGHTS_SMEM) ? IA_RAD_END : IA_GEO_END) * sizeof(float))
+#define WF_SMEM_BYTES(GI) (((sizeof(WfShared) + 15) & ~(size_t)15) + (((GI) && WF_GI_WEIGHTS_SMEM) ? IA_RAD_END : IA_GEO_END) * sizeof(float) + \
+                           IA_GEO_KSTEPS * 8 * 32 * sizeof(float4) + (WF_THREADS / 32) * 16 * IA_GEO_LD * sizeof(float))
 
 template <bool GI, int MODE>
 __global__ void __launch_bounds__(WF_THREADS, WF_CTAS_PER_SM) k_shade_wf(const __grid_constant__ IaFrame p, WfShadePolicy<MODE> pol,

@@ -32,6 +32,7 @@ _ARGTYPES = {
     "ia_op_broyden": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "ia_op_query": [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ia_op_shade_fields": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "ia_op_geometry": [_vp, _vp, _i64, _vp, _vp],
     "ia_op_traverse": [_vp, _vp, _vp, _i64, _f32, _f32, _f32] + [_vp] * 9 + [_vp],
     "ia_op_ray_resampling": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp] + [_vp] * 6 + [_vp],
     "ia_op_ray_resampling_merge": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp] + [_vp] * 6 + [_vp],
@@ -313,6 +314,13 @@ class RenderEngine:
         check(self.lib.ia_op_shade_fields(self.h, *[ptr(t) for t in a], n, ptr(rgb), ptr(mat), _stream()),
               "ia_op_shade_fields")
         return rgb, mat
+
+    def op_geometry(self, xc):
+        """Canonical SDF of points [n,3] on the tensor-core path of the wavefront integrator's geometry phase."""
+        xc = xc.to(self.dev, torch.float32).contiguous()
+        sdf = torch.empty(xc.shape[0], device=self.dev)
+        check(self.lib.ia_op_geometry(self.h, ptr(xc), xc.shape[0], ptr(sdf), _stream()), "ia_op_geometry")
+        return sdf
 
     def op_traverse(self, rays_o, rays_d, near, far, step):
         o = rays_o.to(self.dev, torch.float32).contiguous()

@@ -4,7 +4,7 @@ pose stream, environment map, explicit random tables.  Host-side, numpy.
   * camera: K = [[1000,0,256],[0,1000,256],[0,0,1]] at 512x512 (AnimationDataset's f=2000 at
     downscale 2, reference datasets/animation.py:72-87), c2w = I, rays as ``make_rays``
     (datasets/animation.py:19-27); near/far = |transl| -/+ 1 (:185-189).
-  * pose: frames of ``load/animation/aist/poses.npz`` (first 8 frames shipped in data/), transl
+  * pose: frames of ``load/animation/aist/poses.npz`` (first 32 frames shipped in data/), transl
     re-based to (0, 0.15, 5) (datasets/animation.py:127-131); ``neutral`` = zero pose.
   * light: ``data/city_1024x2048_f16.npz`` = the reference's hdri_images/city.hdr as AnimationDataset hands it
     to the model (cv2.imread ANYDEPTH|COLOR -> RGB -> cv2.resize(2048, 1024, INTER_AREA), datasets/animation.py:196-204),
@@ -37,11 +37,14 @@ def make_rays(H: int, W: int, transl) -> np.ndarray:
     return np.concatenate([o, d, near, far], axis=1).astype(np.float32)
 
 
+N_FRAMES = 32   # frames of the AIST sequence shipped in data/
+
+
 def load_pose(frame: int | None):
     """-> body_pose[69], global_orient[3], transl[3].  frame=None: neutral (zero) pose."""
     if frame is None:
         return np.zeros(69, np.float32), np.zeros(3, np.float32), np.array([0, 0.15, 5], np.float32)
-    z = np.load(os.path.join(_DATA, "aist_poses_0_8.npz"))
+    z = np.load(os.path.join(_DATA, "aist_poses_0_32.npz"))
     poses, trans = z["poses"], z["trans"]
     t = trans[frame] - trans[0] + np.array([0, 0.15, 5], np.float32)
     return poses[frame, 3:].astype(np.float32), poses[frame, :3].astype(np.float32), t.astype(np.float32)

@@ -8,6 +8,9 @@
 //   format 3: 24-B voxel (12 x fp16), LDG.128 + LDG.64 per corner (8-B aligned: 3 x LDG.64)
 //   format 4: 16-B voxel, 1 x LDG.128 per corner           (lower bound of one request per corner)
 //   format 5: 64-B voxel, 2 x LDG.256 per corner
+//   format 6: 48-B voxel, 3 x tex1Dfetch<float4> per corner (texture path: bit-exact point fetch from linear memory)
+//   format 7: 48-B voxel, 2 x LDG.128 + 1 x tex1Dfetch per corner (do the LSU and TEX address stages run in parallel?)
+//   format 8: 48-B voxel, 3 x plain ld.global (not .nc) per corner
 // `spread`: the lanes of a warp pick cells within a cube of that side around a per-warp base cell (1 = all lanes the same
 // cell, 128 = independent random cells); `smem_kb` of dynamic shared memory shrink the L1 like the kernel's own use does.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gather_microbench scripts/gather_microbench.cu
@@ -25,6 +28,11 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
     return x;
 }
+__device__ __forceinline__ float4 ld_plain(const float4* ptr) {   // ld.global (coherent path), not hoistable past stores
+    float4 v;
+    asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr));
+    return v;
+}
 __device__ __forceinline__ void ld256(const void* ptr, float r[8]) {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
@@ -32,7 +40,8 @@ __device__ __forceinline__ void ld256(const void* ptr, float r[8]) {
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(512, 1) k_gather(const unsigned char* __restrict__ tab, int iters, int spread, float* out) {
+__global__ void __launch_bounds__(512, 1) k_gather(const unsigned char* __restrict__ tab, int iters, int spread, float* out,
+                                                   cudaTextureObject_t tex) {
     extern __shared__ float pad[];
     const int lane = threadIdx.x & 31;
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -79,6 +88,16 @@ __global__ void __launch_bounds__(512, 1) k_gather(const unsigned char* __restri
                     float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[k]));
                     acc[2 * k] = fmaf(f.x, w, acc[2 * k]); acc[2 * k + 1] = fmaf(f.y, w, acc[2 * k + 1]);
                 }
+            } else if (FMT == 6 || FMT == 7 || FMT == 8) {
+                const float4* p = reinterpret_cast<const float4*>(tab + v * 48);
+                float4 a, b, cc;
+                if (FMT == 6) { a = tex1Dfetch<float4>(tex, (int)(v * 3)); b = tex1Dfetch<float4>(tex, (int)(v * 3 + 1)); }
+                else if (FMT == 7) { a = __ldg(p); b = __ldg(p + 1); }
+                else { a = ld_plain(p); b = ld_plain(p + 1); }
+                if (FMT == 8) cc = ld_plain(p + 2); else cc = tex1Dfetch<float4>(tex, (int)(v * 3 + 2));
+                acc[0] = fmaf(a.x, w, acc[0]); acc[1] = fmaf(a.y, w, acc[1]); acc[2] = fmaf(a.z, w, acc[2]); acc[3] = fmaf(a.w, w, acc[3]);
+                acc[4] = fmaf(b.x, w, acc[4]); acc[5] = fmaf(b.y, w, acc[5]); acc[6] = fmaf(b.z, w, acc[6]); acc[7] = fmaf(b.w, w, acc[7]);
+                acc[8] = fmaf(cc.x, w, acc[8]); acc[9] = fmaf(cc.y, w, acc[9]); acc[10] = fmaf(cc.z, w, acc[10]); acc[11] = fmaf(cc.w, w, acc[11]);
             } else if (FMT == 4) {
                 float4 a = __ldg(reinterpret_cast<const float4*>(tab + v * 16));
                 acc[0] = fmaf(a.x, w, acc[0]); acc[1] = fmaf(a.y, w, acc[1]); acc[2] = fmaf(a.z, w, acc[2]); acc[3] = fmaf(a.w, w, acc[3]);
@@ -101,14 +120,14 @@ __global__ void __launch_bounds__(512, 1) k_gather(const unsigned char* __restri
 }
 
 template <int FMT>
-static void run(const unsigned char* tab, int smem_kb, int spread, float* out) {
+static void run(const unsigned char* tab, int smem_kb, int spread, float* out, cudaTextureObject_t tex) {
     const int iters = 2000;
     cudaFuncSetAttribute(k_gather<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kb * 1024);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    k_gather<FMT><<<148, 512, smem_kb * 1024>>>(tab, 200, spread, out);
+    k_gather<FMT><<<148, 512, smem_kb * 1024>>>(tab, 200, spread, out, tex);
     cudaEventRecord(e0);
-    k_gather<FMT><<<148, 512, smem_kb * 1024>>>(tab, iters, spread, out);
+    k_gather<FMT><<<148, 512, smem_kb * 1024>>>(tab, iters, spread, out, tex);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms = 0;
@@ -125,16 +144,26 @@ int main() {
     cudaMemset(tab, 0, nvox * 64);
     float* out;
     cudaMalloc(&out, 4);
-    const int smems[2] = {48, 90};
-    const int spreads[5] = {1, 2, 4, 8, 128};
-    for (int si = 0; si < 2; si++)
-        for (int sp = 0; sp < 5; sp++) {
-            run<0>(tab, smems[si], spreads[sp], out);
-            run<1>(tab, smems[si], spreads[sp], out);
-            run<2>(tab, smems[si], spreads[sp], out);
-            run<3>(tab, smems[si], spreads[sp], out);
-            run<4>(tab, smems[si], spreads[sp], out);
-            run<5>(tab, smems[si], spreads[sp], out);
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypeLinear;
+    rd.res.linear.devPtr = tab;
+    rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+    rd.res.linear.sizeInBytes = nvox * 48;
+    cudaTextureDesc td = {};
+    td.readMode = cudaReadModeElementType;
+    cudaTextureObject_t tex = 0;
+    cudaError_t te = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
+    printf("texture object: %s\n", cudaGetErrorString(te));
+    const int smems[1] = {48};
+    const int spreads[4] = {2, 4, 8, 128};
+    for (int si = 0; si < 1; si++)
+        for (int sp = 0; sp < 4; sp++) {
+            run<0>(tab, smems[si], spreads[sp], out, tex);
+            run<1>(tab, smems[si], spreads[sp], out, tex);
+            run<4>(tab, smems[si], spreads[sp], out, tex);
+            run<6>(tab, smems[si], spreads[sp], out, tex);
+            run<7>(tab, smems[si], spreads[sp], out, tex);
+            run<8>(tab, smems[si], spreads[sp], out, tex);
         }
     return 0;
 }

@@ -2,8 +2,8 @@
 # run bench.py against several builds of the library (tuning variants under build/): prints stage times
 ARGS=${ARGS:---res 256 --spp 256 --steps 3 --warmup 1 --no-e2e --no-cpu-baseline}
 for lib in "$@"; do
-  IA_B200_LIB=$PWD/$lib timeout -s KILL 300 python bench.py $ARGS 2>&1 | tail -1 | python -c "
+  IA_B200_LIB=$PWD/$lib timeout -s KILL 300 python bench.py $ARGS 2>/dev/null | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); s=d['stages_ms']
-print('$lib', 'value=%.3e'%d['value'], 'ms/step=%.1f'%d['ms_per_step'], 'shade=%.1f primary=%.1f occ=%.2f'%(s['shade'],s['primary'],s['occupancy']))"
+print('$lib', 'value=%.3e'%d['value'], 'ms/step=%.1f'%d['ms_per_step'], 'shade=%.1f primary=%.1f occ=%.2f resample=%.2f setup=%.2f'%(s['shade'],s['primary'],s['occupancy'],s['resample'],s['setup']))"
 done

@@ -25,13 +25,13 @@ def test_header_symbols_exported():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/ia_b200.h but not exported"
     assert sorted(capi.EXPORTS) == names, "capi.EXPORTS out of sync with the header"
-    assert lib.ia_version() == 100
+    assert lib.ia_version() == 200 and lib.ia_voxel_format() in (0, 1)
 
 
 def test_argtypes_cover_every_entry_point():
     from intrinsicavatar_b200 import engine
     for n in _declared():
-        if n in ("ia_last_error", "ia_version"):
+        if n in ("ia_last_error", "ia_version", "ia_voxel_format"):
             continue
         assert n in engine._ARGTYPES, n
 

@@ -72,6 +72,24 @@ def test_query_sdf(eng, posed):
     assert (got["sdf"].cpu()[~gv] == 1e5).all()
 
 
+def test_geometry_tensor_core_path(eng, scene):
+    """The geometry phase of the wavefront integrator evaluates the 35 -> 64 layer with warp-level mma (3xTF32,
+    csrc/ia_mma.cuh): canonical SDF against the oracle's fp32 VolumeSDF (models/rf/geometry.py:124-146), at points inside
+    the canonical bbox, ragged point counts (partial 16-point batches, a single point, none)."""
+    g = torch.Generator().manual_seed(11)
+    bb = torch.as_tensor(scene.snarf.bbox, dtype=torch.float32).reshape(2, 3)
+    for n in (20000, 17, 1, 0):
+        xc = bb[0] + torch.rand(n, 3, generator=g) * (bb[1] - bb[0])
+        got = eng.op_geometry(xc).cpu()
+        assert got.shape == (n,)
+        if n == 0:
+            continue
+        ref = scene.fields.geometry(xc)[0].reshape(-1)
+        d = (got - ref).abs()
+        # fp32 summation-order noise: |sdf| ~ 0.1-1, 3xTF32 keeps ~22 bits per product
+        assert d.max() < 2e-6 and d.mean() < 3e-7, (n, d.max().item(), d.mean().item())
+
+
 def test_query_grad_feature(eng, posed):
     R = posed["oracle"]
     xd = _points(posed, 6000, seed=2)
@@ -419,7 +437,7 @@ def test_animation_frames_producer(scene):
     """frames.AnimationFrames feeds IntrinsicAvatarModel like the reference's dataset + preprocess_data."""
     from intrinsicavatar_b200.frames import AnimationFrames, images_to_uint8
     from intrinsicavatar_b200.model import IntrinsicAvatarModel
-    z = np.load(scene.syn._DATA + "/aist_poses_0_8.npz")
+    z = np.load(scene.syn._DATA + "/aist_poses_0_32.npz")
     H = W = 48
     f = 1000.0 * W / 512.0
     K = np.array([[f, 0, W / 2.0], [0, f, H / 2.0], [0, 0, 1]])

@@ -49,6 +49,18 @@ def _worker(rank, world, port, q):
                 ok = ok and all(float(bufs[r][0, 0]) == r * 100 + 3 + 1000.0 * (step + 1) for r in range(world))
             else:
                 ok = ok and bufs is None
+        # FrameCollector, gather transport (the p2p transport needs CUDA IPC: covered on the GPU box by bench.py --gpus 2)
+        col = parallel.FrameCollector(n_pix, slots=2, device="cpu", transport="nccl", dst=0)
+        for step in range(3):
+            col.collect(step, block + 10.0 * step)
+        col.finish()
+        if rank == 0:
+            for step in (1, 2):        # slot of step 0 was reused by step 2
+                fr = col.frames(step)
+                ok = ok and fr.shape == (world, n_pix, 16)
+                ok = ok and all(float(fr[r, 0, 0]) == r * 100 + 3 + 10.0 * step for r in range(world))
+        else:
+            ok = ok and col.frames(1) is None
         t = torch.tensor([float(len(mine))])
         dist.all_reduce(t)
         q.put((rank, mine, bool(ok), float(t)))
@@ -78,3 +90,17 @@ def test_single_process_gather_is_identity():
     assert bufs[0] is b and work is None
     un = parallel.unpack_frame(b)
     assert torch.equal(parallel.pack_frame(un), b)
+
+
+def test_frame_of_step_covers_every_frame_once_per_pass_and_rotates():
+    for world, n_frames in ((1, 16), (2, 16), (8, 16), (4, 32)):
+        steps = n_frames // world
+        seen = sorted(parallel.frame_of_step(s, r, world, n_frames) for s in range(steps) for r in range(world))
+        assert seen == list(range(n_frames))                      # one pass = every frame exactly once
+        # inside a step the ranks render distinct frames
+        for s in range(steps):
+            assert len({parallel.frame_of_step(s, r, world, n_frames) for r in range(world)}) == world
+        if world > 1:
+            # over world passes' worth of steps a rank sees every residue class
+            res = {parallel.frame_of_step(s, 0, world, n_frames) % world for s in range(world)}
+            assert res == set(range(world))
