@@ -264,9 +264,6 @@ __device__ __forceinline__ IaLevel ia_level(const IaFrame& p, int l) {
 #ifndef IA_FETCH_BRANCHLESS
 #define IA_FETCH_BRANCHLESS 0
 #endif
-#ifndef IA_HASH_PAIR
-#define IA_HASH_PAIR 0   // 1: x-neighbour table entries that form an aligned 16-byte pair are read with one LDG.128
-#endif
 __device__ __forceinline__ float2 ia_ldg_na(const float2* ptr) {
     float2 v;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(ptr));
@@ -292,26 +289,6 @@ __device__ __forceinline__ void ia_hash_level(const float2* __restrict__ table, 
         w[d] = v - fl;
     }
     float2 v[8];
-#if IA_HASH_PAIR
-    // The two x-neighbours of a corner pair are table entries e and o.  Whenever they differ only in bit 0 -- hashed
-    // levels: always when the lower x is even (the x coordinate enters the hash unmultiplied); dense levels: when e is
-    // even -- they are the two halves of ONE aligned 16-byte pair, read with one LDG.128 instead of two LDG.64 (same
-    // sector, one request less); otherwise the second entry is read on its own.
-#pragma unroll
-    for (int c = 0; c < 8; c += 2) {
-        const uint32_t cy = g[1] + ((c >> 1) & 1), cz = g[2] + (c >> 2);
-        uint32_t e, o;
-        if (dense) { e = g[0] + cy * res + cz * res * res; o = e + 1u; }
-        else { const uint32_t r = (cy * 2654435761u) ^ (cz * 805459861u); e = g[0] ^ r; o = (g[0] + 1u) ^ r; }
-        if (pow2) { e &= size - 1u; o &= size - 1u; }
-        else { if (e >= size) e %= size; if (o >= size) o %= size; }
-        const float4 pr = __ldg(reinterpret_cast<const float4*>(tab + (e & ~1u)));
-        const bool hi = e & 1u;
-        v[c] = hi ? make_float2(pr.z, pr.w) : make_float2(pr.x, pr.y);
-        v[c + 1] = hi ? make_float2(pr.x, pr.y) : make_float2(pr.z, pr.w);
-        if ((e ^ o) != 1u) v[c + 1] = __ldg(tab + o);
-    }
-#else
 #pragma unroll
     for (int c = 0; c < 8; c++) {
         uint32_t cx = g[0] + (c & 1), cy = g[1] + ((c >> 1) & 1), cz = g[2] + (c >> 2);
@@ -328,7 +305,6 @@ __device__ __forceinline__ void ia_hash_level(const float2* __restrict__ table, 
         v[c] = ia_ldg_na(tab + idx);
 #endif
     }
-#endif
     f0 = 0.f; f1 = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; c++) {

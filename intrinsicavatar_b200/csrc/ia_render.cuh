@@ -559,7 +559,7 @@ __device__ __forceinline__ float ia_srgb(float f) {
 }
 
 __global__ void k_composite(const __grid_constant__ IaFrame p, long long n, const float* __restrict__ acc6, ia_outputs out,
-                            int primary_only, const float* __restrict__ vis) {
+                            int primary_only, const float* __restrict__ vis, const float* __restrict__ bg_rgb) {
     long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     if (out.visibility) out.visibility[r] = vis ? vis[r] : 0.f;  // uniform_light only (models/intrinsic_avatar.py:1427-1432)
@@ -567,8 +567,9 @@ __global__ void k_composite(const __grid_constant__ IaFrame p, long long n, cons
     float bgm = (p.background[0] + p.background[1] + p.background[2]) / 3.0f;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        float phys = primary_only ? p.background[k] : acc6[r * 6 + k];  // (primary-only: acc6 may hold a hit ray's zero)
-        float dem = primary_only ? p.background[k] : acc6[r * 6 + 3 + k];
+        // primary-only: the background colour, or with add_emitter the envmap along the ray (acc6 may hold a hit ray's zero)
+        float phys = primary_only ? bg_rgb[r * 3 + k] : acc6[r * 6 + k];
+        float dem = primary_only ? bg_rgb[r * 3 + k] : acc6[r * 6 + 3 + k];
         if (out.comp_rgb_phys) out.comp_rgb_phys[r * 3 + k] = phys;
         if (out.comp_demod_phys) out.comp_demod_phys[r * 3 + k] = dem;
         if (out.comp_rgb_phys_full) out.comp_rgb_phys_full[r * 3 + k] = ia_srgb(phys);
@@ -650,7 +651,9 @@ extern "C" int ia_render(ia_ctx* c, const float* d_rays, int64_t n_rays, int64_t
     const bool primary_only = flags & IA_RENDER_PRIMARY_ONLY;
     const bool gi = flags & IA_RENDER_GI;
     const int mode = (flags & IA_RENDER_MODE_MASK) >> IA_RENDER_MODE_SHIFT;
-    const bool add_emitter = (flags & IA_RENDER_ADD_EMITTER) && !primary_only;
+    // add_emitter also applies to a primary-only (albedo_only) render: comp_rgb_phys is then the envmap along every ray
+    // (models/intrinsic_avatar.py:1468-1478); it needs the light tables of ia_set_light*
+    const bool add_emitter = (flags & IA_RENDER_ADD_EMITTER) && c->have_light;
     IA_REQUIRE(primary_only || c->have_light, IA_ESTATE, "ia_render: call ia_set_light first");
     IA_REQUIRE(primary_only || (mode == IA_MODE_UNIFORM_LIGHT) == c->light_uniform, IA_ESTATE,
                "ia_render: render_mode uniform_light needs ia_set_light_uniform, the other modes ia_set_light");
@@ -715,7 +718,7 @@ extern "C" int ia_render(ia_ctx* c, const float* d_rays, int64_t n_rays, int64_t
     }
     IA_STAGE_BEGIN(c, IA_STAGE_COMPOSITE, st);
     k_composite<<<(unsigned)((n_rays + 255) / 256), 256, 0, st>>>(c->f, n_rays, c->d_acc, *out, primary_only ? 1 : 0,
-                                                                  (!primary_only && mode == IA_MODE_UNIFORM_LIGHT) ? c->d_vis : nullptr);
+                                                                  (!primary_only && mode == IA_MODE_UNIFORM_LIGHT) ? c->d_vis : nullptr, c->d_bg);
     IA_STAGE_END(c, IA_STAGE_COMPOSITE, st, 1);
     IA_LAUNCH_CHECK();
     return IA_OK;

@@ -10,15 +10,15 @@ import torch
 from . import capi
 from .capi import IaOutputs, check, fptr, ptr
 
-_vp, _i32, _i64, _f32, _u32 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32
+_vp, _i32, _i64, _cf32, _u32 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32
 
 _ARGTYPES = {
     "ia_create": [C.POINTER(_vp), _i32],
     "ia_destroy": [_vp],
-    "ia_set_fields": [_vp, _vp, _vp, _i64] + [_vp] * 4 + [_vp] * 18 + [_vp, _f32, _vp],
+    "ia_set_fields": [_vp, _vp, _vp, _i64] + [_vp] * 4 + [_vp] * 18 + [_vp, _cf32, _vp],
     "ia_set_lbs_voxels": [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp],
     "ia_set_pose": [_vp, _vp, _vp, _vp],
-    "ia_set_render_config": [_vp, _vp, _i32, _i32, _f32, _f32, _f32, _vp, _vp],
+    "ia_set_render_config": [_vp, _vp, _i32, _i32, _cf32, _cf32, _cf32, _vp, _vp],
     "ia_reserve_samples": [_vp, _i64],
     "ia_build_occupancy": [_vp, _vp, _i32, _vp, _vp, _vp],
     "ia_set_occupancy": [_vp, _vp, _i32, _vp, _vp],
@@ -33,7 +33,7 @@ _ARGTYPES = {
     "ia_op_query": [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ia_op_shade_fields": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     "ia_op_geometry": [_vp, _vp, _i64, _vp, _vp],
-    "ia_op_traverse": [_vp, _vp, _vp, _i64, _f32, _f32, _f32] + [_vp] * 9 + [_vp],
+    "ia_op_traverse": [_vp, _vp, _vp, _i64, _cf32, _cf32, _cf32] + [_vp] * 9 + [_vp],
     "ia_op_ray_resampling": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp] + [_vp] * 6 + [_vp],
     "ia_op_ray_resampling_merge": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp] + [_vp] * 6 + [_vp],
     "ia_op_ray_resampling_sdf_fine": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
@@ -42,8 +42,8 @@ _ARGTYPES = {
     "ia_op_brdf": [_vp] * 7 + [_i64, _vp, _vp, _vp],
     "ia_op_bsdf_sample_pdf": [_vp] * 8 + [_i64, _vp, _vp, _vp],
     "ia_op_env": [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
-    "ia_make_rays": [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32, _vp, _vp],
-    "ia_pack_rgb8": [_vp, _vp, _i64, _i32, _f32, _f32, _i32, _vp, _vp],
+    "ia_make_rays": [_vp, _vp, _vp, _vp, _i32, _i32, _cf32, _cf32, _vp, _vp],
+    "ia_pack_rgb8": [_vp, _vp, _i64, _i32, _cf32, _cf32, _i32, _vp, _vp],
 }
 
 OUTPUT_SPECS = [  # name, channels, dtype
@@ -111,12 +111,20 @@ class RenderEngine:
         names = ["geo_w1", "geo_b1", "geo_w2", "geo_b2", "rad_w1", "rad_b1", "rad_w2", "rad_b2", "rad_w3", "rad_b3",
                  "mat_w1", "mat_b1", "mat_w2", "mat_b2", "mat_w3", "mat_b3"]
         host = [_f32(folded[n].cpu().numpy()) for n in names]
+        shapes = {"geo_w1": (64, 35), "geo_b1": (64,), "geo_w2": (13, 64), "geo_b2": (13,), "rad_w1": (64, 67), "rad_b1": (64,),
+                  "rad_w2": (64, 64), "rad_b2": (64,), "rad_w3": (3, 64), "rad_b3": (3,), "mat_w1": (64, 48), "mat_b1": (64,),
+                  "mat_w2": (64, 64), "mat_b2": (64,), "mat_w3": (5, 64), "mat_b3": (5,)}
+        for n, a in zip(names, host):            # ia_set_fields copies fixed extents out of these host arrays
+            if tuple(a.shape) != shapes[n]:
+                raise ValueError(f"set_fields: {n} has shape {tuple(a.shape)}, libia_b200 is built for {shapes[n]}")
         lv = [_f32(layout["scale"]), np.ascontiguousarray(layout["res"], np.int32),
               np.ascontiguousarray(layout["size"], np.int32), np.ascontiguousarray(layout["offset"], np.int32)]
         mat_scale = _f32(folded.get("mat_scale", [0.77, 0.77, 0.77, 0.9, 1.0]))
         mat_bias = _f32(folded.get("mat_bias", [0.03, 0.03, 0.03, 0.09, 0.0]))
         bb = _f32(bbox).reshape(6)
-        check(self.lib.ia_set_fields(self.h, ptr(geo), ptr(rad), geo.numel() // 2, *[fptr(a) for a in lv],
+        # both hash tables are gathered with the same level layout: the smaller one bounds what may be indexed
+        n_entries = min(geo.numel(), rad.numel()) // 2
+        check(self.lib.ia_set_fields(self.h, ptr(geo), ptr(rad), n_entries, *[fptr(a) for a in lv],
                                      *[fptr(a) for a in host], fptr(mat_scale), fptr(mat_bias), fptr(bb),
                                      float(folded["beta"]), _stream()), "ia_set_fields")
 
@@ -319,6 +327,8 @@ class RenderEngine:
         """Canonical SDF of points [n,3] on the tensor-core path of the wavefront integrator's geometry phase."""
         xc = xc.to(self.dev, torch.float32).contiguous()
         sdf = torch.empty(xc.shape[0], device=self.dev)
+        if xc.shape[0] == 0:
+            return sdf
         check(self.lib.ia_op_geometry(self.h, ptr(xc), xc.shape[0], ptr(sdf), _stream()), "ia_op_geometry")
         return sdf
 

@@ -1,17 +1,30 @@
 """Drop-in model for the reference's ``IntrinsicAvatarModel`` on the render path.
 
-Keeps the reference surface (models/intrinsic_avatar.py:166-305, 1653-1674):
-  ``prepare(batch)``, ``forward(rays[N,8]) -> dict`` (CPU tensors in eval, same keys incl. ``*_bg`` /
-  ``*_full`` and ``beta``), ``update_step(epoch, global_step)``, ``train()/eval()``, externally set
-  attributes ``background_color``, ``albedo_only``, ``albedo_align_ratio``, ``t_idx``; ``state_dict`` /
-  ``load_state_dict`` with the reference's parameter keys (weights.py).
+Keeps the reference surface (models/intrinsic_avatar.py:166-305, 1653-1674; models/base.py):
+  ``__init__(config)`` + ``setup()``, ``prepare(batch)``, ``forward(rays[N,8]) -> dict`` (CPU tensors in eval, same keys incl.
+  ``*_bg`` / ``*_full`` and ``beta``), ``update_step(epoch, global_step)``, ``train()/eval()``, the externally set attributes
+  ``background_color``, ``albedo_only``, ``albedo_align_ratio``, ``t_idx``, and the reference's PARAMETER TREE: the render-path
+  parameters are registered under the reference's names (``geometry.network.layers.0.weight_v`` ...), so ``state_dict`` /
+  ``load_state_dict`` behave like any ``nn.Module``'s, also when the model is a sub-module (the reference keeps it as
+  ``system.model``; launch.py:110-124 loads checkpoints with ``strict=False``).
 It adds ``render_image`` / ``render_image_relight`` conveniences named by BASELINE.json.
+
+``config`` is the reference's ``config.model`` node (Hydra DictConfig or plain dict, configs/config.yaml:43-80 with its nested
+geometry / radiance / material / density / deformer / light / scatterer nodes).  The subject is built the way
+``SNARFDeformer`` does (models/deformers/snarf_deformer.py:37-104): the SMPL model named by
+``config.deformer.rigid_deformer.{model_path, gender}``, initialised lazily from ``batch["betas"]`` on the first ``prepare``,
+voxelised at ``deformer_config.resolution``.  A config WITHOUT a ``deformer`` node (the tests and the bench: the licensed SMPL
+file is not shipped) or with ``subject: synthetic`` uses the procedural 24-joint body of ``body.SyntheticBody``.
+Nested nodes are checked against what the kernels are compiled for (hash-grid layout, MLP widths, ...): a mismatch raises.
 
 Only the eval render path is implemented (render_mode = light | uniform_light | mats | mis, with or without
 global_illumination / add_emitter); training-mode calls raise.
 Every numeric step runs in libia_b200.so; this file is glue (pose -> 24 matrices, pointer passing).
 """
 from __future__ import annotations
+
+import math
+import os
 
 import numpy as np
 import torch
@@ -44,13 +57,71 @@ DEFAULT_CONFIG = {
     "occ_resolution": 64,
 }
 
+# What the kernels are compiled for (csrc/ia_types.cuh, weights.py).  A nested config node may omit a key (the reference's
+# default applies) but may not contradict one.
+_HASH_ENCODING = {"otype": "ProgressiveBandHashGrid", "n_levels": W.N_LEVELS, "n_features_per_level": W.N_FEAT,
+                  "log2_hashmap_size": W.LOG2_T, "base_resolution": W.BASE_RES, "per_level_scale": W.PER_LEVEL_SCALE,
+                  "interpolation": "Linear", "include_xyz": True}
+EXPECTED_NESTED = {
+    "geometry": {"name": "volume-sdf", "feature_dim": 13, "grad_type": "analytic", "xyz_encoding_config": _HASH_ENCODING,
+                 "mlp_network_config": {"otype": "VanillaMLP", "output_activation": "none", "n_neurons": 64,
+                                        "n_hidden_layers": 1, "weight_norm": True}},
+    "radiance": {"name": "volume-ref-dir-radiance", "input_feature_dim": 16, "xyz_encoding_config": _HASH_ENCODING,
+                 "dir_encoding_config": {"otype": "SphericalHarmonics", "degree": 4},
+                 "mlp_network_config": {"otype": "VanillaMLP", "activation": "ReLU", "output_activation": "none",
+                                        "n_neurons": 64, "n_hidden_layers": 2},
+                 "color_activation": "sigmoid"},
+    "material": {"name": "volume-material", "input_feature_dim": 48, "n_output_dim": 5,
+                 "mlp_network_config": {"otype": "LipshitzMLP", "activation": "ReLU", "output_activation": "none",
+                                        "n_neurons": 64, "n_hidden_layers": 2},
+                 "material_activation": "sigmoid"},
+    "density": {"name": "learned-laplace-density"},
+    "scatterer": {"name": "brdf-multi-lobe"},
+    "light": {"name": "envlight-tensor", "xyz2lonlat_mode": None},
+    "deformer": {"name": "snarf_deformer",
+                 "rigid_deformer": {"name": "fast-snarf",
+                                    "deformer_config": {"cano_pose": "A_pose", "use_j_inv": False, "optimize_betas": False}},
+                 "non_rigid_deformer": {"name": "dummy_non_rigid_deformer"}},
+}
+_MATERIAL_AFFINE = ("albedo_scale", "albedo_bias", "roughness_scale", "roughness_bias", "metallic_scale", "metallic_bias")
+
+
+def _plain(node):
+    """Hydra DictConfig / attribute dict / dict -> plain nested dict (lists stay lists)."""
+    if hasattr(node, "items"):
+        return {k: _plain(v) for k, v in node.items()}
+    if isinstance(node, (list, tuple)):
+        return [_plain(v) for v in node]
+    return node
+
+
+def _check_nested(cfg, expected, path, errors):
+    for k, want in expected.items():
+        if k not in cfg:
+            continue
+        got = cfg[k]
+        if isinstance(want, dict):
+            if isinstance(got, dict):
+                _check_nested(got, want, f"{path}.{k}", errors)
+            else:
+                errors.append(f"{path}.{k}: expected a config node, got {got!r}")
+        elif isinstance(want, float):
+            if not (isinstance(got, (int, float)) and math.isclose(float(got), want, rel_tol=1e-9)):
+                errors.append(f"{path}.{k} = {got!r}, the kernels are built for {want!r}")
+        elif got != want:
+            errors.append(f"{path}.{k} = {got!r}, the kernels are built for {want!r}")
+
+
+class _Node(torch.nn.Module):
+    """Empty container: the reference's module tree only as far as its parameter NAMES go."""
+
 
 class IntrinsicAvatarModel(torch.nn.Module):
-    def __init__(self, config: dict | None = None, body=None, device: int | None = None, seed: int = 0):
+    def __init__(self, config=None, body=None, device: int | None = None, seed: int = 0):
         super().__init__()
+        user = _plain(config) if config is not None else {}
         self.config = dict(DEFAULT_CONFIG)
-        if config:
-            self.config.update(config)
+        self.config.update(user)
         cfg = self.config
         if cfg["render_mode"] not in ("light", "uniform_light", "mats", "mis"):
             # same failure as the reference's dispatch (models/intrinsic_avatar.py:1435-1438)
@@ -59,42 +130,115 @@ class IntrinsicAvatarModel(torch.nn.Module):
             assert cfg["samples_per_pixel"] == 512  # models/intrinsic_avatar.py:1391 (16 x 32 stratified sphere)
         if not (cfg["secondary_importance_sample"] and cfg["zero_crossing_search"]) or cfg["material_feature"] != "hybrid":
             raise NotImplementedError("non-default secondary sampling / material_feature not supported")
-        self.engine = RenderEngine(device)
-        self.setup_snarf = SnarfSetup(body)
-        self.layout = W.hashgrid_layout()
-        self._params = torch.nn.ParameterDict()  # reference-keyed parameters ('.' -> '/')
+        errors = []
+        _check_nested(cfg, EXPECTED_NESTED, "config", errors)
+        if errors:
+            raise ValueError("IntrinsicAvatarModel: this build of libia_b200 cannot render the configured model:\n  "
+                             + "\n  ".join(errors))
+        self._body_arg = body
+        self._device_arg = device
+        self.seed = seed
         self.background_color = torch.ones(3)
         self.albedo_only = False
         self.t_idx = 0.0
         self.enable_phys = True
         self.importance_sample = True
-        self.seed = seed
         self._frame = None
         self._light_key = None
-        self.engine.set_lbs_voxels(self.setup_snarf.lbs_voxel, self.setup_snarf.offset_kernel,
-                                   self.setup_snarf.scale_kernel)
-        self.load_state_dict(W.random_state_dict(seed))
+        self._light_hdri = None
+        self._betas = None
+        self.setup_snarf = None
+        self.engine = None
+        self.setup()
+
+    # ------------------------------------------------------------------- set-up ----
+    def setup(self):
+        """models/base.py: BaseModel.__init__ calls setup().  Creates the device context and the parameter tree (random
+        initial values as ``weights.random_state_dict``; a checkpoint replaces them through ``load_state_dict``).  The
+        subject (skinning-weight voxels, canonical bbox) follows on the first ``prepare`` -- it needs ``batch["betas"]`` --
+        unless a body object was handed to the constructor."""
+        self.engine = RenderEngine(self._device_arg)
+        self.layout = W.hashgrid_layout()
+        for key, v in W.random_state_dict(self.seed).items():
+            self._register(key, v)
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._upload_fields())
+        if self._body_arg is not None:
+            self._init_subject(self._body_arg)
+
+    def _register(self, key: str, value: torch.Tensor):
+        parts = key.split(".")
+        node = self
+        for p in parts[:-1]:
+            if not hasattr(node, p):
+                node.add_module(p, _Node())
+            node = getattr(node, p)
+        node.register_parameter(parts[-1], torch.nn.Parameter(value.detach().clone().float(), requires_grad=False))
+
+    def _resolve_body(self, betas):
+        """SNARFDeformer.__init__ (snarf_deformer.py:39): ``SMPL(config.model_path, gender=config.gender)``."""
+        from .body import SMPLBody, SyntheticBody
+        dcfg = self.config.get("deformer")
+        subject = self.config.get("subject", "smpl" if dcfg else "synthetic")
+        if subject == "synthetic":
+            return SyntheticBody()
+        rigid = (dcfg or {}).get("rigid_deformer", {})
+        model_path, gender = rigid.get("model_path"), str(rigid.get("gender", "neutral"))
+        if not model_path:
+            raise ValueError("config.deformer.rigid_deformer.model_path is not set (or pass subject='synthetic')")
+        cands = [model_path] if os.path.isfile(model_path) else [
+            os.path.join(model_path, f"SMPL_{gender.upper()}{ext}") for ext in (".pkl", ".npz")]
+        for c in cands:
+            if os.path.isfile(c):
+                return SMPLBody.from_file(c, betas=betas)
+        raise FileNotFoundError(f"SMPL model not found (tried {cands}); the reference reads it the same way "
+                                "(models/deformers/smplx/body_models.py:113-129).  Use subject='synthetic' for the "
+                                "procedural test body.")
+
+    def _init_subject(self, body):
+        res = int(self.config.get("deformer", {}).get("rigid_deformer", {}).get("deformer_config", {}).get("resolution", 128))
+        self.setup_snarf = SnarfSetup(body, resolution=res)
+        self.engine.set_lbs_voxels(self.setup_snarf.lbs_voxel, self.setup_snarf.offset_kernel, self.setup_snarf.scale_kernel)
+        self._upload_fields()
 
     # ---------------------------------------------------------------- parameters ----
-    def state_dict(self, *a, **k):
-        return {key.replace("/", "."): v.detach() for key, v in self._params.items()}
-
-    def load_state_dict(self, sd, strict=False):
-        for k, v in sd.items():
-            if k.startswith("model."):
-                k = k[len("model."):]
-            if k.split(".")[0] in ("geometry", "radiance", "material", "density"):
-                self._params[k.replace(".", "/")] = torch.nn.Parameter(torch.as_tensor(v).clone().float(),
-                                                                      requires_grad=False)
-        self._upload_fields()
+    def load_state_dict(self, state_dict, strict: bool = False, assign: bool = False):
+        """Reference-keyed state dict, optionally under a ``model.`` prefix (a Lightning checkpoint's ``state_dict``).  Keys
+        outside the render path are reported as unexpected, not loaded; every accepted tensor must have the element count
+        of the parameter it replaces (tiny-cuda-nn stores the hash grids as flat fp16).  Returns torch's
+        ``_IncompatibleKeys(missing_keys, unexpected_keys)``; ``strict=True`` raises on either, like nn.Module."""
+        own = dict(self.named_parameters())
+        sd, unexpected = {}, []
+        for k, v in state_dict.items():
+            k2 = k[len("model."):] if k.startswith("model.") else k
+            if k2 not in own:
+                unexpected.append(k)
+                continue
+            v = torch.as_tensor(v)
+            if v.numel() != own[k2].numel():
+                raise ValueError(f"load_state_dict: {k} has shape {tuple(v.shape)}, the render path is built for "
+                                 f"{tuple(own[k2].shape)}")
+            sd[k2] = v.detach().float().reshape(own[k2].shape)
+        res = super().load_state_dict(sd, strict=False)
+        missing = list(res.missing_keys)
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"load_state_dict(strict=True): missing {missing[:4]}, unexpected {unexpected[:4]}")
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
 
     def load_checkpoint(self, path: str):
         """Ingest a Lightning checkpoint of the reference (launch.py:110-124): the render-path parameters under
         ``model.`` are taken, everything else is ignored (strict=False semantics)."""
-        self.load_state_dict(W.load_lightning_checkpoint(path))
+        return self.load_state_dict(W.load_lightning_checkpoint(path))
 
     def _upload_fields(self):
-        folded = W.fold(self.state_dict())
+        if self.setup_snarf is None:
+            return                                       # the canonical bbox is not known before the subject is
+        sd = {k: v.detach() for k, v in self.named_parameters()}
+        folded = W.fold(sd)
+        mcfg = self.config.get("material") or {}
+        if any(k in mcfg for k in _MATERIAL_AFFINE):     # configs/material/shallow_mlp.yaml:4-9
+            g = lambda k, d: float(mcfg.get(k, d))
+            folded["mat_scale"] = [g("albedo_scale", 0.77)] * 3 + [g("roughness_scale", 0.9), g("metallic_scale", 1.0)]
+            folded["mat_bias"] = [g("albedo_bias", 0.03)] * 3 + [g("roughness_bias", 0.09), g("metallic_bias", 0.0)]
         self._beta = folded["beta"]
         self.engine.set_fields(folded, self.layout, self.setup_snarf.bbox)
 
@@ -121,11 +265,19 @@ class IntrinsicAvatarModel(torch.nn.Module):
             None if ratio is None else np.asarray(torch.as_tensor(ratio).cpu(), np.float32))
 
     def prepare(self, batch: dict, jitter=None, light_uniforms=None):
-        """models/intrinsic_avatar.py:281-305.  ``batch`` holds body_pose[1,69], global_orient[1,3],
-        transl[1,3] and optionally hdri[H,W,3].  Randomness of the reference (occupancy jitter, light
-        sample uniforms) is drawn from torch's generator unless given explicitly."""
+        """models/intrinsic_avatar.py:281-305.  ``batch`` holds betas[1,10] (first call: the subject is built from them,
+        snarf_deformer.py:89-91), body_pose[1,69], global_orient[1,3], transl[1,3] and optionally hdri[H,W,3].
+        Randomness of the reference (occupancy jitter, light sample uniforms) is drawn from torch's generator unless
+        given explicitly."""
         def _np(x):
             return np.asarray(torch.as_tensor(x).detach().cpu(), np.float32).reshape(-1)
+        betas = _np(batch["betas"])[:10] if "betas" in batch else None
+        if self.setup_snarf is None:
+            self._betas = betas
+            self._init_subject(self._resolve_body(betas))
+        elif betas is not None and self._betas is not None and not np.allclose(betas, self._betas, atol=1e-6):
+            # optimize_betas is false: the shape is fixed at initialisation (snarf_deformer.py:83-91)
+            raise ValueError("prepare: batch['betas'] differ from the betas the subject was initialised with")
         fr = self.setup_snarf.frame(_np(batch["body_pose"]), _np(batch["global_orient"]), _np(batch["transl"]))
         self._frame = fr
         self._apply_config()
@@ -138,14 +290,17 @@ class IntrinsicAvatarModel(torch.nn.Module):
             spp = self.config["samples_per_pixel"]
             resample = self.config["resample_light"] or self._light_key is None
             if resample:
+                # emitter.base = hdri; update_pdf(); emitter.sample(spp) (models/intrinsic_avatar.py:291-301).  With
+                # resample_light = false all of that happens once: later frames keep the first envmap, pdf and directions.
                 if light_uniforms is None:
                     light_uniforms = (torch.rand(spp, device=self.engine.dev), torch.rand(spp, device=self.engine.dev))
                 self._light_key = light_uniforms
-            # directions live in the per-frame SMPL-root frame: refresh the tables every frame
+                self._light_hdri = batch["hdri"]
+            # the directions are used in the per-frame SMPL-root frame: the tables are rebuilt from the kept envmap / uniforms
             if self.config["render_mode"] == "uniform_light":
-                self.engine.set_light_uniform(batch["hdri"], 16, 32)
+                self.engine.set_light_uniform(self._light_hdri, 16, 32)
             else:
-                self.engine.set_light(batch["hdri"], self._light_key[0], self._light_key[1])
+                self.engine.set_light(self._light_hdri, self._light_key[0], self._light_key[1])
 
     # -------------------------------------------------------------------- forward ----
     def forward(self, rays: torch.Tensor, move_to_cpu: bool = True) -> dict:

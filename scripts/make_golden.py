@@ -559,6 +559,50 @@ def main_e2e_hi():
     print("wrote", out_path, len(g), "arrays")
 
 
+def main_config():
+    """The reference's ``config.model`` node for the relighting test run (configs/config.yaml with its defaults list, dataset
+    animation/male-3-casual, light envlight_tensor as README.md:84-95 selects), Hydra interpolations resolved by hand ->
+    tests/golden/reference_model_config.json.  tests/test_host_logic.py and tests/test_gpu_render.py build
+    IntrinsicAvatarModel from it through a models.register / models.make registry like the reference's."""
+    import json
+    import yaml
+    C = os.path.join(REF, "configs")
+    load = lambda rel: yaml.safe_load(open(os.path.join(C, rel)))
+    root = load("config.yaml")
+    choice = {"dataset": "animation/male-3-casual", "light": "envlight_tensor"}
+    groups = {}
+    for d in root["defaults"]:
+        if isinstance(d, dict):
+            for g, name in d.items():
+                if not g.startswith("override"):
+                    groups[g] = choice.get(g, name)
+    nodes = {g: load(f"{g}/{name}.yaml") for g, name in groups.items()}
+    model = root["model"]
+    subst = {"${dataset.scene_aabb}": nodes["dataset"]["scene_aabb"], "${dataset.gender}": nodes["dataset"]["gender"],
+             "${trainer.precision}": 32, "${add:${model.geometry.feature_dim}, 3}": 16,
+             "${add:${model.geometry.feature_dim}, 35}": 48}
+
+    def resolve(v):
+        if isinstance(v, dict):
+            return {k: resolve(x) for k, x in v.items()}
+        if isinstance(v, list):
+            return [resolve(x) for x in v]
+        if isinstance(v, str):
+            if v in subst:
+                return subst[v]
+            if v.startswith("${") and v[2:-1] in nodes:
+                return resolve(nodes[v[2:-1]])
+        return v
+    out = resolve(model)
+    # what the README's relight command overrides (README.md:84-95)
+    out.update({"render_mode": "light", "global_illumination": False, "samples_per_pixel": 1024, "resample_light": False,
+                "add_emitter": True})
+    path = os.path.join(ROOT, "tests", "golden", "reference_model_config.json")
+    with open(path, "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print("wrote", path, sorted(out))
+
+
 def main_snarf():
     """The reference's own SNARFDeformer.initialize + prepare_deformer (models/deformers/snarf_deformer.py:46-126) driven
     by a body model that calls the reference's lbs() on the random SMPL-shaped arrays of reference_vectors_smpl.npz (the
@@ -637,6 +681,8 @@ def main_snarf():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "e2e":
         main_e2e()
+    elif len(sys.argv) > 1 and sys.argv[1] == "config":
+        main_config()
     elif len(sys.argv) > 1 and sys.argv[1] == "e2e_hi":
         main_e2e_hi()
     elif len(sys.argv) > 1 and sys.argv[1] == "fields":

