@@ -59,7 +59,8 @@ __device__ __forceinline__ void ia_stage_bfrag(float4* dst, int k_steps, int n_t
 // One dense layer for a 16-row tile whose inputs sit in shared memory, row-major with leading dimension `ld` floats
 // (ld % 32 == 12 or 4 keeps the A-fragment loads conflict-free): c[nt][.] += X[16 x 8 K_STEPS] W.
 // N_TILES consecutive n-tiles of a layer staged with N_TILES_TOTAL per k-step (wfrag points at the first of them).
-template <int K_STEPS, int N_TILES, int N_TILES_TOTAL = N_TILES>
+// ROWS = 8: the tile holds rows 0..7 only (rows 8..15 of the m16 operand are zero, c[.][2..3] stay at their initial value).
+template <int K_STEPS, int N_TILES, int N_TILES_TOTAL = N_TILES, int ROWS = 16>
 __device__ __forceinline__ void ia_mma_layer_smem(const float* __restrict__ xs, int ld, const float4* __restrict__ wfrag,
                                                   float c[N_TILES][4]) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -67,9 +68,13 @@ __device__ __forceinline__ void ia_mma_layer_smem(const float* __restrict__ xs, 
     for (int s = 0; s < K_STEPS; s++) {
         uint32_t ahi[4], alo[4];
         ia_split_tf32(xs[g * ld + 8 * s + t], ahi[0], alo[0]);
-        ia_split_tf32(xs[(g + 8) * ld + 8 * s + t], ahi[1], alo[1]);
         ia_split_tf32(xs[g * ld + 8 * s + t + 4], ahi[2], alo[2]);
-        ia_split_tf32(xs[(g + 8) * ld + 8 * s + t + 4], ahi[3], alo[3]);
+        if (ROWS == 16) {
+            ia_split_tf32(xs[(g + 8) * ld + 8 * s + t], ahi[1], alo[1]);
+            ia_split_tf32(xs[(g + 8) * ld + 8 * s + t + 4], ahi[3], alo[3]);
+        } else {
+            ahi[1] = alo[1] = ahi[3] = alo[3] = 0u;
+        }
 #pragma unroll
         for (int nt = 0; nt < N_TILES; nt++) ia_mma_3xtf32(c[nt], ahi, alo, wfrag[(s * N_TILES_TOTAL + nt) * 32 + lane]);
     }

@@ -416,7 +416,10 @@ __device__ __forceinline__ void ia_warp_resample(const IaResampleIn& in, int ste
                                                  float* __restrict__ o_t, float* __restrict__ o_off, long long* __restrict__ o_idx64,
                                                  int* __restrict__ o_src, float* __restrict__ o_w,
                                                  int* __restrict__ o_fg_counts, int* __restrict__ o_bg_count,
-                                                 long long* __restrict__ o_surface) {
+                                                 long long* __restrict__ o_surface, const bool perm = false,
+                                                 const uint32_t perm_key = 0u, const long long o_stride = 1) {
+    // o_t / o_src / o_w of output j go to position (perm ? ia_permute(j, spp, perm_key) : j) * o_stride: the light-major
+    // layout of the shading stage (k_resample)
     const int lane = threadIdx.x & 31;
     const int st = in.stride;
     if (lane == 0) {
@@ -509,45 +512,58 @@ __device__ __forceinline__ void ia_warp_resample(const IaResampleIn& in, int ste
             float offset = (u - cp) * scaling;
             float t = offset + s;
             if (j >= j0) t = t_snap;
-            if (o_t) o_t[j] = t;
+            const long long jo = (long long)(perm ? ia_permute((uint32_t)j, (uint32_t)spp, perm_key) : (uint32_t)j) * o_stride;
+            if (o_t) o_t[jo] = t;
             if (o_off) o_off[j] = offset;
             if (o_idx64) o_idx64[j] = idx + src_base;
-            if (o_src) o_src[j] = (int)(idx + src_base);
+            if (o_src) o_src[jo] = (int)(idx + src_base);
             if (o_w) {
                 int cnt = ia_count_below(u_table, spp, cn) - ia_count_below(u_table, spp, cp);
-                o_w[j] = in.weights[(size_t)idx * st] / (float)cnt;
+                o_w[jo] = in.weights[(size_t)idx * st] / (float)cnt;
             }
         } else {
             float offset = 10000.f;
-            if (o_t) o_t[j] = offset + end_last;
+            const long long jo = (long long)(perm ? ia_permute((uint32_t)j, (uint32_t)spp, perm_key) : (uint32_t)j) * o_stride;
+            if (o_t) o_t[jo] = offset + end_last;
             if (o_off) o_off[j] = offset;
             if (o_idx64) o_idx64[j] = steps - 1 + src_base;
-            if (o_src) o_src[j] = -1;
-            if (o_w) o_w[j] = transmittance / (float)n_bg;
+            if (o_src) o_src[jo] = -1;
+            if (o_w) o_w[jo] = transmittance / (float)n_bg;
         }
     }
 }
 
+// Layout of the resampled streams (rs_t, rs_src, rs_w):
+//   pixel-major  [slot][j]          mats / mis: sample j of hit ray `slot`
+//   light-major  [kk][slot]         light-table modes with WF_LIGHT_MAJOR: kk = the light direction the keyed permutation
+//                                   assigns to sample j of that ray (models/intrinsic_avatar.py:1355-1378).  The shading
+//                                   stage then feeds bundles of PARALLEL rays from neighbouring pixels (ia_wavefront.cuh).
 __global__ void __launch_bounds__(256) k_resample(const int* __restrict__ hit_info, const float* __restrict__ hit_od,
                                                   const IaSample* __restrict__ samples, const int* __restrict__ work,
                                                   int spp, const float* __restrict__ u_table, float* __restrict__ rs_t,
-                                                  int* __restrict__ rs_src, float* __restrict__ rs_w) {
+                                                  int* __restrict__ rs_src, float* __restrict__ rs_w, int light_major,
+                                                  const int* __restrict__ hit_rays, long long ray_index_base, uint32_t seed) {
     __shared__ float cdf_s[8][IA_CAP];
     const int n_hit = work[IA_W_NHIT];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int slot = blockIdx.x * 8 + warp; slot < n_hit; slot += gridDim.x * 8) {
         int base = hit_info[slot * 2], steps = hit_info[slot * 2 + 1];
-        size_t ob = (size_t)slot * spp;
+        const size_t ob = light_major ? (size_t)slot : (size_t)slot * spp;
+        const long long stride = light_major ? (long long)n_hit : 1;
+        const uint32_t key = light_major ? ia_pixel_key(seed, (uint64_t)(ray_index_base + hit_rays[slot])) : 0u;
         if (steps == 0) {
             // no shading sample survived: all background with the ray's full transmittance
-            for (int j = lane; j < spp; j += 32) { rs_t[ob + j] = 0.f; rs_src[ob + j] = -1; rs_w[ob + j] = 1.0f / (float)spp; }
+            for (int j = lane; j < spp; j += 32) {
+                const size_t o = ob + (size_t)j * stride;   // (every position of the ray is written: the order does not matter)
+                rs_t[o] = 0.f; rs_src[o] = -1; rs_w[o] = 1.0f / (float)spp;
+            }
             continue;
         }
         const float* sp = reinterpret_cast<const float*>(samples + base);
         IaResampleIn in{sp + 0, sp + 1, sp + 2, sp + 3, (int)(sizeof(IaSample) / sizeof(float))};
         float trans = 1.0f - hit_od[(size_t)slot * 8 + 7];
         ia_warp_resample(in, steps, spp, u_table, cdf_s[warp], trans, (long long)base, rs_t + ob, nullptr, nullptr,
-                         rs_src + ob, rs_w + ob, nullptr, nullptr, nullptr);
+                         rs_src + ob, rs_w + ob, nullptr, nullptr, nullptr, light_major != 0, key, stride);
         __syncwarp();
     }
 }
@@ -695,7 +711,8 @@ extern "C" int ia_render(ia_ctx* c, const float* d_rays, int64_t n_rays, int64_t
     if (!primary_only) {
         IA_STAGE_BEGIN(c, IA_STAGE_RESAMPLE, st);
         k_resample<<<c->n_sm * 4, 256, 0, st>>>(c->d_hit_info, c->d_hit_od, c->d_samples, c->d_work, c->spp, c->d_u_table,
-                                                c->d_rs_t, c->d_rs_src, c->d_rs_w);
+                                                c->d_rs_t, c->d_rs_src, c->d_rs_w, (WF_LIGHT_MAJOR && mode <= IA_MODE_UNIFORM_LIGHT) ? 1 : 0,
+                                                c->d_hit_rays, ray_index_base, seed);
         IA_STAGE_END(c, IA_STAGE_RESAMPLE, st, 1);
         IA_LAUNCH_CHECK();
         if (mode == IA_MODE_UNIFORM_LIGHT) IA_CHECK_CUDA(cudaMemsetAsync(c->d_vis, 0, (size_t)n_rays * sizeof(float), st));
@@ -922,7 +939,7 @@ extern "C" int ia_op_secondary(ia_ctx* c, const float* d_o, const float* d_d, in
 }
 
 // op-level twin of the wavefront kernel's geometry phase: canonical SDF of n points on the tensor cores
-// (ia_warp_geometry16: hash grid -> 35 -> 64 layer as 3xTF32 mma -> softplus -> sdf row)
+// (ia_warp_geometry: hash grid -> 35 -> 64 layer as 3xTF32 mma -> softplus -> sdf row)
 __global__ void __launch_bounds__(256) k_op_geometry(const __grid_constant__ IaFrame p, const float* __restrict__ xc, long long n,
                                                      float* __restrict__ sdf) {
     extern __shared__ __align__(16) float smem[];
@@ -942,7 +959,7 @@ __global__ void __launch_bounds__(256) k_op_geometry(const __grid_constant__ IaF
         const int nb = (int)min((long long)16, n - b0);
         float x0 = 0.f, x1 = 0.f, x2 = 0.f;
         if (lane < nb) { x0 = xc[(b0 + lane) * 3]; x1 = xc[(b0 + lane) * 3 + 1]; x2 = xc[(b0 + lane) * 3 + 2]; }
-        const float s = ia_warp_geometry16(p, lvl, w, w1f, xs, x0, x1, x2, nb);
+        const float s = ia_warp_geometry<16>(p, lvl, w, w1f, xs, x0, x1, x2, nb);
         if (lane < nb) sdf[b0 + lane] = s;
     }
 }

@@ -43,6 +43,16 @@
 #define WF_QCAP 8192
 #endif
 #define WF_NST 36      // state words per ray
+#ifndef WF_LIGHT_MAJOR
+#define WF_LIGHT_MAJOR 1   // light-table modes: shading samples are stored and fed light-major -- for each light direction all
+#endif                     // hit pixels in ray order (k_resample) -- so that the rays in flight are bundles of parallel rays from
+                           // neighbouring surface points and, with WF_QSORT, neighbouring lanes gather the same voxel / hash cells.
+                           // 0: pixel-major (all samples of a pixel, then the next pixel).  Only the processing order differs.
+#ifndef WF_QSORT
+#define WF_QSORT 1     // 1: the pending queries of a round are sorted along a Morton curve over their posed position before the
+#endif                 // task lists are built: neighbouring lanes of the Broyden and geometry phases then touch the same voxel
+                       // cells / hash cells (scripts/gather_microbench.cu: a warp whose lanes stay within 2 cells gathers 1.5x, within
+                       // one cell 4.7x faster than a warp of scattered lanes).  Only the processing order changes.
 #ifndef WF_STATE_GLOBAL
 #define WF_STATE_GLOBAL 1
 #endif
@@ -63,7 +73,8 @@
 #define WF_SCRATCH_BYTES (WF_OFF_STATE + WF_NST * WF_R * 4)
 
 enum { WF_C_Q = 0, WF_C_FETCH, WF_C_GEO, WF_C_RAYS, WF_C_SKIP, WF_C_QG, WF_C_RAD };
-enum { WF_IDLE = 0, WF_FIRST = 1, WF_SEARCH = 2, WF_CDF = 3, WF_FINE = 4, WF_GIWAIT = 5 };
+enum { WF_IDLE = 0, WF_FIRST = 1, WF_SEARCH = 2, WF_CDF = 3, WF_FINE = 4, WF_GIWAIT = 5,
+       WF_DONE = 6, WF_DONE_IND = 7 };   // ray ended (6: without, 7: with indirect radiance in WS_IND); estimator pending
 enum { WF_ACT_NEXT = 0, WF_ACT_CDF = 1, WF_ACT_FINE_START = 2, WF_ACT_FINISH = 3 };
 
 // state word indices
@@ -101,6 +112,11 @@ struct WfShared {
     float qx[3][WF_R];
     unsigned int qmask[WF_R];
     unsigned short qlist[WF_R];
+    unsigned short rlist[WF_R];   // advance phase: slots to finish and / or refill
+    int n_rlist;
+#if WF_QSORT
+    unsigned int sortk[WF_R];     // (Morton code of the query position << 10) | slot
+#endif
     uint2 ring[WF_QCAP];
     // tensor-core geometry phase (ia_mma.cuh): pre-split B fragments of the 35 -> 64 layer, one 16-point input tile per warp
     float4* w1f;            // [IA_GEO_KSTEPS][8][32]
@@ -175,6 +191,50 @@ __device__ __forceinline__ void wf_count(WfShared& S, int which, unsigned v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(&S.cnt[which], v);
 }
+
+#if WF_QSORT
+// qlist <- the pending queries ordered along a Morton curve (7 bits per axis over the occupancy grid's box, cells of
+// ~1.6 cm: the size of a skinning-weight voxel).  Bitonic sort of WF_R keys in shared memory, < 1 % of a round.
+static_assert((WF_R & (WF_R - 1)) == 0 && WF_R <= 1024, "WF_QSORT: WF_R must be a power of two <= 1024 (10-bit slot field)");
+__device__ __forceinline__ unsigned wf_morton7(unsigned v) {   // 7 bits -> every third bit
+    v &= 0x7fu;
+    v = (v | (v << 8)) & 0x0000700fu;
+    v = (v | (v << 4)) & 0x000430c3u;
+    v = (v | (v << 2)) & 0x00049249u;
+    return v;
+}
+__device__ __forceinline__ void wf_sort_phase(const IaFrame& p, WfShared& S, int n_q) {
+    for (int i = threadIdx.x; i < WF_R; i += blockDim.x) {
+        unsigned key = 0xffffffffu;
+        if (i < n_q) {
+            const int q = S.qlist[i];
+            unsigned m = 0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float u = (S.qx[k][q] - p.aabb[k]) / (p.aabb[3 + k] - p.aabb[k]);
+                const unsigned c = (unsigned)fminf(fmaxf(u * 128.0f, 0.f), 127.f);
+                m |= wf_morton7(c) << k;
+            }
+            key = (m << 10) | (unsigned)q;
+        }
+        S.sortk[i] = key;
+    }
+    for (int k = 2; k <= WF_R; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < WF_R / 2; t += blockDim.x) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int hi = lo | j;
+                const unsigned a = S.sortk[lo], b = S.sortk[hi];
+                const bool up = (lo & k) == 0;
+                if ((a > b) == up) { S.sortk[lo] = b; S.sortk[hi] = a; }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_q; i += blockDim.x) S.qlist[i] = (unsigned short)(S.sortk[i] & 1023u);
+}
+#endif
 
 // Broyden chains of all pending queries (fuse_cuda_kernel_fast.cu:250-413), one voxel fetch per trip.
 // Dense pre-pass over the 13 x n_q (query, init bone) pairs: chains whose initial point has all 8 corners
@@ -331,11 +391,15 @@ __device__ __forceinline__ void wf_filter_phase(WfShared& S, int n_q) {
 // 32..34 the scaled position 2 xn - 1, 35..39 zero (set once at kernel start, never written).
 #define IA_GEO_KSTEPS 5
 #define IA_GEO_LD 44
+#ifndef WF_MMA_ROWS
+#define WF_MMA_ROWS 16   // points per tensor-core batch of a warp: 16 (the full m16 tile) or 8 (half the shared memory for the input
+#endif                   // tiles -- L1 capacity for the gathers -- at twice the weight-fragment reads per point)
 __device__ __forceinline__ float ia_geo_w1(const float* __restrict__ mlp, int k, int n) {   // layer-1 weight of tile column k
     const int in = k < 32 ? 3 + k : (k < 35 ? k - 32 : -1);
     return in < 0 ? 0.f : mlp[IA_GEO_W1T + in * 64 + n];
 }
-__device__ __forceinline__ float ia_warp_geometry16(const IaFrame& p, const IaLevel* __restrict__ lvl, const float* __restrict__ w,
+template <int ROWS>
+__device__ __forceinline__ float ia_warp_geometry(const IaFrame& p, const IaLevel* __restrict__ lvl, const float* __restrict__ w,
                                                     const float4* __restrict__ w1f, float* __restrict__ xs, float px, float py,
                                                     float pz, int n_pts) {
     const unsigned FULL = 0xffffffffu;
@@ -366,12 +430,12 @@ __device__ __forceinline__ float ia_warp_geometry16(const IaFrame& p, const IaLe
             const float2 b = *reinterpret_cast<const float2*>(w + IA_GEO_B1 + 8 * (4 * nh + nt) + 2 * t);
             c[nt][0] = b.x; c[nt][1] = b.y; c[nt][2] = b.x; c[nt][3] = b.y;
         }
-        ia_mma_layer_smem<IA_GEO_KSTEPS, 4, 8>(xs, IA_GEO_LD, w1f + 4 * nh * 32, c);
+        ia_mma_layer_smem<IA_GEO_KSTEPS, 4, 8, ROWS>(xs, IA_GEO_LD, w1f + 4 * nh * 32, c);
 #pragma unroll
         for (int nt = 0; nt < 4; nt++) {
             const float2 w2 = *reinterpret_cast<const float2*>(w + IA_GEO_W2 + 8 * (4 * nh + nt) + 2 * t);
             lo = fmaf(w2.x, ia_softplus100(c[nt][0]), lo); lo = fmaf(w2.y, ia_softplus100(c[nt][1]), lo);
-            hi = fmaf(w2.x, ia_softplus100(c[nt][2]), hi); hi = fmaf(w2.y, ia_softplus100(c[nt][3]), hi);
+            if (ROWS == 16) { hi = fmaf(w2.x, ia_softplus100(c[nt][2]), hi); hi = fmaf(w2.y, ia_softplus100(c[nt][3]), hi); }
         }
     }
     __syncwarp();   // the tile may be overwritten by the next batch
@@ -390,30 +454,30 @@ __device__ __forceinline__ void wf_geometry_phase(const IaFrame& p, WfShared& S)
     // an even split of the task list over the warps (the gathers of step A are the cost, and they are per point)
     const int per = (n + n_warps - 1) / n_warps;
     const int end = min(n, (warp + 1) * per);
-    float* xs = S.xs + warp * 16 * IA_GEO_LD;
+    float* xs = S.xs + warp * WF_MMA_ROWS * IA_GEO_LD;
     // software pipeline: the task ids and roots of the NEXT batch (two dependent L2 round trips: the lists were just
     // written by other warps) are fetched while the current one is evaluated
     int b0 = warp * per;
     int ci = 0;
     float x0 = 0.f, x1 = 0.f, x2 = 0.f;
-    if (b0 + lane < end && lane < 16) {
+    if (b0 + lane < end && lane < WF_MMA_ROWS) {
         const int tk = S.gtask[b0 + lane];
         ci = (tk >> 4) * IA_N_INIT + (tk & 15);
         const float* cd = S.cand + ci * 3;
         x0 = cd[0]; x1 = cd[1]; x2 = cd[2];
     }
     while (b0 < end) {
-        const int nb = min(16, end - b0);
-        const int bn = b0 + 16;
+        const int nb = min(WF_MMA_ROWS, end - b0);
+        const int bn = b0 + WF_MMA_ROWS;
         int ci_n = 0;
         float y0 = 0.f, y1 = 0.f, y2 = 0.f;
-        if (bn + lane < end && lane < 16) {
+        if (bn + lane < end && lane < WF_MMA_ROWS) {
             const int tk = S.gtask[bn + lane];
             ci_n = (tk >> 4) * IA_N_INIT + (tk & 15);
             const float* cd = S.cand + ci_n * 3;
             y0 = cd[0]; y1 = cd[1]; y2 = cd[2];
         }
-        const float s = ia_warp_geometry16(p, S.lvl, S.w, S.w1f, xs, x0, x1, x2, nb);
+        const float s = ia_warp_geometry<WF_MMA_ROWS>(p, S.lvl, S.w, S.w1f, xs, x0, x1, x2, nb);
         if (lane < nb) { S.csdf[ci] = s; c_geo++; }
         b0 = bn; ci = ci_n; x0 = y0; x1 = y1; x2 = y2;
     }
@@ -458,12 +522,23 @@ __device__ __forceinline__ void wf_gi_phase(const IaFrame& p, WfShared& S) {
 //   void P::finish(const uint2 entry, float T, const float ind[3], const float d[3])   shade / store (ind = indirect
 //                                                                     radiance, GI; d = the ray direction)
 //   int P::tile_items()   shading samples examined per feed step (each may push up to WF_QCAP / 2 / tile_items() rays)
+// The advance phase runs in two passes so that the expensive, rare events do not serialise the warps (round 1 ran
+// everything in one pass: a slot whose ray ended -- ~1 of 12 per round -- dragged its 31 neighbours through BRDF
+// evaluation, ray set-up and the march to the first occupied cell at 2-3 lanes of 32):
+//   consume : one thread per slot: SDF of the previous query -> state machine -> next query point.  A slot whose ray has
+//             ended only records its transmittance and joins the refill list, as does an idle slot.
+//   refill  : one thread per LIST ENTRY (dense): estimator of the finished ray (P::finish), next ray from the ring
+//             (P::init, marcher set-up, march to its first sample), its first query.
+// Measured at 512^2 x 1024 spp, GI on, frames 2-4: 1159 -> 1102 ms (and 1088 -> 1035 ms with WF_QSORT).
 template <bool GI, class P>
-__device__ __forceinline__ void wf_advance_slot(const IaFrame& p, P& pol, WfShared& S, const int t, int ring_tail,
-                                                unsigned& c_q, unsigned& c_rays) {
+__device__ __forceinline__ void wf_advance_consume(const IaFrame& p, P& pol, WfShared& S, const int t, unsigned& c_q) {
     unsigned pack = __float_as_uint(S.st[WS_PACK][t]);
     int stage = pack & 7u, j = (pack >> 3) & 7u, i = (pack >> 6) & 7u;
-    uint2 entry = make_uint2(__float_as_uint(S.st[WS_ID][t]), pack >> 16);
+    const unsigned ey = pack >> 16;
+    if (stage == WF_IDLE) {
+        S.rlist[atomicAdd(&S.n_rlist, 1)] = (unsigned short)t;
+        return;
+    }
     float o[3], d[3];
     IaMarcher m;
     float sdf_prev = 0, cs = 0, ce = 0, ts = 0, te = 0, trans = 0, cdf_prev = 0, cdf_next = 0, cdf_u = 0;
@@ -471,192 +546,210 @@ __device__ __forceinline__ void wf_advance_slot(const IaFrame& p, P& pol, WfShar
     bool pending = false;
     float sdf_cur = 0, Tfin = 1.0f;
     const float cdf_step_size = (1.0f - 1.0 / 5) / 4;
-    bool active = stage != WF_IDLE;
-    if (active) {
-        // ---- min SDF over the kept roots of the previous query (snarf_deformer.py:242-259)
-        unsigned keep = S.qmask[t];
-        float sdf = 1e5f;
-        int best = -1;
-        while (keep) {
-            int c = __ffs(keep) - 1;
-            keep &= keep - 1;
-            float s = S.csdf[t * IA_N_INIT + c];
-            if (s < sdf) { sdf = s; best = c; }
-        }
-#pragma unroll
-        for (int k = 0; k < 3; k++) { o[k] = S.st[WS_O + k][t]; d[k] = S.st[WS_D + k][t]; }
-        wf_load_marcher(S, t, m, p.sec_step);
-        ts = S.st[WS_TS][t]; te = S.st[WS_TE][t];
-        if (stage == WF_FIRST) {
-            sdf_prev = sdf; cs = ts; ce = te;
-            stage = WF_SEARCH;
-            action = WF_ACT_NEXT;
-        } else if (stage == WF_SEARCH) {
-            sdf_prev = S.st[WS_SDFPREV][t];
-            if (sdf_prev >= 0 && sdf < 0) {
-                cs = S.st[WS_CS][t]; ce = S.st[WS_CE][t];
-                sdf_cur = sdf;
-                pending = true;  // (ts, te, sdf_cur) is the already-queried interval after the crossing one
-                j = 0;
-                float a = ia_alpha(sdf_prev, ce - cs, p.beta);
-                float weight = a;
-                trans = 1.0f;
-                trans *= (1.0f - a);
-                cdf_prev = 0.0f; cdf_next = weight;
-                cdf_u = 1.0 / (2 * 5);
-                action = WF_ACT_CDF;
-            } else {
-                sdf_prev = sdf; cs = ts; ce = te;
-                action = WF_ACT_NEXT;
-            }
-        } else if (stage == WF_CDF) {
-            trans = S.st[WS_TRANS][t]; cdf_prev = S.st[WS_CDFPREV][t]; cdf_next = S.st[WS_CDFNEXT][t];
-            cdf_u = S.st[WS_CDFU][t];
-            cs = ts; ce = te;
-            float a = ia_alpha(sdf, ce - cs, p.beta);
-            float weight = trans * a;
-            trans *= (1.0f - a);
-            cdf_prev = cdf_next;
-            cdf_next += weight;
-            action = WF_ACT_CDF;
-        } else if (GI && stage == WF_GIWAIT) {
-            Tfin = S.st[WS_TRANS][t];
-            stage = WF_FINE;
-            action = WF_ACT_FINISH;
-        } else {  // WF_FINE
-            float Tacc = S.st[WS_TRANS][t], acc = S.st[WS_CDFPREV][t];
-            float s0 = S.st[WS_TPL + i][t], e0 = S.st[WS_TPL + i + 1][t];
-            float al = ia_alpha(sdf, e0 - s0, p.beta);
-            float w = Tacc * al;
-            Tacc *= (1.0f - al);
-            acc += w;
-            bool gi_pushed = false;
-            if (GI && best >= 0) {
-                // radiance at the arg-min root of this fine sample is added by the GI phase of this round
-                // (before the Broyden phase overwrites the slot's roots): ind += w * rgb
-                int gi = atomicAdd(&S.n_gitask, 1);
-                S.gitask[gi] = make_uint2((unsigned)t | ((unsigned)best << 16), __float_as_uint(w));
-                gi_pushed = true;
-            }
-            i++;
-            if (i + 1 < j) {
-                float s1 = S.st[WS_TPL + i][t], e1 = S.st[WS_TPL + i + 1][t];
-                float mid = (s1 + e1) / 2.0f;
-                S.st[WS_TRANS][t] = Tacc; S.st[WS_CDFPREV][t] = acc;
-                S.st[WS_PACK][t] = __uint_as_float((unsigned)WF_FINE | (j << 3) | (i << 6) | (entry.y << 16));
-                int idx = atomicAdd(&S.n_q, 1);
-                S.qlist[idx] = (unsigned short)t;
-                S.qmask[t] = 0;
-#pragma unroll
-                for (int k = 0; k < 3; k++) S.qx[k][t] = o[k] + d[k] * mid;
-                c_q++;
-                return;
-            }
-            Tfin = 1.0f - acc;
-            if (GI && gi_pushed) {
-                // the last fine sample's radiance arrives in this round's GI phase: finish next round
-                S.st[WS_TRANS][t] = Tfin;
-                S.st[WS_PACK][t] = __uint_as_float((unsigned)WF_GIWAIT | (j << 3) | (i << 6) | (entry.y << 16));
-                return;
-            }
-            action = WF_ACT_FINISH;
-        }
+    // ---- min SDF over the kept roots of the previous query (snarf_deformer.py:242-259)
+    unsigned keep = S.qmask[t];
+    float sdf = 1e5f;
+    int best = -1;
+    while (keep) {
+        int c = __ffs(keep) - 1;
+        keep &= keep - 1;
+        float s = S.csdf[t * IA_N_INIT + c];
+        if (s < sdf) { sdf = s; best = c; }
     }
+#pragma unroll
+    for (int k = 0; k < 3; k++) { o[k] = S.st[WS_O + k][t]; d[k] = S.st[WS_D + k][t]; }
+    wf_load_marcher(S, t, m, p.sec_step);
+    ts = S.st[WS_TS][t]; te = S.st[WS_TE][t];
+    if (stage == WF_FIRST) {
+        sdf_prev = sdf; cs = ts; ce = te;
+        stage = WF_SEARCH;
+        action = WF_ACT_NEXT;
+    } else if (stage == WF_SEARCH) {
+        sdf_prev = S.st[WS_SDFPREV][t];
+        if (sdf_prev >= 0 && sdf < 0) {
+            cs = S.st[WS_CS][t]; ce = S.st[WS_CE][t];
+            sdf_cur = sdf;
+            pending = true;  // (ts, te, sdf_cur) is the already-queried interval after the crossing one
+            j = 0;
+            float a = ia_alpha(sdf_prev, ce - cs, p.beta);
+            float weight = a;
+            trans = 1.0f;
+            trans *= (1.0f - a);
+            cdf_prev = 0.0f; cdf_next = weight;
+            cdf_u = 1.0 / (2 * 5);
+            action = WF_ACT_CDF;
+        } else {
+            sdf_prev = sdf; cs = ts; ce = te;
+            action = WF_ACT_NEXT;
+        }
+    } else if (stage == WF_CDF) {
+        trans = S.st[WS_TRANS][t]; cdf_prev = S.st[WS_CDFPREV][t]; cdf_next = S.st[WS_CDFNEXT][t];
+        cdf_u = S.st[WS_CDFU][t];
+        cs = ts; ce = te;
+        float a = ia_alpha(sdf, ce - cs, p.beta);
+        float weight = trans * a;
+        trans *= (1.0f - a);
+        cdf_prev = cdf_next;
+        cdf_next += weight;
+        action = WF_ACT_CDF;
+    } else if (GI && stage == WF_GIWAIT) {
+        Tfin = S.st[WS_TRANS][t];
+        stage = WF_FINE;
+        action = WF_ACT_FINISH;
+    } else {  // WF_FINE
+        float Tacc = S.st[WS_TRANS][t], acc = S.st[WS_CDFPREV][t];
+        float s0 = S.st[WS_TPL + i][t], e0 = S.st[WS_TPL + i + 1][t];
+        float al = ia_alpha(sdf, e0 - s0, p.beta);
+        float w = Tacc * al;
+        Tacc *= (1.0f - al);
+        acc += w;
+        bool gi_pushed = false;
+        if (GI && best >= 0) {
+            // radiance at the arg-min root of this fine sample is added by the GI phase of this round
+            // (before the Broyden phase overwrites the slot's roots): ind += w * rgb
+            int gi = atomicAdd(&S.n_gitask, 1);
+            S.gitask[gi] = make_uint2((unsigned)t | ((unsigned)best << 16), __float_as_uint(w));
+            gi_pushed = true;
+        }
+        i++;
+        if (i + 1 < j) {
+            float s1 = S.st[WS_TPL + i][t], e1 = S.st[WS_TPL + i + 1][t];
+            float mid = (s1 + e1) / 2.0f;
+            S.st[WS_TRANS][t] = Tacc; S.st[WS_CDFPREV][t] = acc;
+            S.st[WS_PACK][t] = __uint_as_float((unsigned)WF_FINE | (j << 3) | (i << 6) | (ey << 16));
+            int idx = atomicAdd(&S.n_q, 1);
+            S.qlist[idx] = (unsigned short)t;
+            S.qmask[t] = 0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) S.qx[k][t] = o[k] + d[k] * mid;
+            c_q++;
+            return;
+        }
+        Tfin = 1.0f - acc;
+        if (GI && gi_pushed) {
+            // the last fine sample's radiance arrives in this round's GI phase: finish next round
+            S.st[WS_TRANS][t] = Tfin;
+            S.st[WS_PACK][t] = __uint_as_float((unsigned)WF_GIWAIT | (j << 3) | (i << 6) | (ey << 16));
+            return;
+        }
+        action = WF_ACT_FINISH;
+    }
+    // ---- run the state machine until it needs an SDF or the ray is finished
     bool have_q = false;
     float tq = 0.f;
-    for (int tries = 0;;) {
-        if (!active) {
-            if (tries >= 4) break;
-            int h = atomicAdd(&S.ring_head, 1);
-            if (h >= ring_tail) { atomicSub(&S.ring_head, 1); break; }
-            tries++;
-            entry = S.ring[h & (WF_QCAP - 1)];
-            pol.init(entry, o, d);
-            m.init(p, o, d, p.sec_near, p.sec_far, p.sec_step);
-            stage = WF_FIRST;
-            action = WF_ACT_NEXT;
-            active = true;
-            j = 0; i = 0;
-            c_rays++;
+    for (;;) {
+        if (action == WF_ACT_NEXT) {
+            bool cont;
+            if (m.next(p.occ_bits, p.occ_res, ts, te, cont)) { tq = ts; have_q = true; break; }
+            if (stage == WF_CDF) { action = WF_ACT_FINE_START; continue; }
+            Tfin = 1.0f;  // no crossing: fully visible
+            action = WF_ACT_FINISH;
+            continue;
         }
-        // ---- run the state machine until it needs an SDF or the ray is finished
-        for (;;) {
-            if (action == WF_ACT_NEXT) {
-                bool cont;
-                if (m.next(p.occ_bits, p.occ_res, ts, te, cont)) { tq = ts; have_q = true; break; }
-                if (stage == WF_CDF) { action = WF_ACT_FINE_START; continue; }
-                Tfin = 1.0f;  // no crossing: fully visible
-                action = WF_ACT_FINISH;
-                continue;
-            }
-            if (action == WF_ACT_CDF) {
-                bool need_next = false;
-                while (j < 5) {
-                    if (cdf_u < cdf_next) {
-                        float scaling = (ce - cs) / (cdf_next - cdf_prev);
-                        float tt = (cdf_u - cdf_prev) * scaling + cs;
-                        S.st[WS_TPL + j][t] = tt;
-                        cdf_u += cdf_step_size;
-                        j += 1;
-                    } else if (pending) {
-                        cs = ts; ce = te;
-                        pending = false;
-                        float a = ia_alpha(sdf_cur, ce - cs, p.beta);
-                        float weight = trans * a;
-                        trans *= (1.0f - a);
-                        cdf_prev = cdf_next;
-                        cdf_next += weight;
-                    } else {
-                        need_next = true;
-                        break;
-                    }
-                }
-                stage = WF_CDF;
-                action = need_next ? WF_ACT_NEXT : WF_ACT_FINE_START;
-                continue;
-            }
-            if (action == WF_ACT_FINE_START) {
-                i = 0;
-                if (j >= 2) {
-                    float s1 = S.st[WS_TPL][t], e1 = S.st[WS_TPL + 1][t];
-                    tq = (s1 + e1) / 2.0f;
-                    trans = 1.0f;      // Tacc
-                    cdf_prev = 0.0f;   // acc
-                    if (GI) { S.st[WS_IND][t] = 0.f; S.st[WS_IND + 1][t] = 0.f; S.st[WS_IND + 2][t] = 0.f; }
-                    stage = WF_FINE;
-                    have_q = true;
+        if (action == WF_ACT_CDF) {
+            bool need_next = false;
+            while (j < 5) {
+                if (cdf_u < cdf_next) {
+                    float scaling = (ce - cs) / (cdf_next - cdf_prev);
+                    float tt = (cdf_u - cdf_prev) * scaling + cs;
+                    S.st[WS_TPL + j][t] = tt;
+                    cdf_u += cdf_step_size;
+                    j += 1;
+                } else if (pending) {
+                    cs = ts; ce = te;
+                    pending = false;
+                    float a = ia_alpha(sdf_cur, ce - cs, p.beta);
+                    float weight = trans * a;
+                    trans *= (1.0f - a);
+                    cdf_prev = cdf_next;
+                    cdf_next += weight;
+                } else {
+                    need_next = true;
                     break;
                 }
-                Tfin = 1.0f;
-                action = WF_ACT_FINISH;
-                continue;
             }
-            // WF_ACT_FINISH
-            {
-                float ind[3] = {0.f, 0.f, 0.f};
-                if (GI && stage == WF_FINE) { ind[0] = S.st[WS_IND][t]; ind[1] = S.st[WS_IND + 1][t]; ind[2] = S.st[WS_IND + 2][t]; }
-                pol.finish(entry, Tfin, ind, d);
-            }
-            stage = WF_IDLE;
-            active = false;
-            break;
+            stage = WF_CDF;
+            action = need_next ? WF_ACT_NEXT : WF_ACT_FINE_START;
+            continue;
         }
-        if (have_q) break;
+        if (action == WF_ACT_FINE_START) {
+            i = 0;
+            if (j >= 2) {
+                float s1 = S.st[WS_TPL][t], e1 = S.st[WS_TPL + 1][t];
+                tq = (s1 + e1) / 2.0f;
+                trans = 1.0f;      // Tacc
+                cdf_prev = 0.0f;   // acc
+                if (GI) { S.st[WS_IND][t] = 0.f; S.st[WS_IND + 1][t] = 0.f; S.st[WS_IND + 2][t] = 0.f; }
+                stage = WF_FINE;
+                have_q = true;
+                break;
+            }
+            Tfin = 1.0f;
+            action = WF_ACT_FINISH;
+            continue;
+        }
+        // WF_ACT_FINISH: the estimator runs in the refill pass; remember the transmittance and whether the slot carries
+        // indirect radiance (stage FINE)
+        S.st[WS_TRANS][t] = Tfin;
+        S.st[WS_PACK][t] = __uint_as_float((unsigned)(GI && stage == WF_FINE ? WF_DONE_IND : WF_DONE) | (ey << 16));
+        S.rlist[atomicAdd(&S.n_rlist, 1)] = (unsigned short)t;
+        return;
     }
-    if (have_q) {
+    // have_q
 #pragma unroll
-        for (int k = 0; k < 3; k++) { S.st[WS_O + k][t] = o[k]; S.st[WS_D + k][t] = d[k]; S.qx[k][t] = o[k] + d[k] * tq; }
-        S.st[WS_ID][t] = __uint_as_float(entry.x);
-        wf_store_marcher(S, t, m);
-        S.st[WS_SDFPREV][t] = sdf_prev; S.st[WS_CS][t] = cs; S.st[WS_CE][t] = ce;
-        S.st[WS_TS][t] = ts; S.st[WS_TE][t] = te;
-        S.st[WS_TRANS][t] = trans; S.st[WS_CDFPREV][t] = cdf_prev; S.st[WS_CDFNEXT][t] = cdf_next; S.st[WS_CDFU][t] = cdf_u;
-        int idx = atomicAdd(&S.n_q, 1);
-        S.qlist[idx] = (unsigned short)t;
-        S.qmask[t] = 0;
-        c_q++;
+    for (int k = 0; k < 3; k++) S.qx[k][t] = o[k] + d[k] * tq;
+    wf_store_marcher(S, t, m);
+    S.st[WS_SDFPREV][t] = sdf_prev; S.st[WS_CS][t] = cs; S.st[WS_CE][t] = ce;
+    S.st[WS_TS][t] = ts; S.st[WS_TE][t] = te;
+    S.st[WS_TRANS][t] = trans; S.st[WS_CDFPREV][t] = cdf_prev; S.st[WS_CDFNEXT][t] = cdf_next; S.st[WS_CDFU][t] = cdf_u;
+    int idx = atomicAdd(&S.n_q, 1);
+    S.qlist[idx] = (unsigned short)t;
+    S.qmask[t] = 0;
+    c_q++;
+    S.st[WS_PACK][t] = __uint_as_float((unsigned)stage | (j << 3) | (i << 6) | (ey << 16));
+}
+
+template <bool GI, class P>
+__device__ __forceinline__ void wf_advance_refill(const IaFrame& p, P& pol, WfShared& S, const int t, int ring_tail,
+                                                  unsigned& c_q, unsigned& c_rays) {
+    const unsigned pack = __float_as_uint(S.st[WS_PACK][t]);
+    const int stage0 = pack & 7u;
+    if (stage0 == WF_DONE || stage0 == WF_DONE_IND) {
+        const uint2 entry = make_uint2(__float_as_uint(S.st[WS_ID][t]), pack >> 16);
+        const float d[3] = {S.st[WS_D][t], S.st[WS_D + 1][t], S.st[WS_D + 2][t]};
+        float ind[3] = {0.f, 0.f, 0.f};
+        if (GI && stage0 == WF_DONE_IND) { ind[0] = S.st[WS_IND][t]; ind[1] = S.st[WS_IND + 1][t]; ind[2] = S.st[WS_IND + 2][t]; }
+        pol.finish(entry, S.st[WS_TRANS][t], ind, d);
     }
-    S.st[WS_PACK][t] = __uint_as_float((unsigned)stage | (j << 3) | (i << 6) | (entry.y << 16));
+    for (int tries = 0; tries < 4; tries++) {
+        int h = atomicAdd(&S.ring_head, 1);
+        if (h >= ring_tail) { atomicSub(&S.ring_head, 1); break; }
+        const uint2 entry = S.ring[h & (WF_QCAP - 1)];
+        float o[3], d[3];
+        pol.init(entry, o, d);
+        IaMarcher m;
+        m.init(p, o, d, p.sec_near, p.sec_far, p.sec_step);
+        c_rays++;
+        float ts, te;
+        bool cont;
+        if (m.next(p.occ_bits, p.occ_res, ts, te, cont)) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) { S.st[WS_O + k][t] = o[k]; S.st[WS_D + k][t] = d[k]; S.qx[k][t] = o[k] + d[k] * ts; }
+            S.st[WS_ID][t] = __uint_as_float(entry.x);
+            wf_store_marcher(S, t, m);
+            S.st[WS_TS][t] = ts; S.st[WS_TE][t] = te;
+            int idx = atomicAdd(&S.n_q, 1);
+            S.qlist[idx] = (unsigned short)t;
+            S.qmask[t] = 0;
+            c_q++;
+            S.st[WS_PACK][t] = __uint_as_float((unsigned)WF_FIRST | (entry.y << 16));
+            return;
+        }
+        // the ray meets no occupied cell: fully visible, no indirect radiance
+        const float zero[3] = {0.f, 0.f, 0.f};
+        pol.finish(entry, 1.0f, zero, d);
+    }
+    S.st[WS_PACK][t] = __uint_as_float((unsigned)WF_IDLE);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -685,7 +778,7 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
     for (int i = tid * 4; i < n_w; i += blockDim.x * 4)
         *reinterpret_cast<float4*>(S.w + i) = __ldg(reinterpret_cast<const float4*>(p.mlp + i));
     ia_stage_bfrag(S.w1f, IA_GEO_KSTEPS, 8, [&](int k, int n) { return ia_geo_w1(p.mlp, k, n); });
-    for (int i = tid; i < (int)(blockDim.x >> 5) * 16 * IA_GEO_LD; i += blockDim.x) S.xs[i] = 0.f;
+    for (int i = tid; i < (int)(blockDim.x >> 5) * WF_MMA_ROWS * IA_GEO_LD; i += blockDim.x) S.xs[i] = 0.f;
     if (tid < IA_N_INIT * 12) S.tfs13[tid] = p.tfs[p.init_bones[tid / 12]][tid % 12];
     if (tid < IA_N_LEVELS) S.lvl[tid] = ia_level(p, tid);
     for (int t = tid; t < WF_R; t += blockDim.x) S.st[WS_PACK][t] = __uint_as_float(0u);
@@ -712,12 +805,15 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
             __syncthreads();
         }
         __syncthreads();
-        if (tid == 0) { S.n_q = 0; S.n_gtask = 0; S.task_next = 0; S.n_btask = 0; S.n_gitask = 0; }
+        if (tid == 0) { S.n_q = 0; S.n_gtask = 0; S.task_next = 0; S.n_btask = 0; S.n_gitask = 0; S.n_rlist = 0; }
         const int ring_tail = S.ring_tail;
         __syncthreads();
         {
             unsigned c_q = 0, c_rays = 0;
-            for (int t = tid; t < WF_R; t += blockDim.x) wf_advance_slot<GI>(p, pol, S, t, ring_tail, c_q, c_rays);
+            for (int t = tid; t < WF_R; t += blockDim.x) wf_advance_consume<GI>(p, pol, S, t, c_q);
+            __syncthreads();
+            const int n_r = S.n_rlist;
+            for (int k = tid; k < n_r; k += blockDim.x) wf_advance_refill<GI>(p, pol, S, S.rlist[k], ring_tail, c_q, c_rays);
             wf_count(S, WF_C_Q, c_q);
             wf_count(S, WF_C_RAYS, c_rays);
         }
@@ -738,6 +834,10 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
             if (S.ring_tail - S.ring_head <= 0 && !S.more_tiles) break;
             continue;
         }
+#if WF_QSORT
+        wf_sort_phase(p, S, n_q);
+        __syncthreads();
+#endif
         wf_prune_phase(p, S, n_q);
         __syncthreads();
         wf_broyden_phase(p, S);
@@ -796,6 +896,12 @@ struct WfShadePolicy {
     float* vis;    // uniform_light: [n_rays] visibility accumulator
     const float* bg_rgb;  // [n_rays][3] radiance of a background-assigned sample (background colour or envmap)
 
+    static constexpr bool light_major = WF_LIGHT_MAJOR && MODE <= IA_MODE_UNIFORM_LIGHT;
+    int n_hit;     // hit rays of the frame (light-major: position e = kk * n_hit + slot)
+    // hit-ray slot of a ring entry (e.x = position in the resampled streams, e.y = light index in the light-table modes)
+    __device__ __forceinline__ int slot_of(const uint2 e) const {
+        return light_major ? (int)(e.x - e.y * (unsigned)n_hit) : (int)(e.x / (unsigned)spp);
+    }
     __device__ __forceinline__ long long n_items() const { return n_total; }
     __device__ __forceinline__ int* tile_counter() const { return &work[IA_W_TILE_NEXT]; }
     __device__ __forceinline__ int tile_items() const { return mode == IA_MODE_MIS ? WF_FEED / 2 : WF_FEED; }
@@ -806,7 +912,10 @@ struct WfShadePolicy {
         e = make_uint2(0, 0);
         if (s >= n_total) return false;
         const unsigned su = (unsigned)s;
-        const int slot = (int)(su / (unsigned)spp), j = (int)(su % (unsigned)spp);
+        int slot, j;
+        uint32_t kk = 0;
+        if (light_major) { kk = su / (unsigned)n_hit; slot = (int)(su - kk * (unsigned)n_hit); j = 0; }
+        else { slot = (int)(su / (unsigned)spp); j = (int)(su % (unsigned)spp); }
         const int src = rs_src[s];
         if (src < 0) {
             // background-assigned shading sample (models/intrinsic_avatar.py:1319-1341)
@@ -825,8 +934,10 @@ struct WfShadePolicy {
             return true;  // no cosine mask: every foreground sample traces its sampled direction(s)
         }
         const float* n = samples[src].n;
-        uint32_t key = ia_pixel_key(seed, (uint64_t)(ray_index_base + hit_rays[slot]));
-        uint32_t kk = ia_permute((uint32_t)j, (uint32_t)spp, key);
+        if (!light_major) {
+            uint32_t key = ia_pixel_key(seed, (uint64_t)(ray_index_base + hit_rays[slot]));
+            kk = ia_permute((uint32_t)j, (uint32_t)spp, key);
+        }
         const float* wo = light_dir_s + kk * 3;
         float cosv = n[0] * wo[0] + n[1] * wo[1] + n[2] * wo[2];
         e = make_uint2(su, kk);
@@ -844,7 +955,7 @@ struct WfShadePolicy {
     }
 
     __device__ __forceinline__ void init(const uint2 e, float o[3], float d[3]) const {
-        const int slot = (int)(e.x / (unsigned)spp);
+        const int slot = slot_of(e);
         const float t = rs_t[e.x];
         const float* od = hit_od + (size_t)slot * 8;
 #pragma unroll
@@ -871,7 +982,7 @@ struct WfShadePolicy {
     }
 
     __device__ __forceinline__ void finish(const uint2 e, float T, const float ind[3], const float d[3]) const {
-        const int slot = (int)(e.x / (unsigned)spp);
+        const int slot = slot_of(e);
         const IaSample sm = samples[rs_src[e.x]];
         const float w = rs_w[e.x];
         const float* od = hit_od + (size_t)slot * 8;
@@ -941,7 +1052,7 @@ struct WfShadePolicy {
 };
 
 #define WF_SMEM_BYTES(GI) (((sizeof(WfShared) + 15) & ~(size_t)15) + (((GI) && WF_GI_WEIGHTS_SMEM) ? IA_RAD_END : IA_GEO_END) * sizeof(float) + \
-                           IA_GEO_KSTEPS * 8 * 32 * sizeof(float4) + (WF_THREADS / 32) * 16 * IA_GEO_LD * sizeof(float))
+                           IA_GEO_KSTEPS * 8 * 32 * sizeof(float4) + (WF_THREADS / 32) * WF_MMA_ROWS * IA_GEO_LD * sizeof(float))
 
 template <bool GI, int MODE>
 __global__ void __launch_bounds__(WF_THREADS, WF_CTAS_PER_SM) k_shade_wf(const __grid_constant__ IaFrame p, WfShadePolicy<MODE> pol,
@@ -950,7 +1061,8 @@ __global__ void __launch_bounds__(WF_THREADS, WF_CTAS_PER_SM) k_shade_wf(const _
     extern __shared__ __align__(16) unsigned char wf_smem[];
     WfShared& S = *reinterpret_cast<WfShared*>(wf_smem);
     pol.p = &p;
-    pol.n_total = (long long)pol.work[IA_W_NHIT] * pol.spp;
+    pol.n_hit = pol.work[IA_W_NHIT];
+    pol.n_total = (long long)pol.n_hit * pol.spp;
     pol.gi = GI ? 1 : 0;
     wf_run<GI>(p, pol, S, scratch, counters);
 }

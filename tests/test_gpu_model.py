@@ -99,7 +99,7 @@ def test_resample_light_false_keeps_the_first_light(scene, built):
     dark = {**b, "hdri": b["hdri"] * 0.0}
     model.prepare(dark)
     c = model(b["rays"])["comp_rgb_phys"]
-    assert float((a - c).abs().max()) < 1e-5
+    assert float((a - c).abs().max()) < 1e-4 * float(a.abs().max())      # (accumulation order into a pixel is not fixed)
 
 
 def test_checkpoint_round_trip_as_a_submodule(scene, built):
@@ -113,7 +113,7 @@ def test_checkpoint_round_trip_as_a_submodule(scene, built):
             super().__init__()
             self.model = m
     system = System(model)
-    sd = system.state_dict()
+    sd = {k: v.clone() for k, v in system.state_dict().items()}     # (state_dict() aliases the live parameters)
     keys = [k for k in sd if k.startswith("model.")]
     from intrinsicavatar_b200.weights import random_state_dict_shapes
     assert sorted(k[len("model."):] for k in keys) == sorted(random_state_dict_shapes())
@@ -142,9 +142,10 @@ def test_render_image_surfaces(scene, built):
     model, cfg, betas = built
     H = 20
     b = _batch(scene, betas, H)
-    prim = model.render_image(b, b["rays"], H, H)
+    jitter = torch.rand(64 ** 3, 3, 3, device="cuda")      # the occupancy grid's jitter, shared by both renders
+    prim = model.render_image(b, b["rays"], H, H, jitter=jitter)
     assert prim["comp_rgb"].shape == (H, H, 3) and prim["opacity"].shape == (H, H, 1)
-    full = model.render_image_relight(b, b["rays"], H, H)
+    full = model.render_image_relight(b, b["rays"], H, H, jitter=jitter)
     assert full["comp_rgb_phys"].shape == (H, H, 3)
     # the primary buffers do not depend on the shading stage
     assert torch.allclose(prim["comp_albedo"], full["comp_albedo"], atol=1e-6)
