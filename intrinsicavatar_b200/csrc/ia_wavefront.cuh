@@ -43,11 +43,16 @@
 #define WF_QCAP 8192
 #endif
 #define WF_NST 36      // state words per ray
+// prune phase: 32-pair trips per warp (its share of the 13 x WF_R pairs, rounded up to 32)
+#define WF_PRUNE_ITERS (((WF_R * 13 + (WF_THREADS / 32) - 1) / (WF_THREADS / 32) + 31) / 32)
 #ifndef WF_LIGHT_MAJOR
-#define WF_LIGHT_MAJOR 1   // light-table modes: shading samples are stored and fed light-major -- for each light direction all
+#define WF_LIGHT_MAJOR 0   // light-table modes: shading samples are stored and fed light-major -- for each light direction all
 #endif                     // hit pixels in ray order (k_resample) -- so that the rays in flight are bundles of parallel rays from
                            // neighbouring surface points and, with WF_QSORT, neighbouring lanes gather the same voxel / hash cells.
                            // 0: pixel-major (all samples of a pixel, then the next pixel).  Only the processing order differs.
+                           // Measured at 512^2 x 1024 spp, GI on, frames 2-4: 1036 ms pixel-major, 1066 ms (+ 6 ms of scattered writes in
+                           // k_resample) light-major: a voxel cell is shared by 2-4 live rays either way, and the gathers only get
+                           // cheaper from ~8 lanes per cell on (scripts/gather_microbench.cu).
 #ifndef WF_QSORT
 #define WF_QSORT 1     // 1: the pending queries of a round are sorted along a Morton curve over their posed position before the
 #endif                 // task lists are built: neighbouring lanes of the Broyden and geometry phases then touch the same voxel
@@ -112,6 +117,7 @@ struct WfShared {
     float qx[3][WF_R];
     unsigned int qmask[WF_R];
     unsigned short qlist[WF_R];
+    unsigned pballot[(WF_THREADS / 32) * WF_PRUNE_ITERS];   // prune phase: live ballots of every warp's pair range
     unsigned short rlist[WF_R];   // advance phase: slots to finish and / or refill
     int n_rlist;
 #if WF_QSORT
@@ -241,16 +247,22 @@ __device__ __forceinline__ void wf_sort_phase(const IaFrame& p, WfShared& S, int
 // outside the voxel grid are exactly invalid (ia_all_corners_oob) and are dropped; the others are
 // compacted, bone-major, into the Broyden task list.
 __device__ __forceinline__ void wf_prune_phase(const IaFrame& p, WfShared& S, int n_q) {
+    // Every warp owns a contiguous range of the bone-major pair list: pass 1 tests its pairs and keeps one ballot per 32 of
+    // them, ONE atomic reserves the warp's stretch of the task list, pass 2 writes it.  (Round 1 took one shared atomic per
+    // 32 pairs: 416 serialised atomics on one address per round.)
     unsigned c_skip = 0;
     const int n_pairs = n_q * IA_N_INIT;
-    const int lane = threadIdx.x & 31;
-    for (int k0 = (threadIdx.x & ~31); k0 < n_pairs; k0 += blockDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int per = ((n_pairs + n_warps - 1) / n_warps + 31) & ~31;      // pairs per warp, a multiple of 32
+    const int k_begin = warp * per, k_end = min(n_pairs, k_begin + per);
+    unsigned* ballots = S.pballot + warp * WF_PRUNE_ITERS;
+    int n_live = 0;
+    for (int k0 = k_begin, it = 0; k0 < k_end; k0 += 32, it++) {
         const int k = k0 + lane;
         bool live = false;
-        int q = 0, c = 0;
-        if (k < n_pairs) {
-            c = k / n_q;
-            q = S.qlist[k - c * n_q];
+        if (k < k_end) {
+            const int c = k / n_q;
+            const int q = S.qlist[k - c * n_q];
             const float xd0 = S.qx[0][q], xd1 = S.qx[1][q], xd2 = S.qx[2][q];
             const float* T = S.tfs13 + c * 12;
             float d0 = xd0 - T[3], d1 = xd1 - T[7], d2 = xd2 - T[11];
@@ -261,10 +273,22 @@ __device__ __forceinline__ void wf_prune_phase(const IaFrame& p, WfShared& S, in
             if (!live) c_skip++;
         }
         const unsigned b = __ballot_sync(0xffffffffu, live);
-        int base = 0;
-        if (lane == 0 && b) base = atomicAdd(&S.n_btask, __popc(b));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (live) S.btask[base + __popc(b & ((1u << lane) - 1u))] = (unsigned short)(q * 16 + c);
+        if (lane == 0) ballots[it] = b;
+        n_live += __popc(b);
+    }
+    int base = 0;
+    if (lane == 0 && n_live) base = atomicAdd(&S.n_btask, n_live);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    __syncwarp();
+    for (int k0 = k_begin, it = 0; k0 < k_end; k0 += 32, it++) {
+        const unsigned b = ballots[it];
+        if ((b >> lane) & 1u) {
+            const int k = k0 + lane;
+            const int c = k / n_q;
+            const int q = S.qlist[k - c * n_q];
+            S.btask[base + __popc(b & ((1u << lane) - 1u))] = (unsigned short)(q * 16 + c);
+        }
+        base += __popc(b);
     }
     wf_count(S, WF_C_SKIP, c_skip);
 }
