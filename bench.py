@@ -17,9 +17,11 @@ The default run also times configs[1] and configs[2] for three steps each and re
 
 Metric: shaded samples/s = (primary rays x spp) / time, whole job over all ranks.  "weak" scaling: one frame per rank
 per step, no data-path collective.  N > 1 is BASELINE configs[4]: the frames of the animation sequence are sharded over
-the ranks -- step s renders the N consecutive frames [sN, sN + N) of a 16-frame AIST sequence, rank assignment rotating by
-one per step (parallel.frame_of_step) -- and every finished frame is delivered to rank 0 inside the timed region
+the ranks -- step s covers N consecutive entries of a 16-frame AIST sequence -- and every finished frame is delivered to
+rank 0 inside the timed region
 (parallel.FrameCollector: stream-ordered peer copies over NVLink, or one asynchronous NCCL gather per step).
+Frame costs differ by 2x (FRAME_COST_MS): the sequence is walked in an order that alternates expensive and cheap frames and
+the frames of a run are dealt to the ranks longest-first (parallel.assign_frames).
   value : inputs resident in HBM when the timed region starts (rays, envmap on device)
   e2e   : through IntrinsicAvatarModel.prepare/forward with HOST rays + HOST hdri, H2D and the D2H of
           every output buffer inside the timed region
@@ -42,6 +44,20 @@ SCENE_AABB = [-1.25, -1.55, -1.25, 1.25, 0.95, 1.25]
 METRIC = "shaded_samples_per_sec"
 UNIT = "samples/s"
 N_SEQ_FRAMES = 16      # frames of the AIST sequence one pass of the multi-GPU job covers
+# Measured cost of every frame of the sequence (ms per frame, configs[3], 1 x B200, profiles/r2_bench_frames16.json): the
+# body turns and its limbs occlude each other differently from frame to frame -- 553 .. 1098 ms.  Used (a) to put the
+# sequence in an order whose every window is representative (expensive and cheap frames alternate), so that a short run
+# does not time an unrepresentative stretch, and (b) as the estimate for the longest-first assignment of a step batch's
+# frames to the ranks (parallel.assign_frames).
+FRAME_COST_MS = [1022.3, 1059.1, 1090.8, 1098.4, 1052.8, 954.1, 822.0, 694.3, 657.5, 642.0, 632.6, 608.1, 552.8, 587.9, 722.5, 737.1]
+
+
+def sequence_order():
+    by_cost = sorted(range(N_SEQ_FRAMES), key=lambda f: -FRAME_COST_MS[f])
+    order = []
+    for i in range(N_SEQ_FRAMES // 2):
+        order += [by_cost[i], by_cost[N_SEQ_FRAMES - 1 - i]]
+    return order
 
 # Algorithmic bytes per unit of work.  SURVEY.md 8(d) fixes them in the B200 DESIGN formats (fp16 channels-last):
 #   voxel_J trilinear fetch 8 corners x 12 x 2 B = 192 B   per Broyden fetch
@@ -259,9 +275,10 @@ def workload_config(args, world):
             f"global_illumination={'true' if args.gi else 'false'}")
     return {
         "workload": f"BASELINE configs[{args.config}]: {args.res}x{args.res} {what}, prepare+forward per step",
-        "frame_source": (f"AIST animation sequence, frames 0..{N_SEQ_FRAMES - 1}: step s renders frames [s*N, s*N+N) mod "
-                         f"{N_SEQ_FRAMES} on the N ranks (assignment rotating by one rank per step); synthetic 24-joint body, "
-                         "random-init hash grids + MLPs (seed 0), the reference's city.hdr at 1024x2048"),
+        "frame_source": (f"AIST animation sequence, frames 0..{N_SEQ_FRAMES - 1} in an order that alternates expensive and cheap "
+                         f"frames ({sequence_order()}; per-frame cost 553..1098 ms): step s covers entries [s*N, s*N+N) of it, the "
+                         "frames of the timed steps are dealt to the N ranks longest-first (parallel.assign_frames); synthetic "
+                         "24-joint body, random-init hash grids + MLPs (seed 0), the reference's city.hdr at 1024x2048"),
         "rays_per_frame": args.res * args.res, "spp": 1 if args.primary_only else args.spp, "gi": bool(args.gi),
         "parallelism": f"frame-per-gpu x{world}",
         "l2": "flushed between steps (256 MiB write) and per-step sample streams (3.2 GB at 512^2 x 1024) exceed L2",
@@ -391,10 +408,21 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     collector = parallel.FrameCollector(n_rays, 2, dev, transport=args.transport) if world > 1 else None
 
+    # Frame schedule.  The job renders the sequence in `sequence_order()`: step s covers its entries [s N, s N + N).  The
+    # frames of the timed steps (and, separately, of the warm-up steps) are dealt to the ranks longest-first, the same
+    # number to every rank; each rank renders its share most expensive first.  N = 1: the sequence in order.
+    order = sequence_order()
+    costs = {f: FRAME_COST_MS[f] for f in range(N_SEQ_FRAMES)}
+
+    def share(first_step, n_steps):
+        seq = [order[i % N_SEQ_FRAMES] for i in range(first_step * world, (first_step + n_steps) * world)]
+        if world == 1 or args.same_frame:
+            return seq[::world] if args.same_frame else seq
+        return parallel.assign_frames(seq, costs, world)[rank]
+    schedule = {}
+
     def frame_of(step):
-        if args.same_frame:
-            return step % N_SEQ_FRAMES
-        return parallel.frame_of_step(step, rank, world, N_SEQ_FRAMES)
+        return schedule[step]
 
     def barrier():
         if world > 1:
@@ -428,6 +456,9 @@ def main():
             if collector is not None:
                 collector.collect(step, parallel.pack_frame({k: out[k].to(dev, non_blocking=True) for k in parallel.FRAME_KEYS}
                                                             if e2e_arm else out))
+        schedule.clear()
+        schedule.update({s: f for s, f in enumerate(share(0, warmup))})
+        schedule.update({warmup + s: f for s, f in enumerate(share(warmup, steps))})
         for s in range(warmup):
             step_fn(s)
             flush.fill_(s & 0xFF)
@@ -507,7 +538,8 @@ def main():
         if world == 1 and stage_ms:
             per_frame = [sum(s[k] for k in ("setup", "primary", "resample", "shade", "composite") if s[k] >= 0) for s in stage_ms]
             line["frame_cost_spread_ms"] = {"min": min(per_frame), "max": max(per_frame),
-                                            "frames": [frame_of(args.warmup + s) for s in range(args.steps)]}
+                                            "frames": [frame_of(args.warmup + s) for s in range(args.steps)],
+                                            "ms": [round(v, 1) for v in per_frame]}
         if world > 1:
             line["frame_transport"] = collector.transport
         if other:

@@ -38,6 +38,25 @@ def frame_of_step(step: int, rank: int, world_size: int, n_frames: int) -> int:
     return (step * world_size + (rank + step) % world_size) % n_frames
 
 
+def assign_frames(frames: list[int], costs: dict, world_size: int) -> list[list[int]]:
+    """Static longest-first assignment of a batch of frames to ``world_size`` ranks, the same number of frames per rank
+    (len(frames) must be a multiple of world_size): frames in order of decreasing estimated cost, each to the rank with the
+    smallest sum so far that still has room (LPT with a cardinality bound), so that the per-rank sums of the estimates are
+    nearly equal.  ``costs[f]`` is any estimate proportional to the render time of frame f (here: measured ms of an earlier
+    pass over the sequence; in a deployment the hit-pixel count of the primary stage serves).  Deterministic: every rank
+    computes the same table, no communication.  Returns per rank the list of its frames, most expensive first."""
+    assert len(frames) % world_size == 0
+    per = len(frames) // world_size
+    order = sorted(range(len(frames)), key=lambda i: (-float(costs[frames[i]]), i))
+    out = [[] for _ in range(world_size)]
+    sums = [0.0] * world_size
+    for i in order:
+        r = min((r for r in range(world_size) if len(out[r]) < per), key=lambda r: (sums[r], r))
+        out[r].append(frames[i])
+        sums[r] += float(costs[frames[i]])
+    return out
+
+
 def pack_frame(out: dict) -> torch.Tensor:
     """[n_pix, 16] float32 image-buffer block of one frame."""
     return torch.cat([out[k].float() for k in FRAME_KEYS], dim=-1).contiguous()

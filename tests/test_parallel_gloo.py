@@ -104,3 +104,16 @@ def test_frame_of_step_covers_every_frame_once_per_pass_and_rotates():
             # over world passes' worth of steps a rank sees every residue class
             res = {parallel.frame_of_step(s, 0, world, n_frames) % world for s in range(world)}
             assert res == set(range(world))
+
+
+def test_assign_frames_longest_first_balances_the_ranks():
+    costs = {f: c for f, c in enumerate([1022, 1059, 1091, 1098, 1053, 954, 822, 694, 658, 642, 633, 608, 553, 588, 723, 737])}
+    frames = [f % 16 for f in range(40)]                       # 5 steps x 8 ranks
+    per_rank = parallel.assign_frames(frames, costs, 8)
+    assert sorted(f for r in per_rank for f in r) == sorted(frames)          # every frame exactly as often as asked
+    assert all(len(r) == 5 for r in per_rank)
+    sums = [sum(costs[f] for f in r) for r in per_rank]
+    assert max(sums) / (sum(sums) / 8) < 1.02                   # (round robin f -> f mod N: 1.07 on this sequence)
+    rr = [sum(costs[f] for f in frames[r::8]) for r in range(8)]
+    assert max(rr) / (sum(rr) / 8) > 1.05
+    assert parallel.assign_frames([3, 1, 2], costs, 1) == [[3, 2, 1]]
