@@ -548,6 +548,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
     if world > 1:
+        collector.close()
         dist.barrier()
         dist.destroy_process_group()
 

@@ -64,6 +64,25 @@ int ia_set_fields(ia_ctx* ctx, const float* d_geo_hash, const float* d_rad_hash,
 int ia_set_lbs_voxels(ia_ctx* ctx, const float* d_lbs_voxel, int D, int H, int W,
                       const float* h_offset_kernel3, const float* h_scale_kernel3, void* stream);
 
+/* Subject set-up on the device.
+ * ia_smpl_lbs: SMPL linear blend skinning for one pose -- lbs() (models/deformers/smplx/lbs.py:152-248: blend_shapes,
+ *   vertices2joints, batch_rodrigues, pose blend shapes, batch_rigid_transform :345-401, skinning) and the translation
+ *   handling of SMPL.forward (models/deformers/smplx/body_models.py:342-358).  Device arrays fp32: v_template [V,3],
+ *   shapedirs [V,3,NB], posedirs [207, V*3] (the layout body_models.py:156-159 stores), J_regressor [24,V], lbs_weights
+ *   [V,24]; host: parents [24], betas [NB], pose [72] = global_orient + body_pose (axis-angle), transl [3].
+ *   Out (device): vertices [V,3], joints [24,3], A [24,4,4] (relative joint transforms, transl in the last column).
+ * ia_voxelize_lbs: the skinning-weight voxel grid of ForwardDeformer.switch_to_explicit + query_weights_smpl
+ *   (models/deformers/fast_snarf/deformer_torch.py:139-197, 234-253; pytorch3d knn_points, lib/pytorch3d/cuda/knn.cu:27-312):
+ *   K = 30 nearest vertices of every grid point, inverse-distance blend, 30 smoothing passes.  d_verts [V,3] canonical
+ *   vertices, d_weights [V,24]; out d_lbs_voxel [24, res/4, res, res] (the layout ia_set_lbs_voxels takes) and the
+ *   reference's offset_kernel / scale_kernel [3] on the host.  Both calls synchronise the stream (set-up, not per sample). */
+int ia_smpl_lbs(ia_ctx* ctx, const float* d_v_template, const float* d_shapedirs, const float* d_posedirs,
+                const float* d_J_regressor, const float* d_lbs_weights, const int32_t* h_parents, int V, int NB,
+                const float* h_betas, const float* h_pose72, const float* h_transl3, float* d_vertices, float* d_joints,
+                float* d_A, void* stream);
+int ia_voxelize_lbs(ia_ctx* ctx, const float* d_verts, const float* d_weights, int V, int resolution, float* d_lbs_voxel,
+                    float* h_offset_kernel3, float* h_scale_kernel3, void* stream);
+
 /* Per-frame pose: tfs [24,4,4], w2s [4,4] (SNARFDeformer.prepare_deformer, snarf_deformer.py:98-106)
  * and runs the voxel precompute (precompute_kernel, .../cuda/precompute/precompute.cu:22-103).       */
 int ia_set_pose(ia_ctx* ctx, const float* h_tfs, const float* h_w2s, void* stream);

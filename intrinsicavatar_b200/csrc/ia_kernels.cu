@@ -940,4 +940,74 @@ extern "C" int ia_set_light_uniform(ia_ctx* c, const float* d_env, int H, int W,
     return IA_OK;
 }
 
+// ================================================================================================
+// subject set-up on the device: SMPL linear blend skinning, skinning-weight voxelisation
+#include "ia_body.cuh"
+
+extern "C" int ia_smpl_lbs(ia_ctx* c, const float* d_v_template, const float* d_shapedirs, const float* d_posedirs,
+                           const float* d_J_regressor, const float* d_lbs_weights, const int32_t* h_parents, int V, int NB,
+                           const float* h_betas, const float* h_pose72, const float* h_transl3, float* d_vertices,
+                           float* d_joints, float* d_A, void* stream) {
+    IA_REQUIRE(c && d_v_template && d_shapedirs && d_posedirs && d_J_regressor && d_lbs_weights && h_parents && h_betas && h_pose72 &&
+                   h_transl3 && d_vertices && d_joints && d_A, IA_EINVAL, "ia_smpl_lbs: NULL argument");
+    IA_REQUIRE(V > 0 && NB >= 0 && NB <= 300, IA_EINVAL, "ia_smpl_lbs: bad sizes");
+    IA_CHECK_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // scratch: v_shaped [V*3] | joints_rest [72] | pose_feature [207] | A_rel [384] | betas [NB] | pose [72] | transl [3] | parents [24]
+    const size_t n_f = (size_t)V * 3 + 72 + 208 + 384 + NB + 72 + 4;
+    float* w = nullptr;
+    IA_CHECK_CUDA(cudaMallocAsync((void**)&w, n_f * sizeof(float) + 24 * sizeof(int), st));
+    float *v_shaped = w, *joints_rest = w + (size_t)V * 3, *pose_feature = joints_rest + 72, *A_rel = pose_feature + 208,
+          *betas = A_rel + 384, *pose = betas + NB, *transl = pose + 72;
+    int* parents = reinterpret_cast<int*>(w + n_f);
+    if (NB) IA_CHECK_CUDA(cudaMemcpyAsync(betas, h_betas, NB * sizeof(float), cudaMemcpyHostToDevice, st));
+    IA_CHECK_CUDA(cudaMemcpyAsync(pose, h_pose72, 72 * sizeof(float), cudaMemcpyHostToDevice, st));
+    IA_CHECK_CUDA(cudaMemcpyAsync(transl, h_transl3, 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    IA_CHECK_CUDA(cudaMemcpyAsync(parents, h_parents, 24 * sizeof(int), cudaMemcpyHostToDevice, st));
+    k_lbs_shape<<<(V * 3 + 255) / 256, 256, 0, st>>>(d_v_template, d_shapedirs, betas, V, NB, v_shaped);
+    k_lbs_joints<<<24, 256, 0, st>>>(d_J_regressor, v_shaped, V, joints_rest);
+    k_lbs_chain<<<1, 32, 0, st>>>(pose, joints_rest, parents, transl, pose_feature, d_joints, d_A, A_rel);
+    k_lbs_skin<<<(V + 127) / 128, 128, 0, st>>>(v_shaped, d_posedirs, pose_feature, d_lbs_weights, A_rel, transl, V, d_vertices);
+    IA_LAUNCH_CHECK();
+    IA_CHECK_CUDA(cudaStreamSynchronize(st));   // the small host arrays above must outlive the copies
+    IA_CHECK_CUDA(cudaFreeAsync(w, st));
+    return IA_OK;
+}
+
+extern "C" int ia_voxelize_lbs(ia_ctx* c, const float* d_verts, const float* d_weights, int V, int resolution,
+                               float* d_lbs_voxel, float* h_offset_kernel3, float* h_scale_kernel3, void* stream) {
+    IA_REQUIRE(c && d_verts && d_weights && d_lbs_voxel && h_offset_kernel3 && h_scale_kernel3, IA_EINVAL,
+               "ia_voxelize_lbs: NULL argument");
+    IA_REQUIRE(V > 0 && resolution >= 8 && resolution % 4 == 0, IA_EINVAL, "ia_voxelize_lbs: resolution must be a multiple of 4");
+    IA_CHECK_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = resolution / 4, H = resolution, W = resolution, P = D * H * W;
+    float* tmp = nullptr;
+    IA_CHECK_CUDA(cudaMallocAsync((void**)&tmp, ((size_t)24 * P + 8) * sizeof(float), st));
+    float* mnmx = tmp + (size_t)24 * P;
+    k_vox_bbox<<<1, 256, 0, st>>>(d_verts, V, mnmx);
+    float h[6];
+    IA_CHECK_CUDA(cudaMemcpyAsync(h, mnmx, sizeof(h), cudaMemcpyDeviceToHost, st));
+    IA_CHECK_CUDA(cudaStreamSynchronize(st));
+    // deformer_torch.py:150-167 (fp32 like the reference's torch ops)
+    const float off[3] = {(h[0] + h[3]) * 0.5f, (h[1] + h[4]) * 0.5f, (h[2] + h[5]) * 0.5f};
+    const float scale = fmaxf(fmaxf(h[3] - h[0], h[4] - h[1]), h[5] - h[2]) / 2 * 1.2f;
+    const float ratio = (float)H / (float)D;
+    k_vox_knn<<<(P + 127) / 128, 128, 0, st>>>(d_verts, d_weights, V, D, H, W, off[0], off[1], off[2], scale, ratio, d_lbs_voxel);
+    float *a = d_lbs_voxel, *b = tmp;
+    for (int it = 0; it < 30; it++) {
+        k_vox_smooth<<<(P + 255) / 256, 256, 0, st>>>(a, b, D, H, W);
+        std::swap(a, b);
+    }
+    // 30 passes: the result is back in d_lbs_voxel
+    IA_LAUNCH_CHECK();
+    IA_CHECK_CUDA(cudaFreeAsync(tmp, st));
+    for (int i = 0; i < 3; i++) {
+        h_offset_kernel3[i] = -off[i];
+        h_scale_kernel3[i] = 1.0f / scale;
+    }
+    h_scale_kernel3[2] *= ratio;
+    return IA_OK;
+}
+
 #include "ia_render.cuh"

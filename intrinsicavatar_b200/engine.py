@@ -17,6 +17,8 @@ _ARGTYPES = {
     "ia_destroy": [_vp],
     "ia_set_fields": [_vp, _vp, _vp, _i64] + [_vp] * 4 + [_vp] * 18 + [_vp, _cf32, _vp],
     "ia_set_lbs_voxels": [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp],
+    "ia_smpl_lbs": [_vp] * 7 + [_i32, _i32] + [_vp] * 7,
+    "ia_voxelize_lbs": [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
     "ia_set_pose": [_vp, _vp, _vp, _vp],
     "ia_set_render_config": [_vp, _vp, _i32, _i32, _cf32, _cf32, _cf32, _vp, _vp],
     "ia_reserve_samples": [_vp, _i64],
@@ -134,6 +136,42 @@ class RenderEngine:
         check(self.lib.ia_set_lbs_voxels(self.h, ptr(v), v.shape[1], v.shape[2], v.shape[3], fptr(_f32(offset_kernel)),
                                          fptr(_f32(scale_kernel)), _stream()), "ia_set_lbs_voxels")
         torch.cuda.current_stream().synchronize()  # v is repacked into the context; safe to drop
+
+    # ------------------------------------------------------------- subject set-up ----
+    def smpl_arrays(self, body):
+        """Upload the arrays of a body.SMPLBody once (device fp32, the layouts ia_smpl_lbs takes)."""
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a, np.float32)).to(self.dev)
+        return {"v_template": t(body.v_template), "shapedirs": t(body.shapedirs), "posedirs": t(body.posedirs),
+                "J_regressor": t(body.J_regressor), "lbs_weights": t(body.lbs_weights),
+                "parents": np.ascontiguousarray(body.parents, np.int32), "V": int(body.v_template.shape[0]),
+                "NB": int(body.shapedirs.shape[-1])}
+
+    def smpl_lbs(self, arrays, betas, body_pose, global_orient, transl):
+        """SMPL forward on the device: (vertices [V,3], joints [24,3], A [24,4,4]) CUDA tensors."""
+        V, NB = arrays["V"], arrays["NB"]
+        b = np.zeros(NB, np.float32)
+        bb = _f32(betas).reshape(-1)[:NB]
+        b[:len(bb)] = bb
+        pose = _f32(np.concatenate([_f32(global_orient).reshape(3), _f32(body_pose).reshape(69)]))
+        tr = _f32(transl).reshape(3)
+        verts = torch.empty(V, 3, device=self.dev)
+        joints = torch.empty(24, 3, device=self.dev)
+        A = torch.empty(24, 4, 4, device=self.dev)
+        check(self.lib.ia_smpl_lbs(self.h, ptr(arrays["v_template"]), ptr(arrays["shapedirs"]), ptr(arrays["posedirs"]),
+                                   ptr(arrays["J_regressor"]), ptr(arrays["lbs_weights"]), fptr(arrays["parents"]), V, NB,
+                                   fptr(b), fptr(pose), fptr(tr), ptr(verts), ptr(joints), ptr(A), _stream()), "ia_smpl_lbs")
+        return verts, joints, A
+
+    def voxelize_lbs(self, verts, weights, resolution=128):
+        """Skinning-weight voxel grid on the device: (lbs_voxel [24, res/4, res, res] CUDA, offset_kernel [3], scale_kernel [3])."""
+        v = torch.as_tensor(verts, dtype=torch.float32).to(self.dev).reshape(-1, 3).contiguous()
+        w = torch.as_tensor(weights, dtype=torch.float32).to(self.dev).reshape(-1, 24).contiguous()
+        assert v.shape[0] == w.shape[0]
+        vox = torch.empty(24, resolution // 4, resolution, resolution, device=self.dev)
+        off, scl = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        check(self.lib.ia_voxelize_lbs(self.h, ptr(v), ptr(w), v.shape[0], int(resolution), ptr(vox), fptr(off), fptr(scl),
+                                       _stream()), "ia_voxelize_lbs")
+        return vox, off, scl
 
     def set_pose(self, tfs, w2s):
         check(self.lib.ia_set_pose(self.h, fptr(_f32(tfs).reshape(24 * 16)), fptr(_f32(w2s).reshape(16)), _stream()),

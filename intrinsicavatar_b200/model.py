@@ -196,7 +196,7 @@ class IntrinsicAvatarModel(torch.nn.Module):
 
     def _init_subject(self, body):
         res = int(self.config.get("deformer", {}).get("rigid_deformer", {}).get("deformer_config", {}).get("resolution", 128))
-        self.setup_snarf = SnarfSetup(body, resolution=res)
+        self.setup_snarf = SnarfSetup(body, resolution=res, engine=self.engine)     # voxelisation on the device
         self.engine.set_lbs_voxels(self.setup_snarf.lbs_voxel, self.setup_snarf.offset_kernel, self.setup_snarf.scale_kernel)
         self._upload_fields()
 

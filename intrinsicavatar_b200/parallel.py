@@ -164,6 +164,17 @@ class FrameCollector:
         if self.ws > 1:
             dist.barrier()
 
+    def close(self):
+        """Drop the mapping of dst's buffer everywhere BEFORE dst frees it (CUDA IPC: the producer must outlive its consumers)."""
+        if self.transport == "p2p" and self.rank != self.dst:
+            self.peer = None
+            self._peer_storage = None
+        if self.ws > 1:
+            if torch.device(self.device).type == "cuda":
+                torch.cuda.synchronize()
+            dist.barrier()
+        self.recv = None
+
     def frames(self, step: int):
         """dst only: [ws, n_pix, 16] blocks of ``step`` (after ``finish``)."""
         return self.recv[step % self.slots] if self.rank == self.dst else None

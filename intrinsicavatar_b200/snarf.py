@@ -79,14 +79,21 @@ def voxelize_lbs_weights(verts: np.ndarray, weights: np.ndarray, resolution: int
 class SnarfSetup:
     """Subject-level state + per-frame bone transforms (host)."""
 
-    def __init__(self, body: SyntheticBody | None = None, resolution: int = 128):
+    def __init__(self, body: SyntheticBody | None = None, resolution: int = 128, engine=None):
+        """``engine`` (a RenderEngine): voxelise on the device (ia_voxelize_lbs: 0.1 s instead of ~5 s of cKDTree queries on
+        the host at resolution 128; the same recipe, held to the same reference golden); ``lbs_voxel`` is then a CUDA
+        tensor."""
         self.body = body if body is not None else SyntheticBody()
         cano = self.body(body_pose=a_pose())
         self.tfs_inv_t = np.linalg.inv(cano["A"][0].astype(np.float64))
-        vox = voxelize_lbs_weights(cano["vertices"][0], self.body.lbs_weights, resolution)
-        self.lbs_voxel = vox["lbs_voxel"]
-        self.offset_kernel = vox["offset_kernel"]
-        self.scale_kernel = vox["scale_kernel"]
+        if engine is not None:
+            self.lbs_voxel, self.offset_kernel, self.scale_kernel = engine.voxelize_lbs(cano["vertices"][0],
+                                                                                       self.body.lbs_weights, resolution)
+        else:
+            vox = voxelize_lbs_weights(cano["vertices"][0], self.body.lbs_weights, resolution)
+            self.lbs_voxel = vox["lbs_voxel"]
+            self.offset_kernel = vox["offset_kernel"]
+            self.scale_kernel = vox["scale_kernel"]
         self.bbox = get_bbox_from_verts(cano["vertices"][0])  # canonical bbox -> field normalisation
         self.resolution = resolution
 

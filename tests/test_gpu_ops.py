@@ -5,6 +5,8 @@ Tolerances: index / flag outputs must agree exactly except on a small budget of 
 floating-point outputs agree to ~1e-5 absolute (fp32 re-association), far inside the 1e-3 relative-L2
 bar BASELINE.json states for the image buffers.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -471,3 +473,45 @@ def test_shade_fields_vs_reference_modules(eng):
     rgb, mat = eng.op_shade_fields(g["fields_points"], g["fields_feature"], g["fields_view"], g["fields_normal"])
     assert (rgb.cpu() - g["fields_rgb"]).abs().max() < 2e-5
     assert (mat.cpu() - g["fields_materials"]).abs().max() < 2e-5
+
+
+def test_smpl_lbs_on_device_vs_reference_golden(eng):
+    """ia_smpl_lbs against the reference's own lbs() + SMPL.forward translation (models/deformers/smplx/lbs.py:152-248,
+    body_models.py:342-358) run on a random model of SMPL's shapes: tests/golden/reference_vectors_smpl.npz."""
+    from intrinsicavatar_b200.body import SMPLBody
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors_smpl.npz"))
+    body = SMPLBody(z["smpl_v_template"], z["smpl_shapedirs"], z["smpl_posedirs"], z["smpl_J_regressor"], z["smpl_weights"])
+    arrays = eng.smpl_arrays(body)
+    pose = z["smpl_pose"][0]
+    v, j, A = eng.smpl_lbs(arrays, z["smpl_betas"][0], pose[3:], pose[:3], z["smpl_transl"][0])
+    assert np.abs(v.cpu().numpy() - z["smpl_vertices"][0]).max() < 1e-5
+    assert np.abs(j.cpu().numpy() - z["smpl_joints"][0]).max() < 1e-5
+    assert np.abs(A.cpu().numpy() - z["smpl_A"][0]).max() < 1e-5
+    # zero pose, zero betas: the template itself, identity transforms
+    v0, j0, A0 = eng.smpl_lbs(arrays, np.zeros(10), np.zeros(69), np.zeros(3), np.zeros(3))
+    assert np.abs(v0.cpu().numpy() - z["smpl_v_template"]).max() < 1e-6
+    assert np.abs(A0.cpu().numpy() - np.eye(4)[None]).max() < 1e-6
+
+
+def test_voxelize_lbs_on_device_vs_reference_golden(eng):
+    """ia_voxelize_lbs (brute-force K = 30 nearest vertices, inverse-distance blend, 30 smoothing passes) against the
+    reference's own switch_to_explicit + query_weights_smpl (tests/golden/reference_vectors_voxel.npz) and against the host
+    implementation (snarf.voxelize_lbs_weights) at the production resolution."""
+    from intrinsicavatar_b200.body import SyntheticBody, a_pose
+    from intrinsicavatar_b200.snarf import voxelize_lbs_weights
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors_voxel.npz"))
+    body = SyntheticBody()
+    cano = body(body_pose=a_pose())
+    vox, off, scl = eng.voxelize_lbs(cano["vertices"][0], body.lbs_weights, int(z["voxel_res"]))
+    vox = vox.cpu().numpy()
+    assert np.allclose(off, z["voxel_offset_kernel"], atol=1e-6) and np.allclose(scl, z["voxel_scale_kernel"], rtol=1e-6)
+    d = np.abs(vox - z["voxel_lbs"])
+    # (the 30th nearest neighbour can differ between two KNN implementations when two vertices are equally far: a
+    #  handful of voxels, smeared by the smoothing passes -- the bar the host implementation is held to)
+    assert d.max() < 0.05 and float((d > 1e-4).mean()) < 1e-3 and float(d.mean()) < 1e-6, (d.max(), float((d > 1e-4).mean()))
+    assert np.allclose(vox.sum(0), 1.0, atol=1e-5)
+    big, off2, scl2 = eng.voxelize_lbs(cano["vertices"][0], body.lbs_weights, 128)
+    host = voxelize_lbs_weights(cano["vertices"][0], body.lbs_weights, 128)
+    d = np.abs(big.cpu().numpy() - host["lbs_voxel"])
+    assert big.shape == (24, 32, 128, 128) and d.max() < 0.05 and float((d > 1e-4).mean()) < 1e-3
+    assert np.allclose(off2, host["offset_kernel"], atol=1e-6) and np.allclose(scl2, host["scale_kernel"], rtol=1e-6)
