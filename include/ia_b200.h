@@ -92,6 +92,13 @@ int ia_set_render_config(ia_ctx* ctx, const float* h_scene_aabb6, int num_sample
                          int num_samples_per_secondary_ray, float secondary_near, float secondary_far,
                          float occ_thre, const float* h_background3, const float* h_albedo_align_ratio3);
 
+/* config.model.secondary_importance_sample / zero_crossing_search (configs/config.yaml:53-54; models/intrinsic_avatar.py:
+ * 482-520).  Defaults (1, 1): the secondary march stops at the first +/- crossing of the SDF and places 4 fine samples
+ * there (ray_resampling_sdf_fine, lib/nerfacc/cuda/csrc/cdf.cu:536-638).  (1, 0): the 4 fine samples follow the CDF of the
+ * compositing weights of all coarse samples (ray_resampling_fine, cdf.cu:403-478).  (0, *): no resampling, the coarse
+ * samples are rendered at their midpoints.                                                                              */
+int ia_set_secondary_sampling(ia_ctx* ctx, int importance_sample, int zero_crossing_search);
+
 /* Capacity of the primary-sample pool of ia_render, in samples (default: 64 per ray of the call).  A frame that needs
  * more renders the rays that did not fit as background and counts them in IA_CNT_OVERFLOW; the host grows the pool with
  * this call and renders again (engine.RenderEngine.render(check_overflow=True)).  The reference has no such limit: its
@@ -249,6 +256,11 @@ int ia_op_ray_resampling_merge(ia_ctx* ctx, const int32_t* d_packed_info, const 
                                int64_t n_rays, const int32_t* d_resample_packed_info, float* d_vals_out,
                                float* d_dists_out, uint8_t* d_is_left_out, uint8_t* d_is_right_out,
                                uint8_t* d_is_resample_out, uint8_t* d_is_fg_out, void* stream);
+/* lib.nerfacc ray_resampling_fine (cdf_resampling_fine_kernel, cdf.cu:403-534): n fine intervals along the CDF of the
+ * compositing weights; outputs pre-zeroed by the caller.                                                 */
+int ia_op_ray_resampling_fine(ia_ctx* ctx, const int32_t* d_packed_info, const float* d_starts, const float* d_ends,
+                              const float* d_weights, int64_t n_rays, const int32_t* d_resample_packed_info,
+                              float* d_starts_out, float* d_ends_out, uint8_t* d_is_fg_out, void* stream);
 /* lib.nerfacc ray_resampling_sdf_fine (cdf.cu:640-696); outputs pre-zeroed by the caller.             */
 int ia_op_ray_resampling_sdf_fine(ia_ctx* ctx, const int32_t* d_packed_info, const float* d_starts,
                                   const float* d_ends, const float* d_alphas, const float* d_sdfs,

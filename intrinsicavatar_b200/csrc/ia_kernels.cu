@@ -342,6 +342,12 @@ extern "C" int ia_set_render_config(ia_ctx* c, const float* aabb, int n_per_ray,
     return IA_OK;
 }
 
+extern "C" int ia_set_secondary_sampling(ia_ctx* c, int importance_sample, int zero_crossing_search) {
+    IA_REQUIRE(c, IA_EINVAL, "ia_set_secondary_sampling: NULL context");
+    c->f.sec_mode = !importance_sample ? IA_SEC_PLAIN : (zero_crossing_search ? IA_SEC_ZERO_CROSSING : IA_SEC_IMPORTANCE);
+    return IA_OK;
+}
+
 // ================================================================================================
 // op-level kernels
 // the blended fp32 transform in the reference's channel-major layout [12][nvox], recomputed from the context's skinning

@@ -897,6 +897,57 @@ extern "C" int ia_op_ray_resampling_sdf_fine(ia_ctx* c, const int32_t* d_packed,
     return IA_OK;
 }
 
+// cdf_resampling_fine_kernel (cdf.cu:403-478): thread per ray.  The CDF of the compositing weights of all samples,
+// n + 1 stratified positions -> n consecutive intervals (op-level twin of the wavefront tracer with
+// zero_crossing_search = false).
+__global__ void k_op_fine(const int* __restrict__ packed, const float* __restrict__ starts_all, const float* __restrict__ ends_all,
+                          const float* __restrict__ weights_all, long long n_rays, const int* __restrict__ rpacked,
+                          float* __restrict__ rs_all, float* __restrict__ re_all, uint8_t* __restrict__ isfg_all) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rays) return;
+    const int base = packed[i * 2], steps = packed[i * 2 + 1];
+    const int rb = rpacked[i * 2], rsteps = rpacked[i * 2 + 1];
+    if (steps == 0) return;
+    const float *starts = starts_all + base, *ends = ends_all + base, *weights = weights_all + base;
+    float *rs = rs_all + rb, *re = re_all + rb;
+    uint8_t* isfg = isfg_all + rb;
+    float weights_sum = 0.0f;
+    for (int j = 0; j < steps; j++) weights_sum += weights[j];
+    weights_sum += fmaxf(1.0f - weights_sum, 0.0f);
+    const int num_bins = rsteps + 1;
+    const float cdf_step_size = (1.0f - 1.0 / num_bins) / rsteps;
+    int idx = 0, j = 0;
+    float cdf_prev = 0.0f, cdf_next = weights[idx] / weights_sum;
+    float cdf_u = 1.0 / (2 * num_bins);
+    while (j < num_bins && idx < steps) {
+        if (cdf_u < cdf_next) {
+            float scaling = (ends[idx] - starts[idx]) / (cdf_next - cdf_prev);
+            float t = (cdf_u - cdf_prev) * scaling + starts[idx];
+            if (j < num_bins - 1) rs[j] = t;
+            if (j > 0) { re[j - 1] = t; isfg[j - 1] = 1; }
+            cdf_u += cdf_step_size;
+            j += 1;
+        } else {
+            idx += 1;
+            if (idx >= steps) break;
+            cdf_prev = cdf_next;
+            cdf_next += weights[idx] / weights_sum;
+        }
+    }
+}
+
+extern "C" int ia_op_ray_resampling_fine(ia_ctx* c, const int32_t* d_packed, const float* d_starts, const float* d_ends,
+                                         const float* d_weights, int64_t n_rays, const int32_t* d_rpacked, float* d_rs,
+                                         float* d_re, uint8_t* d_isfg, void* stream) {
+    IA_REQUIRE(c && d_packed && d_starts && d_ends && d_weights && d_rpacked && d_rs && d_re && d_isfg, IA_EINVAL,
+               "ia_op_ray_resampling_fine: NULL argument");
+    if (n_rays == 0) return IA_OK;
+    k_op_fine<<<(unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_packed, d_starts, d_ends, d_weights, n_rays,
+                                                                                 d_rpacked, d_rs, d_re, d_isfg);
+    IA_LAUNCH_CHECK();
+    return IA_OK;
+}
+
 __global__ void k_op_unpack_info(const int* __restrict__ packed, long long n_rays, long long* __restrict__ ray_indices) {
     // one warp per ray, coalesced fill (unpack_info_kernel, pack.cu:7-28)
     long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;

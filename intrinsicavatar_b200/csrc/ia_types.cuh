@@ -51,6 +51,10 @@ namespace cg = cooperative_groups;
 #define IA_MAT_B3 (IA_MAT_W3 + 5 * 64)        // [8]
 #define IA_MLP_END (IA_MAT_B3 + 8)
 
+#define IA_SEC_ZERO_CROSSING 0
+#define IA_SEC_IMPORTANCE 1
+#define IA_SEC_PLAIN 2
+
 // Per-frame constants, passed to every kernel by value (__grid_constant__).
 struct IaFrame {
     // --- fast-SNARF
@@ -78,6 +82,8 @@ struct IaFrame {
     float aabb[6];
     float step_primary;         // diag(scene_aabb) / num_samples_per_ray
     float sec_near, sec_far, sec_step;
+    int sec_mode;               // secondary rays: 0 importance sampling + zero-crossing search (default), 1 importance sampling
+                                // from the ray start (zero_crossing_search = false), 2 no importance sampling (IA_SEC_*)
     float background[3];
 };
 

@@ -584,7 +584,62 @@ __device__ __forceinline__ void wf_advance_consume(const IaFrame& p, P& pol, WfS
     for (int k = 0; k < 3; k++) { o[k] = S.st[WS_O + k][t]; d[k] = S.st[WS_D + k][t]; }
     wf_load_marcher(S, t, m, p.sec_step);
     ts = S.st[WS_TS][t]; te = S.st[WS_TE][t];
-    if (stage == WF_FIRST) {
+    if (p.sec_mode == IA_SEC_PLAIN) {
+        // secondary_importance_sample = false (models/intrinsic_avatar.py:482-520 skipped): the coarse samples themselves are
+        // rendered -- query at the MIDPOINT of every sample, w = T alpha, T *= 1 - alpha, radiance at every sample (GI).
+        // Stage SEARCH = accumulating; WS_TRANS = T, WS_CDFPREV = sum of weights.
+        float Tacc = 1.0f, acc = 0.0f;
+        if (stage == WF_GIWAIT) {
+            Tfin = S.st[WS_TRANS][t];
+            stage = WF_FINE;                       // (marks "indirect radiance present" for the finish)
+            action = WF_ACT_FINISH;
+        } else {
+            if (stage == WF_SEARCH) { Tacc = S.st[WS_TRANS][t]; acc = S.st[WS_CDFPREV][t]; }
+            else if (GI) { S.st[WS_IND][t] = 0.f; S.st[WS_IND + 1][t] = 0.f; S.st[WS_IND + 2][t] = 0.f; }   // first sample
+            const float al = ia_alpha(sdf, te - ts, p.beta);
+            const float w = Tacc * al;
+            Tacc *= (1.0f - al);
+            acc += w;
+            bool gi_pushed = false;
+            if (GI && best >= 0) {
+                int gi = atomicAdd(&S.n_gitask, 1);
+                S.gitask[gi] = make_uint2((unsigned)t | ((unsigned)best << 16), __float_as_uint(w));
+                gi_pushed = true;
+            }
+            bool cont;
+            if (m.next(p.occ_bits, p.occ_res, ts, te, cont)) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) S.qx[k][t] = o[k] + d[k] * ((ts + te) / 2.0f);
+                wf_store_marcher(S, t, m);
+                S.st[WS_TS][t] = ts; S.st[WS_TE][t] = te;
+                S.st[WS_TRANS][t] = Tacc; S.st[WS_CDFPREV][t] = acc;
+                int idx = atomicAdd(&S.n_q, 1);
+                S.qlist[idx] = (unsigned short)t;
+                S.qmask[t] = 0;
+                c_q++;
+                S.st[WS_PACK][t] = __uint_as_float((unsigned)WF_SEARCH | (ey << 16));
+                return;
+            }
+            Tfin = 1.0f - acc;
+            if (GI && gi_pushed) {
+                S.st[WS_TRANS][t] = Tfin;
+                S.st[WS_PACK][t] = __uint_as_float((unsigned)WF_GIWAIT | (ey << 16));
+                return;
+            }
+            stage = GI ? WF_FINE : WF_SEARCH;
+            action = WF_ACT_FINISH;
+        }
+    } else if (stage == WF_FIRST && p.sec_mode == IA_SEC_IMPORTANCE) {
+        // zero_crossing_search = false: ray_resampling_fine (cdf.cu:403-478) over the weights of ALL coarse samples, i.e.
+        // the CDF walk starts at the first sample (weights_sum = max(sum w, 1) = 1: sum w = 1 - T <= 1)
+        cs = ts; ce = te;
+        j = 0;
+        float a = ia_alpha(sdf, ce - cs, p.beta);
+        trans = 1.0f - a;
+        cdf_prev = 0.0f; cdf_next = a;
+        cdf_u = 1.0 / (2 * 5);
+        action = WF_ACT_CDF;
+    } else if (stage == WF_FIRST) {
         sdf_prev = sdf; cs = ts; ce = te;
         stage = WF_SEARCH;
         action = WF_ACT_NEXT;
@@ -757,8 +812,9 @@ __device__ __forceinline__ void wf_advance_refill(const IaFrame& p, P& pol, WfSh
         float ts, te;
         bool cont;
         if (m.next(p.occ_bits, p.occ_res, ts, te, cont)) {
+            const float tq = p.sec_mode == IA_SEC_PLAIN ? (ts + te) / 2.0f : ts;
 #pragma unroll
-            for (int k = 0; k < 3; k++) { S.st[WS_O + k][t] = o[k]; S.st[WS_D + k][t] = d[k]; S.qx[k][t] = o[k] + d[k] * ts; }
+            for (int k = 0; k < 3; k++) { S.st[WS_O + k][t] = o[k]; S.st[WS_D + k][t] = d[k]; S.qx[k][t] = o[k] + d[k] * tq; }
             S.st[WS_ID][t] = __uint_as_float(entry.x);
             wf_store_marcher(S, t, m);
             S.st[WS_TS][t] = ts; S.st[WS_TE][t] = te;

@@ -22,6 +22,7 @@ _ARGTYPES = {
     "ia_set_pose": [_vp, _vp, _vp, _vp],
     "ia_set_render_config": [_vp, _vp, _i32, _i32, _cf32, _cf32, _cf32, _vp, _vp],
     "ia_reserve_samples": [_vp, _i64],
+    "ia_set_secondary_sampling": [_vp, _i32, _i32],
     "ia_build_occupancy": [_vp, _vp, _i32, _vp, _vp, _vp],
     "ia_set_occupancy": [_vp, _vp, _i32, _vp, _vp],
     "ia_set_light": [_vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
@@ -39,6 +40,7 @@ _ARGTYPES = {
     "ia_op_ray_resampling": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp] + [_vp] * 6 + [_vp],
     "ia_op_ray_resampling_merge": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp] + [_vp] * 6 + [_vp],
     "ia_op_ray_resampling_sdf_fine": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
+    "ia_op_ray_resampling_fine": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "ia_op_unpack_info": [_vp, _vp, _i64, _vp, _vp],
     "ia_op_secondary": [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp],
     "ia_op_brdf": [_vp] * 7 + [_i64, _vp, _vp, _vp],
@@ -184,6 +186,10 @@ class RenderEngine:
         check(self.lib.ia_set_render_config(self.h, fptr(_f32(scene_aabb)), num_samples_per_ray,
                                             num_samples_per_secondary_ray, secondary_near, secondary_far, occ_thre,
                                             fptr(_f32(background)), ratio), "ia_set_render_config")
+
+    def set_secondary_sampling(self, importance_sample=True, zero_crossing_search=True):
+        check(self.lib.ia_set_secondary_sampling(self.h, int(bool(importance_sample)), int(bool(zero_crossing_search))),
+              "ia_set_secondary_sampling")
 
     def build_occupancy(self, aabb, jitter, res=64, return_grid=False):
         j = torch.as_tensor(jitter, dtype=torch.float32).to(self.dev).contiguous()
@@ -436,6 +442,17 @@ class RenderEngine:
         fg = torch.zeros(total, dtype=torch.uint8, device=self.dev)
         check(self.lib.ia_op_ray_resampling_sdf_fine(self.h, ptr(pi), *[ptr(t) for t in a], n, ptr(rpi), ptr(rs), ptr(re),
                                                      ptr(fg), _stream()), "ia_op_ray_resampling_sdf_fine")
+        return rpi, rs, re, fg.bool()
+
+    def op_ray_resampling_fine(self, packed_info, starts, ends, weights, n_samples):
+        pi = packed_info.to(self.dev).int().contiguous()
+        a = [t.to(self.dev, torch.float32).reshape(-1).contiguous() for t in (starts, ends, weights)]
+        n = pi.shape[0]
+        rpi, total = self._rpacked(pi[:, 1], (pi[:, 1] > 0) * n_samples)
+        rs, re = torch.zeros(total, 1, device=self.dev), torch.zeros(total, 1, device=self.dev)
+        fg = torch.zeros(total, dtype=torch.uint8, device=self.dev)
+        check(self.lib.ia_op_ray_resampling_fine(self.h, ptr(pi), *[ptr(t) for t in a], n, ptr(rpi), ptr(rs), ptr(re), ptr(fg),
+                                                 _stream()), "ia_op_ray_resampling_fine")
         return rpi, rs, re, fg.bool()
 
     def op_unpack_info(self, packed_info, n_samples):

@@ -71,7 +71,7 @@ EXPECTED_NESTED = {
                  "mlp_network_config": {"otype": "VanillaMLP", "activation": "ReLU", "output_activation": "none",
                                         "n_neurons": 64, "n_hidden_layers": 2},
                  "color_activation": "sigmoid"},
-    "material": {"name": "volume-material", "input_feature_dim": 48, "n_output_dim": 5,
+    "material": {"name": "volume-material", "n_output_dim": 5,
                  "mlp_network_config": {"otype": "LipshitzMLP", "activation": "ReLU", "output_activation": "none",
                                         "n_neurons": 64, "n_hidden_layers": 2},
                  "material_activation": "sigmoid"},
@@ -128,10 +128,14 @@ class IntrinsicAvatarModel(torch.nn.Module):
             raise NotImplementedError(f"Render mode {cfg['render_mode']} not supported.")
         if cfg["render_mode"] == "uniform_light":
             assert cfg["samples_per_pixel"] == 512  # models/intrinsic_avatar.py:1391 (16 x 32 stratified sphere)
-        if not (cfg["secondary_importance_sample"] and cfg["zero_crossing_search"]) or cfg["material_feature"] != "hybrid":
-            raise NotImplementedError("non-default secondary sampling / material_feature not supported")
+        if cfg["material_feature"] not in W.MATERIAL_IN:
+            raise ValueError(f"material_feature {cfg['material_feature']!r}: geometry | radiance | hybrid (models/intrinsic_avatar.py:1102-1113)")
         errors = []
         _check_nested(cfg, EXPECTED_NESTED, "config", errors)
+        want_in = W.MATERIAL_IN[cfg["material_feature"]]
+        if isinstance(cfg.get("material"), dict) and cfg["material"].get("input_feature_dim", want_in) != want_in:
+            errors.append(f"config.material.input_feature_dim = {cfg['material']['input_feature_dim']!r}, material_feature = "
+                          f"{cfg['material_feature']!r} needs {want_in}")
         if errors:
             raise ValueError("IntrinsicAvatarModel: this build of libia_b200 cannot render the configured model:\n  "
                              + "\n  ".join(errors))
@@ -159,7 +163,7 @@ class IntrinsicAvatarModel(torch.nn.Module):
         unless a body object was handed to the constructor."""
         self.engine = RenderEngine(self._device_arg)
         self.layout = W.hashgrid_layout()
-        for key, v in W.random_state_dict(self.seed).items():
+        for key, v in W.material_state_dict_for(W.random_state_dict(self.seed), self.config["material_feature"]).items():
             self._register(key, v)
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._upload_fields())
         if self._body_arg is not None:
@@ -227,13 +231,13 @@ class IntrinsicAvatarModel(torch.nn.Module):
     def load_checkpoint(self, path: str):
         """Ingest a Lightning checkpoint of the reference (launch.py:110-124): the render-path parameters under
         ``model.`` are taken, everything else is ignored (strict=False semantics)."""
-        return self.load_state_dict(W.load_lightning_checkpoint(path))
+        return self.load_state_dict(W.load_lightning_checkpoint(path, material_feature=self.config["material_feature"]))
 
     def _upload_fields(self):
         if self.setup_snarf is None:
             return                                       # the canonical bbox is not known before the subject is
         sd = {k: v.detach() for k, v in self.named_parameters()}
-        folded = W.fold(sd)
+        folded = W.fold(sd, self.config["material_feature"])
         mcfg = self.config.get("material") or {}
         if any(k in mcfg for k in _MATERIAL_AFFINE):     # configs/material/shallow_mlp.yaml:4-9
             g = lambda k, d: float(mcfg.get(k, d))
@@ -263,6 +267,7 @@ class IntrinsicAvatarModel(torch.nn.Module):
             cfg["secondary_near_plane"], cfg["secondary_far_plane"], cfg["grid_prune_occ_thre"],
             np.asarray(torch.as_tensor(self.background_color).cpu(), np.float32),
             None if ratio is None else np.asarray(torch.as_tensor(ratio).cpu(), np.float32))
+        self.engine.set_secondary_sampling(cfg["secondary_importance_sample"], cfg["zero_crossing_search"])
 
     def prepare(self, batch: dict, jitter=None, light_uniforms=None):
         """models/intrinsic_avatar.py:281-305.  ``batch`` holds betas[1,10] (first call: the subject is built from them,

@@ -116,8 +116,27 @@ def random_state_dict(seed: int = 0, beta: float = 0.01, geo_hash_amp: float = 0
     return sd
 
 
-def fold(sd: dict) -> dict:
-    """Reference state_dict -> dense fp32 matrices (row-major [out,in]) + scalars for the kernels."""
+MATERIAL_IN = {"hybrid": 48, "geometry": 13, "radiance": 35}     # config.model.material_feature -> material MLP input width
+
+
+def material_state_dict_for(sd: dict, material_feature: str) -> dict:
+    """The state dict of a model whose material net sees only the geometry feature / only the radiance encoding
+    (models/intrinsic_avatar.py:1102-1113), cut out of a hybrid one: the first material layer keeps the columns of that
+    input (hybrid input = cat[xyz_embd 35, feature 13])."""
+    out = dict(sd)
+    w = sd["material.network.layers.0.weight"]
+    assert w.shape[1] == 48
+    if material_feature == "geometry":
+        out["material.network.layers.0.weight"] = w[:, 35:].clone()
+    elif material_feature == "radiance":
+        out["material.network.layers.0.weight"] = w[:, :35].clone()
+    return out
+
+
+def fold(sd: dict, material_feature: str = "hybrid") -> dict:
+    """Reference state_dict -> dense fp32 matrices (row-major [out,in]) + scalars for the kernels.  The kernels evaluate the
+    material net on the hybrid input cat[xyz_embd 35, feature 13]; a model with material_feature = geometry | radiance has a
+    13- / 35-wide first layer, which is the hybrid layer with zero columns for the input it does not see."""
     out = {}
     out["geo_hash"] = sd["geometry.encoding.encoding.encoding.params"].float().contiguous()
     out["rad_hash"] = sd["radiance.xyz_encoding.encoding.encoding.params"].float().contiguous()
@@ -133,7 +152,16 @@ def fold(sd: dict) -> dict:
         w = sd[f"material.network.layers.{li}.weight"].float()
         c = F.softplus(sd[f"material.network.lipshitz_bound_per_layer.{li}"].float())
         s = torch.clamp(c / w.abs().sum(1), max=1.0)
-        out[f"mat_w{li + 1}"] = (w * s[:, None]).contiguous()
+        wf = w * s[:, None]
+        if li == 0 and wf.shape[1] != 48:
+            assert wf.shape[1] == MATERIAL_IN[material_feature], (tuple(wf.shape), material_feature)
+            pad = torch.zeros(wf.shape[0], 48)
+            if material_feature == "geometry":
+                pad[:, 35:] = wf
+            else:
+                pad[:, :35] = wf
+            wf = pad
+        out[f"mat_w{li + 1}"] = wf.contiguous()
         out[f"mat_b{li + 1}"] = sd[f"material.network.layers.{li}.bias"].float().contiguous()
     out["beta"] = float(sd["density.beta"].abs() + 1e-4)  # LearnedLaplaceDensity.get_beta, density.py:32-34
     return out
@@ -142,7 +170,7 @@ def fold(sd: dict) -> dict:
 RENDER_PATH_PREFIXES = ("geometry.", "radiance.", "material.", "density.")
 
 
-def load_lightning_checkpoint(path: str, map_location="cpu") -> dict:
+def load_lightning_checkpoint(path: str, map_location="cpu", material_feature: str = "hybrid") -> dict:
     """Reference-keyed state dict of the render path out of a Lightning checkpoint (launch.py:110-124 loads
     ``ckpt['state_dict']`` into the system with ``strict=False``; the model's parameters live under ``model.``).
     Keys outside the render path (pose correction, non-rigid, occupancy grids, emitter, loss state) are dropped;
@@ -155,7 +183,7 @@ def load_lightning_checkpoint(path: str, map_location="cpu") -> dict:
             k = k[len("model."):]
         if k.startswith(RENDER_PATH_PREFIXES) and torch.is_tensor(v):
             out[k] = v.detach().float()
-    expect = {k: tuple(v.shape) for k, v in random_state_dict_shapes().items()}
+    expect = {k: tuple(v.shape) for k, v in random_state_dict_shapes(material_feature).items()}
     missing = sorted(set(expect) - set(out))
     if missing:
         raise KeyError(f"checkpoint {path} lacks render-path parameters: {missing[:4]}{'...' if len(missing) > 4 else ''}")
@@ -166,7 +194,7 @@ def load_lightning_checkpoint(path: str, map_location="cpu") -> dict:
     return out
 
 
-def random_state_dict_shapes() -> dict:
+def random_state_dict_shapes(material_feature: str = "hybrid") -> dict:
     """Shapes of every render-path parameter (meta tensors, no allocation)."""
     lay = hashgrid_layout()
     n = lay["total"] * N_FEAT
@@ -178,7 +206,7 @@ def random_state_dict_shapes() -> dict:
         sd[k + ".weight_v"], sd[k + ".weight_g"], sd[k + ".bias"] = m(o, i_), m(o, 1), m(o)
     for li, (o, i_) in enumerate([(64, 67), (64, 64), (3, 64)]):
         sd[f"radiance.network.layers.{2 * li}.weight"], sd[f"radiance.network.layers.{2 * li}.bias"] = m(o, i_), m(o)
-    for li, (o, i_) in enumerate([(64, 48), (64, 64), (5, 64)]):
+    for li, (o, i_) in enumerate([(64, MATERIAL_IN[material_feature]), (64, 64), (5, 64)]):
         sd[f"material.network.layers.{li}.weight"], sd[f"material.network.layers.{li}.bias"] = m(o, i_), m(o)
         sd[f"material.network.lipshitz_bound_per_layer.{li}"] = m(1)
     return sd

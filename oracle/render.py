@@ -39,10 +39,13 @@ class OracleRenderer:
     def __init__(self, fields, lbs_voxel, offset_kernel, scale_kernel, *, samples_per_pixel=4,
                  global_illumination=False, num_samples_per_ray=128, num_samples_per_secondary_ray=64,
                  secondary_near=0.0, secondary_far=1.5, occ_thre=0.001, grid_res=64,
-                 query_chunk=65536, render_mode="light", add_emitter=False):
+                 query_chunk=65536, render_mode="light", add_emitter=False, secondary_importance_sample=True,
+                 zero_crossing_search=True):
         assert render_mode in ("light", "uniform_light", "mats", "mis")
         self.render_mode = render_mode
         self.add_emitter = add_emitter
+        # models/intrinsic_avatar.py:482-520
+        self.secondary_importance_sample, self.zero_crossing_search = secondary_importance_sample, zero_crossing_search
         self.fields = fields
         self.lbs_voxel = torch.as_tensor(lbs_voxel, dtype=torch.float32)
         self.offset = torch.as_tensor(offset_kernel, dtype=torch.float32)
@@ -130,13 +133,17 @@ class OracleRenderer:
         tg = ops.traverse_grid(rays_o, rays_d, self.binaries, self.grid_aabb, self.sec_near, self.sec_far,
                                self.sec_step)
         t_starts, t_ends, ray_indices = tg["t_starts"], tg["t_ends"], tg["sample_ray_indices"]
-        if t_starts.numel() > 0:
+        if t_starts.numel() > 0 and self.secondary_importance_sample:
             pos = rays_o[ray_indices] + rays_d[ray_indices] * t_starts[:, None]
             sdfs = self._deform(pos)["sdf"]
             alphas = self.fields.alpha_from_sdf(sdfs, t_ends - t_starts)
             packed = ops.pack_info(ray_indices, n_rays)
-            rpi, rs, re, is_fg = ops.ray_resampling_sdf_fine(packed, t_starts[:, None], t_ends[:, None],
-                                                             alphas, sdfs, 4)
+            if self.zero_crossing_search:
+                rpi, rs, re, is_fg = ops.ray_resampling_sdf_fine(packed, t_starts[:, None], t_ends[:, None],
+                                                                 alphas, sdfs, 4)
+            else:
+                weights, _ = ops.render_weight_from_alpha(alphas, packed)
+                rpi, rs, re, is_fg = ops.ray_resampling_fine(packed, t_starts[:, None], t_ends[:, None], weights, 4)
             rri = ops.unpack_info(rpi, len(rs))
             ray_indices = rri[is_fg]
             t_starts = rs[is_fg, 0]

@@ -603,6 +603,36 @@ def main_config():
     print("wrote", path, sorted(out))
 
 
+def main_e2e_switch():
+    """The reference's own forward_ with the non-default switches of config.model: zero_crossing_search = false
+    (ray_resampling_fine), secondary_importance_sample = false (coarse samples rendered), material_feature = geometry /
+    radiance.  -> tests/golden/reference_vectors_e2e_switch.npz"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import e2e_cases as E2E
+    import ref_harness as H
+    from conftest import Scene
+    H.install()
+    sc = Scene()
+    env = sc.syn.load_envmap()
+    base = E2E.load()                      # the frame-0 occupancy grid of the main golden (the reference's own build)
+    grid = E2E.grid(base, 0)
+    g = {}
+    for name, frame, side, spp, gi, opts in E2E.SWITCH_CASES:
+        fr = sc.frame(frame)
+        tabs = sc.syn.random_tables(spp, E2E.GRID_RES, seed=0)
+        m = H.build_model(sc, fr, spp, gi=gi, render_mode="light", binaries=grid, env=env, u1=tabs["u1"], u2=tabs["u2"], **opts)
+        rays = torch.from_numpy(sc.syn.make_rays(side, side, fr["transl"]))
+        out = H.forward(m, rays, seed=0)
+        for k in E2E_KEYS:
+            g[f"{name}/{k}"] = out[k].detach().numpy().astype(np.float32)
+        print(name, "hit rays", int((out["opacity"] > 0.5).sum()), "of", rays.shape[0], "mean rgb_phys over hits",
+              float(out["comp_rgb_phys"][out["opacity"][:, 0] > 0.5].mean()), flush=True)
+    out_path = os.path.join(ROOT, "tests", "golden", "reference_vectors_e2e_switch.npz")
+    np.savez_compressed(out_path, **g)
+    print("wrote", out_path, len(g), "arrays")
+
+
 def main_snarf():
     """The reference's own SNARFDeformer.initialize + prepare_deformer (models/deformers/snarf_deformer.py:46-126) driven
     by a body model that calls the reference's lbs() on the random SMPL-shaped arrays of reference_vectors_smpl.npz (the
@@ -681,6 +711,8 @@ def main_snarf():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "e2e":
         main_e2e()
+    elif len(sys.argv) > 1 and sys.argv[1] == "e2e_switch":
+        main_e2e_switch()
     elif len(sys.argv) > 1 and sys.argv[1] == "config":
         main_config()
     elif len(sys.argv) > 1 and sys.argv[1] == "e2e_hi":

@@ -237,7 +237,8 @@ class RandTables:
         torch.rand = self._orig
 
 
-def build_model(scene, frame, spp, gi=False, render_mode="light", add_emitter=False, binaries=None, env=None, u1=None, u2=None):
+def build_model(scene, frame, spp, gi=False, render_mode="light", add_emitter=False, binaries=None, env=None, u1=None, u2=None,
+                material_feature="hybrid", secondary_importance_sample=True, zero_crossing_search=True):
     """The reference's IntrinsicAvatarModel with its own sub-modules, in the fully warmed-up test-time state, for one
     frame.  ``scene`` = tests/conftest.Scene (synthetic body, our state dict); ``frame`` = scene.frame(idx)."""
     install()
@@ -256,7 +257,8 @@ def build_model(scene, frame, spp, gi=False, render_mode="light", add_emitter=Fa
     gcfg = load_yaml("geometry/progressive_hash_grid.yaml", **{"${model.radius}": 1.0})
     gcfg["isosurface"] = None
     rcfg = load_yaml("radiance/progressive_hash_grid.yaml", **{"${add:${model.geometry.feature_dim}, 3}": 16})
-    mcfg = load_yaml("material/shallow_mlp.yaml", **{"${add:${model.geometry.feature_dim}, 35}": 48})
+    mat_in = {"hybrid": 48, "geometry": 13, "radiance": 35}[material_feature]      # models/intrinsic_avatar.py:1102-1113
+    mcfg = load_yaml("material/shallow_mlp.yaml", **{"${add:${model.geometry.feature_dim}, 35}": mat_in})
     geo, rad, mat = ref_geo.VolumeSDF(gcfg), ref_rad.VolumeRefDirRadiance(rcfg), ref_mat.VolumeMaterial(mcfg)
     den = ref_den.LearnedLaplaceDensity(cfg({"params_init": {"beta": 0.1}, "beta_min": 0.0001}))
     sd = scene.state_dict
@@ -264,6 +266,11 @@ def build_model(scene, frame, spp, gi=False, render_mode="light", add_emitter=Fa
     geo.load_state_dict(sub("geometry."), strict=True)
     rad.load_state_dict(sub("radiance."), strict=False)
     msd = sub("material.")
+    if material_feature != "hybrid":
+        # the material net then sees only the geometry feature (13) / only the radiance encoding (35): the matching
+        # columns of the 48-wide first layer (weights.material_state_dict_for)
+        from intrinsicavatar_b200.weights import material_state_dict_for
+        msd = {k[len("material."):]: v for k, v in material_state_dict_for(sd, material_feature).items() if k.startswith("material.")}
     mat.load_state_dict(msd, strict=False)
     for i in range(3):
         mat.network.weights_per_layer[i].data.copy_(msd[f"network.layers.{i}.weight"])
@@ -326,14 +333,14 @@ def build_model(scene, frame, spp, gi=False, render_mode="light", add_emitter=Fa
                                  envlight_config=types.SimpleNamespace(scale=1.0, bias=0.0, base_res=8, hdr_filepath=None))
     m.emitter = ref_light.EnvironmentLightTensor(ecfg)
     m.emitter.train(False)
-    m.material_feature = "hybrid"
+    m.material_feature = material_feature
     aabb = torch.tensor([-1.25, -1.55, -1.25, 1.25, 0.95, 1.25])
     m.register_buffer("scene_aabb", aabb)
     m.randomized, m.background_color, m.samples_per_pixel = False, torch.ones(3), spp
     m.render_step_size = torch.norm(aabb[3:] - aabb[:3]).item() / 128
     m.num_samples_per_secondary_ray, m.secondary_near_plane, m.secondary_far_plane = 64, 0.0, 1.5
-    m.secondary_shader_chunk, m.secondary_importance_sample = 160000, True
-    m.enable_phys, m.importance_sample, m.add_emitter, m.zero_crossing_search = True, True, add_emitter, True
+    m.secondary_shader_chunk, m.secondary_importance_sample = 160000, secondary_importance_sample
+    m.enable_phys, m.importance_sample, m.add_emitter, m.zero_crossing_search = True, True, add_emitter, zero_crossing_search
     m.albedo_only, m.t_idx = False, 0.0
     m.train(False)
     geo.prepare_bbox(rigid.bbox)

@@ -49,6 +49,24 @@ def load_hi():
     return {k: z[k] for k in z.files}
 
 
+# The non-default switches of config.model (configs/config.yaml:53-54, 66): name, frame, image side, spp, global_illumination,
+# options.  tests/golden/reference_vectors_e2e_switch.npz = the reference's own forward_ on them (make_golden.py e2e_switch).
+GOLD_SWITCH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors_e2e_switch.npz")
+SWITCH_CASES = [
+    ("no_zero_crossing", 0, 16, 8, False, {"zero_crossing_search": False}),
+    ("no_zero_crossing_gi", 0, 12, 4, True, {"zero_crossing_search": False}),
+    ("no_importance", 0, 14, 4, False, {"secondary_importance_sample": False}),
+    ("no_importance_gi", 0, 10, 4, True, {"secondary_importance_sample": False}),
+    ("material_geometry", 0, 16, 4, False, {"material_feature": "geometry"}),
+    ("material_radiance", 0, 16, 4, False, {"material_feature": "radiance"}),
+]
+
+
+def load_switch():
+    z = np.load(GOLD_SWITCH)
+    return {k: z[k] for k in z.files}
+
+
 KEYS = ("comp_rgb", "comp_normal", "opacity", "depth", "comp_albedo", "comp_roughness", "comp_metallic", "comp_rgb_phys",
         "comp_demod_phys", "comp_rgb_full", "comp_rgb_phys_full", "comp_albedo_full", "comp_roughness_full")
 GRID_RES = 32

@@ -177,16 +177,19 @@ def test_ray_resampling_sdf_fine_vs_reference(eng):
         assert (other[2][same] - ref[2][same]).abs().max() < 2e-5, name
 
 
-def test_ray_resampling_fine_oracle_vs_reference():
+def test_ray_resampling_fine_vs_reference(eng):
     C = _ref("nerfacc_cuda")
     packed, starts, ends, sdfs, alphas, weights = _fake(2000, 5)
     ref = C.ray_resampling_fine(packed.cuda().int(), starts[:, None].cuda().contiguous(), ends[:, None].cuda().contiguous(),
                                 weights.cuda(), 4)
     orc = [t.cuda() for t in oops.ray_resampling_fine(packed, starts[:, None], ends[:, None], weights, 4)]
-    assert torch.equal(orc[0].int(), ref[0].int())
-    assert (orc[3] != ref[3]).float().mean() < 1e-3
-    same = orc[3] & ref[3]
-    assert (orc[1][same] - ref[1][same]).abs().max() < 2e-5
+    got = eng.op_ray_resampling_fine(packed, starts, ends, weights, 4)
+    for name, other in (("oracle", orc), ("product", got)):
+        assert torch.equal(other[0].int(), ref[0].int()), name
+        assert (other[3] != ref[3]).float().mean() < 1e-3, name
+        same = other[3] & ref[3]
+        assert (other[1][same] - ref[1][same]).abs().max() < 2e-5, name
+        assert (other[2][same] - ref[2][same]).abs().max() < 2e-5, name
 
 
 def test_unpack_vs_reference(eng):

@@ -280,6 +280,37 @@ def test_product_matches_reference_forward_hi_spp(scene, case):
         assert n_flip <= E2E.HI_MAX_FLIPS and full <= 5e-2, (name, k, n_flip, full)
 
 
+@pytest.mark.parametrize("case", E2E.SWITCH_CASES, ids=[c[0] for c in E2E.SWITCH_CASES])
+def test_product_matches_reference_forward_switches(scene, case):
+    """libia_b200 with the non-default switches of config.model -- zero_crossing_search = false, secondary_importance_sample =
+    false (with and without global illumination), material_feature = geometry | radiance -- against the reference's own
+    forward_ (tests/golden/reference_vectors_e2e_switch.npz): relative L2 <= 1e-3 on every buffer."""
+    from intrinsicavatar_b200.engine import RenderEngine
+    from intrinsicavatar_b200.weights import fold, material_state_dict_for
+    name, frame, side, spp, gi, opts = case
+    gold, base = E2E.load_switch(), E2E.load()
+    fr = scene.frame(frame)
+    mf = opts.get("material_feature", "hybrid")
+    if mf == "hybrid":
+        e = scene.engine()
+    else:
+        e = RenderEngine()
+        e.set_fields(fold(material_state_dict_for(scene.state_dict, mf), mf), scene.layout, scene.snarf.bbox)
+        e.set_lbs_voxels(scene.snarf.lbs_voxel, scene.snarf.offset_kernel, scene.snarf.scale_kernel)
+        e.set_render_config([-1.25, -1.55, -1.25, 1.25, 0.95, 1.25])
+    e.set_secondary_sampling(opts.get("secondary_importance_sample", True), opts.get("zero_crossing_search", True))
+    e.set_pose(fr["tfs"], fr["w2s"])
+    e.set_occupancy(fr["deformed_bbox"], E2E.grid(base, frame))
+    tabs = scene.syn.random_tables(spp, E2E.GRID_RES, seed=0)
+    e.set_light(scene.syn.load_envmap(), tabs["u1"], tabs["u2"])
+    rays = torch.from_numpy(scene.syn.make_rays(side, side, fr["transl"])).cuda()
+    got = e.render(rays, gi=gi, seed=0)
+    torch.cuda.synchronize()
+    for k in E2E.KEYS:
+        r = torch.from_numpy(gold[f"{name}/{k}"])
+        assert E2E.rel_l2(got[k], r) <= 1e-3, (name, k, E2E.rel_l2(got[k], r))
+
+
 @pytest.mark.parametrize("frame", [None, 0])
 def test_product_occupancy_grid_matches_reference(scene, frame):
     """ia_build_occupancy against the reference's own _compute_occupancy_grid (resolution 32, same jitter table)."""

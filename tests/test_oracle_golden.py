@@ -328,6 +328,34 @@ def test_oracle_matches_reference_forward_hi_spp(scene, case):
         assert E2E.rel_l2(got[k], r) <= 1e-4, (name, k, E2E.rel_l2(got[k], r))
 
 
+@pytest.mark.parametrize("case", E2E.SWITCH_CASES, ids=[c[0] for c in E2E.SWITCH_CASES])
+def test_oracle_matches_reference_forward_switches(scene, case):
+    """The non-default switches of config.model against the reference's own forward_: zero_crossing_search = false
+    (ray_resampling_fine, cdf.cu:403-478), secondary_importance_sample = false (models/intrinsic_avatar.py:482-520 skipped),
+    material_feature = geometry | radiance (:1102-1113)."""
+    from intrinsicavatar_b200.weights import fold, material_state_dict_for
+    from oracle.fields import Fields
+    from oracle.render import OracleRenderer
+    name, frame, side, spp, gi, opts = case
+    gold, base = E2E.load_switch(), E2E.load()
+    fr = scene.frame(frame)
+    mf = opts.get("material_feature", "hybrid")
+    fields = scene.fields if mf == "hybrid" else Fields(fold(material_state_dict_for(scene.state_dict, mf), mf), scene.layout,
+                                                        scene.snarf.bbox)
+    R = OracleRenderer(fields, scene.snarf.lbs_voxel, scene.snarf.offset_kernel, scene.snarf.scale_kernel,
+                       samples_per_pixel=spp, global_illumination=gi, grid_res=E2E.GRID_RES,
+                       **{k: v for k, v in opts.items() if k != "material_feature"})
+    R.set_pose(fr["tfs"], fr["w2s"])
+    R.binaries = E2E.grid(base, frame)
+    R.grid_aabb = torch.as_tensor(fr["deformed_bbox"], dtype=torch.float32)
+    tabs = scene.syn.random_tables(spp, E2E.GRID_RES, seed=0)
+    R.set_light(scene.syn.load_envmap(), tabs["u1"], tabs["u2"])
+    got = R.forward(torch.from_numpy(scene.syn.make_rays(side, side, fr["transl"])), seed=0)
+    for k in E2E.KEYS:
+        r = torch.from_numpy(gold[f"{name}/{k}"])
+        assert E2E.rel_l2(got[k], r) <= 1e-4, (name, k, E2E.rel_l2(got[k], r))
+
+
 @pytest.mark.parametrize("frame", [None, 0])
 def test_oracle_occupancy_grid_matches_reference(scene, frame):
     """OracleRenderer.build_occupancy against the reference's own _compute_occupancy_grid (models/intrinsic_avatar.py:
