@@ -224,6 +224,16 @@ int ia_op_broyden(ia_ctx* ctx, const float* d_xd, int64_t n, float* d_x, float* 
 int ia_op_query(ia_ctx* ctx, const float* d_xd, int64_t n, int with_grad, float* d_sdf, float* d_xc,
                 uint8_t* d_valid, float* d_grad, float* d_grad_cano, float* d_feature, void* stream);
 
+/* Training-mode building block: backward of VolumeSDF's network (models/rf/geometry.py:124-172:
+ * hash-grid encoding + VanillaMLP 35 -> 64 -> 13, models/network_utils.py:58-79, 201-244; the reference differentiates it
+ * with autograd through tiny-cuda-nn).  d_xc [n,3] canonical points, d_dout [n,13] upstream gradient of the 13 outputs
+ * (channel 0 = sdf).  ADDS into: d_g_hash [2 * n_entries] (gradient of the geometry hash table, the layout of the table),
+ * d_g_mlp [IA_GEO_END floats: W1^T [35][64] | b1 [64] | W2 [13][64] | b2 [16]] (gradient of the effective, weight-norm
+ * folded weights; 3152 floats); writes d_g_x [n,3] (may be NULL): gradient with respect to the canonical position.   */
+#define IA_GEO_GRAD_FLOATS 3152
+int ia_op_geometry_backward(ia_ctx* ctx, const float* d_xc, const float* d_dout, int64_t n, float* d_g_hash, float* d_g_mlp,
+                            float* d_g_x, void* stream);
+
 /* Canonical SDF of n points, evaluated the way the wavefront integrator's geometry phase does: hash grid, then the
  * 35 -> 64 layer as warp-level tensor-core mma (TF32 inputs split in two, fp32 accumulate), softplus(beta = 100), sdf row
  * of the output layer.  Replaces VolumeSDF.forward without gradient (models/rf/geometry.py:124-146: encoding ->

@@ -1016,4 +1016,21 @@ extern "C" int ia_voxelize_lbs(ia_ctx* c, const float* d_verts, const float* d_w
     return IA_OK;
 }
 
+// ================================================================================================
+// training-mode building block: backward of the canonical geometry network
+#include "ia_train.cuh"
+
+extern "C" int ia_op_geometry_backward(ia_ctx* c, const float* d_xc, const float* d_dout, int64_t n, float* d_g_hash,
+                                       float* d_g_mlp, float* d_g_x, void* stream) {
+    IA_REQUIRE(c && d_xc && d_dout && d_g_hash && d_g_mlp, IA_EINVAL, "ia_op_geometry_backward: NULL argument");
+    IA_REQUIRE(c->have_fields, IA_ESTATE, "ia_op_geometry_backward: call ia_set_fields first");
+    if (n == 0) return IA_OK;
+    IA_CHECK_CUDA(cudaSetDevice(c->device));
+    const size_t sm = 2 * IA_GEO_END * sizeof(float);
+    IA_CHECK_CUDA(cudaFuncSetAttribute(k_geometry_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_geometry_backward<<<ia_query_blocks(c, n), 256, sm, (cudaStream_t)stream>>>(c->f, d_xc, d_dout, n, d_g_hash, d_g_mlp, d_g_x);
+    IA_LAUNCH_CHECK();
+    return IA_OK;
+}
+
 #include "ia_render.cuh"

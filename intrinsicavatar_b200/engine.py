@@ -36,6 +36,7 @@ _ARGTYPES = {
     "ia_op_query": [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ia_op_shade_fields": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     "ia_op_geometry": [_vp, _vp, _i64, _vp, _vp],
+    "ia_op_geometry_backward": [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
     "ia_op_traverse": [_vp, _vp, _vp, _i64, _cf32, _cf32, _cf32] + [_vp] * 9 + [_vp],
     "ia_op_ray_resampling": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp] + [_vp] * 6 + [_vp],
     "ia_op_ray_resampling_merge": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp] + [_vp] * 6 + [_vp],
@@ -375,6 +376,21 @@ class RenderEngine:
             return sdf
         check(self.lib.ia_op_geometry(self.h, ptr(xc), xc.shape[0], ptr(sdf), _stream()), "ia_op_geometry")
         return sdf
+
+    def op_geometry_backward(self, xc, d_out):
+        """Gradients of sum_i <d_out[i], net(xc[i])> for the geometry network: dict with ``hash`` (the table's layout),
+        ``w1`` [64,35], ``b1`` [64], ``w2`` [13,64], ``b2`` [13] (effective weights) and ``x`` [n,3]."""
+        xc = xc.to(self.dev, torch.float32).contiguous()
+        d_out = d_out.to(self.dev, torch.float32).reshape(-1, 13).contiguous()
+        n = xc.shape[0]
+        g_hash = torch.zeros_like(self._keep["geo"])
+        g_mlp = torch.zeros(3152, device=self.dev)
+        g_x = torch.empty(n, 3, device=self.dev)
+        check(self.lib.ia_op_geometry_backward(self.h, ptr(xc), ptr(d_out), n, ptr(g_hash), ptr(g_mlp), ptr(g_x), _stream()),
+              "ia_op_geometry_backward")
+        w1t, b1 = g_mlp[:35 * 64].reshape(35, 64), g_mlp[35 * 64:36 * 64]
+        w2, b2 = g_mlp[36 * 64:49 * 64].reshape(13, 64), g_mlp[49 * 64:49 * 64 + 13]
+        return {"hash": g_hash, "w1": w1t.t().contiguous(), "b1": b1, "w2": w2, "b2": b2, "x": g_x}
 
     def op_traverse(self, rays_o, rays_d, near, far, step):
         o = rays_o.to(self.dev, torch.float32).contiguous()
