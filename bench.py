@@ -495,6 +495,7 @@ def main():
     with ClockSampler(local_rank, enabled=(rank == 0)) as clk:
         ms_total, stage_ms, cnts, launches = run_arm(args, False, args.steps, args.warmup, world == 1)
     clocks = clk.summary()
+    main_frames = [schedule[args.warmup + s] for s in range(args.steps)]     # (the later arms re-plan the schedule)
     value = samples_per_step * args.steps / (ms_total * 1e-3)
 
     e2e = None
@@ -538,7 +539,7 @@ def main():
         if world == 1 and stage_ms:
             per_frame = [sum(s[k] for k in ("setup", "primary", "resample", "shade", "composite") if s[k] >= 0) for s in stage_ms]
             line["frame_cost_spread_ms"] = {"min": min(per_frame), "max": max(per_frame),
-                                            "frames": [frame_of(args.warmup + s) for s in range(args.steps)],
+                                            "frames": main_frames,
                                             "ms": [round(v, 1) for v in per_frame]}
         if world > 1:
             line["frame_transport"] = collector.transport
