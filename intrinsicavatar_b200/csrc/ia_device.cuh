@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda_fp16.h>
 #include "ia_types.cuh"
+#include "ia_mma.cuh"
 
 #define IA_FULL_TEAM 0xFFFFu
 

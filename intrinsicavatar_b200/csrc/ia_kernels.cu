@@ -211,8 +211,40 @@ extern "C" int ia_set_fields(ia_ctx* c, const float* d_geo_hash, const float* d_
     put(IA_RAD_B2, rad_b2, 64); put(IA_RAD_W3, rad_w3, 3 * 64); put(IA_RAD_B3, rad_b3, 3);
     put_T(IA_MAT_W1T, mat_w1, 64, 48); put(IA_MAT_B1, mat_b1, 64); put_T(IA_MAT_W2T, mat_w2, 64, 64);
     put(IA_MAT_B2, mat_b2, 64); put(IA_MAT_W3, mat_w3, 5 * 64); put(IA_MAT_B3, mat_b3, 5);
-    if (ia_realloc(&c->d_mlp, IA_MLP_END)) return IA_ECUDA;
-    IA_CHECK_CUDA(cudaMemcpyAsync(c->d_mlp, blob.data(), IA_MLP_END * sizeof(float), cudaMemcpyHostToDevice,
+    // mma.sync B fragments (layout: ia_mma.cuh): frag(f0, k_steps, n_tiles, W) with W(k, n) = weight between input slot k and
+    // output n of the layer; layers fed from C fragments take their inputs in ia_kperm order
+    blob.resize(IA_BLOB_FLOATS, 0.f);
+    auto rna_tf32 = [](float x) {   // cvt.rna.tf32.f32: round the magnitude to 10 mantissa bits, ties away from zero
+        uint32_t u;
+        memcpy(&u, &x, 4);
+        u = (u + 0x1000u) & 0xffffe000u;
+        float r;
+        memcpy(&r, &u, 4);
+        return r;
+    };
+    auto frag = [&](int f0, int k_steps, int n_tiles, auto W) {
+        for (int s = 0; s < k_steps; s++)
+            for (int nt = 0; nt < n_tiles; nt++)
+                for (int lane = 0; lane < 32; lane++) {
+                    const int g = lane >> 2, t = lane & 3;
+                    float* d = &blob[IA_MLP_END + ((size_t)(f0 + s * n_tiles + nt) * 32 + lane) * 4];
+                    const float b0 = W(8 * s + t, 8 * nt + g), b1 = W(8 * s + t + 4, 8 * nt + g);
+                    d[0] = rna_tf32(b0); d[1] = rna_tf32(b0 - d[0]);
+                    d[2] = rna_tf32(b1); d[3] = rna_tf32(b1 - d[2]);
+                }
+    };
+    const float* B = blob.data();
+    auto geo_in = [](int k) { return k < 32 ? 3 + k : (k < 35 ? k - 32 : -1); };   // tile column -> geometry input
+    frag(IA_FRAG_FEAT, 8, 2, [&](int k, int n) { return n < 13 ? B[IA_GEO_W2 + n * 64 + ia_kperm(k)] : 0.f; });
+    frag(IA_FRAG_BWD, 8, 5, [&](int k, int n) { return geo_in(n) < 0 ? 0.f : B[IA_GEO_W1T + geo_in(n) * 64 + ia_kperm(k)]; });
+    frag(IA_FRAG_RAD1, 9, 8, [&](int k, int n) { return ia_rad_in_of(k) < 0 ? 0.f : B[IA_RAD_W1T + ia_rad_in_of(k) * 64 + n]; });
+    frag(IA_FRAG_RAD2, 8, 8, [&](int k, int n) { return B[IA_RAD_W2T + ia_kperm(k) * 64 + n]; });
+    frag(IA_FRAG_RAD3, 8, 1, [&](int k, int n) { return n < 3 ? B[IA_RAD_W3 + n * 64 + ia_kperm(k)] : 0.f; });
+    frag(IA_FRAG_MAT1, 6, 8, [&](int k, int n) { return ia_mat_in_of(k) < 0 ? 0.f : B[IA_MAT_W1T + ia_mat_in_of(k) * 64 + n]; });
+    frag(IA_FRAG_MAT2, 8, 8, [&](int k, int n) { return B[IA_MAT_W2T + ia_kperm(k) * 64 + n]; });
+    frag(IA_FRAG_MAT3, 8, 1, [&](int k, int n) { return n < 5 ? B[IA_MAT_W3 + n * 64 + ia_kperm(k)] : 0.f; });
+    if (ia_realloc(&c->d_mlp, IA_BLOB_FLOATS)) return IA_ECUDA;
+    IA_CHECK_CUDA(cudaMemcpyAsync(c->d_mlp, blob.data(), (size_t)IA_BLOB_FLOATS * sizeof(float), cudaMemcpyHostToDevice,
                                   (cudaStream_t)stream));
     IA_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));  // blob is a stack-scoped host buffer
     c->f.mlp = c->d_mlp;

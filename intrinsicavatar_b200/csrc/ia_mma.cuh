@@ -24,9 +24,12 @@ __device__ __forceinline__ uint32_t ia_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return u;
 }
+// x = hi + lo with hi = x rounded to TF32 (10 mantissa bits, ties away from zero -- what cvt.rna.tf32.f32 computes, without
+// its Inf / NaN guard: three extra instructions per conversion on sm_100a) and lo = x - hi (exact in fp32) TRUNCATED to
+// TF32: a relative error of 2^-21 of x at most.
 __device__ __forceinline__ void ia_split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    hi = ia_tf32(x);
-    lo = ia_tf32(x - __uint_as_float(hi));
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
 }
 __device__ __forceinline__ void ia_mma_tf32(float c[4], const uint32_t a[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -39,24 +42,6 @@ __device__ __forceinline__ void ia_mma_3xtf32(float c[4], const uint32_t ahi[4],
     ia_mma_tf32(c, alo, b0h, b1h);
     ia_mma_tf32(c, ahi, b0l, b1l);
     ia_mma_tf32(c, ahi, b0h, b1h);
-}
-
-// the same with an UNSPLIT fragment {b0, b1} (half the shared memory; the split costs four ALU operations per fragment)
-__device__ __forceinline__ void ia_mma_3xtf32(float c[4], const uint32_t ahi[4], const uint32_t alo[4], const float2 bf) {
-    uint32_t b0h, b0l, b1h, b1l;
-    ia_split_tf32(bf.x, b0h, b0l);
-    ia_split_tf32(bf.y, b1h, b1l);
-    ia_mma_tf32(c, alo, b0h, b1h);
-    ia_mma_tf32(c, ahi, b0l, b1l);
-    ia_mma_tf32(c, ahi, b0h, b1h);
-}
-template <class WFn>
-__device__ __forceinline__ void ia_stage_bfrag_raw(float2* dst, int k_steps, int n_tiles, WFn W) {
-    for (int i = threadIdx.x; i < k_steps * n_tiles * 32; i += blockDim.x) {
-        const int lane = i & 31, nt = (i >> 5) % n_tiles, s = (i >> 5) / n_tiles;
-        const int g = lane >> 2, t = lane & 3;
-        dst[i] = make_float2(W(8 * s + t, 8 * nt + g), W(8 * s + t + 4, 8 * nt + g));
-    }
 }
 
 // Pre-split B fragments of one dense layer y[n] = sum_k W(k, n) x[k]:
@@ -102,7 +87,7 @@ __device__ __forceinline__ void ia_mma_layer_smem(const float* __restrict__ xs, 
 // of a 64-wide layer is in C layout -- lane (g, t) holds columns 8nt + 2t, 8nt + 2t + 1 of rows g, g + 8 -- and is fed as
 // the A operand of k-step nt with the k order PERMUTED inside the step: slot t <- column 2t, slot t + 4 <- column 2t + 1.
 // The B fragments of that layer must be staged with the same permutation: ia_kperm(k) below.
-__device__ __forceinline__ int ia_kperm(int k) {   // k-slot -> input column of a layer fed from C fragments
+__host__ __device__ __forceinline__ int ia_kperm(int k) {   // k-slot -> input column of a layer fed from C fragments
     const int s = k >> 3, j = k & 7;
     return 8 * s + (j < 4 ? 2 * j : 2 * (j - 4) + 1);
 }
@@ -122,67 +107,62 @@ __device__ __forceinline__ void ia_mma_layer_regs(const float h[8][4], const BF*
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// The radiance network (models/rf/radiance.py:111-135: 67 -> 64 -> 64 -> 3, ReLU, sigmoid) for 16 points whose inputs sit
-// in a shared-memory tile, columns in the order
+// The radiance network (models/rf/radiance.py:111-135: 67 -> 64 -> 64 -> 3, ReLU, sigmoid) and the material network
+// (models/pbr/material.py:31-51: 48 -> 64 -> 64 -> 5) for 16 points whose inputs sit in a shared-memory "shading tile",
+// row-major with leading dimension IA_SHADE_LD, columns
 //   0..31 hash features | 32..34 the scaled position 2 xn - 1 | 35..47 geometry feature | 48..63 SH(reflected dir) |
-//   64..66 world normal | 67..71 zero
-// (the reference's input order is [xyz, hash, feature, SH, normal]: ia_rad_in_of maps a tile column to it).  The first 48
-// columns are the material network's input (cat[xyz_embd 35, feature 13], models/pbr/material.py:31-51).
-#define IA_RAD_K 72
-#define IA_RAD_LD 76
-__device__ __forceinline__ int ia_rad_in_of(int k) {    // tile column -> input index of the radiance net (-1: padding)
+//   64..66 world normal | 67 unused
+// (the reference's radiance input order is [xyz, hash, feature, SH, normal]: ia_rad_in_of maps a tile column to it; the
+// first 48 columns are the material network's input, cat[xyz_embd 35, feature 13]).  The radiance layer 1 runs 9 k-steps
+// = 72 columns: columns 67..71 carry zero weights and alias column 67 and the first four columns of the NEXT row, so every
+// float of the tile -- and the 16 bytes behind the last one -- must be finite.
+#define IA_SHADE_LD 68
+__host__ __device__ __forceinline__ int ia_rad_in_of(int k) {    // tile column -> input index of the radiance net (-1: padding)
     return k < 32 ? 3 + k : (k < 35 ? k - 32 : (k < 67 ? k : -1));
 }
-__device__ __forceinline__ int ia_mat_in_of(int k) {    // tile column -> input index of the material net (48 inputs)
+__host__ __device__ __forceinline__ int ia_mat_in_of(int k) {    // tile column -> input index of the material net (48 inputs)
     return k < 32 ? 3 + k : (k < 35 ? k - 32 : (k < 48 ? k : -1));
 }
-// fragment counts of the three layers
-#define IA_RAD_F1 (9 * 8)
-#define IA_RAD_F2 (8 * 8)
-#define IA_RAD_F3 (8 * 1)
-#define IA_RAD_FRAGS (IA_RAD_F1 + IA_RAD_F2 + IA_RAD_F3)
-#define IA_MAT_F1 (6 * 8)
-#define IA_MAT_FRAGS (IA_MAT_F1 + IA_RAD_F2 + IA_RAD_F3)
 
-// `wf`: IA_RAD_FRAGS * 32 unsplit fragments (layer 1 | layer 2 | layer 3); `wmlp`: the fp32 blob (biases).
-// Returns the pre-sigmoid outputs of rows g = lane >> 2 (lo) and g + 8 (hi) in the lanes with (lane & 3) == 0.
+// `wf`: pre-split fragments of the three layers, contiguous (layer 1 | layer 2 | layer 3: IA_FRAG_RAD1.. / IA_FRAG_MAT1..);
+// b1, b2, b3: the biases.  Every lane returns the N_OUT pre-activation outputs of row (lane & 15).
 template <int K1_STEPS, int N_OUT>
-__device__ __forceinline__ void ia_warp_mlp3(const float* __restrict__ xs, int ld, const float2* __restrict__ wf,
+__device__ __forceinline__ void ia_warp_mlp3(const float* __restrict__ xs, int ld, const float4* __restrict__ wf,
                                              const float* __restrict__ b1, const float* __restrict__ b2,
-                                             const float* __restrict__ b3, float lo[N_OUT], float hi[N_OUT]) {
+                                             const float* __restrict__ b3, float out[N_OUT]) {
     const int lane = threadIdx.x & 31, t = lane & 3;
     float c[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) {
-        const float2 b = *reinterpret_cast<const float2*>(b1 + 8 * nt + 2 * t);
+        const float2 b = __ldg(reinterpret_cast<const float2*>(b1 + 8 * nt + 2 * t));
         c[nt][0] = b.x; c[nt][1] = b.y; c[nt][2] = b.x; c[nt][3] = b.y;
     }
-    ia_mma_layer_smem<K1_STEPS, 8, 8, 16, float2>(xs, ld, wf, c);
+    ia_mma_layer_smem<K1_STEPS, 8, 8, 16>(xs, ld, wf, c);
     float h[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) {
-        const float2 b = *reinterpret_cast<const float2*>(b2 + 8 * nt + 2 * t);
+        const float2 b = __ldg(reinterpret_cast<const float2*>(b2 + 8 * nt + 2 * t));
 #pragma unroll
         for (int k = 0; k < 4; k++) h[nt][k] = fmaxf(c[nt][k], 0.f);
         c[nt][0] = b.x; c[nt][1] = b.y; c[nt][2] = b.x; c[nt][3] = b.y;
     }
-    ia_mma_layer_regs<8, float2>(h, wf + K1_STEPS * 8 * 32, c);
+    ia_mma_layer_regs<8>(h, wf + K1_STEPS * 8 * 32, c);
 #pragma unroll
     for (int nt = 0; nt < 8; nt++)
 #pragma unroll
         for (int k = 0; k < 4; k++) h[nt][k] = fmaxf(c[nt][k], 0.f);
     float o[1][4];
     {
-        const float bx = 2 * t < N_OUT ? b3[2 * t] : 0.f, by = 2 * t + 1 < N_OUT ? b3[2 * t + 1] : 0.f;
+        const float bx = 2 * t < N_OUT ? __ldg(b3 + 2 * t) : 0.f, by = 2 * t + 1 < N_OUT ? __ldg(b3 + 2 * t + 1) : 0.f;
         o[0][0] = bx; o[0][1] = by; o[0][2] = bx; o[0][3] = by;
     }
-    ia_mma_layer_regs<1, float2>(h, wf + (K1_STEPS * 8 + 64) * 32, o);
-    // lane (g, t) holds outputs 2t, 2t + 1 of rows g (o[0][0..1]) and g + 8 (o[0][2..3]): gather a row's outputs in its t = 0 lane
+    ia_mma_layer_regs<1>(h, wf + (K1_STEPS * 8 + 64) * 32, o);
+    // lane (g, t) holds outputs 2t, 2t + 1 of rows g (o[0][0..1]) and g + 8 (o[0][2..3]); row j wants them from lanes 4 (j & 7) + (k >> 1)
 #pragma unroll
     for (int k = 0; k < N_OUT; k++) {
-        const int src_t = k >> 1, comp = k & 1;
-        const float vlo = __shfl_sync(0xffffffffu, comp ? o[0][1] : o[0][0], (lane & ~3) + src_t);
-        const float vhi = __shfl_sync(0xffffffffu, comp ? o[0][3] : o[0][2], (lane & ~3) + src_t);
-        lo[k] = vlo; hi[k] = vhi;
+        const int src = 4 * (lane & 7) + (k >> 1);
+        const float vlo = __shfl_sync(0xffffffffu, (k & 1) ? o[0][1] : o[0][0], src);
+        const float vhi = __shfl_sync(0xffffffffu, (k & 1) ? o[0][3] : o[0][2], src);
+        out[k] = (lane & 8) ? vhi : vlo;
     }
 }

@@ -50,6 +50,18 @@ namespace cg = cooperative_groups;
 #define IA_MAT_W3 (IA_MAT_B2 + 64)            // [5][64]
 #define IA_MAT_B3 (IA_MAT_W3 + 5 * 64)        // [8]
 #define IA_MLP_END (IA_MAT_B3 + 8)
+// Behind the fp32 blob: mma.sync B fragments of the layers the tensor-core shading paths use (ia_mma.cuh), one float4
+// {b0_hi, b0_lo, b1_hi, b1_lo} (TF32 split) per lane, [k-step][n-tile][32 lanes] per layer; built on the host by ia_set_fields.
+#define IA_FRAG_FEAT 0                          // geometry 64 -> 13 (8 k-steps x 2 n-tiles), A from C fragments
+#define IA_FRAG_BWD (IA_FRAG_FEAT + 8 * 2)      // d sdf / d input: hidden 64 -> 35 tile columns (8 x 5), A from C fragments
+#define IA_FRAG_RAD1 (IA_FRAG_BWD + 8 * 5)      // radiance 67 -> 64 (9 x 8), A from the shading tile
+#define IA_FRAG_RAD2 (IA_FRAG_RAD1 + 9 * 8)     // radiance 64 -> 64 (8 x 8), A from C fragments
+#define IA_FRAG_RAD3 (IA_FRAG_RAD2 + 8 * 8)     // radiance 64 -> 3 (8 x 1)
+#define IA_FRAG_MAT1 (IA_FRAG_RAD3 + 8)         // material 48 -> 64 (6 x 8), A from the shading tile
+#define IA_FRAG_MAT2 (IA_FRAG_MAT1 + 6 * 8)     // material 64 -> 64
+#define IA_FRAG_MAT3 (IA_FRAG_MAT2 + 8 * 8)     // material 64 -> 5 (8 x 1)
+#define IA_FRAG_END (IA_FRAG_MAT3 + 8)
+#define IA_BLOB_FLOATS (IA_MLP_END + IA_FRAG_END * 128)
 
 #define IA_SEC_ZERO_CROSSING 0
 #define IA_SEC_IMPORTANCE 1

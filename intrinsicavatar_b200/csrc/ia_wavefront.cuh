@@ -19,7 +19,6 @@
 // Same arithmetic, in the same order, as the reference (models/intrinsic_avatar.py:396-545; cdf.cu:536-638;
 // fuse_cuda_kernel_fast.cu:250-413; filter.cu:10-54); only the accumulation order into a pixel differs.
 #pragma once
-#include "ia_mma.cuh"
 
 #ifndef WF_THREADS
 #define WF_THREADS 512
@@ -61,10 +60,6 @@
 #ifndef WF_STATE_GLOBAL
 #define WF_STATE_GLOBAL 1
 #endif
-#ifndef WF_GI_WEIGHTS_SMEM
-#define WF_GI_WEIGHTS_SMEM 1  // global illumination: 1 = the radiance MLP (47 KB) is staged in shared memory next to the geometry
-#endif                        // MLP; 0 = it is read through L1 while the GI phase runs, leaving that capacity to the Broyden gathers.
-                              // Measured at 512^2 x 1024 spp, GI on: shade 887 ms (1) vs 938 ms (0)
 #ifndef WF_BTASK_SMEM
 #define WF_BTASK_SMEM 0   // 1: Broyden task list in shared memory, so that a chain start reads its task id with shared-memory
 #endif                    // latency (from the global scratch that read is an exposed L2 round trip: 6 % of the Broyden phase's
@@ -105,6 +100,11 @@ enum { WF_ACT_NEXT = 0, WF_ACT_CDF = 1, WF_ACT_FINE_START = 2, WF_ACT_FINISH = 3
 #define WS_TPL 27     // 27..31
 #define WS_IND 32      // 32..34 indirect radiance accumulated over the fine samples (global illumination)
 
+#define IA_GEO_KSTEPS 5   // geometry tile: [16][IA_GEO_LD], 40 columns read (layout: ia_warp_geometry)
+#define IA_GEO_LD 44
+// per-warp input tiles of the tensor-core phases: [16][IA_GEO_LD] for the geometry phase; with global illumination the same
+// memory is the [16][IA_SHADE_LD] shading tile of the GI phase (+ 4 floats: its last k-step reads 16 bytes past the end)
+#define WF_TILE_FLOATS(GI) ((WF_THREADS / 32) * 16 * ((GI) ? IA_SHADE_LD : 44) + 4)
 struct WfShared {
     float* w;               // MLP weights staged behind this struct (geometry only, or geometry + radiance for GI)
     float tfs13[IA_N_INIT * 12];
@@ -143,6 +143,14 @@ struct WfShared {
     int n_q, task_next, n_gtask, ring_head, ring_tail, tile, more_tiles, pad;
     unsigned cnt[8];        // work counters of this CTA (WF_C_*), flushed to the global counters when the kernel ends
 };
+
+// The arrays staged behind the struct, addressed from &S (an address the compiler can prove to be shared memory: loads and
+// stores through the pointer FIELDS S.w / S.w1f / S.xs compile to generic LD / ST)
+__device__ __forceinline__ float* wf_w(WfShared& S) {
+    return reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&S) + ((sizeof(WfShared) + 15) & ~(size_t)15));
+}
+__device__ __forceinline__ float4* wf_w1f(WfShared& S) { return reinterpret_cast<float4*>(wf_w(S) + IA_GEO_END); }
+__device__ __forceinline__ float* wf_xs(WfShared& S) { return reinterpret_cast<float*>(wf_w1f(S) + IA_GEO_KSTEPS * 8 * 32); }
 
 // ------------------------------------------------------------------------------------------------
 // marcher <-> shared state
@@ -413,8 +421,6 @@ __device__ __forceinline__ void wf_filter_phase(WfShared& S, int n_q) {
 // SDF of up to 16 canonical points by one warp on the tensor cores (ia_mma.cuh).  Lane j < n_pts holds point j in
 // (px, py, pz); returns the sdf of point j in lane j < 16.  Tile columns: 0..31 hash features (level l: 2l, 2l + 1),
 // 32..34 the scaled position 2 xn - 1, 35..39 zero (set once at kernel start, never written).
-#define IA_GEO_KSTEPS 5
-#define IA_GEO_LD 44
 #ifndef WF_MMA_ROWS
 #define WF_MMA_ROWS 16   // points per tensor-core batch of a warp: 16 (the full m16 tile) or 8 (half the shared memory for the input
 #endif                   // tiles -- L1 capacity for the gathers -- at twice the weight-fragment reads per point)
@@ -478,7 +484,7 @@ __device__ __forceinline__ void wf_geometry_phase(const IaFrame& p, WfShared& S)
     // an even split of the task list over the warps (the gathers of step A are the cost, and they are per point)
     const int per = (n + n_warps - 1) / n_warps;
     const int end = min(n, (warp + 1) * per);
-    float* xs = S.xs + warp * WF_MMA_ROWS * IA_GEO_LD;
+    float* xs = wf_xs(S) + warp * WF_MMA_ROWS * IA_GEO_LD;
     // software pipeline: the task ids and roots of the NEXT batch (two dependent L2 round trips: the lists were just
     // written by other warps) are fetched while the current one is evaluated
     int b0 = warp * per;
@@ -501,43 +507,185 @@ __device__ __forceinline__ void wf_geometry_phase(const IaFrame& p, WfShared& S)
             const float* cd = S.cand + ci_n * 3;
             y0 = cd[0]; y1 = cd[1]; y2 = cd[2];
         }
-        const float s = ia_warp_geometry<WF_MMA_ROWS>(p, S.lvl, S.w, S.w1f, xs, x0, x1, x2, nb);
+        const float s = ia_warp_geometry<WF_MMA_ROWS>(p, S.lvl, wf_w(S), wf_w1f(S), xs, x0, x1, x2, nb);
         if (lane < nb) { S.csdf[ci] = s; c_geo++; }
         b0 = bn; ci = ci_n; x0 = y0; x1 = y1; x2 = y2;
     }
     wf_count(S, WF_C_GEO, c_geo);
 }
 
-// GI: radiance at the arg-min root of every fine sample consumed this round (rgb_alpha_fn,
-// models/intrinsic_avatar.py:430-456): geometry with gradient + feature, blended forward rotation, radiance MLP.
-__device__ __forceinline__ void wf_gi_phase(const IaFrame& p, WfShared& S) {
-    unsigned c_qg = 0;
-    Team team = cg::tiled_partition<IA_TEAM>(cg::this_thread_block());
-    const int n = S.n_gitask;
-    const int n_teams = blockDim.x / IA_TEAM;
-    for (int k = threadIdx.x / IA_TEAM; k < n; k += n_teams) {
-        const uint2 tk = S.gitask[k];
-        const int t = tk.x & 0xffffu, c = tk.x >> 16;
-        const float w = __uint_as_float(tk.y);
-        const float* cd = S.cand + (t * IA_N_INIT + c) * 3;
-        const float xc[3] = {cd[0], cd[1], cd[2]};
-        const float d[3] = {S.st[WS_D][t], S.st[WS_D + 1][t], S.st[WS_D + 2][t]};
-        float feat[13], gc[3], R[9];
-        ia_team_geometry<true>(team, p, S.w, xc, feat, gc, S.lvl);
-        ia_team_fwd_rotation(team, p, xc, R);
-        const float g[3] = {R[0] * gc[0] + R[1] * gc[1] + R[2] * gc[2], R[3] * gc[0] + R[4] * gc[1] + R[5] * gc[2],
-                            R[6] * gc[0] + R[7] * gc[1] + R[8] * gc[2]};
-        float nw[3], view_w[3], rgb[3];
-        ia_dir_s2w(p, g, nw);
-        ia_dir_s2w(p, d, view_w);
-        ia_team_radiance<false>(team, p, WF_GI_WEIGHTS_SMEM ? S.w : p.mlp, xc, feat, view_w, nw, rgb, nullptr);
-        if (team.thread_rank() == 0) {
-#pragma unroll
-            for (int ch = 0; ch < 3; ch++) S.st[WS_IND + ch][t] += w * rgb[ch];
-            c_qg++;
+// ------------------------------------------------------------------------------------------------
+// Tensor-core shading of up to 16 canonical points by one warp: geometry feature + SDF gradient, blended forward rotation,
+// radiance network (rgb_alpha_fn, models/intrinsic_avatar.py:430-456; models/rf/geometry.py:147-172 forward + autograd
+// normal; models/rf/radiance.py:111-135).  Lane j < 16 passes point j (canonical root) and its ray direction (SMPL space);
+// lanes j and j + 16 return rgb of point j.  `xs` is the warp's shading tile [16][IA_SHADE_LD] (layout: ia_mma.cuh).
+//   A1  hash-grid features of the geometry network, two points per trip (lane = level)             -> tile cols 0..34
+//   B   35 -> 64 layer as 3xTF32 mma, softplus; the 64 -> 13 layer (feature) and the BACKWARD of the sdf row through the
+//       35 -> 64 layer (d sdf / d tile column), both fed from the accumulator registers            -> cols 35..47, 0..31, 64..66
+//   A2  per point (16-lane team): hash-grid gradient (corners re-gathered, L1-hot) x d sdf / d feature -> canonical normal,
+//       blended rotation -> world normal, reflected direction -> SH, radiance hash features        -> cols 0..31, 48..66
+//   C   radiance network 67 -> 64 -> 64 -> 3 as 3xTF32 mma, sigmoid
+// The weights of B (second half) and C are read as B fragments straight from global memory (IA_FRAG_*, 102 KB pre-split, L1-resident
+// while this phase runs and evicted for the voxel gathers otherwise) instead of living in shared memory.
+__device__ __forceinline__ void ia_warp_radiance16(const IaFrame& p, const IaLevel* __restrict__ lvl, const float* __restrict__ w,
+                                                   const float4* __restrict__ w1f, float* __restrict__ xs, float px, float py,
+                                                   float pz, float dx, float dy, float dz, int n_pts, float rgb[3]) {
+    const unsigned FULL = 0xffffffffu;
+    constexpr int LD = IA_SHADE_LD;
+    const int lane = threadIdx.x & 31, l = lane & 15, half = lane >> 4, g = lane >> 2, t = lane & 3;
+    const float4* frags = reinterpret_cast<const float4*>(p.mlp + IA_MLP_END);
+    // ---- A1
+#pragma unroll 1
+    for (int i = 0; i < n_pts; i += 2) {
+        const int r = i + half;
+        const float x0 = __shfl_sync(FULL, px, r & 15), x1 = __shfl_sync(FULL, py, r & 15), x2 = __shfl_sync(FULL, pz, r & 15);
+        if (r < n_pts) {
+            float xn[3] = {(x0 - p.center[0]) / p.scale[0] + 0.5f, (x1 - p.center[1]) / p.scale[1] + 0.5f,
+                           (x2 - p.center[2]) / p.scale[2] + 0.5f};
+            float f0, f1;
+            ia_hash_level<false>(p.geo_hash, lvl[l], xn, f0, f1, nullptr);
+            *reinterpret_cast<float2*>(xs + r * LD + 2 * l) = make_float2(f0, f1);
+            if (l < 3) xs[r * LD + 32 + l] = xn[l] * 2.0f - 1.0f;
         }
     }
-    wf_count(S, WF_C_QG, c_qg);   // = geometry evaluations with gradient = radiance evaluations = skinning fetches of this phase
+    __syncwarp();
+    // ---- B
+    {
+        float c[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            const float2 b = *reinterpret_cast<const float2*>(w + IA_GEO_B1 + 8 * nt + 2 * t);
+            c[nt][0] = b.x; c[nt][1] = b.y; c[nt][2] = b.x; c[nt][3] = b.y;
+        }
+        ia_mma_layer_smem<IA_GEO_KSTEPS, 8, 8, 16>(xs, LD, w1f, c);
+        __syncwarp();   // columns 0..39 of the tile are free
+        // h = softplus_100(pre) in place; delta = W2[0][n] softplus'(pre) = W2[0][n] sigmoid(100 pre)
+        float dl[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            const float2 w2 = *reinterpret_cast<const float2*>(w + IA_GEO_W2 + 8 * nt + 2 * t);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float x = c[nt][k];
+                dl[nt][k] = ((k & 1) ? w2.y : w2.x) * ia_sigmoid(100.f * x);
+                c[nt][k] = ia_softplus100(x);
+            }
+        }
+        float f[2][4];
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+            const float2 b = *reinterpret_cast<const float2*>(w + IA_GEO_B2 + 8 * nt + 2 * t);   // [16], 13 used, rest 0
+            f[nt][0] = b.x; f[nt][1] = b.y; f[nt][2] = b.x; f[nt][3] = b.y;
+        }
+        ia_mma_layer_regs<2>(c, frags + IA_FRAG_FEAT * 32, f);
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int col = 8 * nt + 2 * t + k;
+                if (col < 13) { xs[g * LD + 35 + col] = f[nt][k]; xs[(g + 8) * LD + 35 + col] = f[nt][2 + k]; }
+            }
+        float gi[5][4];
+#pragma unroll
+        for (int nt = 0; nt < 5; nt++) gi[nt][0] = gi[nt][1] = gi[nt][2] = gi[nt][3] = 0.f;
+        ia_mma_layer_regs<5>(dl, frags + IA_FRAG_BWD * 32, gi);
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            *reinterpret_cast<float2*>(xs + g * LD + 8 * nt + 2 * t) = make_float2(gi[nt][0], gi[nt][1]);
+            *reinterpret_cast<float2*>(xs + (g + 8) * LD + 8 * nt + 2 * t) = make_float2(gi[nt][2], gi[nt][3]);
+        }
+        // d sdf / d (2 xn - 1): tile columns 32..34 keep the position for the radiance network, the gradient goes to 64..66
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int col = 2 * t + k;
+            if (col < 3) { xs[g * LD + 64 + col] = gi[4][k]; xs[(g + 8) * LD + 64 + col] = gi[4][2 + k]; }
+        }
+    }
+    __syncwarp();
+    // ---- A2
+    Team team = cg::tiled_partition<IA_TEAM>(cg::this_thread_block());   // = half-warp: lane l, point i + half
+#pragma unroll 1
+    for (int i = 0; i < n_pts; i += 2) {
+        const int r = i + half;
+        const float x0 = __shfl_sync(FULL, px, r & 15), x1 = __shfl_sync(FULL, py, r & 15), x2 = __shfl_sync(FULL, pz, r & 15);
+        const float d0 = __shfl_sync(FULL, dx, r & 15), d1 = __shfl_sync(FULL, dy, r & 15), d2 = __shfl_sync(FULL, dz, r & 15);
+        if (r < n_pts) {
+            float* row = xs + r * LD;
+            const float xc[3] = {x0, x1, x2};
+            float xn[3] = {(x0 - p.center[0]) / p.scale[0] + 0.5f, (x1 - p.center[1]) / p.scale[1] + 0.5f,
+                           (x2 - p.center[2]) / p.scale[2] + 0.5f};
+            float f0, f1, dfdx[6];
+            ia_hash_level<true>(p.geo_hash, lvl[l], xn, f0, f1, dfdx);
+            const float2 gf = *reinterpret_cast<const float2*>(row + 2 * l);
+            float gc[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+                gc[d] = (row[64 + d] * 2.0f + ia_team_sum(team, gf.x * dfdx[d * 2 + 0] + gf.y * dfdx[d * 2 + 1])) / p.scale[d];
+            float R[9];
+            ia_team_fwd_rotation(team, p, xc, R);
+            const float gs[3] = {R[0] * gc[0] + R[1] * gc[1] + R[2] * gc[2], R[3] * gc[0] + R[4] * gc[1] + R[5] * gc[2],
+                                 R[6] * gc[0] + R[7] * gc[1] + R[8] * gc[2]};
+            const float dir[3] = {d0, d1, d2};
+            float nw[3], view_w[3];
+            ia_dir_s2w(p, gs, nw);
+            ia_dir_s2w(p, dir, view_w);
+            ia_hash_level<false>(p.rad_hash, lvl[l], xn, f0, f1, nullptr);
+            // reflect(-view, n) (models/utils.py:115), then the (d + 1) / 2 -> 2 x - 1 round trip of the encoding
+            const float v[3] = {-view_w[0], -view_w[1], -view_w[2]};
+            const float dn = v[0] * nw[0] + v[1] * nw[1] + v[2] * nw[2];
+            float rr[3], sh[16];
+#pragma unroll
+            for (int d = 0; d < 3; d++) rr[d] = ((2.f * dn * nw[d] - v[d] + 1.f) / 2.f) * 2.f - 1.f;
+            ia_sh4(rr[0], rr[1], rr[2], sh);
+            float my_sh = 0.f, my_n = 0.f;
+#pragma unroll
+            for (int o = 0; o < 16; o++) my_sh = l == o ? sh[o] : my_sh;
+#pragma unroll
+            for (int o = 0; o < 3; o++) my_n = l == o ? nw[o] : my_n;
+            team.sync();   // every lane of the team has read the row's gradient columns
+            *reinterpret_cast<float2*>(row + 2 * l) = make_float2(f0, f1);
+            row[48 + l] = my_sh;
+            if (l < 3) row[64 + l] = my_n;
+        }
+    }
+    __syncwarp();
+    // ---- C
+    float o[3];
+    ia_warp_mlp3<9, 3>(xs, LD, frags + IA_FRAG_RAD1 * 32, p.mlp + IA_RAD_B1, p.mlp + IA_RAD_B2, p.mlp + IA_RAD_B3, o);
+#pragma unroll
+    for (int k = 0; k < 3; k++) rgb[k] = ia_sigmoid(o[k]);
+    __syncwarp();   // the tile may be overwritten by the next batch
+}
+
+// GI: radiance at the arg-min root of every fine sample consumed this round.
+__device__ __forceinline__ void wf_gi_phase(const IaFrame& p, WfShared& S) {
+    const int n = S.n_gitask;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    const int per = (n + n_warps - 1) / n_warps;
+    const int end = min(n, (warp + 1) * per);
+    float* xs = wf_xs(S) + warp * 16 * IA_SHADE_LD;
+    for (int b0 = warp * per; b0 < end; b0 += 16) {
+        const int nb = min(16, end - b0);
+        int t = 0;
+        float wgt = 0.f, x0 = 0.f, x1 = 0.f, x2 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 1.f;
+        if ((lane & 15) < nb) {
+            const uint2 tk = S.gitask[b0 + (lane & 15)];
+            t = tk.x & 0xffffu;
+            wgt = __uint_as_float(tk.y);
+            const float* cd = S.cand + (t * IA_N_INIT + (int)(tk.x >> 16)) * 3;
+            x0 = cd[0]; x1 = cd[1]; x2 = cd[2];
+            d0 = S.st[WS_D][t]; d1 = S.st[WS_D + 1][t]; d2 = S.st[WS_D + 2][t];
+        }
+        float rgb[3];
+        ia_warp_radiance16(p, S.lvl, wf_w(S), wf_w1f(S), xs, x0, x1, x2, d0, d1, d2, nb, rgb);
+        if (lane < nb) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) S.st[WS_IND + ch][t] += wgt * rgb[ch];
+        }
+    }
+    // the geometry phase reads columns 35..39 of ITS tile layout ([16][IA_GEO_LD] at the same address) against zero weights
+    for (int i = lane; i < WF_MMA_ROWS * 5; i += 32) xs[(i / 5) * IA_GEO_LD + 35 + i % 5] = 0.f;
+    wf_count(S, WF_C_QG, (lane == 0 && end > warp * per) ? (unsigned)(end - warp * per) : 0u);   // = geometry evaluations with gradient = radiance evaluations = skinning fetches of this phase
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -837,7 +985,7 @@ template <bool GI, class P>
 __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, unsigned char* __restrict__ scratch,
                                        unsigned long long* __restrict__ counters) {
     const int tid = threadIdx.x;
-    const int n_w = (GI && WF_GI_WEIGHTS_SMEM) ? IA_RAD_END : IA_GEO_END;
+    const int n_w = IA_GEO_END;
     if (tid == 0) {
         unsigned char* mine = scratch + (size_t)blockIdx.x * WF_SCRATCH_BYTES;
         S.w = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&S) + ((sizeof(WfShared) + 15) & ~15));
@@ -858,7 +1006,7 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
     for (int i = tid * 4; i < n_w; i += blockDim.x * 4)
         *reinterpret_cast<float4*>(S.w + i) = __ldg(reinterpret_cast<const float4*>(p.mlp + i));
     ia_stage_bfrag(S.w1f, IA_GEO_KSTEPS, 8, [&](int k, int n) { return ia_geo_w1(p.mlp, k, n); });
-    for (int i = tid; i < (int)(blockDim.x >> 5) * WF_MMA_ROWS * IA_GEO_LD; i += blockDim.x) S.xs[i] = 0.f;
+    for (int i = tid; i < (int)(WF_TILE_FLOATS(GI)); i += blockDim.x) S.xs[i] = 0.f;
     if (tid < IA_N_INIT * 12) S.tfs13[tid] = p.tfs[p.init_bones[tid / 12]][tid % 12];
     if (tid < IA_N_LEVELS) S.lvl[tid] = ia_level(p, tid);
     for (int t = tid; t < WF_R; t += blockDim.x) S.st[WS_PACK][t] = __uint_as_float(0u);
@@ -1131,8 +1279,8 @@ struct WfShadePolicy {
     }
 };
 
-#define WF_SMEM_BYTES(GI) (((sizeof(WfShared) + 15) & ~(size_t)15) + (((GI) && WF_GI_WEIGHTS_SMEM) ? IA_RAD_END : IA_GEO_END) * sizeof(float) + \
-                           IA_GEO_KSTEPS * 8 * 32 * sizeof(float4) + (WF_THREADS / 32) * WF_MMA_ROWS * IA_GEO_LD * sizeof(float))
+#define WF_SMEM_BYTES(GI) (((sizeof(WfShared) + 15) & ~(size_t)15) + IA_GEO_END * sizeof(float) + \
+                           IA_GEO_KSTEPS * 8 * 32 * sizeof(float4) + WF_TILE_FLOATS(GI) * sizeof(float))
 
 template <bool GI, int MODE>
 __global__ void __launch_bounds__(WF_THREADS, WF_CTAS_PER_SM) k_shade_wf(const __grid_constant__ IaFrame p, WfShadePolicy<MODE> pol,

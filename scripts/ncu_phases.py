@@ -5,14 +5,17 @@ wavefronts, a few marker opcodes (HMMA = tensor-core geometry phase, LDG.E.128 =
 barrier is sampled at the first instruction AFTER it, so a barrier wait is listed with the segment that follows it
 (column `first`: samples on the segment's first instruction).
 
-usage: python scripts/ncu_phases.py report.ncu-rep [kernel-name substring]"""
+usage: python scripts/ncu_phases.py report.ncu-rep [kernel-name substring] [--warpsync]
+--warpsync also cuts at WARPSYNC instructions (the stages of the tensor-core phases inside one barrier interval)."""
 import csv
 import io
 import subprocess
 import sys
 
-rep = sys.argv[1]
-want = sys.argv[2] if len(sys.argv) > 2 else "k_shade_wf"
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+cuts = ("BAR.SYNC", "WARPSYNC") if "--warpsync" in sys.argv else ("BAR.SYNC",)
+rep = args[0]
+want = args[1] if len(args) > 1 else "k_shade_wf"
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 blocks, cur = [], None
 for line in out.splitlines():
@@ -37,7 +40,7 @@ for b in blocks:
     segs, seg = [], {"rows": []}
     for r in rows:
         seg["rows"].append(r)
-        if "BAR.SYNC" in r[col["Source"]]:
+        if any(c in r[col["Source"]] for c in cuts):
             segs.append(seg)
             seg = {"rows": []}
     segs.append(seg)
