@@ -289,10 +289,136 @@ k_prim_edges(const __grid_constant__ IaFrame p, const float* __restrict__ hit_od
     if (c_fetch) atomicAdd(&counters[IA_CNT_BROYDEN_FETCH], c_fetch);
 }
 
-// rendering_with_normals_mats_sdf's per-sample part (rgb_normal_mats_alpha_fn, models/intrinsic_avatar.py:1066-1156)
+// rendering_with_normals_mats_sdf's per-sample part (rgb_normal_mats_alpha_fn, models/intrinsic_avatar.py:1066-1156).
+// A warp owns 16 consecutive shading samples: its two 16-lane teams run the fused query (Broyden + geometry with gradient +
+// blended rotation) sample by sample and leave the inputs of the two colour networks as a row of the warp's shading tile
+// (ia_mma.cuh); the radiance (67 -> 64 -> 64 -> 3) and material (48 -> 64 -> 64 -> 5) networks then run once per 16 samples
+// on the tensor cores (3xTF32 mma.sync, pre-split B fragments from global memory through L1).  IA_PRIM_SHADE_MMA=0: the
+// round-1 form (both networks per sample on the 16 lanes of the team, all weights in shared memory).
 #ifndef IA_PRIM_SHADE_CTAS
 #define IA_PRIM_SHADE_CTAS 2
 #endif
+#ifndef IA_PRIM_SHADE_MMA
+#define IA_PRIM_SHADE_MMA 1
+#endif
+#if IA_PRIM_SHADE_MMA
+#define IA_PRIM_SHADE_SMEM ((IA_GEO_END + (IA_PRIMARY_THREADS / 32) * 16 * IA_SHADE_LD + 4) * sizeof(float))
+__global__ void __launch_bounds__(IA_PRIMARY_THREADS, IA_PRIM_SHADE_CTAS)
+k_prim_shade(const __grid_constant__ IaFrame p, const float* __restrict__ hit_od, IaSample* __restrict__ samples,
+             IaSampleAux* __restrict__ aux, long long sample_cap, const int* __restrict__ work,
+             unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) float smem[];
+    float* wgeo = smem;
+    float* xs_all = smem + IA_GEO_END;
+    ia_stage(wgeo, p.mlp, IA_GEO_END);
+    for (int i = threadIdx.x; i < (IA_PRIMARY_THREADS / 32) * 16 * IA_SHADE_LD + 4; i += blockDim.x) xs_all[i] = 0.f;
+    __syncthreads();
+    Team team = cg::tiled_partition<IA_TEAM>(cg::this_thread_block());
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, l = lane & 15, half = lane >> 4, warp = threadIdx.x >> 5;
+    float* xs = xs_all + warp * 16 * IA_SHADE_LD;
+    const float4* frags = reinterpret_cast<const float4*>(p.mlp + IA_MLP_END);
+    const long long n = min((long long)work[IA_W_NSAMPLES], sample_cap);
+    const long long n_batches = (n + 15) / 16;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    unsigned c_qg = 0, c_fetch = 0, c_geo = 0, c_rad = 0;
+    for (long long bb = (long long)blockIdx.x * (blockDim.x >> 5); bb < n_batches; bb += warps) {
+        const long long b = bb + warp;
+        unsigned vmask = 0;
+#pragma unroll 1
+        for (int r0 = 0; r0 < 16; r0 += 2) {
+            const int r = r0 + half;
+            const long long i = b * 16 + r;
+            const int slot = (b < n_batches && i < n) ? aux[i].slot : -1;
+            if (slot < 0) continue;  // past the end, or the dead record of a ray that did not fit the pool (k_prim_edges)
+            const float* od = hit_od + (size_t)slot * 8;
+            const float o[3] = {od[0], od[1], od[2]}, d[3] = {od[3], od[4], od[5]};
+            const float ts = samples[i].ts, te = samples[i].te;
+            const float tm = (ts + te) / 2.0f;
+            float x[3] = {o[0] + d[0] * tm, o[1] + d[1] * tm, o[2] + d[2] * tm};
+            IaQuery q;
+            ia_team_query<true>(team, p, wgeo, x, q);
+            c_qg++; c_fetch += q.n_fetch; c_geo += q.n_valid + (q.valid ? 1 : 0);
+            float view_w[3], nsm[3], nw[3];
+            ia_dir_s2w(p, d, view_w);
+            ia_normalize(q.grad, nsm, 1e-6f);
+            ia_dir_s2w(p, q.grad, nw);
+            if (q.valid) {
+                // the row of the shading tile: radiance hash features, position, geometry feature, SH(reflected dir), normal
+                float* row = xs + r * IA_SHADE_LD;
+                float xn[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) xn[k] = (q.xc[k] - p.center[k]) / p.scale[k] + 0.5f;
+                float f0, f1;
+                ia_hash_level<false>(p.rad_hash, ia_level(p, l), xn, f0, f1, nullptr);
+                const float v[3] = {-view_w[0], -view_w[1], -view_w[2]};
+                const float dn = v[0] * nw[0] + v[1] * nw[1] + v[2] * nw[2];
+                float rr[3], sh[16];
+#pragma unroll
+                for (int k = 0; k < 3; k++) rr[k] = ((2.f * dn * nw[k] - v[k] + 1.f) / 2.f) * 2.f - 1.f;
+                ia_sh4(rr[0], rr[1], rr[2], sh);
+                float my_sh = 0.f, my_f = 0.f, my_3 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 16; k++) my_sh = l == k ? sh[k] : my_sh;
+#pragma unroll
+                for (int k = 0; k < 13; k++) my_f = l == k ? q.feat[k] : my_f;
+#pragma unroll
+                for (int k = 0; k < 3; k++) my_3 = l == k ? xn[k] * 2.0f - 1.0f : (l == 3 + k ? nw[k] : my_3);
+                *reinterpret_cast<float2*>(row + 2 * l) = make_float2(f0, f1);
+                row[48 + l] = my_sh;
+                if (l < 13) row[35 + l] = my_f;
+                if (l < 3) row[32 + l] = my_3;
+                else if (l < 6) row[64 + l - 3] = my_3;
+                vmask |= 1u << r;
+                c_rad++;
+            }
+            if (l == 0) {
+                IaSample s;
+                s.ts = ts; s.te = te; s.w = 0.f; s.sdf = q.sdf;
+                s.n[0] = nsm[0]; s.n[1] = nsm[1]; s.n[2] = nsm[2];
+                s.albedo[0] = 0.f; s.albedo[1] = 0.f; s.albedo[2] = 0.f;
+                s.rough = 0.f; s.metal = 0.f;
+                samples[i] = s;
+                IaSampleAux a;
+                a.rgb[0] = 0.f; a.rgb[1] = 0.f; a.rgb[2] = 0.f;
+                a.nw[0] = nw[0]; a.nw[1] = nw[1]; a.nw[2] = nw[2];
+                a.slot = slot; a.pad = 0;
+                aux[i] = a;
+            }
+        }
+        vmask |= __shfl_xor_sync(FULL, vmask, 16);
+        // The warps of the CTA walk the weight fragments together (264 fragments = 135 KB per 16 samples, more than L1 keeps
+        // next to the voxel gathers): one L2 read per CTA instead of one per warp.  Measured, primary stage at 512^2:
+        // 44.0 ms (round-1 form) / 60.5 ms (this form without the barrier) / 41.1 ms (with it).
+        __syncthreads();
+        if (vmask) {
+            float rgb[3], mat[5];
+            ia_warp_mlp3<9, 3>(xs, IA_SHADE_LD, frags + IA_FRAG_RAD1 * 32, p.mlp + IA_RAD_B1, p.mlp + IA_RAD_B2, p.mlp + IA_RAD_B3, rgb);
+            ia_warp_mlp3<6, 5>(xs, IA_SHADE_LD, frags + IA_FRAG_MAT1 * 32, p.mlp + IA_MAT_B1, p.mlp + IA_MAT_B2, p.mlp + IA_MAT_B3, mat);
+            if (lane < 16 && ((vmask >> lane) & 1u)) {
+                const long long i = b * 16 + lane;
+#pragma unroll
+                for (int k = 0; k < 3; k++) aux[i].rgb[k] = ia_sigmoid(rgb[k]);
+#pragma unroll
+                for (int k = 0; k < 5; k++) mat[k] = ia_sigmoid(mat[k]) * p.mat_scale[k] + p.mat_bias[k];
+#pragma unroll
+                for (int k = 0; k < 3; k++) samples[i].albedo[k] = mat[k] * p.albedo_ratio[k];
+                samples[i].rough = mat[3];
+                samples[i].metal = mat[4];
+            }
+        }
+        __syncwarp();
+    }
+    if (l == 0) {
+        if (c_qg) atomicAdd(&counters[IA_CNT_QUERIES_GRAD], c_qg);
+        if (c_rad) atomicAdd(&counters[IA_CNT_RAD_EVAL], c_rad);
+        if (c_geo) atomicAdd(&counters[IA_CNT_GEO_EVAL], c_geo);
+        if (c_qg) atomicAdd(&counters[IA_CNT_SKIN_FETCH], c_qg);
+    }
+    if (c_fetch) atomicAdd(&counters[IA_CNT_BROYDEN_FETCH], c_fetch);
+}
+#else
+#define IA_PRIM_SHADE_SMEM (IA_MLP_END * sizeof(float))
 __global__ void __launch_bounds__(IA_PRIMARY_THREADS, IA_PRIM_SHADE_CTAS)
 k_prim_shade(const __grid_constant__ IaFrame p, const float* __restrict__ hit_od, IaSample* __restrict__ samples,
              IaSampleAux* __restrict__ aux, long long sample_cap, const int* __restrict__ work,
@@ -347,6 +473,7 @@ k_prim_shade(const __grid_constant__ IaFrame p, const float* __restrict__ hit_od
     }
     if (c_fetch) atomicAdd(&counters[IA_CNT_BROYDEN_FETCH], c_fetch);
 }
+#endif
 
 // weights (render_weight_from_alpha) and the 7 accumulations (models/volrend.py:952-1010), one thread per hit ray,
 // samples in ray order (same summation order as the fused first generation)
@@ -693,7 +820,7 @@ extern "C" int ia_render(ia_ctx* c, const float* d_rays, int64_t n_rays, int64_t
     IA_LAUNCH_CHECK();
     {
         size_t sm1 = IA_GEO_END * sizeof(float) + (IA_PRIMARY_THREADS / IA_TEAM) * sizeof(IaPrimarySmem);
-        size_t sm2 = IA_MLP_END * sizeof(float);
+        size_t sm2 = IA_PRIM_SHADE_SMEM;
         IA_CHECK_CUDA(cudaFuncSetAttribute(k_prim_edges, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
         IA_CHECK_CUDA(cudaFuncSetAttribute(k_prim_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
         IA_STAGE_BEGIN(c, IA_STAGE_PRIMARY, st);
