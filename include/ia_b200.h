@@ -311,6 +311,13 @@ int ia_make_rays(ia_ctx* ctx, const double* h_Kinv9, const double* h_c2w12, cons
  * optional RGB->BGR for cv2.imwrite.  d_img [n_pix, channels] fp32 -> d_out [n_pix, channels] uint8.     */
 int ia_pack_rgb8(ia_ctx* ctx, const float* d_img, int64_t n_pix, int channels, float lo, float hi, int bgr,
                  uint8_t* d_out, void* stream);
+/* One column of SaverMixin.get_image_grid_ / save_image_grid (utils/mixins.py:116-157) written into the uint8 grid
+ * d_grid [H][grid_w][3] at pixel column x0.  kind 0 = 'rgb' (get_rgb_image_, :43-53; 1-2 channels zero-padded),
+ * kind 1 = 'grayscale' (get_grayscale_image_, :87-101: nan_to_num, clip/scale, colour map d_lut [256][3] or NULL =
+ * cmap None).  d_range (device, 2 floats) overrides lo/hi (data_range=None: min/max of the image).  The grid is in
+ * the channel order of the file (RGB); bgr=1 writes BGR for a cv2.imwrite caller.                            */
+int ia_pack_grid8(ia_ctx* ctx, const float* d_img, int H, int W, int channels, int kind, float lo, float hi,
+                  const float* d_range, const uint8_t* d_lut, uint8_t* d_grid, int grid_w, int x0, int bgr, void* stream);
 
 #ifdef __cplusplus
 }

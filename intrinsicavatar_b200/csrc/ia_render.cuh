@@ -1325,3 +1325,56 @@ extern "C" int ia_pack_rgb8(ia_ctx* c, const float* d_img, int64_t n_pix, int ch
     IA_LAUNCH_CHECK();
     return IA_OK;
 }
+
+// k_pack_grid8: one column of SaverMixin.get_image_grid_ (utils/mixins.py:116-144) written straight into the uint8 image
+// grid [H][grid_w][3] at pixel column x0, so that a frame's whole PNG leaves the device as one 3-byte-per-pixel copy.
+//   kind 0 'rgb'       get_rgb_image_ (:43-53): clip to [lo, hi], scale to 0..255, truncate; a 1- or 2-channel image is
+//                      padded with zeros
+//   kind 1 'grayscale' get_grayscale_image_ (:87-101): nan_to_num, clip / scale, truncate, then the colour map `lut`
+//                      [256][3] (NULL = cmap None: the grey value three times)
+// range: two floats on the DEVICE overriding lo / hi (data_range=None: the image's own min / max, computed without a
+// host round trip).  The grid holds the channel order of the FILE (RGB); bgr = 1 swaps it for a cv2.imwrite caller.
+__global__ void k_pack_grid8(const float* __restrict__ img, int H, int W, int C, int kind, float lo, float hi,
+                             const float* __restrict__ range, const uint8_t* __restrict__ lut, uint8_t* __restrict__ grid,
+                             int grid_w, int x0, int bgr) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)H * W) return;
+    const int y = (int)(i / W), x = (int)(i - (long long)y * W);
+    if (range) { lo = range[0]; hi = range[1]; }
+    uint8_t px[3] = {0, 0, 0};
+    if (kind == 0) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++)
+            if (ch < C) {
+                float v = fminf(fmaxf(img[i * C + ch], lo), hi);
+                px[ch] = (uint8_t)((v - lo) / (hi - lo) * 255.f);
+            }
+    } else {
+        float v = img[i];
+        if (isnan(v)) v = 0.f;                                   // np.nan_to_num; +-inf end up clipped
+        v = fminf(fmaxf(v, lo), hi);
+        const uint8_t q = (uint8_t)((v - lo) / (hi - lo) * 255.f);
+        if (lut) { px[0] = lut[q * 3]; px[1] = lut[q * 3 + 1]; px[2] = lut[q * 3 + 2]; }
+        else px[0] = px[1] = px[2] = q;
+    }
+    uint8_t* o = grid + ((long long)y * grid_w + x0 + x) * 3;
+    o[0] = bgr ? px[2] : px[0]; o[1] = px[1]; o[2] = bgr ? px[0] : px[2];
+}
+
+extern "C" int ia_pack_grid8(ia_ctx* c, const float* d_img, int H, int W, int channels, int kind, float lo, float hi,
+                             const float* d_range, const uint8_t* d_lut, uint8_t* d_grid, int grid_w, int x0, int bgr,
+                             void* stream) {
+    IA_REQUIRE(c && d_img && d_grid, IA_EINVAL, "ia_pack_grid8: NULL argument");
+    IA_REQUIRE(kind == 0 || kind == 1, IA_EINVAL, "ia_pack_grid8: kind must be 0 (rgb) or 1 (grayscale)");
+    IA_REQUIRE(channels > 0 && channels <= 3 && (kind == 0 || channels == 1), IA_EINVAL, "ia_pack_grid8: bad channel count");
+    IA_REQUIRE(d_range || hi > lo, IA_EINVAL, "ia_pack_grid8: empty data range");
+    IA_REQUIRE(x0 >= 0 && x0 + W <= grid_w, IA_EINVAL, "ia_pack_grid8: column outside the grid");
+    if ((long long)H * W == 0) return IA_OK;
+    IA_CHECK_CUDA(cudaSetDevice(c->device));
+    const long long n = (long long)H * W;
+    k_pack_grid8<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_img, H, W, channels, kind, lo, hi, d_range, d_lut,
+                                                                                d_grid, grid_w, x0, bgr);
+    c->n_launches += 1;
+    IA_LAUNCH_CHECK();
+    return IA_OK;
+}

@@ -49,6 +49,7 @@ _ARGTYPES = {
     "ia_op_env": [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
     "ia_make_rays": [_vp, _vp, _vp, _vp, _i32, _i32, _cf32, _cf32, _vp, _vp],
     "ia_pack_rgb8": [_vp, _vp, _i64, _i32, _cf32, _cf32, _i32, _vp, _vp],
+    "ia_pack_grid8": [_vp, _vp, _i32, _i32, _i32, _i32, _cf32, _cf32, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
 }
 
 OUTPUT_SPECS = [  # name, channels, dtype
@@ -261,6 +262,29 @@ class RenderEngine:
         check(self.lib.ia_pack_rgb8(self.h, ptr(img), n, ch, float(data_range[0]), float(data_range[1]), int(bgr), ptr(out),
                                     _stream()), "ia_pack_rgb8")
         return out.reshape(img.shape)
+
+    def pack_grid8(self, grid, x0, img, kind="rgb", data_range=(0.0, 1.0), lut=None, bgr=False):
+        """One column of SaverMixin.get_image_grid_ written into the uint8 grid [H, grid_w, 3] (CUDA) at pixel column
+        x0.  img [H, W, C] float (C <= 3; grayscale: [H, W]); data_range None = the image's own min / max after
+        nan_to_num (utils/mixins.py:89-91), computed on the device; lut uint8 [256, 3] (CUDA) or None."""
+        H, gw = int(grid.shape[0]), int(grid.shape[1])
+        img = img.to(self.dev, torch.float32)
+        if img.dim() == 2:
+            img = img[..., None]
+        img = img.contiguous()
+        if tuple(img.shape[:1]) != (H,) or grid.dtype != torch.uint8 or not grid.is_contiguous():
+            raise ValueError("pack_grid8: the image must have the grid's height and the grid must be contiguous uint8")
+        W, ch = int(img.shape[1]), int(img.shape[2])
+        rng, lo, hi = None, 0.0, 1.0
+        if data_range is None:
+            mn, mx = torch.aminmax(torch.nan_to_num(img))
+            rng = torch.stack([mn, mx]).contiguous()
+        else:
+            lo, hi = float(data_range[0]), float(data_range[1])
+        check(self.lib.ia_pack_grid8(self.h, ptr(img), H, W, ch, 0 if kind == "rgb" else 1, lo, hi,
+                                     ptr(rng) if rng is not None else None, ptr(lut) if lut is not None else None,
+                                     ptr(grid), gw, int(x0), int(bgr), _stream()), "ia_pack_grid8")
+        return grid
 
     # ------------------------------------------------------------------------ render ----
     def alloc_outputs(self, n, device=None, pin_memory=False):

@@ -708,8 +708,46 @@ def main_snarf():
     print("wrote", out, {k: tuple(v.shape) for k, v in g.items()})
 
 
+def main_saver():
+    """The image grid of test_step as the reference's own SaverMixin builds it (utils/mixins.py:43-53, 87-101, 116-144):
+    random columns of the kinds test_step uses (systems/intrinsic_avatar.py:721-841) -> the uint8 grid in the channel order
+    of the written file (get_image_grid_ returns BGR for cv2.imwrite) -> tests/golden/reference_vectors_saver.npz."""
+    install_stubs()
+    _stub("matplotlib", cm=types.SimpleNamespace())
+    _stub("matplotlib.cm")
+    _stub("matplotlib.colors", LinearSegmentedColormap=object)
+    _stub("utils.obj", write_obj=None)
+    from utils.mixins import SaverMixin
+    g = torch.Generator().manual_seed(11)
+    H, W = 12, 16
+    rgb = torch.rand(H, W, 3, generator=g) * 1.5 - 0.25            # out of range on both sides
+    chw = torch.rand(3, H, W, generator=g)
+    normal = torch.rand(H, W, 3, generator=g) * 2.4 - 1.2
+    rough = torch.rand(H, W, generator=g) * 1.2 - 0.1
+    depth = torch.rand(H, W, generator=g) * 4 + 1
+    depth[0, 0] = float("nan")
+    depth[1, 1] = float("inf")
+    two = torch.rand(H, W, 2, generator=g)                          # fewer than three channels: zero-padded
+    imgs = [
+        {"type": "rgb", "img": rgb, "kwargs": {"data_format": "HWC"}},
+        {"type": "rgb", "img": chw, "kwargs": {}},
+        {"type": "grayscale", "img": rough, "kwargs": {"data_range": (0, 1), "cmap": None}},
+        {"type": "grayscale", "img": depth.clone().nan_to_num(posinf=5.0), "kwargs": {}},
+        {"type": "rgb", "img": normal, "kwargs": {"data_format": "HWC", "data_range": (-1, 1)}},
+        {"type": "rgb", "img": two, "kwargs": {"data_format": "HWC"}},
+        {"type": "grayscale", "img": depth, "kwargs": {"data_range": (0, 6), "cmap": "jet"}},
+    ]
+    grid, cols = SaverMixin().get_image_grid_(imgs)
+    out = os.path.join(ROOT, "tests", "golden", "reference_vectors_saver.npz")
+    np.savez_compressed(out, rgb=rgb.numpy(), chw=chw.numpy(), normal=normal.numpy(), rough=rough.numpy(), depth=depth.numpy(),
+                        two=two.numpy(), grid_file_rgb=np.ascontiguousarray(grid[..., ::-1]))
+    print("wrote", out, grid.shape, grid.dtype)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "e2e":
+    if len(sys.argv) > 1 and sys.argv[1] == "saver":
+        main_saver()
+    elif len(sys.argv) > 1 and sys.argv[1] == "e2e":
         main_e2e()
     elif len(sys.argv) > 1 and sys.argv[1] == "e2e_switch":
         main_e2e_switch()

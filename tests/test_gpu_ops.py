@@ -448,6 +448,10 @@ def test_animation_frames_producer(scene):
     m.update_step(250, 25000)
     frames = AnimationFrames(m.engine, z["poses"], z["trans"], K, H, W, hdri=scene.syn.load_envmap())
     assert len(frames) == len(z["poses"])
+    # start / end / skip are applied AFTER the re-base with frame 0 of the full sequence (datasets/animation.py:127-139)
+    sub = AnimationFrames(m.engine, z["poses"], z["trans"], K, H, W, start=2, end=8, skip=3)
+    assert len(sub) == 2 and np.allclose(sub[0]["transl"].numpy(), frames[2]["transl"].numpy())
+    assert np.allclose(sub[1]["body_pose"].numpy(), frames[5]["body_pose"].numpy())
     b = frames[2]
     bp, go, tr = scene.syn.load_pose(2)
     assert np.allclose(b["transl"].numpy()[0], tr) and np.allclose(b["body_pose"].numpy()[0], bp)
@@ -457,11 +461,77 @@ def test_animation_frames_producer(scene):
     m.prepare(b)
     out = m.forward(b["rays"])
     assert out["comp_rgb_phys_full"].shape == (H * W, 3) and not out["comp_rgb_phys_full"].is_cuda
+    # the pipelined test loop: image grids of three frames written while the next frame renders
+    import cv2
+    import tempfile
+    from intrinsicavatar_b200.frames import FrameWriter, render_sequence
+    short = AnimationFrames(m.engine, z["poses"], z["trans"], K, H, W, hdri=scene.syn.load_envmap(), start=2, end=5)
+    with tempfile.TemporaryDirectory() as d, FrameWriter(m.engine, d) as wr:
+        kept = {i: o["comp_albedo_full"].clone() for i, o in render_sequence(m, short, wr, step=7)}
+        assert sorted(kept) == [0, 1, 2]             # batch['index'] counts the sliced sequence, as the reference's dataset does
+        for i in kept:
+            grid = cv2.imread(f"{d}/it7-test-all/{i}.png", cv2.IMREAD_UNCHANGED)
+            assert grid.shape == (H, 8 * W, 3)
+            alb = (kept[i].cpu().numpy().clip(0, 1) * 255.).astype(np.uint8).reshape(H, W, 3)
+            assert np.abs(grid[:, 3 * W:4 * W, ::-1].astype(int) - alb.astype(int)).max() <= 1
+            assert cv2.imread(f"{d}/it7-test-with-alpha/{i:04}-pbr.png", cv2.IMREAD_UNCHANGED).shape == (H, W, 4)
+    m.prepare(b)
+    out = m.forward(b["rays"])
     imgs = images_to_uint8(m.engine, out, H, W)
     im = imgs["comp_rgb_phys_full"]
     assert im.dtype == np.uint8 and im.shape == (H, W, 3)
     ref = (out["comp_rgb_phys_full"].numpy().clip(0, 1) * 255.).astype(np.uint8).reshape(H, W, 3)[..., ::-1]
     assert np.abs(im.astype(int) - ref.astype(int)).max() <= 1
+
+
+def _saver_columns(z, dev="cuda"):
+    t = lambda k: torch.from_numpy(z[k]).to(dev)
+    return [
+        {"type": "rgb", "img": t("rgb"), "kwargs": {"data_format": "HWC"}},
+        {"type": "rgb", "img": t("chw"), "kwargs": {}},
+        {"type": "grayscale", "img": t("rough"), "kwargs": {"data_range": (0, 1), "cmap": None}},
+        {"type": "grayscale", "img": t("depth").nan_to_num(posinf=5.0), "kwargs": {}},
+        {"type": "rgb", "img": t("normal"), "kwargs": {"data_format": "HWC", "data_range": (-1, 1)}},
+        {"type": "rgb", "img": t("two"), "kwargs": {"data_format": "HWC"}},
+        {"type": "grayscale", "img": t("depth"), "kwargs": {"data_range": (0, 6), "cmap": "jet"}},
+    ]
+
+
+def test_image_grid_matches_reference_saver(eng, tmp_path):
+    """frames.FrameWriter.save_image_grid (ia_pack_grid8 + PNG encode on a worker thread) against the grid the REFERENCE's
+    own SaverMixin.get_image_grid_ builds from the same columns (tests/golden/reference_vectors_saver.npz, made by
+    scripts/make_golden.py saver): rgb HWC / CHW / other data range / two channels, grayscale with cmap None, jet with
+    data_range None (min-max on the device) and with NaN / inf.  Also the per-column and RGBA files of test_step."""
+    import os
+    import cv2
+    from intrinsicavatar_b200.frames import FrameWriter
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors_saver.npz"))
+    ref = z["grid_file_rgb"]
+    H, W = z["rough"].shape
+    caps = ["rgb", "chw", "rough", "depth", "normal", "two", "jet"]
+    alpha = torch.from_numpy(z["rough"]).cuda()
+    with FrameWriter(eng, str(tmp_path)) as w:
+        for i in range(4):                       # more frames than staging slots: the ring must recycle them
+            w.save_image_grid(f"it0-test-all/{i}.png", _saver_columns(z), captions=caps,
+                              column_pattern="it0-test/%04d-{caption}.png" % i, alpha=alpha,
+                              alpha_pattern="it0-test-with-alpha/%04d-{caption}.png" % i)
+        w.save_rgb_image("single.png", torch.from_numpy(z["chw"]).cuda())
+        w.flush()
+        for i in range(4):
+            got = cv2.imread(str(tmp_path / f"it0-test-all/{i}.png"), cv2.IMREAD_UNCHANGED)[..., ::-1]
+            assert got.shape == ref.shape
+            d = np.abs(got.astype(int) - ref.astype(int))
+            # float32 on both sides; a value exactly on a bin edge may land one level off in the min-max normalised column
+            assert (d > 0).mean() < 2e-3 and d.max() <= 4, (d.max(), (d > 0).mean())
+        col = cv2.imread(str(tmp_path / "it0-test/0002-normal.png"), cv2.IMREAD_UNCHANGED)[..., ::-1]
+        assert np.abs(col.astype(int) - ref[:, 4 * W:5 * W].astype(int)).max() <= 1
+        rgba = cv2.imread(str(tmp_path / "it0-test-with-alpha/0001-rgb.png"), cv2.IMREAD_UNCHANGED)
+        assert rgba.shape == (H, W, 4)
+        a_ref = (z["rough"].clip(0, 1) * 255).astype(np.uint8)
+        assert np.abs(rgba[..., 3].astype(int) - a_ref.astype(int)).max() <= 1
+        assert np.abs(rgba[..., 2::-1].astype(int) - ref[:, :W].astype(int)).max() <= 1
+        one = cv2.imread(str(tmp_path / "single.png"), cv2.IMREAD_UNCHANGED)[..., ::-1]
+        assert np.abs(one.astype(int) - ref[:, W:2 * W].astype(int)).max() <= 1
 
 
 def test_shade_fields_vs_reference_modules(eng):

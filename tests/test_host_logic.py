@@ -324,3 +324,86 @@ def test_nested_config_validation_against_the_reference_yaml():
     class Attr(dict):          # Hydra's DictConfig quacks like this
         __getattr__ = dict.__getitem__
     assert M._plain(Attr(a=Attr(b=[1, Attr(c=2)]))) == {"a": {"b": [1, {"c": 2}]}}
+
+
+def test_png_and_exr_encoders_round_trip(tmp_path):
+    """frames.png_bytes (cv2 and the zlib-only fallback) and frames.exr_bytes decode back to the pixels they were given."""
+    import struct
+    import zlib
+    from intrinsicavatar_b200 import frames
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (9, 13, 3), dtype=np.uint8)
+    rgba = rng.integers(0, 256, (9, 13, 4), dtype=np.uint8)
+
+    def decode(b):        # minimal PNG reader: 8-bit RGB / RGBA, any filter type
+        assert b[:8] == b"\x89PNG\r\n\x1a\n"
+        pos, idat, hdr = 8, b"", None
+        while pos < len(b):
+            n, tag = struct.unpack(">I4s", b[pos:pos + 8])
+            data = b[pos + 8:pos + 8 + n]
+            assert struct.unpack(">I", b[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(tag + data) & 0xffffffff
+            if tag == b"IHDR":
+                hdr = struct.unpack(">IIBBBBB", data)
+            elif tag == b"IDAT":
+                idat += data
+            pos += 12 + n
+        W, H, depth, ctype = hdr[:4]
+        C = {2: 3, 6: 4}[ctype]
+        raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(H, 1 + W * C).astype(np.int64)
+        out = np.zeros((H, W * C), np.int64)
+        for y in range(H):
+            f, line = raw[y, 0], raw[y, 1:]
+            up = out[y - 1] if y else np.zeros(W * C, np.int64)
+            for x in range(W * C):
+                a = out[y, x - C] if x >= C else 0
+                c = up[x - C] if x >= C else 0
+                pred = {0: 0, 1: a, 2: up[x], 3: (a + up[x]) // 2}.get(int(f))
+                if pred is None:
+                    p = a + up[x] - c
+                    pa, pb, pc = abs(p - a), abs(p - up[x]), abs(p - c)
+                    pred = a if pa <= pb and pa <= pc else (up[x] if pb <= pc else c)
+                out[y, x] = (line[x] + pred) & 255
+        return out.reshape(H, W, C).astype(np.uint8)
+    assert np.array_equal(decode(frames.png_bytes(img)), img)
+    assert np.array_equal(decode(frames.png_bytes(rgba)), rgba)
+    import builtins
+    real_import = builtins.__import__
+
+    def no_cv2(name, *a, **k):
+        if name == "cv2":
+            raise ImportError(name)
+        return real_import(name, *a, **k)
+    builtins.__import__ = no_cv2
+    try:
+        fallback = frames.png_bytes(img)
+    finally:
+        builtins.__import__ = real_import
+    assert np.array_equal(decode(fallback), img)
+    # EXR: header attributes, offset table, B / G / R float rows
+    hdr = rng.random((5, 7, 3), dtype=np.float32) * 40
+    b = frames.exr_bytes(hdr)
+    assert struct.unpack("<II", b[:8]) == (20000630, 2)
+    pos, attrs = 8, {}
+    while b[pos] != 0:
+        e = b.index(b"\0", pos); name = b[pos:e].decode(); pos = e + 1
+        e = b.index(b"\0", pos); typ = b[pos:e].decode(); pos = e + 1
+        n = struct.unpack("<i", b[pos:pos + 4])[0]
+        attrs[name] = (typ, b[pos + 4:pos + 4 + n]); pos += 4 + n
+    pos += 1
+    assert attrs["compression"][1] == b"\0" and struct.unpack("<iiii", attrs["dataWindow"][1]) == (0, 0, 6, 4)
+    offs = struct.unpack("<5Q", b[pos:pos + 40])
+    for y, o in enumerate(offs):
+        yy, n = struct.unpack("<ii", b[o:o + 8])
+        assert yy == y and n == 3 * 7 * 4
+        row = np.frombuffer(b[o + 8:o + 8 + n], np.float32).reshape(3, 7)
+        assert np.array_equal(row[::-1].T, hdr[y])
+    try:
+        os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+        import cv2
+        path = str(tmp_path / "e.exr")
+        open(path, "wb").write(b)
+        back = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+        if back is not None:                     # OpenEXR support is optional in cv2 builds
+            assert np.allclose(back[..., ::-1], hdr)
+    except Exception:
+        pass
