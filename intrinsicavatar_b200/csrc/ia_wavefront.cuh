@@ -69,7 +69,8 @@
 #define WF_OFF_GTASK (WF_OFF_CSDF + WF_R * IA_N_INIT * 4)
 #define WF_OFF_BTASK (WF_OFF_GTASK + WF_R * IA_N_INIT * 2)
 #define WF_OFF_GITASK (WF_OFF_BTASK + WF_R * IA_N_INIT * 2)
-#define WF_OFF_STATE (WF_OFF_GITASK + WF_R * 8)
+#define WF_OFF_GIXC (WF_OFF_GITASK + WF_R * 8)
+#define WF_OFF_STATE (WF_OFF_GIXC + WF_R * 3 * 4)
 #define WF_SCRATCH_BYTES (WF_OFF_STATE + WF_NST * WF_R * 4)
 
 enum { WF_C_Q = 0, WF_C_FETCH, WF_C_GEO, WF_C_RAYS, WF_C_SKIP, WF_C_QG, WF_C_RAD };
@@ -132,6 +133,8 @@ struct WfShared {
     float* cand;            // [WF_R][13][3] Broyden roots
     float* csdf;            // [WF_R][13] SDF of the kept roots
     uint2* gitask;          // [WF_R] GI: (slot | root << 16, weight bits) of the fine samples consumed this round
+    float* gixc;            // [WF_R][3] their canonical roots (copied: the GI phase runs next to the Broyden phase, which
+                            // overwrites the slot's roots)
     int n_gitask;
     unsigned short* gtask;  // [WF_R * 13] geometry task list
 #if WF_BTASK_SMEM
@@ -672,7 +675,7 @@ __device__ __forceinline__ void wf_gi_phase(const IaFrame& p, WfShared& S) {
             const uint2 tk = S.gitask[b0 + (lane & 15)];
             t = tk.x & 0xffffu;
             wgt = __uint_as_float(tk.y);
-            const float* cd = S.cand + (t * IA_N_INIT + (int)(tk.x >> 16)) * 3;
+            const float* cd = S.gixc + (b0 + (lane & 15)) * 3;
             x0 = cd[0]; x1 = cd[1]; x2 = cd[2];
             d0 = S.st[WS_D][t]; d1 = S.st[WS_D + 1][t]; d2 = S.st[WS_D + 2][t];
         }
@@ -702,6 +705,12 @@ __device__ __forceinline__ void wf_gi_phase(const IaFrame& p, WfShared& S) {
 //   refill  : one thread per LIST ENTRY (dense): estimator of the finished ray (P::finish), next ray from the ring
 //             (P::init, marcher set-up, march to its first sample), its first query.
 // Measured at 512^2 x 1024 spp, GI on, frames 2-4: 1159 -> 1102 ms (and 1088 -> 1035 ms with WF_QSORT).
+__device__ __forceinline__ void wf_push_gi(WfShared& S, int t, int best, float w) {
+    const int gi = atomicAdd(&S.n_gitask, 1);
+    S.gitask[gi] = make_uint2((unsigned)t | ((unsigned)best << 16), __float_as_uint(w));
+    const float* cd = S.cand + (t * IA_N_INIT + best) * 3;
+    S.gixc[gi * 3] = cd[0]; S.gixc[gi * 3 + 1] = cd[1]; S.gixc[gi * 3 + 2] = cd[2];
+}
 template <bool GI, class P>
 __device__ __forceinline__ void wf_advance_consume(const IaFrame& p, P& pol, WfShared& S, const int t, unsigned& c_q) {
     unsigned pack = __float_as_uint(S.st[WS_PACK][t]);
@@ -750,8 +759,7 @@ __device__ __forceinline__ void wf_advance_consume(const IaFrame& p, P& pol, WfS
             acc += w;
             bool gi_pushed = false;
             if (GI && best >= 0) {
-                int gi = atomicAdd(&S.n_gitask, 1);
-                S.gitask[gi] = make_uint2((unsigned)t | ((unsigned)best << 16), __float_as_uint(w));
+                wf_push_gi(S, t, best, w);
                 gi_pushed = true;
             }
             bool cont;
@@ -832,10 +840,8 @@ __device__ __forceinline__ void wf_advance_consume(const IaFrame& p, P& pol, WfS
         acc += w;
         bool gi_pushed = false;
         if (GI && best >= 0) {
-            // radiance at the arg-min root of this fine sample is added by the GI phase of this round
-            // (before the Broyden phase overwrites the slot's roots): ind += w * rgb
-            int gi = atomicAdd(&S.n_gitask, 1);
-            S.gitask[gi] = make_uint2((unsigned)t | ((unsigned)best << 16), __float_as_uint(w));
+            // radiance at the arg-min root of this fine sample is added by the GI phase of this round: ind += w * rgb
+            wf_push_gi(S, t, best, w);
             gi_pushed = true;
         }
         i++;
@@ -998,6 +1004,7 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
         S.btask = reinterpret_cast<unsigned short*>(mine + WF_OFF_BTASK);
 #endif
         S.gitask = reinterpret_cast<uint2*>(mine + WF_OFF_GITASK);
+        S.gixc = reinterpret_cast<float*>(mine + WF_OFF_GIXC);
 #if WF_STATE_GLOBAL
         S.st = reinterpret_cast<float (*)[WF_R]>(mine + WF_OFF_STATE);
 #endif
@@ -1046,20 +1053,12 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
             wf_count(S, WF_C_RAYS, c_rays);
         }
         __syncthreads();
-        if (GI) {
-            const int n_gi = S.n_gitask;
-            if (n_gi) wf_gi_phase(p, S);
-            __syncthreads();
-            const int n_q0 = S.n_q;
-            if (n_q0 == 0) {
-                // rays waiting for their last radiance (WF_GIWAIT) need one more advance round
-                if (n_gi == 0 && S.ring_tail - S.ring_head <= 0 && !S.more_tiles) break;
-                continue;
-            }
-        }
+        const int n_gi = GI ? S.n_gitask : 0;
         const int n_q = S.n_q;
         if (n_q == 0) {
-            if (S.ring_tail - S.ring_head <= 0 && !S.more_tiles) break;
+            if (n_gi) wf_gi_phase(p, S);
+            // (GI: rays waiting for their last radiance, WF_GIWAIT, need one more advance round)
+            if (n_gi == 0 && S.ring_tail - S.ring_head <= 0 && !S.more_tiles) break;
             continue;
         }
 #if WF_QSORT
@@ -1068,6 +1067,11 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
 #endif
         wf_prune_phase(p, S, n_q);
         __syncthreads();
+        // The GI phase (static share per warp, uneven in time) runs WITHOUT a barrier in front of the Broyden phase, whose
+        // tasks are grabbed dynamically: a warp that finishes its radiance batches early takes more chains instead of
+        // waiting (the barrier behind the GI phase was 2.5 % of the kernel's stall samples).  The two phases share no
+        // data: the GI tasks carry their own copy of the root.
+        if (n_gi) wf_gi_phase(p, S);
         wf_broyden_phase(p, S);
         __syncthreads();
         wf_filter_phase(S, n_q);
