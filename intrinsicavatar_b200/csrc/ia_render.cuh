@@ -151,13 +151,6 @@ struct IaPrimarySmem {
 };
 
 // per-sample record written by k_prim_shade next to IaSample (which carries ts, te, sdf, n, albedo, rough, metal)
-struct IaSampleAux {
-    float rgb[3];
-    float nw[3];   // world-space unit normal
-    int slot;      // hit-ray slot of the sample
-    int pad;
-};
-static_assert(sizeof(IaSampleAux) == 32, "IaSampleAux layout");
 
 __global__ void __launch_bounds__(IA_PRIMARY_THREADS, 2)
 k_prim_edges(const __grid_constant__ IaFrame p, const float* __restrict__ hit_od, int* __restrict__ hit_info,
@@ -474,6 +467,136 @@ k_prim_shade(const __grid_constant__ IaFrame p, const float* __restrict__ hit_od
     if (c_fetch) atomicAdd(&counters[IA_CNT_BROYDEN_FETCH], c_fetch);
 }
 #endif
+
+// ------------------------------------------------------------------------------------------------
+// k_prim_shade_wf: the same per-sample work on the WAVEFRONT machinery of the shading stage (ia_wavefront.cuh).  One
+// persistent 512-thread CTA per SM takes tiles of WF_R = 1024 consecutive samples; their midpoints are the queries of one
+// "round": Morton sort -> exact prune -> dense Broyden -> filter -> tensor-core geometry, then the arg-min root of every
+// sample goes through the tensor-core shading batch (ia_warp_radiance16<PRIMARY>: feature + normal + rotation + radiance +
+// material) in full 16-row batches.  The team kernel above spends 23 of its 27 ms in the per-sample query (13 chains in
+// lock-step per 16 lanes, 283 M voxel fetches); here the chains are independent dense tasks.
+#ifndef IA_PRIM_SHADE_WF
+#define IA_PRIM_SHADE_WF 1
+#endif
+__global__ void __launch_bounds__(WF_THREADS, WF_CTAS_PER_SM)
+k_prim_shade_wf(const __grid_constant__ IaFrame p, const float* __restrict__ hit_od, IaSample* __restrict__ samples,
+                IaSampleAux* __restrict__ aux, long long sample_cap, const int* __restrict__ work,
+                unsigned char* __restrict__ scratch, unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) unsigned char wf_smem[];
+    WfShared& S = *reinterpret_cast<WfShared*>(wf_smem);
+    wf_setup<true>(p, S, scratch);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, n_warps = blockDim.x >> 5;
+    const long long n = min((long long)work[IA_W_NSAMPLES], sample_cap);
+    const long long n_tiles = (n + WF_R - 1) / WF_R;
+    unsigned c_live = 0;
+    float nw_def[3];
+    {
+        const float up[3] = {0.f, 0.f, 1.f};      // invalid query: gradient (0, 0, 1) (snarf_deformer.py:192)
+        ia_dir_s2w(p, up, nw_def);
+    }
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long base = tile * WF_R;
+        __syncthreads();
+        if (tid == 0) { S.n_q = 0; S.n_gtask = 0; S.task_next = 0; S.n_btask = 0; S.n_gitask = 0; }
+        __syncthreads();
+        // ---- queries: the midpoint of every live sample of the tile
+        for (int t = tid; t < WF_R; t += blockDim.x) {
+            const long long i = base + t;
+            const int slot = i < n ? aux[i].slot : -1;   // < 0: past the end / dead record of a ray that did not fit the pool
+            S.qmask[t] = 0;
+            if (slot >= 0) {
+                const float* od = hit_od + (size_t)slot * 8;
+                const float tm = (samples[i].ts + samples[i].te) / 2.0f;
+#pragma unroll
+                for (int k = 0; k < 3; k++) S.qx[k][t] = od[k] + od[3 + k] * tm;
+                S.qlist[atomicAdd(&S.n_q, 1)] = (unsigned short)t;
+                c_live++;
+            }
+        }
+        __syncthreads();
+        const int n_q = S.n_q;
+        if (n_q == 0) continue;
+#if WF_QSORT
+        wf_sort_phase(p, S, n_q);
+        __syncthreads();
+#endif
+        wf_prune_phase(p, S, n_q);
+        __syncthreads();
+        wf_broyden_phase(p, S);
+        __syncthreads();
+        wf_filter_phase(S, n_q);
+        __syncthreads();
+        wf_geometry_phase(p, S);
+        __syncthreads();
+        // ---- min SDF over the kept roots (snarf_deformer.py:242-259); the record of a sample without a root is final
+        for (int t = tid; t < WF_R; t += blockDim.x) {
+            const long long i = base + t;
+            const int slot = i < n ? aux[i].slot : -1;
+            if (slot < 0) continue;
+            unsigned keep = S.qmask[t];
+            float sdf = 1e5f;
+            int best = -1;
+            while (keep) {
+                const int c = __ffs(keep) - 1;
+                keep &= keep - 1;
+                const float s = S.csdf[t * IA_N_INIT + c];
+                if (s < sdf) { sdf = s; best = c; }
+            }
+            IaSample r = samples[i];
+            r.w = 0.f; r.sdf = sdf;
+            r.n[0] = 0.f; r.n[1] = 0.f; r.n[2] = 1.f;
+            r.albedo[0] = 0.f; r.albedo[1] = 0.f; r.albedo[2] = 0.f; r.rough = 0.f; r.metal = 0.f;
+            samples[i] = r;
+            IaSampleAux a;
+            a.rgb[0] = 0.f; a.rgb[1] = 0.f; a.rgb[2] = 0.f;
+            a.nw[0] = nw_def[0]; a.nw[1] = nw_def[1]; a.nw[2] = nw_def[2];
+            a.slot = slot; a.pad = 0;
+            aux[i] = a;
+            if (best >= 0) wf_push_gi(S, t, best, 0.f);
+        }
+        __syncthreads();
+        // ---- shading batches
+        {
+            const int n_sh = S.n_gitask;
+            const int per = (((n_sh + n_warps - 1) / n_warps) + 15) & ~15;    // whole 16-row batches per warp
+            const int end = min(n_sh, (warp + 1) * per);
+            float* xs = wf_xs(S) + warp * 16 * IA_SHADE_LD;
+            for (int b0 = warp * per; b0 < end; b0 += 16) {
+                const int nb = min(16, end - b0);
+                long long rec = 0;
+                float x0 = 0.f, x1 = 0.f, x2 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 1.f;
+                if ((lane & 15) < nb) {
+                    const int t = (int)(S.gitask[b0 + (lane & 15)].x & 0xffffu);
+                    rec = base + t;
+                    const float* cd = S.gixc + (b0 + (lane & 15)) * 3;
+                    x0 = cd[0]; x1 = cd[1]; x2 = cd[2];
+                    const float* od = hit_od + (size_t)aux[rec].slot * 8;
+                    d0 = od[3]; d1 = od[4]; d2 = od[5];
+                }
+                float rgb[3], mat[5];
+                ia_warp_radiance16<true>(p, S.lvl, wf_w(S), wf_w1f(S), xs, x0, x1, x2, d0, d1, d2, nb, rgb, mat, rec, samples, aux);
+                if (lane < nb) {
+#pragma unroll
+                    for (int k = 0; k < 3; k++) { aux[rec].rgb[k] = rgb[k]; samples[rec].albedo[k] = mat[k]; }
+                    samples[rec].rough = mat[3];
+                    samples[rec].metal = mat[4];
+                }
+            }
+            for (int i = lane; i < WF_MMA_ROWS * 5; i += 32) xs[(i / 5) * IA_GEO_LD + 35 + i % 5] = 0.f;   // (see wf_gi_phase)
+            wf_count(S, WF_C_QG, (lane == 0 && end > warp * per) ? (unsigned)(end - warp * per) : 0u);
+        }
+    }
+    wf_count(S, WF_C_Q, c_live);
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned long long q = S.cnt[WF_C_Q], f = S.cnt[WF_C_FETCH], g = S.cnt[WF_C_GEO], k = S.cnt[WF_C_SKIP], qg = S.cnt[WF_C_QG];
+        if (q) atomicAdd(&counters[IA_CNT_QUERIES_GRAD], q);
+        if (f) atomicAdd(&counters[IA_CNT_BROYDEN_FETCH], f);
+        if (g + qg) atomicAdd(&counters[IA_CNT_GEO_EVAL], g + qg);
+        if (k) atomicAdd(&counters[IA_CNT_CHAINS_SKIPPED], k);
+        if (qg) { atomicAdd(&counters[IA_CNT_RAD_EVAL], qg); atomicAdd(&counters[IA_CNT_SKIN_FETCH], qg); }
+    }
+}
 
 // weights (render_weight_from_alpha) and the 7 accumulations (models/volrend.py:952-1010), one thread per hit ray,
 // samples in ray order (same summation order as the fused first generation)
@@ -823,11 +946,18 @@ extern "C" int ia_render(ia_ctx* c, const float* d_rays, int64_t n_rays, int64_t
         size_t sm2 = IA_PRIM_SHADE_SMEM;
         IA_CHECK_CUDA(cudaFuncSetAttribute(k_prim_edges, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
         IA_CHECK_CUDA(cudaFuncSetAttribute(k_prim_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        IA_CHECK_CUDA(cudaFuncSetAttribute(k_prim_shade_wf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_BYTES(true)));
+        if (int e = ia_wf_scratch(c)) return e;
         IA_STAGE_BEGIN(c, IA_STAGE_PRIMARY, st);
         k_prim_edges<<<c->n_sm * 2, IA_PRIMARY_THREADS, sm1, st>>>(c->f, c->d_hit_od, c->d_hit_info, c->d_samples, c->d_samples_aux,
                                                                    c->ws_samples, c->d_work, c->d_counters);
+#if IA_PRIM_SHADE_WF
+        k_prim_shade_wf<<<c->n_sm * WF_CTAS_PER_SM, WF_THREADS, WF_SMEM_BYTES(true), st>>>(c->f, c->d_hit_od, c->d_samples, c->d_samples_aux,
+                                                                                         c->ws_samples, c->d_work, c->d_wf_scratch, c->d_counters);
+#else
         k_prim_shade<<<c->n_sm * IA_PRIM_SHADE_CTAS, IA_PRIMARY_THREADS, sm2, st>>>(c->f, c->d_hit_od, c->d_samples, c->d_samples_aux, c->ws_samples,
                                                                    c->d_work, c->d_counters);
+#endif
         k_prim_accum<<<(unsigned)((n_rays + 127) / 128), 128, 0, st>>>(c->f, c->d_hit_rays, c->d_hit_od, c->d_hit_info, c->d_samples,
                                                                        c->d_samples_aux, c->d_work, *out);
         IA_STAGE_END(c, IA_STAGE_PRIMARY, st, 3);

@@ -107,5 +107,12 @@ struct IaSample {
     float rough, metal;
 };
 static_assert(sizeof(IaSample) == 48, "IaSample layout");
+struct IaSampleAux {
+    float rgb[3];
+    float nw[3];   // world-space unit normal
+    int slot;      // hit-ray slot of the sample
+    int pad;
+};
+static_assert(sizeof(IaSampleAux) == 32, "IaSampleAux layout");
 
 typedef cg::thread_block_tile<IA_TEAM> Team;

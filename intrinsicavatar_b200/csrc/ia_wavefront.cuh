@@ -530,9 +530,15 @@ __device__ __forceinline__ void wf_geometry_phase(const IaFrame& p, WfShared& S)
 //   C   radiance network 67 -> 64 -> 64 -> 3 as 3xTF32 mma, sigmoid
 // The weights of B (second half) and C are read as B fragments straight from global memory (IA_FRAG_*, 102 KB pre-split, L1-resident
 // while this phase runs and evicted for the voxel gathers otherwise) instead of living in shared memory.
+// PRIMARY (the shading kernel of the primary stage, k_prim_shade_wf): lane j also passes the index of its sample record;
+// A2 stores the posed-space unit normal and the world normal there (rgb_normal_mats_alpha_fn, models/intrinsic_avatar.py:
+// 1066-1156), and the material network (48 -> 64 -> 64 -> 5 on the first 48 tile columns) runs after the radiance network.
+template <bool PRIMARY = false>
 __device__ __forceinline__ void ia_warp_radiance16(const IaFrame& p, const IaLevel* __restrict__ lvl, const float* __restrict__ w,
                                                    const float4* __restrict__ w1f, float* __restrict__ xs, float px, float py,
-                                                   float pz, float dx, float dy, float dz, int n_pts, float rgb[3]) {
+                                                   float pz, float dx, float dy, float dz, int n_pts, float rgb[3],
+                                                   float mat[5] = nullptr, long long rec = 0, IaSample* __restrict__ samples = nullptr,
+                                                   IaSampleAux* __restrict__ aux = nullptr) {
     const unsigned FULL = 0xffffffffu;
     constexpr int LD = IA_SHADE_LD;
     const int lane = threadIdx.x & 31, l = lane & 15, half = lane >> 4, g = lane >> 2, t = lane & 3;
@@ -612,6 +618,7 @@ __device__ __forceinline__ void ia_warp_radiance16(const IaFrame& p, const IaLev
         const int r = i + half;
         const float x0 = __shfl_sync(FULL, px, r & 15), x1 = __shfl_sync(FULL, py, r & 15), x2 = __shfl_sync(FULL, pz, r & 15);
         const float d0 = __shfl_sync(FULL, dx, r & 15), d1 = __shfl_sync(FULL, dy, r & 15), d2 = __shfl_sync(FULL, dz, r & 15);
+        const long long rec_r = PRIMARY ? __shfl_sync(FULL, rec, r & 15) : 0;
         if (r < n_pts) {
             float* row = xs + r * LD;
             const float xc[3] = {x0, x1, x2};
@@ -632,6 +639,12 @@ __device__ __forceinline__ void ia_warp_radiance16(const IaFrame& p, const IaLev
             float nw[3], view_w[3];
             ia_dir_s2w(p, gs, nw);
             ia_dir_s2w(p, dir, view_w);
+            if (PRIMARY && l == 0) {
+                float nsm[3];
+                ia_normalize(gs, nsm, 1e-6f);
+                samples[rec_r].n[0] = nsm[0]; samples[rec_r].n[1] = nsm[1]; samples[rec_r].n[2] = nsm[2];
+                aux[rec_r].nw[0] = nw[0]; aux[rec_r].nw[1] = nw[1]; aux[rec_r].nw[2] = nw[2];
+            }
             ia_hash_level<false>(p.rad_hash, lvl[l], xn, f0, f1, nullptr);
             // reflect(-view, n) (models/utils.py:115), then the (d + 1) / 2 -> 2 x - 1 round trip of the encoding
             const float v[3] = {-view_w[0], -view_w[1], -view_w[2]};
@@ -657,6 +670,14 @@ __device__ __forceinline__ void ia_warp_radiance16(const IaFrame& p, const IaLev
     ia_warp_mlp3<9, 3>(xs, LD, frags + IA_FRAG_RAD1 * 32, p.mlp + IA_RAD_B1, p.mlp + IA_RAD_B2, p.mlp + IA_RAD_B3, o);
 #pragma unroll
     for (int k = 0; k < 3; k++) rgb[k] = ia_sigmoid(o[k]);
+    if (PRIMARY) {
+        float m[5];
+        ia_warp_mlp3<6, 5>(xs, LD, frags + IA_FRAG_MAT1 * 32, p.mlp + IA_MAT_B1, p.mlp + IA_MAT_B2, p.mlp + IA_MAT_B3, m);
+#pragma unroll
+        for (int k = 0; k < 5; k++) mat[k] = ia_sigmoid(m[k]) * p.mat_scale[k] + p.mat_bias[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) mat[k] *= p.albedo_ratio[k];
+    }
     __syncwarp();   // the tile may be overwritten by the next batch
 }
 
@@ -986,10 +1007,9 @@ __device__ __forceinline__ void wf_advance_refill(const IaFrame& p, P& pol, WfSh
     S.st[WS_PACK][t] = __uint_as_float((unsigned)WF_IDLE);
 }
 
-// ------------------------------------------------------------------------------------------------
-template <bool GI, class P>
-__device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, unsigned char* __restrict__ scratch,
-                                       unsigned long long* __restrict__ counters) {
+// shared memory + scratch set-up of a wavefront CTA (weights, fragments, tiles, per-CTA scratch pointers, empty ray slots)
+template <bool GI>
+__device__ __forceinline__ void wf_setup(const IaFrame& p, WfShared& S, unsigned char* __restrict__ scratch) {
     const int tid = threadIdx.x;
     const int n_w = IA_GEO_END;
     if (tid == 0) {
@@ -1020,6 +1040,14 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
     if (tid == 0) { S.ring_head = 0; S.ring_tail = 0; S.more_tiles = 1; S.n_q = 0; S.n_gtask = 0; S.task_next = 0; }
     if (tid < 8) S.cnt[tid] = 0;
     __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool GI, class P>
+__device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, unsigned char* __restrict__ scratch,
+                                       unsigned long long* __restrict__ counters) {
+    const int tid = threadIdx.x;
+    wf_setup<GI>(p, S, scratch);
     const int tile_items = pol.tile_items();
     const long long n_tiles = (pol.n_items() + tile_items - 1) / tile_items;
     while (true) {
