@@ -60,6 +60,12 @@
 #ifndef WF_STATE_GLOBAL
 #define WF_STATE_GLOBAL 1
 #endif
+#ifndef WF_DEFER_FINISH
+#define WF_DEFER_FINISH 1   // the estimator of a finished ray (BRDF, 6 atomics) is not evaluated in the refill pass, which the whole
+#endif                      // CTA waits for, but listed and evaluated in front of the dynamically scheduled Broyden phase
+#ifndef WF_GI_FULL_BATCHES
+#define WF_GI_FULL_BATCHES 1
+#endif
 #ifndef WF_BTASK_SMEM
 #define WF_BTASK_SMEM 0   // 1: Broyden task list in shared memory, so that a chain start reads its task id with shared-memory
 #endif                    // latency (from the global scratch that read is an exposed L2 round trip: 6 % of the Broyden phase's
@@ -70,7 +76,9 @@
 #define WF_OFF_BTASK (WF_OFF_GTASK + WF_R * IA_N_INIT * 2)
 #define WF_OFF_GITASK (WF_OFF_BTASK + WF_R * IA_N_INIT * 2)
 #define WF_OFF_GIXC (WF_OFF_GITASK + WF_R * 8)
-#define WF_OFF_STATE (WF_OFF_GIXC + WF_R * 3 * 4)
+#define WF_FCAP (2 * WF_R)     // finished rays whose estimator is deferred to the front of the Broyden phase (per round)
+#define WF_OFF_FLIST (WF_OFF_GIXC + WF_R * 3 * 4)
+#define WF_OFF_STATE (WF_OFF_FLIST + WF_FCAP * 9 * 4)
 #define WF_SCRATCH_BYTES (WF_OFF_STATE + WF_NST * WF_R * 4)
 
 enum { WF_C_Q = 0, WF_C_FETCH, WF_C_GEO, WF_C_RAYS, WF_C_SKIP, WF_C_QG, WF_C_RAD };
@@ -133,6 +141,8 @@ struct WfShared {
     float* cand;            // [WF_R][13][3] Broyden roots
     float* csdf;            // [WF_R][13] SDF of the kept roots
     uint2* gitask;          // [WF_R] GI: (slot | root << 16, weight bits) of the fine samples consumed this round
+    float* flist;           // [WF_FCAP][9] finished rays: entry.x, entry.y, T, ind[3], d[3] (WF_DEFER_FINISH)
+    int n_flist;
     float* gixc;            // [WF_R][3] their canonical roots (copied: the GI phase runs next to the Broyden phase, which
                             // overwrites the slot's roots)
     int n_gitask;
@@ -685,7 +695,13 @@ __device__ __forceinline__ void ia_warp_radiance16(const IaFrame& p, const IaLev
 __device__ __forceinline__ void wf_gi_phase(const IaFrame& p, WfShared& S) {
     const int n = S.n_gitask;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+#if WF_GI_FULL_BATCHES
+    // whole 16-row batches: a round has 100-200 tasks, i.e. 6-12 rows per warp if split evenly, and the tensor-core stages
+    // cost the same for 6 rows as for 16.  The warps left without a batch go straight to the Broyden phase's task loop.
+    const int per = (((n + n_warps - 1) / n_warps) + 15) & ~15;
+#else
     const int per = (n + n_warps - 1) / n_warps;
+#endif
     const int end = min(n, (warp + 1) * per);
     float* xs = wf_xs(S) + warp * 16 * IA_SHADE_LD;
     for (int b0 = warp * per; b0 < end; b0 += 16) {
@@ -731,6 +747,30 @@ __device__ __forceinline__ void wf_push_gi(WfShared& S, int t, int best, float w
     S.gitask[gi] = make_uint2((unsigned)t | ((unsigned)best << 16), __float_as_uint(w));
     const float* cd = S.cand + (t * IA_N_INIT + best) * 3;
     S.gixc[gi * 3] = cd[0]; S.gixc[gi * 3 + 1] = cd[1]; S.gixc[gi * 3 + 2] = cd[2];
+}
+template <class P>
+__device__ __forceinline__ void wf_finish(P& pol, WfShared& S, const uint2 entry, float T, const float ind[3], const float d[3]) {
+#if WF_DEFER_FINISH
+    const int k = atomicAdd(&S.n_flist, 1);
+    if (k < WF_FCAP) {
+        float* f = S.flist + k * 9;
+        f[0] = __uint_as_float(entry.x); f[1] = __uint_as_float(entry.y); f[2] = T;
+        f[3] = ind[0]; f[4] = ind[1]; f[5] = ind[2]; f[6] = d[0]; f[7] = d[1]; f[8] = d[2];
+        return;
+    }
+#endif
+    pol.finish(entry, T, ind, d);
+}
+template <class P>
+__device__ __forceinline__ void wf_finish_phase(P& pol, WfShared& S) {
+#if WF_DEFER_FINISH
+    const int n = min(S.n_flist, WF_FCAP);
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const float* f = S.flist + k * 9;
+        const float ind[3] = {f[3], f[4], f[5]}, d[3] = {f[6], f[7], f[8]};
+        pol.finish(make_uint2(__float_as_uint(f[0]), __float_as_uint(f[1])), f[2], ind, d);
+    }
+#endif
 }
 template <bool GI, class P>
 __device__ __forceinline__ void wf_advance_consume(const IaFrame& p, P& pol, WfShared& S, const int t, unsigned& c_q) {
@@ -973,7 +1013,7 @@ __device__ __forceinline__ void wf_advance_refill(const IaFrame& p, P& pol, WfSh
         const float d[3] = {S.st[WS_D][t], S.st[WS_D + 1][t], S.st[WS_D + 2][t]};
         float ind[3] = {0.f, 0.f, 0.f};
         if (GI && stage0 == WF_DONE_IND) { ind[0] = S.st[WS_IND][t]; ind[1] = S.st[WS_IND + 1][t]; ind[2] = S.st[WS_IND + 2][t]; }
-        pol.finish(entry, S.st[WS_TRANS][t], ind, d);
+        wf_finish(pol, S, entry, S.st[WS_TRANS][t], ind, d);
     }
     for (int tries = 0; tries < 4; tries++) {
         int h = atomicAdd(&S.ring_head, 1);
@@ -1002,7 +1042,7 @@ __device__ __forceinline__ void wf_advance_refill(const IaFrame& p, P& pol, WfSh
         }
         // the ray meets no occupied cell: fully visible, no indirect radiance
         const float zero[3] = {0.f, 0.f, 0.f};
-        pol.finish(entry, 1.0f, zero, d);
+        wf_finish(pol, S, entry, 1.0f, zero, d);
     }
     S.st[WS_PACK][t] = __uint_as_float((unsigned)WF_IDLE);
 }
@@ -1025,6 +1065,7 @@ __device__ __forceinline__ void wf_setup(const IaFrame& p, WfShared& S, unsigned
 #endif
         S.gitask = reinterpret_cast<uint2*>(mine + WF_OFF_GITASK);
         S.gixc = reinterpret_cast<float*>(mine + WF_OFF_GIXC);
+        S.flist = reinterpret_cast<float*>(mine + WF_OFF_FLIST);
 #if WF_STATE_GLOBAL
         S.st = reinterpret_cast<float (*)[WF_R]>(mine + WF_OFF_STATE);
 #endif
@@ -1068,7 +1109,7 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
             __syncthreads();
         }
         __syncthreads();
-        if (tid == 0) { S.n_q = 0; S.n_gtask = 0; S.task_next = 0; S.n_btask = 0; S.n_gitask = 0; S.n_rlist = 0; }
+        if (tid == 0) { S.n_q = 0; S.n_gtask = 0; S.task_next = 0; S.n_btask = 0; S.n_gitask = 0; S.n_rlist = 0; S.n_flist = 0; }
         const int ring_tail = S.ring_tail;
         __syncthreads();
         {
@@ -1084,6 +1125,7 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
         const int n_gi = GI ? S.n_gitask : 0;
         const int n_q = S.n_q;
         if (n_q == 0) {
+            wf_finish_phase(pol, S);
             if (n_gi) wf_gi_phase(p, S);
             // (GI: rays waiting for their last radiance, WF_GIWAIT, need one more advance round)
             if (n_gi == 0 && S.ring_tail - S.ring_head <= 0 && !S.more_tiles) break;
@@ -1099,6 +1141,7 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
         // tasks are grabbed dynamically: a warp that finishes its radiance batches early takes more chains instead of
         // waiting (the barrier behind the GI phase was 2.5 % of the kernel's stall samples).  The two phases share no
         // data: the GI tasks carry their own copy of the root.
+        wf_finish_phase(pol, S);   // (deferred estimators of the rays that ended this round: same reasoning)
         if (n_gi) wf_gi_phase(p, S);
         wf_broyden_phase(p, S);
         __syncthreads();
