@@ -243,6 +243,7 @@ extern "C" int ia_set_fields(ia_ctx* c, const float* d_geo_hash, const float* d_
     frag(IA_FRAG_MAT1, 6, 8, [&](int k, int n) { return ia_mat_in_of(k) < 0 ? 0.f : B[IA_MAT_W1T + ia_mat_in_of(k) * 64 + n]; });
     frag(IA_FRAG_MAT2, 8, 8, [&](int k, int n) { return B[IA_MAT_W2T + ia_kperm(k) * 64 + n]; });
     frag(IA_FRAG_MAT3, 8, 1, [&](int k, int n) { return n < 5 ? B[IA_MAT_W3 + n * 64 + ia_kperm(k)] : 0.f; });
+    frag(IA_FRAG_GEO1, 5, 8, [&](int k, int n) { return geo_in(k) < 0 ? 0.f : B[IA_GEO_W1T + geo_in(k) * 64 + n]; });
     if (ia_realloc(&c->d_mlp, IA_BLOB_FLOATS)) return IA_ECUDA;
     IA_CHECK_CUDA(cudaMemcpyAsync(c->d_mlp, blob.data(), (size_t)IA_BLOB_FLOATS * sizeof(float), cudaMemcpyHostToDevice,
                                   (cudaStream_t)stream));

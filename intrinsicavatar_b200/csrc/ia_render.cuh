@@ -484,7 +484,7 @@ k_prim_shade_wf(const __grid_constant__ IaFrame p, const float* __restrict__ hit
                 unsigned char* __restrict__ scratch, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char wf_smem[];
     WfShared& S = *reinterpret_cast<WfShared*>(wf_smem);
-    wf_setup<true>(p, S, scratch);
+    wf_setup<WF_THREADS / 32>(p, S, scratch);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, n_warps = blockDim.x >> 5;
     const long long n = min((long long)work[IA_W_NSAMPLES], sample_cap);
     const long long n_tiles = (n + WF_R - 1) / WF_R;
@@ -574,7 +574,7 @@ k_prim_shade_wf(const __grid_constant__ IaFrame p, const float* __restrict__ hit
                     d0 = od[3]; d1 = od[4]; d2 = od[5];
                 }
                 float rgb[3], mat[5];
-                ia_warp_radiance16<true>(p, S.lvl, wf_w(S), wf_w1f(S), xs, x0, x1, x2, d0, d1, d2, nb, rgb, mat, rec, samples, aux);
+                ia_warp_radiance16<true>(p, S.lvl, wf_w(S), wf_w1f(p, S), xs, x0, x1, x2, d0, d1, d2, nb, rgb, mat, rec, samples, aux);
                 if (lane < nb) {
 #pragma unroll
                     for (int k = 0; k < 3; k++) { aux[rec].rgb[k] = rgb[k]; samples[rec].albedo[k] = mat[k]; }
@@ -582,7 +582,7 @@ k_prim_shade_wf(const __grid_constant__ IaFrame p, const float* __restrict__ hit
                     samples[rec].metal = mat[4];
                 }
             }
-            for (int i = lane; i < WF_MMA_ROWS * 5; i += 32) xs[(i / 5) * IA_GEO_LD + 35 + i % 5] = 0.f;   // (see wf_gi_phase)
+            if (end > warp * per) wf_restore_geo_pads(S, warp);
             wf_count(S, WF_C_QG, (lane == 0 && end > warp * per) ? (unsigned)(end - warp * per) : 0u);
         }
     }
@@ -946,13 +946,13 @@ extern "C" int ia_render(ia_ctx* c, const float* d_rays, int64_t n_rays, int64_t
         size_t sm2 = IA_PRIM_SHADE_SMEM;
         IA_CHECK_CUDA(cudaFuncSetAttribute(k_prim_edges, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
         IA_CHECK_CUDA(cudaFuncSetAttribute(k_prim_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
-        IA_CHECK_CUDA(cudaFuncSetAttribute(k_prim_shade_wf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_BYTES(true)));
+        IA_CHECK_CUDA(cudaFuncSetAttribute(k_prim_shade_wf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_BYTES_SW(WF_THREADS / 32)));
         if (int e = ia_wf_scratch(c)) return e;
         IA_STAGE_BEGIN(c, IA_STAGE_PRIMARY, st);
         k_prim_edges<<<c->n_sm * 2, IA_PRIMARY_THREADS, sm1, st>>>(c->f, c->d_hit_od, c->d_hit_info, c->d_samples, c->d_samples_aux,
                                                                    c->ws_samples, c->d_work, c->d_counters);
 #if IA_PRIM_SHADE_WF
-        k_prim_shade_wf<<<c->n_sm * WF_CTAS_PER_SM, WF_THREADS, WF_SMEM_BYTES(true), st>>>(c->f, c->d_hit_od, c->d_samples, c->d_samples_aux,
+        k_prim_shade_wf<<<c->n_sm * WF_CTAS_PER_SM, WF_THREADS, WF_SMEM_BYTES_SW(WF_THREADS / 32), st>>>(c->f, c->d_hit_od, c->d_samples, c->d_samples_aux,
                                                                                          c->ws_samples, c->d_work, c->d_wf_scratch, c->d_counters);
 #else
         k_prim_shade<<<c->n_sm * IA_PRIM_SHADE_CTAS, IA_PRIMARY_THREADS, sm2, st>>>(c->f, c->d_hit_od, c->d_samples, c->d_samples_aux, c->ws_samples,
@@ -1252,10 +1252,10 @@ __global__ void __launch_bounds__(256) k_op_geometry(const __grid_constant__ IaF
                                                      float* __restrict__ sdf) {
     extern __shared__ __align__(16) float smem[];
     float* w = smem;
-    float4* w1f = reinterpret_cast<float4*>(smem + IA_GEO_END);
+    float4* w1f = reinterpret_cast<float4*>(smem + IA_GEOC_END);
     float* xs_all = reinterpret_cast<float*>(w1f + IA_GEO_KSTEPS * 8 * 32);
     __shared__ IaLevel lvl[IA_N_LEVELS];
-    ia_stage(w, p.mlp, IA_GEO_END);
+    ia_stage_geoc(w, p.mlp);
     ia_stage_bfrag(w1f, IA_GEO_KSTEPS, 8, [&](int k, int nn) { return ia_geo_w1(p.mlp, k, nn); });
     for (int i = threadIdx.x; i < (int)(blockDim.x >> 5) * 16 * IA_GEO_LD; i += blockDim.x) xs_all[i] = 0.f;
     if (threadIdx.x < IA_N_LEVELS) lvl[threadIdx.x] = ia_level(p, threadIdx.x);
@@ -1277,7 +1277,7 @@ extern "C" int ia_op_geometry(ia_ctx* c, const float* d_xc, int64_t n, float* d_
     IA_REQUIRE(c->have_fields, IA_ESTATE, "ia_op_geometry: call ia_set_fields first");
     if (n == 0) return IA_OK;
     IA_CHECK_CUDA(cudaSetDevice(c->device));
-    const size_t sm = IA_GEO_END * sizeof(float) + IA_GEO_KSTEPS * 8 * 32 * sizeof(float4) + 8 * 16 * IA_GEO_LD * sizeof(float);
+    const size_t sm = IA_GEOC_END * sizeof(float) + IA_GEO_KSTEPS * 8 * 32 * sizeof(float4) + 8 * 16 * IA_GEO_LD * sizeof(float);
     IA_CHECK_CUDA(cudaFuncSetAttribute(k_op_geometry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 127) / 128, (int64_t)c->n_sm * 2));
     k_op_geometry<<<blocks, 256, sm, (cudaStream_t)stream>>>(c->f, d_xc, n, d_sdf);

@@ -60,7 +60,8 @@ namespace cg = cooperative_groups;
 #define IA_FRAG_MAT1 (IA_FRAG_RAD3 + 8)         // material 48 -> 64 (6 x 8), A from the shading tile
 #define IA_FRAG_MAT2 (IA_FRAG_MAT1 + 6 * 8)     // material 64 -> 64
 #define IA_FRAG_MAT3 (IA_FRAG_MAT2 + 8 * 8)     // material 64 -> 5 (8 x 1)
-#define IA_FRAG_END (IA_FRAG_MAT3 + 8)
+#define IA_FRAG_GEO1 (IA_FRAG_MAT3 + 8)         // geometry 35 -> 64 (5 x 8), A from the geometry / shading tile
+#define IA_FRAG_END (IA_FRAG_GEO1 + 5 * 8)
 #define IA_BLOB_FLOATS (IA_MLP_END + IA_FRAG_END * 128)
 
 #define IA_SEC_ZERO_CROSSING 0

@@ -63,9 +63,6 @@
 #ifndef WF_DEFER_FINISH
 #define WF_DEFER_FINISH 1   // the estimator of a finished ray (BRDF, 6 atomics) is not evaluated in the refill pass, which the whole
 #endif                      // CTA waits for, but listed and evaluated in front of the dynamically scheduled Broyden phase
-#ifndef WF_GI_FULL_BATCHES
-#define WF_GI_FULL_BATCHES 1
-#endif
 #ifndef WF_BTASK_SMEM
 #define WF_BTASK_SMEM 0   // 1: Broyden task list in shared memory, so that a chain start reads its task id with shared-memory
 #endif                    // latency (from the global scratch that read is an exposed L2 round trip: 6 % of the Broyden phase's
@@ -109,11 +106,28 @@ enum { WF_ACT_NEXT = 0, WF_ACT_CDF = 1, WF_ACT_FINE_START = 2, WF_ACT_FINISH = 3
 #define WS_TPL 27     // 27..31
 #define WS_IND 32      // 32..34 indirect radiance accumulated over the fine samples (global illumination)
 
+// What the tensor-core paths read of the fp32 geometry weights, staged compactly in shared memory (the 35 -> 64 layer and the
+// rows 1..12 of the 64 -> 13 layer are read as B fragments): 576 bytes instead of the 12.6 KB blob -- the rest is L1.
+#define IA_GEOC_B1 0      // [64] bias of the 35 -> 64 layer
+#define IA_GEOC_W2 64     // [64] row 0 of the 64 -> 13 layer (the sdf)
+#define IA_GEOC_B2 128    // [16] bias of the 64 -> 13 layer (13 used)
+#define IA_GEOC_END 144
+__device__ __forceinline__ void ia_stage_geoc(float* __restrict__ dst, const float* __restrict__ mlp) {
+    for (int i = threadIdx.x; i < IA_GEOC_END; i += blockDim.x)
+        dst[i] = i < 64 ? mlp[IA_GEO_B1 + i] : (i < 128 ? mlp[IA_GEO_W2 + i - 64] : mlp[IA_GEO_B2 + i - 128]);
+}
 #define IA_GEO_KSTEPS 5   // geometry tile: [16][IA_GEO_LD], 40 columns read (layout: ia_warp_geometry)
 #define IA_GEO_LD 44
 // per-warp input tiles of the tensor-core phases: [16][IA_GEO_LD] for the geometry phase; with global illumination the same
 // memory is the [16][IA_SHADE_LD] shading tile of the GI phase (+ 4 floats: its last k-step reads 16 bytes past the end)
-#define WF_TILE_FLOATS(GI) ((WF_THREADS / 32) * 16 * ((GI) ? IA_SHADE_LD : 44) + 4)
+// SW = number of warps that own a shading tile: WF_GI_WARPS in the shading stage's GI phase (it runs next to the Broyden phase
+// and a round has <= 16 batches: half the warps are enough, and every KB not spent here is L1 for the gathers), all of them
+// in k_prim_shade_wf (0 = geometry tiles only).
+#ifndef WF_GI_WARPS
+#define WF_GI_WARPS 8
+#endif
+#define WF_TILE_FLOATS_SW(SW) (((SW) * 16 * IA_SHADE_LD > (WF_THREADS / 32) * 16 * IA_GEO_LD ? (SW) * 16 * IA_SHADE_LD : (WF_THREADS / 32) * 16 * IA_GEO_LD) + 4)
+#define WF_TILE_FLOATS(GI) WF_TILE_FLOATS_SW((GI) ? WF_GI_WARPS : 0)
 struct WfShared {
     float* w;               // MLP weights staged behind this struct (geometry only, or geometry + radiance for GI)
     float tfs13[IA_N_INIT * 12];
@@ -162,8 +176,21 @@ struct WfShared {
 __device__ __forceinline__ float* wf_w(WfShared& S) {
     return reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&S) + ((sizeof(WfShared) + 15) & ~(size_t)15));
 }
-__device__ __forceinline__ float4* wf_w1f(WfShared& S) { return reinterpret_cast<float4*>(wf_w(S) + IA_GEO_END); }
-__device__ __forceinline__ float* wf_xs(WfShared& S) { return reinterpret_cast<float*>(wf_w1f(S) + IA_GEO_KSTEPS * 8 * 32); }
+#ifndef WF_W1F_SMEM
+#define WF_W1F_SMEM 0   // B fragments of the geometry 35 -> 64 layer: 1 = staged in shared memory (20 KB), 0 = read from global memory
+#endif                  // through L1 like the other layers' (IA_FRAG_GEO1).
+// Shared memory is taken from L1 in steps (.. 64, 100, 132, 164 .. KB per SM): measured at 512^2 x 1024 spp, GI on, frames
+// 2 / 13 / 1, shade stage: 146 KB (16 shading tiles) 795 ms -> 122 KB (8 tiles) 775 ms -> 110 KB (compact fp32 weights: same
+// step, 776 ms) -> 90 KB (these fragments through L1) 764 ms.
+#define WF_W1F_FLOATS (WF_W1F_SMEM ? IA_GEO_KSTEPS * 8 * 32 * 4 : 0)
+__device__ __forceinline__ const float4* wf_w1f(const IaFrame& p, WfShared& S) {
+#if WF_W1F_SMEM
+    return reinterpret_cast<const float4*>(wf_w(S) + IA_GEOC_END);
+#else
+    return reinterpret_cast<const float4*>(p.mlp + IA_MLP_END) + IA_FRAG_GEO1 * 32;
+#endif
+}
+__device__ __forceinline__ float* wf_xs(WfShared& S) { return wf_w(S) + IA_GEOC_END + WF_W1F_FLOATS; }
 
 // ------------------------------------------------------------------------------------------------
 // marcher <-> shared state
@@ -470,13 +497,13 @@ __device__ __forceinline__ float ia_warp_geometry(const IaFrame& p, const IaLeve
         float c[4][4];
 #pragma unroll
         for (int nt = 0; nt < 4; nt++) {
-            const float2 b = *reinterpret_cast<const float2*>(w + IA_GEO_B1 + 8 * (4 * nh + nt) + 2 * t);
+            const float2 b = *reinterpret_cast<const float2*>(w + IA_GEOC_B1 + 8 * (4 * nh + nt) + 2 * t);
             c[nt][0] = b.x; c[nt][1] = b.y; c[nt][2] = b.x; c[nt][3] = b.y;
         }
         ia_mma_layer_smem<IA_GEO_KSTEPS, 4, 8, ROWS>(xs, IA_GEO_LD, w1f + 4 * nh * 32, c);
 #pragma unroll
         for (int nt = 0; nt < 4; nt++) {
-            const float2 w2 = *reinterpret_cast<const float2*>(w + IA_GEO_W2 + 8 * (4 * nh + nt) + 2 * t);
+            const float2 w2 = *reinterpret_cast<const float2*>(w + IA_GEOC_W2 + 8 * (4 * nh + nt) + 2 * t);
             lo = fmaf(w2.x, ia_softplus100(c[nt][0]), lo); lo = fmaf(w2.y, ia_softplus100(c[nt][1]), lo);
             if (ROWS == 16) { hi = fmaf(w2.x, ia_softplus100(c[nt][2]), hi); hi = fmaf(w2.y, ia_softplus100(c[nt][3]), hi); }
         }
@@ -487,7 +514,7 @@ __device__ __forceinline__ float ia_warp_geometry(const IaFrame& p, const IaLeve
     lo += __shfl_xor_sync(FULL, lo, 2); hi += __shfl_xor_sync(FULL, hi, 2);
     // row j < 8 sits in lanes 4j .. 4j + 3 (lo), row j >= 8 in lanes 4 (j - 8) .. (hi)
     const float slo = __shfl_sync(FULL, lo, 4 * (lane & 7)), shi = __shfl_sync(FULL, hi, 4 * (lane & 7));
-    return ((lane & 8) ? shi : slo) + w[IA_GEO_B2];
+    return ((lane & 8) ? shi : slo) + w[IA_GEOC_B2];
 }
 
 __device__ __forceinline__ void wf_geometry_phase(const IaFrame& p, WfShared& S) {
@@ -520,7 +547,7 @@ __device__ __forceinline__ void wf_geometry_phase(const IaFrame& p, WfShared& S)
             const float* cd = S.cand + ci_n * 3;
             y0 = cd[0]; y1 = cd[1]; y2 = cd[2];
         }
-        const float s = ia_warp_geometry<WF_MMA_ROWS>(p, S.lvl, wf_w(S), wf_w1f(S), xs, x0, x1, x2, nb);
+        const float s = ia_warp_geometry<WF_MMA_ROWS>(p, S.lvl, wf_w(S), wf_w1f(p, S), xs, x0, x1, x2, nb);
         if (lane < nb) { S.csdf[ci] = s; c_geo++; }
         b0 = bn; ci = ci_n; x0 = y0; x1 = y1; x2 = y2;
     }
@@ -573,7 +600,7 @@ __device__ __forceinline__ void ia_warp_radiance16(const IaFrame& p, const IaLev
         float c[8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; nt++) {
-            const float2 b = *reinterpret_cast<const float2*>(w + IA_GEO_B1 + 8 * nt + 2 * t);
+            const float2 b = *reinterpret_cast<const float2*>(w + IA_GEOC_B1 + 8 * nt + 2 * t);
             c[nt][0] = b.x; c[nt][1] = b.y; c[nt][2] = b.x; c[nt][3] = b.y;
         }
         ia_mma_layer_smem<IA_GEO_KSTEPS, 8, 8, 16>(xs, LD, w1f, c);
@@ -582,7 +609,7 @@ __device__ __forceinline__ void ia_warp_radiance16(const IaFrame& p, const IaLev
         float dl[8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; nt++) {
-            const float2 w2 = *reinterpret_cast<const float2*>(w + IA_GEO_W2 + 8 * nt + 2 * t);
+            const float2 w2 = *reinterpret_cast<const float2*>(w + IA_GEOC_W2 + 8 * nt + 2 * t);
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const float x = c[nt][k];
@@ -593,7 +620,7 @@ __device__ __forceinline__ void ia_warp_radiance16(const IaFrame& p, const IaLev
         float f[2][4];
 #pragma unroll
         for (int nt = 0; nt < 2; nt++) {
-            const float2 b = *reinterpret_cast<const float2*>(w + IA_GEO_B2 + 8 * nt + 2 * t);   // [16], 13 used, rest 0
+            const float2 b = *reinterpret_cast<const float2*>(w + IA_GEOC_B2 + 8 * nt + 2 * t);   // [16], 13 used, rest 0
             f[nt][0] = b.x; f[nt][1] = b.y; f[nt][2] = b.x; f[nt][3] = b.y;
         }
         ia_mma_layer_regs<2>(c, frags + IA_FRAG_FEAT * 32, f);
@@ -691,17 +718,27 @@ __device__ __forceinline__ void ia_warp_radiance16(const IaFrame& p, const IaLev
     __syncwarp();   // the tile may be overwritten by the next batch
 }
 
+// The geometry phase reads columns 35..39 of the rows of ITS tiles ([warps][16][IA_GEO_LD] over the same memory as the shading
+// tiles) against zero weights; they must stay finite: a warp that used its shading tile zeroes the ones inside it.
+__device__ __forceinline__ void wf_restore_geo_pads(WfShared& S, int warp) {
+    const int lane = threadIdx.x & 31;
+    float* all = wf_xs(S);
+    const int f0 = warp * 16 * IA_SHADE_LD, f1 = f0 + 16 * IA_SHADE_LD;
+    for (int r = f0 / IA_GEO_LD + (lane / 5); r * IA_GEO_LD + 35 < f1 && r < (WF_THREADS / 32) * 16; r += 6) {
+        const int o = r * IA_GEO_LD + 35 + lane % 5;
+        if (lane < 30 && o >= f0 && o < f1) all[o] = 0.f;
+    }
+}
+
 // GI: radiance at the arg-min root of every fine sample consumed this round.
 __device__ __forceinline__ void wf_gi_phase(const IaFrame& p, WfShared& S) {
     const int n = S.n_gitask;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
-#if WF_GI_FULL_BATCHES
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int n_warps = WF_GI_WARPS;     // the warps that own a shading tile; the others go straight to the Broyden phase
+    if (warp >= n_warps) return;
     // whole 16-row batches: a round has 100-200 tasks, i.e. 6-12 rows per warp if split evenly, and the tensor-core stages
     // cost the same for 6 rows as for 16.  The warps left without a batch go straight to the Broyden phase's task loop.
     const int per = (((n + n_warps - 1) / n_warps) + 15) & ~15;
-#else
-    const int per = (n + n_warps - 1) / n_warps;
-#endif
     const int end = min(n, (warp + 1) * per);
     float* xs = wf_xs(S) + warp * 16 * IA_SHADE_LD;
     for (int b0 = warp * per; b0 < end; b0 += 16) {
@@ -717,14 +754,13 @@ __device__ __forceinline__ void wf_gi_phase(const IaFrame& p, WfShared& S) {
             d0 = S.st[WS_D][t]; d1 = S.st[WS_D + 1][t]; d2 = S.st[WS_D + 2][t];
         }
         float rgb[3];
-        ia_warp_radiance16(p, S.lvl, wf_w(S), wf_w1f(S), xs, x0, x1, x2, d0, d1, d2, nb, rgb);
+        ia_warp_radiance16(p, S.lvl, wf_w(S), wf_w1f(p, S), xs, x0, x1, x2, d0, d1, d2, nb, rgb);
         if (lane < nb) {
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) S.st[WS_IND + ch][t] += wgt * rgb[ch];
         }
     }
-    // the geometry phase reads columns 35..39 of ITS tile layout ([16][IA_GEO_LD] at the same address) against zero weights
-    for (int i = lane; i < WF_MMA_ROWS * 5; i += 32) xs[(i / 5) * IA_GEO_LD + 35 + i % 5] = 0.f;
+    if (end > warp * per) wf_restore_geo_pads(S, warp);
     wf_count(S, WF_C_QG, (lane == 0 && end > warp * per) ? (unsigned)(end - warp * per) : 0u);   // = geometry evaluations with gradient = radiance evaluations = skinning fetches of this phase
 }
 
@@ -1048,15 +1084,15 @@ __device__ __forceinline__ void wf_advance_refill(const IaFrame& p, P& pol, WfSh
 }
 
 // shared memory + scratch set-up of a wavefront CTA (weights, fragments, tiles, per-CTA scratch pointers, empty ray slots)
-template <bool GI>
+template <int SHADE_WARPS>
 __device__ __forceinline__ void wf_setup(const IaFrame& p, WfShared& S, unsigned char* __restrict__ scratch) {
     const int tid = threadIdx.x;
-    const int n_w = IA_GEO_END;
+    const int n_w = IA_GEOC_END;
     if (tid == 0) {
         unsigned char* mine = scratch + (size_t)blockIdx.x * WF_SCRATCH_BYTES;
         S.w = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&S) + ((sizeof(WfShared) + 15) & ~15));
         S.w1f = reinterpret_cast<float4*>(S.w + n_w);
-        S.xs = reinterpret_cast<float*>(S.w1f + IA_GEO_KSTEPS * 8 * 32);
+        S.xs = S.w + n_w + WF_W1F_FLOATS;
         S.cand = reinterpret_cast<float*>(mine);
         S.csdf = reinterpret_cast<float*>(mine + WF_OFF_CSDF);
         S.gtask = reinterpret_cast<unsigned short*>(mine + WF_OFF_GTASK);
@@ -1071,10 +1107,11 @@ __device__ __forceinline__ void wf_setup(const IaFrame& p, WfShared& S, unsigned
 #endif
     }
     __syncthreads();
-    for (int i = tid * 4; i < n_w; i += blockDim.x * 4)
-        *reinterpret_cast<float4*>(S.w + i) = __ldg(reinterpret_cast<const float4*>(p.mlp + i));
+    ia_stage_geoc(S.w, p.mlp);
+#if WF_W1F_SMEM
     ia_stage_bfrag(S.w1f, IA_GEO_KSTEPS, 8, [&](int k, int n) { return ia_geo_w1(p.mlp, k, n); });
-    for (int i = tid; i < (int)(WF_TILE_FLOATS(GI)); i += blockDim.x) S.xs[i] = 0.f;
+#endif
+    for (int i = tid; i < (int)(WF_TILE_FLOATS_SW(SHADE_WARPS)); i += blockDim.x) S.xs[i] = 0.f;
     if (tid < IA_N_INIT * 12) S.tfs13[tid] = p.tfs[p.init_bones[tid / 12]][tid % 12];
     if (tid < IA_N_LEVELS) S.lvl[tid] = ia_level(p, tid);
     for (int t = tid; t < WF_R; t += blockDim.x) S.st[WS_PACK][t] = __uint_as_float(0u);
@@ -1088,7 +1125,7 @@ template <bool GI, class P>
 __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, unsigned char* __restrict__ scratch,
                                        unsigned long long* __restrict__ counters) {
     const int tid = threadIdx.x;
-    wf_setup<GI>(p, S, scratch);
+    wf_setup<(GI ? WF_GI_WARPS : 0)>(p, S, scratch);
     const int tile_items = pol.tile_items();
     const long long n_tiles = (pol.n_items() + tile_items - 1) / tile_items;
     while (true) {
@@ -1354,8 +1391,9 @@ struct WfShadePolicy {
     }
 };
 
-#define WF_SMEM_BYTES(GI) (((sizeof(WfShared) + 15) & ~(size_t)15) + IA_GEO_END * sizeof(float) + \
-                           IA_GEO_KSTEPS * 8 * 32 * sizeof(float4) + WF_TILE_FLOATS(GI) * sizeof(float))
+#define WF_SMEM_BYTES_SW(SW) (((sizeof(WfShared) + 15) & ~(size_t)15) + IA_GEOC_END * sizeof(float) + \
+                              WF_W1F_FLOATS * sizeof(float) + WF_TILE_FLOATS_SW(SW) * sizeof(float))
+#define WF_SMEM_BYTES(GI) WF_SMEM_BYTES_SW((GI) ? WF_GI_WARPS : 0)
 
 template <bool GI, int MODE>
 __global__ void __launch_bounds__(WF_THREADS, WF_CTAS_PER_SM) k_shade_wf(const __grid_constant__ IaFrame p, WfShadePolicy<MODE> pol,
