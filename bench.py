@@ -45,11 +45,11 @@ METRIC = "shaded_samples_per_sec"
 UNIT = "samples/s"
 N_SEQ_FRAMES = 16      # frames of the AIST sequence one pass of the multi-GPU job covers
 # Measured cost of every frame of the sequence (ms per frame, configs[3], 1 x B200, profiles/r2_bench_frames16.json): the
-# body turns and its limbs occlude each other differently from frame to frame -- 553 .. 1098 ms.  Used (a) to put the
+# body turns and its limbs occlude each other differently from frame to frame -- 480 .. 947 ms.  Used (a) to put the
 # sequence in an order whose every window is representative (expensive and cheap frames alternate), so that a short run
 # does not time an unrepresentative stretch, and (b) as the estimate for the longest-first assignment of a step batch's
 # frames to the ranks (parallel.assign_frames).
-FRAME_COST_MS = [1022.3, 1059.1, 1090.8, 1098.4, 1052.8, 954.1, 822.0, 694.3, 657.5, 642.0, 632.6, 608.1, 552.8, 587.9, 722.5, 737.1]
+FRAME_COST_MS = [891.9, 922.6, 944.7, 947.1, 898.8, 816.4, 703.1, 594.3, 565.6, 555.7, 549.7, 527.8, 479.7, 508.9, 625.5, 635.9]   # profiles/r2_bench_frames16.json
 
 
 def sequence_order():
@@ -276,7 +276,7 @@ def workload_config(args, world):
     return {
         "workload": f"BASELINE configs[{args.config}]: {args.res}x{args.res} {what}, prepare+forward per step",
         "frame_source": (f"AIST animation sequence, frames 0..{N_SEQ_FRAMES - 1} in an order that alternates expensive and cheap "
-                         f"frames ({sequence_order()}; per-frame cost 553..1098 ms): step s covers entries [s*N, s*N+N) of it, the "
+                         f"frames ({sequence_order()}; per-frame cost 480..947 ms): step s covers entries [s*N, s*N+N) of it, the "
                          "frames of the timed steps are dealt to the N ranks longest-first (parallel.assign_frames); synthetic "
                          "24-joint body, random-init hash grids + MLPs (seed 0), the reference's city.hdr at 1024x2048"),
         "rays_per_frame": args.res * args.res, "spp": 1 if args.primary_only else args.spp, "gi": bool(args.gi),
