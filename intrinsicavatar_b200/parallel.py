@@ -169,6 +169,9 @@ class FrameCollector:
         if self.transport == "p2p" and self.rank != self.dst:
             self.peer = None
             self._peer_storage = None
+            import gc
+            gc.collect()
+            torch.cuda.ipc_collect()      # hand the consumer-side references back now, not at interpreter exit
         if self.ws > 1:
             if torch.device(self.device).type == "cuda":
                 torch.cuda.synchronize()
