@@ -114,9 +114,12 @@ __device__ __forceinline__ void ia_mma_layer_regs(const float h[8][4], const BF*
 //   64..66 world normal | 67 unused
 // (the reference's radiance input order is [xyz, hash, feature, SH, normal]: ia_rad_in_of maps a tile column to it; the
 // first 48 columns are the material network's input, cat[xyz_embd 35, feature 13]).  The radiance layer 1 runs 9 k-steps
-// = 72 columns: columns 67..71 carry zero weights and alias column 67 and the first four columns of the NEXT row, so every
-// float of the tile -- and the 16 bytes behind the last one -- must be finite.
+// = 72 columns: columns 67..71 carry zero weights and alias column 67 and the first four columns of the NEXT row (the
+// four padding floats of IA_SHADE_TILE for the last row), so every float of the tile must be finite.
 #define IA_SHADE_LD 68
+// floats per warp tile: 16 rows + 4 floats that stay zero -- the last k-step of row 15 reads them, so that no warp ever
+// reads another warp's tile (rows 0..14 read the first four columns of the next row of the SAME tile)
+#define IA_SHADE_TILE (16 * IA_SHADE_LD + 4)
 __host__ __device__ __forceinline__ int ia_rad_in_of(int k) {    // tile column -> input index of the radiance net (-1: padding)
     return k < 32 ? 3 + k : (k < 35 ? k - 32 : (k < 67 ? k : -1));
 }

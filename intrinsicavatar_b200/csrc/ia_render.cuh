@@ -295,7 +295,7 @@ k_prim_edges(const __grid_constant__ IaFrame p, const float* __restrict__ hit_od
 #define IA_PRIM_SHADE_MMA 1
 #endif
 #if IA_PRIM_SHADE_MMA
-#define IA_PRIM_SHADE_SMEM ((IA_GEO_END + (IA_PRIMARY_THREADS / 32) * 16 * IA_SHADE_LD + 4) * sizeof(float))
+#define IA_PRIM_SHADE_SMEM ((IA_GEO_END + (IA_PRIMARY_THREADS / 32) * IA_SHADE_TILE) * sizeof(float))
 __global__ void __launch_bounds__(IA_PRIMARY_THREADS, IA_PRIM_SHADE_CTAS)
 k_prim_shade(const __grid_constant__ IaFrame p, const float* __restrict__ hit_od, IaSample* __restrict__ samples,
              IaSampleAux* __restrict__ aux, long long sample_cap, const int* __restrict__ work,
@@ -304,12 +304,12 @@ k_prim_shade(const __grid_constant__ IaFrame p, const float* __restrict__ hit_od
     float* wgeo = smem;
     float* xs_all = smem + IA_GEO_END;
     ia_stage(wgeo, p.mlp, IA_GEO_END);
-    for (int i = threadIdx.x; i < (IA_PRIMARY_THREADS / 32) * 16 * IA_SHADE_LD + 4; i += blockDim.x) xs_all[i] = 0.f;
+    for (int i = threadIdx.x; i < (IA_PRIMARY_THREADS / 32) * IA_SHADE_TILE; i += blockDim.x) xs_all[i] = 0.f;
     __syncthreads();
     Team team = cg::tiled_partition<IA_TEAM>(cg::this_thread_block());
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, l = lane & 15, half = lane >> 4, warp = threadIdx.x >> 5;
-    float* xs = xs_all + warp * 16 * IA_SHADE_LD;
+    float* xs = xs_all + warp * IA_SHADE_TILE;
     const float4* frags = reinterpret_cast<const float4*>(p.mlp + IA_MLP_END);
     const long long n = min((long long)work[IA_W_NSAMPLES], sample_cap);
     const long long n_batches = (n + 15) / 16;
@@ -560,7 +560,7 @@ k_prim_shade_wf(const __grid_constant__ IaFrame p, const float* __restrict__ hit
             const int n_sh = S.n_gitask;
             const int per = (((n_sh + n_warps - 1) / n_warps) + 15) & ~15;    // whole 16-row batches per warp
             const int end = min(n_sh, (warp + 1) * per);
-            float* xs = wf_xs(S) + warp * 16 * IA_SHADE_LD;
+            float* xs = wf_xs(S) + warp * IA_SHADE_TILE;
             for (int b0 = warp * per; b0 < end; b0 += 16) {
                 const int nb = min(16, end - b0);
                 long long rec = 0;

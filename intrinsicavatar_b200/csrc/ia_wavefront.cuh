@@ -126,7 +126,7 @@ __device__ __forceinline__ void ia_stage_geoc(float* __restrict__ dst, const flo
 #ifndef WF_GI_WARPS
 #define WF_GI_WARPS 8
 #endif
-#define WF_TILE_FLOATS_SW(SW) (((SW) * 16 * IA_SHADE_LD > (WF_THREADS / 32) * 16 * IA_GEO_LD ? (SW) * 16 * IA_SHADE_LD : (WF_THREADS / 32) * 16 * IA_GEO_LD) + 4)
+#define WF_TILE_FLOATS_SW(SW) ((SW) * IA_SHADE_TILE > (WF_THREADS / 32) * 16 * IA_GEO_LD ? (SW) * IA_SHADE_TILE : (WF_THREADS / 32) * 16 * IA_GEO_LD)
 #define WF_TILE_FLOATS(GI) WF_TILE_FLOATS_SW((GI) ? WF_GI_WARPS : 0)
 struct WfShared {
     float* w;               // MLP weights staged behind this struct (geometry only, or geometry + radiance for GI)
@@ -723,7 +723,7 @@ __device__ __forceinline__ void ia_warp_radiance16(const IaFrame& p, const IaLev
 __device__ __forceinline__ void wf_restore_geo_pads(WfShared& S, int warp) {
     const int lane = threadIdx.x & 31;
     float* all = wf_xs(S);
-    const int f0 = warp * 16 * IA_SHADE_LD, f1 = f0 + 16 * IA_SHADE_LD;
+    const int f0 = warp * IA_SHADE_TILE, f1 = f0 + IA_SHADE_TILE;
     for (int r = f0 / IA_GEO_LD + (lane / 5); r * IA_GEO_LD + 35 < f1 && r < (WF_THREADS / 32) * 16; r += 6) {
         const int o = r * IA_GEO_LD + 35 + lane % 5;
         if (lane < 30 && o >= f0 && o < f1) all[o] = 0.f;
@@ -740,7 +740,7 @@ __device__ __forceinline__ void wf_gi_phase(const IaFrame& p, WfShared& S) {
     // cost the same for 6 rows as for 16.  The warps left without a batch go straight to the Broyden phase's task loop.
     const int per = (((n + n_warps - 1) / n_warps) + 15) & ~15;
     const int end = min(n, (warp + 1) * per);
-    float* xs = wf_xs(S) + warp * 16 * IA_SHADE_LD;
+    float* xs = wf_xs(S) + warp * IA_SHADE_TILE;
     for (int b0 = warp * per; b0 < end; b0 += 16) {
         const int nb = min(16, end - b0);
         int t = 0;

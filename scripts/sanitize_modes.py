@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Tiny frame in every render mode (for compute-sanitizer): 20x20 rays, 8 spp, light / light+GI / uniform_light /
-mats / mis+GI / add_emitter, plus the frame producer / consumer kernels.  Prints one line per mode."""
+mats / mis+GI / add_emitter, the non-default secondary-sampling switches, primary only, plus the frame producer / consumer
+kernels, the tensor-core geometry op, the geometry backward and the device voxelisation.  Prints one line per case."""
 import os
 import sys
 
@@ -40,3 +41,23 @@ for mode, gi, emit in (("light", False, False), ("light", True, False), ("unifor
     torch.cuda.synchronize()
     print(mode, "gi" if gi else "", "emitter" if emit else "", "mean rgb_phys", float(o["comp_rgb_phys"].mean()),
           "uint8 mean", float(img.float().mean()), "rays", e.counters()["secondary_rays"])
+
+# round 2: the secondary-sampling switches, primary only, image grid, tensor-core geometry op, geometry backward, voxelisation
+e.set_light(env, tabs["u1"], tabs["u2"])
+for imp, zc in ((False, True), (True, False), (False, False)):
+    e.set_secondary_sampling(importance_sample=imp, zero_crossing_search=zc)
+    o = e.render(rays, gi=True, seed=0, render_mode="light")
+    torch.cuda.synchronize()
+    print("switches", imp, zc, "mean rgb_phys", float(o["comp_rgb_phys"].mean()))
+e.set_secondary_sampling(True, True)
+o = e.render(rays, primary_only=True, seed=0)
+grid = torch.empty(H, 3 * H, 3, dtype=torch.uint8, device="cuda")
+e.pack_grid8(grid, 0, o["comp_rgb_full"].reshape(H, H, 3))
+e.pack_grid8(grid, H, o["depth"].reshape(H, H), kind="grayscale", data_range=None)
+e.pack_grid8(grid, 2 * H, o["comp_normal"].reshape(H, H, 3), data_range=(-1, 1))
+bb = torch.as_tensor(snarf.bbox, dtype=torch.float32).reshape(2, 3)
+xc = (bb[0] + torch.rand(1000, 3) * (bb[1] - bb[0])).cuda()
+sd = e.op_geometry(xc)
+gb = e.op_geometry_backward(xc, torch.randn(1000, 13).cuda())
+torch.cuda.synchronize()
+print("primary only / grid / geometry ops", float(grid.float().mean()), float(sd.mean()))
