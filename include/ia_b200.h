@@ -111,6 +111,13 @@ int ia_reserve_samples(ia_ctx* ctx, int64_t n_samples);
  * d_binaries_out (optional, may be NULL): res^3 bytes.                                              */
 int ia_build_occupancy(ia_ctx* ctx, const float* h_aabb6, int res, const float* d_jitter,
                        uint8_t* d_binaries_out, void* stream);
+/* Training-time occupancy update (OccGridEstimator._update, models/occ_grid/temporal_occ_grid.py:369-411, driven by
+ * IntrinsicAvatarModel.update_step, models/intrinsic_avatar.py:232-264): ONE jittered point per cell
+ * (d_jitter [res^3,3]), occs = max(occs * ema_decay, alpha) on the caller's EMA state d_occs [res^3] of the frame's
+ * level (updated in place), then max-pool / threshold min(mean, occ_thre) / largest component like the test-time
+ * build; the result becomes the context's occupancy grid.  d_binaries_out optional.                     */
+int ia_update_occupancy_ema(ia_ctx* ctx, const float* h_aabb6, int res, const float* d_jitter, float* d_occs,
+                            float ema_decay, float occ_thre, uint8_t* d_binaries_out, void* stream);
 /* Install a caller-provided grid instead (res^3 bytes, cell = (x*res+y)*res+z).                      */
 int ia_set_occupancy(ia_ctx* ctx, const float* h_aabb6, int res, const uint8_t* d_binaries, void* stream);
 

@@ -41,7 +41,7 @@ EXPORTS = [
     "ia_op_precompute", "ia_op_broyden", "ia_op_query", "ia_op_shade_fields", "ia_op_geometry", "ia_op_geometry_backward", "ia_op_traverse",
     "ia_op_ray_resampling", "ia_op_ray_resampling_merge", "ia_op_ray_resampling_sdf_fine", "ia_op_ray_resampling_fine", "ia_op_unpack_info",
     "ia_op_secondary", "ia_op_brdf", "ia_op_bsdf_sample_pdf", "ia_op_env",
-    "ia_make_rays", "ia_pack_rgb8", "ia_pack_grid8",
+    "ia_make_rays", "ia_pack_rgb8", "ia_pack_grid8", "ia_update_occupancy_ema",
 ]
 
 

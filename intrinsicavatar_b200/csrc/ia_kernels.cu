@@ -590,10 +590,14 @@ extern "C" int ia_op_traverse(ia_ctx* c, const float* d_o, const float* d_d, int
 
 // ================================================================================================
 // occupancy grid build (models/intrinsic_avatar.py:307-381)
+// N_S jittered points per cell (3: test-time grid, max over them; 1: the training-time update).  ema != NULL: the EMA state of
+// the level, occs = max(ema * decay, alpha), written back (OccGridEstimator._update, temporal_occ_grid.py:392-394).
+template <int N_S>
 __global__ void __launch_bounds__(256) k_occ_eval(const __grid_constant__ IaFrame p, int res, float aabb0, float aabb1,
                                                   float aabb2, float ext0, float ext1, float ext2,
                                                   const float* __restrict__ jitter, float* __restrict__ occs,
-                                                  unsigned long long* __restrict__ counters) {
+                                                  unsigned long long* __restrict__ counters, float* __restrict__ ema = nullptr,
+                                                  float decay = 0.f) {
     extern __shared__ __align__(16) float smem[];
     ia_stage(smem, p.mlp, IA_GEO_END);
     __syncthreads();
@@ -604,8 +608,8 @@ __global__ void __launch_bounds__(256) k_occ_eval(const __grid_constant__ IaFram
     for (int v = blockIdx.x * (blockDim.x / IA_TEAM) + threadIdx.x / IA_TEAM; v < nvox; v += teams) {
         int cz = v % res, cy = (v / res) % res, cx = v / (res * res);
         float best = 0.f;
-        for (int s = 0; s < 3; s++) {
-            const float* j = jitter + ((size_t)v * 3 + s) * 3;
+        for (int s = 0; s < N_S; s++) {
+            const float* j = jitter + ((size_t)v * N_S + s) * 3;
             float x[3];
             x[0] = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn((float)cx, j[0]), (float)res), ext0), aabb0);
             x[1] = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn((float)cy, j[1]), (float)res), ext1), aabb1);
@@ -616,7 +620,10 @@ __global__ void __launch_bounds__(256) k_occ_eval(const __grid_constant__ IaFram
             float a = ia_alpha(q.sdf, p.step_primary, p.beta);
             best = s == 0 ? a : fmaxf(best, a);
         }
-        if (team.thread_rank() == 0) occs[v] = best;
+        if (team.thread_rank() == 0) {
+            if (ema) { best = fmaxf(ema[v] * decay, best); ema[v] = best; }
+            occs[v] = best;
+        }
     }
     if (team.thread_rank() == 0 && nq) atomicAdd(&counters[IA_CNT_QUERIES], nq);
     if (nfetch) atomicAdd(&counters[IA_CNT_BROYDEN_FETCH], nfetch);
@@ -737,24 +744,24 @@ static int ia_occ_alloc(ia_ctx* c, int res) {
     return IA_OK;
 }
 
-extern "C" int ia_build_occupancy(ia_ctx* c, const float* aabb, int res, const float* d_jitter, uint8_t* d_bin_out,
-                                  void* stream) {
-    IA_REQUIRE(c && aabb && d_jitter, IA_EINVAL, "ia_build_occupancy: NULL argument");
-    IA_REQUIRE(c->have_pose && c->have_fields && c->have_cfg, IA_ESTATE, "ia_build_occupancy: fields/pose/config not set");
-    IA_CHECK_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = (cudaStream_t)stream;
+static int ia_occupancy_pipeline(ia_ctx* c, const float* aabb, int res, const float* d_jitter, float* d_ema, float decay,
+                                 float occ_thre, uint8_t* d_bin_out, cudaStream_t st) {
     if (int e = ia_occ_alloc(c, res)) return e;
     for (int i = 0; i < 6; i++) c->f.aabb[i] = aabb[i];
     int nvox = res * res * res;
     size_t sm = IA_GEO_END * sizeof(float);
     IA_STAGE_BEGIN(c, IA_STAGE_OCCUPANCY, st);
-    k_occ_eval<<<c->n_sm * 8, 256, sm, st>>>(c->f, res, aabb[0], aabb[1], aabb[2], aabb[3] - aabb[0], aabb[4] - aabb[1],
-                                             aabb[5] - aabb[2], d_jitter, c->d_occ_a, c->d_counters);
+    if (d_ema)
+        k_occ_eval<1><<<c->n_sm * 8, 256, sm, st>>>(c->f, res, aabb[0], aabb[1], aabb[2], aabb[3] - aabb[0], aabb[4] - aabb[1],
+                                                    aabb[5] - aabb[2], d_jitter, c->d_occ_a, c->d_counters, d_ema, decay);
+    else
+        k_occ_eval<3><<<c->n_sm * 8, 256, sm, st>>>(c->f, res, aabb[0], aabb[1], aabb[2], aabb[3] - aabb[0], aabb[4] - aabb[1],
+                                                    aabb[5] - aabb[2], d_jitter, c->d_occ_a, c->d_counters);
     IA_LAUNCH_CHECK();
     IA_CHECK_CUDA(cudaMemsetAsync(c->d_occ_sum, 0, sizeof(double), st));
     int nb = (nvox + 255) / 256;
     k_occ_maxpool<<<nb, 256, 0, st>>>(c->d_occ_a, c->d_occ_b, res, c->d_occ_sum);
-    k_occ_thresh<<<nb, 256, 0, st>>>(c->d_occ_b, c->d_occ_a, nvox, c->d_occ_sum, c->occ_thre);
+    k_occ_thresh<<<nb, 256, 0, st>>>(c->d_occ_b, c->d_occ_a, nvox, c->d_occ_sum, occ_thre);
     float *a = c->d_occ_a, *b = c->d_occ_b;
     for (int it = 0; it < res * 3; it++) {
         k_cc_iter<<<nb, 256, 0, st>>>(a, b, res);
@@ -768,6 +775,23 @@ extern "C" int ia_build_occupancy(ia_ctx* c, const float* aabb, int res, const f
     IA_LAUNCH_CHECK();
     c->have_occ = true;
     return IA_OK;
+}
+
+extern "C" int ia_build_occupancy(ia_ctx* c, const float* aabb, int res, const float* d_jitter, uint8_t* d_bin_out,
+                                  void* stream) {
+    IA_REQUIRE(c && aabb && d_jitter, IA_EINVAL, "ia_build_occupancy: NULL argument");
+    IA_REQUIRE(c->have_pose && c->have_fields && c->have_cfg, IA_ESTATE, "ia_build_occupancy: fields/pose/config not set");
+    IA_CHECK_CUDA(cudaSetDevice(c->device));
+    return ia_occupancy_pipeline(c, aabb, res, d_jitter, nullptr, 0.f, c->occ_thre, d_bin_out, (cudaStream_t)stream);
+}
+
+extern "C" int ia_update_occupancy_ema(ia_ctx* c, const float* aabb, int res, const float* d_jitter, float* d_occs,
+                                       float ema_decay, float occ_thre, uint8_t* d_bin_out, void* stream) {
+    IA_REQUIRE(c && aabb && d_jitter && d_occs, IA_EINVAL, "ia_update_occupancy_ema: NULL argument");
+    IA_REQUIRE(c->have_pose && c->have_fields && c->have_cfg, IA_ESTATE, "ia_update_occupancy_ema: fields/pose/config not set");
+    IA_REQUIRE(ema_decay >= 0.f && ema_decay <= 1.f && occ_thre > 0.f, IA_EINVAL, "ia_update_occupancy_ema: bad decay / threshold");
+    IA_CHECK_CUDA(cudaSetDevice(c->device));
+    return ia_occupancy_pipeline(c, aabb, res, d_jitter, d_occs, ema_decay, occ_thre, d_bin_out, (cudaStream_t)stream);
 }
 
 extern "C" int ia_set_occupancy(ia_ctx* c, const float* aabb, int res, const uint8_t* d_bin, void* stream) {

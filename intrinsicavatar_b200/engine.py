@@ -49,6 +49,7 @@ _ARGTYPES = {
     "ia_op_env": [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
     "ia_make_rays": [_vp, _vp, _vp, _vp, _i32, _i32, _cf32, _cf32, _vp, _vp],
     "ia_pack_rgb8": [_vp, _vp, _i64, _i32, _cf32, _cf32, _i32, _vp, _vp],
+    "ia_update_occupancy_ema": [_vp, _vp, _i32, _vp, _vp, _cf32, _cf32, _vp, _vp],
     "ia_pack_grid8": [_vp, _vp, _i32, _i32, _i32, _i32, _cf32, _cf32, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
 }
 
@@ -199,6 +200,19 @@ class RenderEngine:
         out = torch.empty(res ** 3, dtype=torch.uint8, device=self.dev) if return_grid else None
         check(self.lib.ia_build_occupancy(self.h, fptr(_f32(aabb).reshape(6)), res, ptr(j), ptr(out), _stream()),
               "ia_build_occupancy")
+        self._keep["jitter"] = j
+        return out.bool().reshape(res, res, res) if return_grid else None
+
+    def update_occupancy_ema(self, aabb, jitter, occs, res=64, ema_decay=0.8, occ_thre=0.001, return_grid=False):
+        """Training-time grid update (OccGridEstimator._update): ``occs`` [res^3] float CUDA tensor, the EMA state of the
+        frame's level, updated IN PLACE; jitter [res^3, 3]."""
+        j = torch.as_tensor(jitter, dtype=torch.float32).to(self.dev).contiguous()
+        if j.numel() != res ** 3 * 3 or not (occs.is_cuda and occs.is_contiguous() and occs.dtype == torch.float32
+                                            and occs.numel() == res ** 3):
+            raise ValueError("update_occupancy_ema: jitter [res^3, 3] and a contiguous float32 CUDA occs [res^3] are required")
+        out = torch.empty(res ** 3, dtype=torch.uint8, device=self.dev) if return_grid else None
+        check(self.lib.ia_update_occupancy_ema(self.h, fptr(_f32(aabb).reshape(6)), res, ptr(j), ptr(occs), float(ema_decay),
+                                               float(occ_thre), ptr(out), _stream()), "ia_update_occupancy_ema")
         self._keep["jitter"] = j
         return out.bool().reshape(res, res, res) if return_grid else None
 

@@ -35,6 +35,26 @@ def _normalize(v, eps=1e-6):
     return F.normalize(v, p=2, dim=-1, eps=eps)
 
 
+def occupancy_ema_step(occs, occ, ema_decay, occ_thre, R):
+    """The grid logic of OccGridEstimator._update (models/occ_grid/temporal_occ_grid.py:392-411): EMA with max, 3^3 max-pool,
+    threshold min(mean, occ_thre), largest connected component (models/utils.py:152-163).  Pinned to the reference's own
+    class by tests/golden/reference_vectors_occ_ema.npz.  Returns (new occs [R^3], binaries [R,R,R])."""
+    occs = torch.maximum(torch.as_tensor(occs, dtype=torch.float32).reshape(-1) * ema_decay,
+                         torch.as_tensor(occ, dtype=torch.float32).reshape(-1))
+    occs_ = F.max_pool3d(occs.reshape(1, 1, R, R, R), kernel_size=3, stride=1, padding=1)[0, 0].reshape(-1)
+    thre = torch.clamp(occs_[occs_ >= 0].mean(), max=occ_thre)
+    binaries = (occs_ > thre).reshape(1, R, R, R)
+    comp = torch.arange(1, R ** 3 + 1).reshape(1, 1, R, R, R).float()
+    grid = binaries[None]
+    comp[~grid] = 0
+    for _ in range(R * 3):
+        comp = F.max_pool3d(comp, kernel_size=3, stride=1, padding=1)
+        comp *= grid
+    mcc = comp[0, 0]
+    label = torch.mode(mcc[binaries[0]], 0).values
+    return occs, (mcc == label).reshape(R, R, R)
+
+
 class OracleRenderer:
     def __init__(self, fields, lbs_voxel, offset_kernel, scale_kernel, *, samples_per_pixel=4,
                  global_illumination=False, num_samples_per_ray=128, num_samples_per_secondary_ray=64,
@@ -106,6 +126,19 @@ class OracleRenderer:
         self.grid_aabb = aabb
         self.occs = occs
         return self.binaries
+
+    def update_occupancy_ema(self, aabb, jitter, occs, ema_decay=0.8, occ_thre=0.001):
+        """OccGridEstimator._update for one level (models/occ_grid/temporal_occ_grid.py:369-411) with the occ_eval_fn of
+        IntrinsicAvatarModel.update_step (models/intrinsic_avatar.py:243-254): one jittered point per cell, EMA with max,
+        max-pool, threshold, largest component.  Returns (new occs [R^3], binaries [R,R,R])."""
+        R = self.grid_res
+        aabb = torch.as_tensor(aabb, dtype=torch.float32).reshape(6)
+        ar = torch.arange(R)
+        coords = torch.stack(torch.meshgrid(ar, ar, ar, indexing="ij"), -1).reshape(-1, 3).float()
+        x = (coords + torch.as_tensor(jitter, dtype=torch.float32).reshape(-1, 3)) / R
+        x = x * (aabb[3:] - aabb[:3]) + aabb[:3]
+        occ = self.fields.alpha_from_sdf(self._deform(x)["sdf"], self.render_step_size).reshape(-1)
+        return occupancy_ema_step(occs, occ, ema_decay, occ_thre, R)
 
     def set_light(self, envmap, u1, u2):
         self.env = EnvLight(torch.as_tensor(envmap, dtype=torch.float32))

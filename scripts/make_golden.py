@@ -744,8 +744,49 @@ def main_saver():
     print("wrote", out, grid.shape, grid.dtype)
 
 
+def main_occ_ema():
+    """The training-time occupancy update as the reference's own TemporalOccGridEstimator._update runs it
+    (models/occ_grid/temporal_occ_grid.py:369-411): two successive updates of a 16^3 level with a synthetic occupancy
+    function (the grid logic is what is pinned: one jittered point per cell, EMA with max, max-pool, threshold
+    min(mean, occ_thre), largest connected component) -> tests/golden/reference_vectors_occ_ema.npz."""
+    install_stubs()
+    sys.modules["nerfacc"].traverse_grids = None
+    sys.modules["nerfacc"].render_visibility_from_alpha = None
+    sys.modules["nerfacc"].render_visibility_from_density = None
+    _pkg("models.occ_grid", os.path.join(REF, "models", "occ_grid"))
+    from models.occ_grid.temporal_occ_grid import TemporalOccGridEstimator
+    R = 16
+    aabb = torch.tensor([[-0.9, -1.1, -0.4, 0.8, 0.7, 0.5]])
+    est = TemporalOccGridEstimator(roi_aabb=aabb, resolution=R, levels=1)
+
+    def occ_fn(x):     # two blobs (the smaller one must be dropped by the connected-component step) with smooth fall-off
+        a = torch.exp(-((x - torch.tensor([0.0, -0.2, 0.0])) ** 2).sum(-1) / 0.08)
+        b = 0.6 * torch.exp(-((x - torch.tensor([0.55, 0.45, 0.3])) ** 2).sum(-1) / 0.004)
+        return (a + b).clamp(max=1.0)[:, None] * 0.05
+    out = {"aabb": aabb[0].numpy(), "res": np.int32(R)}
+    for k, (seed, decay, thre) in enumerate(((3, 0.8, 0.001), (4, 0.8, 0.001), (5, 0.95, 0.01))):
+        torch.manual_seed(seed)
+        jitter = torch.rand(R ** 3, 3)
+        x = (est.grid_coords + jitter) / est.resolution
+        x = est.aabbs[0, :3] + x * (est.aabbs[0, 3:] - est.aabbs[0, :3])
+        out[f"occ_in_{k}"] = occ_fn(x)[:, 0].numpy()
+        out[f"state_in_{k}"] = est.occs.clone().numpy()
+        torch.manual_seed(seed)                  # _update draws torch.rand_like(grid_coords): the same numbers
+        est._update(step=0, t_idx=0, occ_eval_fn=occ_fn, occ_thre=thre, ema_decay=decay)
+        out[f"jitter_{k}"] = jitter.numpy()
+        out[f"state_out_{k}"] = est.occs.clone().numpy()
+        out[f"binaries_{k}"] = est.binaries[0].clone().numpy()
+        out[f"params_{k}"] = np.array([decay, thre], np.float32)
+        print(k, "occupied", int(est.binaries.sum()))
+    path = os.path.join(ROOT, "tests", "golden", "reference_vectors_occ_ema.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "saver":
+    if len(sys.argv) > 1 and sys.argv[1] == "occ_ema":
+        main_occ_ema()
+    elif len(sys.argv) > 1 and sys.argv[1] == "saver":
         main_saver()
     elif len(sys.argv) > 1 and sys.argv[1] == "e2e":
         main_e2e()

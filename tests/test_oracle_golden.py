@@ -396,3 +396,18 @@ def test_e2e_golden_is_what_the_reference_produces(scene):
     assert res.returncode == 0, res.stderr[-2000:]
     worst = float([l for l in res.stdout.splitlines() if l.startswith("WORST")][-1].split()[1])
     assert worst < 1e-6, worst
+
+
+def test_occupancy_ema_step_vs_reference_estimator():
+    """oracle.render.occupancy_ema_step against the reference's own TemporalOccGridEstimator._update
+    (models/occ_grid/temporal_occ_grid.py:369-411; scripts/make_golden.py occ_ema): three successive updates of one level,
+    two decay / threshold settings; the second blob of the synthetic field must fall to the connected-component step."""
+    from oracle.render import occupancy_ema_step
+    z = np.load(os.path.join(os.path.dirname(GOLD), "reference_vectors_occ_ema.npz"))
+    R = int(z["res"])
+    for k in range(3):
+        decay, thre = (float(v) for v in z[f"params_{k}"])
+        occs, binaries = occupancy_ema_step(z[f"state_in_{k}"], z[f"occ_in_{k}"], decay, thre, R)
+        assert np.array_equal(occs.numpy(), z[f"state_out_{k}"])
+        assert np.array_equal(binaries.numpy(), z[f"binaries_{k}"])
+        assert 0 < binaries.sum() < R ** 3
