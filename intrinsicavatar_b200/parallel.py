@@ -151,12 +151,18 @@ class FrameCollector:
         elif self.transport == "p2p":
             self.peer[slot, self.rank].copy_(block, non_blocking=True)     # stream-ordered peer copy, no SM
         else:
+            # a slot is reused only after the gather that filled it last has completed (NCCL orders collectives on its
+            # stream, gloo runs asynchronous work on a thread pool and may finish two gathers into one slot in either order)
+            for s_, _, w_ in self.pending:
+                if s_ == slot:
+                    w_.wait()
+            self.pending = [e for e in self.pending if e[0] != slot]
             bufs = [self.recv[slot, r] for r in range(self.ws)] if self.rank == self.dst else None
             work = dist.gather(block, gather_list=bufs, dst=self.dst, async_op=True)
-            self.pending.append((block, work))
+            self.pending.append((slot, block, work))
 
     def finish(self):
-        for _, work in self.pending:
+        for _, _, work in self.pending:
             work.wait()
         self.pending.clear()
         if torch.device(self.device).type == "cuda":
