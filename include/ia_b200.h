@@ -241,6 +241,15 @@ int ia_op_query(ia_ctx* ctx, const float* d_xd, int64_t n, int with_grad, float*
 int ia_op_geometry_backward(ia_ctx* ctx, const float* d_xc, const float* d_dout, int64_t n, float* d_g_hash, float* d_g_mlp,
                             float* d_g_x, void* stream);
 
+/* Training-mode building block: backward of the implicit-differentiation correction of the Broyden roots,
+ * ForwardDeformer.forward version 1 (models/deformers/fast_snarf/deformer_torch.py:57-76; forward_skinning / skinning_mask
+ * :127-137, 213-227; query_weights :199-210) -- the reference builds  x_c = x_c* - J_inv (x_d(x_c*) - x_d(x_c*).detach())  and
+ * lets autograd carry dL/dx_c to the bone transforms.  Inputs as ia_op_broyden returns them: d_xc [n,13,3] roots, d_valid [n,13]
+ * (after filter), d_J_inv [n,13,3,3]; d_g_xc [n,13,3] upstream gradient (ia_op_geometry_backward's d_g_x of the valid roots).
+ * ADDS into d_g_tfs [24][3][4]: the gradient with respect to rows 0..2 of the 24 bone transforms set by ia_set_pose.       */
+int ia_op_deform_backward(ia_ctx* ctx, const float* d_xc, const uint8_t* d_valid, const float* d_J_inv, const float* d_g_xc,
+                          int64_t n, float* d_g_tfs, void* stream);
+
 /* Canonical SDF of n points, evaluated the way the wavefront integrator's geometry phase does: hash grid, then the
  * 35 -> 64 layer as warp-level tensor-core mma (TF32 inputs split in two, fp32 accumulate), softplus(beta = 100), sdf row
  * of the output layer.  Replaces VolumeSDF.forward without gradient (models/rf/geometry.py:124-146: encoding ->

@@ -1090,4 +1090,17 @@ extern "C" int ia_op_geometry_backward(ia_ctx* c, const float* d_xc, const float
     return IA_OK;
 }
 
+extern "C" int ia_op_deform_backward(ia_ctx* c, const float* d_xc, const uint8_t* d_valid, const float* d_J_inv,
+                                     const float* d_g_xc, int64_t n, float* d_g_tfs, void* stream) {
+    IA_REQUIRE(c && d_g_tfs && n >= 0, IA_EINVAL, "ia_op_deform_backward: NULL argument");
+    IA_REQUIRE(c->have_lbs && c->have_pose, IA_ESTATE, "ia_op_deform_backward: call ia_set_lbs_voxels and ia_set_pose first");
+    if (n == 0) return IA_OK;     // (an empty batch has no buffers)
+    IA_REQUIRE(d_xc && d_valid && d_J_inv && d_g_xc, IA_EINVAL, "ia_op_deform_backward: NULL argument");
+    IA_CHECK_CUDA(cudaSetDevice(c->device));
+    k_deform_backward<<<ia_query_blocks(c, n * IA_N_INIT), 256, 0, (cudaStream_t)stream>>>(c->f, d_xc, d_valid, d_J_inv, d_g_xc,
+                                                                                         n * IA_N_INIT, d_g_tfs);
+    IA_LAUNCH_CHECK();
+    return IA_OK;
+}
+
 #include "ia_render.cuh"

@@ -145,3 +145,78 @@ __global__ void __launch_bounds__(256) k_geometry_backward(const __grid_constant
     for (int i = threadIdx.x; i < IA_GEO_END; i += blockDim.x)
         if (gw[i] != 0.f) atomicAdd(&g_mlp[i], gw[i]);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Training-mode building block: backward of the implicit-differentiation correction of the Broyden roots
+// (ForwardDeformer.forward, version 1, models/deformers/fast_snarf/deformer_torch.py:57-76):
+//   x_c = x_c* - J_inv (x_d(x_c*) - stopgrad(x_d(x_c*))),   x_d(x_c*) = sum_j w_j(x_c*) T_j [x_c*, 1]     (skinning_mask, :213-227)
+// The roots x_c* and the skinning weights w_j(x_c*) (trilinear fetch of the fixed weight voxels, border padding, :199-210) are
+// constants of the graph; the value of x_c is the root, and its only gradient path leads to the bone transforms:
+//   u = -J_inv^T g_xc,      dL/dT_j[r][k] += w_j(x_c*) u[r] [x_c*, 1][k]        (r < 3, k < 4)
+// One 16-lane team per (point, init bone) root: lane = corner (lane & 7) x channel half (lane >> 3), like ia_team_fwd_rotation;
+// the 24 x 12 sums accumulate in shared memory per CTA and are flushed once.
+__global__ void __launch_bounds__(256) k_deform_backward(const __grid_constant__ IaFrame p, const float* __restrict__ xc,
+                                                         const uint8_t* __restrict__ valid, const float* __restrict__ J_inv,
+                                                         const float* __restrict__ g_xc, long long n_roots,
+                                                         float* __restrict__ g_tfs) {
+    __shared__ float gt[IA_N_BONES * 12];
+    for (int i = threadIdx.x; i < IA_N_BONES * 12; i += blockDim.x) gt[i] = 0.f;
+    __syncthreads();
+    Team team = cg::tiled_partition<IA_TEAM>(cg::this_thread_block());
+    const int lane = team.thread_rank();
+    const long long teams = (long long)gridDim.x * (blockDim.x / IA_TEAM);
+    const int W = p.W, H = p.H, D = p.D;
+    for (long long i = (long long)blockIdx.x * (blockDim.x / IA_TEAM) + threadIdx.x / IA_TEAM; i < n_roots; i += teams) {
+        if (!valid[i]) continue;
+        const float x[4] = {xc[i * 3], xc[i * 3 + 1], xc[i * 3 + 2], 1.0f};
+        const float* Ji = J_inv + i * 9;
+        const float g0 = g_xc[i * 3], g1 = g_xc[i * 3 + 1], g2 = g_xc[i * 3 + 2];
+        float u[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) u[r] = -(Ji[r] * g0 + Ji[3 + r] * g1 + Ji[6 + r] * g2);
+        // skinning weights at the root: this lane's corner, its 12 channels
+        float ix = ((p.scl[0] * (x[0] + p.off[0]) + 1.f) / 2) * (W - 1);
+        float iy = ((p.scl[1] * (x[1] + p.off[1]) + 1.f) / 2) * (H - 1);
+        float iz = ((p.scl[2] * (x[2] + p.off[2]) + 1.f) / 2) * (D - 1);
+        ix = fminf(fmaxf(ix, 0.f), (float)(W - 1));
+        iy = fminf(fmaxf(iy, 0.f), (float)(H - 1));
+        iz = fminf(fmaxf(iz, 0.f), (float)(D - 1));
+        const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+        const int c = lane & 7, half = lane >> 3;
+        const int xi = (int)fx + (c & 1), yi = (int)fy + ((c >> 1) & 1), zi = (int)fz + (c >> 2);
+        const float wt = ((c & 1) ? ix - fx : 1.f - (ix - fx)) * ((c & 2) ? iy - fy : 1.f - (iy - fy)) *
+                         ((c & 4) ? iz - fz : 1.f - (iz - fz));
+        float w[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) w[k] = 0.f;
+        if (xi < W && yi < H && zi < D) {   // after clamping, an out-of-range corner has weight 0
+            const float4* v = p.lbs_w + ((size_t)((zi * H + yi) * W + xi)) * 6 + half * 3;
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const float4 a = __ldg(v + q);
+                w[q * 4] = a.x * wt; w[q * 4 + 1] = a.y * wt; w[q * 4 + 2] = a.z * wt; w[q * 4 + 3] = a.w * wt;
+            }
+        }
+        // sum over the 8 corners (lanes of one half)
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            w[k] += team.shfl_xor(w[k], 1);
+            w[k] += team.shfl_xor(w[k], 2);
+            w[k] += team.shfl_xor(w[k], 4);
+        }
+        if (c == 0) {
+#pragma unroll
+            for (int k = 0; k < 12; k++) {
+                if (w[k] == 0.f) continue;
+                float* dst = gt + (half * 12 + k) * 12;
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) atomicAdd(dst + r * 4 + e, w[k] * u[r] * x[e]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < IA_N_BONES * 12; i += blockDim.x)
+        if (gt[i] != 0.f) atomicAdd(&g_tfs[i], gt[i]);
+}

@@ -239,6 +239,12 @@ __device__ __forceinline__ int wf_grab(WfShared& S, int n_tasks) {
     return t < n_tasks ? t : -1;
 }
 
+// Broyden chains are taken by all lanes of the CTA from ONE list (bone-major, Morton-ordered queries).  Per-warp stretches of
+// the list (a warp's chains stay spatial neighbours, other warps' stretches are taken when its own is exhausted) were measured
+// at 512^2 x 1024 spp, GI on, frames 2 / 13 / 1: shade 755.0 -> 789.5 ms -- sixteen warps in sixteen places of the voxel grid
+// share less of the L1 than sixteen warps sweeping one window of the list together.
+__device__ __forceinline__ int wf_grab_chain(WfShared& S) { return wf_grab(S, S.n_btask); }
+
 // A phase counts its work in a register and adds it to the CTA's counters when it ends (the counters do not live in
 // registers across phases: seven of them cost the Broyden loop spills at the 128-register cap).
 __device__ __forceinline__ void wf_count(WfShared& S, int which, unsigned v) {
@@ -257,36 +263,59 @@ __device__ __forceinline__ unsigned wf_morton7(unsigned v) {   // 7 bits -> ever
     v = (v | (v << 2)) & 0x00049249u;
     return v;
 }
-__device__ __forceinline__ void wf_sort_phase(const IaFrame& p, WfShared& S, int n_q) {
-    for (int i = threadIdx.x; i < WF_R; i += blockDim.x) {
-        unsigned key = 0xffffffffu;
-        if (i < n_q) {
-            const int q = S.qlist[i];
-            unsigned m = 0;
+__device__ __forceinline__ unsigned wf_morton_key(const IaFrame& p, const WfShared& S, int q) {
+    unsigned m = 0;
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const float u = (S.qx[k][q] - p.aabb[k]) / (p.aabb[3 + k] - p.aabb[k]);
-                const unsigned c = (unsigned)fminf(fmaxf(u * 128.0f, 0.f), 127.f);
-                m |= wf_morton7(c) << k;
-            }
-            key = (m << 10) | (unsigned)q;
-        }
-        S.sortk[i] = key;
+    for (int k = 0; k < 3; k++) {
+        const float u = (S.qx[k][q] - p.aabb[k]) / (p.aabb[3 + k] - p.aabb[k]);
+        const unsigned c = (unsigned)fminf(fmaxf(u * 128.0f, 0.f), 127.f);
+        m |= wf_morton7(c) << k;
     }
-    for (int k = 2; k <= WF_R; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
+    return m;
+}
+// Bitonic network with the sub-steps of distance <= 32 in registers: a warp owns 64 consecutive keys (lane: keys lane and
+// lane + 32 of its block), distance 32 is a compare of the thread's own two keys, distances 16 .. 1 are shuffles; only the
+// distances >= 64 go through shared memory (10 of the 55 sub-steps, 14 barriers).  Measured at 512^2 x 1024 spp, GI on,
+// frames 2 / 13 / 1 together with WF_FILTER_PRELOAD: shade 765.0 -> 755.2 ms against all 55 sub-steps through shared memory.
+// A counting sort on the top 10 bits of the key (4 barriers, arbitrary order inside a bucket) LOST 2.5 % (784.2 ms): the
+// gathers of the following phases live on the full order.
+__device__ __forceinline__ void wf_cx(unsigned& a, unsigned& b, bool up) {
+    if ((a > b) == up) { const unsigned t = a; a = b; b = t; }
+}
+__device__ __forceinline__ void wf_sort_warp_steps(unsigned& a, unsigned& b, int ia, int k, int j_from) {
+    const int lane = threadIdx.x & 31;
+    if (j_from >= 32) wf_cx(a, b, (ia & k) == 0);
+    for (int j = j_from >= 32 ? 16 : j_from; j > 0; j >>= 1) {
+        const unsigned oa = __shfl_xor_sync(0xffffffffu, a, j), ob = __shfl_xor_sync(0xffffffffu, b, j);
+        const bool lower = (lane & j) == 0;
+        const bool upa = (ia & k) == 0, upb = ((ia + 32) & k) == 0;
+        a = (lower == upa) ? min(a, oa) : max(a, oa);
+        b = (lower == upb) ? min(b, ob) : max(b, ob);
+    }
+}
+__device__ __forceinline__ void wf_sort_phase(const IaFrame& p, WfShared& S, int n_q) {
+    static_assert(WF_R == 2 * WF_THREADS, "WF_QSORT: two keys per thread");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ia = warp * 64 + lane, ib = ia + 32;
+    unsigned a = 0xffffffffu, b = 0xffffffffu;
+    if (ia < n_q) { const int q = S.qlist[ia]; a = (wf_morton_key(p, S, q) << 10) | (unsigned)q; }
+    if (ib < n_q) { const int q = S.qlist[ib]; b = (wf_morton_key(p, S, q) << 10) | (unsigned)q; }
+    for (int k = 2; k <= 64; k <<= 1) wf_sort_warp_steps(a, b, ia, k, k >> 1);
+    for (int k = 128; k <= WF_R; k <<= 1) {
+        S.sortk[ia] = a; S.sortk[ib] = b;
+        for (int j = k >> 1; j >= 64; j >>= 1) {
             __syncthreads();
-            for (int t = threadIdx.x; t < WF_R / 2; t += blockDim.x) {
-                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int hi = lo | j;
-                const unsigned a = S.sortk[lo], b = S.sortk[hi];
-                const bool up = (lo & k) == 0;
-                if ((a > b) == up) { S.sortk[lo] = b; S.sortk[hi] = a; }
-            }
+            const int lo = ((tid & ~(j - 1)) << 1) | (tid & (j - 1));
+            const int hi = lo | j;
+            const unsigned x = S.sortk[lo], y = S.sortk[hi];
+            if ((x > y) == ((lo & k) == 0)) { S.sortk[lo] = y; S.sortk[hi] = x; }
         }
+        __syncthreads();
+        a = S.sortk[ia]; b = S.sortk[ib];
+        wf_sort_warp_steps(a, b, ia, k, 32);
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < n_q; i += blockDim.x) S.qlist[i] = (unsigned short)(S.sortk[i] & 1023u);
+    if (ia < n_q) S.qlist[ia] = (unsigned short)(a & 1023u);
+    if (ib < n_q) S.qlist[ib] = (unsigned short)(b & 1023u);
 }
 #endif
 
@@ -347,7 +376,7 @@ __device__ __forceinline__ void wf_broyden_phase(const IaFrame& p, WfShared& S) 
     const int FRESH = 1 << 20;
     int st;
     {
-        const int t = wf_grab(S, S.n_btask);
+        const int t = wf_grab_chain(S);
         st = t >= 0 ? ((int)S.btask[t] | FRESH) : -1;
     }
     float x0 = 0, x1 = 0, x2 = 0, xd0 = 0, xd1 = 0, xd2 = 0, g0 = 0, g1 = 0, g2 = 0;
@@ -418,7 +447,7 @@ __device__ __forceinline__ void wf_broyden_phase(const IaFrame& p, WfShared& S) 
                 // voxel fetches of this chain: the initial one + one per later trip (`it` counts the rank-1 updates).
                 // Counted here, at the chain's end, so that no counter lives in a register across the loop.
                 atomicAdd(&S.cnt[WF_C_FETCH], 1u + (it >= 10 ? 10u : (unsigned)it + 1u));
-                const int t = wf_grab(S, S.n_btask);
+                const int t = wf_grab_chain(S);
                 st = t >= 0 ? ((int)S.btask[t] | FRESH) : -1;
             }
         }
@@ -426,12 +455,40 @@ __device__ __forceinline__ void wf_broyden_phase(const IaFrame& p, WfShared& S) 
 }
 
 // filter.cu:10-54 per pending query, then the list of geometry tasks
+#ifndef WF_FILTER_PRELOAD
+#define WF_FILTER_PRELOAD 1   // 1: a query with two or more roots loads all of them at once (independent loads from the CTA's
+#endif                        // global scratch, one L2 round trip) and compares in registers; 0: the reference's nested loops,
+                              // one dependent round trip per compared pair while the rest of the warp waits
 __device__ __forceinline__ void wf_filter_phase(WfShared& S, int n_q) {
-    for (int k = threadIdx.x; k < n_q; k += blockDim.x) {
-        const int q = S.qlist[k];
-        const unsigned mask = S.qmask[q];
+    for (int k0 = 0; k0 < n_q; k0 += blockDim.x) {
+        const int k = k0 + threadIdx.x;
+        const bool act = k < n_q;
+        const int q = act ? S.qlist[k] : 0;
+        const unsigned mask = act ? S.qmask[q] : 0u;
         unsigned keep = mask;
         const float* cd = S.cand + q * IA_N_INIT * 3;
+#if WF_FILTER_PRELOAD
+        if (mask & (mask - 1u)) {
+            float c0[IA_N_INIT], c1[IA_N_INIT], c2[IA_N_INIT];
+#pragma unroll
+            for (int i = 0; i < IA_N_INIT; i++) {
+                const bool v = (mask >> i) & 1u;
+                c0[i] = v ? cd[i * 3] : 0.f; c1[i] = v ? cd[i * 3 + 1] : 0.f; c2[i] = v ? cd[i * 3 + 2] : 0.f;
+            }
+            // root i goes when a LATER valid root lies within 1e-4 of it
+#pragma unroll
+            for (int i = 0; i < IA_N_INIT - 1; i++) {
+                bool dup = false;
+#pragma unroll
+                for (int j = i + 1; j < IA_N_INIT; j++) {
+                    const float e0 = c0[i] - c0[j], e1 = c1[i] - c1[j], e2 = c2[i] - c2[j];
+                    dup = dup || (((mask >> j) & 1u) && e0 * e0 + e1 * e1 + e2 * e2 < 0.0001f * 0.0001f);
+                }
+                if (dup) keep &= ~(1u << i);
+            }
+            keep &= mask;
+        }
+#else
         unsigned mi = mask;
         while (mi) {
             int i = __ffs(mi) - 1;
@@ -444,16 +501,26 @@ __device__ __forceinline__ void wf_filter_phase(WfShared& S, int n_q) {
                 if (e0 * e0 + e1 * e1 + e2 * e2 < 0.0001f * 0.0001f) { keep &= ~(1u << i); break; }
             }
         }
-        S.qmask[q] = keep;
-        int n = __popc(keep);
-        if (n) {
-            int base = atomicAdd(&S.n_gtask, n);
-            unsigned m = keep;
-            while (m) {
-                int c = __ffs(m) - 1;
-                m &= m - 1;
-                S.gtask[base++] = (unsigned short)(q * 16 + c);
-            }
+#endif
+        if (act) S.qmask[q] = keep;
+        // the warp's kept roots go to ONE stretch of the task list, in query (Morton) order: one atomic per warp
+        const int lane = threadIdx.x & 31;
+        const int n = act ? __popc(keep) : 0;
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int base = 0;
+        if (lane == 0 && total) base = atomicAdd(&S.n_gtask, total);
+        base = __shfl_sync(0xffffffffu, base, 0) + incl - n;
+        unsigned m = keep;
+        while (m) {
+            int c = __ffs(m) - 1;
+            m &= m - 1;
+            S.gtask[base++] = (unsigned short)(q * 16 + c);
         }
     }
 }
@@ -521,13 +588,15 @@ __device__ __forceinline__ void wf_geometry_phase(const IaFrame& p, WfShared& S)
     unsigned c_geo = 0;
     const int n = S.n_gtask;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
-    // an even split of the task list over the warps (the gathers of step A are the cost, and they are per point)
+    // an even split of the task list over the warps (the gathers of step A are the cost, and they are per point).  Batches dealt
+    // round-robin instead (the sixteen warps walking the Morton-ordered list side by side) measured the same: 756.6 vs 754.9 ms.
     const int per = (n + n_warps - 1) / n_warps;
     const int end = min(n, (warp + 1) * per);
+    const int b_step = WF_MMA_ROWS;
+    int b0 = warp * per;
     float* xs = wf_xs(S) + warp * WF_MMA_ROWS * IA_GEO_LD;
     // software pipeline: the task ids and roots of the NEXT batch (two dependent L2 round trips: the lists were just
     // written by other warps) are fetched while the current one is evaluated
-    int b0 = warp * per;
     int ci = 0;
     float x0 = 0.f, x1 = 0.f, x2 = 0.f;
     if (b0 + lane < end && lane < WF_MMA_ROWS) {
@@ -538,7 +607,7 @@ __device__ __forceinline__ void wf_geometry_phase(const IaFrame& p, WfShared& S)
     }
     while (b0 < end) {
         const int nb = min(WF_MMA_ROWS, end - b0);
-        const int bn = b0 + WF_MMA_ROWS;
+        const int bn = b0 + b_step;
         int ci_n = 0;
         float y0 = 0.f, y1 = 0.f, y2 = 0.f;
         if (bn + lane < end && lane < WF_MMA_ROWS) {

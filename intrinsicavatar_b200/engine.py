@@ -37,6 +37,7 @@ _ARGTYPES = {
     "ia_op_shade_fields": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     "ia_op_geometry": [_vp, _vp, _i64, _vp, _vp],
     "ia_op_geometry_backward": [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
+    "ia_op_deform_backward": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "ia_op_traverse": [_vp, _vp, _vp, _i64, _cf32, _cf32, _cf32] + [_vp] * 9 + [_vp],
     "ia_op_ray_resampling": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp] + [_vp] * 6 + [_vp],
     "ia_op_ray_resampling_merge": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp] + [_vp] * 6 + [_vp],
@@ -429,6 +430,20 @@ class RenderEngine:
         w1t, b1 = g_mlp[:35 * 64].reshape(35, 64), g_mlp[35 * 64:36 * 64]
         w2, b2 = g_mlp[36 * 64:49 * 64].reshape(13, 64), g_mlp[49 * 64:49 * 64 + 13]
         return {"hash": g_hash, "w1": w1t.t().contiguous(), "b1": b1, "w2": w2, "b2": b2, "x": g_x}
+
+    def op_deform_backward(self, xc, valid, J_inv, g_xc):
+        """Gradient with respect to the bone transforms (rows 0..2, [24,3,4]) of  sum <g_xc, x_c>  through the implicit-
+        differentiation correction of the roots (ForwardDeformer.forward, training mode): inputs as ``op_broyden`` returns them."""
+        xc = xc.to(self.dev, torch.float32).reshape(-1, 13, 3).contiguous()
+        valid = valid.to(self.dev, torch.uint8).reshape(-1, 13).contiguous()
+        J_inv = J_inv.to(self.dev, torch.float32).reshape(-1, 13, 3, 3).contiguous()
+        g_xc = g_xc.to(self.dev, torch.float32).reshape(-1, 13, 3).contiguous()
+        n = xc.shape[0]
+        assert valid.shape[0] == n and J_inv.shape[0] == n and g_xc.shape[0] == n
+        g_tfs = torch.zeros(24, 3, 4, device=self.dev)
+        check(self.lib.ia_op_deform_backward(self.h, ptr(xc), ptr(valid), ptr(J_inv), ptr(g_xc), n, ptr(g_tfs), _stream()),
+              "ia_op_deform_backward")
+        return g_tfs
 
     def op_traverse(self, rays_o, rays_d, near, far, step):
         o = rays_o.to(self.dev, torch.float32).contiguous()

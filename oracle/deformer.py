@@ -131,6 +131,28 @@ def forward_rotation(xc: torch.Tensor, lbs_voxel: torch.Tensor, tfs: torch.Tenso
     return torch.einsum("pn,nij->pij", w, tfs)[:, :3, :3]
 
 
+def implicit_correction(xc_opt: torch.Tensor, valid: torch.Tensor, J_inv: torch.Tensor, lbs_voxel: torch.Tensor,
+                        tfs: torch.Tensor, offset, scale) -> torch.Tensor:
+    """Training-mode ``ForwardDeformer.forward`` (version 1, deformer_torch.py:57-76) after the search: the value is the root,
+    the gradient reaches ``tfs`` through  x_c = x_c* - J_inv (x_d(x_c*) - stopgrad(x_d(x_c*)))  with
+    x_d = skinning_mask(x_c*, w(x_c*), tfs) (:127-137, 199-227).  xc_opt [N,13,3], valid [N,13], J_inv [N,13,3,3],
+    tfs [24,4,4] (requires_grad) -> x_c [N,13,3]."""
+    xc_opt = xc_opt.detach().clone()
+    xc_opt[~valid] = 0
+    pts = xc_opt[valid]
+    g = scale[None] * (pts + offset[None])
+    w = F.grid_sample(lbs_voxel[None], g[None, :, None, None, :], align_corners=True, mode="bilinear",
+                      padding_mode="border")[0, :, :, 0, 0].t()      # [M,24]
+    w_tf = torch.einsum("pn,nij->pij", w, tfs)
+    x_h = F.pad(pts, (0, 1), value=1.0)
+    xd_opt = (w_tf * x_h[:, None, :]).sum(-1)[:, :3]
+    correction = xd_opt - xd_opt.detach()
+    correction = torch.einsum("pij,pj->pi", -J_inv[valid], correction)
+    xc = xc_opt.clone()
+    xc[valid] = xc[valid] + correction
+    return xc
+
+
 def deform(xd: torch.Tensor, fields, voxel_J, lbs_voxel, tfs, offset, scale, with_grad: bool):
     """SNARFDeformer.deform (snarf_deformer.py:187-261) with the dummy non-rigid deformer.
 

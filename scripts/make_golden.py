@@ -23,6 +23,8 @@ and, in tests/golden/reference_vectors_bsdf.npz (`make_golden.py bsdf`; the inte
   sphere     EnvironmentLightBase.sample_uniform_sphere_stratified(1, 16, 32), eval mode
                                                                   lib/torch_pbr/light.py:161-217
 and, in tests/golden/reference_vectors_voxel.npz (`make_golden.py voxel`):
+  deform_train  ForwardDeformer.forward, training mode (implicit-differentiation correction) + autograd to the bone transforms
+                                                                  models/deformers/fast_snarf/deformer_torch.py:57-76
   voxel      ForwardDeformer.switch_to_explicit + query_weights_smpl (skinning-weight voxel grid, offset / scale kernels)
                                                                   models/deformers/fast_snarf/deformer_torch.py:139-197, 234-253
 and, in tests/golden/reference_vectors_e2e.npz (`make_golden.py e2e`, through scripts/ref_harness.py):
@@ -331,6 +333,67 @@ def main_voxel():
     out = os.path.join(ROOT, "tests", "golden", "reference_vectors_voxel.npz")
     np.savez_compressed(out, **{k: (v.detach().cpu().numpy() if torch.is_tensor(v) else v) for k, v in g.items()})
     print("wrote", out, {k: tuple(np.shape(v)) for k, v in g.items()})
+
+
+def main_deform_train():
+    """The reference's own training-mode ForwardDeformer.forward (version 1: implicit-differentiation correction,
+    models/deformers/fast_snarf/deformer_torch.py:57-76, with forward_skinning / skinning_mask / query_weights :127-137,
+    199-227) and autograd through it, on the voxel grid of main_voxel.  Only ``search`` -- the CUDA Broyden kernel -- is
+    replaced: it returns prescribed roots, validity flags and inverse Jacobians, which is all the correction reads."""
+    install_stubs()
+    sys.path.insert(0, ROOT)
+    import torch.utils.cpp_extension as cpp
+    cpp.load = lambda *a, **k: types.SimpleNamespace()
+
+    def knn_points(x, y, K=1):
+        d2 = torch.cdist(x.double(), y.double()) ** 2
+        val, idx = torch.topk(d2, K, dim=-1, largest=False)
+        return val.to(x.dtype), idx, None
+    _pkg("lib", os.path.join(REF, "lib"))
+    _pkg("lib.pytorch3d", os.path.join(REF, "lib", "pytorch3d"))
+    _stub("lib.pytorch3d.ops", knn_points=knn_points)
+    sys.modules["lib.pytorch3d"].ops = sys.modules["lib.pytorch3d.ops"]
+    _pkg("models.deformers.fast_snarf", os.path.join(REF, "models", "deformers", "fast_snarf"))
+    from models.deformers.fast_snarf import deformer_torch as ref_def
+    from intrinsicavatar_b200.body import SyntheticBody, a_pose
+    body = SyntheticBody()
+    cano = body(body_pose=a_pose())
+    verts = torch.from_numpy(cano["vertices"])
+    weights = torch.from_numpy(body.lbs_weights)[None]
+    fd = ref_def.ForwardDeformer.__new__(ref_def.ForwardDeformer)
+    torch.nn.Module.__init__(fd)
+    fd.global_scale = 1.2
+    fd.version = 1
+    fd.device = torch.device("cpu")
+    fd.init_bones = [0, 1, 2, 4, 5, 10, 11, 12, 15, 16, 17, 18, 19]
+    fd.switch_to_explicit(resolution=32, smpl_verts=verts, smpl_weights=weights, use_smpl=True)
+    g = torch.Generator().manual_seed(21)
+    n = 300
+    bb = fd.bbox.reshape(2, 3) if torch.is_tensor(fd.bbox) else torch.as_tensor(np.asarray(fd.bbox), dtype=torch.float32).reshape(2, 3)
+    lo, hi = bb[0] - 0.1 * (bb[1] - bb[0]), bb[1] + 0.1 * (bb[1] - bb[0])      # some roots outside the grid: border padding
+    xc_opt = lo + torch.rand(1, n, 13, 3, generator=g) * (hi - lo)
+    valid = torch.rand(1, n, 13, generator=g) < 0.4
+    J_inv = torch.eye(3)[None, None, None] + 0.3 * torch.randn(1, n, 13, 3, 3, generator=g)
+    # 24 rigid-ish bone transforms
+    A = torch.randn(24, 3, 3, generator=g)
+    Q, _ = torch.linalg.qr(A)
+    tfs = torch.zeros(1, 24, 4, 4)
+    tfs[0, :, :3, :3] = Q
+    tfs[0, :, :3, 3] = 0.2 * torch.randn(24, 3, generator=g)
+    tfs[0, :, 3, 3] = 1.0
+    tfs.requires_grad_(True)
+    G = torch.randn(1, n, 13, 3, generator=g)
+    fd.search = lambda xd, cond, tfs_, eval_mode=False: (xc_opt.clone(), {"result": xc_opt.clone(), "valid_ids": valid.clone(),
+                                                                         "J_inv": J_inv.clone()})
+    xd = torch.zeros(1, n, 3)
+    xc, others = fd.forward(xd, None, tfs, eval_mode=False)
+    (xc * G).sum().backward()
+    out = dict(xc_opt=xc_opt[0], valid=valid[0], J_inv=J_inv[0], tfs=tfs.detach()[0], g_xc=G[0], xc=xc.detach()[0],
+               g_tfs=tfs.grad[0], fwd_tfs=others["fwd_tfs"].detach()[0])
+    path = os.path.join(ROOT, "tests", "golden", "reference_vectors_deform_train.npz")
+    np.savez_compressed(path, **{k: v.numpy() for k, v in out.items()})
+    print("wrote", path, {k: tuple(v.shape) for k, v in out.items()}, "valid roots", int(valid.sum()),
+          "|g_tfs|", float(tfs.grad.norm()))
 
 
 def main_fields():
@@ -802,6 +865,8 @@ if __name__ == "__main__":
         main_snarf()
     elif len(sys.argv) > 1 and sys.argv[1] == "voxel":
         main_voxel()
+    elif len(sys.argv) > 1 and sys.argv[1] == "deform_train":
+        main_deform_train()
     elif len(sys.argv) > 1 and sys.argv[1] == "smpl":
         main_smpl()
     elif len(sys.argv) > 1 and sys.argv[1] == "bsdf":

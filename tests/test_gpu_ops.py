@@ -622,6 +622,75 @@ def test_geometry_backward_vs_autograd(eng, scene):
     assert float((gx - grad).abs().max()) < 2e-4
 
 
+def test_deform_backward_vs_reference_golden():
+    """ia_op_deform_backward against the gradient the reference's own training-mode ForwardDeformer.forward + autograd
+    produced (tests/golden/reference_vectors_deform_train.npz: prescribed roots / flags / inverse Jacobians on the
+    resolution-32 weight voxels of reference_vectors_voxel.npz, some roots outside the grid -> border padding)."""
+    from intrinsicavatar_b200.engine import RenderEngine
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z = np.load(os.path.join(here, "reference_vectors_deform_train.npz"))
+    v = np.load(os.path.join(here, "reference_vectors_voxel.npz"))
+    e = RenderEngine()
+    e.set_lbs_voxels(v["voxel_lbs"], v["voxel_offset_kernel"], v["voxel_scale_kernel"])
+    e.set_pose(z["tfs"], np.eye(4, dtype=np.float32))
+    got = e.op_deform_backward(torch.from_numpy(z["xc_opt"]), torch.from_numpy(z["valid"]), torch.from_numpy(z["J_inv"]),
+                               torch.from_numpy(z["g_xc"])).cpu()
+    ref = torch.from_numpy(z["g_tfs"])[:, :3, :]
+    err = float(torch.linalg.norm(got - ref) / torch.linalg.norm(ref))
+    assert err < 1e-5, err
+    # ragged: no point at all, and a batch without a valid root
+    assert float(e.op_deform_backward(torch.zeros(0, 13, 3), torch.zeros(0, 13, dtype=torch.bool), torch.zeros(0, 13, 3, 3),
+                                      torch.zeros(0, 13, 3)).abs().max()) == 0.0
+    assert float(e.op_deform_backward(torch.from_numpy(z["xc_opt"]), torch.zeros(300, 13, dtype=torch.bool),
+                                      torch.from_numpy(z["J_inv"]), torch.from_numpy(z["g_xc"])).abs().max()) == 0.0
+
+
+def test_deform_backward_vs_autograd(eng, posed, scene):
+    """ia_op_deform_backward (training path) against torch autograd through the oracle's restatement of the
+    reference's implicit-differentiation trick (ForwardDeformer.forward version 1, deformer_torch.py:57-76): gradient of the
+    bone transforms for a random upstream gradient on every root, then chained behind ia_op_geometry_backward -- the whole
+    backward of  L = sum_i r_i sdf(x_c,i)  over the valid roots with respect to hash table, MLP weights and bone transforms."""
+    R = posed["oracle"]
+    xd = _points(posed, 6000, seed=4)
+    x, J, _, v = eng.op_broyden(xd)
+    assert int(v.sum()) > 1000
+    g = torch.Generator().manual_seed(8)
+    g_xc = torch.randn(xd.shape[0], 13, 3, generator=g)
+    got = eng.op_deform_backward(x, v, J, g_xc).cpu()
+    tfs = R.tfs.clone().requires_grad_(True)
+    xc = odef.implicit_correction(x.cpu(), v.cpu(), J.cpu(), R.lbs_voxel, tfs, R.offset, R.scale)
+    assert torch.equal(xc.detach()[v.cpu()], x.cpu()[v.cpu()])            # the value is the root
+    (xc * g_xc).sum().backward()
+    ref = tfs.grad[:, :3, :]
+    assert float((tfs.grad[:, 3, :]).abs().max()) == 0.0
+    def rel(a, b):
+        return float(torch.linalg.norm(a.reshape(-1) - b.reshape(-1)) / torch.linalg.norm(b).clamp_min(1e-20))
+    assert rel(got, ref) < 1e-4, rel(got, ref)
+    # an invalid root contributes nothing, whatever its upstream gradient
+    g2 = g_xc.clone(); g2[~v.cpu()] = 1e6
+    assert rel(eng.op_deform_backward(x, v, J, g2).cpu(), ref) < 1e-4
+    # chained: d/d(tfs, hash, mlp) of sum r * sdf over the valid roots
+    vc = v.cpu()
+    pts = x.cpu()[vc]
+    r = torch.randn(pts.shape[0], generator=g)
+    d_out = torch.zeros(pts.shape[0], 13); d_out[:, 0] = r
+    gb = eng.op_geometry_backward(pts, d_out)
+    g_full = torch.zeros(xd.shape[0], 13, 3); g_full[vc] = gb["x"].cpu()
+    got_tfs = eng.op_deform_backward(x, v, J, g_full).cpu()
+    F_ = scene.fields
+    tfs2 = R.tfs.clone().requires_grad_(True)
+    hash_ = F_.w["geo_hash"].clone().requires_grad_(True)
+    xc2 = odef.implicit_correction(x.cpu(), vc, J.cpu(), R.lbs_voxel, tfs2, R.offset, R.scale)[vc]
+    from oracle.fields import hashgrid
+    import torch.nn.functional as F
+    xn = (xc2 - F_.center) / F_.scale + 0.5
+    inp = torch.cat([xn * 2.0 - 1.0, hashgrid(xn, hash_, F_.layout)], dim=-1)
+    out = F.linear(F.softplus(F.linear(inp, F_.w["geo_w1"], F_.w["geo_b1"]), beta=100), F_.w["geo_w2"], F_.w["geo_b2"])
+    (out[:, 0] * r).sum().backward()
+    assert rel(got_tfs, tfs2.grad[:, :3, :]) < 2e-4, rel(got_tfs, tfs2.grad[:, :3, :])
+    assert rel(gb["hash"].cpu(), hash_.grad) < 1e-4
+
+
 def test_occupancy_ema_update_vs_oracle(scene):
     """ia_update_occupancy_ema (training-time grid update, SURVEY 8f.4: OccGridEstimator._update driven by
     IntrinsicAvatarModel.update_step, models/occ_grid/temporal_occ_grid.py:369-411, models/intrinsic_avatar.py:232-264) against

@@ -214,6 +214,27 @@ def test_lbs_voxelisation_matches_reference():
     assert np.allclose(vox["lbs_voxel"].sum(0), 1.0, atol=1e-5)
 
 
+def test_implicit_correction_matches_reference_training_forward():
+    """oracle.deformer.implicit_correction against the reference's own training-mode ForwardDeformer.forward (version 1,
+    models/deformers/fast_snarf/deformer_torch.py:57-76) and autograd through it (tests/golden/
+    reference_vectors_deform_train.npz, scripts/make_golden.py deform_train: only the CUDA search is replaced by prescribed
+    roots): value of x_c, gradient of the bone transforms."""
+    import torch
+    from oracle import deformer as odef
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z = np.load(os.path.join(here, "reference_vectors_deform_train.npz"))
+    v = np.load(os.path.join(here, "reference_vectors_voxel.npz"))
+    tfs = torch.from_numpy(z["tfs"]).clone().requires_grad_(True)
+    xc = odef.implicit_correction(torch.from_numpy(z["xc_opt"]), torch.from_numpy(z["valid"]), torch.from_numpy(z["J_inv"]),
+                                  torch.from_numpy(v["voxel_lbs"]), tfs, torch.from_numpy(v["voxel_offset_kernel"]),
+                                  torch.from_numpy(v["voxel_scale_kernel"]))
+    assert np.array_equal(xc.detach().numpy(), z["xc"])
+    (xc * torch.from_numpy(z["g_xc"])).sum().backward()
+    ref = torch.from_numpy(z["g_tfs"])
+    assert float(torch.linalg.norm(tfs.grad - ref) / torch.linalg.norm(ref)) < 1e-5
+    assert float(ref[:, 3].abs().max()) == 0.0
+
+
 def test_snarf_setup_matches_reference_prepare_deformer():
     """SnarfSetup.__init__ / .frame against the reference's own SNARFDeformer.initialize + prepare_deformer
     (models/deformers/snarf_deformer.py:46-126: tfs = w2s . A . A_cano^-1, root-frame vertices, canonical and deformed
