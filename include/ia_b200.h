@@ -250,6 +250,21 @@ int ia_op_geometry_backward(ia_ctx* ctx, const float* d_xc, const float* d_dout,
 int ia_op_deform_backward(ia_ctx* ctx, const float* d_xc, const uint8_t* d_valid, const float* d_J_inv, const float* d_g_xc,
                           int64_t n, float* d_g_tfs, void* stream);
 
+/* Training-mode forward / backward of the fused query: SNARFDeformer.deform with eval_mode=False
+ * (models/deformers/snarf_deformer.py:170-261) = ForwardDeformer.forward version 1 (search + implicit-differentiation
+ * correction, deformer_torch.py:34-76) -> VolumeSDF at every kept root -> min over the roots.
+ * ia_op_query_train: the values ia_op_query(with_grad=1) returns (the correction is zero-valued) plus what the backward pass
+ * reads: d_J_inv [n,3,3] = others['J_inv'] of the arg-min root (zeros without a root), d_best [n] = its init-bone slot 0..12.
+ * d_grad / d_grad_cano / d_feature may be NULL.
+ * ia_op_query_backward: for an upstream gradient d_dout [n,13] on the 13 network outputs at the arg-min root (channel 0 = sdf;
+ * torch.min routes the gradient to that root only; a query without a root has the constant sdf 1e5 and no gradient):
+ * ADDS into d_g_hash / d_g_mlp (layouts of ia_op_geometry_backward) and d_g_tfs [24][3][4] (ia_op_deform_backward);
+ * writes d_g_x [n,3] = dL/dx_c (zeros for queries without a root).  The reference gets all of this from autograd.           */
+int ia_op_query_train(ia_ctx* ctx, const float* d_xd, int64_t n, float* d_sdf, float* d_xc, uint8_t* d_valid, float* d_grad,
+                      float* d_grad_cano, float* d_feature, float* d_J_inv, int32_t* d_best, void* stream);
+int ia_op_query_backward(ia_ctx* ctx, const float* d_xc, const uint8_t* d_valid, const float* d_J_inv, const float* d_dout,
+                         int64_t n, float* d_g_hash, float* d_g_mlp, float* d_g_tfs, float* d_g_x, void* stream);
+
 /* Canonical SDF of n points, evaluated the way the wavefront integrator's geometry phase does: hash grid, then the
  * 35 -> 64 layer as warp-level tensor-core mma (TF32 inputs split in two, fp32 accumulate), softplus(beta = 100), sdf row
  * of the output layer.  Replaces VolumeSDF.forward without gradient (models/rf/geometry.py:124-146: encoding ->

@@ -1085,7 +1085,43 @@ extern "C" int ia_op_geometry_backward(ia_ctx* c, const float* d_xc, const float
     IA_CHECK_CUDA(cudaSetDevice(c->device));
     const size_t sm = 2 * IA_GEO_END * sizeof(float);
     IA_CHECK_CUDA(cudaFuncSetAttribute(k_geometry_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_geometry_backward<<<ia_query_blocks(c, n), 256, sm, (cudaStream_t)stream>>>(c->f, d_xc, d_dout, n, d_g_hash, d_g_mlp, d_g_x);
+    k_geometry_backward<<<ia_query_blocks(c, n), 256, sm, (cudaStream_t)stream>>>(c->f, d_xc, d_dout, n, d_g_hash, d_g_mlp, d_g_x,
+                                                                                  nullptr);
+    IA_LAUNCH_CHECK();
+    return IA_OK;
+}
+
+extern "C" int ia_op_query_train(ia_ctx* c, const float* d_xd, int64_t n, float* d_sdf, float* d_xc, uint8_t* d_valid,
+                                 float* d_grad, float* d_grad_cano, float* d_feature, float* d_J_inv, int32_t* d_best,
+                                 void* stream) {
+    IA_REQUIRE(c && n >= 0, IA_EINVAL, "ia_op_query_train: NULL argument");
+    IA_REQUIRE(c->have_pose && c->have_fields, IA_ESTATE, "ia_op_query_train: fields and pose must be set");
+    if (n == 0) return IA_OK;
+    IA_REQUIRE(d_xd && d_sdf && d_xc && d_valid && d_J_inv && d_best, IA_EINVAL, "ia_op_query_train: NULL argument");
+    IA_CHECK_CUDA(cudaSetDevice(c->device));
+    const size_t sm = IA_GEO_END * sizeof(float);
+    k_query_train<<<ia_query_blocks(c, n), 256, sm, (cudaStream_t)stream>>>(c->f, d_xd, n, d_sdf, d_xc, d_valid, d_grad,
+                                                                            d_grad_cano, d_feature, d_J_inv, d_best);
+    IA_LAUNCH_CHECK();
+    return IA_OK;
+}
+
+extern "C" int ia_op_query_backward(ia_ctx* c, const float* d_xc, const uint8_t* d_valid, const float* d_J_inv,
+                                    const float* d_dout, int64_t n, float* d_g_hash, float* d_g_mlp, float* d_g_tfs,
+                                    float* d_g_x, void* stream) {
+    IA_REQUIRE(c && d_g_hash && d_g_mlp && d_g_tfs && n >= 0, IA_EINVAL, "ia_op_query_backward: NULL argument");
+    IA_REQUIRE(c->have_pose && c->have_fields, IA_ESTATE, "ia_op_query_backward: fields and pose must be set");
+    if (n == 0) return IA_OK;
+    IA_REQUIRE(d_xc && d_valid && d_J_inv && d_dout && d_g_x, IA_EINVAL, "ia_op_query_backward: NULL argument");
+    IA_CHECK_CUDA(cudaSetDevice(c->device));
+    const size_t sm = 2 * IA_GEO_END * sizeof(float);
+    IA_CHECK_CUDA(cudaFuncSetAttribute(k_geometry_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    // network backward at the arg-min roots (gradient of hash table and weights, and dL/dx_c), then dL/dx_c through the
+    // implicit-differentiation correction to the bone transforms
+    k_geometry_backward<<<ia_query_blocks(c, n), 256, sm, (cudaStream_t)stream>>>(c->f, d_xc, d_dout, n, d_g_hash, d_g_mlp, d_g_x,
+                                                                                  d_valid);
+    IA_LAUNCH_CHECK();
+    k_deform_backward<<<ia_query_blocks(c, n), 256, 0, (cudaStream_t)stream>>>(c->f, d_xc, d_valid, d_J_inv, d_g_x, n, d_g_tfs);
     IA_LAUNCH_CHECK();
     return IA_OK;
 }

@@ -39,7 +39,7 @@ __device__ __forceinline__ void ia_hash_corners(const IaLevel lv, const float xn
 __global__ void __launch_bounds__(256) k_geometry_backward(const __grid_constant__ IaFrame p, const float* __restrict__ xc,
                                                            const float* __restrict__ d_out, long long n,
                                                            float* __restrict__ g_hash, float* __restrict__ g_mlp,
-                                                           float* __restrict__ g_x) {
+                                                           float* __restrict__ g_x, const uint8_t* __restrict__ valid) {
     extern __shared__ __align__(16) float smem[];
     float* w = smem;                    // geometry weights (IA_GEO_* layout)
     float* gw = smem + IA_GEO_END;      // their gradients, same layout
@@ -51,6 +51,10 @@ __global__ void __launch_bounds__(256) k_geometry_backward(const __grid_constant
     const long long teams = (long long)gridDim.x * (blockDim.x / IA_TEAM);
     const float2* tab = p.geo_hash;
     for (long long i = (long long)blockIdx.x * (blockDim.x / IA_TEAM) + threadIdx.x / IA_TEAM; i < n; i += teams) {
+        if (valid && !valid[i]) {      // a query without a root: no gradient (its sdf is the constant 1e5)
+            if (g_x && lane < 3) g_x[i * 3 + lane] = 0.f;
+            continue;
+        }
         // ---- forward (as ia_team_geometry)
         float xn[3];
 #pragma unroll
@@ -219,4 +223,79 @@ __global__ void __launch_bounds__(256) k_deform_backward(const __grid_constant__
     __syncthreads();
     for (int i = threadIdx.x; i < IA_N_BONES * 12; i += blockDim.x)
         if (gt[i] != 0.f) atomicAdd(&g_tfs[i], gt[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Training-mode forward of the fused query (SNARFDeformer.deform, models/deformers/snarf_deformer.py:187-261, with
+// ForwardDeformer.forward in training mode): the VALUES are those of the render path's query (the implicit-differentiation
+// correction is zero-valued), and the kernel additionally keeps what the backward pass needs -- the arg-min candidate and the
+// inverse Jacobian its Broyden chain ended with (others['J_inv'], deformer_torch.py:66).
+__global__ void __launch_bounds__(256) k_query_train(const __grid_constant__ IaFrame p, const float* __restrict__ xd, long long n,
+                                                     float* __restrict__ sdf, float* __restrict__ xc_out,
+                                                     uint8_t* __restrict__ valid, float* __restrict__ grad,
+                                                     float* __restrict__ grad_cano, float* __restrict__ feat,
+                                                     float* __restrict__ J_inv, int* __restrict__ best_out) {
+    extern __shared__ __align__(16) float smem[];
+    ia_stage(smem, p.mlp, IA_GEO_END);
+    __syncthreads();
+    Team team = cg::tiled_partition<IA_TEAM>(cg::this_thread_block());
+    const int lane = team.thread_rank();
+    const long long teams = (long long)gridDim.x * (blockDim.x / IA_TEAM);
+    for (long long i = (long long)blockIdx.x * (blockDim.x / IA_TEAM) + threadIdx.x / IA_TEAM; i < n; i += teams) {
+        const float pt[3] = {xd[i * 3 + 0], xd[i * 3 + 1], xd[i * 3 + 2]};
+        float x[3] = {0.f, 0.f, 0.f}, Ji[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        bool ok = false;
+        if (lane < IA_N_INIT) ok = ia_broyden_chain(p, p.init_bones[lane], pt, x, Ji, nullptr);
+        bool keep = ok;     // filter.cu: candidate i is dropped if a LATER valid candidate lies within 1e-4
+#pragma unroll
+        for (int j = 1; j < IA_N_INIT; j++) {
+            const float xj0 = team.shfl(x[0], j), xj1 = team.shfl(x[1], j), xj2 = team.shfl(x[2], j);
+            const bool vj = team.shfl((int)ok, j) != 0;
+            const float e0 = x[0] - xj0, e1 = x[1] - xj1, e2 = x[2] - xj2;
+            if (vj && j > lane && e0 * e0 + e1 * e1 + e2 * e2 < 0.0001f * 0.0001f) keep = false;
+        }
+        const unsigned mask = team.ballot(keep);
+        float s_min = 1e5f;
+        int best = 0;
+        unsigned m = mask;
+        while (m) {
+            const int c = __ffs(m) - 1;
+            m &= m - 1;
+            const float xc[3] = {team.shfl(x[0], c), team.shfl(x[1], c), team.shfl(x[2], c)};
+            const float s = ia_team_geometry<false>(team, p, smem, xc, nullptr, nullptr);
+            if (s < s_min) { s_min = s; best = c; }
+        }
+        const bool bvalid = (mask >> best) & 1u;
+        float bx[3], bJ[9];
+#pragma unroll
+        for (int d = 0; d < 3; d++) { bx[d] = team.shfl(x[d], best); if (!bvalid) bx[d] = 0.f; }
+#pragma unroll
+        for (int k = 0; k < 9; k++) { bJ[k] = team.shfl(Ji[k], best); if (!bvalid) bJ[k] = 0.f; }
+        float g[3] = {0.f, 0.f, 1.f}, gc[3] = {0.f, 0.f, 1.f}, f[13];
+#pragma unroll
+        for (int o = 0; o < 13; o++) f[o] = 0.f;
+        if (bvalid) {
+            ia_team_geometry<true>(team, p, smem, bx, f, gc);
+            float R[9];
+            ia_team_fwd_rotation(team, p, bx, R);
+#pragma unroll
+            for (int d = 0; d < 3; d++) g[d] = R[d * 3] * gc[0] + R[d * 3 + 1] * gc[1] + R[d * 3 + 2] * gc[2];
+        }
+        if (lane == 0) {
+            sdf[i] = s_min;
+            valid[i] = bvalid;
+            best_out[i] = best;
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                xc_out[i * 3 + d] = bx[d];
+                if (grad) grad[i * 3 + d] = g[d];
+                if (grad_cano) grad_cano[i * 3 + d] = gc[d];
+            }
+#pragma unroll
+            for (int k = 0; k < 9; k++) J_inv[i * 9 + k] = bJ[k];
+            if (feat)
+#pragma unroll
+                for (int o = 0; o < 13; o++) feat[i * 13 + o] = f[o];
+        }
+    }
 }

@@ -38,6 +38,8 @@ _ARGTYPES = {
     "ia_op_geometry": [_vp, _vp, _i64, _vp, _vp],
     "ia_op_geometry_backward": [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
     "ia_op_deform_backward": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
+    "ia_op_query_train": [_vp, _vp, _i64] + [_vp] * 9,
+    "ia_op_query_backward": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "ia_op_traverse": [_vp, _vp, _vp, _i64, _cf32, _cf32, _cf32] + [_vp] * 9 + [_vp],
     "ia_op_ray_resampling": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp] + [_vp] * 6 + [_vp],
     "ia_op_ray_resampling_merge": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp] + [_vp] * 6 + [_vp],
@@ -444,6 +446,39 @@ class RenderEngine:
         check(self.lib.ia_op_deform_backward(self.h, ptr(xc), ptr(valid), ptr(J_inv), ptr(g_xc), n, ptr(g_tfs), _stream()),
               "ia_op_deform_backward")
         return g_tfs
+
+    def op_query_train(self, xd):
+        """Training-mode forward of the fused query: ``op_query(with_grad=True)`` plus ``J_inv`` [n,3,3] and ``best`` [n] of the
+        arg-min root (what ``op_query_backward`` reads)."""
+        xd = xd.to(self.dev, torch.float32).contiguous()
+        n = xd.shape[0]
+        r = {"sdf": torch.empty(n, device=self.dev), "x_c": torch.empty(n, 3, device=self.dev),
+             "valid": torch.empty(n, dtype=torch.uint8, device=self.dev), "grad": torch.empty(n, 3, device=self.dev),
+             "grad_cano": torch.empty(n, 3, device=self.dev), "feature": torch.empty(n, 13, device=self.dev),
+             "J_inv": torch.empty(n, 3, 3, device=self.dev), "best": torch.empty(n, dtype=torch.int32, device=self.dev)}
+        check(self.lib.ia_op_query_train(self.h, ptr(xd), n, ptr(r["sdf"]), ptr(r["x_c"]), ptr(r["valid"]), ptr(r["grad"]),
+                                         ptr(r["grad_cano"]), ptr(r["feature"]), ptr(r["J_inv"]), ptr(r["best"]), _stream()),
+              "ia_op_query_train")
+        r["valid"] = r["valid"].bool()
+        return r
+
+    def op_query_backward(self, fwd, d_out):
+        """Backward of the fused query for an upstream gradient ``d_out`` [n,13] on the network outputs at the arg-min root
+        (channel 0 = sdf): dict with ``hash``, ``w1``, ``b1``, ``w2``, ``b2`` (as ``op_geometry_backward``), ``tfs`` [24,3,4]
+        and ``x`` [n,3].  ``fwd``: what ``op_query_train`` returned."""
+        xc = fwd["x_c"].contiguous()
+        n = xc.shape[0]
+        valid = fwd["valid"].to(torch.uint8).contiguous()
+        d_out = d_out.to(self.dev, torch.float32).reshape(n, 13).contiguous()
+        g_hash = torch.zeros_like(self._keep["geo"])
+        g_mlp = torch.zeros(3152, device=self.dev)
+        g_tfs = torch.zeros(24, 3, 4, device=self.dev)
+        g_x = torch.empty(n, 3, device=self.dev)
+        check(self.lib.ia_op_query_backward(self.h, ptr(xc), ptr(valid), ptr(fwd["J_inv"].contiguous()), ptr(d_out), n,
+                                            ptr(g_hash), ptr(g_mlp), ptr(g_tfs), ptr(g_x), _stream()), "ia_op_query_backward")
+        w1t, b1 = g_mlp[:35 * 64].reshape(35, 64), g_mlp[35 * 64:36 * 64]
+        w2, b2 = g_mlp[36 * 64:49 * 64].reshape(13, 64), g_mlp[49 * 64:49 * 64 + 13]
+        return {"hash": g_hash, "w1": w1t.t().contiguous(), "b1": b1, "w2": w2, "b2": b2, "tfs": g_tfs, "x": g_x}
 
     def op_traverse(self, rays_o, rays_d, near, far, step):
         o = rays_o.to(self.dev, torch.float32).contiguous()

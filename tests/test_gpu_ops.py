@@ -691,6 +691,54 @@ def test_deform_backward_vs_autograd(eng, posed, scene):
     assert rel(gb["hash"].cpu(), hash_.grad) < 1e-4
 
 
+def test_query_train_forward_backward(eng, posed, scene):
+    """Training-mode forward / backward of the fused query: ia_op_query_train returns the eval query's values
+    (bit for bit) plus the arg-min root's inverse Jacobian and slot -- those of the Broyden op -- and ia_op_query_backward
+    matches torch autograd through the oracle's restatement of the reference's graph (implicit-differentiation correction,
+    pinned to the reference's own training forward in test_oracle_golden.py, then VolumeSDF's network) for a random upstream
+    gradient on all 13 outputs: hash table, MLP weights, bone transforms."""
+    from oracle.fields import hashgrid
+    import torch.nn.functional as F
+    R = posed["oracle"]
+    xd = _points(posed, 8000, seed=6)
+    n = xd.shape[0]
+    fwd = eng.op_query_train(xd)
+    ev = eng.op_query(xd, with_grad=True)
+    for k, k2 in (("sdf", "sdf"), ("x_c", "x_c"), ("valid", "valid"), ("grad", "grad"), ("grad_cano", "grad_cano"),
+                  ("feature", "feature")):
+        assert torch.equal(fwd[k], ev[k2]), k
+    x, J, _, v = eng.op_broyden(xd)
+    ok = fwd["valid"]
+    assert int(ok.sum()) > 1000 and int((~ok).sum()) > 100
+    ar, idx = torch.arange(n, device=x.device), fwd["best"].long()
+    assert bool(v[ar, idx][ok].all()) and torch.equal(ok, v.any(-1))
+    assert torch.equal(fwd["x_c"][ok], x[ar, idx][ok]) and torch.equal(fwd["J_inv"][ok], J[ar, idx][ok])
+    assert float(fwd["J_inv"][~ok].abs().max()) == 0.0
+    g = torch.Generator().manual_seed(12)
+    d_out = torch.randn(n, 13, generator=g)
+    got = eng.op_query_backward(fwd, d_out)
+    F_ = scene.fields
+    params = {k: F_.w[k].clone().requires_grad_(True) for k in ("geo_hash", "geo_w1", "geo_b1", "geo_w2", "geo_b2")}
+    tfs = R.tfs.clone().requires_grad_(True)
+    okc = ok.cpu()
+    xc = odef.implicit_correction(fwd["x_c"].cpu()[:, None], okc[:, None], fwd["J_inv"].cpu()[:, None], R.lbs_voxel, tfs,
+                                  R.offset, R.scale)[:, 0][okc]
+    xn = (xc - F_.center) / F_.scale + 0.5
+    inp = torch.cat([xn * 2.0 - 1.0, hashgrid(xn, params["geo_hash"], F_.layout)], dim=-1)
+    out = F.linear(F.softplus(F.linear(inp, params["geo_w1"], params["geo_b1"]), beta=100), params["geo_w2"], params["geo_b2"])
+    assert float((out[:, 0].detach() - fwd["sdf"].cpu()[okc]).abs().max()) < 1e-4
+    (out * d_out[okc]).sum().backward()
+    def rel(a, b):
+        return float(torch.linalg.norm(a.cpu().reshape(-1) - b.reshape(-1)) / torch.linalg.norm(b).clamp_min(1e-20))
+    assert rel(got["tfs"], tfs.grad[:, :3, :]) < 2e-4, rel(got["tfs"], tfs.grad[:, :3, :])
+    for k, kk in (("hash", "geo_hash"), ("w1", "geo_w1"), ("b1", "geo_b1"), ("w2", "geo_w2"), ("b2", "geo_b2")):
+        assert rel(got[k], params[kk].grad) < 1e-4, k
+    assert float(got["x"][~ok].abs().max()) == 0.0
+    # empty batch
+    e0 = eng.op_query_train(torch.zeros(0, 3))
+    assert e0["sdf"].shape == (0,) and float(eng.op_query_backward(e0, torch.zeros(0, 13))["tfs"].abs().max()) == 0.0
+
+
 def test_occupancy_ema_update_vs_oracle(scene):
     """ia_update_occupancy_ema (training-time grid update, SURVEY 8f.4: OccGridEstimator._update driven by
     IntrinsicAvatarModel.update_step, models/occ_grid/temporal_occ_grid.py:369-411, models/intrinsic_avatar.py:232-264) against
