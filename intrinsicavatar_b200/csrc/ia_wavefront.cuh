@@ -1220,6 +1220,8 @@ __device__ __forceinline__ void wf_run(const IaFrame& p, P& pol, WfShared& S, un
         __syncthreads();
         {
             unsigned c_q = 0, c_rays = 0;
+            // (asking for the state lines of a warp's slots all at once with prefetch.global.L1 in front of this loop changes
+            //  nothing: 752.9 vs 752.6 ms -- the pass is not bound by its dependent L2 round trips)
             for (int t = tid; t < WF_R; t += blockDim.x) wf_advance_consume<GI>(p, pol, S, t, c_q);
             __syncthreads();
             const int n_r = S.n_rlist;
