@@ -250,6 +250,21 @@ int ia_op_geometry_backward(ia_ctx* ctx, const float* d_xc, const float* d_dout,
 int ia_op_deform_backward(ia_ctx* ctx, const float* d_xc, const uint8_t* d_valid, const float* d_J_inv, const float* d_g_xc,
                           int64_t n, float* d_g_tfs, void* stream);
 
+/* Training-mode building block: backward of the two shading networks the render path evaluates with
+ * ia_op_shade_fields -- VolumeRadiance.forward (models/rf/radiance.py:111-135: radiance hash grid + SH of the reflected view
+ * direction + VanillaMLP 67 -> 64 -> 64 -> 3, sigmoid) and the material network (models/pbr/material.py:31-51: 48 -> 64 -> 64 -> 5,
+ * sigmoid * scale (* albedo_align_ratio) + bias; models/network_utils.py:201-244, 360-428) -- which the reference differentiates
+ * with autograd through tiny-cuda-nn.  Inputs as ia_op_shade_fields; d_drgb [n,3], d_dmat [n,5] upstream gradients of its outputs.
+ * ADDS into d_g_rad_hash [2 * n_entries] (the radiance table's layout) and d_g_mlp [IA_SHADE_GRAD_FLOATS: radiance W1^T [67][64] |
+ * b1 [64] | W2^T [64][64] | b2 [64] | W3 [3][64] | b3 [4] | material W1^T [48][64] | b1 | W2^T | b2 | W3 [5][64] | b3 [8]]
+ * (effective, folded weights); writes (any may be NULL) d_g_x [n,3] (canonical position), d_g_feature [n,13] (feed it to
+ * ia_op_query_backward as d_dout), d_g_normal [n,3] (world-space normal; the view direction is data).                       */
+#define IA_SHADE_GRAD_FLOATS 16332
+int ia_op_shade_fields_backward(ia_ctx* ctx, const float* d_xc, const float* d_feature, const float* d_view,
+                                const float* d_normal, const float* d_drgb, const float* d_dmat, int64_t n,
+                                float* d_g_rad_hash, float* d_g_mlp, float* d_g_x, float* d_g_feature, float* d_g_normal,
+                                void* stream);
+
 /* Training-mode forward / backward of the fused query: SNARFDeformer.deform with eval_mode=False
  * (models/deformers/snarf_deformer.py:170-261) = ForwardDeformer.forward version 1 (search + implicit-differentiation
  * correction, deformer_torch.py:34-76) -> VolumeSDF at every kept root -> min over the roots.

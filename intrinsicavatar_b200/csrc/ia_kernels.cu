@@ -1091,6 +1091,24 @@ extern "C" int ia_op_geometry_backward(ia_ctx* c, const float* d_xc, const float
     return IA_OK;
 }
 
+extern "C" int ia_op_shade_fields_backward(ia_ctx* c, const float* d_xc, const float* d_feature, const float* d_view,
+                                           const float* d_normal, const float* d_drgb, const float* d_dmat, int64_t n,
+                                           float* d_g_rad_hash, float* d_g_mlp, float* d_g_x, float* d_g_feature,
+                                           float* d_g_normal, void* stream) {
+    IA_REQUIRE(c && d_g_rad_hash && d_g_mlp && n >= 0, IA_EINVAL, "ia_op_shade_fields_backward: NULL argument");
+    IA_REQUIRE(c->have_fields, IA_ESTATE, "ia_op_shade_fields_backward: call ia_set_fields first");
+    if (n == 0) return IA_OK;
+    IA_REQUIRE(d_xc && d_feature && d_view && d_normal && d_drgb && d_dmat, IA_EINVAL,
+               "ia_op_shade_fields_backward: NULL argument");
+    IA_CHECK_CUDA(cudaSetDevice(c->device));
+    const size_t sm = (IA_SHADE_GRAD_FLOATS + (256 / IA_TEAM) * IA_SHB_TEAM_FLOATS) * sizeof(float);
+    IA_CHECK_CUDA(cudaFuncSetAttribute(k_shade_fields_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_shade_fields_backward<<<ia_query_blocks(c, n), 256, sm, (cudaStream_t)stream>>>(
+        c->f, d_xc, d_feature, d_view, d_normal, d_drgb, d_dmat, n, d_g_rad_hash, d_g_mlp, d_g_x, d_g_feature, d_g_normal);
+    IA_LAUNCH_CHECK();
+    return IA_OK;
+}
+
 extern "C" int ia_op_query_train(ia_ctx* c, const float* d_xd, int64_t n, float* d_sdf, float* d_xc, uint8_t* d_valid,
                                  float* d_grad, float* d_grad_cano, float* d_feature, float* d_J_inv, int32_t* d_best,
                                  void* stream) {

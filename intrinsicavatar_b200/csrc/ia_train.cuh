@@ -299,3 +299,199 @@ __global__ void __launch_bounds__(256) k_query_train(const __grid_constant__ IaF
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Training-mode building block: backward of the two shading networks at a canonical point
+//   rgb  = sigmoid(MLP_67-64-64-3 ([2 xn - 1, hashgrid_rad(xn), feature, SH4(reflect(-view, n)), n]))      models/rf/radiance.py:111-135
+//   mats = sigmoid(MLP_48-64-64-5 ([2 xn - 1, hashgrid_rad(xn), feature])) * scale (* albedo ratio) + bias  models/pbr/material.py:31-51
+// (VanillaMLP / LipshitzMLP with ReLU, models/network_utils.py:201-244, 360-428; weights here are the effective, folded ones)
+// with respect to the radiance hash table, both networks' weights, and the inputs: position, geometry feature, normal.
+// The reference gets these from autograd.  Team layout of ia_team_radiance: lane = hash level = hidden units 4 lane .. + 3.
+// Weight gradients accumulate in shared memory per CTA (layout of the blob from IA_RAD_W1T on) and are flushed once.
+static_assert(IA_SHADE_GRAD_FLOATS == IA_MLP_END - IA_RAD_W1T, "ia_b200.h: IA_SHADE_GRAD_FLOATS out of sync with the blob layout");
+
+// One three-layer network: recomputes the forward from the team's input vector `inp` (shared memory, IN floats), applies the
+// upstream gradient `dsig` [OUT] on the sigmoid outputs, adds the weight gradients into `gw` (shared, indexed like the blob
+// relative to IA_RAD_W1T) and writes dL/d inp to `dinp` (shared, IN floats).  Returns the sigmoid outputs in `out`.
+template <int IN, int OUT>
+__device__ __forceinline__ void ia_team_mlp3_backward(const Team& team, const float* __restrict__ blob, float* __restrict__ gw,
+                                                      int o_w1t, int o_b1, int o_w2t, int o_b2, int o_w3, int o_b3,
+                                                      const float* __restrict__ inp, const float* __restrict__ dsig,
+                                                      float* __restrict__ dinp, float* __restrict__ out) {
+    const int lane = team.thread_rank();
+    const float4* W1 = reinterpret_cast<const float4*>(blob + o_w1t) + lane;
+    const float4* W2 = reinterpret_cast<const float4*>(blob + o_w2t) + lane;
+    const float4* W3 = reinterpret_cast<const float4*>(blob + o_w3) + lane;
+    // ---- forward
+    float4 a1 = reinterpret_cast<const float4*>(blob + o_b1)[lane];
+#pragma unroll 1
+    for (int i = 0; i < IN; i++) ia_axpy4(a1, W1 + i * 16, inp[i]);
+    const float h1[4] = {fmaxf(a1.x, 0.f), fmaxf(a1.y, 0.f), fmaxf(a1.z, 0.f), fmaxf(a1.w, 0.f)};
+    const float4 a2 = ia_team_dense64(team, blob + o_w2t, blob + o_b2, h1);
+    const float h2[4] = {fmaxf(a2.x, 0.f), fmaxf(a2.y, 0.f), fmaxf(a2.z, 0.f), fmaxf(a2.w, 0.f)};
+    float ds[OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; o++) {
+        const float4 ww = W3[o * 16];
+        const float s = ia_team_sum(team, ww.x * h2[0] + ww.y * h2[1] + ww.z * h2[2] + ww.w * h2[3]) + blob[o_b3 + o];
+        const float sg = ia_sigmoid(s);
+        out[o] = sg;
+        ds[o] = dsig[o] * sg * (1.0f - sg);
+    }
+    // ---- output layer
+    float dh2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int o = 0; o < OUT; o++) {
+        const float4 ww = W3[o * 16];
+        dh2[0] = fmaf(ww.x, ds[o], dh2[0]); dh2[1] = fmaf(ww.y, ds[o], dh2[1]);
+        dh2[2] = fmaf(ww.z, ds[o], dh2[2]); dh2[3] = fmaf(ww.w, ds[o], dh2[3]);
+        float* g3 = gw + (o_w3 - IA_RAD_W1T) + o * 64 + 4 * lane;
+#pragma unroll
+        for (int k = 0; k < 4; k++) atomicAdd(g3 + k, ds[o] * h2[k]);
+        if (lane == 0) atomicAdd(gw + (o_b3 - IA_RAD_W1T) + o, ds[o]);
+    }
+    const float da2[4] = {a2.x > 0.f ? dh2[0] : 0.f, a2.y > 0.f ? dh2[1] : 0.f, a2.z > 0.f ? dh2[2] : 0.f, a2.w > 0.f ? dh2[3] : 0.f};
+    // ---- hidden layer 64 -> 64 (input-major W2T[j][k]): gradient of the weights, and dL/dh1[j] = sum_k W2T[j][k] da2[k]
+    float dh1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int s = 0; s < IA_TEAM; s++) {
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            const int j = s * 4 + kk;
+            const float hj = team.shfl(h1[kk], s);
+            const float4 ww = W2[j * 16];
+            float* g2 = gw + (o_w2t - IA_RAD_W1T) + j * 64 + 4 * lane;
+            if (hj != 0.f) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) atomicAdd(g2 + k, hj * da2[k]);
+            }
+            const float t = ia_team_sum(team, ww.x * da2[0] + ww.y * da2[1] + ww.z * da2[2] + ww.w * da2[3]);
+            if (lane == s) dh1[kk] = t;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) atomicAdd(gw + (o_b2 - IA_RAD_W1T) + 4 * lane + k, da2[k]);
+    const float da1[4] = {a1.x > 0.f ? dh1[0] : 0.f, a1.y > 0.f ? dh1[1] : 0.f, a1.z > 0.f ? dh1[2] : 0.f, a1.w > 0.f ? dh1[3] : 0.f};
+    // ---- first layer
+#pragma unroll 1
+    for (int i = 0; i < IN; i++) {
+        const float4 ww = W1[i * 16];
+        const float x = inp[i];
+        float* g1 = gw + (o_w1t - IA_RAD_W1T) + i * 64 + 4 * lane;
+#pragma unroll
+        for (int k = 0; k < 4; k++) atomicAdd(g1 + k, x * da1[k]);
+        const float t = ia_team_sum(team, ww.x * da1[0] + ww.y * da1[1] + ww.z * da1[2] + ww.w * da1[3]);
+        if (lane == 0) dinp[i] = t;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) atomicAdd(gw + (o_b1 - IA_RAD_W1T) + 4 * lane + k, da1[k]);
+}
+
+// Jacobian-transpose product of ia_sh4: g[16] -> d/d(x, y, z)
+__device__ __forceinline__ void ia_sh4_backward(float x, float y, float z, const float* __restrict__ g, float d[3]) {
+    const float a = 0.48860251190291987f, b = 1.0925484305920792f, c = 0.94617469575755997f, e = 0.54627421529603959f,
+                f = 0.59004358992664352f, q = 2.8906114426405538f, h = 0.45704579946446572f, k = 0.3731763325901154f,
+                m = 1.4453057213202769f;
+    const float x2 = x * x, y2 = y * y, z2 = z * z;
+    d[0] = -a * g[3] + b * y * g[4] - b * z * g[7] + 2.f * e * x * g[8] - 6.f * f * x * y * g[9] + q * y * z * g[10] +
+           h * (1.f - 5.f * z2) * g[13] + 2.f * m * x * z * g[14] + f * (-3.f * x2 + 3.f * y2) * g[15];
+    d[1] = -a * g[1] + b * x * g[4] - b * z * g[5] - 2.f * e * y * g[8] + f * (-3.f * x2 + 3.f * y2) * g[9] + q * x * z * g[10] +
+           h * (1.f - 5.f * z2) * g[11] - 2.f * m * y * z * g[14] + 6.f * f * x * y * g[15];
+    d[2] = a * g[2] - b * y * g[5] + 2.f * c * z * g[6] - b * x * g[7] + q * x * y * g[10] - 10.f * h * y * z * g[11] +
+           k * (15.f * z2 - 3.f) * g[12] - 10.f * h * x * z * g[13] + m * (x2 - y2) * g[14];
+}
+
+#define IA_SHB_TEAM_FLOATS (67 + 67 + 48)    // per team in shared memory: input vector, dL/d input of the two networks
+__global__ void __launch_bounds__(256) k_shade_fields_backward(const __grid_constant__ IaFrame p, const float* __restrict__ xc,
+                                                               const float* __restrict__ feat, const float* __restrict__ view,
+                                                               const float* __restrict__ nrm, const float* __restrict__ d_rgb,
+                                                               const float* __restrict__ d_mat, long long n,
+                                                               float* __restrict__ g_hash, float* __restrict__ g_mlp,
+                                                               float* __restrict__ g_x, float* __restrict__ g_feat,
+                                                               float* __restrict__ g_nrm) {
+    extern __shared__ __align__(16) float smem[];
+    float* gw = smem;                                   // IA_SHADE_GRAD_FLOATS
+    float* mine = smem + IA_SHADE_GRAD_FLOATS + (threadIdx.x / IA_TEAM) * IA_SHB_TEAM_FLOATS;
+    float* inp = mine;
+    float* dr = mine + 67;
+    float* dm = mine + 134;
+    for (int i = threadIdx.x; i < IA_SHADE_GRAD_FLOATS; i += blockDim.x) gw[i] = 0.f;
+    __syncthreads();
+    Team team = cg::tiled_partition<IA_TEAM>(cg::this_thread_block());
+    const int lane = team.thread_rank();
+    const long long teams = (long long)gridDim.x * (blockDim.x / IA_TEAM);
+    for (long long i = (long long)blockIdx.x * (blockDim.x / IA_TEAM) + threadIdx.x / IA_TEAM; i < n; i += teams) {
+        // ---- inputs
+        float xn[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) xn[d] = (xc[i * 3 + d] - p.center[d]) / p.scale[d] + 0.5f;
+        const IaLevel lv = ia_level(p, lane);
+        uint32_t idx[8];
+        float wt[8], wl[3];
+        ia_hash_corners(lv, xn, idx, wt, wl);
+        float2 v[8];
+        float f0 = 0.f, f1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; c++) { v[c] = __ldg(p.rad_hash + idx[c]); f0 = fmaf(wt[c], v[c].x, f0); f1 = fmaf(wt[c], v[c].y, f1); }
+        const float vw[3] = {-view[i * 3], -view[i * 3 + 1], -view[i * 3 + 2]};
+        const float nw[3] = {nrm[i * 3], nrm[i * 3 + 1], nrm[i * 3 + 2]};
+        const float dn = vw[0] * nw[0] + vw[1] * nw[1] + vw[2] * nw[2];
+        float r[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) r[d] = ((2.f * dn * nw[d] - vw[d] + 1.f) / 2.f) * 2.f - 1.f;
+        team.sync();
+        if (lane < 3) { inp[lane] = xn[lane] * 2.0f - 1.0f; inp[64 + lane] = nw[lane]; }
+        inp[3 + 2 * lane] = f0; inp[4 + 2 * lane] = f1;
+        if (lane < 13) inp[35 + lane] = feat[i * 13 + lane];
+        if (lane == 0) ia_sh4(r[0], r[1], r[2], inp + 48);
+        team.sync();
+        // ---- the two networks
+        float dsig_r[3], dsig_m[5], out_r[3], out_m[5];
+#pragma unroll
+        for (int o = 0; o < 3; o++) dsig_r[o] = d_rgb[i * 3 + o];
+#pragma unroll
+        for (int o = 0; o < 5; o++) dsig_m[o] = d_mat[i * 5 + o] * p.mat_scale[o] * (o < 3 ? p.albedo_ratio[o] : 1.0f);
+        ia_team_mlp3_backward<67, 3>(team, p.mlp, gw, IA_RAD_W1T, IA_RAD_B1, IA_RAD_W2T, IA_RAD_B2, IA_RAD_W3, IA_RAD_B3, inp,
+                                     dsig_r, dr, out_r);
+        ia_team_mlp3_backward<48, 5>(team, p.mlp, gw, IA_MAT_W1T, IA_MAT_B1, IA_MAT_W2T, IA_MAT_B2, IA_MAT_W3, IA_MAT_B3, inp,
+                                     dsig_m, dm, out_m);
+        team.sync();
+        // ---- inputs: hash entries of this lane's level, position, feature, normal
+        const float de0 = dr[3 + 2 * lane] + dm[3 + 2 * lane], de1 = dr[4 + 2 * lane] + dm[4 + 2 * lane];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            atomicAdd(&g_hash[(size_t)idx[c] * 2 + 0], wt[c] * de0);
+            atomicAdd(&g_hash[(size_t)idx[c] * 2 + 1], wt[c] * de1);
+        }
+        float gx[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int b1 = k & 1, b2 = k >> 1;
+                const float t = (b1 ? wl[d1] : 1.f - wl[d1]) * (b2 ? wl[d2] : 1.f - wl[d2]);
+                const int lo = (b1 << d1) | (b2 << d2), hi = lo | (1 << d);
+                a0 = fmaf(t, v[hi].x - v[lo].x, a0);
+                a1 = fmaf(t, v[hi].y - v[lo].y, a1);
+            }
+            gx[d] = ia_team_sum(team, lv.scale * (a0 * de0 + a1 * de1));
+        }
+        if (lane < 3) {
+            if (g_x) g_x[i * 3 + lane] = ((lane == 0 ? gx[0] : lane == 1 ? gx[1] : gx[2]) + 2.0f * (dr[lane] + dm[lane])) / p.scale[lane];
+        }
+        if (g_feat && lane < 13) g_feat[i * 13 + lane] = dr[35 + lane] + dm[35 + lane];
+        if (g_nrm && lane == 0) {
+            float gr[3];
+            ia_sh4_backward(r[0], r[1], r[2], dr + 48, gr);
+            // refl = 2 (v . n) n - v:  d/dn_j = 2 v_j (g . n) + 2 (v . n) g_j
+            const float gn = gr[0] * nw[0] + gr[1] * nw[1] + gr[2] * nw[2];
+#pragma unroll
+            for (int d = 0; d < 3; d++) g_nrm[i * 3 + d] = dr[64 + d] + 2.f * vw[d] * gn + 2.f * dn * gr[d];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < IA_SHADE_GRAD_FLOATS; i += blockDim.x)
+        if (gw[i] != 0.f) atomicAdd(&g_mlp[i], gw[i]);
+}

@@ -39,6 +39,7 @@ _ARGTYPES = {
     "ia_op_geometry_backward": [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
     "ia_op_deform_backward": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "ia_op_query_train": [_vp, _vp, _i64] + [_vp] * 9,
+    "ia_op_shade_fields_backward": [_vp] * 7 + [_i64] + [_vp] * 6,
     "ia_op_query_backward": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "ia_op_traverse": [_vp, _vp, _vp, _i64, _cf32, _cf32, _cf32] + [_vp] * 9 + [_vp],
     "ia_op_ray_resampling": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp] + [_vp] * 6 + [_vp],
@@ -408,6 +409,31 @@ class RenderEngine:
         check(self.lib.ia_op_shade_fields(self.h, *[ptr(t) for t in a], n, ptr(rgb), ptr(mat), _stream()),
               "ia_op_shade_fields")
         return rgb, mat
+
+    def op_shade_fields_backward(self, xc, feature, view_world, normal_world, d_rgb, d_mat):
+        """Gradients of  sum <d_rgb, rgb> + <d_mat, mat>  for the outputs of ``op_shade_fields``: dict with ``hash`` (radiance
+        table), ``rad`` / ``mat`` = {w1, b1, w2, b2, w3, b3} in the shapes of the folded weights, and the input gradients
+        ``x`` [n,3], ``feature`` [n,13], ``normal`` [n,3]."""
+        a = [t.to(self.dev, torch.float32).contiguous() for t in (xc, feature, view_world, normal_world, d_rgb, d_mat)]
+        n = a[0].shape[0]
+        g_hash = torch.zeros_like(self._keep["rad"])
+        g_mlp = torch.zeros(16332, device=self.dev)
+        g_x, g_f, g_n = (torch.empty(n, 3, device=self.dev), torch.empty(n, 13, device=self.dev),
+                         torch.empty(n, 3, device=self.dev))
+        check(self.lib.ia_op_shade_fields_backward(self.h, *[ptr(t) for t in a], n, ptr(g_hash), ptr(g_mlp), ptr(g_x), ptr(g_f),
+                                                   ptr(g_n), _stream()), "ia_op_shade_fields_backward")
+
+        def net(o, n_in, n_out, pad):
+            w1 = g_mlp[o:o + n_in * 64].reshape(n_in, 64).t().contiguous(); o += n_in * 64
+            b1 = g_mlp[o:o + 64]; o += 64
+            w2 = g_mlp[o:o + 4096].reshape(64, 64).t().contiguous(); o += 4096
+            b2 = g_mlp[o:o + 64]; o += 64
+            w3 = g_mlp[o:o + n_out * 64].reshape(n_out, 64); o += n_out * 64
+            b3 = g_mlp[o:o + n_out]; o += pad
+            return {"w1": w1, "b1": b1, "w2": w2, "b2": b2, "w3": w3, "b3": b3}, o
+        rad, o = net(0, 67, 3, 4)
+        mat, o = net(o, 48, 5, 8)
+        return {"hash": g_hash, "rad": rad, "mat": mat, "x": g_x, "feature": g_f, "normal": g_n}
 
     def op_geometry(self, xc):
         """Canonical SDF of points [n,3] on the tensor-core path of the wavefront integrator's geometry phase."""

@@ -7,7 +7,7 @@ grep -v "^==PROF==" gpurun_out/traffic_full.csv > profiles/${R}_k_shade_wf_gi1_t
 python scripts/ncu_summary.py gpurun_out/k_shade_wf_full.ncu-rep > profiles/${R}_k_shade_wf_gi1_ncu_full_256x256x256.txt
 python scripts/ncu_phases.py gpurun_out/k_shade_wf_full.ncu-rep k_shade_wf > profiles/${R}_k_shade_wf_gi1_phases_256x256x256.txt
 python scripts/ncu_phases.py gpurun_out/k_shade_wf_full.ncu-rep k_shade_wf --warpsync | awk 'NR<=2 || $5+0 >= 0.3' > profiles/${R}_k_shade_wf_gi1_phases_warpsync_256x256x256.txt
-python scripts/ncu_summary.py gpurun_out/k_prim_shade_full.ncu-rep > profiles/${R}_k_prim_shade_ncu_full_512x512.txt
+[ -f gpurun_out/k_prim_shade_full.ncu-rep ] && python scripts/ncu_summary.py gpurun_out/k_prim_shade_full.ncu-rep > profiles/${R}_k_prim_shade_ncu_full_512x512.txt || true
 python - <<PY
 import csv, json
 rows = list(csv.DictReader(l for l in open("profiles/${R}_k_shade_wf_gi1_traffic_fullsize.csv") if l.startswith('"')))

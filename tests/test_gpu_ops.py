@@ -739,6 +739,35 @@ def test_query_train_forward_backward(eng, posed, scene):
     assert e0["sdf"].shape == (0,) and float(eng.op_query_backward(e0, torch.zeros(0, 13))["tfs"].abs().max()) == 0.0
 
 
+def test_fused_query_autograd_function(eng, posed, scene):
+    """train.fused_query routes ia_op_query_train / ia_op_query_backward into torch autograd: a loss on sdf and feature
+    back-propagates to the hash table, the effective MLP weights and the bone transforms exactly as the op (held to the
+    oracle's autograd in test_query_train_forward_backward) says."""
+    from intrinsicavatar_b200.train import fused_query
+    R = posed["oracle"]
+    xd = _points(posed, 3000, seed=7).cuda()
+    F_ = scene.fields
+    leaves = [F_.w[k].clone().cuda().requires_grad_(True) for k in ("geo_hash", "geo_w1", "geo_b1", "geo_w2", "geo_b2")]
+    tfs = R.tfs.clone().cuda().requires_grad_(True)
+    sdf, feature, x_c, valid = fused_query(eng, xd, *leaves, tfs)
+    assert not x_c.requires_grad and sdf.requires_grad and feature.requires_grad
+    g = torch.Generator().manual_seed(3)
+    r, Fm = torch.randn(xd.shape[0], generator=g).cuda(), torch.randn(xd.shape[0], 13, generator=g).cuda()
+    ((sdf * r).sum() + (feature * Fm).sum()).backward()
+    d_out = Fm.clone(); d_out[:, 0] += r
+    fwd = eng.op_query_train(xd)
+    assert torch.equal(fwd["sdf"], sdf.detach()) and torch.equal(fwd["valid"], valid)
+    ref = eng.op_query_backward(fwd, d_out)
+    def rel(a, b):
+        return float(torch.linalg.norm((a - b).reshape(-1)) / torch.linalg.norm(b).clamp_min(1e-20))
+    # (float atomics: the two backward runs add in a different order)
+    assert rel(leaves[0].grad.reshape(-1), ref["hash"].reshape(-1)) < 1e-5
+    for t, k in zip(leaves[1:], ("w1", "b1", "w2", "b2")):
+        assert t.grad.shape == t.shape and rel(t.grad, ref[k]) < 1e-5, k
+    assert tfs.grad.shape == (24, 4, 4) and rel(tfs.grad[:, :3, :], ref["tfs"]) < 1e-5
+    assert float(tfs.grad[:, 3, :].abs().max()) == 0.0
+
+
 def test_occupancy_ema_update_vs_oracle(scene):
     """ia_update_occupancy_ema (training-time grid update, SURVEY 8f.4: OccGridEstimator._update driven by
     IntrinsicAvatarModel.update_step, models/occ_grid/temporal_occ_grid.py:369-411, models/intrinsic_avatar.py:232-264) against
