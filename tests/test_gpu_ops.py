@@ -768,6 +768,53 @@ def test_fused_query_autograd_function(eng, posed, scene):
     assert float(tfs.grad[:, 3, :].abs().max()) == 0.0
 
 
+def test_shade_fields_backward_vs_autograd(eng, scene):
+    """ia_op_shade_fields_backward (training path) against torch autograd through the oracle's restatement of the
+    radiance and material networks (oracle/fields.py, pinned to the reference's own modules by the fields golden): gradients of
+    the radiance hash table, all twelve weight tensors, and the inputs -- position, geometry feature, world normal -- for a
+    random upstream gradient on rgb and on the five material channels."""
+    from oracle.fields import hashgrid, sh4
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(31)
+    n = 3000
+    F_ = scene.fields
+    xc = F_.center + (torch.rand(n, 3, generator=g) - 0.5) * F_.scale * 0.6
+    _, feat = F_.geometry(xc)
+    v = F.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    nw = F.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    d_rgb, d_mat = torch.randn(n, 3, generator=g), torch.randn(n, 5, generator=g)
+    got = eng.op_shade_fields_backward(xc, feat, v, nw, d_rgb, d_mat)
+    names = ["rad_hash"] + [f"{net}_{t}{i}" for net in ("rad", "mat") for i in (1, 2, 3) for t in ("w", "b")]
+    P = {k: F_.w[k].clone().requires_grad_(True) for k in names}
+    x, f, nn_ = xc.clone().requires_grad_(True), feat.clone().requires_grad_(True), nw.clone().requires_grad_(True)
+    xn = (x - F_.center) / F_.scale + 0.5
+    emb = torch.cat([xn * 2.0 - 1.0, hashgrid(xn, P["rad_hash"], F_.layout)], dim=-1)
+    vv = -v
+    refl = 2.0 * (vv * nn_).sum(-1, keepdim=True) * nn_ - vv
+    inp = torch.cat([emb, f, sh4(((refl + 1.0) / 2.0) * 2.0 - 1.0), nn_], dim=-1)
+    h = F.relu(F.linear(inp, P["rad_w1"], P["rad_b1"]))
+    h = F.relu(F.linear(h, P["rad_w2"], P["rad_b2"]))
+    rgb = torch.sigmoid(F.linear(h, P["rad_w3"], P["rad_b3"]))
+    m = F.relu(F.linear(torch.cat([emb, f], dim=-1), P["mat_w1"], P["mat_b1"]))
+    m = F.relu(F.linear(m, P["mat_w2"], P["mat_b2"]))
+    mat = torch.sigmoid(F.linear(m, P["mat_w3"], P["mat_b3"])) * F_.mat_scale + F_.mat_bias
+    frgb, fmat = eng.op_shade_fields(xc, feat, v, nw)
+    assert float((frgb.cpu() - rgb.detach()).abs().max()) < 2e-5 and float((fmat.cpu() - mat.detach()).abs().max()) < 2e-5
+    ((rgb * d_rgb).sum() + (mat * d_mat).sum()).backward()
+    def rel(a, b):
+        return float(torch.linalg.norm(a.cpu().reshape(-1) - b.reshape(-1)) / torch.linalg.norm(b).clamp_min(1e-20))
+    assert rel(got["hash"], P["rad_hash"].grad) < 1e-4
+    for net in ("rad", "mat"):
+        for t in ("w1", "b1", "w2", "b2", "w3", "b3"):
+            ref = P[f"{net}_{t}"].grad
+            assert got[net][t].shape == ref.shape, (net, t)
+            assert rel(got[net][t], ref) < 1e-4, (net, t, rel(got[net][t], ref))
+    assert rel(got["x"], x.grad) < 1e-4 and rel(got["feature"], f.grad) < 1e-4 and rel(got["normal"], nn_.grad) < 1e-4
+    # empty batch
+    e0 = eng.op_shade_fields_backward(*[torch.zeros(0, k) for k in (3, 13, 3, 3, 3, 5)])
+    assert float(e0["hash"].abs().max()) == 0.0 and e0["x"].shape == (0, 3)
+
+
 def test_occupancy_ema_update_vs_oracle(scene):
     """ia_update_occupancy_ema (training-time grid update, SURVEY 8f.4: OccGridEstimator._update driven by
     IntrinsicAvatarModel.update_step, models/occ_grid/temporal_occ_grid.py:369-411, models/intrinsic_avatar.py:232-264) against
