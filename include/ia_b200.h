@@ -265,6 +265,21 @@ int ia_op_shade_fields_backward(ia_ctx* ctx, const float* d_xc, const float* d_f
                                 float* d_g_rad_hash, float* d_g_mlp, float* d_g_x, float* d_g_feature, float* d_g_normal,
                                 void* stream);
 
+/* Training-mode building block: compositing along the primary rays and its backward -- what
+ * rendering_with_normals_mats_sdf (models/volrend.py:336-364) builds from get_alpha (Laplace-CDF density, models/rf/density.py:17-34;
+ * models/intrinsic_avatar.py:390-394), nerfacc 0.5.3 render_weight_from_alpha and accumulate_along_rays, and differentiates with
+ * autograd.  d_packed_info [n_rays,2] = (first sample, count) like nerfacc; d_sdf / d_dists [n_samples]; d_values [n_samples, C]
+ * (C <= IA_VOLREND_MAX_C: rgb, normal, materials ... concatenated by the caller); beta = LearnedLaplaceDensity.get_beta().
+ * ia_op_volrend: d_weights [n_samples] (may be NULL), d_comp [n_rays, C], d_opacity [n_rays].
+ * ia_op_volrend_backward: upstream d_dcomp [n_rays, C], d_dopacity [n_rays] (may be NULL) -> writes d_g_sdf [n_samples],
+ * d_g_values [n_samples, C] (may be NULL); ADDS into d_g_beta [1].                                                        */
+#define IA_VOLREND_MAX_C 16
+int ia_op_volrend(ia_ctx* ctx, const int32_t* d_packed_info, const float* d_sdf, const float* d_dists, const float* d_values,
+                  int n_channels, float beta, int64_t n_rays, float* d_weights, float* d_comp, float* d_opacity, void* stream);
+int ia_op_volrend_backward(ia_ctx* ctx, const int32_t* d_packed_info, const float* d_sdf, const float* d_dists,
+                           const float* d_values, int n_channels, float beta, const float* d_dcomp, const float* d_dopacity,
+                           int64_t n_rays, float* d_g_sdf, float* d_g_values, float* d_g_beta, void* stream);
+
 /* Training-mode forward / backward of the fused query: SNARFDeformer.deform with eval_mode=False
  * (models/deformers/snarf_deformer.py:170-261) = ForwardDeformer.forward version 1 (search + implicit-differentiation
  * correction, deformer_torch.py:34-76) -> VolumeSDF at every kept root -> min over the roots.

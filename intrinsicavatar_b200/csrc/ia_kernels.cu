@@ -1109,6 +1109,38 @@ extern "C" int ia_op_shade_fields_backward(ia_ctx* c, const float* d_xc, const f
     return IA_OK;
 }
 
+extern "C" int ia_op_volrend(ia_ctx* c, const int32_t* d_packed_info, const float* d_sdf, const float* d_dists,
+                             const float* d_values, int n_channels, float beta, int64_t n_rays, float* d_weights,
+                             float* d_comp, float* d_opacity, void* stream) {
+    IA_REQUIRE(c && n_rays >= 0 && n_channels >= 0 && n_channels <= IA_VOLREND_MAX_C && beta > 0.f, IA_EINVAL,
+               "ia_op_volrend: bad argument (channels <= 16, beta > 0)");
+    if (n_rays == 0) return IA_OK;
+    IA_REQUIRE(d_packed_info && d_sdf && d_dists && (d_values || n_channels == 0) && (d_comp || n_channels == 0) && d_opacity,
+               IA_EINVAL, "ia_op_volrend: NULL argument");
+    IA_CHECK_CUDA(cudaSetDevice(c->device));
+    k_volrend<<<(unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_packed_info, d_sdf, d_dists, d_values,
+                                                                                 n_channels, beta, n_rays, d_weights, d_comp,
+                                                                                 d_opacity);
+    IA_LAUNCH_CHECK();
+    return IA_OK;
+}
+
+extern "C" int ia_op_volrend_backward(ia_ctx* c, const int32_t* d_packed_info, const float* d_sdf, const float* d_dists,
+                                      const float* d_values, int n_channels, float beta, const float* d_dcomp,
+                                      const float* d_dopacity, int64_t n_rays, float* d_g_sdf, float* d_g_values,
+                                      float* d_g_beta, void* stream) {
+    IA_REQUIRE(c && n_rays >= 0 && n_channels >= 0 && n_channels <= IA_VOLREND_MAX_C && beta > 0.f && d_g_beta, IA_EINVAL,
+               "ia_op_volrend_backward: bad argument (channels <= 16, beta > 0)");
+    if (n_rays == 0) return IA_OK;
+    IA_REQUIRE(d_packed_info && d_sdf && d_dists && (d_values || n_channels == 0) && (d_dcomp || n_channels == 0) && d_g_sdf,
+               IA_EINVAL, "ia_op_volrend_backward: NULL argument");
+    IA_CHECK_CUDA(cudaSetDevice(c->device));
+    k_volrend_backward<<<(unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        d_packed_info, d_sdf, d_dists, d_values, n_channels, beta, d_dcomp, d_dopacity, n_rays, d_g_sdf, d_g_values, d_g_beta);
+    IA_LAUNCH_CHECK();
+    return IA_OK;
+}
+
 extern "C" int ia_op_query_train(ia_ctx* c, const float* d_xd, int64_t n, float* d_sdf, float* d_xc, uint8_t* d_valid,
                                  float* d_grad, float* d_grad_cano, float* d_feature, float* d_J_inv, int32_t* d_best,
                                  void* stream) {

@@ -495,3 +495,91 @@ __global__ void __launch_bounds__(256) k_shade_fields_backward(const __grid_cons
     for (int i = threadIdx.x; i < IA_SHADE_GRAD_FLOATS; i += blockDim.x)
         if (gw[i] != 0.f) atomicAdd(&g_mlp[i], gw[i]);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Training-mode building block: compositing along the primary rays and its backward.
+//   alpha_i = 1 - exp(-sigma(sdf_i) dist_i),  sigma = Laplace-CDF density        models/rf/density.py:17-34; intrinsic_avatar.py:390-394
+//   w_i = alpha_i prod_{j<i} (1 - alpha_j)                                       nerfacc 0.5.3 render_weight_from_alpha
+//   comp[c] = sum_i w_i value_i[c],  opacity = sum_i w_i                         nerfacc accumulate_along_rays
+// as `rendering_with_normals_mats_sdf` strings them together (models/volrend.py:336-364); the reference differentiates the
+// chain with autograd (nerfacc's custom backward for the weights).  One thread per ray, samples in packed order.
+//   dL/dalpha_i = dL/dw_i T_i - (sum_{j>i} dL/dw_j w_j) / (1 - alpha_i)
+__device__ __forceinline__ float ia_sigma(float sdf, float beta) {
+    const float sgn = (sdf > 0.0f) ? 1.0f : ((sdf < 0.0f) ? -1.0f : 0.0f);
+    return (1.0f / beta) * (0.5f + 0.5f * sgn * expm1f(-fabsf(sdf) / beta));
+}
+
+__global__ void __launch_bounds__(128) k_volrend(const int* __restrict__ packed_info, const float* __restrict__ sdf,
+                                                 const float* __restrict__ dists, const float* __restrict__ values, int C,
+                                                 float beta, long long n_rays, float* __restrict__ weights,
+                                                 float* __restrict__ comp, float* __restrict__ opacity) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    const int s = packed_info[r * 2], cnt = packed_info[r * 2 + 1];
+    float acc[IA_VOLREND_MAX_C];
+#pragma unroll
+    for (int c = 0; c < IA_VOLREND_MAX_C; c++) acc[c] = 0.f;
+    float T = 1.0f, op = 0.f;
+    for (int i = s; i < s + cnt; i++) {
+        const float a = ia_alpha(sdf[i], dists[i], beta);
+        const float w = T * a;
+        T *= (1.0f - a);
+        if (weights) weights[i] = w;
+        op += w;
+#pragma unroll
+        for (int c = 0; c < IA_VOLREND_MAX_C; c++)
+            if (c < C) acc[c] = fmaf(w, values[(size_t)i * C + c], acc[c]);
+    }
+    opacity[r] = op;
+#pragma unroll
+    for (int c = 0; c < IA_VOLREND_MAX_C; c++)
+        if (c < C) comp[r * C + c] = acc[c];
+}
+
+__global__ void __launch_bounds__(128) k_volrend_backward(const int* __restrict__ packed_info, const float* __restrict__ sdf,
+                                                          const float* __restrict__ dists, const float* __restrict__ values,
+                                                          int C, float beta, const float* __restrict__ d_comp,
+                                                          const float* __restrict__ d_opacity, long long n_rays,
+                                                          float* __restrict__ g_sdf, float* __restrict__ g_values,
+                                                          float* __restrict__ g_beta) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float gb = 0.f;
+    if (r < n_rays) {
+        const int s = packed_info[r * 2], cnt = packed_info[r * 2 + 1];
+        float dc[IA_VOLREND_MAX_C];
+#pragma unroll
+        for (int c = 0; c < IA_VOLREND_MAX_C; c++) dc[c] = c < C ? d_comp[r * C + c] : 0.f;
+        const float dop = d_opacity ? d_opacity[r] : 0.f;
+        // forward: the transmittance in front of every sample, parked in g_sdf
+        float T = 1.0f;
+        for (int i = s; i < s + cnt; i++) {
+            g_sdf[i] = T;
+            T *= (1.0f - ia_alpha(sdf[i], dists[i], beta));
+        }
+        // reverse: suffix sum of dL/dw_j w_j
+        float suffix = 0.f;
+        for (int i = s + cnt - 1; i >= s; i--) {
+            const float sd = sdf[i], dist = dists[i];
+            const float sigma = ia_sigma(sd, beta);
+            const float a = 1.0f - expf(-sigma * dist);
+            const float Ti = g_sdf[i];
+            const float w = Ti * a;
+            float dw = dop;
+#pragma unroll
+            for (int c = 0; c < IA_VOLREND_MAX_C; c++)
+                if (c < C) {
+                    dw = fmaf(dc[c], values[(size_t)i * C + c], dw);
+                    if (g_values) g_values[(size_t)i * C + c] = w * dc[c];
+                }
+            const float da = dw * Ti - suffix / fmaxf(1.0f - a, 1e-10f);
+            suffix = fmaf(dw, w, suffix);
+            // alpha = 1 - exp(-sigma dist);  sigma = (1/beta)(1/2 + 1/2 sgn(s) expm1(-|s| / beta))
+            const float dsig = da * dist * (1.0f - a);
+            const float e = expf(-fabsf(sd) / beta);
+            g_sdf[i] = sd == 0.0f ? 0.0f : dsig * (-0.5f * e / (beta * beta));
+            gb += dsig * (-sigma / beta + 0.5f * sd * e / (beta * beta * beta));
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) gb += __shfl_xor_sync(0xffffffffu, gb, o);
+    if ((threadIdx.x & 31) == 0 && gb != 0.f) atomicAdd(g_beta, gb);
+}

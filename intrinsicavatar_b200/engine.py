@@ -39,6 +39,8 @@ _ARGTYPES = {
     "ia_op_geometry_backward": [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
     "ia_op_deform_backward": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "ia_op_query_train": [_vp, _vp, _i64] + [_vp] * 9,
+    "ia_op_volrend": [_vp, _vp, _vp, _vp, _vp, _i32, _cf32, _i64, _vp, _vp, _vp, _vp],
+    "ia_op_volrend_backward": [_vp, _vp, _vp, _vp, _vp, _i32, _cf32, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
     "ia_op_shade_fields_backward": [_vp] * 7 + [_i64] + [_vp] * 6,
     "ia_op_query_backward": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "ia_op_traverse": [_vp, _vp, _vp, _i64, _cf32, _cf32, _cf32] + [_vp] * 9 + [_vp],
@@ -434,6 +436,29 @@ class RenderEngine:
         rad, o = net(0, 67, 3, 4)
         mat, o = net(o, 48, 5, 8)
         return {"hash": g_hash, "rad": rad, "mat": mat, "x": g_x, "feature": g_f, "normal": g_n}
+
+    def op_volrend(self, packed_info, sdf, dists, values, beta):
+        """Laplace-density alpha, nerfacc weights and accumulation along packed rays: (weights [m], comp [n_rays,C], opacity)."""
+        pi = packed_info.to(self.dev, torch.int32).contiguous()
+        sdf, dists, values = [t.to(self.dev, torch.float32).contiguous() for t in (sdf, dists, values)]
+        n_rays, C = pi.shape[0], values.shape[1]
+        w = torch.empty_like(sdf)
+        comp, op = torch.empty(n_rays, C, device=self.dev), torch.empty(n_rays, device=self.dev)
+        check(self.lib.ia_op_volrend(self.h, ptr(pi), ptr(sdf), ptr(dists), ptr(values), C, float(beta), n_rays, ptr(w),
+                                     ptr(comp), ptr(op), _stream()), "ia_op_volrend")
+        return w, comp, op
+
+    def op_volrend_backward(self, packed_info, sdf, dists, values, beta, d_comp, d_opacity=None):
+        """Backward of ``op_volrend``: (g_sdf [m], g_values [m,C], g_beta [1])."""
+        pi = packed_info.to(self.dev, torch.int32).contiguous()
+        sdf, dists, values, d_comp = [t.to(self.dev, torch.float32).contiguous() for t in (sdf, dists, values, d_comp)]
+        d_op = d_opacity.to(self.dev, torch.float32).contiguous() if d_opacity is not None else None
+        n_rays, C = pi.shape[0], values.shape[1]
+        g_sdf, g_val, g_beta = torch.zeros_like(sdf), torch.zeros_like(values), torch.zeros(1, device=self.dev)
+        check(self.lib.ia_op_volrend_backward(self.h, ptr(pi), ptr(sdf), ptr(dists), ptr(values), C, float(beta), ptr(d_comp),
+                                              ptr(d_op), n_rays, ptr(g_sdf), ptr(g_val), ptr(g_beta), _stream()),
+              "ia_op_volrend_backward")
+        return g_sdf, g_val, g_beta
 
     def op_geometry(self, xc):
         """Canonical SDF of points [n,3] on the tensor-core path of the wavefront integrator's geometry phase."""

@@ -815,6 +815,59 @@ def test_shade_fields_backward_vs_autograd(eng, scene):
     assert float(e0["hash"].abs().max()) == 0.0 and e0["x"].shape == (0, 3)
 
 
+def test_volrend_forward_backward(eng, scene):
+    """ia_op_volrend / ia_op_volrend_backward (training path): Laplace-density alpha + nerfacc weights +
+    accumulation along packed rays.  Forward against the oracle (alpha_from_sdf, restated render_weight_from_alpha /
+    accumulate_along_rays), backward against torch autograd through the same chain: gradients of the sdf, the accumulated
+    values and beta.  Ragged rays, among them empty ones and a single-sample one."""
+    g = torch.Generator().manual_seed(17)
+    counts = torch.randint(0, 40, (300,), generator=g)
+    counts[:3] = torch.tensor([0, 1, 0])
+    starts = torch.cumsum(counts, 0) - counts
+    pi = torch.stack([starts, counts], 1).int()
+    m, C = int(counts.sum()), 7
+    beta = 0.0123
+    sdf = (torch.rand(m, generator=g) - 0.35) * 0.08           # both signs, |sdf| up to a few beta
+    dists = 0.005 + 0.02 * torch.rand(m, generator=g)
+    vals = torch.randn(m, C, generator=g)
+    w, comp, op = eng.op_volrend(pi, sdf, dists, vals, beta)
+    F_ = scene.fields
+    old_beta, F_.beta = F_.beta, beta
+    try:
+        alpha = F_.alpha_from_sdf(sdf, dists)
+    finally:
+        F_.beta = old_beta
+    ow, _ = oops.render_weight_from_alpha(alpha, pi)
+    ridx = torch.repeat_interleave(torch.arange(300), counts)
+    assert float((w.cpu() - ow).abs().max()) < 2e-6
+    assert float((comp.cpu() - oops.accumulate_along_rays(ow, vals, ridx, 300)).abs().max()) < 2e-5
+    assert float((op.cpu() - oops.accumulate_along_rays(ow, None, ridx, 300).reshape(-1)).abs().max()) < 2e-6
+    # autograd restatement
+    s_, v_, b_ = sdf.clone().requires_grad_(True), vals.clone().requires_grad_(True), torch.tensor(beta, requires_grad=True)
+    sigma = (1.0 / b_) * (0.5 + 0.5 * torch.sign(s_) * torch.expm1(-s_.abs() / b_))
+    a = 1.0 - torch.exp(-sigma * dists)
+    d_comp, d_op = torch.randn(300, C, generator=g), torch.randn(300, generator=g)
+    loss = 0.0
+    for r in range(300):
+        s0, c0 = int(starts[r]), int(counts[r])
+        if c0 == 0:
+            continue
+        ar = a[s0:s0 + c0]
+        T = torch.cumprod(torch.cat([torch.ones(1), 1.0 - ar[:-1]]), 0)
+        wr = T * ar
+        loss = loss + ((wr[:, None] * v_[s0:s0 + c0]).sum(0) * d_comp[r]).sum() + wr.sum() * d_op[r]
+    loss.backward()
+    g_sdf, g_val, g_beta = eng.op_volrend_backward(pi, sdf, dists, vals, beta, d_comp, d_op)
+    def rel(x, y):
+        return float(torch.linalg.norm(x.cpu().reshape(-1) - y.reshape(-1)) / torch.linalg.norm(y).clamp_min(1e-20))
+    assert rel(g_sdf, s_.grad) < 1e-4, rel(g_sdf, s_.grad)
+    assert rel(g_val, v_.grad) < 1e-5
+    assert abs(float(g_beta.cpu()) - float(b_.grad)) < 1e-4 * abs(float(b_.grad)), (float(g_beta.cpu()), float(b_.grad))
+    # no rays
+    w0, c0_, o0 = eng.op_volrend(torch.zeros(0, 2, dtype=torch.int32), torch.zeros(0), torch.zeros(0), torch.zeros(0, 3), beta)
+    assert c0_.shape == (0, 3) and o0.shape == (0,)
+
+
 def test_occupancy_ema_update_vs_oracle(scene):
     """ia_update_occupancy_ema (training-time grid update, SURVEY 8f.4: OccGridEstimator._update driven by
     IntrinsicAvatarModel.update_step, models/occ_grid/temporal_occ_grid.py:369-411, models/intrinsic_avatar.py:232-264) against
