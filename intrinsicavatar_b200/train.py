@@ -1,19 +1,28 @@
-"""Training-mode seam of the fused query: ``SNARFDeformer.deform(pts, model, eval_mode=False)``
-(models/deformers/snarf_deformer.py:170-261) as ONE differentiable call.
+"""Training-mode seam of the render path: the reference's differentiable graph for the radiance-field
+branch of ``forward_`` -- posed sample -> canonical root -> SDF / feature -> radiance + material networks -> Laplace-density
+volume rendering -- as three autograd nodes over the CUDA ops, and ``render_radiance`` which chains them.
 
-The reference builds the graph out of ``ForwardDeformer.forward`` (search under ``no_grad`` + the implicit-differentiation
-correction, models/deformers/fast_snarf/deformer_torch.py:34-76), ``VolumeSDF`` (tiny-cuda-nn hash grid + MLP,
-models/rf/geometry.py:147-172) and ``torch.min`` over the candidate roots, and lets autograd walk it.  Here the forward is
-``ia_op_query_train`` and the backward ``ia_op_query_backward`` (csrc/ia_train.cuh); this module only routes their
-buffers into autograd.  There is no fallback: without the CUDA library the calls raise.
+* ``fused_query``: ``SNARFDeformer.deform(pts, model, eval_mode=False)`` (models/deformers/snarf_deformer.py:170-261) as ONE
+  differentiable call.  The reference builds the graph out of ``ForwardDeformer.forward`` (search under ``no_grad`` + the
+  implicit-differentiation correction, models/deformers/fast_snarf/deformer_torch.py:34-76), ``VolumeSDF`` (tiny-cuda-nn hash
+  grid + MLP, models/rf/geometry.py:147-172) and ``torch.min`` over the candidate roots, and lets autograd walk it.  Here the
+  forward is ``ia_op_query_train`` and the backward ``ia_op_query_backward`` (+ ``ia_op_deform_backward`` for a gradient that
+  arrives on the canonical point itself), csrc/ia_train.cuh.
+* ``shade_fields``: ``VolumeRadiance`` + the material network at the canonical point (models/rf/radiance.py:82-135,
+  models/pbr/material.py:31-51): ``ia_op_shade_fields`` / ``ia_op_shade_fields_backward``.
+* ``volrend``: ``get_alpha`` + ``render_weight_from_alpha`` + ``accumulate_along_rays`` (models/rf/density.py:17-34,
+  models/volrend.py:336-364): ``ia_op_volrend`` / ``ia_op_volrend_backward``.
+
+This module only routes the ops' buffers into autograd.  There is no fallback: without the CUDA library the calls raise.
 
     sdf, feature, x_c, valid = fused_query(engine, xd, geo_hash, geo_w1, geo_b1, geo_w2, geo_b2, tfs)
 
-``geo_hash`` ... ``geo_b2`` are the tensors the engine's fields were set from (``RenderEngine.set_fields``: the hash table
-and the effective -- weight-norm folded -- MLP weights) and ``tfs`` [24,4,4] the bone transforms of ``set_pose``: they
-are graph leaves here, the VALUES are the engine's, so call ``set_fields`` / ``set_pose`` after every optimiser step.
-Gradients reach them from ``sdf`` and ``feature``; ``x_c`` and ``valid`` are returned without a graph (the reference's
-canonical points carry the correction's gradient too -- route it through ``engine.op_deform_backward`` if a loss reads them).
+The parameter tensors are the ones the engine's fields were set from (``RenderEngine.set_fields``: the hash tables and the
+effective -- weight-norm folded -- MLP weights) and ``tfs`` [24,4,4] the bone transforms of ``set_pose``: they are graph
+leaves here, the VALUES are the engine's, so call ``set_fields`` / ``set_pose`` after every optimiser step.
+
+Not differentiated: the SDF normal is a constant of the graph (the reference differentiates through it --
+second order -- for the eikonal loss and the radiance network's normal input), and so are the sample positions along the ray.
 """
 from __future__ import annotations
 
@@ -27,24 +36,120 @@ class _FusedQuery(torch.autograd.Function):
         ctx.engine = engine
         ctx.fwd = {k: fwd[k] for k in ("x_c", "valid", "J_inv")}
         ctx.meta = (geo_hash.shape, geo_hash.dtype, tfs.shape)
-        ctx.mark_non_differentiable(fwd["x_c"], fwd["valid"])
-        return fwd["sdf"], fwd["feature"], fwd["x_c"], fwd["valid"]
+        ctx.mark_non_differentiable(fwd["valid"], fwd["grad"])
+        return fwd["sdf"], fwd["feature"], fwd["x_c"], fwd["valid"], fwd["grad"]
 
     @staticmethod
-    def backward(ctx, g_sdf, g_feature, _g_xc, _g_valid):
-        n = ctx.fwd["x_c"].shape[0]
-        dev = ctx.fwd["x_c"].device
+    def backward(ctx, g_sdf, g_feature, g_xc, _g_valid, _g_normal):
+        x_c, valid, J_inv = ctx.fwd["x_c"], ctx.fwd["valid"], ctx.fwd["J_inv"]
+        n, dev = x_c.shape[0], x_c.device
         # the 13 network outputs at the arg-min root: `feature` IS the output vector (channel 0 = sdf, geometry.py:160-166)
         d_out = torch.zeros(n, 13, device=dev) if g_feature is None else g_feature.to(dev, torch.float32).clone()
         if g_sdf is not None:
             d_out[:, 0] += g_sdf.to(dev, torch.float32)
         g = ctx.engine.op_query_backward(ctx.fwd, d_out)
+        g_tfs3 = g["tfs"]
+        if g_xc is not None and n:
+            # a gradient on the canonical point itself reaches the bone transforms through the same implicit-differentiation
+            # correction; ia_op_deform_backward takes roots in groups of 13, so pad the list with invalid ones
+            pad = (-n) % 13
+            def grp(t, *shape):
+                return torch.cat([t, t.new_zeros((pad,) + t.shape[1:])]).reshape(-1, 13, *shape)
+            g_tfs3 = g_tfs3 + ctx.engine.op_deform_backward(grp(x_c, 3), grp(valid.to(torch.uint8)), grp(J_inv, 3, 3),
+                                                            grp(g_xc.to(dev, torch.float32), 3))
         hash_shape, hash_dtype, tfs_shape = ctx.meta
         g_tfs = torch.zeros(tfs_shape, device=dev)
-        g_tfs[..., :3, :] = g["tfs"].reshape(g_tfs[..., :3, :].shape)
+        g_tfs[..., :3, :] = g_tfs3.reshape(g_tfs[..., :3, :].shape)
         return (None, None, g["hash"].reshape(hash_shape).to(hash_dtype), g["w1"], g["b1"], g["w2"], g["b2"], g_tfs)
 
 
-def fused_query(engine, xd, geo_hash, geo_w1, geo_b1, geo_w2, geo_b2, tfs):
-    """Differentiable posed point -> (sdf [n], feature [n,13], x_c [n,3], valid [n]); see the module docstring."""
-    return _FusedQuery.apply(engine, xd, geo_hash, geo_w1, geo_b1, geo_w2, geo_b2, tfs)
+def fused_query(engine, xd, geo_hash, geo_w1, geo_b1, geo_w2, geo_b2, tfs, with_normal=False):
+    """Differentiable posed point -> (sdf [n], feature [n,13], x_c [n,3], valid [n]) and, ``with_normal``, the posed-space
+    SDF gradient [n,3] (a constant of the graph); see the module docstring.  Invalid points: sdf 1e5, no gradient."""
+    out = _FusedQuery.apply(engine, xd, geo_hash, geo_w1, geo_b1, geo_w2, geo_b2, tfs)
+    return out if with_normal else out[:4]
+
+
+SHADE_PARAMS = ("rad_hash",) + tuple(f"{net}_{t}{i}" for net in ("rad", "mat") for i in (1, 2, 3) for t in ("w", "b"))
+
+
+class _ShadeFields(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, xc, feature, view_world, normal_world, *params):
+        assert len(params) == len(SHADE_PARAMS)
+        a = [t.detach() for t in (xc, feature, view_world, normal_world)]
+        rgb, mat = engine.op_shade_fields(*a)
+        ctx.engine, ctx.a = engine, a
+        ctx.meta = (params[0].shape, params[0].dtype)
+        return rgb, mat
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_mat):
+        n, dev = ctx.a[0].shape[0], ctx.engine.dev
+        g_rgb = torch.zeros(n, 3, device=dev) if g_rgb is None else g_rgb
+        g_mat = torch.zeros(n, 5, device=dev) if g_mat is None else g_mat
+        g = ctx.engine.op_shade_fields_backward(*ctx.a, g_rgb, g_mat)
+        hash_shape, hash_dtype = ctx.meta
+        weights = [g[net][f"{t}{i}"] for net in ("rad", "mat") for i in (1, 2, 3) for t in ("w", "b")]
+        return (None, g["x"], g["feature"], None, g["normal"], g["hash"].reshape(hash_shape).to(hash_dtype), *weights)
+
+
+def shade_fields(engine, xc, feature, view_world, normal_world, params: dict):
+    """Differentiable (rgb [n,3], material [n,5]) of the radiance and material networks at canonical points ``xc`` with the
+    geometry ``feature``, the ray direction and the world normal.  ``params``: the folded weights by name (``SHADE_PARAMS``).
+    Gradients reach ``xc``, ``feature``, ``normal_world`` and every entry of ``params``."""
+    return _ShadeFields.apply(engine, xc, feature, view_world, normal_world, *[params[k] for k in SHADE_PARAMS])
+
+
+class _VolRend(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, packed_info, sdf, dists, values, beta):
+        b = float(beta)
+        w, comp, op = engine.op_volrend(packed_info, sdf.detach(), dists, values.detach(), b)
+        ctx.engine, ctx.a = engine, (packed_info, sdf.detach(), dists, values.detach(), b)
+        ctx.beta_like = beta if torch.is_tensor(beta) else None
+        ctx.mark_non_differentiable(w)
+        return w, comp, op
+
+    @staticmethod
+    def backward(ctx, _g_w, g_comp, g_op):
+        pi, sdf, dists, values, b = ctx.a
+        if g_comp is None:
+            g_comp = torch.zeros(pi.shape[0], values.shape[1], device=ctx.engine.dev)
+        g_sdf, g_val, g_beta = ctx.engine.op_volrend_backward(pi, sdf, dists, values, b, g_comp, g_op)
+        bl = ctx.beta_like
+        return None, None, g_sdf, None, g_val, (g_beta.reshape(bl.shape).to(bl.dtype).to(bl.device) if bl is not None else None)
+
+
+def volrend(engine, packed_info, sdf, dists, values, beta):
+    """Differentiable (weights [m] -- no graph --, comp [n_rays,C], opacity [n_rays]) along packed rays (``packed_info``
+    [n_rays,2] = first sample, count).  Gradients reach ``sdf``, ``values`` and ``beta`` (a tensor, e.g. the Laplace density's
+    parameter, or a float)."""
+    return _VolRend.apply(engine, packed_info, sdf, dists, values, beta)
+
+
+def render_radiance(engine, params: dict, tfs, w2s, rays_o, rays_d, packed_info, t_starts, t_ends, beta):
+    """The radiance-field branch of the training forward (models/intrinsic_avatar.py:1068-1182: ``rgb_normal_mats_alpha_fn`` at
+    the interval midpoints, then ``rendering_with_normals_mats_sdf``) for samples already placed on the rays: dict with
+    ``comp_rgb`` [n_rays,3], ``comp_mats`` [n_rays,5], ``comp_normal`` [n_rays,3] (unnormalised accumulation), ``depth``,
+    ``opacity``, ``weights`` and the per-sample ``sdf`` / ``valid``.  ``params``: folded weights by name (geometry + shading);
+    ``tfs`` the bone transforms and ``w2s`` [4,4] the world-to-SMPL transform of ``set_pose`` (rays are SMPL-space; view direction
+    and normal go to the networks in world space, ``transform_dirs_s2w``); ``beta`` the Laplace density's scale.  A loss on the result back-propagates to all of them."""
+    dev = engine.dev
+    pi = packed_info.to(dev, torch.int32)
+    counts = pi[:, 1].long()
+    ridx = torch.repeat_interleave(torch.arange(pi.shape[0], device=dev), counts)
+    t0, t1 = t_starts.to(dev, torch.float32).reshape(-1), t_ends.to(dev, torch.float32).reshape(-1)
+    o, d = rays_o.to(dev, torch.float32)[ridx], rays_d.to(dev, torch.float32)[ridx]
+    t_mid = 0.5 * (t0 + t1)
+    xd = o + d * t_mid[:, None]
+    sdf, feature, x_c, valid, normal = fused_query(engine, xd, *[params[k] for k in ("geo_hash", "geo_w1", "geo_b1", "geo_w2",
+                                                                                   "geo_b2")], tfs, with_normal=True)
+    rot = torch.as_tensor(w2s, dtype=torch.float32, device=dev)[:3, :3]
+    view_w = torch.nn.functional.normalize(d @ rot, dim=-1, eps=1e-6)
+    normal_w = torch.nn.functional.normalize(normal @ rot, dim=-1, eps=1e-6)
+    rgb, mat = shade_fields(engine, x_c, feature, view_w, normal_w, params)
+    values = torch.cat([rgb, mat, normal_w, t_mid[:, None]], dim=-1)
+    weights, comp, opacity = volrend(engine, pi, sdf, t1 - t0, values, beta)
+    return {"comp_rgb": comp[:, 0:3], "comp_mats": comp[:, 3:8], "comp_normal": comp[:, 8:11], "depth": comp[:, 11],
+            "opacity": opacity, "weights": weights, "sdf": sdf, "valid": valid}
