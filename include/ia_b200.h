@@ -354,6 +354,28 @@ int ia_op_brdf(ia_ctx* ctx, const float* d_wi, const float* d_n, const float* d_
 int ia_op_bsdf_sample_pdf(ia_ctx* ctx, const float* d_wi, const float* d_n, const float* d_rough,
                           const float* d_albedo, const float* d_metal, const float* d_sample,
                           const float* d_wo_query, int64_t n, float* d_wo, float* d_pdf, void* stream);
+/* Training-mode building block: the differentiable part of the physically based integrators.  The reference
+ * traces the secondary rays under torch.no_grad() (models/intrinsic_avatar.py:673-706 pbr_uniform_light_forward -- the training
+ * default, configs/config.yaml:46 --, :575-640, :763-800, :880-896), so light direction d_wo, inverse pdf, and
+ * Li = em_li * transmittance + indirect radiance enter as per-sample arrays; what autograd walks is MultiLobe.eval
+ * (lib/torch_pbr/bxdf.py:111-146, 217-265, 321-330), Lo_diff = Li diff inv_pdf, Lo_spec = Li spec inv_pdf,
+ * Lo = (1 - metallic) albedo Lo_diff + Lo_spec (:736-751), with diff = spec = 0 where n.wo <= 1e-6 (:690).
+ * All arrays are per shading sample: d_wi (towards the viewer), d_n (unit normal), d_wo, d_albedo, d_Li [n,3]; d_rough, d_metal,
+ * d_inv_pdf [n].  ia_op_pbr_shade writes d_Lo and (unless NULL) d_Lo_diff, d_Lo_spec [n,3].  ia_op_pbr_shade_backward takes the
+ * upstream gradients d_dLo and (may be NULL) d_dLo_diff, d_dLo_spec and writes d_g_n [n,3] (defined up to a component along n,
+ * which the backward of the normalisation that produced n removes), d_g_rough [n], d_g_albedo [n,3], d_g_metal [n], d_g_Li [n,3]. */
+int ia_op_pbr_shade(ia_ctx* ctx, const float* d_wi, const float* d_n, const float* d_wo, const float* d_rough,
+                    const float* d_albedo, const float* d_metal, const float* d_Li, const float* d_inv_pdf, int64_t n,
+                    float* d_Lo, float* d_Lo_diff, float* d_Lo_spec, void* stream);
+int ia_op_pbr_shade_backward(ia_ctx* ctx, const float* d_wi, const float* d_n, const float* d_wo, const float* d_rough,
+                             const float* d_albedo, const float* d_metal, const float* d_Li, const float* d_inv_pdf,
+                             const float* d_dLo, const float* d_dLo_diff, const float* d_dLo_spec, int64_t n, float* d_g_n,
+                             float* d_g_rough, float* d_g_albedo, float* d_g_metal, float* d_g_Li, void* stream);
+/* Backward of EnvironmentLightTensor.eval (lib/torch_pbr/light.py:298-339, bilinear grid_sample, align_corners, border): ADDS
+ * the gradient d_dem [n,3] on the emission of the WORLD directions d_dirs_world [n,3] into d_g_env [H,W,3], the texels of the
+ * map of the last ia_set_light* call (the trainable light's softplus stays with the caller).                                  */
+int ia_op_env_backward(ia_ctx* ctx, const float* d_dirs_world, const float* d_dem, int64_t n, float* d_g_env, void* stream);
+
 /* EnvironmentLightTensor.sample / pdf / eval per direction, on the tables of the last ia_set_light*
  * call (light.py:259-446): d_u [n,2] -> d_dirs_world_out [n,3] (may be NULL); d_dirs_world [n,3] ->
  * d_pdf_out [n], d_em_out [n,3] (d_dirs_world NULL: the directions just sampled are used).             */

@@ -40,7 +40,7 @@ EXPORTS = [
     "ia_set_render_config", "ia_set_secondary_sampling", "ia_reserve_samples", "ia_build_occupancy", "ia_set_occupancy", "ia_set_light", "ia_set_light_uniform", "ia_render", "ia_get_counters", "ia_set_timing", "ia_get_timings",
     "ia_op_precompute", "ia_op_broyden", "ia_op_query", "ia_op_shade_fields", "ia_op_geometry", "ia_op_geometry_backward", "ia_op_deform_backward", "ia_op_shade_fields_backward", "ia_op_volrend", "ia_op_volrend_backward", "ia_op_query_train", "ia_op_query_backward", "ia_op_traverse",
     "ia_op_ray_resampling", "ia_op_ray_resampling_merge", "ia_op_ray_resampling_sdf_fine", "ia_op_ray_resampling_fine", "ia_op_unpack_info",
-    "ia_op_secondary", "ia_op_brdf", "ia_op_bsdf_sample_pdf", "ia_op_env",
+    "ia_op_secondary", "ia_op_brdf", "ia_op_bsdf_sample_pdf", "ia_op_env", "ia_op_pbr_shade", "ia_op_pbr_shade_backward", "ia_op_env_backward",
     "ia_make_rays", "ia_pack_rgb8", "ia_pack_grid8", "ia_update_occupancy_ema",
 ]
 

@@ -1190,3 +1190,4 @@ extern "C" int ia_op_deform_backward(ia_ctx* c, const float* d_xc, const uint8_t
 }
 
 #include "ia_render.cuh"
+#include "ia_train_pbr.cuh"

@@ -39,6 +39,9 @@ _ARGTYPES = {
     "ia_op_geometry_backward": [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
     "ia_op_deform_backward": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "ia_op_query_train": [_vp, _vp, _i64] + [_vp] * 9,
+    "ia_op_pbr_shade": [_vp] * 9 + [_i64] + [_vp] * 4,
+    "ia_op_pbr_shade_backward": [_vp] * 12 + [_i64] + [_vp] * 6,
+    "ia_op_env_backward": [_vp, _vp, _vp, _i64, _vp, _vp],
     "ia_op_volrend": [_vp, _vp, _vp, _vp, _vp, _i32, _cf32, _i64, _vp, _vp, _vp, _vp],
     "ia_op_volrend_backward": [_vp, _vp, _vp, _vp, _vp, _i32, _cf32, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
     "ia_op_shade_fields_backward": [_vp] * 7 + [_i64] + [_vp] * 6,
@@ -459,6 +462,42 @@ class RenderEngine:
                                               ptr(d_op), n_rays, ptr(g_sdf), ptr(g_val), ptr(g_beta), _stream()),
               "ia_op_volrend_backward")
         return g_sdf, g_val, g_beta
+
+    def _pbr_args(self, wi, n, wo, rough, albedo, metal, Li, inv_pdf):
+        v3 = [t.to(self.dev, torch.float32).reshape(-1, 3).contiguous() for t in (wi, n, wo)]
+        m = v3[0].shape[0]
+        s1 = [t.to(self.dev, torch.float32).reshape(-1).contiguous() for t in (rough, metal, inv_pdf)]
+        al, Li = [t.to(self.dev, torch.float32).reshape(-1, 3).contiguous() for t in (albedo, Li)]
+        assert all(t.shape[0] == m for t in v3 + s1 + [al, Li])
+        return m, [*v3, s1[0], al, s1[1], Li, s1[2]]
+
+    def op_pbr_shade(self, wi, n, wo, rough, albedo, metal, Li, inv_pdf):
+        """The integrators' differentiable combine (training path): (Lo, Lo_diff, Lo_spec) [n,3] of one light direction per
+        shading sample -- MultiLobe.eval under the cosine mask, times Li and the inverse pdf."""
+        m, a = self._pbr_args(wi, n, wo, rough, albedo, metal, Li, inv_pdf)
+        Lo, Ld, Ls = (torch.empty(m, 3, device=self.dev) for _ in range(3))
+        check(self.lib.ia_op_pbr_shade(self.h, *[ptr(t) for t in a], m, ptr(Lo), ptr(Ld), ptr(Ls), _stream()), "ia_op_pbr_shade")
+        return Lo, Ld, Ls
+
+    def op_pbr_shade_backward(self, wi, n, wo, rough, albedo, metal, Li, inv_pdf, d_Lo, d_Lo_diff=None, d_Lo_spec=None):
+        """Backward of ``op_pbr_shade``: dict with ``normal`` [n,3], ``rough`` [n], ``albedo`` [n,3], ``metal`` [n], ``Li`` [n,3]."""
+        m, a = self._pbr_args(wi, n, wo, rough, albedo, metal, Li, inv_pdf)
+        up = [None if t is None else t.to(self.dev, torch.float32).reshape(m, 3).contiguous() for t in (d_Lo, d_Lo_diff, d_Lo_spec)]
+        g_n, g_al, g_Li = (torch.empty(m, 3, device=self.dev) for _ in range(3))
+        g_r, g_m = torch.empty(m, device=self.dev), torch.empty(m, device=self.dev)
+        check(self.lib.ia_op_pbr_shade_backward(self.h, *[ptr(t) for t in a], *[ptr(t) for t in up], m, ptr(g_n), ptr(g_r),
+                                                ptr(g_al), ptr(g_m), ptr(g_Li), _stream()), "ia_op_pbr_shade_backward")
+        return {"normal": g_n, "rough": g_r, "albedo": g_al, "metal": g_m, "Li": g_Li}
+
+    def op_env_backward(self, dirs_world, d_em, env_shape):
+        """Gradient of  sum <d_em, emitter.eval(dirs_world)>  with respect to the texels of the map set by ``set_light*``
+        (``env_shape`` = (H, W) of that map)."""
+        d = dirs_world.to(self.dev, torch.float32).reshape(-1, 3).contiguous()
+        g = d_em.to(self.dev, torch.float32).reshape(-1, 3).contiguous()
+        assert d.shape == g.shape
+        g_env = torch.zeros(int(env_shape[0]), int(env_shape[1]), 3, device=self.dev)
+        check(self.lib.ia_op_env_backward(self.h, ptr(d), ptr(g), d.shape[0], ptr(g_env), _stream()), "ia_op_env_backward")
+        return g_env
 
     def op_geometry(self, xc):
         """Canonical SDF of points [n,3] on the tensor-core path of the wavefront integrator's geometry phase."""

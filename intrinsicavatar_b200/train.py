@@ -153,3 +153,70 @@ def render_radiance(engine, params: dict, tfs, w2s, rays_o, rays_d, packed_info,
     weights, comp, opacity = volrend(engine, pi, sdf, t1 - t0, values, beta)
     return {"comp_rgb": comp[:, 0:3], "comp_mats": comp[:, 3:8], "comp_normal": comp[:, 8:11], "depth": comp[:, 11],
             "opacity": opacity, "weights": weights, "sdf": sdf, "valid": valid}
+
+
+class _PbrShade(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, wi, n, wo, rough, albedo, metal, Li, inv_pdf):
+        a = [t.detach() for t in (wi, n, wo, rough, albedo, metal, Li, inv_pdf)]
+        ctx.engine, ctx.a = engine, a
+        ctx.shapes = (rough.shape, metal.shape)
+        return engine.op_pbr_shade(*a)
+
+    @staticmethod
+    def backward(ctx, g_Lo, g_Ld, g_Ls):
+        m, dev = ctx.a[0].shape[0], ctx.engine.dev
+        g = ctx.engine.op_pbr_shade_backward(*ctx.a, torch.zeros(m, 3, device=dev) if g_Lo is None else g_Lo, g_Ld, g_Ls)
+        return (None, None, g["normal"], None, g["rough"].reshape(ctx.shapes[0]), g["albedo"], g["metal"].reshape(ctx.shapes[1]),
+                g["Li"], None)
+
+
+def pbr_shade(engine, wi, n, wo, rough, albedo, metal, Li, inv_pdf):
+    """Differentiable (Lo, Lo_diff, Lo_spec) [n,3] of one light direction ``wo`` per shading sample: ``MultiLobe.eval`` under the
+    cosine mask times the incoming radiance ``Li`` and the inverse pdf (models/intrinsic_avatar.py:708-751).  Gradients reach
+    the normal (pass the output of a normalisation: the component along ``n`` is left to its backward), ``rough``, ``albedo``,
+    ``metal`` and ``Li``."""
+    return _PbrShade.apply(engine, wi, n, wo, rough, albedo, metal, Li, inv_pdf)
+
+
+class _EnvEval(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, dirs_world, env):
+        ctx.engine, ctx.dirs, ctx.meta = engine, dirs_world.detach(), (env.shape, env.dtype, env.device)
+        return engine.op_env(dirs_world=ctx.dirs)[2]
+
+    @staticmethod
+    def backward(ctx, g_em):
+        shape, dtype, device = ctx.meta
+        g = ctx.engine.op_env_backward(ctx.dirs, g_em, shape[:2])
+        return None, None, g.reshape(shape).to(dtype).to(device)
+
+
+def env_eval(engine, dirs_world, env):
+    """Differentiable ``EnvironmentLightTensor.eval`` (lib/torch_pbr/light.py:298-339): emission [n,3] of world directions on the
+    map the engine's light was set from; ``env`` [H,W,3] is that map as a graph leaf (or the softplus of the trainable one)."""
+    return _EnvEval.apply(engine, dirs_world, env)
+
+
+def pbr_light(engine, env, w2s, normal, albedo, rough, metal, positions, view_dirs, light_dirs, inv_pdf, gi=True):
+    """One light direction per shading sample, the way the training-time integrators combine it (``pbr_uniform_light_forward``,
+    models/intrinsic_avatar.py:654-760, the training default; its siblings differ in where ``light_dirs`` / ``inv_pdf`` come
+    from): secondary rays traced without a graph (transmittance and indirect radiance are constants, :673-706), emission
+    looked up in world space, BRDF and combine differentiable.  ``normal`` unit, SMPL space, like ``view_dirs`` (camera ray
+    direction), ``light_dirs`` and ``positions``.  Returns (Lo, Lo_diff, Lo_spec, vis) per sample."""
+    dev = engine.dev
+    n_, wo = normal.to(dev, torch.float32), light_dirs.to(dev, torch.float32)
+    with torch.no_grad():
+        cos_mask = (n_ * wo).sum(-1) > 1e-6
+        tr = torch.zeros(wo.shape[0], device=dev)
+        rgb = torch.zeros(wo.shape[0], 3, device=dev)
+        if bool(cos_mask.any()):
+            t_, r_ = engine.op_secondary(positions.to(dev, torch.float32)[cos_mask], wo[cos_mask], gi=gi)
+            tr[cos_mask], rgb[cos_mask] = t_.clamp(0.0, 1.0), r_
+        rot = torch.as_tensor(w2s, dtype=torch.float32, device=dev)[:3, :3]
+        dirs_world = torch.nn.functional.normalize(wo @ rot, dim=-1, eps=1e-6)
+    em = env_eval(engine, dirs_world, env)
+    Li = em * tr[:, None] + rgb if gi else em * tr[:, None]
+    Lo, Lo_diff, Lo_spec = pbr_shade(engine, -view_dirs.to(dev, torch.float32), n_, wo, rough, albedo, metal, Li,
+                                     inv_pdf.to(dev, torch.float32))
+    return Lo, Lo_diff, Lo_spec, 2.0 * tr[:, None].expand(-1, 3)

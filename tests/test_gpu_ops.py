@@ -950,6 +950,76 @@ def test_render_radiance_training_step(eng, posed, scene):
         assert v < 1e-4, (kk, v)                                      # measured: 1e-7 .. 7e-6
 
 
+def test_pbr_light_training_backward(scene, posed):
+    """train.pbr_light: the differentiable part of the training-time integrators (pbr_uniform_light_forward, the
+    training default) -- MultiLobe.eval under the cosine mask, the environment lookup, Li = em tr + indirect, Lo = kd Lo_diff +
+    Lo_spec -- on ia_op_pbr_shade / ia_op_pbr_shade_backward / ia_op_env_backward, with the secondary rays traced without a
+    graph as the reference does.  Forward against the oracle's multilobe_eval / EnvLight.eval (pinned to the reference's
+    modules by the bsdf / env goldens), backward against torch autograd through them: gradients of the (un-normalised) normal,
+    albedo, roughness, metallic and the environment map's texels for a random upstream gradient on Lo, Lo_diff and Lo_spec."""
+    from intrinsicavatar_b200.train import pbr_light
+    import torch.nn.functional as F
+    R = posed["oracle"]
+    e = scene.engine()
+    fr = posed["frame"]
+    e.set_pose(fr["tfs"], fr["w2s"])
+    e.set_occupancy(fr["deformed_bbox"], R.binaries)
+    g = torch.Generator().manual_seed(41)
+    env0 = torch.rand(32, 64, 3, generator=g) * 2.0 + 0.05
+    e.set_light_uniform(env0, 16, 32)
+    n = 6000
+    bb = torch.as_tensor(fr["deformed_bbox"])
+    c = (bb[:3] + bb[3:]) / 2
+    pos = c + F.normalize(torch.randn(n, 3, generator=g), dim=-1) * (0.25 + 0.4 * torch.rand(n, 1, generator=g))
+    n_raw0 = torch.randn(n, 3, generator=g) * (0.5 + torch.rand(n, 1, generator=g))
+    view = -F.normalize(F.normalize(n_raw0, dim=-1) + 0.8 * torch.randn(n, 3, generator=g), dim=-1)   # mostly facing the normal
+    light = opbr.uniform_sphere_stratified(16, 32)[torch.randint(0, 512, (n,), generator=g)]
+    inv_pdf = torch.full((n,), 4.0 * np.pi)
+    lv = {"n_raw": n_raw0, "albedo": torch.rand(n, 3, generator=g), "rough": 0.05 + 0.9 * torch.rand(n, generator=g),
+          "metal": torch.rand(n, generator=g), "env": env0}
+    P = {k: v.clone().cuda().requires_grad_(True) for k, v in lv.items()}
+    Q = {k: v.clone().requires_grad_(True) for k, v in lv.items()}
+    ups = [torch.randn(n, 3, generator=g) for _ in range(3)]
+    for gi in (True, False):
+        for t in list(P.values()) + list(Q.values()):
+            t.grad = None
+        normal = F.normalize(P["n_raw"], dim=-1, eps=1e-6)
+        Lo, Ld, Ls, vis = pbr_light(e, P["env"], R.w2s, normal, P["albedo"], P["rough"], P["metal"], pos, view, light, inv_pdf,
+                                    gi=gi)
+        sum((a * u.cuda()).sum() for a, u in zip((Lo, Ld, Ls), ups)).backward()
+        # the reference's graph on the CPU; transmittance and indirect radiance are the device's (constants of the graph)
+        nq = F.normalize(Q["n_raw"], dim=-1, eps=1e-6)
+        cm = ((nq * light).sum(-1) > 1e-6).detach()
+        assert torch.equal(cm, ((normal.detach().cpu() * light).sum(-1) > 1e-6))
+        tr, rgb = torch.zeros(n), torch.zeros(n, 3)
+        t_, r_ = e.op_secondary(pos[cm], light[cm], gi=gi)
+        tr[cm], rgb[cm] = t_.cpu().clamp(0.0, 1.0), r_.cpu()
+        assert float((vis.cpu() - 2.0 * tr[:, None]).abs().max()) == 0.0
+        assert 0.1 < float((tr[cm] > 0.5).float().mean()) < 0.98             # lit and shadowed samples
+        diff, spec = opbr.multilobe_eval(-view, nq, light, Q["rough"], Q["albedo"], Q["metal"][:, None])
+        diff, spec = diff * cm[:, None], spec * cm[:, None]
+        em = opbr.EnvLight(Q["env"]).eval(R.dirs_s2w(light))
+        Li = em * tr[:, None] + rgb if gi else em * tr[:, None]
+        rLd, rLs = Li * diff * inv_pdf[:, None], Li * spec * inv_pdf[:, None]
+        rLo = (1.0 - Q["metal"][:, None]) * Q["albedo"] * rLd + rLs
+        for a, b, nm in ((Lo, rLo, "Lo"), (Ld, rLd, "Lo_diff"), (Ls, rLs, "Lo_spec")):
+            err = (a.detach().cpu() - b.detach()).abs() / (b.detach().abs() + 1e-2)
+            assert float(err.max()) < 1e-3, (nm, float(err.max()))
+        assert float((rLs.detach().abs().sum(-1) > 0).float().mean()) > 0.1  # the specular lobe's support is exercised
+        sum((a * u).sum() for a, u in zip((rLo, rLd, rLs), ups)).backward()
+        def rel(x, y):
+            return float(torch.linalg.norm(x.cpu().reshape(-1) - y.reshape(-1)) / torch.linalg.norm(y).clamp_min(1e-20))
+        errs = {k: rel(P[k].grad, Q[k].grad) for k in lv}
+        print("pbr_light relative gradient errors (gi=%s):" % gi, {k: f"{v:.2e}" for k, v in errs.items()})
+        for k, v in errs.items():
+            assert v < 3e-4, (k, v)                                 # measured: 3e-6 .. 4e-5
+    # empty batch
+    z3, z1 = torch.zeros(0, 3), torch.zeros(0)
+    assert e.op_pbr_shade(z3, z3, z3, z1, z3, z1, z3, z1)[0].shape == (0, 3)
+    assert e.op_pbr_shade_backward(z3, z3, z3, z1, z3, z1, z3, z1, z3)["rough"].shape == (0,)
+    assert float(e.op_env_backward(z3, z3, (32, 64)).abs().max()) == 0.0
+
+
 def test_occupancy_ema_update_vs_oracle(scene):
     """ia_update_occupancy_ema (training-time grid update, SURVEY 8f.4: OccGridEstimator._update driven by
     IntrinsicAvatarModel.update_step, models/occ_grid/temporal_occ_grid.py:369-411, models/intrinsic_avatar.py:232-264) against
