@@ -1101,9 +1101,11 @@ extern "C" int ia_op_shade_fields_backward(ia_ctx* c, const float* d_xc, const f
     IA_REQUIRE(d_xc && d_feature && d_view && d_normal && d_drgb && d_dmat, IA_EINVAL,
                "ia_op_shade_fields_backward: NULL argument");
     IA_CHECK_CUDA(cudaSetDevice(c->device));
-    const size_t sm = (IA_SHADE_GRAD_FLOATS + (256 / IA_TEAM) * IA_SHB_TEAM_FLOATS) * sizeof(float);
+    const size_t sm = ((IA_SHB_THREADS / IA_TEAM) * IA_SHB_TEAM_FLOATS + IA_SHADE_GRAD_FLOATS) * sizeof(float);
     IA_CHECK_CUDA(cudaFuncSetAttribute(k_shade_fields_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_shade_fields_backward<<<ia_query_blocks(c, n), 256, sm, (cudaStream_t)stream>>>(
+    const int per_cta = IA_SHB_THREADS / IA_TEAM;       // one CTA per SM: its threads own the weight-gradient accumulators
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + per_cta - 1) / per_cta, (int64_t)c->n_sm));
+    k_shade_fields_backward<<<blocks, IA_SHB_THREADS, sm, (cudaStream_t)stream>>>(
         c->f, d_xc, d_feature, d_view, d_normal, d_drgb, d_dmat, n, d_g_rad_hash, d_g_mlp, d_g_x, d_g_feature, d_g_normal);
     IA_LAUNCH_CHECK();
     return IA_OK;

@@ -307,14 +307,26 @@ __global__ void __launch_bounds__(256) k_query_train(const __grid_constant__ IaF
 // (VanillaMLP / LipshitzMLP with ReLU, models/network_utils.py:201-244, 360-428; weights here are the effective, folded ones)
 // with respect to the radiance hash table, both networks' weights, and the inputs: position, geometry feature, normal.
 // The reference gets these from autograd.  Team layout of ia_team_radiance: lane = hash level = hidden units 4 lane .. + 3.
-// Weight gradients accumulate in shared memory per CTA (layout of the blob from IA_RAD_W1T on) and are flushed once.
+// Weight gradients: a CTA stages the activations of its 16 teams' points in shared memory (per network: relu(a1), dL/da1,
+// relu(a2), dL/da2, dL/ds), then all 512 threads add the 32 outer products into accumulators they own for the whole launch
+// (thread t: column k = t & 63 of rows q = t >> 6, q + 8, ... of every weight matrix -- 34 registers), so that there is no
+// atomic on a weight until the one flush per CTA at the end.  The weights are read from a shared-memory copy.  (The first
+// version added every product with a shared-memory atomic from 16 teams at once and read the weights through L1: 35.9 ms per
+// 2^20 points against 2.8 ms for the forward.)
 static_assert(IA_SHADE_GRAD_FLOATS == IA_MLP_END - IA_RAD_W1T, "ia_b200.h: IA_SHADE_GRAD_FLOATS out of sync with the blob layout");
 
+#define IA_ST_H1 0
+#define IA_ST_DA1 64
+#define IA_ST_H2 128
+#define IA_ST_DA2 192
+#define IA_ST_DS 256
+#define IA_ST_FLOATS 264                     // one network's staged activations of one point
+
 // One three-layer network: recomputes the forward from the team's input vector `inp` (shared memory, IN floats), applies the
-// upstream gradient `dsig` [OUT] on the sigmoid outputs, adds the weight gradients into `gw` (shared, indexed like the blob
-// relative to IA_RAD_W1T) and writes dL/d inp to `dinp` (shared, IN floats).  Returns the sigmoid outputs in `out`.
+// upstream gradient `dsig` [OUT] on the sigmoid outputs, stages the activations the weight gradients need in `st` (shared,
+// IA_ST_FLOATS) and writes dL/d inp to `dinp` (shared, IN floats).  Returns the sigmoid outputs in `out`.
 template <int IN, int OUT>
-__device__ __forceinline__ void ia_team_mlp3_backward(const Team& team, const float* __restrict__ blob, float* __restrict__ gw,
+__device__ __forceinline__ void ia_team_mlp3_backward(const Team& team, const float* __restrict__ blob, float* __restrict__ st,
                                                       int o_w1t, int o_b1, int o_w2t, int o_b2, int o_w3, int o_b3,
                                                       const float* __restrict__ inp, const float* __restrict__ dsig,
                                                       float* __restrict__ dinp, float* __restrict__ out) {
@@ -345,47 +357,84 @@ __device__ __forceinline__ void ia_team_mlp3_backward(const Team& team, const fl
         const float4 ww = W3[o * 16];
         dh2[0] = fmaf(ww.x, ds[o], dh2[0]); dh2[1] = fmaf(ww.y, ds[o], dh2[1]);
         dh2[2] = fmaf(ww.z, ds[o], dh2[2]); dh2[3] = fmaf(ww.w, ds[o], dh2[3]);
-        float* g3 = gw + (o_w3 - IA_RAD_W1T) + o * 64 + 4 * lane;
-#pragma unroll
-        for (int k = 0; k < 4; k++) atomicAdd(g3 + k, ds[o] * h2[k]);
-        if (lane == 0) atomicAdd(gw + (o_b3 - IA_RAD_W1T) + o, ds[o]);
+        if (lane == 0) st[IA_ST_DS + o] = ds[o];
     }
     const float da2[4] = {a2.x > 0.f ? dh2[0] : 0.f, a2.y > 0.f ? dh2[1] : 0.f, a2.z > 0.f ? dh2[2] : 0.f, a2.w > 0.f ? dh2[3] : 0.f};
-    // ---- hidden layer 64 -> 64 (input-major W2T[j][k]): gradient of the weights, and dL/dh1[j] = sum_k W2T[j][k] da2[k]
+    // ---- hidden layer 64 -> 64 (input-major W2T[j][k]): dL/dh1[j] = sum_k W2T[j][k] da2[k]
     float dh1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
     for (int s = 0; s < IA_TEAM; s++) {
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) {
-            const int j = s * 4 + kk;
-            const float hj = team.shfl(h1[kk], s);
-            const float4 ww = W2[j * 16];
-            float* g2 = gw + (o_w2t - IA_RAD_W1T) + j * 64 + 4 * lane;
-            if (hj != 0.f) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) atomicAdd(g2 + k, hj * da2[k]);
-            }
+            const float4 ww = W2[(s * 4 + kk) * 16];
             const float t = ia_team_sum(team, ww.x * da2[0] + ww.y * da2[1] + ww.z * da2[2] + ww.w * da2[3]);
             if (lane == s) dh1[kk] = t;
         }
     }
-#pragma unroll
-    for (int k = 0; k < 4; k++) atomicAdd(gw + (o_b2 - IA_RAD_W1T) + 4 * lane + k, da2[k]);
     const float da1[4] = {a1.x > 0.f ? dh1[0] : 0.f, a1.y > 0.f ? dh1[1] : 0.f, a1.z > 0.f ? dh1[2] : 0.f, a1.w > 0.f ? dh1[3] : 0.f};
-    // ---- first layer
-#pragma unroll 1
+    reinterpret_cast<float4*>(st + IA_ST_H1)[lane] = make_float4(h1[0], h1[1], h1[2], h1[3]);
+    reinterpret_cast<float4*>(st + IA_ST_DA1)[lane] = make_float4(da1[0], da1[1], da1[2], da1[3]);
+    reinterpret_cast<float4*>(st + IA_ST_H2)[lane] = make_float4(h2[0], h2[1], h2[2], h2[3]);
+    reinterpret_cast<float4*>(st + IA_ST_DA2)[lane] = make_float4(da2[0], da2[1], da2[2], da2[3]);
+    // ---- first layer: dL/d inp[i] = sum_k W1T[i][k] da1[k]
+#pragma unroll 4
     for (int i = 0; i < IN; i++) {
         const float4 ww = W1[i * 16];
-        const float x = inp[i];
-        float* g1 = gw + (o_w1t - IA_RAD_W1T) + i * 64 + 4 * lane;
-#pragma unroll
-        for (int k = 0; k < 4; k++) atomicAdd(g1 + k, x * da1[k]);
         const float t = ia_team_sum(team, ww.x * da1[0] + ww.y * da1[1] + ww.z * da1[2] + ww.w * da1[3]);
         if (lane == 0) dinp[i] = t;
     }
-#pragma unroll
-    for (int k = 0; k < 4; k++) atomicAdd(gw + (o_b1 - IA_RAD_W1T) + 4 * lane + k, da1[k]);
 }
+
+#define IA_SHB_THREADS 512
+#define IA_SHB_NQ (IA_SHB_THREADS / 64)
+// The weight gradients of one network a thread owns: column k = threadIdx.x & 63 of rows q + 8 r (q = threadIdx.x >> 6) of
+// W1T [IN][64], W2T [64][64], W3 [OUT][64], and one bias entry (q = 0: b1[k], q = 1: b2[k], q = 2 and k < OUT: b3[k]).
+template <int IN, int OUT>
+struct IaMlpGrad {
+    static constexpr int NQ = IA_SHB_NQ, R1 = (IN + NQ - 1) / NQ, R2 = 64 / NQ, R3 = (OUT + NQ - 1) / NQ;
+    float w1[R1], w2[R2], w3[R3], b;
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int r = 0; r < R1; r++) w1[r] = 0.f;
+#pragma unroll
+        for (int r = 0; r < R2; r++) w2[r] = 0.f;
+#pragma unroll
+        for (int r = 0; r < R3; r++) w3[r] = 0.f;
+        b = 0.f;
+    }
+    // adds the outer products of one staged point: `inp` its input vector, `st` its staged activations
+    __device__ __forceinline__ void add(const float* __restrict__ inp, const float* __restrict__ st) {
+        const int k = threadIdx.x & 63, q = threadIdx.x >> 6;
+        const float da1 = st[IA_ST_DA1 + k], da2 = st[IA_ST_DA2 + k], h2 = st[IA_ST_H2 + k];
+#pragma unroll
+        for (int r = 0; r < R1; r++)
+            if (q + NQ * r < IN) w1[r] = fmaf(inp[q + NQ * r], da1, w1[r]);
+#pragma unroll
+        for (int r = 0; r < R2; r++) w2[r] = fmaf(st[IA_ST_H1 + q + NQ * r], da2, w2[r]);
+#pragma unroll
+        for (int r = 0; r < R3; r++)
+            if (q + NQ * r < OUT) w3[r] = fmaf(st[IA_ST_DS + q + NQ * r], h2, w3[r]);
+        b += q == 0 ? da1 : q == 1 ? da2 : (q == 2 && k < OUT) ? st[IA_ST_DS + k] : 0.f;
+    }
+    // g: the gradient blob (indexed like the weight blob relative to IA_RAD_W1T)
+    __device__ __forceinline__ void flush(float* __restrict__ g, int o_w1t, int o_b1, int o_w2t, int o_b2, int o_w3, int o_b3) const {
+        const int k = threadIdx.x & 63, q = threadIdx.x >> 6;
+#pragma unroll
+        for (int r = 0; r < R1; r++)
+            if (q + NQ * r < IN && w1[r] != 0.f) atomicAdd(g + (o_w1t - IA_RAD_W1T) + (q + NQ * r) * 64 + k, w1[r]);
+#pragma unroll
+        for (int r = 0; r < R2; r++)
+            if (w2[r] != 0.f) atomicAdd(g + (o_w2t - IA_RAD_W1T) + (q + NQ * r) * 64 + k, w2[r]);
+#pragma unroll
+        for (int r = 0; r < R3; r++)
+            if (q + NQ * r < OUT && w3[r] != 0.f) atomicAdd(g + (o_w3 - IA_RAD_W1T) + (q + NQ * r) * 64 + k, w3[r]);
+        if (b != 0.f) {
+            if (q == 0) atomicAdd(g + (o_b1 - IA_RAD_W1T) + k, b);
+            else if (q == 1) atomicAdd(g + (o_b2 - IA_RAD_W1T) + k, b);
+            else if (q == 2 && k < OUT) atomicAdd(g + (o_b3 - IA_RAD_W1T) + k, b);
+        }
+    }
+};
 
 // Jacobian-transpose product of ia_sh4: g[16] -> d/d(x, y, z)
 __device__ __forceinline__ void ia_sh4_backward(float x, float y, float z, const float* __restrict__ g, float d[3]) {
@@ -401,8 +450,8 @@ __device__ __forceinline__ void ia_sh4_backward(float x, float y, float z, const
            k * (15.f * z2 - 3.f) * g[12] - 10.f * h * x * z * g[13] + m * (x2 - y2) * g[14];
 }
 
-#define IA_SHB_TEAM_FLOATS (67 + 67 + 48)    // per team in shared memory: input vector, dL/d input of the two networks
-__global__ void __launch_bounds__(256) k_shade_fields_backward(const __grid_constant__ IaFrame p, const float* __restrict__ xc,
+#define IA_SHB_TEAM_FLOATS (68 + 68 + 48 + 2 * IA_ST_FLOATS)    // per team: input vector, dL/d input of the two networks, staged activations
+__global__ void __launch_bounds__(IA_SHB_THREADS) k_shade_fields_backward(const __grid_constant__ IaFrame p, const float* __restrict__ xc,
                                                                const float* __restrict__ feat, const float* __restrict__ view,
                                                                const float* __restrict__ nrm, const float* __restrict__ d_rgb,
                                                                const float* __restrict__ d_mat, long long n,
@@ -410,21 +459,30 @@ __global__ void __launch_bounds__(256) k_shade_fields_backward(const __grid_cons
                                                                float* __restrict__ g_x, float* __restrict__ g_feat,
                                                                float* __restrict__ g_nrm) {
     extern __shared__ __align__(16) float smem[];
-    float* gw = smem;                                   // IA_SHADE_GRAD_FLOATS
-    float* mine = smem + IA_SHADE_GRAD_FLOATS + (threadIdx.x / IA_TEAM) * IA_SHB_TEAM_FLOATS;
-    float* inp = mine;
-    float* dr = mine + 67;
-    float* dm = mine + 134;
-    for (int i = threadIdx.x; i < IA_SHADE_GRAD_FLOATS; i += blockDim.x) gw[i] = 0.f;
+    constexpr int TEAMS = IA_SHB_THREADS / IA_TEAM;
+    float* wsm = smem + TEAMS * IA_SHB_TEAM_FLOATS;     // the two networks' weights, IA_SHADE_GRAD_FLOATS
+    for (int i = threadIdx.x; i < IA_SHADE_GRAD_FLOATS / 4; i += IA_SHB_THREADS)
+        reinterpret_cast<float4*>(wsm)[i] = __ldg(reinterpret_cast<const float4*>(p.mlp + IA_RAD_W1T) + i);
+    const float* blob = wsm - IA_RAD_W1T;               // indexed with the blob's offsets
     __syncthreads();
+    float* mine = smem + (threadIdx.x / IA_TEAM) * IA_SHB_TEAM_FLOATS;
+    float* inp = mine;
+    float* dr = mine + 68;
+    float* dm = mine + 136;
+    float* st_r = mine + 184;
+    float* st_m = st_r + IA_ST_FLOATS;
+    IaMlpGrad<67, 3> acc_r;
+    IaMlpGrad<48, 5> acc_m;
+    acc_r.zero(); acc_m.zero();
     Team team = cg::tiled_partition<IA_TEAM>(cg::this_thread_block());
     const int lane = team.thread_rank();
-    const long long teams = (long long)gridDim.x * (blockDim.x / IA_TEAM);
-    for (long long i = (long long)blockIdx.x * (blockDim.x / IA_TEAM) + threadIdx.x / IA_TEAM; i < n; i += teams) {
+    for (long long base = (long long)blockIdx.x * TEAMS; base < n; base += (long long)gridDim.x * TEAMS) {
+        const long long i = base + threadIdx.x / IA_TEAM;
+        const bool active = i < n;                      // an idle team runs the same code on zeros: its products vanish
         // ---- inputs
         float xn[3];
 #pragma unroll
-        for (int d = 0; d < 3; d++) xn[d] = (xc[i * 3 + d] - p.center[d]) / p.scale[d] + 0.5f;
+        for (int d = 0; d < 3; d++) xn[d] = active ? (xc[i * 3 + d] - p.center[d]) / p.scale[d] + 0.5f : 0.5f;
         const IaLevel lv = ia_level(p, lane);
         uint32_t idx[8];
         float wt[8], wl[3];
@@ -433,67 +491,82 @@ __global__ void __launch_bounds__(256) k_shade_fields_backward(const __grid_cons
         float f0 = 0.f, f1 = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; c++) { v[c] = __ldg(p.rad_hash + idx[c]); f0 = fmaf(wt[c], v[c].x, f0); f1 = fmaf(wt[c], v[c].y, f1); }
-        const float vw[3] = {-view[i * 3], -view[i * 3 + 1], -view[i * 3 + 2]};
-        const float nw[3] = {nrm[i * 3], nrm[i * 3 + 1], nrm[i * 3 + 2]};
+        float vw[3] = {0.f, 0.f, 1.f}, nw[3] = {0.f, 0.f, 1.f};
+        if (active) {
+#pragma unroll
+            for (int d = 0; d < 3; d++) { vw[d] = -view[i * 3 + d]; nw[d] = nrm[i * 3 + d]; }
+        }
         const float dn = vw[0] * nw[0] + vw[1] * nw[1] + vw[2] * nw[2];
         float r[3];
 #pragma unroll
         for (int d = 0; d < 3; d++) r[d] = ((2.f * dn * nw[d] - vw[d] + 1.f) / 2.f) * 2.f - 1.f;
-        team.sync();
         if (lane < 3) { inp[lane] = xn[lane] * 2.0f - 1.0f; inp[64 + lane] = nw[lane]; }
         inp[3 + 2 * lane] = f0; inp[4 + 2 * lane] = f1;
-        if (lane < 13) inp[35 + lane] = feat[i * 13 + lane];
+        if (lane < 13) inp[35 + lane] = active ? feat[i * 13 + lane] : 0.f;
         if (lane == 0) ia_sh4(r[0], r[1], r[2], inp + 48);
         team.sync();
         // ---- the two networks
         float dsig_r[3], dsig_m[5], out_r[3], out_m[5];
 #pragma unroll
-        for (int o = 0; o < 3; o++) dsig_r[o] = d_rgb[i * 3 + o];
+        for (int o = 0; o < 3; o++) dsig_r[o] = active ? d_rgb[i * 3 + o] : 0.f;
 #pragma unroll
-        for (int o = 0; o < 5; o++) dsig_m[o] = d_mat[i * 5 + o] * p.mat_scale[o] * (o < 3 ? p.albedo_ratio[o] : 1.0f);
-        ia_team_mlp3_backward<67, 3>(team, p.mlp, gw, IA_RAD_W1T, IA_RAD_B1, IA_RAD_W2T, IA_RAD_B2, IA_RAD_W3, IA_RAD_B3, inp,
+        for (int o = 0; o < 5; o++) dsig_m[o] = active ? d_mat[i * 5 + o] * p.mat_scale[o] * (o < 3 ? p.albedo_ratio[o] : 1.0f) : 0.f;
+        ia_team_mlp3_backward<67, 3>(team, blob, st_r, IA_RAD_W1T, IA_RAD_B1, IA_RAD_W2T, IA_RAD_B2, IA_RAD_W3, IA_RAD_B3, inp,
                                      dsig_r, dr, out_r);
-        ia_team_mlp3_backward<48, 5>(team, p.mlp, gw, IA_MAT_W1T, IA_MAT_B1, IA_MAT_W2T, IA_MAT_B2, IA_MAT_W3, IA_MAT_B3, inp,
+        ia_team_mlp3_backward<48, 5>(team, blob, st_m, IA_MAT_W1T, IA_MAT_B1, IA_MAT_W2T, IA_MAT_B2, IA_MAT_W3, IA_MAT_B3, inp,
                                      dsig_m, dm, out_m);
-        team.sync();
+        __syncthreads();
+        // ---- weight gradients: the CTA's 16 staged points into the accumulators each thread owns
+#pragma unroll 1
+        for (int t = 0; t < TEAMS; t++) {
+            const float* T = smem + t * IA_SHB_TEAM_FLOATS;
+            acc_r.add(T, T + 184);
+            acc_m.add(T, T + 184 + IA_ST_FLOATS);
+        }
         // ---- inputs: hash entries of this lane's level, position, feature, normal
-        const float de0 = dr[3 + 2 * lane] + dm[3 + 2 * lane], de1 = dr[4 + 2 * lane] + dm[4 + 2 * lane];
+        if (active) {
+            const float de0 = dr[3 + 2 * lane] + dm[3 + 2 * lane], de1 = dr[4 + 2 * lane] + dm[4 + 2 * lane];
+            // (samples without a root arrive with a zero upstream gradient, all at the same canonical point: their atomics
+            // would queue on the same few table entries)
+            if (de0 != 0.f || de1 != 0.f) {
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-            atomicAdd(&g_hash[(size_t)idx[c] * 2 + 0], wt[c] * de0);
-            atomicAdd(&g_hash[(size_t)idx[c] * 2 + 1], wt[c] * de1);
-        }
-        float gx[3];
-#pragma unroll
-        for (int d = 0; d < 3; d++) {
-            const int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int b1 = k & 1, b2 = k >> 1;
-                const float t = (b1 ? wl[d1] : 1.f - wl[d1]) * (b2 ? wl[d2] : 1.f - wl[d2]);
-                const int lo = (b1 << d1) | (b2 << d2), hi = lo | (1 << d);
-                a0 = fmaf(t, v[hi].x - v[lo].x, a0);
-                a1 = fmaf(t, v[hi].y - v[lo].y, a1);
+                for (int c = 0; c < 8; c++) {
+                    atomicAdd(&g_hash[(size_t)idx[c] * 2 + 0], wt[c] * de0);
+                    atomicAdd(&g_hash[(size_t)idx[c] * 2 + 1], wt[c] * de1);
+                }
             }
-            gx[d] = ia_team_sum(team, lv.scale * (a0 * de0 + a1 * de1));
-        }
-        if (lane < 3) {
-            if (g_x) g_x[i * 3 + lane] = ((lane == 0 ? gx[0] : lane == 1 ? gx[1] : gx[2]) + 2.0f * (dr[lane] + dm[lane])) / p.scale[lane];
-        }
-        if (g_feat && lane < 13) g_feat[i * 13 + lane] = dr[35 + lane] + dm[35 + lane];
-        if (g_nrm && lane == 0) {
-            float gr[3];
-            ia_sh4_backward(r[0], r[1], r[2], dr + 48, gr);
-            // refl = 2 (v . n) n - v:  d/dn_j = 2 v_j (g . n) + 2 (v . n) g_j
-            const float gn = gr[0] * nw[0] + gr[1] * nw[1] + gr[2] * nw[2];
+            float gx[3];
 #pragma unroll
-            for (int d = 0; d < 3; d++) g_nrm[i * 3 + d] = dr[64 + d] + 2.f * vw[d] * gn + 2.f * dn * gr[d];
+            for (int d = 0; d < 3; d++) {
+                const int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int b1 = k & 1, b2 = k >> 1;
+                    const float t = (b1 ? wl[d1] : 1.f - wl[d1]) * (b2 ? wl[d2] : 1.f - wl[d2]);
+                    const int lo = (b1 << d1) | (b2 << d2), hi = lo | (1 << d);
+                    a0 = fmaf(t, v[hi].x - v[lo].x, a0);
+                    a1 = fmaf(t, v[hi].y - v[lo].y, a1);
+                }
+                gx[d] = ia_team_sum(team, lv.scale * (a0 * de0 + a1 * de1));
+            }
+            if (lane < 3) {
+                if (g_x) g_x[i * 3 + lane] = ((lane == 0 ? gx[0] : lane == 1 ? gx[1] : gx[2]) + 2.0f * (dr[lane] + dm[lane])) / p.scale[lane];
+            }
+            if (g_feat && lane < 13) g_feat[i * 13 + lane] = dr[35 + lane] + dm[35 + lane];
+            if (g_nrm && lane == 0) {
+                float gr[3];
+                ia_sh4_backward(r[0], r[1], r[2], dr + 48, gr);
+                // refl = 2 (v . n) n - v:  d/dn_j = 2 v_j (g . n) + 2 (v . n) g_j
+                const float gn = gr[0] * nw[0] + gr[1] * nw[1] + gr[2] * nw[2];
+#pragma unroll
+                for (int d = 0; d < 3; d++) g_nrm[i * 3 + d] = dr[64 + d] + 2.f * vw[d] * gn + 2.f * dn * gr[d];
+            }
         }
+        __syncthreads();                                // the staging is rewritten by the next round
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < IA_SHADE_GRAD_FLOATS; i += blockDim.x)
-        if (gw[i] != 0.f) atomicAdd(&g_mlp[i], gw[i]);
+    acc_r.flush(g_mlp, IA_RAD_W1T, IA_RAD_B1, IA_RAD_W2T, IA_RAD_B2, IA_RAD_W3, IA_RAD_B3);
+    acc_m.flush(g_mlp, IA_MAT_W1T, IA_MAT_B1, IA_MAT_W2T, IA_MAT_B2, IA_MAT_W3, IA_MAT_B3);
 }
 
 // ------------------------------------------------------------------------------------------------
