@@ -407,3 +407,106 @@ def test_png_and_exr_encoders_round_trip(tmp_path):
             assert np.allclose(back[..., ::-1], hdr)
     except Exception:
         pass
+
+
+def test_training_seam_routes_gradients_without_a_device():
+    """intrinsicavatar_b200.train on a stand-in engine (no device here): every leaf of render_radiance / pbr_light receives the
+    gradient the ops return, in its own shape, dtype and place -- the bone transforms get the query's and the canonical
+    point's contribution in rows 0..2 only, roots are handed to the deformer backward in groups of 13, beta may be a tensor
+    or a float.  (The ops themselves are held to autograd on the GPU, tests/test_gpu_ops.py.)"""
+    from intrinsicavatar_b200.train import SHADE_PARAMS, pbr_light, render_radiance, volrend
+    calls = {}
+
+    class StandIn:
+        dev = torch.device("cpu")
+
+        def op_query_train(self, xd):
+            n = xd.shape[0]
+            return {"sdf": torch.randn(n) * 0.01, "x_c": torch.randn(n, 3), "valid": torch.rand(n) > 0.3, "grad": torch.randn(n, 3),
+                    "feature": torch.randn(n, 13), "J_inv": torch.randn(n, 3, 3), "best": torch.zeros(n, dtype=torch.int32)}
+
+        def op_query_backward(self, fwd, d_out):
+            calls["query_d_out"] = d_out.clone()
+            return {"hash": torch.full((100, 2), 2.0), "w1": torch.ones(64, 35), "b1": torch.ones(64), "w2": torch.ones(13, 64),
+                    "b2": torch.ones(13), "tfs": torch.ones(24, 3, 4), "x": None}
+
+        def op_deform_backward(self, xc, valid, J_inv, g_xc):
+            assert xc.shape[1:] == (13, 3) and valid.shape[1:] == (13,) and J_inv.shape[1:] == (13, 3, 3) and g_xc.shape == xc.shape
+            calls["deform_roots"] = xc.shape[0] * 13
+            return torch.full((24, 3, 4), 0.5)
+
+        def op_shade_fields(self, xc, f, v, n):
+            return torch.rand(xc.shape[0], 3), torch.rand(xc.shape[0], 5)
+
+        def op_shade_fields_backward(self, xc, f, v, n, d_rgb, d_mat):
+            assert d_rgb.shape == (xc.shape[0], 3) and d_mat.shape == (xc.shape[0], 5)
+            net = lambda i, o: {"w1": torch.ones(64, i), "b1": torch.ones(64), "w2": torch.ones(64, 64), "b2": torch.ones(64),
+                                "w3": torch.ones(o, 64), "b3": torch.ones(o)}
+            return {"hash": torch.ones(100, 2), "rad": net(67, 3), "mat": net(48, 5), "x": torch.ones_like(xc),
+                    "feature": torch.ones_like(f), "normal": torch.ones_like(n)}
+
+        def op_volrend(self, pi, sdf, dists, vals, beta):
+            calls["beta"] = beta
+            return torch.rand_like(sdf), torch.rand(pi.shape[0], vals.shape[1]), torch.rand(pi.shape[0])
+
+        def op_volrend_backward(self, pi, sdf, dists, vals, beta, d_comp, d_op):
+            assert d_comp.shape == (pi.shape[0], vals.shape[1])
+            return torch.ones_like(sdf), torch.ones_like(vals), torch.full((1,), 3.0)
+
+        def op_secondary(self, o, d, gi=False):
+            return torch.full((o.shape[0],), 0.5), torch.zeros(o.shape[0], 3)
+
+        def op_env(self, u=None, dirs_world=None):
+            return None, None, torch.ones(dirs_world.shape[0], 3)
+
+        def op_env_backward(self, dirs, d_em, shape):
+            calls["env_d_em"] = d_em.clone()
+            return torch.ones(shape[0], shape[1], 3)
+
+        def op_pbr_shade(self, *a):
+            m = a[0].shape[0]
+            return torch.rand(m, 3), torch.rand(m, 3), torch.rand(m, 3)
+
+        def op_pbr_shade_backward(self, wi, n, wo, rough, albedo, metal, Li, inv_pdf, d_Lo, d_Ld=None, d_Ls=None):
+            m = wi.shape[0]
+            return {"normal": torch.ones(m, 3), "rough": torch.ones(m), "albedo": torch.ones(m, 3), "metal": torch.ones(m),
+                    "Li": torch.full((m, 3), 2.0)}
+
+    shapes = {"geo_hash": (100, 2), "geo_w1": (64, 35), "geo_b1": (64,), "geo_w2": (13, 64), "geo_b2": (13,), "rad_hash": (200,),
+              "rad_w1": (64, 67), "rad_b1": (64,), "rad_w2": (64, 64), "rad_b2": (64,), "rad_w3": (3, 64), "rad_b3": (3,),
+              "mat_w1": (64, 48), "mat_b1": (64,), "mat_w2": (64, 64), "mat_b2": (64,), "mat_w3": (5, 64), "mat_b3": (5,)}
+    assert set(SHADE_PARAMS) < set(shapes)
+    P = {k: torch.zeros(v, requires_grad=True) for k, v in shapes.items()}
+    tfs = torch.eye(4).repeat(24, 1, 1).requires_grad_(True)
+    beta = torch.tensor(0.01, requires_grad=True)
+    counts = torch.tensor([0, 3, 5, 1])
+    pi = torch.stack([torch.cumsum(counts, 0) - counts, counts], 1).int()
+    e = StandIn()
+    out = render_radiance(e, P, tfs, torch.eye(4), torch.randn(4, 3), torch.randn(4, 3), pi, torch.rand(9), torch.rand(9) + 1, beta)
+    assert out["comp_rgb"].shape == (4, 3) and out["comp_mats"].shape == (4, 5) and out["depth"].shape == (4,)
+    assert not out["weights"].requires_grad and not out["valid"].requires_grad
+    (out["comp_rgb"].sum() + out["depth"].sum() + out["opacity"].sum()).backward()
+    for k, v in shapes.items():
+        assert P[k].grad is not None and P[k].grad.shape == v, k
+    assert float(P["geo_hash"].grad[0, 0]) == 2.0 and float(P["rad_hash"].grad[0]) == 1.0      # reshaped to the leaf's layout
+    assert torch.equal(tfs.grad[:, :3, :], torch.full((24, 3, 4), 1.5)) and float(tfs.grad[:, 3, :].abs().max()) == 0.0
+    assert calls["deform_roots"] == 13 and float(beta.grad) == 3.0 and calls["beta"] == pytest.approx(0.01)
+    # d sdf from the compositing (ones) lands in channel 0 of the query's upstream gradient next to the shading's (ones)
+    assert torch.equal(calls["query_d_out"][:, 0], torch.full((9,), 2.0)) and torch.equal(calls["query_d_out"][:, 1:], torch.ones(9, 12))
+    # beta as a plain float: no gradient slot, same call
+    w, comp, op = volrend(e, pi, torch.randn(9, requires_grad=True), torch.rand(9), torch.randn(9, 2), 0.02)
+    assert calls["beta"] == 0.02 and comp.requires_grad
+    # physically based branch
+    m = 50
+    leaves = {"n_raw": torch.randn(m, 3), "albedo": torch.rand(m, 3), "rough": torch.rand(m, 1), "metal": torch.rand(m), "env": torch.rand(4, 8, 3)}
+    L = {k: v.requires_grad_(True) for k, v in leaves.items()}
+    nrm = torch.nn.functional.normalize(L["n_raw"], dim=-1)
+    light = torch.nn.functional.normalize(torch.randn(m, 3), dim=-1)
+    Lo, Ld, Ls, vis = pbr_light(e, L["env"], torch.eye(4), nrm, L["albedo"], L["rough"], L["metal"], torch.randn(m, 3),
+                                torch.randn(m, 3), light, torch.full((m,), 12.566))
+    cm = (nrm.detach() * light).sum(-1) > 1e-6
+    assert torch.equal(vis[:, 0], torch.where(cm, torch.ones(m), torch.zeros(m)))            # 2 x the stand-in's 0.5
+    Lo.sum().backward()
+    assert L["rough"].grad.shape == (m, 1) and L["metal"].grad.shape == (m,) and L["env"].grad.shape == (4, 8, 3)
+    assert torch.equal(calls["env_d_em"], 2.0 * torch.where(cm, 0.5, 0.0)[:, None].expand(-1, 3))  # dLi x transmittance
+    assert L["n_raw"].grad is not None and float(L["albedo"].grad.min()) == 1.0
