@@ -70,6 +70,23 @@ def fused_query(engine, xd, geo_hash, geo_w1, geo_b1, geo_w2, geo_b2, tfs, with_
     return out if with_normal else out[:4]
 
 
+GEO_PARAMS = ("geo_hash", "geo_w1", "geo_b1", "geo_w2", "geo_b2")
+
+
+def folded_leaves(named_parameters: dict, device, material_feature: str = "hybrid") -> dict:
+    """The effective weights the ops differentiate (``geo_*``, ``rad_*``, ``mat_*``, ``beta``) as tensors on ``device`` that
+    stay attached to the reference-keyed parameters they are folded from (``dict(model.named_parameters())`` or a
+    checkpoint's ``state_dict`` with ``requires_grad``): weight normalisation of the geometry network
+    (models/network_utils.py:201-244), the Lipschitz bound of the material network (:360-428) and
+    ``beta = |b| + 1e-4`` (models/rf/density.py:32-34) are ordinary tensor code in ``weights.fold``, so a backward through
+    ``render_radiance`` / ``pbr_light`` arrives at the reference's own parameter tree -- what an optimiser over
+    ``model.parameters()`` steps.  After the step, upload the new values (``engine.set_fields(weights.fold(...))``)."""
+    from .weights import fold
+    sd = {k[len("model."):] if k.startswith("model.") else k: v for k, v in named_parameters.items()}
+    out = fold(sd, material_feature, keep_graph=True)
+    return {k: v.to(device) for k, v in out.items()}
+
+
 SHADE_PARAMS = ("rad_hash",) + tuple(f"{net}_{t}{i}" for net in ("rad", "mat") for i in (1, 2, 3) for t in ("w", "b"))
 
 
@@ -104,7 +121,7 @@ def shade_fields(engine, xc, feature, view_world, normal_world, params: dict):
 class _VolRend(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, packed_info, sdf, dists, values, beta):
-        b = float(beta)
+        b = float(beta.detach()) if torch.is_tensor(beta) else float(beta)
         w, comp, op = engine.op_volrend(packed_info, sdf.detach(), dists, values.detach(), b)
         ctx.engine, ctx.a = engine, (packed_info, sdf.detach(), dists, values.detach(), b)
         ctx.beta_like = beta if torch.is_tensor(beta) else None
@@ -143,8 +160,7 @@ def render_radiance(engine, params: dict, tfs, w2s, rays_o, rays_d, packed_info,
     o, d = rays_o.to(dev, torch.float32)[ridx], rays_d.to(dev, torch.float32)[ridx]
     t_mid = 0.5 * (t0 + t1)
     xd = o + d * t_mid[:, None]
-    sdf, feature, x_c, valid, normal = fused_query(engine, xd, *[params[k] for k in ("geo_hash", "geo_w1", "geo_b1", "geo_w2",
-                                                                                   "geo_b2")], tfs, with_normal=True)
+    sdf, feature, x_c, valid, normal = fused_query(engine, xd, *[params[k] for k in GEO_PARAMS], tfs, with_normal=True)
     rot = torch.as_tensor(w2s, dtype=torch.float32, device=dev)[:3, :3]
     view_w = torch.nn.functional.normalize(d @ rot, dim=-1, eps=1e-6)
     normal_w = torch.nn.functional.normalize(normal @ rot, dim=-1, eps=1e-6)

@@ -133,10 +133,12 @@ def material_state_dict_for(sd: dict, material_feature: str) -> dict:
     return out
 
 
-def fold(sd: dict, material_feature: str = "hybrid") -> dict:
+def fold(sd: dict, material_feature: str = "hybrid", keep_graph: bool = False) -> dict:
     """Reference state_dict -> dense fp32 matrices (row-major [out,in]) + scalars for the kernels.  The kernels evaluate the
     material net on the hybrid input cat[xyz_embd 35, feature 13]; a model with material_feature = geometry | radiance has a
-    13- / 35-wide first layer, which is the hybrid layer with zero columns for the input it does not see."""
+    13- / 35-wide first layer, which is the hybrid layer with zero columns for the input it does not see.
+    ``keep_graph``: plain tensor code throughout, so with parameters that require grad the result stays attached to them
+    (``beta`` is then a tensor): the training seam differentiates weight norm, Lipschitz bound and beta through this function."""
     out = {}
     out["geo_hash"] = sd["geometry.encoding.encoding.encoding.params"].float().contiguous()
     out["rad_hash"] = sd["radiance.xyz_encoding.encoding.encoding.params"].float().contiguous()
@@ -155,7 +157,7 @@ def fold(sd: dict, material_feature: str = "hybrid") -> dict:
         wf = w * s[:, None]
         if li == 0 and wf.shape[1] != 48:
             assert wf.shape[1] == MATERIAL_IN[material_feature], (tuple(wf.shape), material_feature)
-            pad = torch.zeros(wf.shape[0], 48)
+            pad = torch.zeros(wf.shape[0], 48, device=wf.device)
             if material_feature == "geometry":
                 pad[:, 35:] = wf
             else:
@@ -163,7 +165,8 @@ def fold(sd: dict, material_feature: str = "hybrid") -> dict:
             wf = pad
         out[f"mat_w{li + 1}"] = wf.contiguous()
         out[f"mat_b{li + 1}"] = sd[f"material.network.layers.{li}.bias"].float().contiguous()
-    out["beta"] = float(sd["density.beta"].abs() + 1e-4)  # LearnedLaplaceDensity.get_beta, density.py:32-34
+    beta = sd["density.beta"].float().abs() + 1e-4        # LearnedLaplaceDensity.get_beta, density.py:32-34
+    out["beta"] = beta if keep_graph else float(beta.detach())
     return out
 
 

@@ -950,6 +950,54 @@ def test_render_radiance_training_step(eng, posed, scene):
         assert v < 1e-4, (kk, v)                                      # measured: 1e-7 .. 7e-6
 
 
+def test_training_step_reaches_reference_parameters(scene, posed):
+    """train.folded_leaves + render_radiance: a loss on the rendered buffers back-propagates through the ops AND through the
+    fold (weight normalisation, Lipschitz bound, beta = |b| + 1e-4) to the reference-keyed parameters -- every one of them
+    receives a gradient -- and a small step against that gradient, uploaded with set_fields, lowers the loss by about what
+    the first-order model predicts."""
+    from intrinsicavatar_b200.train import folded_leaves, render_radiance
+    from intrinsicavatar_b200.weights import fold
+    import torch.nn.functional as F
+    R = posed["oracle"]
+    fr = posed["frame"]
+    e = scene.engine()
+    e.set_pose(fr["tfs"], fr["w2s"])
+    g = torch.Generator().manual_seed(5)
+    n_rays, spr, step = 512, 16, 0.012
+    p0 = _points(posed, 2 * n_rays, seed=13)[n_rays:]
+    rays_d = F.normalize(torch.randn(n_rays, 3, generator=g), dim=-1)
+    rays_o = p0 - rays_d * (spr * step / 2)
+    pi = torch.stack([torch.arange(n_rays) * spr, torch.full((n_rays,), spr)], 1).int()
+    t0 = (torch.arange(spr) * step).repeat(n_rays)
+    t1 = t0 + step
+    targets = {"comp_rgb": torch.rand(n_rays, 3, generator=g).cuda(), "comp_mats": torch.rand(n_rays, 5, generator=g).cuda(),
+               "opacity": torch.full((n_rays,), 0.5).cuda()}
+    tfs = R.tfs.clone().cuda()
+
+    def loss_of(params):
+        out = render_radiance(e, params, tfs, R.w2s, rays_o, rays_d, pi, t0, t1, params["beta"])
+        return sum(((out[k] - t) ** 2).mean() for k, t in targets.items())
+
+    theta = {k: v.clone().float().requires_grad_(True) for k, v in scene.state_dict.items() if v.is_floating_point()}
+    loss = loss_of(folded_leaves(theta, e.dev))
+    loss.backward()
+    missing = [k for k, v in theta.items() if v.grad is None or not bool(torch.isfinite(v.grad).all())]
+    assert not missing, missing
+    # (a Lipschitz bound above its layer's row sums is inactive -- scale clamped to 1 -- and has a zero gradient, as in the reference)
+    zero = [k for k, v in theta.items() if float(v.grad.abs().max()) == 0.0 and "lipshitz_bound" not in k]
+    assert not zero, zero
+    g2 = float(sum((v.grad.double() ** 2).sum() for v in theta.values()))
+    L0 = float(loss.detach())
+    lr = 0.05 * L0 / g2                                   # first-order prediction: the loss drops by 5 %
+    with torch.no_grad():
+        stepped = {k: v - lr * v.grad for k, v in theta.items()}
+    e.set_fields(fold(stepped), scene.layout, scene.snarf.bbox)
+    with torch.no_grad():
+        L1 = float(loss_of(folded_leaves(stepped, e.dev)))
+    print("training step: loss %.6f -> %.6f (predicted %.6f)" % (L0, L1, 0.95 * L0))
+    assert L1 < L0 and abs((L0 - L1) / (0.05 * L0) - 1.0) < 0.5, (L0, L1)     # measured: 0.6099 -> 0.5902, 0.65 of the prediction
+
+
 def test_pbr_light_training_backward(scene, posed):
     """train.pbr_light: the differentiable part of the training-time integrators (pbr_uniform_light_forward, the
     training default) -- MultiLobe.eval under the cosine mask, the environment lookup, Li = em tr + indirect, Lo = kd Lo_diff +
