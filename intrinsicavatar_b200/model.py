@@ -18,7 +18,8 @@ file is not shipped) or with ``subject: synthetic`` uses the procedural 24-joint
 Nested nodes are checked against what the kernels are compiled for (hash-grid layout, MLP widths, ...): a mismatch raises.
 
 Only the eval render path is implemented (render_mode = light | uniform_light | mats | mis, with or without
-global_illumination / add_emitter); training-mode calls raise.
+global_illumination / add_emitter); ``train(True)`` raises -- the training-mode forward / backward lives below this seam,
+in ``intrinsicavatar_b200.train`` (autograd nodes over the CUDA ops).
 Every numeric step runs in libia_b200.so; this file is glue (pose -> 24 matrices, pointer passing).
 """
 from __future__ import annotations
@@ -255,7 +256,8 @@ class IntrinsicAvatarModel(torch.nn.Module):
 
     def train(self, mode=True):
         if mode:
-            raise NotImplementedError("training is out of scope of the render-path drop-in (SURVEY.md 8f.4)")
+            raise NotImplementedError("forward() implements the eval render path; the training-mode forward / backward is "
+                                      "intrinsicavatar_b200.train (fused_query, shade_fields, volrend, pbr_light; SURVEY.md 8f.4)")
         return super().train(False)
 
     # -------------------------------------------------------------------- prepare ----
