@@ -271,14 +271,16 @@ int ia_op_shade_fields_backward(ia_ctx* ctx, const float* d_xc, const float* d_f
  * autograd.  d_packed_info [n_rays,2] = (first sample, count) like nerfacc; d_sdf / d_dists [n_samples]; d_values [n_samples, C]
  * (C <= IA_VOLREND_MAX_C: rgb, normal, materials ... concatenated by the caller); beta = LearnedLaplaceDensity.get_beta().
  * ia_op_volrend: d_weights [n_samples] (may be NULL), d_comp [n_rays, C], d_opacity [n_rays].
- * ia_op_volrend_backward: upstream d_dcomp [n_rays, C], d_dopacity [n_rays] (may be NULL) -> writes d_g_sdf [n_samples],
- * d_g_values [n_samples, C] (may be NULL); ADDS into d_g_beta [1].                                                        */
+ * ia_op_volrend_backward: upstream d_dcomp [n_rays, C], d_dopacity [n_rays] (may be NULL), d_dweights [n_samples] (may be NULL:
+ * the gradient on the weights themselves -- the physically based branch re-uses them for its shading samples,
+ * models/pbr/utils.py:146-161) -> writes d_g_sdf [n_samples], d_g_values [n_samples, C] (may be NULL); ADDS into d_g_beta [1]. */
 #define IA_VOLREND_MAX_C 16
 int ia_op_volrend(ia_ctx* ctx, const int32_t* d_packed_info, const float* d_sdf, const float* d_dists, const float* d_values,
                   int n_channels, float beta, int64_t n_rays, float* d_weights, float* d_comp, float* d_opacity, void* stream);
 int ia_op_volrend_backward(ia_ctx* ctx, const int32_t* d_packed_info, const float* d_sdf, const float* d_dists,
                            const float* d_values, int n_channels, float beta, const float* d_dcomp, const float* d_dopacity,
-                           int64_t n_rays, float* d_g_sdf, float* d_g_values, float* d_g_beta, void* stream);
+                           const float* d_dweights, int64_t n_rays, float* d_g_sdf, float* d_g_values, float* d_g_beta,
+                           void* stream);
 
 /* Training-mode forward / backward of the fused query: SNARFDeformer.deform with eval_mode=False
  * (models/deformers/snarf_deformer.py:170-261) = ForwardDeformer.forward version 1 (search + implicit-differentiation

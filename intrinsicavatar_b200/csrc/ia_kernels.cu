@@ -1129,8 +1129,8 @@ extern "C" int ia_op_volrend(ia_ctx* c, const int32_t* d_packed_info, const floa
 
 extern "C" int ia_op_volrend_backward(ia_ctx* c, const int32_t* d_packed_info, const float* d_sdf, const float* d_dists,
                                       const float* d_values, int n_channels, float beta, const float* d_dcomp,
-                                      const float* d_dopacity, int64_t n_rays, float* d_g_sdf, float* d_g_values,
-                                      float* d_g_beta, void* stream) {
+                                      const float* d_dopacity, const float* d_dweights, int64_t n_rays, float* d_g_sdf,
+                                      float* d_g_values, float* d_g_beta, void* stream) {
     IA_REQUIRE(c && n_rays >= 0 && n_channels >= 0 && n_channels <= IA_VOLREND_MAX_C && beta > 0.f && d_g_beta, IA_EINVAL,
                "ia_op_volrend_backward: bad argument (channels <= 16, beta > 0)");
     if (n_rays == 0) return IA_OK;
@@ -1138,7 +1138,8 @@ extern "C" int ia_op_volrend_backward(ia_ctx* c, const int32_t* d_packed_info, c
                IA_EINVAL, "ia_op_volrend_backward: NULL argument");
     IA_CHECK_CUDA(cudaSetDevice(c->device));
     k_volrend_backward<<<(unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        d_packed_info, d_sdf, d_dists, d_values, n_channels, beta, d_dcomp, d_dopacity, n_rays, d_g_sdf, d_g_values, d_g_beta);
+        d_packed_info, d_sdf, d_dists, d_values, n_channels, beta, d_dcomp, d_dopacity, d_dweights, n_rays, d_g_sdf, d_g_values,
+        d_g_beta);
     IA_LAUNCH_CHECK();
     return IA_OK;
 }

@@ -612,7 +612,8 @@ __global__ void __launch_bounds__(128) k_volrend(const int* __restrict__ packed_
 __global__ void __launch_bounds__(128) k_volrend_backward(const int* __restrict__ packed_info, const float* __restrict__ sdf,
                                                           const float* __restrict__ dists, const float* __restrict__ values,
                                                           int C, float beta, const float* __restrict__ d_comp,
-                                                          const float* __restrict__ d_opacity, long long n_rays,
+                                                          const float* __restrict__ d_opacity,
+                                                          const float* __restrict__ d_weights, long long n_rays,
                                                           float* __restrict__ g_sdf, float* __restrict__ g_values,
                                                           float* __restrict__ g_beta) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -637,7 +638,7 @@ __global__ void __launch_bounds__(128) k_volrend_backward(const int* __restrict_
             const float a = 1.0f - expf(-sigma * dist);
             const float Ti = g_sdf[i];
             const float w = Ti * a;
-            float dw = dop;
+            float dw = dop + (d_weights ? d_weights[i] : 0.f);
 #pragma unroll
             for (int c = 0; c < IA_VOLREND_MAX_C; c++)
                 if (c < C) {

@@ -43,7 +43,7 @@ _ARGTYPES = {
     "ia_op_pbr_shade_backward": [_vp] * 12 + [_i64] + [_vp] * 6,
     "ia_op_env_backward": [_vp, _vp, _vp, _i64, _vp, _vp],
     "ia_op_volrend": [_vp, _vp, _vp, _vp, _vp, _i32, _cf32, _i64, _vp, _vp, _vp, _vp],
-    "ia_op_volrend_backward": [_vp, _vp, _vp, _vp, _vp, _i32, _cf32, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
+    "ia_op_volrend_backward": [_vp, _vp, _vp, _vp, _vp, _i32, _cf32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
     "ia_op_shade_fields_backward": [_vp] * 7 + [_i64] + [_vp] * 6,
     "ia_op_query_backward": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "ia_op_traverse": [_vp, _vp, _vp, _i64, _cf32, _cf32, _cf32] + [_vp] * 9 + [_vp],
@@ -451,15 +451,17 @@ class RenderEngine:
                                      ptr(comp), ptr(op), _stream()), "ia_op_volrend")
         return w, comp, op
 
-    def op_volrend_backward(self, packed_info, sdf, dists, values, beta, d_comp, d_opacity=None):
-        """Backward of ``op_volrend``: (g_sdf [m], g_values [m,C], g_beta [1])."""
+    def op_volrend_backward(self, packed_info, sdf, dists, values, beta, d_comp, d_opacity=None, d_weights=None):
+        """Backward of ``op_volrend``: (g_sdf [m], g_values [m,C], g_beta [1]) for upstream gradients on comp, opacity and
+        (optionally) the weights themselves."""
         pi = packed_info.to(self.dev, torch.int32).contiguous()
         sdf, dists, values, d_comp = [t.to(self.dev, torch.float32).contiguous() for t in (sdf, dists, values, d_comp)]
         d_op = d_opacity.to(self.dev, torch.float32).contiguous() if d_opacity is not None else None
+        d_w = d_weights.to(self.dev, torch.float32).reshape(sdf.shape).contiguous() if d_weights is not None else None
         n_rays, C = pi.shape[0], values.shape[1]
         g_sdf, g_val, g_beta = torch.zeros_like(sdf), torch.zeros_like(values), torch.zeros(1, device=self.dev)
         check(self.lib.ia_op_volrend_backward(self.h, ptr(pi), ptr(sdf), ptr(dists), ptr(values), C, float(beta), ptr(d_comp),
-                                              ptr(d_op), n_rays, ptr(g_sdf), ptr(g_val), ptr(g_beta), _stream()),
+                                              ptr(d_op), ptr(d_w), n_rays, ptr(g_sdf), ptr(g_val), ptr(g_beta), _stream()),
               "ia_op_volrend_backward")
         return g_sdf, g_val, g_beta
 

@@ -125,21 +125,20 @@ class _VolRend(torch.autograd.Function):
         w, comp, op = engine.op_volrend(packed_info, sdf.detach(), dists, values.detach(), b)
         ctx.engine, ctx.a = engine, (packed_info, sdf.detach(), dists, values.detach(), b)
         ctx.beta_like = beta if torch.is_tensor(beta) else None
-        ctx.mark_non_differentiable(w)
         return w, comp, op
 
     @staticmethod
-    def backward(ctx, _g_w, g_comp, g_op):
+    def backward(ctx, g_w, g_comp, g_op):
         pi, sdf, dists, values, b = ctx.a
         if g_comp is None:
             g_comp = torch.zeros(pi.shape[0], values.shape[1], device=ctx.engine.dev)
-        g_sdf, g_val, g_beta = ctx.engine.op_volrend_backward(pi, sdf, dists, values, b, g_comp, g_op)
+        g_sdf, g_val, g_beta = ctx.engine.op_volrend_backward(pi, sdf, dists, values, b, g_comp, g_op, g_w)
         bl = ctx.beta_like
         return None, None, g_sdf, None, g_val, (g_beta.reshape(bl.shape).to(bl.dtype).to(bl.device) if bl is not None else None)
 
 
 def volrend(engine, packed_info, sdf, dists, values, beta):
-    """Differentiable (weights [m] -- no graph --, comp [n_rays,C], opacity [n_rays]) along packed rays (``packed_info``
+    """Differentiable (weights [m], comp [n_rays,C], opacity [n_rays]) along packed rays (``packed_info``
     [n_rays,2] = first sample, count).  Gradients reach ``sdf``, ``values`` and ``beta`` (a tensor, e.g. the Laplace density's
     parameter, or a float)."""
     return _VolRend.apply(engine, packed_info, sdf, dists, values, beta)
@@ -149,7 +148,8 @@ def render_radiance(engine, params: dict, tfs, w2s, rays_o, rays_d, packed_info,
     """The radiance-field branch of the training forward (models/intrinsic_avatar.py:1068-1182: ``rgb_normal_mats_alpha_fn`` at
     the interval midpoints, then ``rendering_with_normals_mats_sdf``) for samples already placed on the rays: dict with
     ``comp_rgb`` [n_rays,3], ``comp_mats`` [n_rays,5], ``comp_normal`` [n_rays,3] (unnormalised accumulation), ``depth``,
-    ``opacity``, ``weights`` and the per-sample ``sdf`` / ``valid``.  ``params``: folded weights by name (geometry + shading);
+    ``opacity``, ``weights`` and the per-sample ``sdf`` / ``valid`` / ``materials`` [m,5] / ``normal_smpl`` [m,3] (unit SDF
+    gradient in SMPL space, no graph) / ``ray_indices`` -- what ``rendering_with_normals_mats_sdf`` hands on in ``extras``.  ``params``: folded weights by name (geometry + shading);
     ``tfs`` the bone transforms and ``w2s`` [4,4] the world-to-SMPL transform of ``set_pose`` (rays are SMPL-space; view direction
     and normal go to the networks in world space, ``transform_dirs_s2w``); ``beta`` the Laplace density's scale.  A loss on the result back-propagates to all of them."""
     dev = engine.dev
@@ -168,7 +168,8 @@ def render_radiance(engine, params: dict, tfs, w2s, rays_o, rays_d, packed_info,
     values = torch.cat([rgb, mat, normal_w, t_mid[:, None]], dim=-1)
     weights, comp, opacity = volrend(engine, pi, sdf, t1 - t0, values, beta)
     return {"comp_rgb": comp[:, 0:3], "comp_mats": comp[:, 3:8], "comp_normal": comp[:, 8:11], "depth": comp[:, 11],
-            "opacity": opacity, "weights": weights, "sdf": sdf, "valid": valid}
+            "opacity": opacity, "weights": weights, "sdf": sdf, "valid": valid, "materials": mat,
+            "normal_smpl": torch.nn.functional.normalize(normal, dim=-1, eps=1e-6), "ray_indices": ridx}
 
 
 class _PbrShade(torch.autograd.Function):
@@ -236,3 +237,47 @@ def pbr_light(engine, env, w2s, normal, albedo, rough, metal, positions, view_di
     Lo, Lo_diff, Lo_spec = pbr_shade(engine, -view_dirs.to(dev, torch.float32), n_, wo, rough, albedo, metal, Li,
                                      inv_pdf.to(dev, torch.float32))
     return Lo, Lo_diff, Lo_spec, 2.0 * tr[:, None].expand(-1, 3)
+
+
+def render_phys(engine, params: dict, tfs, w2s, env, rays_o, rays_d, packed_info, t_starts, t_ends, beta, light_dirs, inv_pdf,
+                light_index, spp=512, background=1.0, gi=False):
+    """Both branches of the training forward for samples already placed on the rays (models/intrinsic_avatar.py:1241-1470 with
+    ``render_mode = uniform_light``, the training default): ``render_radiance``, then -- without a graph -- ``spp`` shading
+    samples per ray drawn from the compositing weights (``sample_volume_interaction``, models/pbr/utils.py:70-229:
+    ``ia_op_ray_resampling``, zero-crossing snap included), each with its source interval's normal and materials and the
+    weight ``w_source / count`` (foreground) or ``(1 - opacity) / count`` (background), both of which keep their graph;
+    one light direction per foreground sample -- ``light_dirs`` / ``inv_pdf`` [L,3] / [L] indexed by ``light_index``
+    [n_rays, spp] (the reference's per-ray shuffle of the stratified sphere, :1391-1411) -- through ``pbr_light``;
+    background samples carry ``background``; ``comp_rgb_phys = sum w Lo`` per ray, rays without samples = background.
+    Returns ``render_radiance``'s dict plus ``comp_rgb_phys`` [n_rays,3], ``visibility`` [n_rays,1] and ``n_shading_samples``."""
+    dev = engine.dev
+    out = render_radiance(engine, params, tfs, w2s, rays_o, rays_d, packed_info, t_starts, t_ends, beta)
+    pi = packed_info.to(dev, torch.int32)
+    n_rays = pi.shape[0]
+    weights, mats, opacity = out["weights"], out["materials"], out["opacity"]
+    bgc = torch.as_tensor(background, dtype=torch.float32, device=dev).expand(3)
+    t0, t1 = t_starts.to(dev, torch.float32).reshape(-1), t_ends.to(dev, torch.float32).reshape(-1)
+    with torch.no_grad():
+        rpi, t_res, offs, src, fg_cnt, bg_cnt, _ = engine.op_ray_resampling(pi, t0, t1, weights.detach(), out["sdf"].detach(), spp)
+        rcount = rpi[:, 1].long()
+        r_ridx = torch.repeat_interleave(torch.arange(n_rays, device=dev), rcount)
+        rank = torch.arange(r_ridx.shape[0], device=dev) - rpi[:, 0].long()[r_ridx]          # position within its ray
+        is_fg = offs.reshape(-1) < 1e4
+        fg, bg = torch.nonzero(is_fg).reshape(-1), torch.nonzero(~is_fg).reshape(-1)
+        fg_src, fg_ray, bg_ray = src[fg], r_ridx[fg], r_ridx[bg]
+        o, d = rays_o.to(dev, torch.float32), rays_d.to(dev, torch.float32)
+        positions = o[fg_ray] + d[fg_ray] * t_res.reshape(-1)[fg][:, None]
+        li = light_index.to(dev).long()[fg_ray, rank[fg]]
+        wo, ip = light_dirs.to(dev, torch.float32)[li], inv_pdf.to(dev, torch.float32)[li]
+    w_fg = weights[fg_src] / fg_cnt[fg_src].float()
+    w_bg = (1.0 - opacity)[bg_ray] / bg_cnt[bg_ray].float()
+    m = mats[fg_src]
+    Lo, _, _, vis = pbr_light(engine, env, w2s, out["normal_smpl"][fg_src], m[:, 0:3], m[:, 3], m[:, 4], positions, d[fg_ray], wo,
+                              ip, gi=gi)
+    phys = torch.zeros(n_rays, 3, device=dev).index_add(0, fg_ray, w_fg[:, None] * Lo)
+    phys = phys.index_add(0, bg_ray, w_bg[:, None] * bgc[None, :])
+    empty = rcount == 0
+    phys = torch.where(empty[:, None], bgc[None, :].expand(n_rays, 3), phys)
+    visibility = torch.zeros(n_rays, 3, device=dev).index_add(0, fg_ray, w_fg.detach()[:, None] * vis).mean(-1, keepdim=True)
+    out.update(comp_rgb_phys=phys, visibility=visibility, n_shading_samples=int(fg.shape[0]))
+    return out

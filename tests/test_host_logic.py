@@ -449,7 +449,7 @@ def test_training_seam_routes_gradients_without_a_device():
             calls["beta"] = beta
             return torch.rand_like(sdf), torch.rand(pi.shape[0], vals.shape[1]), torch.rand(pi.shape[0])
 
-        def op_volrend_backward(self, pi, sdf, dists, vals, beta, d_comp, d_op):
+        def op_volrend_backward(self, pi, sdf, dists, vals, beta, d_comp, d_op, d_w=None):
             assert d_comp.shape == (pi.shape[0], vals.shape[1])
             return torch.ones_like(sdf), torch.ones_like(vals), torch.full((1,), 3.0)
 
@@ -484,7 +484,7 @@ def test_training_seam_routes_gradients_without_a_device():
     e = StandIn()
     out = render_radiance(e, P, tfs, torch.eye(4), torch.randn(4, 3), torch.randn(4, 3), pi, torch.rand(9), torch.rand(9) + 1, beta)
     assert out["comp_rgb"].shape == (4, 3) and out["comp_mats"].shape == (4, 5) and out["depth"].shape == (4,)
-    assert not out["weights"].requires_grad and not out["valid"].requires_grad
+    assert out["weights"].requires_grad and not out["valid"].requires_grad and not out["normal_smpl"].requires_grad
     (out["comp_rgb"].sum() + out["depth"].sum() + out["opacity"].sum()).backward()
     for k, v in shapes.items():
         assert P[k].grad is not None and P[k].grad.shape == v, k
