@@ -497,6 +497,9 @@ class RenderEngine:
         d = dirs_world.to(self.dev, torch.float32).reshape(-1, 3).contiguous()
         g = d_em.to(self.dev, torch.float32).reshape(-1, 3).contiguous()
         assert d.shape == g.shape
+        if "env" not in self._keep or tuple(self._keep["env"].shape[:2]) != (int(env_shape[0]), int(env_shape[1])):
+            raise ValueError("op_env_backward: env_shape does not match the map of the last set_light* call "
+                             "(the kernel scatters into that map's texel grid)")
         g_env = torch.zeros(int(env_shape[0]), int(env_shape[1]), 3, device=self.dev)
         check(self.lib.ia_op_env_backward(self.h, ptr(d), ptr(g), d.shape[0], ptr(g_env), _stream()), "ia_op_env_backward")
         return g_env
