@@ -510,3 +510,28 @@ def test_training_seam_routes_gradients_without_a_device():
     assert L["rough"].grad.shape == (m, 1) and L["metal"].grad.shape == (m,) and L["env"].grad.shape == (4, 8, 3)
     assert torch.equal(calls["env_d_em"], 2.0 * torch.where(cm, 0.5, 0.0)[:, None].expand(-1, 3))  # dLi x transmittance
     assert L["n_raw"].grad is not None and float(L["albedo"].grad.min()) == 1.0
+
+
+def test_folded_leaves_keep_the_reference_parameters_in_the_graph():
+    """train.folded_leaves: the effective weights equal weights.fold's and stay attached to the reference-keyed parameters --
+    a gradient of ones on the effective first geometry layer arrives at weight_g as sum_i v_oi / |v_o| (weight normalisation,
+    models/network_utils.py:201-244), beta = |b| + 1e-4 passes d|b|, and the hash tables pass through unchanged."""
+    from intrinsicavatar_b200.train import folded_leaves
+    from intrinsicavatar_b200.weights import fold, random_state_dict
+    sd = random_state_dict(3)
+    theta = {("model." + k): v.clone().float().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()}
+    f, f0 = folded_leaves(theta, "cpu"), fold(sd)
+    for k, v in f0.items():
+        if k == "beta":
+            assert float(f[k].detach()) == pytest.approx(v)
+        else:
+            assert torch.equal(f[k].detach(), v), k
+    (f["geo_w1"].sum() + 3.0 * f["beta"] + 2.0 * f["geo_hash"].sum() + f["mat_w2"].sum()).backward()
+    v = theta["model.geometry.network.layers.0.weight_v"].detach()
+    g = theta["model.geometry.network.layers.0.weight_g"]
+    assert torch.allclose(g.grad, (v / v.norm(dim=1, keepdim=True)).sum(1, keepdim=True), atol=1e-5)
+    assert torch.equal(theta["model.geometry.encoding.encoding.encoding.params"].grad,
+                       torch.full_like(theta["model.geometry.encoding.encoding.encoding.params"], 2.0))
+    b = theta["model.density.beta"]
+    assert float(b.grad) == pytest.approx(3.0 * float(torch.sign(b.detach())))
+    assert theta["model.material.network.layers.1.weight"].grad is not None
