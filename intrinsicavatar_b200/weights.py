@@ -139,6 +139,8 @@ def fold(sd: dict, material_feature: str = "hybrid", keep_graph: bool = False) -
     13- / 35-wide first layer, which is the hybrid layer with zero columns for the input it does not see.
     ``keep_graph``: plain tensor code throughout, so with parameters that require grad the result stays attached to them
     (``beta`` is then a tensor): the training seam differentiates weight norm, Lipschitz bound and beta through this function."""
+    if not keep_graph:
+        sd = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in sd.items()}
     out = {}
     out["geo_hash"] = sd["geometry.encoding.encoding.encoding.params"].float().contiguous()
     out["rad_hash"] = sd["radiance.xyz_encoding.encoding.encoding.params"].float().contiguous()
